@@ -1,0 +1,73 @@
+// Context management and error plumbing of libdpig.so (C ABI in include/dpig.h).
+#include <cstdarg>
+#include <cstdio>
+#include "common.cuh"
+
+namespace dpig {
+
+int set_error(dpig_ctx* ctx, int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  if (ctx) ctx->last_error = buf;
+  return code;
+}
+
+int check_launch(dpig_ctx* ctx, const char* what) {
+  cudaError_t e = cudaPeekAtLastError();
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return set_error(ctx, DPIG_ECUDA, "%s: %s", what, cudaGetErrorString(e));
+  }
+  return DPIG_OK;
+}
+
+}  // namespace dpig
+
+using namespace dpig;
+
+extern "C" int dpig_ctx_create(int device, dpig_ctx** out) {
+  if (!out) return DPIG_EINVAL;
+  *out = nullptr;
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || device < 0 || device >= count) {
+    cudaGetLastError();
+    return DPIG_ENODEVICE;
+  }
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return DPIG_ECUDA;
+  if (prop.major != 10) return DPIG_ENODEVICE;  // kernels are sm_100a only; there is no fallback
+  if (cudaSetDevice(device) != cudaSuccess) return DPIG_ECUDA;
+  dpig_ctx* ctx = new dpig_ctx();
+  ctx->device = device;
+  ctx->num_sms = prop.multiProcessorCount;
+  ctx->max_smem_optin = static_cast<int>(prop.sharedMemPerBlockOptin);
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess ||
+      !fn) {
+    delete ctx;
+    return DPIG_ECUDA;
+  }
+  ctx->encode_tiled = reinterpret_cast<decltype(ctx->encode_tiled)>(fn);
+  *out = ctx;
+  return DPIG_OK;
+}
+
+extern "C" void dpig_ctx_destroy(dpig_ctx* ctx) { delete ctx; }
+
+extern "C" const char* dpig_last_error(const dpig_ctx* ctx) {
+  return ctx ? ctx->last_error.c_str() : "null context";
+}
+
+extern "C" int dpig_ctx_set_fast_mode(dpig_ctx* ctx, int fast) {
+  DPIG_CHECK_CTX(ctx);
+  ctx->fast_mode = fast != 0;
+  return DPIG_OK;
+}
+
+extern "C" unsigned long long dpig_launch_count(const dpig_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+extern "C" const char* dpig_version(void) { return "dpig-b200 0.1 (sm_100a)"; }

@@ -1,0 +1,55 @@
+// Shared declarations for the DPIG hot-path kernels (internal; the public surface is include/dpig.h).
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <string>
+#include "../../include/dpig.h"
+
+struct dpig_ctx {
+  int device = 0;
+  int num_sms = 148;
+  int max_smem_optin = 0;
+  std::string last_error;
+  // driver entry point, resolved at ctx creation (no link-time libcuda dependency)
+  CUresult (*encode_tiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                           const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                           CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                           CUtensorMapFloatOOBfill) = nullptr;
+  bool fast_mode = false;  // hi-plane only (single bf16 MMA pass); NOT the parity mode
+  unsigned long long launches = 0;
+};
+
+namespace dpig {
+
+int set_error(dpig_ctx* ctx, int code, const char* fmt, ...);
+int check_launch(dpig_ctx* ctx, const char* what);
+
+// Split-bf16 storage: x ~= float(hi) + float(lo), |x - hi - lo| <= 2^-18 |x|.
+__device__ __forceinline__ void split_bf16(float v, __nv_bfloat16& hi, __nv_bfloat16& lo) {
+  hi = __float2bfloat16_rn(v);
+  lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+}
+__device__ __forceinline__ float join_bf16(__nv_bfloat16 hi, __nv_bfloat16 lo) {
+  return __bfloat162float(hi) + __bfloat162float(lo);
+}
+__device__ __forceinline__ float bf16_bits_to_float(uint16_t b) {
+  return __uint_as_float(static_cast<uint32_t>(b) << 16);
+}
+
+// TF 'SAME' padding (tensorflow/core/framework/common_shape_fns.cc semantics):
+// out = ceil(in / s), pad_total = max((out-1)*s + k - in, 0), pad_before = pad_total / 2.
+inline int same_out(int in, int s) { return (in + s - 1) / s; }
+inline int same_pad_before(int in, int k, int s) {
+  int out = same_out(in, s);
+  int total = (out - 1) * s + k - in;
+  if (total < 0) total = 0;
+  return total / 2;
+}
+inline int floordiv(int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b); }
+
+}  // namespace dpig
+
+#define DPIG_CHECK_CTX(ctx) \
+  if (!(ctx)) return DPIG_EINVAL;

@@ -1,0 +1,895 @@
+// Tensor-core convolutions for sm_100a: TMA-staged implicit GEMM on tcgen05 with TMEM accumulators.
+//
+// Replaces the TensorFlow kernels behind slim.conv2d (reference models.py:396-399, 425-429,
+// 458-462, 528-539, 564-573) and tflib/ops/conv2d.py:106-120, forward and both gradients.
+//
+// Numerics: operands are split-bf16 planes (x = hi + lo).  Each 64-deep K step issues
+// hi*hi + hi*lo + lo*hi into one fp32 TMEM accumulator, i.e. a ~2^-17-accurate product, so the
+// result matches an fp32 convolution to ~1e-5 relative (see DESIGN.md "precision").
+//
+// conv kernel (forward and data-gradient):
+//   GEMM M = a box of <=128 output pixels (BW x BH x BN), N = block_n output channels,
+//   K = (filter taps) x (input channels in chunks of 64).
+//   A tile  : one 4-D TMA box of the NHWC activation per (tap, chunk); the tap shift is applied to
+//             the box coordinates and TMA's out-of-bounds zero fill *is* the SAME padding.
+//             Stride-2 convs read one of four parity views of the input (src index), so every
+//             load is a plain dense box.
+//   B tile  : 3-D TMA box of the packed weights [tap][n][k] (K-major).
+//   both land in 128B-swizzled shared memory and are consumed by tcgen05.mma via descriptors.
+//   Warp roles: warp0 = TMA producer, warp1 = MMA issuer (+TMEM alloc), warps2..5 = epilogue
+//   (tcgen05.ld -> bias/act/residual/mask -> split-bf16 stores).
+//
+// wgrad kernel (filter gradient):
+//   GEMM M = 128 input channels, N = block_n output channels, K = pixels (64 per step).
+//   Both operands are MN-major views of the same kind of TMA boxes (rows = pixels).
+//   One filter tap per CTA (blockIdx.y), split-K over pixel tiles (blockIdx.z), fp32 atomics.
+#include <algorithm>
+#include <cstring>
+#include <vector>
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace dpig {
+
+struct ConvTap {
+  int16_t src, dh, dw, wtap;
+};
+constexpr int kMaxTaps = 25;
+constexpr uint32_t kABytes = 16384;  // 128 rows x 128 B, per plane per stage
+
+struct ConvUmmaParams {
+  CUtensorMap a_map[4][2];
+  CUtensorMap b_map[2];
+  ConvTap taps[kMaxTaps];
+  int num_taps, planes, kchunks;
+  int BW, BH, BN;
+  int tiles_w, tiles_h, tiles_n;
+  int Wo, Ho, No;
+  int block_n, cout, stages;
+  uint32_t a_tx_bytes, b_bytes, tmem_cols;
+  const float* bias;
+  int act;
+  float alpha;
+  int sh, sw, oh, ow, rep, out_H, out_W;
+  __nv_bfloat16 *out_hi, *out_lo;
+  long long out_ps;
+  __nv_bfloat16 *out2_hi, *out2_lo;
+  long long out2_ps;
+  float* out_f32;
+  long long out_f32_ps;
+  const __nv_bfloat16 *add_hi, *add_lo;
+  long long add_ps;
+  uint32_t* mask_out;
+  int mask_out_words;
+  const uint32_t* mask_in;
+  int mask_in_words;
+  float mask_neg;
+};
+
+__device__ __forceinline__ uint8_t* align1024(uint8_t* p) {
+  return reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(p) + 1023) & ~uintptr_t(1023));
+}
+
+__device__ __forceinline__ uint32_t pack2(__nv_bfloat16 a, __nv_bfloat16 b) {
+  return static_cast<uint32_t>(__bfloat16_as_ushort(a)) |
+         (static_cast<uint32_t>(__bfloat16_as_ushort(b)) << 16);
+}
+
+// Store 32 consecutive channels of one pixel as split bf16 (hi / lo planes).
+__device__ __forceinline__ void store_split32(__nv_bfloat16* hi, __nv_bfloat16* lo, long long off,
+                                              const float (&f)[32], int nvalid, bool vec) {
+  if (vec) {
+    uint32_t h[16], l[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      __nv_bfloat16 h0, l0, h1, l1;
+      split_bf16(f[2 * i], h0, l0);
+      split_bf16(f[2 * i + 1], h1, l1);
+      h[i] = pack2(h0, h1);
+      l[i] = pack2(l0, l1);
+    }
+    uint4* ph = reinterpret_cast<uint4*>(hi + off);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) ph[i] = make_uint4(h[4 * i], h[4 * i + 1], h[4 * i + 2], h[4 * i + 3]);
+    if (lo) {
+      uint4* pl = reinterpret_cast<uint4*>(lo + off);
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        pl[i] = make_uint4(l[4 * i], l[4 * i + 1], l[4 * i + 2], l[4 * i + 3]);
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      if (i < nvalid) {
+        __nv_bfloat16 h0, l0;
+        split_bf16(f[i], h0, l0);
+        hi[off + i] = h0;
+        if (lo) lo[off + i] = l0;
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(192, 1)
+conv_umma_kernel(const __grid_constant__ ConvUmmaParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = align1024(smem_raw);
+  const uint32_t b_off = p.planes * kABytes;
+  const uint32_t stage_bytes = p.planes * (kABytes + p.b_bytes);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + p.stages * stage_bytes);
+  uint64_t* empty = full + p.stages;
+  uint64_t* tmem_full = empty + p.stages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  // tile coordinates
+  const int tw = blockIdx.x % p.tiles_w;
+  const int th = (blockIdx.x / p.tiles_w) % p.tiles_h;
+  const int tn = blockIdx.x / (p.tiles_w * p.tiles_h);
+  const int w0 = tw * p.BW, h0 = th * p.BH, n0 = tn * p.BN;
+  const int nt = blockIdx.y;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.stages; ++s) {
+      ptx::mbar_init(&full[s], 1);
+      ptx::mbar_init(&empty[s], 1);
+    }
+    ptx::mbar_init(tmem_full, 1);
+    ptx::fence_barrier_init();
+  }
+  if (warp == 1) {
+    // power-of-two column count >= block_n
+    switch (p.tmem_cols) {
+      case 32: ptx::tmem_alloc<32>(tmem_slot); break;
+      case 64: ptx::tmem_alloc<64>(tmem_slot); break;
+      case 128: ptx::tmem_alloc<128>(tmem_slot); break;
+      default: ptx::tmem_alloc<256>(tmem_slot); break;
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int total_steps = p.num_taps * p.kchunks;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int s = 0; s < 4; ++s)
+        for (int pl = 0; pl < p.planes; ++pl) ptx::prefetch_tmap(&p.a_map[s][pl]);
+      for (int pl = 0; pl < p.planes; ++pl) ptx::prefetch_tmap(&p.b_map[pl]);
+      int s = 0;
+      uint32_t ph = 0;
+      for (int t = 0; t < p.num_taps; ++t) {
+        const ConvTap tap = p.taps[t];
+        for (int kc = 0; kc < p.kchunks; ++kc) {
+          ptx::mbar_wait(&empty[s], ph ^ 1);
+          uint8_t* st = smem + s * stage_bytes;
+          ptx::mbar_expect_tx(&full[s], p.planes * (p.a_tx_bytes + p.b_bytes));
+          for (int pl = 0; pl < p.planes; ++pl)
+            ptx::tma_load_4d(st + pl * kABytes, &p.a_map[tap.src][pl], &full[s], kc * 64,
+                             w0 + tap.dw, h0 + tap.dh, n0);
+          for (int pl = 0; pl < p.planes; ++pl)
+            ptx::tma_load_3d(st + b_off + pl * p.b_bytes, &p.b_map[pl], &full[s], kc * 64,
+                             nt * p.block_n, tap.wtap);
+          if (++s == p.stages) {
+            s = 0;
+            ph ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = ptx::make_idesc_bf16(128, p.block_n, 0, 0);
+      int s = 0;
+      uint32_t ph = 0;
+      for (int step = 0; step < total_steps; ++step) {
+        ptx::mbar_wait(&full[s], ph);
+        ptx::tc_fence_after();
+        const uint32_t a_hi = ptx::smem_u32(smem + s * stage_bytes);
+        const uint32_t a_lo = a_hi + kABytes;
+        const uint32_t b_hi = a_hi + b_off;
+        const uint32_t b_lo = b_hi + p.b_bytes;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const uint64_t da_hi = ptx::make_desc_sw128(a_hi + k * 32, 16, 1024);
+          const uint64_t db_hi = ptx::make_desc_sw128(b_hi + k * 32, 16, 1024);
+          ptx::umma_bf16(tmem_base, da_hi, db_hi, idesc, (step | k) ? 1u : 0u);
+          if (p.planes == 2) {
+            const uint64_t da_lo = ptx::make_desc_sw128(a_lo + k * 32, 16, 1024);
+            const uint64_t db_lo = ptx::make_desc_sw128(b_lo + k * 32, 16, 1024);
+            ptx::umma_bf16(tmem_base, da_hi, db_lo, idesc, 1u);
+            ptx::umma_bf16(tmem_base, da_lo, db_hi, idesc, 1u);
+          }
+        }
+        ptx::umma_commit(&empty[s]);
+        if (++s == p.stages) {
+          s = 0;
+          ph ^= 1;
+        }
+      }
+      ptx::umma_commit(tmem_full);
+    }
+  } else {
+    // ---------------- epilogue: 4 warps, thread = one accumulator row (= one output pixel)
+    const int lg = warp & 3;
+    const int r = lg * 32 + lane;
+    const int wl = r % p.BW;
+    const int tq = r / p.BW;
+    const int hl = tq % p.BH;
+    const int nl = tq / p.BH;
+    const int w = w0 + wl, h = h0 + hl, n = n0 + nl;
+    const bool valid = (nl < p.BN) && (w < p.Wo) && (h < p.Ho) && (n < p.No);
+    const long long lpix = (static_cast<long long>(n) * p.Ho + h) * p.Wo + w;  // logical pixel
+    const int py = h * p.sh + p.oh, px = w * p.sw + p.ow;
+    const long long ppix = (static_cast<long long>(n) * p.out_H + py) * p.out_W + px;
+
+    ptx::mbar_wait(tmem_full, 0);
+    ptx::tc_fence_after();
+
+    for (int c0 = 0; c0 < p.block_n; c0 += 32) {
+      uint32_t v[32];
+      ptx::tmem_ld32(tmem_base + (static_cast<uint32_t>(lg * 32) << 16) + c0, v);
+      ptx::tmem_ld_wait();
+      const int cbase = nt * p.block_n + c0;
+      const int nvalid = min(32, p.cout - cbase);
+      if (!valid || nvalid <= 0) continue;
+      float f[32];
+      uint32_t mbits = 0;
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        float x = __uint_as_float(v[i]);
+        if (p.bias && i < nvalid) x += __ldg(p.bias + cbase + i);
+        mbits |= (x > 0.f ? 1u : 0u) << i;
+        if (p.act == DPIG_ACT_RELU) x = fmaxf(x, 0.f);
+        else if (p.act == DPIG_ACT_LRELU) x = x > 0.f ? x : p.alpha * x;
+        f[i] = x;
+      }
+      const bool full32 = (nvalid == 32);
+      if (p.add_hi) {
+        const long long off = ppix * p.add_ps + cbase;
+        if (full32 && (p.add_ps % 8 == 0)) {
+          const uint4* ah = reinterpret_cast<const uint4*>(p.add_hi + off);
+          const uint4* al = p.add_lo ? reinterpret_cast<const uint4*>(p.add_lo + off) : nullptr;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const uint4 a = __ldg(ah + q);
+            const uint32_t aw[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              f[q * 8 + 2 * j] += bf16_bits_to_float(aw[j] & 0xFFFF);
+              f[q * 8 + 2 * j + 1] += bf16_bits_to_float(aw[j] >> 16);
+            }
+            if (al) {
+              const uint4 b = __ldg(al + q);
+              const uint32_t bw[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                f[q * 8 + 2 * j] += bf16_bits_to_float(bw[j] & 0xFFFF);
+                f[q * 8 + 2 * j + 1] += bf16_bits_to_float(bw[j] >> 16);
+              }
+            }
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (i < nvalid) {
+              float a = __bfloat162float(p.add_hi[off + i]);
+              if (p.add_lo) a += __bfloat162float(p.add_lo[off + i]);
+              f[i] += a;
+            }
+        }
+      }
+      if (p.mask_out) p.mask_out[lpix * p.mask_out_words + (cbase >> 5)] = mbits;
+      if (p.out_hi) {
+        const bool vec = full32 && (p.out_ps % 8 == 0);
+        for (int dy = 0; dy < p.rep; ++dy)
+          for (int dx = 0; dx < p.rep; ++dx) {
+            const long long off = (ppix + static_cast<long long>(dy) * p.out_W + dx) * p.out_ps + cbase;
+            store_split32(p.out_hi, p.out_lo, off, f, nvalid, vec);
+          }
+      }
+      if (p.out_f32) {
+        for (int dy = 0; dy < p.rep; ++dy)
+          for (int dx = 0; dx < p.rep; ++dx) {
+            float* o = p.out_f32 + (ppix + static_cast<long long>(dy) * p.out_W + dx) * p.out_f32_ps + cbase;
+            if (full32 && (p.out_f32_ps % 4 == 0)) {
+#pragma unroll
+              for (int q = 0; q < 8; ++q)
+                reinterpret_cast<float4*>(o)[q] =
+                    make_float4(f[4 * q], f[4 * q + 1], f[4 * q + 2], f[4 * q + 3]);
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; ++i)
+                if (i < nvalid) o[i] = f[i];
+            }
+          }
+      }
+      if (p.out2_hi) {
+        const uint32_t mi = p.mask_in ? p.mask_in[ppix * p.mask_in_words + (cbase >> 5)] : 0xFFFFFFFFu;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) f[i] *= ((mi >> i) & 1u) ? 1.f : p.mask_neg;
+        const bool vec = full32 && (p.out2_ps % 8 == 0);
+        store_split32(p.out2_hi, p.out2_lo, ppix * p.out2_ps + cbase, f, nvalid, vec);
+      }
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    switch (p.tmem_cols) {
+      case 32: ptx::tmem_dealloc<32>(tmem_base); break;
+      case 64: ptx::tmem_dealloc<64>(tmem_base); break;
+      case 128: ptx::tmem_dealloc<128>(tmem_base); break;
+      default: ptx::tmem_dealloc<256>(tmem_base); break;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------- wgrad
+struct WgradParams {
+  CUtensorMap x_map[4][2];
+  CUtensorMap dy_map[2];
+  ConvTap taps[kMaxTaps];
+  int planes;
+  int PW, PH, PN, tiles_w, tiles_h;
+  int total_tiles, tiles_per_cta;
+  int block_n, n_tiles, cin, cout, stages;
+  uint32_t b_bytes, tmem_cols;
+  float* dw;
+};
+
+__global__ void __launch_bounds__(192, 1)
+wgrad_umma_kernel(const __grid_constant__ WgradParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = align1024(smem_raw);
+  const uint32_t b_off = p.planes * kABytes;
+  const uint32_t stage_bytes = p.planes * (kABytes + p.b_bytes);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + p.stages * stage_bytes);
+  uint64_t* empty = full + p.stages;
+  uint64_t* tmem_full = empty + p.stages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int nt = blockIdx.x % p.n_tiles;  // output-channel tile
+  const int mt = blockIdx.x / p.n_tiles;  // input-channel tile (128 wide)
+  const ConvTap tap = p.taps[blockIdx.y];
+  const int tile_begin = blockIdx.z * p.tiles_per_cta;
+  const int tile_end = min(tile_begin + p.tiles_per_cta, p.total_tiles);
+  const int nsteps = tile_end - tile_begin;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.stages; ++s) {
+      ptx::mbar_init(&full[s], 1);
+      ptx::mbar_init(&empty[s], 1);
+    }
+    ptx::mbar_init(tmem_full, 1);
+    ptx::fence_barrier_init();
+  }
+  if (warp == 1) {
+    switch (p.tmem_cols) {
+      case 64: ptx::tmem_alloc<64>(tmem_slot); break;
+      case 128: ptx::tmem_alloc<128>(tmem_slot); break;
+      default: ptx::tmem_alloc<256>(tmem_slot); break;
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int nboxes_b = p.block_n / 64;
+
+  if (nsteps > 0) {
+    if (warp == 0) {
+      if (lane == 0) {
+        int s = 0;
+        uint32_t ph = 0;
+        for (int t = tile_begin; t < tile_end; ++t) {
+          const int tw = t % p.tiles_w;
+          const int th = (t / p.tiles_w) % p.tiles_h;
+          const int tn = t / (p.tiles_w * p.tiles_h);
+          const int w0 = tw * p.PW, h0 = th * p.PH, n0 = tn * p.PN;
+          ptx::mbar_wait(&empty[s], ph ^ 1);
+          uint8_t* st = smem + s * stage_bytes;
+          ptx::mbar_expect_tx(&full[s], p.planes * (kABytes + p.b_bytes));
+          for (int pl = 0; pl < p.planes; ++pl)
+            for (int j = 0; j < 2; ++j)
+              ptx::tma_load_4d(st + pl * kABytes + j * 8192, &p.x_map[tap.src][pl], &full[s],
+                               mt * 128 + j * 64, w0 + tap.dw, h0 + tap.dh, n0);
+          for (int pl = 0; pl < p.planes; ++pl)
+            for (int j = 0; j < nboxes_b; ++j)
+              ptx::tma_load_4d(st + b_off + pl * p.b_bytes + j * 8192, &p.dy_map[pl], &full[s],
+                               nt * p.block_n + j * 64, w0, h0, n0);
+          if (++s == p.stages) {
+            s = 0;
+            ph ^= 1;
+          }
+        }
+      }
+    } else if (warp == 1) {
+      if (lane == 0) {
+        const uint32_t idesc = ptx::make_idesc_bf16(128, p.block_n, 1, 1);
+        int s = 0;
+        uint32_t ph = 0;
+        for (int step = 0; step < nsteps; ++step) {
+          ptx::mbar_wait(&full[s], ph);
+          ptx::tc_fence_after();
+          const uint32_t a_hi = ptx::smem_u32(smem + s * stage_bytes);
+          const uint32_t a_lo = a_hi + kABytes;
+          const uint32_t b_hi = a_hi + b_off;
+          const uint32_t b_lo = b_hi + p.b_bytes;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {  // 16 pixels (K) per MMA = 2 KB of rows
+            const uint64_t da_hi = ptx::make_desc_sw128(a_hi + k * 2048, 8192, 1024);
+            const uint64_t db_hi = ptx::make_desc_sw128(b_hi + k * 2048, 8192, 1024);
+            ptx::umma_bf16(tmem_base, da_hi, db_hi, idesc, (step | k) ? 1u : 0u);
+            if (p.planes == 2) {
+              const uint64_t da_lo = ptx::make_desc_sw128(a_lo + k * 2048, 8192, 1024);
+              const uint64_t db_lo = ptx::make_desc_sw128(b_lo + k * 2048, 8192, 1024);
+              ptx::umma_bf16(tmem_base, da_hi, db_lo, idesc, 1u);
+              ptx::umma_bf16(tmem_base, da_lo, db_hi, idesc, 1u);
+            }
+          }
+          ptx::umma_commit(&empty[s]);
+          if (++s == p.stages) {
+            s = 0;
+            ph ^= 1;
+          }
+        }
+        ptx::umma_commit(tmem_full);
+      }
+    } else {
+      const int lg = warp & 3;
+      const int ci = mt * 128 + lg * 32 + lane;
+      ptx::mbar_wait(tmem_full, 0);
+      ptx::tc_fence_after();
+      for (int c0 = 0; c0 < p.block_n; c0 += 32) {
+        uint32_t v[32];
+        ptx::tmem_ld32(tmem_base + (static_cast<uint32_t>(lg * 32) << 16) + c0, v);
+        ptx::tmem_ld_wait();
+        const int cbase = nt * p.block_n + c0;
+        if (ci < p.cin) {
+          float* o = p.dw + (static_cast<long long>(tap.wtap) * p.cin + ci) * p.cout + cbase;
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (cbase + i < p.cout) atomicAdd(o + i, __uint_as_float(v[i]));
+        }
+      }
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    switch (p.tmem_cols) {
+      case 64: ptx::tmem_dealloc<64>(tmem_base); break;
+      case 128: ptx::tmem_dealloc<128>(tmem_base); break;
+      default: ptx::tmem_dealloc<256>(tmem_base); break;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------- host
+static int encode_map(dpig_ctx* ctx, CUtensorMap* map, const void* base, int rank,
+                      const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box) {
+  cuuint64_t gdim[5];
+  cuuint64_t gstr[4];
+  cuuint32_t bdim[5];
+  cuuint32_t estr[5];
+  for (int i = 0; i < rank; ++i) {
+    gdim[i] = dims[i];
+    bdim[i] = box[i];
+    estr[i] = 1;
+    if (dims[i] == 0) return set_error(ctx, DPIG_EUNSUPPORTED, "tensor map: empty dimension %d", i);
+  }
+  for (int i = 0; i + 1 < rank; ++i) {
+    gstr[i] = strides_bytes[i];
+    if (strides_bytes[i] % 16) return set_error(ctx, DPIG_EINVAL, "tensor map: stride %d not 16B aligned", i);
+  }
+  if (reinterpret_cast<uintptr_t>(base) % 16) return set_error(ctx, DPIG_EINVAL, "tensor map: base not 16B aligned");
+  CUresult r = ctx->encode_tiled(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(base),
+                                 gdim, gstr, bdim, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                 CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return set_error(ctx, DPIG_ECUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+  return DPIG_OK;
+}
+
+// Activation view -> 4-D map over (C, W', H', N) where W'/H' are either the full grid or one
+// parity class of it (step = 2, offset = parity).
+static int act_map(dpig_ctx* ctx, CUtensorMap* map, const void* plane, const dpig_tensor* t,
+                   int step, int py, int px, int box_w, int box_h, int box_n) {
+  const uint64_t ps = static_cast<uint64_t>(t->pix_stride);
+  const int W2 = (t->w - px + step - 1) / step;
+  const int H2 = (t->h - py + step - 1) / step;
+  uint64_t dims[4] = {static_cast<uint64_t>(t->c), static_cast<uint64_t>(W2), static_cast<uint64_t>(H2),
+                      static_cast<uint64_t>(t->n)};
+  uint64_t strides[3] = {ps * 2 * step, ps * 2 * t->w * step, ps * 2 * t->w * t->h};
+  uint32_t box[4] = {64, static_cast<uint32_t>(box_w), static_cast<uint32_t>(box_h),
+                     static_cast<uint32_t>(box_n)};
+  const char* base = static_cast<const char*>(plane) + (static_cast<uint64_t>(py) * t->w + px) * ps * 2;
+  return encode_map(ctx, map, base, 4, dims, strides, box);
+}
+
+struct Box {
+  int bw, bh, bn;
+};
+// Pick the pixel box (<= max_rows rows) with the best tile utilisation.
+static Box choose_box(int W, int H, int N, int max_rows, bool pow2_exact) {
+  Box best{1, 1, 1};
+  double best_u = -1;
+  for (int bw = 1; bw <= std::min(W, max_rows); ++bw) {
+    if (pow2_exact && (bw & (bw - 1))) continue;
+    for (int bh = 1; bh <= std::min(H, max_rows / bw); ++bh) {
+      if (pow2_exact && (bh & (bh - 1))) continue;
+      int bn = std::min(N, max_rows / (bw * bh));
+      if (pow2_exact) {
+        bn = max_rows / (bw * bh);  // exact product; TMA zero-fills images beyond N
+        if (bn > 256) continue;
+      }
+      if (bn < 1) continue;
+      const double tiles = double((W + bw - 1) / bw) * ((H + bh - 1) / bh) * ((N + bn - 1) / bn);
+      const double u = double(W) * H * N / (tiles * max_rows) + 1e-6 * bw + 1e-9 * bh;
+      if (u > best_u) {
+        best_u = u;
+        best = {bw, bh, bn};
+      }
+    }
+  }
+  if (pow2_exact && best_u < 0) {
+    // tensors smaller than the box in every dimension: let TMA zero-fill
+    int bw = 1;
+    while (bw < W && bw < max_rows) bw <<= 1;
+    int bh = 1;
+    while (bh < H && bw * bh < max_rows) bh <<= 1;
+    best = {bw, bh, max_rows / (bw * bh)};
+  }
+  return best;
+}
+
+static uint32_t pow2_cols(int n) {
+  uint32_t c = 32;
+  while (static_cast<int>(c) < n) c <<= 1;
+  return c;
+}
+
+static int pick_block_n(int cout) {
+  // Largest multiple of 32 that is <= 256 and splits cout (rounded up to 32) evenly.
+  const int c32 = (cout + 31) / 32 * 32;
+  if (c32 <= 256) return c32;
+  int best = 32;
+  for (int bn = 32; bn <= 256; bn += 32)
+    if (c32 % bn == 0) best = bn;
+  return best;
+}
+
+struct EpilogueGeom {
+  int sh, sw, oh, ow, rep, out_H, out_W;
+};
+
+static int fill_epilogue(dpig_ctx* ctx, ConvUmmaParams& P, const dpig_conv_epilogue* ep,
+                         const EpilogueGeom& g, int n, int cout) {
+  P.bias = ep->bias;
+  P.act = ep->act;
+  P.alpha = ep->alpha;
+  P.sh = g.sh;
+  P.sw = g.sw;
+  P.oh = g.oh;
+  P.ow = g.ow;
+  P.rep = g.rep;
+  P.out_H = g.out_H;
+  P.out_W = g.out_W;
+  auto chk = [&](const dpig_tensor* t, const char* name) -> int {
+    if (t->n != n || t->h != g.out_H || t->w != g.out_W || t->c < cout)
+      return set_error(ctx, DPIG_EINVAL, "%s shape [%d,%d,%d,%d] does not match conv output [%d,%d,%d,%d]",
+                       name, t->n, t->h, t->w, t->c, n, g.out_H, g.out_W, cout);
+    return DPIG_OK;
+  };
+  int rc;
+  if (ep->out) {
+    if ((rc = chk(ep->out, "out"))) return rc;
+    P.out_hi = static_cast<__nv_bfloat16*>(ep->out->hi);
+    P.out_lo = static_cast<__nv_bfloat16*>(ep->out->lo);
+    P.out_ps = ep->out->pix_stride;
+  }
+  if (ep->out_masked) {
+    if ((rc = chk(ep->out_masked, "out_masked"))) return rc;
+    P.out2_hi = static_cast<__nv_bfloat16*>(ep->out_masked->hi);
+    P.out2_lo = static_cast<__nv_bfloat16*>(ep->out_masked->lo);
+    P.out2_ps = ep->out_masked->pix_stride;
+  }
+  if (ep->addend) {
+    if ((rc = chk(ep->addend, "addend"))) return rc;
+    P.add_hi = static_cast<const __nv_bfloat16*>(ep->addend->hi);
+    P.add_lo = static_cast<const __nv_bfloat16*>(ep->addend->lo);
+    P.add_ps = ep->addend->pix_stride;
+  }
+  P.out_f32 = ep->out_f32;
+  P.out_f32_ps = ep->out_f32_pix_stride;
+  P.mask_out = ep->mask_out;
+  P.mask_out_words = (cout + 31) / 32;
+  P.mask_in = ep->mask_in;
+  P.mask_in_words = (cout + 31) / 32;
+  P.mask_neg = ep->mask_neg;
+  if (g.rep != 1 && (ep->addend || ep->out_masked))
+    return set_error(ctx, DPIG_EUNSUPPORTED, "upsampling epilogue cannot take addend/out_masked");
+  return DPIG_OK;
+}
+
+static int launch_conv(dpig_ctx* ctx, ConvUmmaParams& P, cudaStream_t stream) {
+  P.planes = ctx->fast_mode ? 1 : P.planes;
+  const uint32_t stage_bytes = P.planes * (kABytes + P.b_bytes);
+  int stages = (ctx->max_smem_optin - 1024 - 256) / stage_bytes;
+  if (stages > 6) stages = 6;
+  if (stages < 2) return set_error(ctx, DPIG_EUNSUPPORTED, "conv tile does not fit shared memory");
+  P.stages = stages;
+  const size_t smem = static_cast<size_t>(stages) * stage_bytes + 1024 + 256;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(conv_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->max_smem_optin);
+    attr_set = true;
+  }
+  dim3 grid(P.tiles_w * P.tiles_h * P.tiles_n, (P.cout + P.block_n - 1) / P.block_n);
+  conv_umma_kernel<<<grid, 192, smem, stream>>>(P);
+  ctx->launches++;
+  return check_launch(ctx, "conv_umma_kernel");
+}
+
+}  // namespace dpig
+
+using namespace dpig;
+
+extern "C" int dpig_conv2d_fwd(dpig_ctx* ctx, const dpig_tensor* x, const void* wf_hi,
+                               const void* wf_lo, int32_t kh, int32_t kw, int32_t stride,
+                               int32_t cout, const dpig_conv_epilogue* ep, dpig_stream stream) {
+  DPIG_CHECK_CTX(ctx);
+  if (!x || !wf_hi || !ep) return set_error(ctx, DPIG_EINVAL, "conv2d_fwd: null argument");
+  if (kh * kw > kMaxTaps || (stride != 1 && stride != 2))
+    return set_error(ctx, DPIG_EUNSUPPORTED, "conv2d_fwd: k=%dx%d stride=%d unsupported", kh, kw, stride);
+  if (x->c % 8 || x->pix_stride % 8)
+    return set_error(ctx, DPIG_EINVAL, "conv2d_fwd: channels / pixel stride must be multiples of 8");
+  const int OH = same_out(x->h, stride), OW = same_out(x->w, stride);
+  const int pt = same_pad_before(x->h, kh, stride), pl = same_pad_before(x->w, kw, stride);
+  const int up = ep->upsample > 1 ? ep->upsample : 1;
+
+  ConvUmmaParams P;
+  memset(&P, 0, sizeof(P));
+  P.planes = (x->lo && wf_lo) ? 2 : 1;
+  const int planes = ctx->fast_mode ? 1 : P.planes;
+  P.kchunks = (x->c + 63) / 64;
+  P.Wo = OW;
+  P.Ho = OH;
+  P.No = x->n;
+  P.cout = cout;
+  P.block_n = pick_block_n(cout);
+  P.b_bytes = P.block_n * 128;
+  P.tmem_cols = pow2_cols(P.block_n);
+  Box b = choose_box(OW, OH, x->n, 128, false);
+  P.BW = b.bw;
+  P.BH = b.bh;
+  P.BN = b.bn;
+  P.tiles_w = (OW + b.bw - 1) / b.bw;
+  P.tiles_h = (OH + b.bh - 1) / b.bh;
+  P.tiles_n = (x->n + b.bn - 1) / b.bn;
+  P.a_tx_bytes = b.bw * b.bh * b.bn * 128;
+
+  int rc;
+  P.num_taps = 0;
+  bool used[4] = {false, false, false, false};
+  for (int i = 0; i < kh; ++i)
+    for (int j = 0; j < kw; ++j) {
+      const int dy = i - pt, dx = j - pl;
+      ConvTap t;
+      if (stride == 1) {
+        t.src = 0;
+        t.dh = dy;
+        t.dw = dx;
+      } else {
+        const int py = ((dy % 2) + 2) % 2, px = ((dx % 2) + 2) % 2;
+        t.src = py * 2 + px;
+        t.dh = floordiv(dy, 2);
+        t.dw = floordiv(dx, 2);
+      }
+      t.wtap = i * kw + j;
+      used[t.src] = true;
+      P.taps[P.num_taps++] = t;
+    }
+  int first_used = -1;
+  for (int s = 0; s < 4; ++s) {
+    if (!used[s]) continue;
+    if (first_used < 0) first_used = s;
+    for (int pln = 0; pln < planes; ++pln) {
+      const void* plane = pln ? x->lo : x->hi;
+      if ((rc = act_map(ctx, &P.a_map[s][pln], plane, x, stride, stride == 1 ? 0 : s / 2,
+                        stride == 1 ? 0 : s % 2, b.bw, b.bh, b.bn)))
+        return rc;
+    }
+  }
+  for (int s = 0; s < 4; ++s)  // unused slots alias a valid map (they are only prefetched)
+    if (!used[s])
+      for (int pln = 0; pln < planes; ++pln) P.a_map[s][pln] = P.a_map[first_used][pln];
+  {
+    const int cin_pad = x->c;
+    uint64_t dims[3] = {static_cast<uint64_t>(cin_pad), static_cast<uint64_t>(cout),
+                        static_cast<uint64_t>(kh * kw)};
+    uint64_t strides[2] = {static_cast<uint64_t>(cin_pad) * 2, static_cast<uint64_t>(cin_pad) * cout * 2};
+    uint32_t box[3] = {64, static_cast<uint32_t>(P.block_n), 1};
+    for (int pln = 0; pln < planes; ++pln)
+      if ((rc = encode_map(ctx, &P.b_map[pln], pln ? wf_lo : wf_hi, 3, dims, strides, box))) return rc;
+  }
+  EpilogueGeom g{up, up, 0, 0, up, OH * up, OW * up};
+  if ((rc = fill_epilogue(ctx, P, ep, g, x->n, cout))) return rc;
+  return launch_conv(ctx, P, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int dpig_conv2d_bwd_data(dpig_ctx* ctx, const dpig_tensor* dy, const void* wb_hi,
+                                    const void* wb_lo, int32_t kh, int32_t kw, int32_t stride,
+                                    int32_t in_h, int32_t in_w, int32_t cin,
+                                    const dpig_conv_epilogue* ep, dpig_stream stream) {
+  DPIG_CHECK_CTX(ctx);
+  if (!dy || !wb_hi || !ep) return set_error(ctx, DPIG_EINVAL, "conv2d_bwd_data: null argument");
+  if (kh * kw > kMaxTaps || (stride != 1 && stride != 2))
+    return set_error(ctx, DPIG_EUNSUPPORTED, "conv2d_bwd_data: k=%dx%d stride=%d unsupported", kh, kw, stride);
+  if (dy->c % 8 || dy->pix_stride % 8)
+    return set_error(ctx, DPIG_EINVAL, "conv2d_bwd_data: channels / pixel stride must be multiples of 8");
+  if (same_out(in_h, stride) != dy->h || same_out(in_w, stride) != dy->w)
+    return set_error(ctx, DPIG_EINVAL, "conv2d_bwd_data: dy %dx%d is not the SAME output of %dx%d / %d",
+                     dy->h, dy->w, in_h, in_w, stride);
+  if (ep->upsample > 1) return set_error(ctx, DPIG_EUNSUPPORTED, "conv2d_bwd_data: no upsample");
+  const int pt = same_pad_before(in_h, kh, stride), pl = same_pad_before(in_w, kw, stride);
+  int rc;
+  for (int py = 0; py < stride; ++py)
+    for (int px = 0; px < stride; ++px) {
+      const int GH = (in_h - py + stride - 1) / stride, GW = (in_w - px + stride - 1) / stride;
+      if (GH <= 0 || GW <= 0) continue;
+      ConvUmmaParams P;
+      memset(&P, 0, sizeof(P));
+      P.planes = (dy->lo && wb_lo) ? 2 : 1;
+      const int planes = ctx->fast_mode ? 1 : P.planes;
+      P.kchunks = (dy->c + 63) / 64;
+      P.Wo = GW;
+      P.Ho = GH;
+      P.No = dy->n;
+      P.cout = cin;
+      P.block_n = pick_block_n(cin);
+      P.b_bytes = P.block_n * 128;
+      P.tmem_cols = pow2_cols(P.block_n);
+      Box b = choose_box(GW, GH, dy->n, 128, false);
+      P.BW = b.bw;
+      P.BH = b.bh;
+      P.BN = b.bn;
+      P.tiles_w = (GW + b.bw - 1) / b.bw;
+      P.tiles_h = (GH + b.bh - 1) / b.bh;
+      P.tiles_n = (dy->n + b.bn - 1) / b.bn;
+      P.a_tx_bytes = b.bw * b.bh * b.bn * 128;
+      P.num_taps = 0;
+      for (int i = 0; i < kh; ++i)
+        for (int j = 0; j < kw; ++j) {
+          // dx[s*a+py] gets dy[(s*a + py + pt - i)/s] when divisible
+          const int ey = py + pt - i, ex = px + pl - j;
+          if (((ey % stride) + stride) % stride || ((ex % stride) + stride) % stride) continue;
+          ConvTap t;
+          t.src = 0;
+          t.dh = floordiv(ey, stride);
+          t.dw = floordiv(ex, stride);
+          t.wtap = i * kw + j;
+          P.taps[P.num_taps++] = t;
+        }
+      if (P.num_taps == 0)
+        return set_error(ctx, DPIG_EUNSUPPORTED, "conv2d_bwd_data: parity class without taps");
+      for (int pln = 0; pln < planes; ++pln) {
+        if ((rc = act_map(ctx, &P.a_map[0][pln], pln ? dy->lo : dy->hi, dy, 1, 0, 0, b.bw, b.bh, b.bn)))
+          return rc;
+        for (int s = 1; s < 4; ++s) P.a_map[s][pln] = P.a_map[0][pln];
+      }
+      {
+        const int cout_pad = dy->c;
+        uint64_t dims[3] = {static_cast<uint64_t>(cout_pad), static_cast<uint64_t>(cin),
+                            static_cast<uint64_t>(kh * kw)};
+        uint64_t strides[2] = {static_cast<uint64_t>(cout_pad) * 2,
+                               static_cast<uint64_t>(cout_pad) * cin * 2};
+        uint32_t box[3] = {64, static_cast<uint32_t>(P.block_n), 1};
+        for (int pln = 0; pln < planes; ++pln)
+          if ((rc = encode_map(ctx, &P.b_map[pln], pln ? wb_lo : wb_hi, 3, dims, strides, box))) return rc;
+      }
+      EpilogueGeom g{stride, stride, py, px, 1, in_h, in_w};
+      if ((rc = fill_epilogue(ctx, P, ep, g, dy->n, cin))) return rc;
+      if ((rc = launch_conv(ctx, P, static_cast<cudaStream_t>(stream)))) return rc;
+    }
+  return DPIG_OK;
+}
+
+extern "C" int dpig_conv2d_bwd_filter(dpig_ctx* ctx, const dpig_tensor* x, const dpig_tensor* dy,
+                                      int32_t kh, int32_t kw, int32_t stride, int32_t cin,
+                                      int32_t cout, float* dw, dpig_stream stream) {
+  DPIG_CHECK_CTX(ctx);
+  if (!x || !dy || !dw) return set_error(ctx, DPIG_EINVAL, "conv2d_bwd_filter: null argument");
+  if (kh * kw > kMaxTaps || (stride != 1 && stride != 2))
+    return set_error(ctx, DPIG_EUNSUPPORTED, "conv2d_bwd_filter: k=%dx%d stride=%d unsupported", kh, kw, stride);
+  if (x->c % 8 || x->pix_stride % 8 || dy->c % 8 || dy->pix_stride % 8)
+    return set_error(ctx, DPIG_EINVAL, "conv2d_bwd_filter: channels / pixel stride must be multiples of 8");
+  const int OH = same_out(x->h, stride), OW = same_out(x->w, stride);
+  if (OH != dy->h || OW != dy->w || x->n != dy->n)
+    return set_error(ctx, DPIG_EINVAL, "conv2d_bwd_filter: x/dy shape mismatch");
+  const int pt = same_pad_before(x->h, kh, stride), pl = same_pad_before(x->w, kw, stride);
+
+  WgradParams P;
+  memset(&P, 0, sizeof(P));
+  P.planes = (x->lo && dy->lo && !ctx->fast_mode) ? 2 : 1;
+  P.cin = cin;
+  P.cout = cout;
+  const int c64 = (cout + 63) / 64 * 64;
+  P.block_n = c64 <= 256 ? c64 : (c64 % 256 == 0 ? 256 : (c64 % 192 == 0 ? 192 : (c64 % 128 == 0 ? 128 : 64)));
+  P.n_tiles = (cout + P.block_n - 1) / P.block_n;
+  P.b_bytes = P.block_n * 128;
+  P.tmem_cols = pow2_cols(P.block_n) < 64 ? 64 : pow2_cols(P.block_n);
+  Box b = choose_box(OW, OH, x->n, 64, true);
+  P.PW = b.bw;
+  P.PH = b.bh;
+  P.PN = b.bn;
+  P.tiles_w = (OW + b.bw - 1) / b.bw;
+  P.tiles_h = (OH + b.bh - 1) / b.bh;
+  const int tiles_n = (x->n + b.bn - 1) / b.bn;
+  P.total_tiles = P.tiles_w * P.tiles_h * tiles_n;
+  const int m_tiles = (cin + 127) / 128;
+  const int base = m_tiles * P.n_tiles * kh * kw;
+  int ksplit = (3 * ctx->num_sms + base - 1) / base;
+  ksplit = std::max(1, std::min(ksplit, P.total_tiles));
+  P.tiles_per_cta = (P.total_tiles + ksplit - 1) / ksplit;
+  ksplit = (P.total_tiles + P.tiles_per_cta - 1) / P.tiles_per_cta;
+  P.dw = dw;
+
+  int rc;
+  int ntaps = 0;
+  bool used[4] = {false, false, false, false};
+  for (int i = 0; i < kh; ++i)
+    for (int j = 0; j < kw; ++j) {
+      const int dyy = i - pt, dxx = j - pl;
+      ConvTap t;
+      if (stride == 1) {
+        t.src = 0;
+        t.dh = dyy;
+        t.dw = dxx;
+      } else {
+        const int py = ((dyy % 2) + 2) % 2, px = ((dxx % 2) + 2) % 2;
+        t.src = py * 2 + px;
+        t.dh = floordiv(dyy, 2);
+        t.dw = floordiv(dxx, 2);
+      }
+      t.wtap = i * kw + j;
+      used[t.src] = true;
+      P.taps[ntaps++] = t;
+    }
+  for (int s = 0; s < 4; ++s) {
+    if (!used[s]) continue;
+    for (int pln = 0; pln < P.planes; ++pln)
+      if ((rc = act_map(ctx, &P.x_map[s][pln], pln ? x->lo : x->hi, x, stride, stride == 1 ? 0 : s / 2,
+                        stride == 1 ? 0 : s % 2, b.bw, b.bh, b.bn)))
+        return rc;
+  }
+  for (int pln = 0; pln < P.planes; ++pln)
+    if ((rc = act_map(ctx, &P.dy_map[pln], pln ? dy->lo : dy->hi, dy, 1, 0, 0, b.bw, b.bh, b.bn))) return rc;
+
+  const uint32_t stage_bytes = P.planes * (kABytes + P.b_bytes);
+  int stages = (ctx->max_smem_optin - 1024 - 256) / stage_bytes;
+  if (stages > 6) stages = 6;
+  if (stages < 2) return set_error(ctx, DPIG_EUNSUPPORTED, "wgrad tile does not fit shared memory");
+  P.stages = stages;
+  const size_t smem = static_cast<size_t>(stages) * stage_bytes + 1024 + 256;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(wgrad_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->max_smem_optin);
+    attr_set = true;
+  }
+  dim3 grid(m_tiles * P.n_tiles, kh * kw, ksplit);
+  wgrad_umma_kernel<<<grid, 192, smem, static_cast<cudaStream_t>(stream)>>>(P);
+  ctx->launches++;
+  return check_launch(ctx, "wgrad_umma_kernel");
+}

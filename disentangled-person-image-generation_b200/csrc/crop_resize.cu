@@ -1,0 +1,149 @@
+// tf.image.crop_and_resize (bilinear, extrapolation_value = 0) and its image gradient, as used for the
+// 7 body-part ROIs of the appearance encoder (reference models.py:406-415; DF: models.py:342-350).
+// Sampling rule restated from TensorFlow 1.4 core/kernels/crop_and_resize_op.cc:
+//   in_y = y1*(H-1) + y*(y2-y1)*(H-1)/(crop_h-1)   (crop_h > 1), 0.5*(y1+y2)*(H-1) otherwise;
+//   rows / columns with in_y outside [0, H-1] (resp. in_x, W-1) produce the extrapolation value;
+//   value = top + (bottom-top)*y_lerp with top = tl + (tr-tl)*x_lerp, bottom = bl + (br-bl)*x_lerp.
+// The optional mask multiplies the image on the fly, so x_fg = x*m (models.py:402) is never stored.
+#include "common.cuh"
+
+namespace dpig {
+
+struct CropGeom {
+  int N, H, W, C, CH, CW;
+};
+
+__device__ __forceinline__ bool sample_coords(const float* box, int y, int x, const CropGeom& g, int& top,
+                                              int& bottom, int& left, int& right, float& ylerp, float& xlerp) {
+  const float y1 = box[0], x1 = box[1], y2 = box[2], x2 = box[3];
+  const float hs = (g.CH > 1) ? (y2 - y1) * (g.H - 1) / (g.CH - 1) : 0.f;
+  const float ws = (g.CW > 1) ? (x2 - x1) * (g.W - 1) / (g.CW - 1) : 0.f;
+  const float in_y = (g.CH > 1) ? y1 * (g.H - 1) + y * hs : 0.5f * (y1 + y2) * (g.H - 1);
+  if (in_y < 0.f || in_y > g.H - 1) return false;
+  const float in_x = (g.CW > 1) ? x1 * (g.W - 1) + x * ws : 0.5f * (x1 + x2) * (g.W - 1);
+  if (in_x < 0.f || in_x > g.W - 1) return false;
+  top = static_cast<int>(floorf(in_y));
+  bottom = static_cast<int>(ceilf(in_y));
+  left = static_cast<int>(floorf(in_x));
+  right = static_cast<int>(ceilf(in_x));
+  ylerp = in_y - top;
+  xlerp = in_x - left;
+  return true;
+}
+
+__device__ __forceinline__ float ld_split(const __nv_bfloat16* hi, const __nv_bfloat16* lo, long long off) {
+  float v = __bfloat162float(hi[off]);
+  if (lo) v += __bfloat162float(lo[off]);
+  return v;
+}
+
+__global__ void crop_resize_fwd_kernel(const __nv_bfloat16* ihi, const __nv_bfloat16* ilo, long long ips,
+                                       const float* mask, const float* boxes, const int* box_ind, int nbox,
+                                       CropGeom g, __nv_bfloat16* ohi, __nv_bfloat16* olo, long long ops) {
+  const long long total = static_cast<long long>(nbox) * g.CH * g.CW * g.C;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % g.C);
+    const long long opix = i / g.C;
+    const int x = static_cast<int>(opix % g.CW);
+    const int y = static_cast<int>((opix / g.CW) % g.CH);
+    const int b = static_cast<int>(opix / (static_cast<long long>(g.CW) * g.CH));
+    const int n = box_ind[b];
+    float v = 0.f;
+    int t, bo, l, r;
+    float yl, xl;
+    if (n >= 0 && n < g.N && sample_coords(boxes + 4 * b, y, x, g, t, bo, l, r, yl, xl)) {
+      const long long base = static_cast<long long>(n) * g.H * g.W;
+      const long long ptl = base + static_cast<long long>(t) * g.W + l, ptr = base + static_cast<long long>(t) * g.W + r;
+      const long long pbl = base + static_cast<long long>(bo) * g.W + l, pbr = base + static_cast<long long>(bo) * g.W + r;
+      float tl = ld_split(ihi, ilo, ptl * ips + c), tr = ld_split(ihi, ilo, ptr * ips + c);
+      float bl = ld_split(ihi, ilo, pbl * ips + c), br = ld_split(ihi, ilo, pbr * ips + c);
+      if (mask) {
+        tl *= mask[ptl];
+        tr *= mask[ptr];
+        bl *= mask[pbl];
+        br *= mask[pbr];
+      }
+      const float top = tl + (tr - tl) * xl;
+      const float bot = bl + (br - bl) * xl;
+      v = top + (bot - top) * yl;
+    }
+    __nv_bfloat16 h, lo2;
+    split_bf16(v, h, lo2);
+    ohi[opix * ops + c] = h;
+    if (olo) olo[opix * ops + c] = lo2;
+  }
+}
+
+__global__ void crop_resize_bwd_kernel(const __nv_bfloat16* ghi, const __nv_bfloat16* glo, long long gps,
+                                       const float* mask, const float* boxes, const int* box_ind, int nbox,
+                                       CropGeom g, float* gimg) {
+  const long long total = static_cast<long long>(nbox) * g.CH * g.CW * g.C;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % g.C);
+    const long long opix = i / g.C;
+    const int x = static_cast<int>(opix % g.CW);
+    const int y = static_cast<int>((opix / g.CW) % g.CH);
+    const int b = static_cast<int>(opix / (static_cast<long long>(g.CW) * g.CH));
+    const int n = box_ind[b];
+    int t, bo, l, r;
+    float yl, xl;
+    if (n < 0 || n >= g.N || !sample_coords(boxes + 4 * b, y, x, g, t, bo, l, r, yl, xl)) continue;
+    const float gv = ld_split(ghi, glo, opix * gps + c);
+    const long long base = static_cast<long long>(n) * g.H * g.W;
+    const long long ptl = base + static_cast<long long>(t) * g.W + l, ptr = base + static_cast<long long>(t) * g.W + r;
+    const long long pbl = base + static_cast<long long>(bo) * g.W + l, pbr = base + static_cast<long long>(bo) * g.W + r;
+    const float dtop = (1.f - yl) * gv, dbot = yl * gv;
+    float wtl = (1.f - xl) * dtop, wtr = xl * dtop, wbl = (1.f - xl) * dbot, wbr = xl * dbot;
+    if (mask) {
+      wtl *= mask[ptl];
+      wtr *= mask[ptr];
+      wbl *= mask[pbl];
+      wbr *= mask[pbr];
+    }
+    atomicAdd(gimg + ptl * g.C + c, wtl);
+    atomicAdd(gimg + ptr * g.C + c, wtr);
+    atomicAdd(gimg + pbl * g.C + c, wbl);
+    atomicAdd(gimg + pbr * g.C + c, wbr);
+  }
+}
+
+}  // namespace dpig
+using namespace dpig;
+
+extern "C" int dpig_crop_and_resize_fwd(dpig_ctx* ctx, const dpig_tensor* image, const float* mask,
+                                        const float* boxes, const int32_t* box_ind, int32_t nbox,
+                                        const dpig_tensor* out, dpig_stream stream) {
+  DPIG_CHECK_CTX(ctx);
+  if (!image || !boxes || !box_ind || !out || out->n != nbox || out->c != image->c)
+    return set_error(ctx, DPIG_EINVAL, "crop_and_resize_fwd: bad argument");
+  CropGeom g{image->n, image->h, image->w, image->c, out->h, out->w};
+  const long long total = static_cast<long long>(nbox) * g.CH * g.CW * g.C;
+  long long grid = (total + 255) / 256;
+  if (grid > 148 * 32) grid = 148 * 32;
+  crop_resize_fwd_kernel<<<static_cast<int>(grid), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(image->hi), static_cast<const __nv_bfloat16*>(image->lo),
+      image->pix_stride, mask, boxes, box_ind, nbox, g, static_cast<__nv_bfloat16*>(out->hi),
+      static_cast<__nv_bfloat16*>(out->lo), out->pix_stride);
+  ctx->launches++;
+  return check_launch(ctx, "crop_resize_fwd");
+}
+
+extern "C" int dpig_crop_and_resize_bwd(dpig_ctx* ctx, const dpig_tensor* grad, const float* mask,
+                                        const float* boxes, const int32_t* box_ind, int32_t nbox,
+                                        float* grad_image, int32_t n, int32_t h, int32_t w_, int32_t c,
+                                        dpig_stream stream) {
+  DPIG_CHECK_CTX(ctx);
+  if (!grad || !boxes || !box_ind || !grad_image || grad->n != nbox || grad->c != c)
+    return set_error(ctx, DPIG_EINVAL, "crop_and_resize_bwd: bad argument");
+  CropGeom g{n, h, w_, c, grad->h, grad->w};
+  const long long total = static_cast<long long>(nbox) * g.CH * g.CW * g.C;
+  long long grid = (total + 255) / 256;
+  if (grid > 148 * 32) grid = 148 * 32;
+  crop_resize_bwd_kernel<<<static_cast<int>(grid), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(grad->hi), static_cast<const __nv_bfloat16*>(grad->lo),
+      grad->pix_stride, mask, boxes, box_ind, nbox, g, grad_image);
+  ctx->launches++;
+  return check_launch(ctx, "crop_resize_bwd");
+}

@@ -1,0 +1,408 @@
+// HBM-bound glue kernels on split-bf16 NHWC tensors: gradient combination / ReLU masks / 2x2 pooling,
+// fp32 <-> split conversion, foreground/background masking (models.py:402-403), embedding
+// broadcast (trainer.py:588-590) and its gradient, bias gradients, weight packing.
+// All kernels move 16 bytes per thread per plane (8 bf16 channels) with grid-stride loops.
+#include <algorithm>
+#include "common.cuh"
+
+namespace dpig {
+
+__device__ __forceinline__ void load8(const __nv_bfloat16* hi, const __nv_bfloat16* lo, long long off,
+                                      float (&f)[8], bool accumulate) {
+  const uint4 a = __ldg(reinterpret_cast<const uint4*>(hi + off));
+  const uint32_t aw[4] = {a.x, a.y, a.z, a.w};
+  float t[8];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    t[2 * j] = bf16_bits_to_float(aw[j] & 0xFFFF);
+    t[2 * j + 1] = bf16_bits_to_float(aw[j] >> 16);
+  }
+  if (lo) {
+    const uint4 b = __ldg(reinterpret_cast<const uint4*>(lo + off));
+    const uint32_t bw[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      t[2 * j] += bf16_bits_to_float(bw[j] & 0xFFFF);
+      t[2 * j + 1] += bf16_bits_to_float(bw[j] >> 16);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) f[j] = accumulate ? f[j] + t[j] : t[j];
+}
+
+__device__ __forceinline__ void store8(__nv_bfloat16* hi, __nv_bfloat16* lo, long long off,
+                                       const float (&f)[8]) {
+  uint32_t h[4], l[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    __nv_bfloat16 h0, l0, h1, l1;
+    split_bf16(f[2 * j], h0, l0);
+    split_bf16(f[2 * j + 1], h1, l1);
+    h[j] = static_cast<uint32_t>(__bfloat16_as_ushort(h0)) | (static_cast<uint32_t>(__bfloat16_as_ushort(h1)) << 16);
+    l[j] = static_cast<uint32_t>(__bfloat16_as_ushort(l0)) | (static_cast<uint32_t>(__bfloat16_as_ushort(l1)) << 16);
+  }
+  *reinterpret_cast<uint4*>(hi + off) = make_uint4(h[0], h[1], h[2], h[3]);
+  if (lo) *reinterpret_cast<uint4*>(lo + off) = make_uint4(l[0], l[1], l[2], l[3]);
+}
+
+struct TView {
+  const __nv_bfloat16* hi;
+  const __nv_bfloat16* lo;
+  long long ps;
+};
+
+__global__ void ew_combine_kernel(__nv_bfloat16* ohi, __nv_bfloat16* olo, long long ops, int N, int H,
+                                  int W, int C, TView a, TView b, TView c, const float* f32,
+                                  long long f32_ps, const uint32_t* mask, float mask_neg, int pool2) {
+  const int C8 = C / 8;
+  const long long total = static_cast<long long>(N) * H * W * C8;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c8 = static_cast<int>(i % C8);
+    const long long pix = i / C8;
+    const int ch = c8 * 8;
+    float f[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    const int reps = pool2 ? 2 : 1;
+    const int x = static_cast<int>(pix % W);
+    const int y = static_cast<int>((pix / W) % H);
+    const int n = static_cast<int>(pix / (static_cast<long long>(W) * H));
+    for (int dy = 0; dy < reps; ++dy)
+      for (int dx = 0; dx < reps; ++dx) {
+        const long long ip = pool2 ? ((static_cast<long long>(n) * (2 * H) + 2 * y + dy) * (2 * W) + 2 * x + dx) : pix;
+        if (a.hi) load8(a.hi, a.lo, ip * a.ps + ch, f, true);
+        if (b.hi) load8(b.hi, b.lo, ip * b.ps + ch, f, true);
+        if (c.hi) load8(c.hi, c.lo, ip * c.ps + ch, f, true);
+        if (f32) {
+          const float* s = f32 + ip * f32_ps + ch;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) f[j] += __ldg(s + j);
+        }
+      }
+    if (mask) {
+      const uint32_t m = mask[pix * ((C + 31) / 32) + (ch >> 5)] >> (ch & 31);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] *= ((m >> j) & 1u) ? 1.f : mask_neg;
+    }
+    store8(ohi, olo, pix * ops + ch, f);
+  }
+}
+
+__global__ void pack_f32_kernel(const float* src, long long sps, int csrc, __nv_bfloat16* ohi,
+                                __nv_bfloat16* olo, long long ops, long long pixels, int C) {
+  const int C8 = C / 8;
+  const long long total = pixels * C8;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int ch = static_cast<int>(i % C8) * 8;
+    const long long pix = i / C8;
+    float f[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) f[j] = (ch + j < csrc) ? __ldg(src + pix * sps + ch + j) : 0.f;
+    store8(ohi, olo, pix * ops + ch, f);
+  }
+}
+
+__global__ void unpack_f32_kernel(TView s, float* dst, long long dps, long long pixels, int C) {
+  const int C8 = C / 8;
+  const long long total = pixels * C8;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int ch = static_cast<int>(i % C8) * 8;
+    const long long pix = i / C8;
+    float f[8];
+    load8(s.hi, s.lo, pix * s.ps + ch, f, false);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) dst[pix * dps + ch + j] = f[j];
+  }
+}
+
+__global__ void mask_split_kernel(TView x, const float* m, __nv_bfloat16* fhi, __nv_bfloat16* flo,
+                                  long long fps, __nv_bfloat16* bhi, __nv_bfloat16* blo, long long bps,
+                                  long long pixels, int C) {
+  const int C8 = C / 8;
+  const long long total = pixels * C8;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int ch = static_cast<int>(i % C8) * 8;
+    const long long pix = i / C8;
+    float f[8], g[8];
+    load8(x.hi, x.lo, pix * x.ps + ch, f, false);
+    const float mv = __ldg(m + pix);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      g[j] = f[j] * (1.0f - mv);
+      f[j] = f[j] * mv;
+    }
+    if (fhi) store8(fhi, flo, pix * fps + ch, f);
+    if (bhi) store8(bhi, blo, pix * bps + ch, g);
+  }
+}
+
+__global__ void broadcast_emb_kernel(const float* emb, int ce, __nv_bfloat16* ohi, __nv_bfloat16* olo,
+                                     long long ops, long long pix_per_img, long long pixels) {
+  const int C8 = ce / 8;
+  const long long total = pixels * C8;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int ch = static_cast<int>(i % C8) * 8;
+    const long long pix = i / C8;
+    const long long n = pix / pix_per_img;
+    float f[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) f[j] = __ldg(emb + n * ce + ch + j);
+    store8(ohi, olo, pix * ops + ch, f);
+  }
+}
+
+// out[n][c] = sum over the image's pixels.  grid = (chunks, n); block = 256 threads.
+__global__ void spatial_sum_kernel(TView g, float* out, int C, long long pix_per_img, int chunk) {
+  const int n = blockIdx.y;
+  const long long p0 = static_cast<long long>(blockIdx.x) * chunk;
+  const long long p1 = min(p0 + chunk, pix_per_img);
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float acc = 0.f;
+    for (long long p = p0; p < p1; ++p) {
+      const long long off = (n * pix_per_img + p) * g.ps + c;
+      float v = __bfloat162float(g.hi[off]);
+      if (g.lo) v += __bfloat162float(g.lo[off]);
+      acc += v;
+    }
+    atomicAdd(out + static_cast<long long>(n) * C + c, acc);
+  }
+}
+
+// db[c] += sum over pixels.  grid = chunks of pixels; block threads stride over channels.
+__global__ void bias_grad_kernel(TView g, const float* f32, long long f32_ps, float* db, int C,
+                                 long long pixels, int chunk) {
+  const long long p0 = static_cast<long long>(blockIdx.x) * chunk;
+  const long long p1 = min(p0 + chunk, pixels);
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float acc = 0.f;
+    for (long long p = p0; p < p1; ++p) {
+      if (f32) {
+        acc += __ldg(f32 + p * f32_ps + c);
+      } else {
+        const long long off = p * g.ps + c;
+        float v = __bfloat162float(g.hi[off]);
+        if (g.lo) v += __bfloat162float(g.lo[off]);
+        acc += v;
+      }
+    }
+    atomicAdd(db + c, acc);
+  }
+}
+
+__global__ void act_bwd_f32_kernel(const float* y, float* dy, long long count, float neg) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < count;
+       i += static_cast<long long>(gridDim.x) * blockDim.x)
+    dy[i] *= (y[i] > 0.f) ? 1.f : neg;
+}
+
+__global__ void denorm_u8_kernel(const float* g, long long count, uint8_t* out) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < count;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    float v = (g[i] + 1.f) * 127.5f;
+    v = fminf(fmaxf(v, 0.f), 255.f);
+    out[i] = static_cast<uint8_t>(v);  // tf.cast(float->uint8) truncates; save_image path
+  }
+}
+
+// One tap at a time: w[tap][ci][co] -> fwd[tap][co][ci_pad] (transposed) and bwd[tap][ci][co_pad].
+__global__ void weight_pack_kernel(const float* w, int cin, int cout, int cin_pad, int cout_pad,
+                                   __nv_bfloat16* fhi, __nv_bfloat16* flo, __nv_bfloat16* bhi,
+                                   __nv_bfloat16* blo) {
+  __shared__ float tile[32][33];
+  const int tap = blockIdx.z;
+  const int ci0 = blockIdx.y * 32, co0 = blockIdx.x * 32;
+  const float* wt = w + static_cast<long long>(tap) * cin * cout;
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    const int ci = ci0 + r, co = co0 + threadIdx.x;
+    const float v = (ci < cin && co < cout) ? wt[static_cast<long long>(ci) * cout + co] : 0.f;
+    tile[r][threadIdx.x] = v;
+    if (bhi && ci < cin && co < cout_pad) {
+      __nv_bfloat16 h, l;
+      split_bf16(v, h, l);
+      const long long o = (static_cast<long long>(tap) * cin + ci) * cout_pad + co;
+      bhi[o] = h;
+      if (blo) blo[o] = l;
+    }
+  }
+  __syncthreads();
+  if (fhi) {
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+      const int co = co0 + r, ci = ci0 + threadIdx.x;
+      if (co < cout && ci < cin_pad) {
+        __nv_bfloat16 h, l;
+        split_bf16(tile[threadIdx.x][r], h, l);
+        const long long o = (static_cast<long long>(tap) * cout + co) * cin_pad + ci;
+        fhi[o] = h;
+        if (flo) flo[o] = l;
+      }
+    }
+  }
+}
+
+static inline int grid_for(long long total, int block = 256, int cap = 148 * 16) {
+  long long g = (total + block - 1) / block;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return static_cast<int>(g);
+}
+static inline TView view(const dpig_tensor* t) {
+  TView v{nullptr, nullptr, 0};
+  if (t) {
+    v.hi = static_cast<const __nv_bfloat16*>(t->hi);
+    v.lo = static_cast<const __nv_bfloat16*>(t->lo);
+    v.ps = t->pix_stride;
+  }
+  return v;
+}
+static inline bool aligned8(const dpig_tensor* t) {
+  return !t || (t->c % 8 == 0 && t->pix_stride % 8 == 0 && reinterpret_cast<uintptr_t>(t->hi) % 16 == 0 &&
+                reinterpret_cast<uintptr_t>(t->lo) % 16 == 0);
+}
+
+}  // namespace dpig
+using namespace dpig;
+
+extern "C" int dpig_ew_combine(dpig_ctx* ctx, const dpig_tensor* out, const dpig_tensor* a,
+                               const dpig_tensor* b, const dpig_tensor* c, const float* f32,
+                               int64_t f32_pix_stride, const uint32_t* mask, float mask_neg,
+                               int32_t pool2, dpig_stream stream) {
+  DPIG_CHECK_CTX(ctx);
+  if (!out || !out->hi) return set_error(ctx, DPIG_EINVAL, "ew_combine: null output");
+  if (!aligned8(out) || !aligned8(a) || !aligned8(b) || !aligned8(c))
+    return set_error(ctx, DPIG_EINVAL, "ew_combine: tensors must be 8-channel / 16-byte aligned");
+  const int k = pool2 ? 2 : 1;
+  const dpig_tensor* ins[3] = {a, b, c};
+  for (auto t : ins)
+    if (t && (t->n != out->n || t->h != out->h * k || t->w != out->w * k || t->c < out->c))
+      return set_error(ctx, DPIG_EINVAL, "ew_combine: input shape mismatch");
+  const long long total = static_cast<long long>(out->n) * out->h * out->w * (out->c / 8);
+  ew_combine_kernel<<<grid_for(total), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<__nv_bfloat16*>(out->hi), static_cast<__nv_bfloat16*>(out->lo), out->pix_stride, out->n,
+      out->h, out->w, out->c, view(a), view(b), view(c), f32, f32_pix_stride, mask, mask_neg, pool2);
+  ctx->launches++;
+  return check_launch(ctx, "ew_combine");
+}
+
+extern "C" int dpig_pack_f32(dpig_ctx* ctx, const float* src, int64_t src_pix_stride, int32_t c_src,
+                             const dpig_tensor* out, dpig_stream stream) {
+  DPIG_CHECK_CTX(ctx);
+  if (!src || !out || !aligned8(out)) return set_error(ctx, DPIG_EINVAL, "pack_f32: bad argument");
+  const long long pixels = static_cast<long long>(out->n) * out->h * out->w;
+  pack_f32_kernel<<<grid_for(pixels * (out->c / 8)), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      src, src_pix_stride, c_src, static_cast<__nv_bfloat16*>(out->hi), static_cast<__nv_bfloat16*>(out->lo),
+      out->pix_stride, pixels, out->c);
+  ctx->launches++;
+  return check_launch(ctx, "pack_f32");
+}
+
+extern "C" int dpig_unpack_f32(dpig_ctx* ctx, const dpig_tensor* src, float* dst, int64_t dst_pix_stride,
+                               dpig_stream stream) {
+  DPIG_CHECK_CTX(ctx);
+  if (!src || !dst || !aligned8(src)) return set_error(ctx, DPIG_EINVAL, "unpack_f32: bad argument");
+  const long long pixels = static_cast<long long>(src->n) * src->h * src->w;
+  unpack_f32_kernel<<<grid_for(pixels * (src->c / 8)), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      view(src), dst, dst_pix_stride, pixels, src->c);
+  ctx->launches++;
+  return check_launch(ctx, "unpack_f32");
+}
+
+extern "C" int dpig_mask_split(dpig_ctx* ctx, const dpig_tensor* x, const float* m, const dpig_tensor* fg,
+                               const dpig_tensor* bg, dpig_stream stream) {
+  DPIG_CHECK_CTX(ctx);
+  if (!x || !m || !aligned8(x) || !aligned8(fg) || !aligned8(bg))
+    return set_error(ctx, DPIG_EINVAL, "mask_split: bad argument");
+  const long long pixels = static_cast<long long>(x->n) * x->h * x->w;
+  mask_split_kernel<<<grid_for(pixels * (x->c / 8)), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      view(x), m, fg ? static_cast<__nv_bfloat16*>(fg->hi) : nullptr,
+      fg ? static_cast<__nv_bfloat16*>(fg->lo) : nullptr, fg ? fg->pix_stride : 0,
+      bg ? static_cast<__nv_bfloat16*>(bg->hi) : nullptr, bg ? static_cast<__nv_bfloat16*>(bg->lo) : nullptr,
+      bg ? bg->pix_stride : 0, pixels, x->c);
+  ctx->launches++;
+  return check_launch(ctx, "mask_split");
+}
+
+extern "C" int dpig_broadcast_embedding(dpig_ctx* ctx, const float* emb, int32_t ce, const dpig_tensor* out,
+                                        dpig_stream stream) {
+  DPIG_CHECK_CTX(ctx);
+  if (!emb || !out || ce % 8 || !aligned8(out) || out->c < ce)
+    return set_error(ctx, DPIG_EINVAL, "broadcast_embedding: bad argument");
+  const long long ppi = static_cast<long long>(out->h) * out->w;
+  const long long pixels = ppi * out->n;
+  broadcast_emb_kernel<<<grid_for(pixels * (ce / 8)), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      emb, ce, static_cast<__nv_bfloat16*>(out->hi), static_cast<__nv_bfloat16*>(out->lo), out->pix_stride,
+      ppi, pixels);
+  ctx->launches++;
+  return check_launch(ctx, "broadcast_embedding");
+}
+
+extern "C" int dpig_spatial_sum(dpig_ctx* ctx, const dpig_tensor* g, float* out, dpig_stream stream) {
+  DPIG_CHECK_CTX(ctx);
+  if (!g || !out) return set_error(ctx, DPIG_EINVAL, "spatial_sum: bad argument");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  cudaMemsetAsync(out, 0, sizeof(float) * g->n * g->c, s);
+  const long long ppi = static_cast<long long>(g->h) * g->w;
+  const int chunk = 64;
+  dim3 grid(static_cast<unsigned>((ppi + chunk - 1) / chunk), g->n);
+  spatial_sum_kernel<<<grid, 256, 0, s>>>(view(g), out, g->c, ppi, chunk);
+  ctx->launches++;
+  return check_launch(ctx, "spatial_sum");
+}
+
+extern "C" int dpig_bias_grad(dpig_ctx* ctx, const dpig_tensor* dy, float* db, dpig_stream stream) {
+  DPIG_CHECK_CTX(ctx);
+  if (!dy || !db) return set_error(ctx, DPIG_EINVAL, "bias_grad: bad argument");
+  const long long pixels = static_cast<long long>(dy->n) * dy->h * dy->w;
+  int chunk = static_cast<int>((pixels + 148 * 4 - 1) / (148 * 4));
+  if (chunk < 16) chunk = 16;
+  bias_grad_kernel<<<static_cast<unsigned>((pixels + chunk - 1) / chunk), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      view(dy), nullptr, 0, db, dy->c, pixels, chunk);
+  ctx->launches++;
+  return check_launch(ctx, "bias_grad");
+}
+
+extern "C" int dpig_bias_grad_f32(dpig_ctx* ctx, const float* dy, int64_t pixels, int32_t c, float* db,
+                                  dpig_stream stream) {
+  DPIG_CHECK_CTX(ctx);
+  if (!dy || !db) return set_error(ctx, DPIG_EINVAL, "bias_grad_f32: bad argument");
+  int chunk = static_cast<int>((pixels + 148 * 4 - 1) / (148 * 4));
+  if (chunk < 16) chunk = 16;
+  TView none{nullptr, nullptr, 0};
+  bias_grad_kernel<<<static_cast<unsigned>((pixels + chunk - 1) / chunk), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      none, dy, c, db, c, pixels, chunk);
+  ctx->launches++;
+  return check_launch(ctx, "bias_grad_f32");
+}
+
+extern "C" int dpig_act_bwd_f32(dpig_ctx* ctx, const float* y, float* dy, int64_t count, float neg,
+                                dpig_stream stream) {
+  DPIG_CHECK_CTX(ctx);
+  act_bwd_f32_kernel<<<grid_for(count), 256, 0, static_cast<cudaStream_t>(stream)>>>(y, dy, count, neg);
+  ctx->launches++;
+  return check_launch(ctx, "act_bwd_f32");
+}
+
+extern "C" int dpig_denorm_u8(dpig_ctx* ctx, const float* g, int64_t count, uint8_t* out, dpig_stream stream) {
+  DPIG_CHECK_CTX(ctx);
+  denorm_u8_kernel<<<grid_for(count), 256, 0, static_cast<cudaStream_t>(stream)>>>(g, count, out);
+  ctx->launches++;
+  return check_launch(ctx, "denorm_u8");
+}
+
+extern "C" int dpig_weight_pack(dpig_ctx* ctx, const float* w_hwio, int32_t taps, int32_t cin, int32_t cout,
+                                int32_t cin_pad, int32_t cout_pad, void* fwd_hi, void* fwd_lo, void* bwd_hi,
+                                void* bwd_lo, dpig_stream stream) {
+  DPIG_CHECK_CTX(ctx);
+  if (!w_hwio || cin_pad < cin || cout_pad < cout)
+    return set_error(ctx, DPIG_EINVAL, "weight_pack: bad argument");
+  dim3 grid((std::max(cout, cout_pad) + 31) / 32, (std::max(cin, cin_pad) + 31) / 32, taps);
+  dim3 block(32, 8);
+  weight_pack_kernel<<<grid, block, 0, static_cast<cudaStream_t>(stream)>>>(
+      w_hwio, cin, cout, cin_pad, cout_pad, static_cast<__nv_bfloat16*>(fwd_hi),
+      static_cast<__nv_bfloat16*>(fwd_lo), static_cast<__nv_bfloat16*>(bwd_hi),
+      static_cast<__nv_bfloat16*>(bwd_lo));
+  ctx->launches++;
+  return check_launch(ctx, "weight_pack");
+}

@@ -1,0 +1,269 @@
+// Losses and optimisers of the Stage-I/II trainers, restating the TensorFlow-1.4 formulas the reference
+// calls:  L1 reconstruction (trainer.py:606-607, 622), GAN losses incl. the WGAN-GP interpolation and
+// penalty (trainer.py:217-252), Adam / RMSProp(+clip) (trainer.py:116-149).  All HBM-bound fp32.
+#include "common.cuh"
+
+namespace dpig {
+
+__device__ __forceinline__ float block_sum(float v, float* sh) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  if (l == 0) sh[w] = v;
+  __syncthreads();
+  float r = 0.f;
+  if (threadIdx.x < 32) {
+    r = (threadIdx.x < (blockDim.x >> 5)) ? sh[threadIdx.x] : 0.f;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) r += __shfl_xor_sync(0xffffffffu, r, o);
+  }
+  __syncthreads();
+  return r;  // valid in thread 0
+}
+
+__global__ void l1_kernel(const float* g, const float* x, long long count, float weight, float* out, float* dg) {
+  __shared__ float sh[32];
+  float acc = 0.f;
+  const float inv = 1.0f / static_cast<float>(count);
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < count;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const float d = g[i] - x[i];
+    acc += fabsf(d);
+    if (dg) dg[i] += weight * inv * (d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f));
+  }
+  const float s = block_sum(acc, sh);
+  if (threadIdx.x == 0) atomicAdd(out, s * inv);
+}
+
+__device__ __forceinline__ float sce(float z, float l) { return fmaxf(z, 0.f) - z * l + log1pf(expf(-fabsf(z))); }
+__device__ __forceinline__ float sigm(float z) { return 1.f / (1.f + expf(-z)); }
+
+// single block; count is the number of logits per side
+__global__ void gan_loss_kernel(int mode, const float* dr, const float* df, int count, float* out, float* dfg,
+                                float* drd, float* dfd) {
+  __shared__ float sh[32];
+  float a = 0.f, b = 0.f, c = 0.f;  // a: generator term on fake, b: disc term on fake, c: disc term on real
+  const float inv = 1.0f / count;
+  for (int i = threadIdx.x; i < count; i += blockDim.x) {
+    const float f = df[i];
+    const float r = dr ? dr[i] : 0.f;
+    if (mode == DPIG_GAN_DCGAN) {
+      a += sce(f, 1.f);
+      b += sce(f, 0.f);
+      c += sce(r, 1.f);
+      if (dfg) dfg[i] = (sigm(f) - 1.f) * inv;
+      if (dfd) dfd[i] = sigm(f) * inv * 0.5f;
+      if (drd) drd[i] = (sigm(r) - 1.f) * inv * 0.5f;
+    } else if (mode == DPIG_GAN_LSGAN) {
+      a += (f - 1.f) * (f - 1.f);
+      b += f * f;
+      c += (r - 1.f) * (r - 1.f);
+      if (dfg) dfg[i] = 2.f * (f - 1.f) * inv;
+      if (dfd) dfd[i] = f * inv;
+      if (drd) drd[i] = (r - 1.f) * inv;
+    } else {  // wgan, wgan-gp (the penalty is added by dpig_gp_penalty)
+      a += -f;
+      b += f;
+      c += -r;
+      if (dfg) dfg[i] = -inv;
+      if (dfd) dfd[i] = inv;
+      if (drd) drd[i] = -inv;
+    }
+  }
+  const float sa = block_sum(a, sh);
+  const float sb = block_sum(b, sh);
+  const float sc = block_sum(c, sh);
+  if (threadIdx.x == 0) {
+    out[0] = sa * inv;
+    const float d = sb * inv + sc * inv;
+    out[1] = (mode == DPIG_GAN_DCGAN || mode == DPIG_GAN_LSGAN) ? 0.5f * d : d;
+  }
+}
+
+__global__ void gp_interp_kernel(const float* x, const float* g, const float* alpha, long long per, long long total,
+                                 float* xhat) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const float a = alpha[i / per];
+    xhat[i] = x[i] + a * (g[i] - x[i]);
+  }
+}
+
+// block = one sample
+__global__ void gp_slopes_kernel(const float* grad, long long per, float* slopes) {
+  __shared__ float sh[32];
+  const float* gptr = grad + blockIdx.x * per;
+  float acc = 0.f;
+  for (long long j = threadIdx.x; j < per; j += blockDim.x) acc = fmaf(gptr[j], gptr[j], acc);
+  const float s = block_sum(acc, sh);
+  if (threadIdx.x == 0) slopes[blockIdx.x] = sqrtf(s);
+}
+__global__ void gp_finish_kernel(const float* grad, const float* slopes, int n, long long per, float lambda,
+                                 float* out, float* dgrad) {
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    float acc = 0.f;
+    for (int i = 0; i < n; ++i) acc += (slopes[i] - 1.f) * (slopes[i] - 1.f);
+    out[0] = acc / n;
+  }
+  if (!dgrad) return;
+  const long long total = per * n;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const float s = slopes[i / per];
+    dgrad[i] = lambda * 2.f * (s - 1.f) / (static_cast<float>(n) * s) * grad[i];
+  }
+}
+
+__global__ void adam_kernel(float* p, const float* g, float* m, float* v, long long count, float lr_t, float b1,
+                            float b2, float eps, float gs) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < count;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const float gi = g[i] * gs;
+    const float mi = b1 * m[i] + (1.f - b1) * gi;
+    const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+    m[i] = mi;
+    v[i] = vi;
+    p[i] -= lr_t * mi / (sqrtf(vi) + eps);
+  }
+}
+
+__global__ void rmsprop_kernel(float* p, const float* g, float* ms, long long count, float lr, float decay,
+                               float eps, float gs, float clip) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < count;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const float gi = g[i] * gs;
+    const float msi = decay * ms[i] + (1.f - decay) * gi * gi;
+    ms[i] = msi;
+    float pi = p[i] - lr * gi / sqrtf(msi + eps);
+    if (clip > 0.f) pi = fminf(fmaxf(pi, -clip), clip);
+    p[i] = pi;
+  }
+}
+
+__global__ void clip_kernel(float* p, long long count, float lo, float hi) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < count;
+       i += static_cast<long long>(gridDim.x) * blockDim.x)
+    p[i] = fminf(fmaxf(p[i], lo), hi);
+}
+
+// tf coord2channel_simple_rcv + tf_poseInflate (utils.py:259-318): +1 inside the radius-4 disc around
+// each visible keypoint (int-truncated row/col), -1 elsewhere.
+__global__ void pose_raster_kernel(const float* rcv, int N, int K, int H, int W, int radius,
+                                   __nv_bfloat16* ohi, __nv_bfloat16* olo, long long ops, float* of32) {
+  const long long total = static_cast<long long>(N) * H * W * K;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int k = static_cast<int>(i % K);
+    const long long pix = i / K;
+    const int x = static_cast<int>(pix % W);
+    const int y = static_cast<int>((pix / W) % H);
+    const int n = static_cast<int>(pix / (static_cast<long long>(W) * H));
+    const float* q = rcv + (static_cast<long long>(n) * K + k) * 3;
+    const int r0 = static_cast<int>(q[0]), c0 = static_cast<int>(q[1]);  // tf.to_int32 truncates
+    const float vis = q[2];
+    const int dr = y - r0, dc = x - c0;
+    const bool inside = (dr * dr + dc * dc <= radius * radius);
+    float v = (inside ? fminf(vis, 1.f) : 0.f) * 2.f - 1.f;
+    if (ohi) {
+      ohi[pix * ops + k] = __float2bfloat16_rn(v);
+      if (olo) olo[pix * ops + k] = __float2bfloat16_rn(v - __bfloat162float(__float2bfloat16_rn(v)));
+    }
+    if (of32) of32[pix * K + k] = v;
+  }
+}
+
+static inline int gridn(long long total, int block = 256, int cap = 148 * 16) {
+  long long g = (total + block - 1) / block;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return static_cast<int>(g);
+}
+
+}  // namespace dpig
+using namespace dpig;
+
+extern "C" int dpig_loss_l1(dpig_ctx* ctx, const float* g, const float* x, int64_t count, float weight,
+                            float* out, float* dg, dpig_stream stream) {
+  DPIG_CHECK_CTX(ctx);
+  if (!g || !x || !out) return set_error(ctx, DPIG_EINVAL, "loss_l1: null argument");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  cudaMemsetAsync(out, 0, sizeof(float), s);
+  l1_kernel<<<gridn(count, 256, 148 * 4), 256, 0, s>>>(g, x, count, weight, out, dg);
+  ctx->launches++;
+  return check_launch(ctx, "loss_l1");
+}
+
+extern "C" int dpig_loss_gan(dpig_ctx* ctx, int32_t mode, const float* d_real, const float* d_fake, int32_t count,
+                             float* out, float* d_fake_g, float* d_real_d, float* d_fake_d, dpig_stream stream) {
+  DPIG_CHECK_CTX(ctx);
+  if (!d_fake || !out) return set_error(ctx, DPIG_EINVAL, "loss_gan: null argument");
+  gan_loss_kernel<<<1, 256, 0, static_cast<cudaStream_t>(stream)>>>(mode, d_real, d_fake, count, out, d_fake_g,
+                                                                     d_real_d, d_fake_d);
+  ctx->launches++;
+  return check_launch(ctx, "loss_gan");
+}
+
+extern "C" int dpig_gp_interpolate(dpig_ctx* ctx, const float* x, const float* g, const float* alpha, int32_t n,
+                                   int64_t per_sample, float* xhat, dpig_stream stream) {
+  DPIG_CHECK_CTX(ctx);
+  if (!x || !g || !alpha || !xhat) return set_error(ctx, DPIG_EINVAL, "gp_interpolate: null argument");
+  const long long total = static_cast<long long>(n) * per_sample;
+  gp_interp_kernel<<<gridn(total), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, g, alpha, per_sample, total, xhat);
+  ctx->launches++;
+  return check_launch(ctx, "gp_interpolate");
+}
+
+extern "C" int dpig_gp_penalty(dpig_ctx* ctx, const float* grad, int32_t n, int64_t per_sample, float lambda,
+                               float* slopes, float* out, float* dgrad, dpig_stream stream) {
+  DPIG_CHECK_CTX(ctx);
+  if (!grad || !slopes || !out) return set_error(ctx, DPIG_EINVAL, "gp_penalty: null argument");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  gp_slopes_kernel<<<n, 256, 0, s>>>(grad, per_sample, slopes);
+  gp_finish_kernel<<<gridn(static_cast<long long>(n) * per_sample), 256, 0, s>>>(grad, slopes, n, per_sample, lambda,
+                                                                                 out, dgrad);
+  ctx->launches += 2;
+  return check_launch(ctx, "gp_penalty");
+}
+
+extern "C" int dpig_adam_step(dpig_ctx* ctx, float* p, const float* g, float* m, float* v, int64_t count, float lr,
+                              float beta1, float beta2, float eps, int32_t t, float grad_scale, dpig_stream stream) {
+  DPIG_CHECK_CTX(ctx);
+  if (!p || !g || !m || !v || t < 1) return set_error(ctx, DPIG_EINVAL, "adam_step: bad argument");
+  const double lr_t = static_cast<double>(lr) * sqrt(1.0 - pow(static_cast<double>(beta2), t)) /
+                      (1.0 - pow(static_cast<double>(beta1), t));
+  adam_kernel<<<gridn(count), 256, 0, static_cast<cudaStream_t>(stream)>>>(p, g, m, v, count, static_cast<float>(lr_t),
+                                                                           beta1, beta2, eps, grad_scale);
+  ctx->launches++;
+  return check_launch(ctx, "adam_step");
+}
+
+extern "C" int dpig_rmsprop_step(dpig_ctx* ctx, float* p, const float* g, float* ms, int64_t count, float lr,
+                                 float decay, float eps, float grad_scale, float clip, dpig_stream stream) {
+  DPIG_CHECK_CTX(ctx);
+  if (!p || !g || !ms) return set_error(ctx, DPIG_EINVAL, "rmsprop_step: null argument");
+  rmsprop_kernel<<<gridn(count), 256, 0, static_cast<cudaStream_t>(stream)>>>(p, g, ms, count, lr, decay, eps,
+                                                                              grad_scale, clip);
+  ctx->launches++;
+  return check_launch(ctx, "rmsprop_step");
+}
+
+extern "C" int dpig_clip(dpig_ctx* ctx, float* p, int64_t count, float lo, float hi, dpig_stream stream) {
+  DPIG_CHECK_CTX(ctx);
+  clip_kernel<<<gridn(count), 256, 0, static_cast<cudaStream_t>(stream)>>>(p, count, lo, hi);
+  ctx->launches++;
+  return check_launch(ctx, "clip");
+}
+
+extern "C" int dpig_pose_rasterize(dpig_ctx* ctx, const float* rcv, int32_t n, int32_t k, int32_t h, int32_t w_,
+                                   int32_t radius, const dpig_tensor* out, float* out_f32, dpig_stream stream) {
+  DPIG_CHECK_CTX(ctx);
+  if (!rcv || (!out && !out_f32)) return set_error(ctx, DPIG_EINVAL, "pose_rasterize: null argument");
+  if (out && (out->n != n || out->h != h || out->w != w_ || out->c < k))
+    return set_error(ctx, DPIG_EINVAL, "pose_rasterize: output shape mismatch");
+  const long long total = static_cast<long long>(n) * h * w_ * k;
+  pose_raster_kernel<<<gridn(total), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      rcv, n, k, h, w_, radius, out ? static_cast<__nv_bfloat16*>(out->hi) : nullptr,
+      out ? static_cast<__nv_bfloat16*>(out->lo) : nullptr, out ? out->pix_stride : 0, out_f32);
+  ctx->launches++;
+  return check_launch(ctx, "pose_rasterize");
+}

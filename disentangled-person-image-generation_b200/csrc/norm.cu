@@ -1,0 +1,275 @@
+// Normalisation + LeakyReLU blocks of the discriminator (reference wgan_gp.py:34-40, 418-430):
+//   MODE 'wgan-gp' -> per-sample LayerNorm over (C,H,W)      tflib/ops/layernorm.py:6-20
+//   otherwise      -> training-mode BatchNorm over (N,H,W)   tflib/ops/batchnorm.py:29-30
+//   (+ InstanceNorm, models.py:154-166, defined in the reference but never called).
+// All use the biased variance and rsqrt(var + eps).  x is the fp32 NHWC conv output (bias added).
+// Raw sums are accumulated in fp64 so var = E[x^2] - mean^2 is safe; the raw-sum interface is also the
+// sync-BN hook: data-parallel ranks all-reduce `sums` (forward) and `red` (backward) between phases.
+#include "common.cuh"
+
+namespace dpig {
+
+__device__ __forceinline__ int group_of(int mode, int n, int c, int C) {
+  return mode == DPIG_NORM_BATCH ? c : (mode == DPIG_NORM_LAYER ? n : n * C + c);
+}
+
+// grid = (pixel chunks, N); threads stride channels.
+__global__ void norm_stats_kernel(const float* x, int C, long long ppi, int chunk, int mode, int groups,
+                                  double* sums) {
+  __shared__ double red[2][32];
+  const int n = blockIdx.y;
+  const long long p0 = static_cast<long long>(blockIdx.x) * chunk;
+  const long long p1 = min(p0 + chunk, ppi);
+  double ls = 0.0, ls2 = 0.0;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float s = 0.f, s2 = 0.f;
+    for (long long p = p0; p < p1; ++p) {
+      const float v = x[(n * ppi + p) * C + c];
+      s += v;
+      s2 = fmaf(v, v, s2);
+    }
+    if (mode == DPIG_NORM_LAYER) {
+      ls += s;
+      ls2 += s2;
+    } else {
+      const int g = group_of(mode, n, c, C);
+      atomicAdd(sums + g, static_cast<double>(s));
+      atomicAdd(sums + groups + g, static_cast<double>(s2));
+    }
+  }
+  if (mode == DPIG_NORM_LAYER) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      ls += __shfl_xor_sync(0xffffffffu, ls, o);
+      ls2 += __shfl_xor_sync(0xffffffffu, ls2, o);
+    }
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    if (l == 0) {
+      red[0][w] = ls;
+      red[1][w] = ls2;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double a = 0, b = 0;
+      for (int i = 0; i < (blockDim.x >> 5); ++i) {
+        a += red[0][i];
+        b += red[1][i];
+      }
+      atomicAdd(sums + n, a);
+      atomicAdd(sums + groups + n, b);
+    }
+  }
+}
+
+__global__ void norm_finalize_kernel(const double* sums, int groups, double count, float eps, float* stats) {
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= groups) return;
+  const double mean = sums[g] / count;
+  double var = sums[groups + g] / count - mean * mean;
+  if (var < 0) var = 0;
+  stats[g] = static_cast<float>(mean);
+  stats[groups + g] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+}
+
+// thread = (pixel, 32-channel word)
+__global__ void norm_act_fwd_kernel(const float* x, int N, long long ppi, int C, int mode, int groups,
+                                    const float* stats, const float* scale, const float* offset, int act,
+                                    float alpha, __nv_bfloat16* ohi, __nv_bfloat16* olo, long long ops,
+                                    uint32_t* mask_out) {
+  const int words = C / 32;
+  const long long total = static_cast<long long>(N) * ppi * words;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int wd = static_cast<int>(i % words);
+    const long long pix = i / words;
+    const int n = static_cast<int>(pix / ppi);
+    uint32_t bits = 0;
+#pragma unroll 4
+    for (int j = 0; j < 32; ++j) {
+      const int c = wd * 32 + j;
+      const int g = group_of(mode, n, c, C);
+      float v = (x[pix * C + c] - stats[g]) * stats[groups + g] * scale[c] + offset[c];
+      if (v > 0.f) bits |= 1u << j;
+      if (act == DPIG_ACT_RELU) v = fmaxf(v, 0.f);
+      else if (act == DPIG_ACT_LRELU) v = v > 0.f ? v : alpha * v;
+      __nv_bfloat16 h, l;
+      split_bf16(v, h, l);
+      ohi[pix * ops + c] = h;
+      if (olo) olo[pix * ops + c] = l;
+    }
+    if (mask_out) mask_out[pix * words + wd] = bits;
+  }
+}
+
+__device__ __forceinline__ float ld_dz(const __nv_bfloat16* hi, const __nv_bfloat16* lo, long long off,
+                                       const uint32_t* mask, long long pix, int words, int c, float alpha) {
+  float v = __bfloat162float(hi[off]);
+  if (lo) v += __bfloat162float(lo[off]);
+  if (mask) {
+    const uint32_t m = mask[pix * words + (c >> 5)];
+    if (!((m >> (c & 31)) & 1u)) v *= alpha;
+  }
+  return v;
+}
+
+// grid = (pixel chunks, N); threads stride channels.
+__global__ void norm_bwd_reduce_kernel(const __nv_bfloat16* ghi, const __nv_bfloat16* glo, long long gps,
+                                       const float* x, int C, long long ppi, int chunk, int mode, int groups,
+                                       const float* stats, const uint32_t* mask, float alpha,
+                                       const float* scale, double* red, float* dscale, float* doffset) {
+  __shared__ double sred[2][32];
+  const int n = blockIdx.y;
+  const int words = C / 32;
+  const long long p0 = static_cast<long long>(blockIdx.x) * chunk;
+  const long long p1 = min(p0 + chunk, ppi);
+  double l1 = 0.0, l2 = 0.0;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const int g = group_of(mode, n, c, C);
+    const float mean = stats[g], rstd = stats[groups + g];
+    float db = 0.f, dg = 0.f;
+    for (long long p = p0; p < p1; ++p) {
+      const long long pix = n * ppi + p;
+      const float dz = ld_dz(ghi, glo, pix * gps + c, mask, pix, words, c, alpha);
+      const float xh = (x[pix * C + c] - mean) * rstd;
+      db += dz;
+      dg = fmaf(dz, xh, dg);
+    }
+    if (doffset) atomicAdd(doffset + c, db);
+    if (dscale) atomicAdd(dscale + c, dg);
+    const float gam = scale[c];
+    if (mode == DPIG_NORM_LAYER) {
+      l1 += static_cast<double>(gam) * db;
+      l2 += static_cast<double>(gam) * dg;
+    } else {
+      atomicAdd(red + g, static_cast<double>(gam) * db);
+      atomicAdd(red + groups + g, static_cast<double>(gam) * dg);
+    }
+  }
+  if (mode == DPIG_NORM_LAYER) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      l1 += __shfl_xor_sync(0xffffffffu, l1, o);
+      l2 += __shfl_xor_sync(0xffffffffu, l2, o);
+    }
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    if (l == 0) {
+      sred[0][w] = l1;
+      sred[1][w] = l2;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double a = 0, b = 0;
+      for (int i = 0; i < (blockDim.x >> 5); ++i) {
+        a += sred[0][i];
+        b += sred[1][i];
+      }
+      atomicAdd(red + n, a);
+      atomicAdd(red + groups + n, b);
+    }
+  }
+}
+
+__global__ void norm_bwd_apply_kernel(const __nv_bfloat16* ghi, const __nv_bfloat16* glo, long long gps,
+                                      const float* x, int N, long long ppi, int C, int mode, int groups,
+                                      const float* stats, const uint32_t* mask, float alpha, const float* scale,
+                                      const double* red, double count, __nv_bfloat16* ohi, __nv_bfloat16* olo,
+                                      long long ops) {
+  const int words = C / 32;
+  const long long total = static_cast<long long>(N) * ppi * C;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % C);
+    const long long pix = i / C;
+    const int n = static_cast<int>(pix / ppi);
+    const int g = group_of(mode, n, c, C);
+    const float mean = stats[g], rstd = stats[groups + g];
+    const float dz = ld_dz(ghi, glo, pix * gps + c, mask, pix, words, c, alpha);
+    const float xh = (x[pix * C + c] - mean) * rstd;
+    const float m1 = static_cast<float>(red[g] / count), m2 = static_cast<float>(red[groups + g] / count);
+    const float dx = rstd * (dz * scale[c] - m1 - xh * m2);
+    __nv_bfloat16 h, l;
+    split_bf16(dx, h, l);
+    ohi[pix * ops + c] = h;
+    if (olo) olo[pix * ops + c] = l;
+  }
+}
+
+static inline int groups_of(int mode, int n, int c) {
+  return mode == DPIG_NORM_BATCH ? c : (mode == DPIG_NORM_LAYER ? n : n * c);
+}
+
+}  // namespace dpig
+using namespace dpig;
+
+extern "C" int dpig_norm_stats(dpig_ctx* ctx, const float* x, int32_t n, int32_t h, int32_t w_, int32_t c,
+                               int32_t mode, double* sums, dpig_stream stream) {
+  DPIG_CHECK_CTX(ctx);
+  if (!x || !sums) return set_error(ctx, DPIG_EINVAL, "norm_stats: null argument");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int groups = groups_of(mode, n, c);
+  cudaMemsetAsync(sums, 0, sizeof(double) * 2 * groups, s);
+  const long long ppi = static_cast<long long>(h) * w_;
+  const int chunk = 32;
+  dim3 grid(static_cast<unsigned>((ppi + chunk - 1) / chunk), n);
+  norm_stats_kernel<<<grid, 256, 0, s>>>(x, c, ppi, chunk, mode, groups, sums);
+  ctx->launches++;
+  return check_launch(ctx, "norm_stats");
+}
+
+extern "C" int dpig_norm_act_fwd(dpig_ctx* ctx, const float* x, int32_t n, int32_t h, int32_t w_, int32_t c,
+                                 int32_t mode, float eps, const double* sums, double count, const float* scale,
+                                 const float* offset, int32_t act, float alpha, float* stats,
+                                 const dpig_tensor* out, uint32_t* mask_out, dpig_stream stream) {
+  DPIG_CHECK_CTX(ctx);
+  if (!x || !sums || !scale || !offset || !stats || !out || c % 32)
+    return set_error(ctx, DPIG_EINVAL, "norm_act_fwd: bad argument (c must be a multiple of 32)");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int groups = groups_of(mode, n, c);
+  norm_finalize_kernel<<<(groups + 127) / 128, 128, 0, s>>>(sums, groups, count, eps, stats);
+  const long long ppi = static_cast<long long>(h) * w_;
+  const long long total = static_cast<long long>(n) * ppi * (c / 32);
+  long long grid = (total + 127) / 128;
+  if (grid > 148 * 32) grid = 148 * 32;
+  norm_act_fwd_kernel<<<static_cast<int>(grid), 128, 0, s>>>(
+      x, n, ppi, c, mode, groups, stats, scale, offset, act, alpha, static_cast<__nv_bfloat16*>(out->hi),
+      static_cast<__nv_bfloat16*>(out->lo), out->pix_stride, mask_out);
+  ctx->launches += 2;
+  return check_launch(ctx, "norm_act_fwd");
+}
+
+extern "C" int dpig_norm_act_bwd_reduce(dpig_ctx* ctx, const dpig_tensor* dy, const float* x, const float* stats,
+                                        const uint32_t* mask, float alpha, int32_t mode, const float* scale,
+                                        double* red, float* dscale, float* doffset, dpig_stream stream) {
+  DPIG_CHECK_CTX(ctx);
+  if (!dy || !x || !stats || !scale || !red) return set_error(ctx, DPIG_EINVAL, "norm_act_bwd_reduce: null argument");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int groups = groups_of(mode, dy->n, dy->c);
+  cudaMemsetAsync(red, 0, sizeof(double) * 2 * groups, s);
+  const long long ppi = static_cast<long long>(dy->h) * dy->w;
+  const int chunk = 32;
+  dim3 grid(static_cast<unsigned>((ppi + chunk - 1) / chunk), dy->n);
+  norm_bwd_reduce_kernel<<<grid, 256, 0, s>>>(static_cast<const __nv_bfloat16*>(dy->hi),
+                                              static_cast<const __nv_bfloat16*>(dy->lo), dy->pix_stride, x, dy->c,
+                                              ppi, chunk, mode, groups, stats, mask, alpha, scale, red, dscale,
+                                              doffset);
+  ctx->launches++;
+  return check_launch(ctx, "norm_act_bwd_reduce");
+}
+
+extern "C" int dpig_norm_act_bwd_apply(dpig_ctx* ctx, const dpig_tensor* dy, const float* x, const float* stats,
+                                       const uint32_t* mask, float alpha, int32_t mode, const float* scale,
+                                       const double* red, double count, const dpig_tensor* dx, dpig_stream stream) {
+  DPIG_CHECK_CTX(ctx);
+  if (!dy || !x || !stats || !scale || !red || !dx) return set_error(ctx, DPIG_EINVAL, "norm_act_bwd_apply: null argument");
+  const int groups = groups_of(mode, dy->n, dy->c);
+  const long long ppi = static_cast<long long>(dy->h) * dy->w;
+  const long long total = static_cast<long long>(dy->n) * ppi * dy->c;
+  long long grid = (total + 255) / 256;
+  if (grid > 148 * 32) grid = 148 * 32;
+  norm_bwd_apply_kernel<<<static_cast<int>(grid), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(dy->hi), static_cast<const __nv_bfloat16*>(dy->lo), dy->pix_stride, x,
+      dy->n, ppi, dy->c, mode, groups, stats, mask, alpha, scale, red, count,
+      static_cast<__nv_bfloat16*>(dx->hi), static_cast<__nv_bfloat16*>(dx->lo), dx->pix_stride);
+  ctx->launches++;
+  return check_launch(ctx, "norm_act_bwd_apply");
+}

@@ -1,0 +1,348 @@
+"""ORACLE (test infrastructure only -- never imported by the product path).
+
+CPU restatement of the reference's hot-path graphs built on oracle/tf_ops.py:
+
+  encoder_fgbg      <- models.GeneratorCNN_ID_Encoder_BodyROIVis_FgBgFeaTwoBranch   models.py:390-471
+  unet_generator    <- models.GeneratorCNN_ID_UAEAfterResidual                      models.py:518-576
+  dcgan_discriminator <- WGAN_GP.DCGANDiscriminator                                 wgan_gp.py:407-440
+  fc_discriminator  <- WGAN_GP.FCDiscriminator                                      wgan_gp.py:399-405
+  gaussian_fc_res   <- models.GaussianFCRes                                         models.py:474-486
+  Stage-I model (--model=1) forward, losses and the g_optim / d_optim updates
+                    <- trainer.DPIG_Encoder_GAN_BodyROI_FgBg.build_model / train    trainer.py:567-625, 336-347
+
+Parameters live in a dict keyed by the reference's TensorFlow variable names (slim auto-numbering
+`Conv`, `Conv_1`, ... / `fully_connected`, `fully_connected_1` inside `Encoder/G_encoder` and
+`ID_AE/G`; `Discriminator.N.Filters` etc. from tflib), weights HWIO / [in,out] exactly as TF stores them.
+Parity is unpinned (no TensorFlow here); see oracle/tf_ops.py.
+"""
+import math
+from collections import OrderedDict
+
+import numpy as np
+import torch
+
+from . import tf_ops as T
+
+
+class NetConfig:
+    """Shapes of the Stage-I Market-1501 graph (config.py:23-25, trainer.py:74-75, 576-582)."""
+
+    def __init__(self, img_h=128, img_w=64, hidden=128, z_num=64, roi_size=48, n_parts=7, part_z=32,
+                 keypoints=18, d_dim=64, repeat_num=None):
+        self.img_h, self.img_w, self.hidden, self.z_num = img_h, img_w, hidden, z_num
+        self.roi_size, self.n_parts, self.part_z, self.keypoints, self.d_dim = roi_size, n_parts, part_z, keypoints, d_dim
+        self.repeat_num = repeat_num if repeat_num is not None else int(math.log2(img_h)) - 2  # trainer.py:75
+        self.emb_dim = n_parts * part_z + 4 * part_z  # 7*32 + 128 = 352 (models.py:464-468)
+
+
+# --------------------------------------------------------------------------------- parameters
+def _xavier(rng, shape, fan_in, fan_out):
+    lim = math.sqrt(6.0 / (fan_in + fan_out))
+    return rng.uniform(-lim, lim, size=shape).astype(np.float32)
+
+
+class _Scope:
+    """Reproduces slim's variable auto-naming inside one variable_scope."""
+
+    def __init__(self, prefix, params, rng):
+        self.prefix, self.params, self.rng = prefix, params, rng
+        self.nconv = 0
+        self.nfc = 0
+
+    def conv(self, k, cin, cout):
+        name = "%s/Conv%s" % (self.prefix, "" if self.nconv == 0 else "_%d" % self.nconv)
+        self.nconv += 1
+        self.params[name + "/weights"] = _xavier(self.rng, (k, k, cin, cout), k * k * cin, k * k * cout)
+        self.params[name + "/biases"] = np.zeros(cout, np.float32)
+        return name
+
+    def fc(self, cin, cout):
+        name = "%s/fully_connected%s" % (self.prefix, "" if self.nfc == 0 else "_%d" % self.nfc)
+        self.nfc += 1
+        self.params[name + "/weights"] = _xavier(self.rng, (cin, cout), cin, cout)
+        self.params[name + "/biases"] = np.zeros(cout, np.float32)
+        return name
+
+
+def init_params(cfg, seed=1234, bias_noise=0.0):
+    """Synthetic parameters with the reference's initialisers (slim xavier_uniform + zero bias;
+    D: U(+-0.02*sqrt(3)), tflib/ops/conv2d.py:56-80, wgan_gp.py:411-413; norm scale 1 / offset 0).
+    bias_noise > 0 perturbs biases / norm params so tests exercise them."""
+    rng = np.random.default_rng(seed)
+    p = OrderedDict()
+    hn, rn = cfg.hidden, cfg.repeat_num
+    # ---- Encoder/G_encoder (models.py:390-471), creation order = slim numbering
+    s = _Scope("Encoder/G_encoder", p, rng)
+    s.conv(3, 3, hn)
+    s.conv(3, hn, hn)
+    s.conv(3, hn, hn)
+    for idx in range(rn):
+        c = hn * (idx + 1)
+        s.conv(3, c, c)
+        s.conv(3, c, c)
+        if idx < rn - 1:
+            s.conv(3, c, hn * (idx + 2))
+    roi_final = cfg.roi_size >> (rn - 1)
+    s.fc(roi_final * roi_final * hn * rn, cfg.part_z)
+    for idx in range(rn):
+        c = hn * (idx + 1)
+        s.conv(3, c, c)
+        s.conv(3, c, c)
+        if idx < rn - 1:
+            s.conv(3, c, hn * (idx + 2))
+    fh, fw = cfg.img_h >> (rn - 1), cfg.img_w >> (rn - 1)
+    s.fc(fh * fw * hn * rn, cfg.part_z * 4)
+    # ---- ID_AE/G (models.py:518-576)
+    s = _Scope("ID_AE/G", p, rng)
+    s.conv(3, cfg.emb_dim + cfg.keypoints, hn)
+    for idx in range(rn):
+        c = hn * (idx + 1)
+        s.conv(3, c, c)
+        s.conv(3, c, c)
+        if idx < rn - 1:
+            s.conv(3, c, hn * (idx + 2))
+    s.fc(fh * fw * hn * rn, cfg.z_num)
+    s.fc(cfg.z_num, fh * fw * hn)
+    x_c = hn
+    for idx in range(rn):
+        c = x_c + hn * (rn - idx)
+        s.conv(3, c, c)
+        s.conv(3, c, c)
+        if idx < rn - 1:
+            x_c = hn * (rn - idx - 1)
+            s.conv(1, c, x_c)
+        else:
+            x_c = c
+    s.conv(3, x_c, 3)
+    # ---- Discriminator (wgan_gp.py:407-440)
+    d = cfg.d_dim
+    lim = 0.02 * math.sqrt(3.0)
+    chans = [3, d, 2 * d, 4 * d, 8 * d]
+    for i in range(4):
+        p["Discriminator.%d.Filters" % (i + 1)] = rng.uniform(-lim, lim, size=(5, 5, chans[i], chans[i + 1])).astype(np.float32)
+        p["Discriminator.%d.Biases" % (i + 1)] = np.zeros(chans[i + 1], np.float32)
+        if i >= 1:
+            p["Discriminator.BN%d.offset" % (i + 1)] = np.zeros(chans[i + 1], np.float32)
+            p["Discriminator.BN%d.scale" % (i + 1)] = np.ones(chans[i + 1], np.float32)
+    d_in = (cfg.img_h // 16) * (cfg.img_w // 16) * 8 * d  # == 8*4*8*dim at 128x64 (wgan_gp.py:433-434)
+    p["Discriminator.Output.W"] = rng.uniform(-lim, lim, size=(d_in, 1)).astype(np.float32)
+    p["Discriminator.Output.b"] = np.zeros(1, np.float32)
+    if bias_noise > 0:
+        for k in p:
+            if k.endswith(("biases", "Biases", ".b", ".offset")):
+                p[k] = (p[k] + rng.normal(0, bias_noise, size=p[k].shape)).astype(np.float32)
+            if k.endswith(".scale"):
+                p[k] = (p[k] + rng.normal(0, bias_noise, size=p[k].shape)).astype(np.float32)
+    return p
+
+
+def to_torch(params, dtype=torch.float64, requires_grad=False):
+    return OrderedDict((k, torch.tensor(v, dtype=dtype).requires_grad_(requires_grad)) for k, v in params.items())
+
+
+def is_generator_param(name):
+    return name.startswith("Encoder/") or name.startswith("ID_AE/")
+
+
+def is_disc_param(name):
+    return name.startswith("Discriminator.")
+
+
+# --------------------------------------------------------------------------------- graphs
+class _Walker:
+    """Hands out the slim layer names in creation order while a graph function runs."""
+
+    def __init__(self, prefix, p):
+        self.prefix, self.p, self.nconv, self.nfc = prefix, p, 0, 0
+
+    def conv(self, x, stride=1, act=True):
+        name = "%s/Conv%s" % (self.prefix, "" if self.nconv == 0 else "_%d" % self.nconv)
+        self.nconv += 1
+        y = T.conv2d_same(x, self.p[name + "/weights"], self.p[name + "/biases"], stride)
+        return torch.relu(y) if act else y  # trainers pass activation_fn=tf.nn.relu (trainer.py:581, 595)
+
+    def fc(self, x):
+        name = "%s/fully_connected%s" % (self.prefix, "" if self.nfc == 0 else "_%d" % self.nfc)
+        self.nfc += 1
+        return x @ self.p[name + "/weights"] + self.p[name + "/biases"]
+
+
+def _pyramid(w, x, hn, rn):
+    for idx in range(rn):
+        res = x
+        x = w.conv(x)
+        x = w.conv(x)
+        x = x + res
+        if idx < rn - 1:
+            x = w.conv(x, stride=2)
+    return x
+
+
+def encoder_fgbg(p, cfg, x, fg_mask, roi_bbox, roi_vis):
+    """models.py:390-471.  x [B,H,W,3]; fg_mask [B,H,W,1]; roi_bbox int [B,7,4] (y1,x1,y2,x2 pixels);
+    roi_vis [B,7].  Returns the [B,352] embedding."""
+    w = _Walker("Encoder/G_encoder", p)
+    B, H, W, _ = x.shape
+    x = w.conv(x)
+    res = x
+    x = w.conv(x)
+    x = w.conv(x)
+    x = x + res
+    x_fg = x * fg_mask
+    x_bg = x * (1.0 - fg_mask)
+    rois = []
+    for i in range(cfg.n_parts):
+        bb = roi_bbox[:, i, :].to(x.dtype)
+        boxes = torch.stack([bb[:, 0] / float(H), bb[:, 1] / float(W), bb[:, 2] / float(H), bb[:, 3] / float(W)], dim=1)
+        rois.append(T.crop_and_resize(x_fg, boxes, torch.arange(B), (cfg.roi_size, cfg.roi_size)))
+    body = torch.cat(rois, dim=0)
+    body = _pyramid(w, body, cfg.hidden, cfg.repeat_num)
+    body = w.fc(body.reshape(body.shape[0], -1))
+    feats = list(torch.split(body, B, dim=0))
+    for i in range(cfg.n_parts):
+        feats[i] = feats[i] * roi_vis[:, i:i + 1].to(x.dtype)
+    bg = _pyramid(w, x_bg, cfg.hidden, cfg.repeat_num)
+    bg = w.fc(bg.reshape(B, -1))
+    feats.append(bg)
+    return torch.cat(feats, dim=-1)
+
+
+def unet_generator(p, cfg, emb, pose):
+    """trainer.py:588-590 (spatial broadcast of the embedding) + models.py:518-576.
+    emb [B,352]; pose [B,H,W,18].  Returns (G [B,H,W,3], z [B,z_num])."""
+    w = _Walker("ID_AE/G", p)
+    B = emb.shape[0]
+    H, W = pose.shape[1], pose.shape[2]
+    hn, rn = cfg.hidden, cfg.repeat_num
+    emb_rep = emb[:, None, None, :].expand(B, H, W, emb.shape[1])
+    x = torch.cat([emb_rep, pose], dim=3)
+    x = w.conv(x)
+    skips = []
+    for idx in range(rn):
+        res = x
+        x = w.conv(x)
+        x = w.conv(x)
+        x = x + res
+        skips.append(x)
+        if idx < rn - 1:
+            x = w.conv(x, stride=2)
+    sh = x.shape
+    z = x = w.fc(x.reshape(B, -1))
+    x = w.fc(z).reshape(B, sh[1], sh[2], hn)
+    for idx in range(rn):
+        x = torch.cat([x, skips[rn - 1 - idx]], dim=-1)
+        res = x
+        x = w.conv(x)
+        x = w.conv(x)
+        x = x + res
+        if idx < rn - 1:
+            x = T.upscale2(x)
+            x = w.conv(x)  # 1x1 (the walker reads the kernel size off the weights)
+    out = w.conv(x, act=False)
+    return out, z
+
+
+def dcgan_discriminator(p, cfg, x_nhwc, mode="dcgan"):
+    """wgan_gp.py:407-440 on an NHWC image (the reference transposes to NCHW first, trainer.py:601-602;
+    the only place the layout matters is the flatten before the Linear, done C-major below)."""
+    norm = T.layernorm if mode == "wgan-gp" else T.batchnorm_train  # wgan_gp.py:34-40
+    h = T.conv2d_same(x_nhwc, p["Discriminator.1.Filters"], p["Discriminator.1.Biases"], 2)
+    h = T.leaky_relu(h)
+    for i in (2, 3, 4):
+        h = T.conv2d_same(h, p["Discriminator.%d.Filters" % i], p["Discriminator.%d.Biases" % i], 2)
+        h = norm(h, p["Discriminator.BN%d.scale" % i], p["Discriminator.BN%d.offset" % i])
+        h = T.leaky_relu(h)
+    flat = h.permute(0, 3, 1, 2).reshape(h.shape[0], -1)  # NCHW flatten: index = c*(h*w) + y*w + x
+    out = flat @ p["Discriminator.Output.W"] + p["Discriminator.Output.b"]
+    return out.reshape(-1)
+
+
+def fc_discriminator(p, x, n_layers=3, name=""):
+    """wgan_gp.py:399-405."""
+    h = T.leaky_relu(x @ p[name + "Discriminator.Input.Linear.W"] + p[name + "Discriminator.Input.Linear.b"])
+    for i in range(n_layers):
+        h = T.leaky_relu(h @ p[name + "Discriminator.%d.Linear.W" % i] + p[name + "Discriminator.%d.Linear.b" % i])
+    return (h @ p[name + "Discriminator.Out.W"] + p[name + "Discriminator.Out.b"]).reshape(-1)
+
+
+def gaussian_fc_res(p, z, repeat_num=4, prefix="G_FC", act=torch.relu):
+    """models.py:474-486 with the noise z supplied by the caller."""
+    w = _Walker(prefix, p)
+    z = act(w.fc(z))
+    for _ in range(repeat_num):
+        res = z
+        z = act(w.fc(z))
+        z = act(w.fc(z))
+        z = res + z
+    return w.fc(z)
+
+
+# --------------------------------------------------------------------------------- Stage-I model
+def stage1_forward(p, cfg, batch, mode="dcgan", gp_alpha=None, lam=10.0):
+    """build_model of --model=1 (trainer.py:568-625).  batch: dict x, pose, mask, part_bbox, part_vis.
+    Returns dict with emb, z, G, D_real, D_fake, g_loss (incl. 20*L1), d_loss, L1."""
+    x = batch["x"]
+    emb = encoder_fgbg(p, cfg, x, batch["mask"], batch["part_bbox"], batch["part_vis"])
+    G, z = unet_generator(p, cfg, emb, batch["pose"])
+    d_real = dcgan_discriminator(p, cfg, x, mode)
+    d_fake = dcgan_discriminator(p, cfg, G, mode)
+    g_gan, d_loss = T.gan_loss(mode, d_real, d_fake)
+    out = dict(emb=emb, z=z, G=G, D_real=d_real, D_fake=d_fake)
+    if mode == "wgan-gp":
+        gp, slopes, _ = T.gradient_penalty(lambda t: dcgan_discriminator(p, cfg, t, mode), x, G, gp_alpha)
+        d_loss = d_loss + lam * gp
+        out.update(gp=gp, slopes=slopes)
+    l1 = (G - x).abs().mean()
+    out.update(L1=l1, g_loss_only=g_gan, g_loss=g_gan + 20.0 * l1, d_loss=d_loss)
+    return out
+
+
+def stage1_grads(p, cfg, batch, which, mode="dcgan", gp_alpha=None):
+    """Gradients of g_loss w.r.t. Encoder+G params (which='g') or of d_loss w.r.t. D params (which='d');
+    what Optimizer.minimize(var_list=...) differentiates (trainer.py:622-625)."""
+    out = stage1_forward(p, cfg, batch, mode, gp_alpha)
+    if which == "g":
+        names = [k for k in p if is_generator_param(k)]
+        loss = out["g_loss"]
+    else:
+        names = [k for k in p if is_disc_param(k)]
+        loss = out["d_loss"]
+    grads = torch.autograd.grad(loss, [p[k] for k in names], allow_unused=True)
+    return out, OrderedDict((k, g) for k, g in zip(names, grads))
+
+
+class Stage1Trainer:
+    """The optimiser half of the step (trainer.py:116-149, 336-347): Adam(b1=.5) in dcgan mode,
+    Adam(b1=.5,b2=.9) in wgan-gp, RMSProp + clip in wgan."""
+
+    def __init__(self, params, cfg, mode="dcgan", g_lr=2e-5, d_lr=2e-5, dtype=torch.float32):
+        self.cfg, self.mode, self.g_lr, self.d_lr = cfg, mode, g_lr, d_lr
+        self.p = to_torch(params, dtype, requires_grad=True)
+        self.m = {k: torch.zeros_like(v) for k, v in self.p.items()}
+        init_v = torch.ones_like if mode in ("wgan", "lsgan") else torch.zeros_like
+        self.v = {k: init_v(v) for k, v in self.p.items()}
+        self.t = {"g": 0, "d": 0}
+
+    def _apply(self, grads, which):
+        self.t[which] += 1
+        lr = self.g_lr if which == "g" else self.d_lr
+        with torch.no_grad():
+            for k, g in grads.items():
+                if g is None:
+                    continue
+                if self.mode in ("wgan", "lsgan"):
+                    clip = 0.01 if (self.mode == "wgan" and which == "d") else None
+                    T.rmsprop_step(self.p[k], g, self.v[k], lr, clip=clip)
+                else:
+                    b2 = 0.9 if self.mode == "wgan-gp" else 0.999
+                    T.adam_step(self.p[k], g, self.m[k], self.v[k], lr, self.t[which], 0.5, b2)
+
+    def g_step(self, batch, gp_alpha=None):
+        out, grads = stage1_grads(self.p, self.cfg, batch, "g", self.mode, gp_alpha)
+        self._apply(grads, "g")
+        return out, grads
+
+    def d_step(self, batch, gp_alpha=None):
+        out, grads = stage1_grads(self.p, self.cfg, batch, "d", self.mode, gp_alpha)
+        self._apply(grads, "d")
+        return out, grads

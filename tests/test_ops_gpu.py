@@ -1,0 +1,495 @@
+"""GPU parity tests, op level: every kernel reached through the C ABI (ctypes) against the CPU oracle
+(oracle/tf_ops.py in float64) on the same seeded inputs.  Tolerances are written next to each check;
+the north-star bound is 1e-3 max-abs on O(1) activations, the kernels are held to much tighter ones.
+
+Run as a script (`python tests/test_ops_gpu.py [filter]`) for a verbose bring-up report.
+"""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+from oracle import tf_ops as T  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+
+_CTX = None
+
+
+def ctx():
+    global _CTX
+    if _CTX is None:
+        import dpig_b200
+        _CTX = dpig_b200.Context(0)
+    return _CTX
+
+
+def _imports():
+    from dpig_b200 import _lib
+    from dpig_b200.tensor import SplitTensor, ptr, split_ref
+    return _lib, SplitTensor, ptr, split_ref
+
+
+def stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def rel_err(a, b):
+    a = a.double().cpu()
+    b = b.double().cpu()
+    return float((a - b).abs().max() / (b.abs().max() + 1e-30))
+
+
+def pack_weights(w_hwio, cin_pad=None, cout_pad=None):
+    """fp32 HWIO (torch cuda) -> packed operand copies via dpig_weight_pack."""
+    _lib, SplitTensor, ptr, _ = _imports()
+    kh, kw, cin, cout = w_hwio.shape
+    cin_pad = cin_pad or (cin + 7) // 8 * 8
+    cout_pad = cout_pad or (cout + 7) // 8 * 8
+    taps = kh * kw
+    f = torch.zeros((2, taps, cout, cin_pad), dtype=torch.bfloat16, device="cuda")
+    b = torch.zeros((2, taps, cin, cout_pad), dtype=torch.bfloat16, device="cuda")
+    ctx().weight_pack(ptr(w_hwio), taps, cin, cout, cin_pad, cout_pad, ptr(f[0]), ptr(f[1]), ptr(b[0]), ptr(b[1]),
+                      stream())
+    return f, b
+
+
+def padded_split(x, cpad=None):
+    """Split tensor whose channel count is zero-padded up to cpad (default: next multiple of 8)."""
+    _lib, SplitTensor, ptr, split_ref = _imports()
+    c = x.shape[-1]
+    cpad = cpad or (c + 7) // 8 * 8
+    if cpad != c:
+        x = torch.cat([x, torch.zeros(x.shape[:-1] + (cpad - c,))], dim=-1)
+    return SplitTensor.from_float(x.cuda())
+
+
+def run_conv_fwd(n, h, w, cin, cout, k, stride, act="relu", residual=False, upsample=1, f32_out=False, seed=0,
+                 c_alloc_in=None):
+    _lib, SplitTensor, ptr, split_ref = _imports()
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn((n, h, w, cin), generator=g)
+    wt = torch.randn((k, k, cin, cout), generator=g) / np.sqrt(k * k * cin)
+    bias = torch.randn((cout,), generator=g) * 0.1
+    oh, ow = -(-h // stride), -(-w // stride)
+    res = torch.randn((n, oh, ow, cout), generator=g) if residual else None
+
+    xs = padded_split(x, c_alloc_in)
+    wd = wt.cuda().contiguous()
+    f, _ = pack_weights(wd, cin_pad=xs.c)
+    bd = bias.cuda()
+    out = SplitTensor(n, oh * upsample, ow * upsample, cout, zero=True)
+    out32 = torch.zeros((n, oh * upsample, ow * upsample, cout), device="cuda") if f32_out else None
+    words = (cout + 31) // 32
+    mask = torch.zeros((n * oh * ow, words), dtype=torch.int32, device="cuda")
+    import ctypes as C
+    ep = _lib.ConvEpilogue()
+    ep.bias = bd.data_ptr()
+    ep.act = {"none": 0, "relu": 1, "lrelu": 2}[act]
+    ep.alpha = 0.2
+    rs = None
+    if residual:
+        rs = SplitTensor.from_float(res.cuda())
+        ep.addend = C.pointer(rs.struct())
+    ep.mask_out = mask.data_ptr()
+    ep.out = C.pointer(out.struct())
+    if f32_out:
+        ep.out_f32 = out32.data_ptr()
+        ep.out_f32_pix_stride = cout
+    ep.upsample = upsample
+    ctx().conv2d_fwd(xs.ref(), ptr(f[0]), ptr(f[1]), k, k, stride, cout, C.byref(ep), stream())
+    torch.cuda.synchronize()
+
+    # oracle on the values the kernel actually saw (split-rounded inputs), float64
+    xr = split_ref(x).double()
+    wr = split_ref(wt).double()
+    pre = T.conv2d_same(xr, wr, bias.double(), stride)
+    y = pre
+    if act == "relu":
+        y = torch.relu(pre)
+    elif act == "lrelu":
+        y = T.leaky_relu(pre, 0.2)
+    if residual:
+        y = y + split_ref(res).double()
+    if upsample == 2:
+        y = T.upscale2(y)
+    got = out.float().cpu()
+    err = rel_err(got, y)
+    info = {"err": err}
+    if f32_out:
+        info["err_f32"] = rel_err(out32.cpu(), y)
+    # mask bits: compare where |pre| is not tiny
+    bits = mask.cpu().numpy().astype(np.uint32).reshape(n, oh, ow, words)
+    exp = (pre > 0).numpy()
+    got_bits = np.zeros_like(exp)
+    for c in range(cout):
+        got_bits[..., c] = (bits[..., c // 32] >> (c % 32)) & 1
+    sure = (pre.abs() > 1e-4).numpy()
+    info["mask_mismatch"] = int(((got_bits != exp) & sure).sum())
+    return info
+
+
+CONV_FWD_CASES = [
+    # n, h, w, cin, cout, k, stride, act, residual, upsample, f32
+    dict(n=2, h=16, w=8, cin=128, cout=128, k=3, stride=1, act="relu", residual=True),
+    dict(n=2, h=16, w=8, cin=64, cout=128, k=3, stride=1, act="none"),
+    dict(n=3, h=12, w=12, cin=128, cout=256, k=3, stride=2, act="relu"),
+    dict(n=2, h=16, w=8, cin=256, cout=384, k=3, stride=1, act="relu", residual=True),
+    dict(n=2, h=32, w=16, cin=64, cout=128, k=5, stride=2, act="none", f32_out=True),
+    dict(n=2, h=8, w=4, cin=192, cout=64, k=1, stride=1, act="relu", upsample=2),
+    dict(n=5, h=3, w=3, cin=640, cout=640, k=3, stride=1, act="relu", residual=True),
+    dict(n=1, h=128, w=64, cin=128, cout=128, k=3, stride=1, act="relu"),
+    dict(n=2, h=16, w=8, cin=256, cout=3, k=3, stride=1, act="none", f32_out=True),
+    dict(n=2, h=16, w=8, cin=370, cout=128, k=3, stride=1, act="relu", c_alloc_in=384),
+]
+
+
+@pytest.mark.parametrize("case", CONV_FWD_CASES)
+def test_conv2d_fwd(case):
+    info = run_conv_fwd(**case)
+    assert info["err"] < 2e-5, info  # 3-pass split-bf16 vs float64 on identical (split-rounded) inputs
+    assert info["mask_mismatch"] == 0, info
+    if "err_f32" in info:
+        assert info["err_f32"] < 2e-5, info
+
+
+def run_conv_bwd_data(n, h, w, cin, cout, k, stride, addend=False, masked=False, seed=1):
+    _lib, SplitTensor, ptr, split_ref = _imports()
+    import ctypes as C
+    g = torch.Generator().manual_seed(seed)
+    oh, ow = -(-h // stride), -(-w // stride)
+    dy = torch.randn((n, oh, ow, cout), generator=g)
+    wt = torch.randn((k, k, cin, cout), generator=g) / np.sqrt(k * k * cout)
+    add = torch.randn((n, h, w, cin), generator=g) if addend else None
+    mbits = torch.randint(0, 2, (n, h, w, cin), generator=g) if masked else None
+
+    dys = padded_split(dy)
+    _, b = pack_weights(wt.cuda().contiguous(), cout_pad=dys.c)
+    out = SplitTensor(n, h, w, cin, zero=True)
+    out2 = SplitTensor(n, h, w, cin, zero=True) if masked else None
+    ep = _lib.ConvEpilogue()
+    ep.act = 0
+    ep.out = C.pointer(out.struct())
+    if addend:
+        adds = SplitTensor.from_float(add.cuda())
+        ep.addend = C.pointer(adds.struct())
+    if masked:
+        words = (cin + 31) // 32
+        mw = np.zeros((n, h, w, words), np.uint32)
+        mb = mbits.numpy().astype(np.uint32)
+        for c in range(cin):
+            mw[..., c // 32] |= mb[..., c] << np.uint32(c % 32)
+        mask_dev = torch.from_numpy(mw.view(np.int32)).cuda()
+        ep.mask_in = mask_dev.data_ptr()
+        ep.mask_neg = 0.2
+        ep.out_masked = C.pointer(out2.struct())
+    ep.upsample = 1
+    ctx().conv2d_bwd_data(dys.ref(), ptr(b[0]), ptr(b[1]), k, k, stride, h, w, cin, C.byref(ep), stream())
+    torch.cuda.synchronize()
+
+    x = torch.zeros((n, h, w, cin), dtype=torch.float64, requires_grad=True)
+    y = T.conv2d_same(x, split_ref(wt).double(), None, stride)
+    gx, = torch.autograd.grad(y, x, split_ref(dy).double())
+    if addend:
+        gx = gx + split_ref(add).double()
+    info = {"err": rel_err(out.float(), gx)}
+    if masked:
+        gm = gx * torch.where(mbits.bool(), 1.0, 0.2)
+        info["err_masked"] = rel_err(out2.float(), gm)
+    return info
+
+
+CONV_BWD_DATA_CASES = [
+    dict(n=2, h=16, w=8, cin=128, cout=128, k=3, stride=1, addend=True, masked=True),
+    dict(n=2, h=16, w=8, cin=128, cout=256, k=3, stride=2, addend=True, masked=True),
+    dict(n=2, h=32, w=16, cin=64, cout=128, k=5, stride=2),
+    dict(n=2, h=8, w=4, cin=192, cout=64, k=1, stride=1),
+    dict(n=3, h=12, w=12, cin=256, cout=384, k=3, stride=2, masked=True),
+    dict(n=2, h=16, w=8, cin=256, cout=3, k=3, stride=1),
+]
+
+
+@pytest.mark.parametrize("case", CONV_BWD_DATA_CASES)
+def test_conv2d_bwd_data(case):
+    info = run_conv_bwd_data(**case)
+    assert info["err"] < 2e-5, info
+    if "err_masked" in info:
+        assert info["err_masked"] < 2e-5, info
+
+
+def run_conv_bwd_filter(n, h, w, cin, cout, k, stride, seed=2):
+    _lib, SplitTensor, ptr, split_ref = _imports()
+    g = torch.Generator().manual_seed(seed)
+    oh, ow = -(-h // stride), -(-w // stride)
+    x = torch.randn((n, h, w, cin), generator=g)
+    dy = torch.randn((n, oh, ow, cout), generator=g)
+    xs = padded_split(x)
+    dys = padded_split(dy)
+    dw = torch.zeros((k, k, cin, cout), device="cuda")
+    ctx().conv2d_bwd_filter(xs.ref(), dys.ref(), k, k, stride, cin, cout, ptr(dw), stream())
+    torch.cuda.synchronize()
+    wv = torch.zeros((k, k, cin, cout), dtype=torch.float64, requires_grad=True)
+    y = T.conv2d_same(split_ref(x).double(), wv, None, stride)
+    gw, = torch.autograd.grad(y, wv, split_ref(dy).double())
+    return {"err": rel_err(dw, gw)}
+
+
+CONV_BWD_FILTER_CASES = [
+    dict(n=2, h=16, w=8, cin=128, cout=128, k=3, stride=1),
+    dict(n=3, h=12, w=12, cin=128, cout=256, k=3, stride=2),
+    dict(n=2, h=32, w=16, cin=64, cout=128, k=5, stride=2),
+    dict(n=2, h=8, w=4, cin=192, cout=64, k=1, stride=1),
+    dict(n=5, h=3, w=3, cin=640, cout=640, k=3, stride=1),
+    dict(n=2, h=16, w=8, cin=256, cout=3, k=3, stride=1),
+    dict(n=2, h=16, w=8, cin=370, cout=128, k=3, stride=1),
+    dict(n=1, h=128, w=64, cin=128, cout=128, k=3, stride=1),
+]
+
+
+@pytest.mark.parametrize("case", CONV_BWD_FILTER_CASES)
+def test_conv2d_bwd_filter(case):
+    info = run_conv_bwd_filter(**case)
+    assert info["err"] < 2e-5, info
+
+
+def test_conv_small():
+    """CUDA-core 3-channel convs (encoder stem, D layer 1) forward and gradients."""
+    _lib, SplitTensor, ptr, split_ref = _imports()
+    g = torch.Generator().manual_seed(3)
+    for (k, stride, cout, act) in [(3, 1, 128, 1), (5, 2, 64, 2)]:
+        n, h, w, cin = 2, 32, 16, 3
+        x = torch.randn((n, h, w, cin), generator=g)
+        wt = torch.randn((k, k, cin, cout), generator=g) * 0.2
+        bias = torch.randn((cout,), generator=g) * 0.1
+        oh, ow = -(-h // stride), -(-w // stride)
+        out = SplitTensor(n, oh, ow, cout, zero=True)
+        o32 = torch.zeros((n, oh, ow, cout), device="cuda")
+        mask = torch.zeros((n * oh * ow, cout // 32), dtype=torch.int32, device="cuda")
+        xd, wd, bd = x.cuda(), wt.cuda(), bias.cuda()
+        ctx().conv2d_small_fwd(ptr(xd), n, h, w, cin, ptr(wd), ptr(bd), k, k, stride, cout, act, 0.2, out.ref(),
+                               ptr(o32), ptr(mask), stream())
+        pre = T.conv2d_same(x.double(), wt.double(), bias.double(), stride)
+        y = torch.relu(pre) if act == 1 else T.leaky_relu(pre, 0.2)
+        assert rel_err(o32, y) < 1e-5
+        assert rel_err(out.float(), y) < 2e-5
+        dy = torch.randn((n, oh, ow, cout), generator=g)
+        dyd = dy.cuda()
+        dx = torch.zeros((n, h, w, cin), device="cuda")
+        dw = torch.zeros((k, k, cin, cout), device="cuda")
+        ctx().conv2d_small_bwd_data(ptr(dyd), n, oh, ow, cout, ptr(wd), k, k, stride, h, w, cin, ptr(dx), stream())
+        ctx().conv2d_small_bwd_filter(ptr(xd), n, h, w, cin, ptr(dyd), k, k, stride, cout, ptr(dw), stream())
+        xv = x.double().requires_grad_(True)
+        wv = wt.double().requires_grad_(True)
+        yy = T.conv2d_same(xv, wv, None, stride)
+        gx, gw = torch.autograd.grad(yy, [xv, wv], dy.double())
+        assert rel_err(dx, gx) < 1e-5
+        assert rel_err(dw, gw) < 1e-5
+
+
+def test_crop_and_resize():
+    _lib, SplitTensor, ptr, split_ref = _imports()
+    g = torch.Generator().manual_seed(4)
+    n, h, w, c, cs = 3, 32, 16, 64, 12
+    img = torch.randn((n, h, w, c), generator=g)
+    m = (torch.rand((n, h, w), generator=g) > 0.4).float()
+    px = torch.tensor([[2, 1, 20, 12], [0, 0, 1, 1], [5, 3, 31, 15], [0, 0, 31, 15], [10, 2, 12, 9], [3, 3, 30, 6]],
+                      dtype=torch.float32)
+    boxes = torch.stack([px[:, 0] / h, px[:, 1] / w, px[:, 2] / h, px[:, 3] / w], dim=1)
+    ind = torch.tensor([0, 1, 2, 0, 1, 2], dtype=torch.int32)
+    nb = boxes.shape[0]
+    ims = SplitTensor.from_float(img.cuda())
+    out = SplitTensor(nb, cs, cs, c, zero=True)
+    md, bd, idd = m.cuda(), boxes.cuda(), ind.cuda()
+    ctx().crop_and_resize_fwd(ims.ref(), ptr(md), ptr(bd), ptr(idd), nb, out.ref(), stream())
+    iv = (split_ref(img).double() * m[..., None].double()).requires_grad_(True)
+    ref = T.crop_and_resize(iv, boxes.double(), ind, (cs, cs))
+    assert rel_err(out.float(), ref) < 2e-5
+    # gradient w.r.t. the un-masked image
+    gy = torch.randn((nb, cs, cs, c), generator=g)
+    gys = SplitTensor.from_float(gy.cuda())
+    gimg = torch.zeros((n, h, w, c), device="cuda")
+    ctx().crop_and_resize_bwd(gys.ref(), ptr(md), ptr(bd), ptr(idd), nb, ptr(gimg), n, h, w, c, stream())
+    gi, = torch.autograd.grad(ref, iv, split_ref(gy).double())
+    gi = gi * m[..., None].double()
+    assert rel_err(gimg, gi) < 2e-5
+
+
+def test_linear():
+    _lib, SplitTensor, ptr, _ = _imports()
+    g = torch.Generator().manual_seed(5)
+    for (m, k, n, act) in [(14, 5760, 32, 0), (4, 20480, 128, 0), (4, 64, 4096, 0), (8, 512, 512, 1)]:
+        x = torch.randn((m, k), generator=g)
+        w = torch.randn((k, n), generator=g) / np.sqrt(k)
+        b = torch.randn((n,), generator=g)
+        xd, wd, bd = x.cuda(), w.cuda(), b.cuda()
+        y = torch.zeros((m, n), device="cuda")
+        ctx().linear_fwd(ptr(xd), ptr(wd), ptr(bd), ptr(y), m, k, n, act, 0.2, stream())
+        ref = x.double() @ w.double() + b.double()
+        if act == 1:
+            ref = torch.relu(ref)
+        assert rel_err(y, ref) < 1e-5
+        dy = torch.randn((m, n), generator=g)
+        dyd = dy.cuda()
+        dx = torch.zeros((m, k), device="cuda")
+        dw = torch.zeros((k, n), device="cuda")
+        db = torch.zeros((n,), device="cuda")
+        ctx().linear_bwd(ptr(xd), ptr(wd), ptr(dyd), ptr(dx), ptr(dw), ptr(db), m, k, n, stream())
+        assert rel_err(dx, dy.double() @ w.double().T) < 1e-5
+        assert rel_err(dw, x.double().T @ dy.double()) < 1e-5
+        assert rel_err(db, dy.double().sum(0)) < 1e-5
+
+
+@pytest.mark.parametrize("mode", ["batch", "layer"])
+def test_norm_act(mode):
+    _lib, SplitTensor, ptr, split_ref = _imports()
+    g = torch.Generator().manual_seed(6)
+    n, h, w, c = 4, 8, 4, 128
+    x = torch.randn((n, h, w, c), generator=g) * 1.5 + 0.3
+    scale = 1 + 0.1 * torch.randn((c,), generator=g)
+    offset = 0.1 * torch.randn((c,), generator=g)
+    md = {"layer": 0, "batch": 1}[mode]
+    groups = n if mode == "layer" else c
+    count = float(h * w * c) if mode == "layer" else float(n * h * w)
+    xd, sd, od = x.cuda(), scale.cuda(), offset.cuda()
+    sums = torch.zeros((2, groups), dtype=torch.float64, device="cuda")
+    stats = torch.zeros((2, groups), device="cuda")
+    out = SplitTensor(n, h, w, c, zero=True)
+    mask = torch.zeros((n * h * w, c // 32), dtype=torch.int32, device="cuda")
+    ctx().norm_stats(ptr(xd), n, h, w, c, md, ptr(sums), stream())
+    ctx().norm_act_fwd(ptr(xd), n, h, w, c, md, 1e-5, ptr(sums), count, ptr(sd), ptr(od), 2, 0.2, ptr(stats),
+                       out.ref(), ptr(mask), stream())
+    xv = x.double().requires_grad_(True)
+    sv = scale.double().requires_grad_(True)
+    ov = offset.double().requires_grad_(True)
+    fn = T.layernorm if mode == "layer" else T.batchnorm_train
+    y = T.leaky_relu(fn(xv, sv, ov), 0.2)
+    assert rel_err(out.float(), y) < 2e-5
+    dy = torch.randn((n, h, w, c), generator=g)
+    dys = SplitTensor.from_float(dy.cuda())
+    red = torch.zeros((2, groups), dtype=torch.float64, device="cuda")
+    dsc = torch.zeros((c,), device="cuda")
+    dof = torch.zeros((c,), device="cuda")
+    dx = SplitTensor(n, h, w, c, zero=True)
+    ctx().norm_act_bwd_reduce(dys.ref(), ptr(xd), ptr(stats), ptr(mask), 0.2, md, ptr(sd), ptr(red), ptr(dsc),
+                              ptr(dof), stream())
+    ctx().norm_act_bwd_apply(dys.ref(), ptr(xd), ptr(stats), ptr(mask), 0.2, md, ptr(sd), ptr(red), count,
+                             dx.ref(), stream())
+    gx, gs, go = torch.autograd.grad(y, [xv, sv, ov], split_ref(dy).double())
+    assert rel_err(dx.float(), gx) < 5e-5
+    assert rel_err(dsc, gs) < 1e-5
+    assert rel_err(dof, go) < 1e-5
+
+
+def test_elementwise_and_losses():
+    _lib, SplitTensor, ptr, split_ref = _imports()
+    g = torch.Generator().manual_seed(7)
+    n, h, w, c = 2, 8, 4, 64
+    a = torch.randn((n, 2 * h, 2 * w, c), generator=g)
+    b = torch.randn((n, 2 * h, 2 * w, c), generator=g)
+    as_, bs = SplitTensor.from_float(a.cuda()), SplitTensor.from_float(b.cuda())
+    mbits = torch.randint(0, 2, (n, h, w, c), generator=g)
+    mw = np.zeros((n, h, w, c // 32), np.uint32)
+    for ch in range(c):
+        mw[..., ch // 32] |= mbits.numpy().astype(np.uint32)[..., ch] << np.uint32(ch % 32)
+    md = torch.from_numpy(mw.view(np.int32)).cuda()
+    out = SplitTensor(n, h, w, c, zero=True)
+    ctx().ew_combine(out.ref(), as_.ref(), bs.ref(), None, None, 0, ptr(md), 0.0, 1, stream())
+    s = split_ref(a).double() + split_ref(b).double()
+    pooled = s.reshape(n, h, 2, w, 2, c).sum(dim=(2, 4)) * mbits.double()
+    assert rel_err(out.float(), pooled) < 2e-5
+    # L1 + GAN losses
+    G = torch.randn((n, h, w, 3), generator=g)
+    X = torch.randn((n, h, w, 3), generator=g)
+    Gd, Xd = G.cuda(), X.cuda()
+    o = torch.zeros((2,), device="cuda")
+    dG = torch.zeros_like(Gd)
+    ctx().loss_l1(ptr(Gd), ptr(Xd), G.numel(), 20.0, ptr(o), ptr(dG), stream())
+    Gv = G.double().requires_grad_(True)
+    l1 = (Gv - X.double()).abs().mean()
+    gl, = torch.autograd.grad(20.0 * l1, Gv)
+    assert abs(float(o[0]) - float(l1)) < 1e-6
+    assert rel_err(dG, gl) < 1e-5
+    for mode, mid in [("dcgan", 0), ("wgan", 1), ("lsgan", 3)]:
+        dr = torch.randn((6,), generator=g)
+        df = torch.randn((6,), generator=g)
+        drd, dfd = dr.cuda(), df.cuda()
+        o = torch.zeros((2,), device="cuda")
+        g1, g2, g3 = (torch.zeros((6,), device="cuda") for _ in range(3))
+        ctx().loss_gan(mid, ptr(drd), ptr(dfd), 6, ptr(o), ptr(g1), ptr(g2), ptr(g3), stream())
+        rv = dr.double().requires_grad_(True)
+        fv = df.double().requires_grad_(True)
+        gl_, dl_ = T.gan_loss(mode, rv, fv)
+        assert abs(float(o[0]) - float(gl_)) < 1e-5 and abs(float(o[1]) - float(dl_)) < 1e-5
+        e1, = torch.autograd.grad(gl_, fv, retain_graph=True)
+        e2, e3 = torch.autograd.grad(dl_, [rv, fv])
+        assert rel_err(g1, e1) < 1e-5 and rel_err(g2, e2) < 1e-5 and rel_err(g3, e3) < 1e-5
+
+
+def test_adam_and_pose():
+    _lib, SplitTensor, ptr, _ = _imports()
+    g = torch.Generator().manual_seed(8)
+    p = torch.randn((1000,), generator=g)
+    pd = p.cuda()
+    m = torch.zeros_like(pd)
+    v = torch.zeros_like(pd)
+    pr, mr, vr = p.double().clone(), torch.zeros(1000, dtype=torch.float64), torch.zeros(1000, dtype=torch.float64)
+    for t in (1, 2, 3):
+        gr = torch.randn((1000,), generator=g)
+        gd = gr.cuda()
+        ctx().adam_step(ptr(pd), ptr(gd), ptr(m), ptr(v), 1000, 2e-5, 0.5, 0.999, 1e-8, t, 1.0, stream())
+        T.adam_step(pr, gr.double(), mr, vr, 2e-5, t)
+    assert float((pd.cpu().double() - pr).abs().max()) < 1e-7
+    from dpig_b200 import synth
+    batch = synth.make_batch(3, 128, 64, seed=5)
+    rcv = torch.from_numpy(batch["pose_rcv"])
+    rd = rcv.cuda()
+    o32 = torch.zeros((3, 128, 64, 18), device="cuda")
+    ctx().pose_rasterize(ptr(rd), 3, 18, 128, 64, 4, None, ptr(o32), stream())
+    assert torch.equal(o32.cpu(), T.pose_rasterize(rcv, 128, 64, 4))
+
+
+if __name__ == "__main__":
+    flt = sys.argv[1] if len(sys.argv) > 1 else ""
+    torch.cuda.init()
+    print("device:", torch.cuda.get_device_name(0), flush=True)
+    groups = [("conv2d_fwd", run_conv_fwd, CONV_FWD_CASES), ("conv2d_bwd_data", run_conv_bwd_data, CONV_BWD_DATA_CASES),
+              ("conv2d_bwd_filter", run_conv_bwd_filter, CONV_BWD_FILTER_CASES)]
+    for name, fn, cases in groups:
+        if flt and flt not in name:
+            continue
+        for case in cases:
+            try:
+                info = fn(**case)
+                print("%-18s %s -> %s" % (name, case, info), flush=True)
+            except Exception as e:  # noqa: BLE001
+                print("%-18s %s -> EXC %r" % (name, case, e), flush=True)
+                try:
+                    torch.cuda.synchronize()
+                except Exception as e2:  # noqa: BLE001
+                    print("CUDA context is dead:", e2, flush=True)
+                    sys.exit(3)
+    for tname in ["test_conv_small", "test_crop_and_resize", "test_linear", "test_elementwise_and_losses",
+                  "test_adam_and_pose"]:
+        if flt and flt not in tname:
+            continue
+        try:
+            globals()[tname]()
+            print(tname, "OK", flush=True)
+        except Exception as e:  # noqa: BLE001
+            import traceback
+            traceback.print_exc()
+            print(tname, "FAILED", repr(e)[:300], flush=True)
+    for mode in ("batch", "layer"):
+        if flt and flt not in "test_norm_act":
+            continue
+        try:
+            test_norm_act(mode)
+            print("test_norm_act", mode, "OK", flush=True)
+        except Exception as e:  # noqa: BLE001
+            import traceback
+            traceback.print_exc()
+            print("test_norm_act", mode, "FAILED", repr(e)[:300], flush=True)

@@ -1,0 +1,127 @@
+"""CPU tests of the oracle itself: the vectorised torch restatement (oracle/tf_ops.py, oracle/nets.py) against
+the independent scalar-loop restatement (oracle/np_ref.py) and against closed-form cases of the
+TensorFlow semantics listed in SURVEY.md §8c.  (Parity with real TF is unpinned: TF is not installable here.)
+"""
+import math
+
+import numpy as np
+import torch
+
+from oracle import nets, np_ref
+from oracle import tf_ops as T
+
+
+def test_same_padding_rule():
+    # k=3,s=2 on even size: pad (0,1); k=5,s=2: pad (1,2); k=3,s=1: (1,1)   
+    assert T.same_pads(128, 3, 2) == (64, 0, 1)
+    assert T.same_pads(128, 5, 2) == (64, 1, 2)
+    assert T.same_pads(48, 3, 1) == (48, 1, 1)
+    assert T.same_pads(3, 3, 2) == (2, 1, 1)
+    assert T.same_pads(6, 1, 1) == (6, 0, 0)
+
+
+def test_conv_matches_scalar_loops():
+    rng = np.random.default_rng(0)
+    for (h, w, ci, co, k, s) in [(6, 6, 3, 4, 3, 2), (5, 7, 2, 3, 3, 1), (8, 4, 3, 2, 5, 2), (4, 4, 5, 2, 1, 1)]:
+        x = rng.normal(size=(2, h, w, ci))
+        wt = rng.normal(size=(k, k, ci, co))
+        b = rng.normal(size=(co,))
+        ref = np_ref.conv2d_same(x, wt, b, s)
+        got = T.conv2d_same(torch.tensor(x), torch.tensor(wt), torch.tensor(b), s).numpy()
+        assert got.shape == ref.shape
+        assert np.abs(got - ref).max() < 1e-12
+
+
+def test_crop_and_resize_matches_scalar_loops():
+    rng = np.random.default_rng(1)
+    img = rng.normal(size=(2, 9, 7, 3))
+    boxes = np.array([[0.1, 0.2, 0.8, 0.9], [0.0, 0.0, 1.0, 1.0], [-0.2, 0.1, 0.5, 1.3], [0.3, 0.3, 0.3, 0.3],
+                      [0.0, 0.0, 1 / 9.0, 1 / 7.0]])
+    ind = np.array([0, 1, 1, 0, 1])
+    for cs in [(4, 4), (1, 3), (6, 5)]:
+        ref = np_ref.crop_and_resize(img, boxes, ind, cs)
+        got = T.crop_and_resize(torch.tensor(img), torch.tensor(boxes), torch.tensor(ind), cs).numpy()
+        assert np.abs(got - ref).max() < 1e-12
+
+
+def test_crop_and_resize_identity_box():
+    # box [0,0,1,1] with crop == image size reproduces the image (in = i exactly)
+    img = torch.arange(2 * 5 * 4 * 1, dtype=torch.float64).reshape(2, 5, 4, 1)
+    out = T.crop_and_resize(img, torch.tensor([[0., 0., 1., 1.]]), torch.tensor([1]), (5, 4))
+    assert torch.equal(out[0], img[1])
+
+
+def test_upscale_and_norms():
+    rng = np.random.default_rng(2)
+    x = rng.normal(size=(2, 3, 2, 4))
+    assert np.array_equal(T.upscale2(torch.tensor(x)).numpy(), np_ref.resize_nn2(x))
+    sc, of = rng.normal(size=4), rng.normal(size=4)
+    assert np.abs(T.batchnorm_train(torch.tensor(x), torch.tensor(sc), torch.tensor(of)).numpy()
+                  - np_ref.batchnorm_train(x, sc, of)).max() < 1e-12
+    assert np.abs(T.layernorm(torch.tensor(x), torch.tensor(sc), torch.tensor(of)).numpy()
+                  - np_ref.layernorm(x, sc, of)).max() < 1e-12
+
+
+def test_losses_and_adam():
+    z = np.array([-3.0, -0.1, 0.0, 0.4, 7.0])
+    l = np.array([0.0, 1.0, 1.0, 0.0, 1.0])
+    assert np.abs(T.sigmoid_ce(torch.tensor(z), torch.tensor(l)).numpy() - np_ref.sigmoid_ce(z, l)).max() < 1e-12
+    # against the textbook definition -l*log(s) - (1-l)*log(1-s)
+    s = 1 / (1 + np.exp(-z))
+    assert np.abs(np_ref.sigmoid_ce(z, l) - (-l * np.log(s) - (1 - l) * np.log(1 - s))).max() < 1e-9
+    rng = np.random.default_rng(3)
+    p = rng.normal(size=7)
+    grads = [rng.normal(size=7) for _ in range(3)]
+    ref = np_ref.adam_steps(p, grads, 2e-5)
+    pt = torch.tensor(p)
+    m, v = torch.zeros(7, dtype=torch.float64), torch.zeros(7, dtype=torch.float64)
+    for t, g in enumerate(grads, 1):
+        T.adam_step(pt, torch.tensor(g), m, v, 2e-5, t)
+    assert np.abs(pt.numpy() - ref).max() < 1e-15
+    # first TF-Adam step moves every weight by ~lr*sign(g) (lr_t*m/(sqrt(v)+eps) with t=1)
+    p1 = np_ref.adam_steps(p, grads[:1], 2e-5)
+    assert np.allclose(p1 - p, -2e-5 * np.sign(grads[0]), rtol=1e-3)
+
+
+def test_pose_rasterize_matches_reference_enumeration():
+    from dpig_b200 import synth
+    batch = synth.make_batch(2, 128, 64, seed=11)
+    rcv = batch["pose_rcv"]
+    got = T.pose_rasterize(torch.tensor(rcv), 128, 64, 4).numpy()
+    ref = np_ref.pose_inflate(rcv, 128, 64)
+    assert np.array_equal(got, ref)
+    assert set(np.unique(got)) <= {-1.0, 1.0}
+
+
+def test_network_shapes_and_names():
+    cfg = nets.NetConfig()
+    p = nets.init_params(cfg)
+    n_gen = sum(v.size for k, v in p.items() if nets.is_generator_param(k))
+    n_enc = sum(v.size for k, v in p.items() if k.startswith("Encoder/"))
+    n_d = sum(v.size for k, v in p.items() if nets.is_disc_param(k))
+    # Enc 47.3 M + G 71.2 M = 118.5 M; D 4.3 M
+    assert abs(n_enc / 1e6 - 47.3) < 0.1 and abs((n_gen - n_enc) / 1e6 - 71.2) < 0.1 and abs(n_d / 1e6 - 4.3) < 0.1
+    assert p["Encoder/G_encoder/Conv/weights"].shape == (3, 3, 3, 128)
+    assert p["Encoder/G_encoder/fully_connected/weights"].shape == (5760, 32)
+    assert p["Encoder/G_encoder/fully_connected_1/weights"].shape == (20480, 128)
+    assert p["ID_AE/G/Conv/weights"].shape == (3, 3, 370, 128)
+    assert p["ID_AE/G/fully_connected_1/weights"].shape == (64, 4096)
+    assert p["ID_AE/G/Conv_29/weights"].shape == (3, 3, 256, 3)
+    assert p["Discriminator.Output.W"].shape == (16384, 1)
+
+
+def test_small_stage1_forward_and_grads():
+    """A reduced graph (32x16, hidden 64) end to end in float64: shapes, finite losses, grads exist."""
+    from dpig_b200 import synth
+    cfg = nets.NetConfig(img_h=32, img_w=16, hidden=64, roi_size=12, d_dim=64)
+    p = nets.to_torch(nets.init_params(cfg, bias_noise=0.05), torch.float64, requires_grad=True)
+    b = synth.make_batch(2, 32, 16, seed=5)
+    batch = dict(x=torch.tensor(b["x"], dtype=torch.float64), mask=torch.tensor(b["mask"], dtype=torch.float64),
+                 pose=T.pose_rasterize(torch.tensor(b["pose_rcv"], dtype=torch.float64), 32, 16),
+                 part_bbox=torch.tensor(b["part_bbox"][:, :7]), part_vis=torch.tensor(b["part_vis"][:, :7]))
+    out, grads = nets.stage1_grads(p, cfg, batch, "g")
+    assert out["emb"].shape == (2, 352) and out["G"].shape == (2, 32, 16, 3) and out["D_fake"].shape == (2,)
+    assert all(g is not None and torch.isfinite(g).all() for g in grads.values())
+    out, grads = nets.stage1_grads(p, cfg, batch, "d", mode="wgan-gp", gp_alpha=torch.tensor([0.3, 0.8], dtype=torch.float64))
+    assert math.isfinite(float(out["d_loss"])) and float(out["gp"]) >= 0
+    assert all(g is not None for g in grads.values())
