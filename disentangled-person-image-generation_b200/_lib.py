@@ -60,6 +60,7 @@ _SIGNATURES = {
     "dpig_mask_split": [_T, _P, _T, _T, _P],
     "dpig_broadcast_embedding": [_P, _I, _T, _P],
     "dpig_spatial_sum": [_T, _P, _P],
+    "dpig_embedding_assemble": [_P, _P, _P, _I, _I, _I, _I, _P, _I, _P],
     "dpig_crop_and_resize_fwd": [_T, _P, _P, _P, _I, _T, _P],
     "dpig_crop_and_resize_bwd": [_T, _P, _P, _P, _I, _P, _I, _I, _I, _I, _P],
     "dpig_linear_fwd": [_P, _P, _P, _P, _I, _I, _I, _I, _F, _P],

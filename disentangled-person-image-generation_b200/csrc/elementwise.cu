@@ -406,3 +406,40 @@ extern "C" int dpig_weight_pack(dpig_ctx* ctx, const float* w_hwio, int32_t taps
   ctx->launches++;
   return check_launch(ctx, "weight_pack");
 }
+
+namespace dpig {
+// Body-part features -> embedding (reference models.py:433-442, 467-468): the 7 ROI feature blocks are the
+// rows i*B..(i+1)*B of `fea` (ROIs are concatenated on the batch axis, models.py:420), each scaled by the
+// part's visibility, followed by the background feature.  backward=1 routes the gradient the other way.
+__global__ void emb_assemble_kernel(float* fea, float* bg, const float* vis, int B, int parts, int pz, int bgz,
+                                    float* emb, int backward) {
+  const int E = parts * pz + bgz;
+  const int total = B * E;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int b = i / E, e = i % E;
+    if (e < parts * pz) {
+      const int part = e / pz, j = e % pz;
+      const float v = vis[b * parts + part];
+      float* f = fea + (static_cast<long long>(part) * B + b) * pz + j;
+      if (backward) *f = emb[i] * v;
+      else emb[i] = *f * v;
+    } else {
+      float* f = bg + static_cast<long long>(b) * bgz + (e - parts * pz);
+      if (backward) *f = emb[i];
+      else emb[i] = *f;
+    }
+  }
+}
+}  // namespace dpig
+
+extern "C" int dpig_embedding_assemble(dpig_ctx* ctx, float* fea, float* bg, const float* vis, int32_t batch,
+                                       int32_t parts, int32_t part_z, int32_t bg_z, float* emb, int32_t backward,
+                                       dpig_stream stream) {
+  DPIG_CHECK_CTX(ctx);
+  if (!fea || !bg || !vis || !emb) return set_error(ctx, DPIG_EINVAL, "embedding_assemble: null argument");
+  const int total = batch * (parts * part_z + bg_z);
+  emb_assemble_kernel<<<(total + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      fea, bg, vis, batch, parts, part_z, bg_z, emb, backward);
+  ctx->launches++;
+  return check_launch(ctx, "embedding_assemble");
+}

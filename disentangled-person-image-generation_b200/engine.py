@@ -1,0 +1,832 @@
+"""Static launch programs for the Stage-I graph of the reference (--model=1):
+
+    build_model   reference trainer.py:568-625   (Encoder -> broadcast -> U-Net -> D(x), D(G) -> losses)
+    train() step  reference trainer.py:336-347   (one g_optim update, then disc_ITERS d_optim updates)
+
+The graph is static, so the engine allocates every activation / gradient buffer once, records the
+sequence of C-ABI calls (ctypes function + frozen argument tuple) once, and a step is a replay of that
+list on the current CUDA stream -- no autograd, no tracing compiler, no per-step allocation.  Backward
+programs are written by hand (dgrad / wgrad kernels with fused ReLU masks and residual adds).
+
+Data layout in HBM: NHWC split-bf16 activations (tensor.SplitTensor); skip connections are written
+straight into the decoder's concat buffers (models.py:560 `tf.concat([x, skip])` never materialises);
+parameters, their gradients and the optimiser slots are flat fp32 arenas (one NCCL all-reduce per step).
+"""
+import ctypes as C
+import math
+from collections import OrderedDict
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import ACT_LRELU, ACT_NONE, ACT_RELU, GAN_MODES, NORM_BATCH, NORM_LAYER
+from .tensor import SplitTensor, ptr
+
+
+def _pad8(c):
+    return (c + 7) // 8 * 8
+
+
+class NetConfig:
+    """Shapes of the Stage-I Market-1501 graph (reference config.py:23-25, trainer.py:74-75, 576-582)."""
+
+    def __init__(self, img_h=128, img_w=64, hidden=128, z_num=64, roi_size=48, n_parts=7, part_z=32,
+                 keypoints=18, d_dim=64, repeat_num=None):
+        self.img_h, self.img_w, self.hidden, self.z_num = img_h, img_w, hidden, z_num
+        self.roi_size, self.n_parts, self.part_z, self.keypoints, self.d_dim = roi_size, n_parts, part_z, keypoints, d_dim
+        self.repeat_num = repeat_num if repeat_num is not None else int(math.log2(img_h)) - 2
+        self.emb_dim = n_parts * part_z + 4 * part_z
+
+
+# ------------------------------------------------------------------------------------- parameters
+class ParamGroup:
+    """Flat fp32 arenas (value, grad, Adam m / v) with named views."""
+
+    def __init__(self, specs, device):
+        self.specs = OrderedDict()
+        off = 0
+        for name, shape in specs:
+            n = int(np.prod(shape))
+            self.specs[name] = (off, n, tuple(shape))
+            off += (n + 63) // 64 * 64
+        self.total = off
+        self.value = torch.zeros(off, device=device)
+        self.grad = torch.zeros(off, device=device)
+        self.m = torch.zeros(off, device=device)
+        self.v = torch.zeros(off, device=device)
+
+    def view(self, name, arena=None):
+        off, n, shape = self.specs[name]
+        return (self.value if arena is None else arena)[off:off + n].view(shape)
+
+    def gview(self, name):
+        return self.view(name, self.grad)
+
+
+class ConvLayer:
+    """One convolution: fp32 HWIO master inside a ParamGroup + packed bf16 operand copies."""
+
+    def __init__(self, group, wname, bname, k, stride, cin, cout, device, need_bwd=True, small=False):
+        self.group, self.wname, self.bname = group, wname, bname
+        self.k, self.stride, self.cin, self.cout = k, stride, cin, cout
+        self.cin_pad, self.cout_pad = _pad8(cin), _pad8(cout)
+        self.small = small  # CUDA-core path (3-channel input): no packed copies
+        taps = k * k
+        if not small:
+            self.fwd = torch.zeros((2, taps, cout, self.cin_pad), dtype=torch.bfloat16, device=device)
+            self.bwd = torch.zeros((2, taps, cin, self.cout_pad), dtype=torch.bfloat16, device=device) if need_bwd else None
+
+    @property
+    def w(self):
+        return self.group.view(self.wname)
+
+    @property
+    def b(self):
+        return self.group.view(self.bname)
+
+    @property
+    def dw(self):
+        return self.group.gview(self.wname)
+
+    @property
+    def db(self):
+        return self.group.gview(self.bname)
+
+
+class Program:
+    """A recorded list of C-ABI calls; run() replays it on the given stream."""
+
+    def __init__(self, ctx):
+        self.ctx = ctx
+        self.calls = []
+        self.keep = []  # keeps ctypes structs / tensors referenced by the frozen arguments alive
+
+    def add(self, name, *args):
+        fn = getattr(self.ctx.lib, "dpig_" + name)
+        self.calls.append((name, fn, args))
+
+    def add_py(self, fn):
+        self.calls.append((None, fn, None))
+
+    def run(self, stream):
+        h = self.ctx.handle
+        for name, fn, args in self.calls:
+            if name is None:
+                fn(stream)
+                continue
+            rc = fn(h, *args, stream)
+            if rc != 0:
+                raise _lib.DpigError("dpig_%s failed (%d): %s" % (name, rc, self.ctx.last_error()))
+
+
+def _mask(pixels, c, device):
+    return torch.zeros((pixels, (c + 31) // 32), dtype=torch.int32, device=device)
+
+
+class _Pyramid:
+    """`repeat_num` levels of {conv, conv, +res, [conv/s2]} (models.py:421-429, 454-462, 530-539)."""
+
+    def __init__(self, eng, prefix, layers, x_in, n, h, w, y_slots=None, in_mask=None):
+        cfg = eng.cfg
+        hn, rn = cfg.hidden, cfg.repeat_num
+        dev = eng.device
+        self.layers = layers  # 3*rn - 1 ConvLayers in creation order
+        self.n, self.rn = n, rn
+        self.x_in, self.a, self.y, self.ma, self.mb, self.md = [x_in], [], [], [], [], []
+        self.dims = []
+        for idx in range(rn):
+            c = hn * (idx + 1)
+            hh, ww = h >> idx, w >> idx
+            self.dims.append((hh, ww, c))
+            self.a.append(SplitTensor(n, hh, ww, c, dev))
+            self.y.append(y_slots[idx] if y_slots else SplitTensor(n, hh, ww, c, dev))
+            self.ma.append(_mask(n * hh * ww, c, dev))
+            self.mb.append(_mask(n * hh * ww, c, dev))
+            if idx < rn - 1:
+                self.x_in.append(SplitTensor(n, hh // 2, ww // 2, c + hn, dev))
+                self.md.append(_mask(n * (hh // 2) * (ww // 2), c + hn, dev))
+        self.in_mask = in_mask
+        # backward buffers
+        self.g_y = [SplitTensor(n, d[0], d[1], d[2], dev) for d in self.dims]
+        self.gb = [SplitTensor(n, d[0], d[1], d[2], dev) for d in self.dims]
+        self.ga = [SplitTensor(n, d[0], d[1], d[2], dev) for d in self.dims]
+        self.gd = [SplitTensor(n, self.dims[i + 1][0], self.dims[i + 1][1], self.dims[i + 1][2], dev)
+                   for i in range(rn - 1)]
+        self.g_in = SplitTensor(n, h, w, hn, dev)  # grad wrt the pyramid input (masked if in_mask)
+
+    def forward(self, eng, prog):
+        li = 0
+        for idx in range(self.rn):
+            eng.conv_fwd(prog, self.layers[li], self.x_in[idx], out=self.a[idx], mask_out=self.ma[idx])
+            eng.conv_fwd(prog, self.layers[li + 1], self.a[idx], out=self.y[idx], addend=self.x_in[idx],
+                         mask_out=self.mb[idx])
+            li += 2
+            if idx < self.rn - 1:
+                eng.conv_fwd(prog, self.layers[li], self.y[idx], out=self.x_in[idx + 1], mask_out=self.md[idx])
+                li += 1
+
+    def backward(self, eng, prog, skip_grads=None, wgrad=True):
+        """Expects g_y[rn-1] (unmasked grad wrt the top level output, all contributions summed) to be
+        filled by the caller.  skip_grads[idx] (idx < rn-1): extra grad wrt y[idx] (decoder skip path)."""
+        rn = self.rn
+        # top level: gb = g_y * mask_b
+        prog.add("ew_combine", self.gb[rn - 1].ref(), self.g_y[rn - 1].ref(), None, None, None, 0,
+                 ptr(self.mb[rn - 1]), 0.0, 0)
+        for idx in range(rn - 1, -1, -1):
+            l1, l2 = self.layers[3 * idx], self.layers[3 * idx + 1]
+            hh, ww, c = self.dims[idx]
+            if wgrad:
+                eng.conv_wgrad(prog, l2, self.a[idx], self.gb[idx])
+            eng.conv_dgrad(prog, l2, self.gb[idx], hh, ww, out_masked=self.ga[idx], mask_in=self.ma[idx])
+            if wgrad:
+                eng.conv_wgrad(prog, l1, self.x_in[idx], self.ga[idx])
+            if idx > 0:
+                # x_in[idx] = relu(conv_s2(y[idx-1])): emit the masked gradient directly
+                eng.conv_dgrad(prog, l1, self.ga[idx], hh, ww, out_masked=self.gd[idx - 1], mask_in=self.md[idx - 1],
+                               addend=self.g_y[idx])
+                ls = self.layers[3 * (idx - 1) + 2]
+                if wgrad:
+                    eng.conv_wgrad(prog, ls, self.y[idx - 1], self.gd[idx - 1])
+                ph, pw, pc = self.dims[idx - 1]
+                eng.conv_dgrad(prog, ls, self.gd[idx - 1], ph, pw, out=self.g_y[idx - 1], out_masked=self.gb[idx - 1],
+                               mask_in=self.mb[idx - 1], addend=skip_grads[idx - 1] if skip_grads else None)
+            else:
+                if self.in_mask is not None:
+                    eng.conv_dgrad(prog, l1, self.ga[0], hh, ww, out_masked=self.g_in, mask_in=self.in_mask,
+                                   addend=self.g_y[0])
+                else:
+                    eng.conv_dgrad(prog, l1, self.ga[0], hh, ww, out=self.g_in, addend=self.g_y[0])
+
+
+class _DiscPass:
+    """Activations of one DCGANDiscriminator application (wgan_gp.py:407-440)."""
+
+    def __init__(self, eng, n):
+        cfg, dev = eng.cfg, eng.device
+        d = cfg.d_dim
+        H, W = cfg.img_h, cfg.img_w
+        self.n = n
+        self.h = [SplitTensor(n, H >> (i + 1), W >> (i + 1), d << i, dev) for i in range(4)]   # activated outputs
+        self.m = [_mask(n * (H >> (i + 1)) * (W >> (i + 1)), d << i, dev) for i in range(4)]
+        self.pre = [None] + [torch.zeros((n, H >> (i + 1), W >> (i + 1), d << i), device=dev) for i in (1, 2, 3)]
+        self.groups = [None] + [(n if eng.norm_mode == NORM_LAYER else (d << i)) for i in (1, 2, 3)]
+        self.sums = [None] + [torch.zeros((2, g), dtype=torch.float64, device=dev) for g in self.groups[1:]]
+        self.stats = [None] + [torch.zeros((2, g), device=dev) for g in self.groups[1:]]
+        self.red = [None] + [torch.zeros((2, g), dtype=torch.float64, device=dev) for g in self.groups[1:]]
+        flat = (H >> 4) * (W >> 4) * 8 * d
+        self.flat = torch.zeros((n, flat), device=dev)
+        self.logits = torch.zeros((n,), device=dev)
+        # backward
+        self.dlogits = torch.zeros((n,), device=dev)
+        self.g_flat = torch.zeros((n, flat), device=dev)
+        self.g_h = [SplitTensor(n, H >> (i + 1), W >> (i + 1), d << i, dev) for i in range(4)]  # grad wrt activated
+        self.g_pre = [SplitTensor(n, H >> (i + 1), W >> (i + 1), d << i, dev) for i in range(4)]  # grad wrt conv out
+        self.g_pre1_f32 = torch.zeros((n, H >> 1, W >> 1, d), device=dev)
+        self.g_x = torch.zeros((n, H, W, 3), device=dev)
+
+
+class Stage1Engine:
+    def __init__(self, ctx, cfg, batch, mode="dcgan", lam=10.0, dist=None, device="cuda"):
+        """dist: optional object with all_reduce_sum(tensor) and world_size (data-parallel hooks)."""
+        self.ctx, self.cfg, self.B, self.mode, self.lam, self.dist = ctx, cfg, int(batch), mode, lam, dist
+        self.device = torch.device(device)
+        self.gan_mode = GAN_MODES[mode]
+        self.norm_mode = NORM_LAYER if mode == "wgan-gp" else NORM_BATCH  # wgan_gp.py:34-40
+        self.world = dist.world_size if dist is not None else 1
+        self._keep = []
+        self._build_params()
+        self._build_buffers()
+        self.t = {"g": 0, "d": 0}
+        self.g_lr = 2e-5
+        self.d_lr = 2e-5
+        self._build_programs()
+
+    # -------------------------------------------------------------------------------- parameters
+    def _build_params(self):
+        cfg, dev = self.cfg, self.device
+        hn, rn = cfg.hidden, cfg.repeat_num
+        gspecs, dspecs = [], []
+        self.layers = OrderedDict()
+
+        def conv(group_specs, scope, counter, k, stride, cin, cout, small=False, need_bwd=True):
+            i = counter[0]
+            counter[0] += 1
+            name = "%s/Conv%s" % (scope, "" if i == 0 else "_%d" % i)
+            group_specs.append((name + "/weights", (k, k, cin, cout)))
+            group_specs.append((name + "/biases", (cout,)))
+            self.layers[name] = dict(k=k, stride=stride, cin=cin, cout=cout, small=small, need_bwd=need_bwd)
+            return name
+
+        def fc(group_specs, scope, counter, cin, cout):
+            i = counter[0]
+            counter[0] += 1
+            name = "%s/fully_connected%s" % (scope, "" if i == 0 else "_%d" % i)
+            group_specs.append((name + "/weights", (cin, cout)))
+            group_specs.append((name + "/biases", (cout,)))
+            return name
+
+        def pyramid(scope, cc):
+            names = []
+            for idx in range(rn):
+                c = hn * (idx + 1)
+                names.append(conv(gspecs, scope, cc, 3, 1, c, c))
+                names.append(conv(gspecs, scope, cc, 3, 1, c, c))
+                if idx < rn - 1:
+                    names.append(conv(gspecs, scope, cc, 3, 2, c, hn * (idx + 2)))
+            return names
+
+        # Encoder/G_encoder (models.py:390-471)
+        sc, cc, fc_c = "Encoder/G_encoder", [0], [0]
+        self.n_e0 = conv(gspecs, sc, cc, 3, 1, 3, hn, small=True, need_bwd=False)
+        self.n_e1 = conv(gspecs, sc, cc, 3, 1, hn, hn)
+        self.n_e2 = conv(gspecs, sc, cc, 3, 1, hn, hn)
+        self.n_roi = pyramid(sc, cc)
+        roi_f = cfg.roi_size >> (rn - 1)
+        self.roi_flat = roi_f * roi_f * hn * rn
+        self.n_roi_fc = fc(gspecs, sc, fc_c, self.roi_flat, cfg.part_z)
+        self.n_bg = pyramid(sc, cc)
+        self.fh, self.fw = cfg.img_h >> (rn - 1), cfg.img_w >> (rn - 1)
+        self.bg_flat = self.fh * self.fw * hn * rn
+        self.n_bg_fc = fc(gspecs, sc, fc_c, self.bg_flat, cfg.part_z * 4)
+        # ID_AE/G (models.py:518-576)
+        sc, cc, fc_c = "ID_AE/G", [0], [0]
+        self.gin_c = cfg.emb_dim + cfg.keypoints
+        self.n_gstem = conv(gspecs, sc, cc, 3, 1, self.gin_c, hn)
+        self.n_genc = pyramid(sc, cc)
+        self.n_gfc1 = fc(gspecs, sc, fc_c, self.bg_flat, cfg.z_num)
+        self.n_gfc2 = fc(gspecs, sc, fc_c, cfg.z_num, self.fh * self.fw * hn)
+        self.n_gdec = []
+        self.dec_c = []
+        x_c = hn
+        for idx in range(rn):
+            c = x_c + hn * (rn - idx)
+            self.dec_c.append((x_c, c))
+            names = [conv(gspecs, sc, cc, 3, 1, c, c), conv(gspecs, sc, cc, 3, 1, c, c)]
+            if idx < rn - 1:
+                x_c = hn * (rn - idx - 1)
+                names.append(conv(gspecs, sc, cc, 1, 1, c, x_c))
+            else:
+                x_c = c
+            self.n_gdec.append(names)
+        self.n_gout = conv(gspecs, sc, cc, 3, 1, x_c, 3)
+        # Discriminator (wgan_gp.py:407-440)
+        d = cfg.d_dim
+        chans = [3, d, 2 * d, 4 * d, 8 * d]
+        self.n_d = []
+        for i in range(4):
+            name = "Discriminator.%d" % (i + 1)
+            dspecs.append((name + ".Filters", (5, 5, chans[i], chans[i + 1])))
+            dspecs.append((name + ".Biases", (chans[i + 1],)))
+            if i >= 1:
+                dspecs.append(("Discriminator.BN%d.offset" % (i + 1), (chans[i + 1],)))
+                dspecs.append(("Discriminator.BN%d.scale" % (i + 1), (chans[i + 1],)))
+            self.layers[name] = dict(k=5, stride=2, cin=chans[i], cout=chans[i + 1], small=(i == 0), need_bwd=True)
+            self.n_d.append(name)
+        self.d_flat = (cfg.img_h // 16) * (cfg.img_w // 16) * 8 * d
+        dspecs.append(("Discriminator.Output.W", (self.d_flat, 1)))
+        dspecs.append(("Discriminator.Output.b", (1,)))
+
+        self.gp = ParamGroup(gspecs, dev)
+        self.dp = ParamGroup(dspecs, dev)
+        self.conv = OrderedDict()
+        for name, s in self.layers.items():
+            if name.startswith("Discriminator"):
+                self.conv[name] = ConvLayer(self.dp, name + ".Filters", name + ".Biases", s["k"], s["stride"], s["cin"],
+                                            s["cout"], dev, s["need_bwd"], s["small"])
+            else:
+                self.conv[name] = ConvLayer(self.gp, name + "/weights", name + "/biases", s["k"], s["stride"], s["cin"],
+                                            s["cout"], dev, s["need_bwd"], s["small"])
+        # BN / LN scale defaults to one
+        for i in (2, 3, 4):
+            self.dp.view("Discriminator.BN%d.scale" % i).fill_(1.0)
+        # the D output weight is kept NHWC-flattened internally; TF order (c-major) at the API boundary
+        hw = (cfg.img_h // 16) * (cfg.img_w // 16)
+        self._dperm = torch.arange(self.d_flat, device=dev).view(8 * d, hw).t().reshape(-1)  # nhwc idx -> nchw idx
+
+    def param_names(self):
+        return list(self.gp.specs) + list(self.dp.specs)
+
+    def load_params(self, params):
+        """params: dict TF-variable-name -> array (TF layouts). Missing names keep their current value."""
+        for grp in (self.gp, self.dp):
+            for name in grp.specs:
+                if name in params:
+                    t = torch.as_tensor(np.asarray(params[name]), dtype=torch.float32).to(self.device)
+                    if name == "Discriminator.Output.W":
+                        t = t.reshape(-1)[self._dperm].reshape(-1, 1)
+                    grp.view(name).copy_(t.reshape(grp.specs[name][2]))
+        self.pack_weights("g")
+        self.pack_weights("d")
+        torch.cuda.synchronize()
+
+    def get_params(self, grads=False):
+        out = OrderedDict()
+        for grp in (self.gp, self.dp):
+            for name in grp.specs:
+                t = (grp.gview(name) if grads else grp.view(name)).detach().clone()
+                if name == "Discriminator.Output.W":
+                    inv = torch.empty_like(self._dperm)
+                    inv[self._dperm] = torch.arange(self.d_flat, device=self.device)
+                    t = t.reshape(-1)[inv].reshape(-1, 1)
+                out[name] = t.cpu().numpy()
+        return out
+
+    def pack_weights(self, which, stream=None):
+        s = stream if stream is not None else torch.cuda.current_stream().cuda_stream
+        for name, layer in self.conv.items():
+            if layer.small or (name.startswith("Discriminator") != (which == "d")):
+                continue
+            self.ctx.weight_pack(ptr(layer.w), layer.k * layer.k, layer.cin, layer.cout, layer.cin_pad, layer.cout_pad,
+                                 ptr(layer.fwd[0]), ptr(layer.fwd[1]),
+                                 ptr(layer.bwd[0]) if layer.bwd is not None else None,
+                                 ptr(layer.bwd[1]) if layer.bwd is not None else None, s)
+
+    # -------------------------------------------------------------------------------- buffers
+    def _build_buffers(self):
+        cfg, dev, B = self.cfg, self.device, self.B
+        H, W, hn, rn = cfg.img_h, cfg.img_w, cfg.hidden, cfg.repeat_num
+        P = cfg.n_parts
+        # inputs (device copies of one batch)
+        self.x = torch.zeros((B, H, W, 3), device=dev)
+        self.pose_rcv = torch.zeros((B, cfg.keypoints, 3), device=dev)
+        self.fg_mask = torch.zeros((B, H, W), device=dev)
+        self.boxes = torch.zeros((P * B, 4), device=dev)
+        self.box_ind = (torch.arange(P * B, device=dev, dtype=torch.int32) % B).contiguous()
+        self.vis = torch.zeros((B, P), device=dev)
+        # encoder
+        self.e0 = SplitTensor(B, H, W, hn, dev)
+        self.me0 = _mask(B * H * W, hn, dev)
+        self.e1 = SplitTensor(B, H, W, hn, dev)
+        self.me1 = _mask(B * H * W, hn, dev)
+        self.xs = SplitTensor(B, H, W, hn, dev)
+        self.me2 = _mask(B * H * W, hn, dev)
+        self.x_bg = SplitTensor(B, H, W, hn, dev)
+        self.rois = SplitTensor(P * B, cfg.roi_size, cfg.roi_size, hn, dev)
+        self.roi_pyr = _Pyramid(self, "roi", [self.conv[n] for n in self.n_roi], self.rois, P * B, cfg.roi_size, cfg.roi_size)
+        self.bg_pyr = _Pyramid(self, "bg", [self.conv[n] for n in self.n_bg], self.x_bg, B, H, W)
+        self.roi_flat_f32 = torch.zeros((P * B, self.roi_flat), device=dev)
+        self.fea = torch.zeros((P * B, cfg.part_z), device=dev)
+        self.bg_flat_f32 = torch.zeros((B, self.bg_flat), device=dev)
+        self.bg_fea = torch.zeros((B, cfg.part_z * 4), device=dev)
+        self.emb = torch.zeros((B, cfg.emb_dim), device=dev)
+        # generator
+        self.gin_cpad = (self.gin_c + 63) // 64 * 64
+        self.gin = SplitTensor(B, H, W, self.gin_cpad, dev, zero=True)
+        self.g0 = SplitTensor(B, H, W, hn, dev)
+        self.mg0 = _mask(B * H * W, hn, dev)
+        # decoder concat buffers; the encoder skip outputs are slices of them
+        self.cat = []
+        for idx in range(rn):
+            xc, c = self.dec_c[idx]
+            lvl = rn - 1 - idx
+            self.cat.append(SplitTensor(B, H >> lvl, W >> lvl, c, dev))
+        y_slots = [None] * rn
+        for idx in range(rn):
+            xc, c = self.dec_c[idx]
+            y_slots[rn - 1 - idx] = self.cat[idx].slice(xc, c - xc)
+        self.genc = _Pyramid(self, "genc", [self.conv[n] for n in self.n_genc], self.g0, B, H, W, y_slots=y_slots,
+                             in_mask=self.mg0)
+        self.gtop_f32 = torch.zeros((B, self.bg_flat), device=dev)
+        self.z = torch.zeros((B, cfg.z_num), device=dev)
+        self.dec_in_f32 = torch.zeros((B, self.fh * self.fw * hn), device=dev)
+        self.dec_a, self.dec_y, self.dec_ma, self.dec_mb, self.dec_mu = [], [], [], [], []
+        for idx in range(rn):
+            xc, c = self.dec_c[idx]
+            lvl = rn - 1 - idx
+            hh, ww = H >> lvl, W >> lvl
+            self.dec_a.append(SplitTensor(B, hh, ww, c, dev))
+            self.dec_y.append(SplitTensor(B, hh, ww, c, dev))
+            self.dec_ma.append(_mask(B * hh * ww, c, dev))
+            self.dec_mb.append(_mask(B * hh * ww, c, dev))
+            if idx < rn - 1:
+                self.dec_mu.append(_mask(B * hh * ww, self.dec_c[idx + 1][0], dev))
+        self.G = torch.zeros((B, H, W, 3), device=dev)
+        # generator backward
+        self.g_G = torch.zeros((B, H, W, 3), device=dev)
+        self.g_G8 = SplitTensor(B, H, W, 8, dev, zero=True)
+        self.g_cat, self.dec_gy, self.dec_gb, self.dec_ga, self.dec_gu = [], [], [], [], []
+        for idx in range(rn):
+            xc, c = self.dec_c[idx]
+            lvl = rn - 1 - idx
+            hh, ww = H >> lvl, W >> lvl
+            self.g_cat.append(SplitTensor(B, hh, ww, c, dev))
+            self.dec_gy.append(SplitTensor(B, hh, ww, c, dev))
+            self.dec_gb.append(SplitTensor(B, hh, ww, c, dev))
+            self.dec_ga.append(SplitTensor(B, hh, ww, c, dev))
+            if idx < rn - 1:
+                self.dec_gu.append(SplitTensor(B, hh, ww, self.dec_c[idx + 1][0], dev))
+        self.g_dec_in_f32 = torch.zeros((B, self.fh * self.fw * hn), device=dev)
+        self.g_z = torch.zeros((B, cfg.z_num), device=dev)
+        self.g_gtop_f32 = torch.zeros((B, self.bg_flat), device=dev)
+        self.g_gin = SplitTensor(B, H, W, self.gin_cpad, dev)
+        self.g_emb = torch.zeros((B, cfg.emb_dim), device=dev)
+        # encoder backward
+        self.g_fea = torch.zeros((P * B, cfg.part_z), device=dev)
+        self.g_bg_fea = torch.zeros((B, cfg.part_z * 4), device=dev)
+        self.g_roi_flat = torch.zeros((P * B, self.roi_flat), device=dev)
+        self.g_bg_flat = torch.zeros((B, self.bg_flat), device=dev)
+        self.g_crop = torch.zeros((B, H, W, hn), device=dev)
+        self.g_xbg_s = SplitTensor(B, H, W, hn, dev)
+        self.g_xs = SplitTensor(B, H, W, hn, dev)
+        self.g_xs_m = SplitTensor(B, H, W, hn, dev)
+        self.g_e1 = SplitTensor(B, H, W, hn, dev)
+        self.g_e0 = SplitTensor(B, H, W, hn, dev)
+        self.g_e0_f32 = torch.zeros((B, H, W, hn), device=dev)
+        # discriminator passes
+        self.d_real = _DiscPass(self, B)
+        self.d_fake = _DiscPass(self, B)
+        # losses: [g_gan, d_loss], [L1], gp
+        self.loss_gan = torch.zeros((2,), device=dev)
+        self.loss_l1 = torch.zeros((1,), device=dev)
+        self.loss_gp = torch.zeros((1,), device=dev)
+
+    # -------------------------------------------------------------------------------- call helpers
+    def _epilogue(self, prog, layer_bias, act, alpha, addend, mask_in, mask_neg, mask_out, out, out_masked, out_f32,
+                  out_f32_ps, upsample):
+        ep = _lib.ConvEpilogue()
+        ep.bias = layer_bias.data_ptr() if layer_bias is not None else None
+        ep.act = act
+        ep.alpha = alpha
+        if addend is not None:
+            ep.addend = C.pointer(addend.struct())
+        if mask_in is not None:
+            ep.mask_in = mask_in.data_ptr()
+        ep.mask_neg = mask_neg
+        if mask_out is not None:
+            ep.mask_out = mask_out.data_ptr()
+        if out is not None:
+            ep.out = C.pointer(out.struct())
+        if out_masked is not None:
+            ep.out_masked = C.pointer(out_masked.struct())
+        if out_f32 is not None:
+            ep.out_f32 = out_f32.data_ptr()
+            ep.out_f32_pix_stride = out_f32_ps
+        ep.upsample = upsample
+        prog.keep.append((ep, addend, out, out_masked))
+        return C.byref(ep)
+
+    def conv_fwd(self, prog, layer, x, out=None, act=ACT_RELU, alpha=0.2, addend=None, mask_out=None, out_f32=None,
+                 out_f32_ps=0, upsample=1):
+        ep = self._epilogue(prog, layer.b, act, alpha, addend, None, 0.0, mask_out, out, None, out_f32, out_f32_ps,
+                            upsample)
+        prog.add("conv2d_fwd", x.ref(), ptr(layer.fwd[0]), ptr(layer.fwd[1]), layer.k, layer.k, layer.stride, layer.cout, ep)
+
+    def conv_dgrad(self, prog, layer, dy, in_h, in_w, out=None, out_masked=None, mask_in=None, mask_neg=0.0, addend=None):
+        ep = self._epilogue(prog, None, ACT_NONE, 0.0, addend, mask_in, mask_neg, None, out, out_masked, None, 0, 1)
+        prog.add("conv2d_bwd_data", dy.ref(), ptr(layer.bwd[0]), ptr(layer.bwd[1]), layer.k, layer.k, layer.stride,
+                 in_h, in_w, layer.cin, ep)
+
+    def conv_wgrad(self, prog, layer, x, dy):
+        prog.add("conv2d_bwd_filter", x.ref(), dy.ref(), layer.k, layer.k, layer.stride, layer.cin, layer.cout,
+                 ptr(layer.dw))
+        prog.add("bias_grad", dy.ref(), ptr(layer.db))
+
+    def _linear(self, grp, name):
+        return grp.view(name + "/weights"), grp.view(name + "/biases"), grp.gview(name + "/weights"), grp.gview(name + "/biases")
+
+    # -------------------------------------------------------------------------------- programs
+    def _build_programs(self):
+        self.p_fwd_gen = Program(self.ctx)     # Encoder + U-Net forward (also the sampling path)
+        self._prog_forward_generator(self.p_fwd_gen)
+        self.p_bwd_gen = Program(self.ctx)     # g_G -> all Encoder+G parameter gradients
+        self._prog_backward_generator(self.p_bwd_gen)
+        self.p_d_fake_fwd = Program(self.ctx)
+        self._prog_disc_forward(self.p_d_fake_fwd, self.d_fake, self.G)
+        self.p_d_real_fwd = Program(self.ctx)
+        self._prog_disc_forward(self.p_d_real_fwd, self.d_real, self.x)
+        self.p_d_fake_bwd_data = Program(self.ctx)   # G step: gradient w.r.t. the generated image only
+        self._prog_disc_backward(self.p_d_fake_bwd_data, self.d_fake, self.G, params=False, data=True)
+        self.p_d_fake_bwd_par = Program(self.ctx)    # D step
+        self._prog_disc_backward(self.p_d_fake_bwd_par, self.d_fake, self.G, params=True, data=False)
+        self.p_d_real_bwd_par = Program(self.ctx)
+        self._prog_disc_backward(self.p_d_real_bwd_par, self.d_real, self.x, params=True, data=False)
+
+    def _prog_forward_generator(self, p):
+        cfg, B = self.cfg, self.B
+        H, W, hn, rn, P = cfg.img_h, cfg.img_w, cfg.hidden, cfg.repeat_num, cfg.n_parts
+        e0, e1, e2 = self.conv[self.n_e0], self.conv[self.n_e1], self.conv[self.n_e2]
+        # ---- encoder (models.py:396-471)
+        p.add("conv2d_small_fwd", ptr(self.x), B, H, W, 3, ptr(e0.w), ptr(e0.b), 3, 3, 1, hn, ACT_RELU, 0.0,
+              self.e0.ref(), None, ptr(self.me0))
+        self.conv_fwd(p, e1, self.e0, out=self.e1, mask_out=self.me1)
+        self.conv_fwd(p, e2, self.e1, out=self.xs, addend=self.e0, mask_out=self.me2)
+        p.add("mask_split", self.xs.ref(), ptr(self.fg_mask), None, self.x_bg.ref())
+        p.add("crop_and_resize_fwd", self.xs.ref(), ptr(self.fg_mask), ptr(self.boxes), ptr(self.box_ind), P * B,
+              self.rois.ref())
+        self.roi_pyr.forward(self, p)
+        p.add("unpack_f32", self.roi_pyr.y[rn - 1].ref(), ptr(self.roi_flat_f32), hn * rn)
+        w, b, _, _ = self._linear(self.gp, self.n_roi_fc)
+        p.add("linear_fwd", ptr(self.roi_flat_f32), ptr(w), ptr(b), ptr(self.fea), P * B, self.roi_flat, cfg.part_z,
+              ACT_NONE, 0.0)
+        self.bg_pyr.forward(self, p)
+        p.add("unpack_f32", self.bg_pyr.y[rn - 1].ref(), ptr(self.bg_flat_f32), hn * rn)
+        w, b, _, _ = self._linear(self.gp, self.n_bg_fc)
+        p.add("linear_fwd", ptr(self.bg_flat_f32), ptr(w), ptr(b), ptr(self.bg_fea), B, self.bg_flat, cfg.part_z * 4,
+              ACT_NONE, 0.0)
+        p.add("embedding_assemble", ptr(self.fea), ptr(self.bg_fea), ptr(self.vis), B, P, cfg.part_z, cfg.part_z * 4,
+              ptr(self.emb), 0)
+        # ---- generator (trainer.py:588-590, models.py:518-576)
+        self._prog_unet_forward(p)
+
+    def _prog_unet_forward(self, p):
+        cfg, B = self.cfg, self.B
+        H, W, hn, rn = cfg.img_h, cfg.img_w, cfg.hidden, cfg.repeat_num
+        p.add("broadcast_embedding", ptr(self.emb), cfg.emb_dim, self.gin.ref())
+        pose_slice = self.gin.slice(cfg.emb_dim, cfg.keypoints)
+        self._keep.append(pose_slice)
+        p.add("pose_rasterize", ptr(self.pose_rcv), B, cfg.keypoints, H, W, 4, pose_slice.ref(), None)
+        self.conv_fwd(p, self.conv[self.n_gstem], self.gin, out=self.g0, mask_out=self.mg0)
+        self.genc.forward(self, p)
+        top = self.genc.y[rn - 1]
+        p.add("unpack_f32", top.ref(), ptr(self.gtop_f32), hn * rn)
+        w, b, _, _ = self._linear(self.gp, self.n_gfc1)
+        p.add("linear_fwd", ptr(self.gtop_f32), ptr(w), ptr(b), ptr(self.z), B, self.bg_flat, cfg.z_num, ACT_NONE, 0.0)
+        w, b, _, _ = self._linear(self.gp, self.n_gfc2)
+        p.add("linear_fwd", ptr(self.z), ptr(w), ptr(b), ptr(self.dec_in_f32), B, cfg.z_num, self.fh * self.fw * hn,
+              ACT_NONE, 0.0)
+        x_slice = self.cat[0].slice(0, hn)
+        self._keep.append(x_slice)
+        p.add("pack_f32", ptr(self.dec_in_f32), hn, hn, x_slice.ref())
+        for idx in range(rn):
+            names = self.n_gdec[idx]
+            self.conv_fwd(p, self.conv[names[0]], self.cat[idx], out=self.dec_a[idx], mask_out=self.dec_ma[idx])
+            self.conv_fwd(p, self.conv[names[1]], self.dec_a[idx], out=self.dec_y[idx], addend=self.cat[idx],
+                          mask_out=self.dec_mb[idx])
+            if idx < rn - 1:
+                up = self.cat[idx + 1].slice(0, self.dec_c[idx + 1][0])
+                self._keep.append(up)
+                self.conv_fwd(p, self.conv[names[2]], self.dec_y[idx], out=up, mask_out=self.dec_mu[idx], upsample=2)
+        self.conv_fwd(p, self.conv[self.n_gout], self.dec_y[rn - 1], act=ACT_NONE, out_f32=self.G, out_f32_ps=3)
+
+    def _prog_backward_generator(self, p):
+        """Consumes self.g_G (fp32 grad wrt the generated image) and accumulates all Encoder+G param grads."""
+        cfg, B = self.cfg, self.B
+        H, W, hn, rn, P = cfg.img_h, cfg.img_w, cfg.hidden, cfg.repeat_num, cfg.n_parts
+        p.add("pack_f32", ptr(self.g_G), 3, 3, self.g_G8.ref())
+        # ---- decoder
+        lo = self.conv[self.n_gout]
+        self.conv_wgrad(p, lo, self.dec_y[rn - 1], self.g_G8)
+        self.conv_dgrad(p, lo, self.g_G8, H, W, out=self.dec_gy[rn - 1], out_masked=self.dec_gb[rn - 1],
+                        mask_in=self.dec_mb[rn - 1])
+        for idx in range(rn - 1, -1, -1):
+            names = self.n_gdec[idx]
+            lvl = rn - 1 - idx
+            hh, ww = H >> lvl, W >> lvl
+            l1, l2 = self.conv[names[0]], self.conv[names[1]]
+            if idx < rn - 1:
+                # gradient of the upsampled 1x1-conv output = x-part of the next level's concat gradient
+                lu = self.conv[names[2]]
+                gup = self.g_cat[idx + 1].slice(0, self.dec_c[idx + 1][0])
+                self._keep.append(gup)
+                p.add("ew_combine", self.dec_gu[idx].ref(), gup.ref(), None, None, None, 0, ptr(self.dec_mu[idx]), 0.0, 1)
+                self.conv_wgrad(p, lu, self.dec_y[idx], self.dec_gu[idx])
+                self.conv_dgrad(p, lu, self.dec_gu[idx], hh, ww, out=self.dec_gy[idx], out_masked=self.dec_gb[idx],
+                                mask_in=self.dec_mb[idx])
+            self.conv_wgrad(p, l2, self.dec_a[idx], self.dec_gb[idx])
+            self.conv_dgrad(p, l2, self.dec_gb[idx], hh, ww, out_masked=self.dec_ga[idx], mask_in=self.dec_ma[idx])
+            self.conv_wgrad(p, l1, self.cat[idx], self.dec_ga[idx])
+            self.conv_dgrad(p, l1, self.dec_ga[idx], hh, ww, out=self.g_cat[idx], addend=self.dec_gy[idx])
+        # ---- bottleneck FCs (models.py:543-555)
+        gx0 = self.g_cat[0].slice(0, hn)
+        self._keep.append(gx0)
+        p.add("unpack_f32", gx0.ref(), ptr(self.g_dec_in_f32), hn)
+        w, b, dw, db = self._linear(self.gp, self.n_gfc2)
+        p.add("linear_bwd", ptr(self.z), ptr(w), ptr(self.g_dec_in_f32), ptr(self.g_z), ptr(dw), ptr(db), B, cfg.z_num,
+              self.fh * self.fw * hn)
+        w, b, dw, db = self._linear(self.gp, self.n_gfc1)
+        p.add("linear_bwd", ptr(self.gtop_f32), ptr(w), ptr(self.g_z), ptr(self.g_gtop_f32), ptr(dw), ptr(db), B,
+              self.bg_flat, cfg.z_num)
+        # ---- U-Net encoder: top gradient = FC path + skip path
+        skip = []
+        for lvl in range(rn):
+            idx = rn - 1 - lvl
+            xc, c = self.dec_c[idx]
+            s = self.g_cat[idx].slice(xc, c - xc)
+            self._keep.append(s)
+            skip.append(s)
+        p.add("ew_combine", self.genc.g_y[rn - 1].ref(), skip[rn - 1].ref(), None, None, ptr(self.g_gtop_f32), hn * rn,
+              None, 0.0, 0)
+        self.genc.backward(self, p, skip_grads=skip)
+        ls = self.conv[self.n_gstem]
+        self.conv_wgrad(p, ls, self.gin, self.genc.g_in)
+        self.conv_dgrad(p, ls, self.genc.g_in, H, W, out=self.g_gin)
+        gemb = self.g_gin.slice(0, cfg.emb_dim)
+        self._keep.append(gemb)
+        p.add("spatial_sum", gemb.ref(), ptr(self.g_emb))
+        # ---- appearance encoder
+        p.add("embedding_assemble", ptr(self.g_fea), ptr(self.g_bg_fea), ptr(self.vis), B, P, cfg.part_z, cfg.part_z * 4,
+              ptr(self.g_emb), 1)
+        w, b, dw, db = self._linear(self.gp, self.n_roi_fc)
+        p.add("linear_bwd", ptr(self.roi_flat_f32), ptr(w), ptr(self.g_fea), ptr(self.g_roi_flat), ptr(dw), ptr(db), P * B,
+              self.roi_flat, cfg.part_z)
+        p.add("pack_f32", ptr(self.g_roi_flat), hn * rn, hn * rn, self.roi_pyr.g_y[rn - 1].ref())
+        self.roi_pyr.backward(self, p)
+        p.add_py(lambda s: self.g_crop.zero_())
+        p.add("crop_and_resize_bwd", self.roi_pyr.g_in.ref(), ptr(self.fg_mask), ptr(self.boxes), ptr(self.box_ind), P * B,
+              ptr(self.g_crop), B, H, W, hn)
+        w, b, dw, db = self._linear(self.gp, self.n_bg_fc)
+        p.add("linear_bwd", ptr(self.bg_flat_f32), ptr(w), ptr(self.g_bg_fea), ptr(self.g_bg_flat), ptr(dw), ptr(db), B,
+              self.bg_flat, cfg.part_z * 4)
+        p.add("pack_f32", ptr(self.g_bg_flat), hn * rn, hn * rn, self.bg_pyr.g_y[rn - 1].ref())
+        self.bg_pyr.backward(self, p)
+        # g_xs = g_crop (already * m) + g_xbg * (1 - m)      (models.py:402-403)
+        p.add("mask_split", self.bg_pyr.g_in.ref(), ptr(self.fg_mask), None, self.g_xbg_s.ref())
+        p.add("ew_combine", self.g_xs.ref(), self.g_xbg_s.ref(), None, None, ptr(self.g_crop), hn, None, 0.0, 0)
+        p.add("ew_combine", self.g_xs_m.ref(), self.g_xs.ref(), None, None, None, 0, ptr(self.me2), 0.0, 0)
+        e0, e1, e2 = self.conv[self.n_e0], self.conv[self.n_e1], self.conv[self.n_e2]
+        self.conv_wgrad(p, e2, self.e1, self.g_xs_m)
+        self.conv_dgrad(p, e2, self.g_xs_m, H, W, out_masked=self.g_e1, mask_in=self.me1)
+        self.conv_wgrad(p, e1, self.e0, self.g_e1)
+        self.conv_dgrad(p, e1, self.g_e1, H, W, out_masked=self.g_e0, mask_in=self.me0, addend=self.g_xs)
+        p.add("unpack_f32", self.g_e0.ref(), ptr(self.g_e0_f32), hn)
+        p.add("conv2d_small_bwd_filter", ptr(self.x), B, H, W, 3, ptr(self.g_e0_f32), 3, 3, 1, hn, ptr(e0.dw))
+        p.add("bias_grad_f32", ptr(self.g_e0_f32), B * H * W, hn, ptr(e0.db))
+
+    def _prog_disc_forward(self, p, dp, img):
+        cfg = self.cfg
+        H, W, d, n = cfg.img_h, cfg.img_w, cfg.d_dim, dp.n
+        l1 = self.conv[self.n_d[0]]
+        p.add("conv2d_small_fwd", ptr(img), n, H, W, 3, ptr(l1.w), ptr(l1.b), 5, 5, 2, d, ACT_LRELU, 0.2, dp.h[0].ref(),
+              None, ptr(dp.m[0]))
+        for i in (1, 2, 3):
+            layer = self.conv[self.n_d[i]]
+            hh, ww, c = H >> (i + 1), W >> (i + 1), d << i
+            self.conv_fwd(p, layer, dp.h[i - 1], act=ACT_NONE, out_f32=dp.pre[i], out_f32_ps=c)
+            p.add("norm_stats", ptr(dp.pre[i]), n, hh, ww, c, self.norm_mode, ptr(dp.sums[i]))
+            count = float(hh * ww * c) if self.norm_mode == NORM_LAYER else float(n * hh * ww * self.world)
+            if self.norm_mode == NORM_BATCH and self.dist is not None:
+                p.add_py(lambda s, t=dp.sums[i]: self.dist.all_reduce_sum(t))
+            sc = self.dp.view("Discriminator.BN%d.scale" % (i + 1))
+            of = self.dp.view("Discriminator.BN%d.offset" % (i + 1))
+            p.add("norm_act_fwd", ptr(dp.pre[i]), n, hh, ww, c, self.norm_mode, 1e-5, ptr(dp.sums[i]), count, ptr(sc),
+                  ptr(of), ACT_LRELU, 0.2, ptr(dp.stats[i]), dp.h[i].ref(), ptr(dp.m[i]))
+        p.add("unpack_f32", dp.h[3].ref(), ptr(dp.flat), d * 8)
+        w = self.dp.view("Discriminator.Output.W")
+        b = self.dp.view("Discriminator.Output.b")
+        p.add("linear_fwd", ptr(dp.flat), ptr(w), ptr(b), ptr(dp.logits), n, self.d_flat, 1, ACT_NONE, 0.0)
+
+    def _prog_disc_backward(self, p, dp, img, params, data):
+        """dp.dlogits -> parameter grads (params=True) and/or the gradient w.r.t. the input image (data=True)."""
+        cfg = self.cfg
+        H, W, d, n = cfg.img_h, cfg.img_w, cfg.d_dim, dp.n
+        w = self.dp.view("Discriminator.Output.W")
+        dw = self.dp.gview("Discriminator.Output.W")
+        db = self.dp.gview("Discriminator.Output.b")
+        p.add("linear_bwd", ptr(dp.flat), ptr(w), ptr(dp.dlogits), ptr(dp.g_flat), ptr(dw) if params else None,
+              ptr(db) if params else None, n, self.d_flat, 1)
+        p.add("pack_f32", ptr(dp.g_flat), d * 8, d * 8, dp.g_h[3].ref())
+        for i in (3, 2, 1):
+            layer = self.conv[self.n_d[i]]
+            hh, ww, c = H >> (i + 1), W >> (i + 1), d << i
+            sc = self.dp.view("Discriminator.BN%d.scale" % (i + 1))
+            dsc = self.dp.gview("Discriminator.BN%d.scale" % (i + 1))
+            dof = self.dp.gview("Discriminator.BN%d.offset" % (i + 1))
+            count = float(hh * ww * c) if self.norm_mode == NORM_LAYER else float(n * hh * ww * self.world)
+            p.add("norm_act_bwd_reduce", dp.g_h[i].ref(), ptr(dp.pre[i]), ptr(dp.stats[i]), ptr(dp.m[i]), 0.2,
+                  self.norm_mode, ptr(sc), ptr(dp.red[i]), ptr(dsc) if params else None, ptr(dof) if params else None)
+            if self.norm_mode == NORM_BATCH and self.dist is not None:
+                p.add_py(lambda s, t=dp.red[i]: self.dist.all_reduce_sum(t))
+            p.add("norm_act_bwd_apply", dp.g_h[i].ref(), ptr(dp.pre[i]), ptr(dp.stats[i]), ptr(dp.m[i]), 0.2,
+                  self.norm_mode, ptr(sc), ptr(dp.red[i]), count, dp.g_pre[i].ref())
+            if params:
+                self.conv_wgrad(p, layer, dp.h[i - 1], dp.g_pre[i])
+            if i > 1:
+                self.conv_dgrad(p, layer, dp.g_pre[i], hh * 2, ww * 2, out=dp.g_h[i - 1])
+            else:
+                # layer-1 output is a plain LeakyReLU: emit the masked gradient wrt its conv output
+                self.conv_dgrad(p, layer, dp.g_pre[i], hh * 2, ww * 2, out_masked=dp.g_pre[0], mask_in=dp.m[0],
+                                mask_neg=0.2)
+        l1 = self.conv[self.n_d[0]]
+        p.add("unpack_f32", dp.g_pre[0].ref(), ptr(dp.g_pre1_f32), d)
+        if params:
+            p.add("conv2d_small_bwd_filter", ptr(img), n, H, W, 3, ptr(dp.g_pre1_f32), 5, 5, 2, d, ptr(l1.dw))
+            p.add("bias_grad_f32", ptr(dp.g_pre1_f32), n * (H // 2) * (W // 2), d, ptr(l1.db))
+        if data:
+            p.add("conv2d_small_bwd_data", ptr(dp.g_pre1_f32), n, H // 2, W // 2, d, ptr(l1.w), 5, 5, 2, H, W, 3,
+                  ptr(dp.g_x))
+
+    # -------------------------------------------------------------------------------- stepping
+    def set_batch(self, batch, non_blocking=True):
+        """Host -> device copy of one batch (dict of numpy arrays / pinned torch tensors as produced by
+        synth.make_batch / the input pipeline): x, pose_rcv, mask, part_bbox, part_vis."""
+        cfg, B, P = self.cfg, self.B, self.cfg.n_parts
+
+        def dev(a, dtype=torch.float32):
+            t = a if isinstance(a, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(a))
+            return t.to(self.device, dtype, non_blocking=non_blocking)
+
+        self.x.copy_(dev(batch["x"]))
+        self.pose_rcv.copy_(dev(batch["pose_rcv"]))
+        self.fg_mask.copy_(dev(batch["mask"]).reshape(B, cfg.img_h, cfg.img_w))
+        bb = dev(batch["part_bbox"])[:, :P, :]                      # [B,P,4] pixels (y1,x1,y2,x2)
+        scale = torch.tensor([cfg.img_h, cfg.img_w, cfg.img_h, cfg.img_w], dtype=torch.float32, device=self.device)
+        self.boxes.copy_((bb / scale).permute(1, 0, 2).reshape(P * B, 4))   # ROI i of image b -> row i*B+b
+        self.vis.copy_(dev(batch["part_vis"])[:, :P])
+
+    def forward(self, with_disc=True):
+        """Encoder + U-Net (+ D on x and G) forward; returns nothing (results stay in HBM)."""
+        s = torch.cuda.current_stream().cuda_stream
+        self.p_fwd_gen.run(s)
+        if with_disc:
+            self.p_d_real_fwd.run(s)
+            self.p_d_fake_fwd.run(s)
+            self.ctx.loss_gan(self.gan_mode, ptr(self.d_real.logits), ptr(self.d_fake.logits), self.B, ptr(self.loss_gan),
+                              None, None, None, s)
+            self.ctx.loss_l1(ptr(self.G), ptr(self.x), self.G.numel(), 20.0, ptr(self.loss_l1), None, s)
+
+    def _optim(self, which, s):
+        grp = self.gp if which == "g" else self.dp
+        lr = self.g_lr if which == "g" else self.d_lr
+        if self.dist is not None:
+            self.dist.all_reduce_sum(grp.grad)
+        gs = 1.0 / self.world
+        self.t[which] += 1
+        if self.mode in ("wgan", "lsgan"):
+            clip = 0.01 if (self.mode == "wgan" and which == "d") else 0.0
+            self.ctx.rmsprop_step(ptr(grp.value), ptr(grp.grad), ptr(grp.v), grp.total, lr, 0.9, 1e-10, gs, clip, s)
+        else:
+            b2 = 0.9 if self.mode == "wgan-gp" else 0.999
+            self.ctx.adam_step(ptr(grp.value), ptr(grp.grad), ptr(grp.m), ptr(grp.v), grp.total, lr, 0.5, b2, 1e-8,
+                               self.t[which], gs, s)
+        self.pack_weights(which, s)
+
+    def g_grads(self):
+        """Forward + backward of g_loss = gan(D(G)) + 20*L1 w.r.t. Encoder+G (trainer.py:605-607, 622-624)."""
+        s = torch.cuda.current_stream().cuda_stream
+        self.gp.grad.zero_()
+        self.p_fwd_gen.run(s)
+        self.p_d_fake_fwd.run(s)
+        self.ctx.loss_gan(self.gan_mode, None, ptr(self.d_fake.logits), self.B, ptr(self.loss_gan),
+                          ptr(self.d_fake.dlogits), None, None, s)
+        if self.world > 1:
+            pass  # batch-mean losses: per-rank grads are means over the local shard; summed then scaled by 1/world
+        self.p_d_fake_bwd_data.run(s)
+        self.g_G.copy_(self.d_fake.g_x)
+        self.ctx.loss_l1(ptr(self.G), ptr(self.x), self.G.numel(), 20.0, ptr(self.loss_l1), ptr(self.g_G), s)
+        self.p_bwd_gen.run(s)
+
+    def d_grads(self):
+        """Forward + backward of d_loss w.r.t. the discriminator (trainer.py:601-605, 625)."""
+        s = torch.cuda.current_stream().cuda_stream
+        self.dp.grad.zero_()
+        self.p_fwd_gen.run(s)
+        self.p_d_real_fwd.run(s)
+        self.p_d_fake_fwd.run(s)
+        self.ctx.loss_gan(self.gan_mode, ptr(self.d_real.logits), ptr(self.d_fake.logits), self.B, ptr(self.loss_gan),
+                          None, ptr(self.d_real.dlogits), ptr(self.d_fake.dlogits), s)
+        self.p_d_real_bwd_par.run(s)
+        self.p_d_fake_bwd_par.run(s)
+
+    def g_step(self):
+        self.g_grads()
+        self._optim("g", torch.cuda.current_stream().cuda_stream)
+
+    def d_step(self):
+        self.d_grads()
+        self._optim("d", torch.cuda.current_stream().cuda_stream)
+
+    def losses(self):
+        """(g_gan, d_loss, L1) as Python floats -- a device->host read."""
+        lg = self.loss_gan.cpu()
+        return float(lg[0]), float(lg[1]), float(self.loss_l1.cpu()[0])

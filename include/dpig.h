@@ -161,6 +161,12 @@ int dpig_broadcast_embedding(dpig_ctx* ctx, const float* emb, int32_t ce, const 
 /* g_emb[n,c] = sum over pixels of g[n,y,x,c] (gradient of the broadcast). */
 int dpig_spatial_sum(dpig_ctx* ctx, const dpig_tensor* g, float* out, dpig_stream stream);
 
+/* emb[b, i*part_z + j] = fea[i*batch + b, j] * vis[b, i]  (i < parts), emb[b, parts*part_z + j] = bg[b, j]
+ * (models.py:433-442, 467-468).  backward=1: fea/bg receive the gradient held in emb. */
+int dpig_embedding_assemble(dpig_ctx* ctx, float* fea, float* bg, const float* vis, int32_t batch,
+                            int32_t parts, int32_t part_z, int32_t bg_z, float* emb, int32_t backward,
+                            dpig_stream stream);
+
 /* ---- tf.image.crop_and_resize (models.py:350,415), bilinear, extrapolation 0 ------------------ */
 /* boxes: fp32 [nbox][4] = (y1,x1,y2,x2) normalised as in the reference (pixel / H, pixel / W);
  * box_ind: int32 [nbox]; mask (optional fp32 [n,h,w]) multiplies the image on the fly (x_fg). */
