@@ -171,24 +171,52 @@ __global__ void spatial_sum_kernel(TView g, float* out, int C, long long pix_per
   }
 }
 
-// db[c] += sum over pixels.  grid = chunks of pixels; block threads stride over channels.
-__global__ void bias_grad_kernel(TView g, const float* f32, long long f32_ps, float* db, int C,
-                                 long long pixels, int chunk) {
+// db[c] += sum over pixels.  256 threads = (C/8 channel groups) x (rows of pixels); each thread streams
+// 16-byte (8-channel) loads down its pixel rows, rows are combined through shared memory, then one fp32
+// atomic per channel per block.  HBM-bound: reads every gradient element exactly once.
+__global__ void __launch_bounds__(256)
+bias_grad_kernel(TView g, const float* f32, long long f32_ps, float* db, int C, long long pixels, int chunk) {
+  __shared__ float sh[256][8];
+  const int C8 = (C + 7) / 8;
+  const int groups = C8 < 256 ? C8 : 256;     // channel groups handled per pass
+  const int rows = 256 / groups;
+  const int cg = threadIdx.x % groups, prow = threadIdx.x / groups;
   const long long p0 = static_cast<long long>(blockIdx.x) * chunk;
   const long long p1 = min(p0 + chunk, pixels);
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    float acc = 0.f;
-    for (long long p = p0; p < p1; ++p) {
-      if (f32) {
-        acc += __ldg(f32 + p * f32_ps + c);
-      } else {
-        const long long off = p * g.ps + c;
-        float v = __bfloat162float(g.hi[off]);
-        if (g.lo) v += __bfloat162float(g.lo[off]);
-        acc += v;
+  for (int cg0 = 0; cg0 < C8; cg0 += groups) {
+    const int ch = (cg0 + cg) * 8;
+    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (prow < rows && ch < C) {
+      for (long long p = p0 + prow; p < p1; p += rows) {
+        if (f32) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            if (ch + j < C) acc[j] += __ldg(f32 + p * f32_ps + ch + j);
+        } else if (ch + 8 <= C && (g.ps % 8 == 0)) {
+          load8(g.hi, g.lo, p * g.ps + ch, acc, true);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            if (ch + j < C) {
+              float v = __bfloat162float(g.hi[p * g.ps + ch + j]);
+              if (g.lo) v += __bfloat162float(g.lo[p * g.ps + ch + j]);
+              acc[j] += v;
+            }
+        }
       }
     }
-    atomicAdd(db + c, acc);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) sh[threadIdx.x][j] = acc[j];
+    __syncthreads();
+    if (prow == 0 && ch < C) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float s = 0.f;
+        for (int r = 0; r < rows; ++r) s += sh[r * groups + cg][j];
+        if (ch + j < C) atomicAdd(db + ch + j, s);
+      }
+    }
+    __syncthreads();
   }
 }
 

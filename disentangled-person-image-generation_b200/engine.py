@@ -67,10 +67,11 @@ class ParamGroup:
 class ConvLayer:
     """One convolution: fp32 HWIO master inside a ParamGroup + packed bf16 operand copies."""
 
-    def __init__(self, group, wname, bname, k, stride, cin, cout, device, need_bwd=True, small=False):
+    def __init__(self, group, wname, bname, k, stride, cin, cout, device, need_bwd=True, small=False, cin_pad=None):
         self.group, self.wname, self.bname = group, wname, bname
         self.k, self.stride, self.cin, self.cout = k, stride, cin, cout
-        self.cin_pad, self.cout_pad = _pad8(cin), _pad8(cout)
+        # cin_pad must equal the channel count of the activation buffer the layer reads (zero-padded)
+        self.cin_pad, self.cout_pad = (cin_pad or _pad8(cin)), _pad8(cout)
         self.small = small  # CUDA-core path (3-channel input): no packed copies
         taps = k * k
         if not small:
@@ -102,20 +103,29 @@ class Program:
         self.calls = []
         self.keep = []  # keeps ctypes structs / tensors referenced by the frozen arguments alive
 
-    def add(self, name, *args):
+    def add(self, name, *args, flops=0.0, tag=""):
         fn = getattr(self.ctx.lib, "dpig_" + name)
-        self.calls.append((name, fn, args))
+        self.calls.append((name, fn, args, flops, tag))
 
     def add_py(self, fn):
-        self.calls.append((None, fn, None))
+        self.calls.append((None, fn, None, 0.0, ""))
 
-    def run(self, stream):
+    def run(self, stream, timings=None):
+        """timings: optional list; when given, every C-ABI call is bracketed by CUDA events on the
+        launching stream and (name, algorithmic_flops, start_event, end_event) is appended."""
         h = self.ctx.handle
-        for name, fn, args in self.calls:
+        for name, fn, args, flops, tag in self.calls:
             if name is None:
                 fn(stream)
                 continue
+            if timings is not None:
+                e0 = torch.cuda.Event(enable_timing=True)
+                e1 = torch.cuda.Event(enable_timing=True)
+                e0.record()
             rc = fn(h, *args, stream)
+            if timings is not None:
+                e1.record()
+                timings.append((name, flops, e0, e1, tag))
             if rc != 0:
                 raise _lib.DpigError("dpig_%s failed (%d): %s" % (name, rc, self.ctx.last_error()))
 
@@ -222,7 +232,6 @@ class _DiscPass:
         self.g_flat = torch.zeros((n, flat), device=dev)
         self.g_h = [SplitTensor(n, H >> (i + 1), W >> (i + 1), d << i, dev) for i in range(4)]  # grad wrt activated
         self.g_pre = [SplitTensor(n, H >> (i + 1), W >> (i + 1), d << i, dev) for i in range(4)]  # grad wrt conv out
-        self.g_pre1_f32 = torch.zeros((n, H >> 1, W >> 1, d), device=dev)
         self.g_x = torch.zeros((n, H, W, 3), device=dev)
 
 
@@ -249,13 +258,14 @@ class Stage1Engine:
         gspecs, dspecs = [], []
         self.layers = OrderedDict()
 
-        def conv(group_specs, scope, counter, k, stride, cin, cout, small=False, need_bwd=True):
+        def conv(group_specs, scope, counter, k, stride, cin, cout, small=False, need_bwd=True, cin_pad=None):
             i = counter[0]
             counter[0] += 1
             name = "%s/Conv%s" % (scope, "" if i == 0 else "_%d" % i)
             group_specs.append((name + "/weights", (k, k, cin, cout)))
             group_specs.append((name + "/biases", (cout,)))
-            self.layers[name] = dict(k=k, stride=stride, cin=cin, cout=cout, small=small, need_bwd=need_bwd)
+            self.layers[name] = dict(k=k, stride=stride, cin=cin, cout=cout, small=small, need_bwd=need_bwd,
+                                     cin_pad=cin_pad)
             return name
 
         def fc(group_specs, scope, counter, cin, cout):
@@ -278,7 +288,7 @@ class Stage1Engine:
 
         # Encoder/G_encoder (models.py:390-471)
         sc, cc, fc_c = "Encoder/G_encoder", [0], [0]
-        self.n_e0 = conv(gspecs, sc, cc, 3, 1, 3, hn, small=True, need_bwd=False)
+        self.n_e0 = conv(gspecs, sc, cc, 3, 1, 3, hn, need_bwd=False)
         self.n_e1 = conv(gspecs, sc, cc, 3, 1, hn, hn)
         self.n_e2 = conv(gspecs, sc, cc, 3, 1, hn, hn)
         self.n_roi = pyramid(sc, cc)
@@ -292,7 +302,8 @@ class Stage1Engine:
         # ID_AE/G (models.py:518-576)
         sc, cc, fc_c = "ID_AE/G", [0], [0]
         self.gin_c = cfg.emb_dim + cfg.keypoints
-        self.n_gstem = conv(gspecs, sc, cc, 3, 1, self.gin_c, hn)
+        self.gin_cpad = (self.gin_c + 63) // 64 * 64
+        self.n_gstem = conv(gspecs, sc, cc, 3, 1, self.gin_c, hn, cin_pad=self.gin_cpad)
         self.n_genc = pyramid(sc, cc)
         self.n_gfc1 = fc(gspecs, sc, fc_c, self.bg_flat, cfg.z_num)
         self.n_gfc2 = fc(gspecs, sc, fc_c, cfg.z_num, self.fh * self.fw * hn)
@@ -321,7 +332,8 @@ class Stage1Engine:
             if i >= 1:
                 dspecs.append(("Discriminator.BN%d.offset" % (i + 1), (chans[i + 1],)))
                 dspecs.append(("Discriminator.BN%d.scale" % (i + 1), (chans[i + 1],)))
-            self.layers[name] = dict(k=5, stride=2, cin=chans[i], cout=chans[i + 1], small=(i == 0), need_bwd=True)
+            self.layers[name] = dict(k=5, stride=2, cin=chans[i], cout=chans[i + 1], small=False, need_bwd=True,
+                                     cin_pad=None)
             self.n_d.append(name)
         self.d_flat = (cfg.img_h // 16) * (cfg.img_w // 16) * 8 * d
         dspecs.append(("Discriminator.Output.W", (self.d_flat, 1)))
@@ -333,10 +345,10 @@ class Stage1Engine:
         for name, s in self.layers.items():
             if name.startswith("Discriminator"):
                 self.conv[name] = ConvLayer(self.dp, name + ".Filters", name + ".Biases", s["k"], s["stride"], s["cin"],
-                                            s["cout"], dev, s["need_bwd"], s["small"])
+                                            s["cout"], dev, s["need_bwd"], s["small"], s["cin_pad"])
             else:
                 self.conv[name] = ConvLayer(self.gp, name + "/weights", name + "/biases", s["k"], s["stride"], s["cin"],
-                                            s["cout"], dev, s["need_bwd"], s["small"])
+                                            s["cout"], dev, s["need_bwd"], s["small"], s["cin_pad"])
         # BN / LN scale defaults to one
         for i in (2, 3, 4):
             self.dp.view("Discriminator.BN%d.scale" % i).fill_(1.0)
@@ -389,6 +401,7 @@ class Stage1Engine:
         P = cfg.n_parts
         # inputs (device copies of one batch)
         self.x = torch.zeros((B, H, W, 3), device=dev)
+        self.x8 = SplitTensor(B, H, W, 8, dev, zero=True)   # image as a channel-padded split tensor (TMA operand)
         self.pose_rcv = torch.zeros((B, cfg.keypoints, 3), device=dev)
         self.fg_mask = torch.zeros((B, H, W), device=dev)
         self.boxes = torch.zeros((P * B, 4), device=dev)
@@ -411,7 +424,6 @@ class Stage1Engine:
         self.bg_fea = torch.zeros((B, cfg.part_z * 4), device=dev)
         self.emb = torch.zeros((B, cfg.emb_dim), device=dev)
         # generator
-        self.gin_cpad = (self.gin_c + 63) // 64 * 64
         self.gin = SplitTensor(B, H, W, self.gin_cpad, dev, zero=True)
         self.g0 = SplitTensor(B, H, W, hn, dev)
         self.mg0 = _mask(B * H * W, hn, dev)
@@ -442,6 +454,7 @@ class Stage1Engine:
             if idx < rn - 1:
                 self.dec_mu.append(_mask(B * hh * ww, self.dec_c[idx + 1][0], dev))
         self.G = torch.zeros((B, H, W, 3), device=dev)
+        self.G8 = SplitTensor(B, H, W, 8, dev, zero=True)
         # generator backward
         self.g_G = torch.zeros((B, H, W, 3), device=dev)
         self.g_G8 = SplitTensor(B, H, W, 8, dev, zero=True)
@@ -472,7 +485,6 @@ class Stage1Engine:
         self.g_xs_m = SplitTensor(B, H, W, hn, dev)
         self.g_e1 = SplitTensor(B, H, W, hn, dev)
         self.g_e0 = SplitTensor(B, H, W, hn, dev)
-        self.g_e0_f32 = torch.zeros((B, H, W, hn), device=dev)
         # discriminator passes
         self.d_real = _DiscPass(self, B)
         self.d_fake = _DiscPass(self, B)
@@ -510,16 +522,28 @@ class Stage1Engine:
                  out_f32_ps=0, upsample=1):
         ep = self._epilogue(prog, layer.b, act, alpha, addend, None, 0.0, mask_out, out, None, out_f32, out_f32_ps,
                             upsample)
-        prog.add("conv2d_fwd", x.ref(), ptr(layer.fwd[0]), ptr(layer.fwd[1]), layer.k, layer.k, layer.stride, layer.cout, ep)
+        assert x.c == layer.cin_pad, (layer.wname, x.c, layer.cin_pad)
+        oh, ow = -(-x.h // layer.stride), -(-x.w // layer.stride)
+        prog.add("conv2d_fwd", x.ref(), ptr(layer.fwd[0]), ptr(layer.fwd[1]), layer.k, layer.k, layer.stride, layer.cout, ep,
+                 flops=2.0 * x.n * oh * ow * layer.cout * layer.k * layer.k * layer.cin,
+                 tag="%s %dx%dx%dx%d->%d k%ds%d" % (layer.wname, x.n, x.h, x.w, layer.cin, layer.cout, layer.k, layer.stride))
 
-    def conv_dgrad(self, prog, layer, dy, in_h, in_w, out=None, out_masked=None, mask_in=None, mask_neg=0.0, addend=None):
-        ep = self._epilogue(prog, None, ACT_NONE, 0.0, addend, mask_in, mask_neg, None, out, out_masked, None, 0, 1)
+    def conv_dgrad(self, prog, layer, dy, in_h, in_w, out=None, out_masked=None, mask_in=None, mask_neg=0.0, addend=None,
+                   out_f32=None, out_f32_ps=0):
+        ep = self._epilogue(prog, None, ACT_NONE, 0.0, addend, mask_in, mask_neg, None, out, out_masked, out_f32,
+                            out_f32_ps, 1)
+        assert dy.c == layer.cout_pad, (layer.wname, dy.c, layer.cout_pad)
         prog.add("conv2d_bwd_data", dy.ref(), ptr(layer.bwd[0]), ptr(layer.bwd[1]), layer.k, layer.k, layer.stride,
-                 in_h, in_w, layer.cin, ep)
+                 in_h, in_w, layer.cin, ep, flops=2.0 * dy.n * dy.h * dy.w * layer.cout * layer.k * layer.k * layer.cin,
+                 tag="%s dy %dx%dx%dx%d->%d k%ds%d" % (layer.wname, dy.n, dy.h, dy.w, layer.cout, layer.cin, layer.k, layer.stride))
 
     def conv_wgrad(self, prog, layer, x, dy):
         prog.add("conv2d_bwd_filter", x.ref(), dy.ref(), layer.k, layer.k, layer.stride, layer.cin, layer.cout,
-                 ptr(layer.dw))
+                 ptr(layer.dw), flops=2.0 * dy.n * dy.h * dy.w * layer.cout * layer.k * layer.k * layer.cin,
+                 tag="%s %dx%dx%dx%d->%d k%ds%d" % (layer.wname, x.n, x.h, x.w, layer.cin, layer.cout, layer.k, layer.stride))
+        if dy.c != layer.cout:  # channel-padded gradient (e.g. the 3-channel image gradient held in 8)
+            dy = dy.slice(0, layer.cout)
+            prog.keep.append(dy)
         prog.add("bias_grad", dy.ref(), ptr(layer.db))
 
     def _linear(self, grp, name):
@@ -532,23 +556,23 @@ class Stage1Engine:
         self.p_bwd_gen = Program(self.ctx)     # g_G -> all Encoder+G parameter gradients
         self._prog_backward_generator(self.p_bwd_gen)
         self.p_d_fake_fwd = Program(self.ctx)
-        self._prog_disc_forward(self.p_d_fake_fwd, self.d_fake, self.G)
+        self._prog_disc_forward(self.p_d_fake_fwd, self.d_fake, self.G8)
         self.p_d_real_fwd = Program(self.ctx)
-        self._prog_disc_forward(self.p_d_real_fwd, self.d_real, self.x)
+        self._prog_disc_forward(self.p_d_real_fwd, self.d_real, self.x8)
         self.p_d_fake_bwd_data = Program(self.ctx)   # G step: gradient w.r.t. the generated image only
-        self._prog_disc_backward(self.p_d_fake_bwd_data, self.d_fake, self.G, params=False, data=True)
+        self._prog_disc_backward(self.p_d_fake_bwd_data, self.d_fake, self.G8, params=False, data=True)
         self.p_d_fake_bwd_par = Program(self.ctx)    # D step
-        self._prog_disc_backward(self.p_d_fake_bwd_par, self.d_fake, self.G, params=True, data=False)
+        self._prog_disc_backward(self.p_d_fake_bwd_par, self.d_fake, self.G8, params=True, data=False)
         self.p_d_real_bwd_par = Program(self.ctx)
-        self._prog_disc_backward(self.p_d_real_bwd_par, self.d_real, self.x, params=True, data=False)
+        self._prog_disc_backward(self.p_d_real_bwd_par, self.d_real, self.x8, params=True, data=False)
 
     def _prog_forward_generator(self, p):
         cfg, B = self.cfg, self.B
         H, W, hn, rn, P = cfg.img_h, cfg.img_w, cfg.hidden, cfg.repeat_num, cfg.n_parts
         e0, e1, e2 = self.conv[self.n_e0], self.conv[self.n_e1], self.conv[self.n_e2]
         # ---- encoder (models.py:396-471)
-        p.add("conv2d_small_fwd", ptr(self.x), B, H, W, 3, ptr(e0.w), ptr(e0.b), 3, 3, 1, hn, ACT_RELU, 0.0,
-              self.e0.ref(), None, ptr(self.me0))
+        p.add("pack_f32", ptr(self.x), 3, 3, self.x8.ref())
+        self.conv_fwd(p, e0, self.x8, out=self.e0, mask_out=self.me0)
         self.conv_fwd(p, e1, self.e0, out=self.e1, mask_out=self.me1)
         self.conv_fwd(p, e2, self.e1, out=self.xs, addend=self.e0, mask_out=self.me2)
         p.add("mask_split", self.xs.ref(), ptr(self.fg_mask), None, self.x_bg.ref())
@@ -597,7 +621,8 @@ class Stage1Engine:
                 up = self.cat[idx + 1].slice(0, self.dec_c[idx + 1][0])
                 self._keep.append(up)
                 self.conv_fwd(p, self.conv[names[2]], self.dec_y[idx], out=up, mask_out=self.dec_mu[idx], upsample=2)
-        self.conv_fwd(p, self.conv[self.n_gout], self.dec_y[rn - 1], act=ACT_NONE, out_f32=self.G, out_f32_ps=3)
+        self.conv_fwd(p, self.conv[self.n_gout], self.dec_y[rn - 1], act=ACT_NONE, out=self.G8, out_f32=self.G,
+                      out_f32_ps=3)
 
     def _prog_backward_generator(self, p):
         """Consumes self.g_G (fp32 grad wrt the generated image) and accumulates all Encoder+G param grads."""
@@ -679,16 +704,13 @@ class Stage1Engine:
         self.conv_dgrad(p, e2, self.g_xs_m, H, W, out_masked=self.g_e1, mask_in=self.me1)
         self.conv_wgrad(p, e1, self.e0, self.g_e1)
         self.conv_dgrad(p, e1, self.g_e1, H, W, out_masked=self.g_e0, mask_in=self.me0, addend=self.g_xs)
-        p.add("unpack_f32", self.g_e0.ref(), ptr(self.g_e0_f32), hn)
-        p.add("conv2d_small_bwd_filter", ptr(self.x), B, H, W, 3, ptr(self.g_e0_f32), 3, 3, 1, hn, ptr(e0.dw))
-        p.add("bias_grad_f32", ptr(self.g_e0_f32), B * H * W, hn, ptr(e0.db))
+        self.conv_wgrad(p, e0, self.x8, self.g_e0)
 
     def _prog_disc_forward(self, p, dp, img):
         cfg = self.cfg
         H, W, d, n = cfg.img_h, cfg.img_w, cfg.d_dim, dp.n
         l1 = self.conv[self.n_d[0]]
-        p.add("conv2d_small_fwd", ptr(img), n, H, W, 3, ptr(l1.w), ptr(l1.b), 5, 5, 2, d, ACT_LRELU, 0.2, dp.h[0].ref(),
-              None, ptr(dp.m[0]))
+        self.conv_fwd(p, l1, img, out=dp.h[0], act=ACT_LRELU, alpha=0.2, mask_out=dp.m[0])
         for i in (1, 2, 3):
             layer = self.conv[self.n_d[i]]
             hh, ww, c = H >> (i + 1), W >> (i + 1), d << i
@@ -738,13 +760,10 @@ class Stage1Engine:
                 self.conv_dgrad(p, layer, dp.g_pre[i], hh * 2, ww * 2, out_masked=dp.g_pre[0], mask_in=dp.m[0],
                                 mask_neg=0.2)
         l1 = self.conv[self.n_d[0]]
-        p.add("unpack_f32", dp.g_pre[0].ref(), ptr(dp.g_pre1_f32), d)
         if params:
-            p.add("conv2d_small_bwd_filter", ptr(img), n, H, W, 3, ptr(dp.g_pre1_f32), 5, 5, 2, d, ptr(l1.dw))
-            p.add("bias_grad_f32", ptr(dp.g_pre1_f32), n * (H // 2) * (W // 2), d, ptr(l1.db))
+            self.conv_wgrad(p, l1, img, dp.g_pre[0])
         if data:
-            p.add("conv2d_small_bwd_data", ptr(dp.g_pre1_f32), n, H // 2, W // 2, d, ptr(l1.w), 5, 5, 2, H, W, 3,
-                  ptr(dp.g_x))
+            self.conv_dgrad(p, l1, dp.g_pre[0], H, W, out_f32=dp.g_x, out_f32_ps=3)
 
     # -------------------------------------------------------------------------------- stepping
     def set_batch(self, batch, non_blocking=True):
@@ -791,42 +810,120 @@ class Stage1Engine:
                                self.t[which], gs, s)
         self.pack_weights(which, s)
 
-    def g_grads(self):
+    def g_grads(self, timings=None):
         """Forward + backward of g_loss = gan(D(G)) + 20*L1 w.r.t. Encoder+G (trainer.py:605-607, 622-624)."""
         s = torch.cuda.current_stream().cuda_stream
         self.gp.grad.zero_()
-        self.p_fwd_gen.run(s)
-        self.p_d_fake_fwd.run(s)
+        self.p_fwd_gen.run(s, timings)
+        self.p_d_fake_fwd.run(s, timings)
         self.ctx.loss_gan(self.gan_mode, None, ptr(self.d_fake.logits), self.B, ptr(self.loss_gan),
                           ptr(self.d_fake.dlogits), None, None, s)
         if self.world > 1:
             pass  # batch-mean losses: per-rank grads are means over the local shard; summed then scaled by 1/world
-        self.p_d_fake_bwd_data.run(s)
+        self.p_d_fake_bwd_data.run(s, timings)
         self.g_G.copy_(self.d_fake.g_x)
         self.ctx.loss_l1(ptr(self.G), ptr(self.x), self.G.numel(), 20.0, ptr(self.loss_l1), ptr(self.g_G), s)
-        self.p_bwd_gen.run(s)
+        self.p_bwd_gen.run(s, timings)
 
-    def d_grads(self):
+    def d_grads(self, timings=None):
         """Forward + backward of d_loss w.r.t. the discriminator (trainer.py:601-605, 625)."""
         s = torch.cuda.current_stream().cuda_stream
         self.dp.grad.zero_()
-        self.p_fwd_gen.run(s)
-        self.p_d_real_fwd.run(s)
-        self.p_d_fake_fwd.run(s)
+        self.p_fwd_gen.run(s, timings)
+        self.p_d_real_fwd.run(s, timings)
+        self.p_d_fake_fwd.run(s, timings)
         self.ctx.loss_gan(self.gan_mode, ptr(self.d_real.logits), ptr(self.d_fake.logits), self.B, ptr(self.loss_gan),
                           None, ptr(self.d_real.dlogits), ptr(self.d_fake.dlogits), s)
-        self.p_d_real_bwd_par.run(s)
-        self.p_d_fake_bwd_par.run(s)
+        self.p_d_real_bwd_par.run(s, timings)
+        self.p_d_fake_bwd_par.run(s, timings)
 
-    def g_step(self):
-        self.g_grads()
+    def g_step(self, timings=None):
+        self.g_grads(timings)
         self._optim("g", torch.cuda.current_stream().cuda_stream)
 
-    def d_step(self):
-        self.d_grads()
+    def d_step(self, timings=None):
+        self.d_grads(timings)
         self._optim("d", torch.cuda.current_stream().cuda_stream)
 
     def losses(self):
         """(g_gan, d_loss, L1) as Python floats -- a device->host read."""
         lg = self.loss_gan.cpu()
         return float(lg[0]), float(lg[1]), float(self.loss_l1.cpu()[0])
+
+
+def init_params(cfg, seed=1234):
+    """Random-init parameters with the reference's initialisers, keyed by TF variable name:
+    slim.conv2d / fully_connected -> xavier_uniform weights, zero biases (models.py:396 ff.);
+    discriminator convs / linear -> U(+-0.02*sqrt(3)) (wgan_gp.py:411-413, tflib/ops/conv2d.py:56-80),
+    zero biases, norm scale 1 / offset 0 (tflib/ops/batchnorm.py:23-24)."""
+    rng = np.random.default_rng(seed)
+    hn, rn = cfg.hidden, cfg.repeat_num
+    p = OrderedDict()
+
+    def xavier(shape, fan_in, fan_out):
+        lim = math.sqrt(6.0 / (fan_in + fan_out))
+        return rng.uniform(-lim, lim, size=shape).astype(np.float32)
+
+    class Scope:
+        def __init__(self, prefix):
+            self.prefix, self.nc, self.nf = prefix, 0, 0
+
+        def conv(self, k, cin, cout):
+            name = "%s/Conv%s" % (self.prefix, "" if self.nc == 0 else "_%d" % self.nc)
+            self.nc += 1
+            p[name + "/weights"] = xavier((k, k, cin, cout), k * k * cin, k * k * cout)
+            p[name + "/biases"] = np.zeros(cout, np.float32)
+
+        def fc(self, cin, cout):
+            name = "%s/fully_connected%s" % (self.prefix, "" if self.nf == 0 else "_%d" % self.nf)
+            self.nf += 1
+            p[name + "/weights"] = xavier((cin, cout), cin, cout)
+            p[name + "/biases"] = np.zeros(cout, np.float32)
+
+        def pyramid(self):
+            for idx in range(rn):
+                c = hn * (idx + 1)
+                self.conv(3, c, c)
+                self.conv(3, c, c)
+                if idx < rn - 1:
+                    self.conv(3, c, hn * (idx + 2))
+
+    fh, fw = cfg.img_h >> (rn - 1), cfg.img_w >> (rn - 1)
+    s = Scope("Encoder/G_encoder")
+    s.conv(3, 3, hn)
+    s.conv(3, hn, hn)
+    s.conv(3, hn, hn)
+    s.pyramid()
+    rf = cfg.roi_size >> (rn - 1)
+    s.fc(rf * rf * hn * rn, cfg.part_z)
+    s.pyramid()
+    s.fc(fh * fw * hn * rn, cfg.part_z * 4)
+    s = Scope("ID_AE/G")
+    s.conv(3, cfg.emb_dim + cfg.keypoints, hn)
+    s.pyramid()
+    s.fc(fh * fw * hn * rn, cfg.z_num)
+    s.fc(cfg.z_num, fh * fw * hn)
+    x_c = hn
+    for idx in range(rn):
+        c = x_c + hn * (rn - idx)
+        s.conv(3, c, c)
+        s.conv(3, c, c)
+        if idx < rn - 1:
+            x_c = hn * (rn - idx - 1)
+            s.conv(1, c, x_c)
+        else:
+            x_c = c
+    s.conv(3, x_c, 3)
+    d = cfg.d_dim
+    lim = 0.02 * math.sqrt(3.0)
+    chans = [3, d, 2 * d, 4 * d, 8 * d]
+    for i in range(4):
+        p["Discriminator.%d.Filters" % (i + 1)] = rng.uniform(-lim, lim, size=(5, 5, chans[i], chans[i + 1])).astype(np.float32)
+        p["Discriminator.%d.Biases" % (i + 1)] = np.zeros(chans[i + 1], np.float32)
+        if i >= 1:
+            p["Discriminator.BN%d.offset" % (i + 1)] = np.zeros(chans[i + 1], np.float32)
+            p["Discriminator.BN%d.scale" % (i + 1)] = np.ones(chans[i + 1], np.float32)
+    d_in = (cfg.img_h // 16) * (cfg.img_w // 16) * 8 * d
+    p["Discriminator.Output.W"] = rng.uniform(-lim, lim, size=(d_in, 1)).astype(np.float32)
+    p["Discriminator.Output.b"] = np.zeros(1, np.float32)
+    return p

@@ -167,18 +167,27 @@ class _Walker:
         return x @ self.p[name + "/weights"] + self.p[name + "/biases"]
 
 
-def _pyramid(w, x, hn, rn):
+def _tap(taps, name, t):
+    """Debug hook: record an intermediate (and keep its gradient) under `name`."""
+    if taps is not None:
+        if t.requires_grad:
+            t.retain_grad()
+        taps[name] = t
+    return t
+
+
+def _pyramid(w, x, hn, rn, taps=None, tag=""):
     for idx in range(rn):
         res = x
+        x = _tap(taps, "%s_a%d" % (tag, idx), w.conv(x))
         x = w.conv(x)
-        x = w.conv(x)
-        x = x + res
+        x = _tap(taps, "%s_y%d" % (tag, idx), x + res)
         if idx < rn - 1:
-            x = w.conv(x, stride=2)
+            x = _tap(taps, "%s_x%d" % (tag, idx + 1), w.conv(x, stride=2))
     return x
 
 
-def encoder_fgbg(p, cfg, x, fg_mask, roi_bbox, roi_vis):
+def encoder_fgbg(p, cfg, x, fg_mask, roi_bbox, roi_vis, taps=None):
     """models.py:390-471.  x [B,H,W,3]; fg_mask [B,H,W,1]; roi_bbox int [B,7,4] (y1,x1,y2,x2 pixels);
     roi_vis [B,7].  Returns the [B,352] embedding."""
     w = _Walker("Encoder/G_encoder", p)
@@ -187,27 +196,27 @@ def encoder_fgbg(p, cfg, x, fg_mask, roi_bbox, roi_vis):
     res = x
     x = w.conv(x)
     x = w.conv(x)
-    x = x + res
+    x = _tap(taps, "xs", x + res)
     x_fg = x * fg_mask
-    x_bg = x * (1.0 - fg_mask)
+    x_bg = _tap(taps, "x_bg", x * (1.0 - fg_mask))
     rois = []
     for i in range(cfg.n_parts):
         bb = roi_bbox[:, i, :].to(x.dtype)
         boxes = torch.stack([bb[:, 0] / float(H), bb[:, 1] / float(W), bb[:, 2] / float(H), bb[:, 3] / float(W)], dim=1)
         rois.append(T.crop_and_resize(x_fg, boxes, torch.arange(B), (cfg.roi_size, cfg.roi_size)))
-    body = torch.cat(rois, dim=0)
-    body = _pyramid(w, body, cfg.hidden, cfg.repeat_num)
+    body = _tap(taps, "rois", torch.cat(rois, dim=0))
+    body = _pyramid(w, body, cfg.hidden, cfg.repeat_num, taps, "roi")
     body = w.fc(body.reshape(body.shape[0], -1))
     feats = list(torch.split(body, B, dim=0))
     for i in range(cfg.n_parts):
         feats[i] = feats[i] * roi_vis[:, i:i + 1].to(x.dtype)
-    bg = _pyramid(w, x_bg, cfg.hidden, cfg.repeat_num)
+    bg = _pyramid(w, x_bg, cfg.hidden, cfg.repeat_num, taps, "bg")
     bg = w.fc(bg.reshape(B, -1))
     feats.append(bg)
     return torch.cat(feats, dim=-1)
 
 
-def unet_generator(p, cfg, emb, pose):
+def unet_generator(p, cfg, emb, pose, taps=None):
     """trainer.py:588-590 (spatial broadcast of the embedding) + models.py:518-576.
     emb [B,352]; pose [B,H,W,18].  Returns (G [B,H,W,3], z [B,z_num])."""
     w = _Walker("ID_AE/G", p)
@@ -216,29 +225,29 @@ def unet_generator(p, cfg, emb, pose):
     hn, rn = cfg.hidden, cfg.repeat_num
     emb_rep = emb[:, None, None, :].expand(B, H, W, emb.shape[1])
     x = torch.cat([emb_rep, pose], dim=3)
-    x = w.conv(x)
+    x = _tap(taps, "g0", w.conv(x))
     skips = []
     for idx in range(rn):
         res = x
+        x = _tap(taps, "genc_a%d" % idx, w.conv(x))
         x = w.conv(x)
-        x = w.conv(x)
-        x = x + res
+        x = _tap(taps, "genc_y%d" % idx, x + res)
         skips.append(x)
         if idx < rn - 1:
-            x = w.conv(x, stride=2)
+            x = _tap(taps, "genc_x%d" % (idx + 1), w.conv(x, stride=2))
     sh = x.shape
     z = x = w.fc(x.reshape(B, -1))
     x = w.fc(z).reshape(B, sh[1], sh[2], hn)
     for idx in range(rn):
-        x = torch.cat([x, skips[rn - 1 - idx]], dim=-1)
+        x = _tap(taps, "cat%d" % idx, torch.cat([x, skips[rn - 1 - idx]], dim=-1))
         res = x
+        x = _tap(taps, "dec_a%d" % idx, w.conv(x))
         x = w.conv(x)
-        x = w.conv(x)
-        x = x + res
+        x = _tap(taps, "dec_y%d" % idx, x + res)
         if idx < rn - 1:
             x = T.upscale2(x)
             x = w.conv(x)  # 1x1 (the walker reads the kernel size off the weights)
-    out = w.conv(x, act=False)
+    out = _tap(taps, "G", w.conv(x, act=False))
     return out, z
 
 
@@ -278,12 +287,12 @@ def gaussian_fc_res(p, z, repeat_num=4, prefix="G_FC", act=torch.relu):
 
 
 # --------------------------------------------------------------------------------- Stage-I model
-def stage1_forward(p, cfg, batch, mode="dcgan", gp_alpha=None, lam=10.0):
+def stage1_forward(p, cfg, batch, mode="dcgan", gp_alpha=None, lam=10.0, taps=None):
     """build_model of --model=1 (trainer.py:568-625).  batch: dict x, pose, mask, part_bbox, part_vis.
     Returns dict with emb, z, G, D_real, D_fake, g_loss (incl. 20*L1), d_loss, L1."""
     x = batch["x"]
-    emb = encoder_fgbg(p, cfg, x, batch["mask"], batch["part_bbox"], batch["part_vis"])
-    G, z = unet_generator(p, cfg, emb, batch["pose"])
+    emb = encoder_fgbg(p, cfg, x, batch["mask"], batch["part_bbox"], batch["part_vis"], taps)
+    G, z = unet_generator(p, cfg, emb, batch["pose"], taps)
     d_real = dcgan_discriminator(p, cfg, x, mode)
     d_fake = dcgan_discriminator(p, cfg, G, mode)
     g_gan, d_loss = T.gan_loss(mode, d_real, d_fake)
