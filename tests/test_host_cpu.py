@@ -1,0 +1,143 @@
+"""CPU tests (no GPU): golden-vector regression of the oracle, the C-ABI surface of libdpig.so, host-side
+logic shared by engine / oracle, and the data-parallel plumbing on gloo with world_size 2."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+
+
+def test_oracle_reproduces_golden_small():
+    import make_golden
+    got = make_golden.compute(make_golden.SMALL, 2)
+    ref = np.load(os.path.join(ROOT, "tests", "golden", "stage1_small_b2.npz"))
+    for k in ("emb", "z", "G", "D_real", "D_fake", "L1", "g_loss", "d_loss"):
+        assert np.abs(got[k] - ref[k]).max() < 1e-6, k
+    assert np.array_equal(got["pose"], ref["pose"])
+
+
+def test_library_builds_and_exports_every_declared_symbol():
+    """include/dpig.h is the contract: every `int dpig_*(` / `const char* dpig_*(` declared there must be an
+    exported symbol of libdpig.so and be bound in _lib.py.  No compute calls (no GPU here)."""
+    import __graft_entry__
+    lib_path = __graft_entry__.build()
+    hdr = open(os.path.join(ROOT, "include", "dpig.h")).read()
+    declared = set(re.findall(r"\b(dpig_[a-z0-9_]+)\s*\(", hdr))
+    declared -= {"dpig_tensor", "dpig_conv_epilogue"}
+    lib = ctypes.CDLL(lib_path)
+    for name in sorted(declared):
+        assert hasattr(lib, name), "libdpig.so does not export %s" % name
+    from dpig_b200 import _lib
+    assert declared == set(_lib.EXPORTS), declared ^ set(_lib.EXPORTS)
+    # product path must fail loudly without a device (no CPU fallback)
+    if not torch.cuda.is_available():
+        with pytest.raises(_lib.DpigError):
+            _lib.Context(0)
+
+
+def test_struct_layouts_match_header(tmp_path):
+    """ctypes mirrors of dpig_tensor / dpig_conv_epilogue must have the C compiler's layout of include/dpig.h."""
+    from dpig_b200 import _lib
+    src = tmp_path / "sz.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "%s"\n'
+                   'int main(){printf("%%zu %%zu %%zu %%zu %%zu %%zu\\n", sizeof(dpig_tensor), offsetof(dpig_tensor,pix_stride),'
+                   ' sizeof(dpig_conv_epilogue), offsetof(dpig_conv_epilogue,mask_neg), offsetof(dpig_conv_epilogue,out_f32),'
+                   ' offsetof(dpig_conv_epilogue,upsample)); return 0;}\n' % os.path.join(ROOT, "include", "dpig.h"))
+    exe = tmp_path / "sz"
+    subprocess.check_call(["gcc", str(src), "-o", str(exe)])
+    c = [int(v) for v in subprocess.check_output([str(exe)]).split()]
+    py = [ctypes.sizeof(_lib.Tensor), _lib.Tensor.pix_stride.offset, ctypes.sizeof(_lib.ConvEpilogue),
+          _lib.ConvEpilogue.mask_neg.offset, _lib.ConvEpilogue.out_f32.offset, _lib.ConvEpilogue.upsample.offset]
+    assert c == py, (c, py)
+
+
+def test_engine_and_oracle_agree_on_parameter_names_and_shapes():
+    from dpig_b200 import engine
+    from oracle import nets
+    for kw in (dict(), dict(img_h=32, img_w=16, hidden=64, roi_size=12)):
+        a = engine.init_params(engine.NetConfig(**kw))
+        b = nets.init_params(nets.NetConfig(**kw))
+        assert list(a.keys()) == list(b.keys())
+        assert all(a[k].shape == b[k].shape for k in a)
+    p = engine.init_params(engine.NetConfig())
+    w = p["ID_AE/G/Conv_5/weights"]
+    lim = np.sqrt(6.0 / (9 * w.shape[2] + 9 * w.shape[3]))       # slim xavier_uniform
+    assert np.abs(w).max() <= lim and np.abs(w).max() > 0.95 * lim
+    assert np.abs(p["Discriminator.2.Filters"]).max() <= 0.02 * np.sqrt(3.0) + 1e-7
+
+
+def test_synthetic_batch_shapes_and_box_rule():
+    from dpig_b200 import synth
+    b = synth.make_batch(3, 128, 64, seed=7)
+    assert b["x"].shape == (3, 128, 64, 3) and b["mask"].shape == (3, 128, 64, 1)
+    assert b["part_bbox"].shape == (3, 37, 4) and b["part_vis"].shape == (3, 37)
+    assert 0.2 < b["mask"].mean() < 0.5
+    bb = b["part_bbox"]
+    assert (bb[..., 0] <= bb[..., 2]).all() and (bb[..., 2] <= 127).all() and (bb[..., 3] <= 63).all()
+    # invisible part -> [0,0,1,1] (convert_market.py:699-702)
+    rcv = b["pose_rcv"].copy()
+    rcv[:, :, 2] = 0
+    bb0, v0 = synth.part_boxes(rcv, 128, 64)
+    assert (bb0 == np.array([0, 0, 1, 1])).all() and (v0 == 0).all()
+
+
+def test_sync_batchnorm_from_shard_sums_equals_global_batch():
+    """The sync-BN hook all-reduces raw (sum x, sum x^2): check that statistic algebra against the oracle's
+    global-batch BatchNorm (tflib/ops/batchnorm.py:29-30)."""
+    from oracle import tf_ops as T
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn((4, 8, 4, 16), generator=g, dtype=torch.float64)
+    sc, of = torch.rand(16, generator=g, dtype=torch.float64) + 0.5, torch.randn(16, generator=g, dtype=torch.float64)
+    ref = T.batchnorm_train(x, sc, of)
+    shards = [x[:2], x[2:]]
+    s1 = sum(s.sum(dim=(0, 1, 2)) for s in shards)
+    s2 = sum((s * s).sum(dim=(0, 1, 2)) for s in shards)
+    cnt = x.numel() / 16
+    mean, var = s1 / cnt, s2 / cnt - (s1 / cnt) ** 2
+    got = torch.cat([(s - mean) * torch.rsqrt(var + 1e-5) * sc + of for s in shards])
+    assert (got - ref).abs().max() < 1e-10
+
+
+_WORKER = r'''
+import os, sys, torch
+sys.path.insert(0, %r)
+from dpig_b200 import ddp
+d = ddp.Dist(backend="gloo")
+t = torch.full((5,), float(d.rank + 1), dtype=torch.float64)
+d.all_reduce_sum(t)
+assert torch.equal(t, torch.full((5,), 3.0, dtype=torch.float64)), t
+m = torch.tensor([float(d.rank)])
+d.all_reduce_max(m)
+assert float(m) == 1.0
+# data-parallel gradient == global-batch gradient: mean loss over the global batch
+w = torch.arange(4, dtype=torch.float64)
+x = torch.arange(24, dtype=torch.float64).reshape(6, 4) / 10.0
+sh = ddp.shard({"x": x.numpy()}, d.rank, d.world_size)["x"]
+g_local = torch.tensor(sh).mean(dim=0)            # grad of mean(x @ w) over the local shard
+d.all_reduce_sum(g_local)
+g_local /= d.world_size
+assert torch.allclose(g_local, x.mean(dim=0)), (g_local, x.mean(dim=0))
+d.barrier()
+print("rank", d.rank, "ok")
+'''
+
+
+def test_ddp_plumbing_gloo_world2(tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(_WORKER % ROOT)
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29533", WORLD_SIZE="2", CUDA_VISIBLE_DEVICES="")
+    procs = []
+    for r in range(2):
+        e = dict(env, RANK=str(r), LOCAL_RANK=str(r))
+        procs.append(subprocess.Popen([sys.executable, str(script)], env=e, stdout=subprocess.PIPE, stderr=subprocess.STDOUT))
+    outs = [p.communicate(timeout=240)[0].decode() for p in procs]
+    assert all(p.returncode == 0 for p in procs), outs
+    assert all("ok" in o for o in outs), outs
