@@ -70,6 +70,8 @@ _SIGNATURES = {
     "dpig_norm_act_fwd": [_P, _I, _I, _I, _I, _I, _F, _P, _D, _P, _P, _I, _F, _P, _T, _P, _P],
     "dpig_norm_act_bwd_reduce": [_T, _P, _P, _P, _F, _I, _P, _P, _P, _P, _P],
     "dpig_norm_act_bwd_apply": [_T, _P, _P, _P, _F, _I, _P, _P, _D, _T, _P],
+    "dpig_layernorm_jvp_fwd": [_P, _P, _I, _I, _I, _I, _P, _P, _P, _F, _P, _T, _P],
+    "dpig_layernorm_jvp_bwd": [_T, _P, _F, _P, _P, _P, _P, _P, _P, _P, _T, _P, _P],
     "dpig_loss_l1": [_P, _P, _L, _F, _P, _P, _P],
     "dpig_loss_gan": [_I, _P, _P, _I, _P, _P, _P, _P, _P],
     "dpig_gp_interpolate": [_P, _P, _P, _I, _L, _P, _P],

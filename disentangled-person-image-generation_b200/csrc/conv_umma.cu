@@ -110,6 +110,9 @@ __device__ __forceinline__ void store_split32(__nv_bfloat16* hi, __nv_bfloat16* 
   }
 }
 
+// Persistent: grid = min(#tiles, #SMs); CTA b processes tiles b, b+grid, ...  The smem pipeline runs
+// continuously across tiles and the fp32 accumulator is double-buffered in TMEM (2 x block_n columns), so
+// the epilogue of tile j overlaps the MMAs of tile j+1.
 __global__ void __launch_bounds__(192, 1)
 conv_umma_kernel(const __grid_constant__ ConvUmmaParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -118,42 +121,40 @@ conv_umma_kernel(const __grid_constant__ ConvUmmaParams p) {
   const uint32_t stage_bytes = p.planes * (kABytes + p.b_bytes);
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + p.stages * stage_bytes);
   uint64_t* empty = full + p.stages;
-  uint64_t* tmem_full = empty + p.stages;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+  uint64_t* tmem_full = empty + p.stages;   // [2]
+  uint64_t* tmem_empty = tmem_full + 2;     // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-
-  // tile coordinates
-  const int tw = blockIdx.x % p.tiles_w;
-  const int th = (blockIdx.x / p.tiles_w) % p.tiles_h;
-  const int tn = blockIdx.x / (p.tiles_w * p.tiles_h);
-  const int w0 = tw * p.BW, h0 = th * p.BH, n0 = tn * p.BN;
-  const int nt = blockIdx.y;
+  const int pix_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
+  const int n_tiles = (p.cout + p.block_n - 1) / p.block_n;
+  const int total_tiles = pix_tiles * n_tiles;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.stages; ++s) {
       ptx::mbar_init(&full[s], 1);
       ptx::mbar_init(&empty[s], 1);
     }
-    ptx::mbar_init(tmem_full, 1);
+    for (int a = 0; a < 2; ++a) {
+      ptx::mbar_init(&tmem_full[a], 1);
+      ptx::mbar_init(&tmem_empty[a], 4);  // one arrive per epilogue warp
+    }
     ptx::fence_barrier_init();
   }
   if (warp == 1) {
-    // power-of-two column count >= block_n
-    switch (p.tmem_cols) {
-      case 32: ptx::tmem_alloc<32>(tmem_slot); break;
+    switch (p.tmem_cols) {  // power of two >= 2 * block_n
       case 64: ptx::tmem_alloc<64>(tmem_slot); break;
       case 128: ptx::tmem_alloc<128>(tmem_slot); break;
-      default: ptx::tmem_alloc<256>(tmem_slot); break;
+      case 256: ptx::tmem_alloc<256>(tmem_slot); break;
+      default: ptx::tmem_alloc<512>(tmem_slot); break;
     }
   }
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-
-  const int total_steps = p.num_taps * p.kchunks;
+  const int steps_per_tile = p.num_taps * p.kchunks;
 
   if (warp == 0) {
     if (lane == 0) {
@@ -162,21 +163,28 @@ conv_umma_kernel(const __grid_constant__ ConvUmmaParams p) {
       for (int pl = 0; pl < p.planes; ++pl) ptx::prefetch_tmap(&p.b_map[pl]);
       int s = 0;
       uint32_t ph = 0;
-      for (int t = 0; t < p.num_taps; ++t) {
-        const ConvTap tap = p.taps[t];
-        for (int kc = 0; kc < p.kchunks; ++kc) {
-          ptx::mbar_wait(&empty[s], ph ^ 1);
-          uint8_t* st = smem + s * stage_bytes;
-          ptx::mbar_expect_tx(&full[s], p.planes * (p.a_tx_bytes + p.b_bytes));
-          for (int pl = 0; pl < p.planes; ++pl)
-            ptx::tma_load_4d(st + pl * kABytes, &p.a_map[tap.src][pl], &full[s], kc * 64,
-                             w0 + tap.dw, h0 + tap.dh, n0);
-          for (int pl = 0; pl < p.planes; ++pl)
-            ptx::tma_load_3d(st + b_off + pl * p.b_bytes, &p.b_map[pl], &full[s], kc * 64,
-                             nt * p.block_n, tap.wtap);
-          if (++s == p.stages) {
-            s = 0;
-            ph ^= 1;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int pt = tile % pix_tiles, nt = tile / pix_tiles;
+        const int tw = pt % p.tiles_w;
+        const int th = (pt / p.tiles_w) % p.tiles_h;
+        const int tn = pt / (p.tiles_w * p.tiles_h);
+        const int w0 = tw * p.BW, h0 = th * p.BH, n0 = tn * p.BN;
+        for (int t = 0; t < p.num_taps; ++t) {
+          const ConvTap tap = p.taps[t];
+          for (int kc = 0; kc < p.kchunks; ++kc) {
+            ptx::mbar_wait(&empty[s], ph ^ 1);
+            uint8_t* st = smem + s * stage_bytes;
+            ptx::mbar_expect_tx(&full[s], p.planes * (p.a_tx_bytes + p.b_bytes));
+            for (int pl = 0; pl < p.planes; ++pl)
+              ptx::tma_load_4d(st + pl * kABytes, &p.a_map[tap.src][pl], &full[s], kc * 64, w0 + tap.dw,
+                               h0 + tap.dh, n0);
+            for (int pl = 0; pl < p.planes; ++pl)
+              ptx::tma_load_3d(st + b_off + pl * p.b_bytes, &p.b_map[pl], &full[s], kc * 64, nt * p.block_n,
+                               tap.wtap);
+            if (++s == p.stages) {
+              s = 0;
+              ph ^= 1;
+            }
           }
         }
       }
@@ -186,32 +194,39 @@ conv_umma_kernel(const __grid_constant__ ConvUmmaParams p) {
       const uint32_t idesc = ptx::make_idesc_bf16(128, p.block_n, 0, 0);
       int s = 0;
       uint32_t ph = 0;
-      for (int step = 0; step < total_steps; ++step) {
-        ptx::mbar_wait(&full[s], ph);
+      int j = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++j) {
+        const int acc = j & 1;
+        ptx::mbar_wait(&tmem_empty[acc], ((j >> 1) & 1) ^ 1);
         ptx::tc_fence_after();
-        const uint32_t a_hi = ptx::smem_u32(smem + s * stage_bytes);
-        const uint32_t a_lo = a_hi + kABytes;
-        const uint32_t b_hi = a_hi + b_off;
-        const uint32_t b_lo = b_hi + p.b_bytes;
+        const uint32_t tmem_acc = tmem_base + acc * p.block_n;
+        for (int step = 0; step < steps_per_tile; ++step) {
+          ptx::mbar_wait(&full[s], ph);
+          ptx::tc_fence_after();
+          const uint32_t a_hi = ptx::smem_u32(smem + s * stage_bytes);
+          const uint32_t a_lo = a_hi + kABytes;
+          const uint32_t b_hi = a_hi + b_off;
+          const uint32_t b_lo = b_hi + p.b_bytes;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const uint64_t da_hi = ptx::make_desc_sw128(a_hi + k * 32, 16, 1024);
-          const uint64_t db_hi = ptx::make_desc_sw128(b_hi + k * 32, 16, 1024);
-          ptx::umma_bf16(tmem_base, da_hi, db_hi, idesc, (step | k) ? 1u : 0u);
-          if (p.planes == 2) {
-            const uint64_t da_lo = ptx::make_desc_sw128(a_lo + k * 32, 16, 1024);
-            const uint64_t db_lo = ptx::make_desc_sw128(b_lo + k * 32, 16, 1024);
-            ptx::umma_bf16(tmem_base, da_hi, db_lo, idesc, 1u);
-            ptx::umma_bf16(tmem_base, da_lo, db_hi, idesc, 1u);
+          for (int k = 0; k < 4; ++k) {
+            const uint64_t da_hi = ptx::make_desc_sw128(a_hi + k * 32, 16, 1024);
+            const uint64_t db_hi = ptx::make_desc_sw128(b_hi + k * 32, 16, 1024);
+            ptx::umma_bf16(tmem_acc, da_hi, db_hi, idesc, (step | k) ? 1u : 0u);
+            if (p.planes == 2) {
+              const uint64_t da_lo = ptx::make_desc_sw128(a_lo + k * 32, 16, 1024);
+              const uint64_t db_lo = ptx::make_desc_sw128(b_lo + k * 32, 16, 1024);
+              ptx::umma_bf16(tmem_acc, da_hi, db_lo, idesc, 1u);
+              ptx::umma_bf16(tmem_acc, da_lo, db_hi, idesc, 1u);
+            }
+          }
+          ptx::umma_commit(&empty[s]);
+          if (++s == p.stages) {
+            s = 0;
+            ph ^= 1;
           }
         }
-        ptx::umma_commit(&empty[s]);
-        if (++s == p.stages) {
-          s = 0;
-          ph ^= 1;
-        }
+        ptx::umma_commit(&tmem_full[acc]);
       }
-      ptx::umma_commit(tmem_full);
     }
   } else {
     // ---------------- epilogue: 4 warps, thread = one accumulator row (= one output pixel)
@@ -221,99 +236,114 @@ conv_umma_kernel(const __grid_constant__ ConvUmmaParams p) {
     const int tq = r / p.BW;
     const int hl = tq % p.BH;
     const int nl = tq / p.BH;
-    const int w = w0 + wl, h = h0 + hl, n = n0 + nl;
-    const bool valid = (nl < p.BN) && (w < p.Wo) && (h < p.Ho) && (n < p.No);
-    const long long lpix = (static_cast<long long>(n) * p.Ho + h) * p.Wo + w;  // logical pixel
-    const int py = h * p.sh + p.oh, px = w * p.sw + p.ow;
-    const long long ppix = (static_cast<long long>(n) * p.out_H + py) * p.out_W + px;
+    int j = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++j) {
+      const int acc = j & 1;
+      const int pt = tile % pix_tiles, nt = tile / pix_tiles;
+      const int tw = pt % p.tiles_w;
+      const int th = (pt / p.tiles_w) % p.tiles_h;
+      const int tn = pt / (p.tiles_w * p.tiles_h);
+      const int w = tw * p.BW + wl, h = th * p.BH + hl, n = tn * p.BN + nl;
+      const bool valid = (nl < p.BN) && (w < p.Wo) && (h < p.Ho) && (n < p.No);
+      const long long lpix = (static_cast<long long>(n) * p.Ho + h) * p.Wo + w;  // logical pixel
+      const int py = h * p.sh + p.oh, px = w * p.sw + p.ow;
+      const long long ppix = (static_cast<long long>(n) * p.out_H + py) * p.out_W + px;
 
-    ptx::mbar_wait(tmem_full, 0);
-    ptx::tc_fence_after();
+      ptx::mbar_wait(&tmem_full[acc], (j >> 1) & 1);
+      ptx::tc_fence_after();
+      const uint32_t tmem_acc = tmem_base + acc * p.block_n + (static_cast<uint32_t>(lg * 32) << 16);
 
-    for (int c0 = 0; c0 < p.block_n; c0 += 32) {
-      uint32_t v[32];
-      ptx::tmem_ld32(tmem_base + (static_cast<uint32_t>(lg * 32) << 16) + c0, v);
-      ptx::tmem_ld_wait();
-      const int cbase = nt * p.block_n + c0;
-      const int nvalid = min(32, p.cout - cbase);
-      if (!valid || nvalid <= 0) continue;
-      float f[32];
-      uint32_t mbits = 0;
+      for (int c0 = 0; c0 < p.block_n; c0 += 32) {
+        uint32_t v[32];
+        ptx::tmem_ld32(tmem_acc + c0, v);
+        ptx::tmem_ld_wait();
+        if (c0 + 32 >= p.block_n) {
+          // last TMEM read of this tile: hand the accumulator stage back to the MMA warp
+          ptx::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(&tmem_empty[acc]);
+        }
+        const int cbase = nt * p.block_n + c0;
+        const int nvalid = min(32, p.cout - cbase);
+        if (!valid || nvalid <= 0) continue;
+        float f[32];
+        uint32_t mbits = 0;
 #pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        float x = __uint_as_float(v[i]);
-        if (p.bias && i < nvalid) x += __ldg(p.bias + cbase + i);
-        mbits |= (x > 0.f ? 1u : 0u) << i;
-        if (p.act == DPIG_ACT_RELU) x = fmaxf(x, 0.f);
-        else if (p.act == DPIG_ACT_LRELU) x = x > 0.f ? x : p.alpha * x;
-        f[i] = x;
-      }
-      const bool full32 = (nvalid == 32);
-      if (p.add_hi) {
-        const long long off = ppix * p.add_ps + cbase;
-        if (full32 && (p.add_ps % 8 == 0)) {
-          const uint4* ah = reinterpret_cast<const uint4*>(p.add_hi + off);
-          const uint4* al = p.add_lo ? reinterpret_cast<const uint4*>(p.add_lo + off) : nullptr;
+        for (int i = 0; i < 32; ++i) {
+          float x = __uint_as_float(v[i]);
+          if (p.bias && i < nvalid) x += __ldg(p.bias + cbase + i);
+          mbits |= (x > 0.f ? 1u : 0u) << i;
+          if (p.act == DPIG_ACT_RELU) x = fmaxf(x, 0.f);
+          else if (p.act == DPIG_ACT_LRELU) x = x > 0.f ? x : p.alpha * x;
+          f[i] = x;
+        }
+        const bool full32 = (nvalid == 32);
+        if (p.add_hi) {
+          const long long off = ppix * p.add_ps + cbase;
+          if (full32 && (p.add_ps % 8 == 0)) {
+            const uint4* ah = reinterpret_cast<const uint4*>(p.add_hi + off);
+            const uint4* al = p.add_lo ? reinterpret_cast<const uint4*>(p.add_lo + off) : nullptr;
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const uint4 a = __ldg(ah + q);
-            const uint32_t aw[4] = {a.x, a.y, a.z, a.w};
+            for (int q = 0; q < 4; ++q) {
+              const uint4 a = __ldg(ah + q);
+              const uint32_t aw[4] = {a.x, a.y, a.z, a.w};
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              f[q * 8 + 2 * j] += bf16_bits_to_float(aw[j] & 0xFFFF);
-              f[q * 8 + 2 * j + 1] += bf16_bits_to_float(aw[j] >> 16);
-            }
-            if (al) {
-              const uint4 b = __ldg(al + q);
-              const uint32_t bw[4] = {b.x, b.y, b.z, b.w};
+              for (int jj = 0; jj < 4; ++jj) {
+                f[q * 8 + 2 * jj] += bf16_bits_to_float(aw[jj] & 0xFFFF);
+                f[q * 8 + 2 * jj + 1] += bf16_bits_to_float(aw[jj] >> 16);
+              }
+              if (al) {
+                const uint4 b = __ldg(al + q);
+                const uint32_t bw[4] = {b.x, b.y, b.z, b.w};
 #pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                f[q * 8 + 2 * j] += bf16_bits_to_float(bw[j] & 0xFFFF);
-                f[q * 8 + 2 * j + 1] += bf16_bits_to_float(bw[j] >> 16);
+                for (int jj = 0; jj < 4; ++jj) {
+                  f[q * 8 + 2 * jj] += bf16_bits_to_float(bw[jj] & 0xFFFF);
+                  f[q * 8 + 2 * jj + 1] += bf16_bits_to_float(bw[jj] >> 16);
+                }
               }
             }
-          }
-        } else {
+          } else {
 #pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (i < nvalid) {
-              float a = __bfloat162float(p.add_hi[off + i]);
-              if (p.add_lo) a += __bfloat162float(p.add_lo[off + i]);
-              f[i] += a;
+            for (int i = 0; i < 32; ++i)
+              if (i < nvalid) {
+                float a = __bfloat162float(p.add_hi[off + i]);
+                if (p.add_lo) a += __bfloat162float(p.add_lo[off + i]);
+                f[i] += a;
+              }
+          }
+        }
+        if (p.mask_out) p.mask_out[lpix * p.mask_out_words + (cbase >> 5)] = mbits;
+        if (p.out_hi) {
+          const bool vec = full32 && (p.out_ps % 8 == 0);
+          for (int dy = 0; dy < p.rep; ++dy)
+            for (int dx = 0; dx < p.rep; ++dx) {
+              const long long off = (ppix + static_cast<long long>(dy) * p.out_W + dx) * p.out_ps + cbase;
+              store_split32(p.out_hi, p.out_lo, off, f, nvalid, vec);
             }
         }
-      }
-      if (p.mask_out) p.mask_out[lpix * p.mask_out_words + (cbase >> 5)] = mbits;
-      if (p.out_hi) {
-        const bool vec = full32 && (p.out_ps % 8 == 0);
-        for (int dy = 0; dy < p.rep; ++dy)
-          for (int dx = 0; dx < p.rep; ++dx) {
-            const long long off = (ppix + static_cast<long long>(dy) * p.out_W + dx) * p.out_ps + cbase;
-            store_split32(p.out_hi, p.out_lo, off, f, nvalid, vec);
-          }
-      }
-      if (p.out_f32) {
-        for (int dy = 0; dy < p.rep; ++dy)
-          for (int dx = 0; dx < p.rep; ++dx) {
-            float* o = p.out_f32 + (ppix + static_cast<long long>(dy) * p.out_W + dx) * p.out_f32_ps + cbase;
-            if (full32 && (p.out_f32_ps % 4 == 0)) {
+        if (p.out_f32) {
+          for (int dy = 0; dy < p.rep; ++dy)
+            for (int dx = 0; dx < p.rep; ++dx) {
+              float* o = p.out_f32 + (ppix + static_cast<long long>(dy) * p.out_W + dx) * p.out_f32_ps + cbase;
+              if (full32 && (p.out_f32_ps % 4 == 0)) {
 #pragma unroll
-              for (int q = 0; q < 8; ++q)
-                reinterpret_cast<float4*>(o)[q] =
-                    make_float4(f[4 * q], f[4 * q + 1], f[4 * q + 2], f[4 * q + 3]);
-            } else {
+                for (int q = 0; q < 8; ++q)
+                  reinterpret_cast<float4*>(o)[q] =
+                      make_float4(f[4 * q], f[4 * q + 1], f[4 * q + 2], f[4 * q + 3]);
+              } else {
 #pragma unroll
-              for (int i = 0; i < 32; ++i)
-                if (i < nvalid) o[i] = f[i];
+                for (int i = 0; i < 32; ++i)
+                  if (i < nvalid) o[i] = f[i];
+              }
             }
-          }
-      }
-      if (p.out2_hi) {
-        const uint32_t mi = p.mask_in ? p.mask_in[ppix * p.mask_in_words + (cbase >> 5)] : 0xFFFFFFFFu;
+        }
+        if (p.out2_hi) {
+          const uint32_t mi = p.mask_in ? p.mask_in[ppix * p.mask_in_words + (cbase >> 5)] : 0xFFFFFFFFu;
 #pragma unroll
-        for (int i = 0; i < 32; ++i) f[i] *= ((mi >> i) & 1u) ? 1.f : p.mask_neg;
-        const bool vec = full32 && (p.out2_ps % 8 == 0);
-        store_split32(p.out2_hi, p.out2_lo, ppix * p.out2_ps + cbase, f, nvalid, vec);
+          for (int i = 0; i < 32; ++i) f[i] *= ((mi >> i) & 1u) ? 1.f : p.mask_neg;
+          const bool vec = full32 && (p.out2_ps % 8 == 0);
+          store_split32(p.out2_hi, p.out2_lo, ppix * p.out2_ps + cbase, f, nvalid, vec);
+        }
       }
     }
   }
@@ -323,10 +353,10 @@ conv_umma_kernel(const __grid_constant__ ConvUmmaParams p) {
   if (warp == 1) {
     ptx::tc_fence_after();
     switch (p.tmem_cols) {
-      case 32: ptx::tmem_dealloc<32>(tmem_base); break;
       case 64: ptx::tmem_dealloc<64>(tmem_base); break;
       case 128: ptx::tmem_dealloc<128>(tmem_base); break;
-      default: ptx::tmem_dealloc<256>(tmem_base); break;
+      case 256: ptx::tmem_dealloc<256>(tmem_base); break;
+      default: ptx::tmem_dealloc<512>(tmem_base); break;
     }
   }
 }
@@ -570,6 +600,13 @@ static int pick_block_n(int cout) {
   return best;
 }
 
+// Few-pixel layers (8x4, 3x3 maps): trade operand reuse for parallelism until the persistent grid fills the SMs.
+static int tune_block_n(const dpig_ctx* ctx, int cout, int pix_tiles) {
+  int bn = pick_block_n(cout);
+  while (bn >= 128 && (bn / 2) % 32 == 0 && pix_tiles * ((cout + bn - 1) / bn) < ctx->num_sms) bn /= 2;
+  return bn;
+}
+
 struct EpilogueGeom {
   int sh, sw, oh, ow, rep, out_H, out_W;
 };
@@ -636,7 +673,10 @@ static int launch_conv(dpig_ctx* ctx, ConvUmmaParams& P, cudaStream_t stream) {
     cudaFuncSetAttribute(conv_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->max_smem_optin);
     attr_set = true;
   }
-  dim3 grid(P.tiles_w * P.tiles_h * P.tiles_n, (P.cout + P.block_n - 1) / P.block_n);
+  const int total_tiles = P.tiles_w * P.tiles_h * P.tiles_n * ((P.cout + P.block_n - 1) / P.block_n);
+  P.tmem_cols = 64;
+  while (static_cast<int>(P.tmem_cols) < 2 * P.block_n) P.tmem_cols <<= 1;
+  dim3 grid(std::min(total_tiles, ctx->num_sms));
   conv_umma_kernel<<<grid, 192, smem, stream>>>(P);
   ctx->launches++;
   return check_launch(ctx, "conv_umma_kernel");
@@ -668,9 +708,6 @@ extern "C" int dpig_conv2d_fwd(dpig_ctx* ctx, const dpig_tensor* x, const void* 
   P.Ho = OH;
   P.No = x->n;
   P.cout = cout;
-  P.block_n = pick_block_n(cout);
-  P.b_bytes = P.block_n * 128;
-  P.tmem_cols = pow2_cols(P.block_n);
   Box b = choose_box(OW, OH, x->n, 128, false);
   P.BW = b.bw;
   P.BH = b.bh;
@@ -679,6 +716,8 @@ extern "C" int dpig_conv2d_fwd(dpig_ctx* ctx, const dpig_tensor* x, const void* 
   P.tiles_h = (OH + b.bh - 1) / b.bh;
   P.tiles_n = (x->n + b.bn - 1) / b.bn;
   P.a_tx_bytes = b.bw * b.bh * b.bn * 128;
+  P.block_n = tune_block_n(ctx, cout, P.tiles_w * P.tiles_h * P.tiles_n);
+  P.b_bytes = P.block_n * 128;
 
   int rc;
   P.num_taps = 0;
@@ -758,9 +797,6 @@ extern "C" int dpig_conv2d_bwd_data(dpig_ctx* ctx, const dpig_tensor* dy, const 
       P.Ho = GH;
       P.No = dy->n;
       P.cout = cin;
-      P.block_n = pick_block_n(cin);
-      P.b_bytes = P.block_n * 128;
-      P.tmem_cols = pow2_cols(P.block_n);
       Box b = choose_box(GW, GH, dy->n, 128, false);
       P.BW = b.bw;
       P.BH = b.bh;
@@ -769,6 +805,8 @@ extern "C" int dpig_conv2d_bwd_data(dpig_ctx* ctx, const dpig_tensor* dy, const 
       P.tiles_h = (GH + b.bh - 1) / b.bh;
       P.tiles_n = (dy->n + b.bn - 1) / b.bn;
       P.a_tx_bytes = b.bw * b.bh * b.bn * 128;
+      P.block_n = tune_block_n(ctx, cin, P.tiles_w * P.tiles_h * P.tiles_n);
+      P.b_bytes = P.block_n * 128;
       P.num_taps = 0;
       for (int i = 0; i < kh; ++i)
         for (int j = 0; j < kw; ++j) {

@@ -273,3 +273,201 @@ extern "C" int dpig_norm_act_bwd_apply(dpig_ctx* ctx, const dpig_tensor* dy, con
   ctx->launches++;
   return check_launch(ctx, "norm_act_bwd_apply");
 }
+
+// ------------------------------------------------------------------------------------------------
+// Second-order pieces for the WGAN-GP gradient penalty (reference trainer.py:226-236, wgan_gp.py:605-619).
+// d(lambda*gp)/d(theta) = d/d(theta) sum_n <v_n, dD(xhat_n)/dxhat_n> with v = d(lambda*gp)/d(grad) held
+// constant, i.e. the parameter gradient of the directional derivative (JVP) of D along v.  Convolutions,
+// LeakyReLU and the linear layer are (piecewise) linear, so their JVP / adjoint reuse the conv kernels; the
+// per-sample LayerNorm (tflib/ops/layernorm.py:6-20) is the only layer with a genuinely second-order term:
+//   forward tangent:  zdot = gamma * u,  u = rstd*(pdot - m1 - xhat*m2),  m1 = mean(pdot), m2 = mean(xhat*pdot)
+//   adjoint (given zbar = dS/dzdot):  ubar = gamma*zbar, wbar = rstd*ubar,
+//        A = mean(wbar), Bq = mean(xhat*wbar), Cq = mean(ubar*u)
+//        pdot_bar = wbar - A - xhat*Bq
+//        p_bar    = rstd*( -m2*(wbar - A) - Bq*(pdot - m1) + xhat*(2*m2*Bq - Cq) )     (via xhat and sigma)
+//        dgamma  += sum zbar*u
+// Means are over the sample's C*H*W elements.  Reductions run in fp64.
+namespace dpig {
+
+// grid = (pixel chunks, N): per-sample sums of (a, xhat*a) where a = pdot (mode 0) or
+// (wbar, xhat*wbar, ubar*u) (mode 1, three sums).
+__global__ void ln_jvp_reduce_kernel(const float* p, const float* pdot, const float* stats, int N, int C,
+                                     long long ppi, int chunk, const float* scale, const __nv_bfloat16* zhi,
+                                     const __nv_bfloat16* zlo, long long zps, const uint32_t* mask, float alpha,
+                                     const double* tsums, double* out, float* dscale, int mode) {
+  __shared__ double red[3][32];
+  const int n = blockIdx.y;
+  const float mean = stats[n], rstd = stats[N + n];
+  const long long p0 = static_cast<long long>(blockIdx.x) * chunk;
+  const long long p1 = min(p0 + chunk, ppi);
+  const double cnt = static_cast<double>(ppi) * C;
+  float m1 = 0.f, m2 = 0.f;
+  if (mode == 1) {
+    m1 = static_cast<float>(tsums[n] / cnt);
+    m2 = static_cast<float>(tsums[N + n] / cnt);
+  }
+  const int words = C / 32;
+  double s0 = 0, s1 = 0, s2 = 0;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, dg = 0.f;
+    const float gam = mode == 1 ? scale[c] : 1.f;
+    for (long long q = p0; q < p1; ++q) {
+      const long long pix = n * ppi + q;
+      const float xh = (p[pix * C + c] - mean) * rstd;
+      const float pd = pdot[pix * C + c];
+      if (mode == 0) {
+        a0 += pd;
+        a1 = fmaf(xh, pd, a1);
+      } else {
+        const float zb = ld_dz(zhi, zlo, pix * zps + c, mask, pix, words, c, alpha);
+        const float u = rstd * (pd - m1 - xh * m2);
+        const float ub = gam * zb;
+        const float wb = rstd * ub;
+        a0 += wb;
+        a1 = fmaf(xh, wb, a1);
+        a2 = fmaf(ub, u, a2);
+        dg = fmaf(zb, u, dg);
+      }
+    }
+    s0 += a0;
+    s1 += a1;
+    s2 += a2;
+    if (mode == 1 && dscale) atomicAdd(dscale + c, dg);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+    s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+    s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+  }
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  if (l == 0) {
+    red[0][w] = s0;
+    red[1][w] = s1;
+    red[2][w] = s2;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double a = 0, b = 0, c2 = 0;
+    for (int i = 0; i < (blockDim.x >> 5); ++i) {
+      a += red[0][i];
+      b += red[1][i];
+      c2 += red[2][i];
+    }
+    atomicAdd(out + n, a);
+    atomicAdd(out + N + n, b);
+    if (mode == 1) atomicAdd(out + 2 * N + n, c2);
+  }
+}
+
+// hdot = lrelu'(z) * gamma * rstd * (pdot - m1 - xhat*m2)   (split output)
+__global__ void ln_jvp_fwd_apply_kernel(const float* p, const float* pdot, const float* stats, int N, int C,
+                                        long long ppi, const float* scale, const uint32_t* mask, float alpha,
+                                        const double* tsums, __nv_bfloat16* ohi, __nv_bfloat16* olo, long long ops) {
+  const long long total = static_cast<long long>(N) * ppi * C;
+  const int words = C / 32;
+  const double cnt = static_cast<double>(ppi) * C;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % C);
+    const long long pix = i / C;
+    const int n = static_cast<int>(pix / ppi);
+    const float mean = stats[n], rstd = stats[N + n];
+    const float m1 = static_cast<float>(tsums[n] / cnt), m2 = static_cast<float>(tsums[N + n] / cnt);
+    const float xh = (p[i] - mean) * rstd;
+    float v = scale[c] * rstd * (pdot[i] - m1 - xh * m2);
+    if (mask) {
+      const uint32_t m = mask[pix * words + (c >> 5)];
+      if (!((m >> (c & 31)) & 1u)) v *= alpha;
+    }
+    __nv_bfloat16 h, l;
+    split_bf16(v, h, l);
+    ohi[pix * ops + c] = h;
+    if (olo) olo[pix * ops + c] = l;
+  }
+}
+
+__global__ void ln_jvp_bwd_apply_kernel(const float* p, const float* pdot, const float* stats, int N, int C,
+                                        long long ppi, const float* scale, const __nv_bfloat16* zhi,
+                                        const __nv_bfloat16* zlo, long long zps, const uint32_t* mask, float alpha,
+                                        const double* tsums, const double* asums, __nv_bfloat16* ohi,
+                                        __nv_bfloat16* olo, long long ops, float* pbar) {
+  const long long total = static_cast<long long>(N) * ppi * C;
+  const int words = C / 32;
+  const double cnt = static_cast<double>(ppi) * C;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % C);
+    const long long pix = i / C;
+    const int n = static_cast<int>(pix / ppi);
+    const float mean = stats[n], rstd = stats[N + n];
+    const float m1 = static_cast<float>(tsums[n] / cnt), m2 = static_cast<float>(tsums[N + n] / cnt);
+    const float A = static_cast<float>(asums[n] / cnt), Bq = static_cast<float>(asums[N + n] / cnt),
+                Cq = static_cast<float>(asums[2 * N + n] / cnt);
+    const float xh = (p[i] - mean) * rstd;
+    const float zb = ld_dz(zhi, zlo, pix * zps + c, mask, pix, words, c, alpha);
+    const float wb = rstd * scale[c] * zb;
+    const float pdb = wb - A - xh * Bq;
+    const float pb = rstd * (-m2 * (wb - A) - Bq * (pdot[i] - m1) + xh * (2.f * m2 * Bq - Cq));
+    __nv_bfloat16 h, l;
+    split_bf16(pdb, h, l);
+    ohi[pix * ops + c] = h;
+    if (olo) olo[pix * ops + c] = l;
+    pbar[i] = pb;
+  }
+}
+
+}  // namespace dpig
+
+extern "C" int dpig_layernorm_jvp_fwd(dpig_ctx* ctx, const float* p, const float* pdot, int32_t n, int32_t h,
+                                      int32_t w_, int32_t c, const float* stats, const float* scale,
+                                      const uint32_t* mask, float alpha, double* tsums, const dpig_tensor* hdot,
+                                      dpig_stream stream) {
+  DPIG_CHECK_CTX(ctx);
+  if (!p || !pdot || !stats || !scale || !tsums || !hdot || c % 32)
+    return set_error(ctx, DPIG_EINVAL, "layernorm_jvp_fwd: bad argument");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  cudaMemsetAsync(tsums, 0, sizeof(double) * 2 * n, s);
+  const long long ppi = static_cast<long long>(h) * w_;
+  const int chunk = 32;
+  dim3 grid(static_cast<unsigned>((ppi + chunk - 1) / chunk), n);
+  ln_jvp_reduce_kernel<<<grid, 256, 0, s>>>(p, pdot, stats, n, c, ppi, chunk, scale, nullptr, nullptr, 0, nullptr, alpha,
+                                            nullptr, tsums, nullptr, 0);
+  const long long total = static_cast<long long>(n) * ppi * c;
+  long long g = (total + 255) / 256;
+  if (g > 148 * 32) g = 148 * 32;
+  ln_jvp_fwd_apply_kernel<<<static_cast<int>(g), 256, 0, s>>>(p, pdot, stats, n, c, ppi, scale, mask, alpha, tsums,
+                                                               static_cast<__nv_bfloat16*>(hdot->hi),
+                                                               static_cast<__nv_bfloat16*>(hdot->lo), hdot->pix_stride);
+  ctx->launches += 2;
+  return check_launch(ctx, "layernorm_jvp_fwd");
+}
+
+extern "C" int dpig_layernorm_jvp_bwd(dpig_ctx* ctx, const dpig_tensor* hdot_bar, const uint32_t* mask, float alpha,
+                                      const float* p, const float* pdot, const float* stats, const float* scale,
+                                      const double* tsums, double* asums, float* dscale, const dpig_tensor* pdot_bar,
+                                      float* p_bar, dpig_stream stream) {
+  DPIG_CHECK_CTX(ctx);
+  if (!hdot_bar || !p || !pdot || !stats || !scale || !tsums || !asums || !pdot_bar || !p_bar || hdot_bar->c % 32)
+    return set_error(ctx, DPIG_EINVAL, "layernorm_jvp_bwd: bad argument");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int n = hdot_bar->n, c = hdot_bar->c;
+  cudaMemsetAsync(asums, 0, sizeof(double) * 3 * n, s);
+  const long long ppi = static_cast<long long>(hdot_bar->h) * hdot_bar->w;
+  const int chunk = 32;
+  dim3 grid(static_cast<unsigned>((ppi + chunk - 1) / chunk), n);
+  const __nv_bfloat16* zhi = static_cast<const __nv_bfloat16*>(hdot_bar->hi);
+  const __nv_bfloat16* zlo = static_cast<const __nv_bfloat16*>(hdot_bar->lo);
+  ln_jvp_reduce_kernel<<<grid, 256, 0, s>>>(p, pdot, stats, n, c, ppi, chunk, scale, zhi, zlo, hdot_bar->pix_stride, mask,
+                                            alpha, tsums, asums, dscale, 1);
+  const long long total = static_cast<long long>(n) * ppi * c;
+  long long g = (total + 255) / 256;
+  if (g > 148 * 32) g = 148 * 32;
+  ln_jvp_bwd_apply_kernel<<<static_cast<int>(g), 256, 0, s>>>(p, pdot, stats, n, c, ppi, scale, zhi, zlo,
+                                                               hdot_bar->pix_stride, mask, alpha, tsums, asums,
+                                                               static_cast<__nv_bfloat16*>(pdot_bar->hi),
+                                                               static_cast<__nv_bfloat16*>(pdot_bar->lo),
+                                                               pdot_bar->pix_stride, p_bar);
+  ctx->launches += 2;
+  return check_launch(ctx, "layernorm_jvp_bwd");
+}

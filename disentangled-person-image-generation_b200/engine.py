@@ -247,6 +247,7 @@ class Stage1Engine:
         self._build_params()
         self._build_buffers()
         self.t = {"g": 0, "d": 0}
+        self.gp_alpha_fixed = False   # tests pin alpha to compare with the oracle
         self.g_lr = 2e-5
         self.d_lr = 2e-5
         self._build_programs()
@@ -488,10 +489,42 @@ class Stage1Engine:
         # discriminator passes
         self.d_real = _DiscPass(self, B)
         self.d_fake = _DiscPass(self, B)
+        if self.mode == "wgan-gp":
+            self._build_gp_buffers()
         # losses: [g_gan, d_loss], [L1], gp
         self.loss_gan = torch.zeros((2,), device=dev)
         self.loss_l1 = torch.zeros((1,), device=dev)
         self.loss_gp = torch.zeros((1,), device=dev)
+
+    def _build_gp_buffers(self):
+        """Interpolates, critic pass on them, tangent (JVP) and adjoint buffers of the gradient penalty."""
+        cfg, dev, B = self.cfg, self.device, self.B
+        H, W, d = cfg.img_h, cfg.img_w, cfg.d_dim
+        self.gp_alpha = torch.zeros((B,), device=dev)
+        self.xhat = torch.zeros((B, H, W, 3), device=dev)
+        self.xhat8 = SplitTensor(B, H, W, 8, dev, zero=True)
+        self.gp_v = torch.zeros((B, H, W, 3), device=dev)
+        self.gp_v8 = SplitTensor(B, H, W, 8, dev, zero=True)
+        self.slopes = torch.zeros((B,), device=dev)
+        self.ones_b = torch.ones((B,), device=dev)
+        dh = self.d_hat = _DiscPass(self, B)
+        dh.dlogits.fill_(1.0)
+
+        def st(i):
+            return SplitTensor(B, H >> (i + 1), W >> (i + 1), d << i, dev)
+
+        dh.hd = [st(i) for i in range(4)]        # tangent activations  hdot_i
+        dh.hdbar = [st(i) for i in range(4)]     # adjoints of hdot_i
+        dh.pdbar = [st(i) for i in range(4)]     # adjoints of the tangent pre-norm conv outputs
+        dh.pbar = [st(i) for i in range(4)]      # adjoints of the primal conv outputs (total)
+        dh.pbarP = [st(i) for i in range(4)]     # ... part through the primal chain
+        dh.hbar = [st(i) for i in range(4)]      # adjoints of the primal activations
+        dh.pd = [None] + [torch.zeros((B, H >> (i + 1), W >> (i + 1), d << i), device=dev) for i in (1, 2, 3)]
+        dh.pbarT = [None] + [torch.zeros((B, H >> (i + 1), W >> (i + 1), d << i), device=dev) for i in (1, 2, 3)]
+        dh.tsums = [None] + [torch.zeros((2, B), dtype=torch.float64, device=dev) for _ in range(3)]
+        dh.asums = [None] + [torch.zeros((3, B), dtype=torch.float64, device=dev) for _ in range(3)]
+        dh.hd_flat = torch.zeros((B, self.d_flat), device=dev)
+        dh.hbar_flat = torch.zeros((B, self.d_flat), device=dev)
 
     # -------------------------------------------------------------------------------- call helpers
     def _epilogue(self, prog, layer_bias, act, alpha, addend, mask_in, mask_neg, mask_out, out, out_masked, out_f32,
@@ -519,9 +552,9 @@ class Stage1Engine:
         return C.byref(ep)
 
     def conv_fwd(self, prog, layer, x, out=None, act=ACT_RELU, alpha=0.2, addend=None, mask_out=None, out_f32=None,
-                 out_f32_ps=0, upsample=1):
-        ep = self._epilogue(prog, layer.b, act, alpha, addend, None, 0.0, mask_out, out, None, out_f32, out_f32_ps,
-                            upsample)
+                 out_f32_ps=0, upsample=1, bias=True, out_masked=None, mask_in=None, mask_neg=0.0):
+        ep = self._epilogue(prog, layer.b if bias else None, act, alpha, addend, mask_in, mask_neg, mask_out, out,
+                            out_masked, out_f32, out_f32_ps, upsample)
         assert x.c == layer.cin_pad, (layer.wname, x.c, layer.cin_pad)
         oh, ow = -(-x.h // layer.stride), -(-x.w // layer.stride)
         prog.add("conv2d_fwd", x.ref(), ptr(layer.fwd[0]), ptr(layer.fwd[1]), layer.k, layer.k, layer.stride, layer.cout, ep,
@@ -537,10 +570,12 @@ class Stage1Engine:
                  in_h, in_w, layer.cin, ep, flops=2.0 * dy.n * dy.h * dy.w * layer.cout * layer.k * layer.k * layer.cin,
                  tag="%s dy %dx%dx%dx%d->%d k%ds%d" % (layer.wname, dy.n, dy.h, dy.w, layer.cout, layer.cin, layer.k, layer.stride))
 
-    def conv_wgrad(self, prog, layer, x, dy):
+    def conv_wgrad(self, prog, layer, x, dy, bias=True):
         prog.add("conv2d_bwd_filter", x.ref(), dy.ref(), layer.k, layer.k, layer.stride, layer.cin, layer.cout,
                  ptr(layer.dw), flops=2.0 * dy.n * dy.h * dy.w * layer.cout * layer.k * layer.k * layer.cin,
                  tag="%s %dx%dx%dx%d->%d k%ds%d" % (layer.wname, x.n, x.h, x.w, layer.cin, layer.cout, layer.k, layer.stride))
+        if not bias:
+            return
         if dy.c != layer.cout:  # channel-padded gradient (e.g. the 3-channel image gradient held in 8)
             dy = dy.slice(0, layer.cout)
             prog.keep.append(dy)
@@ -565,6 +600,71 @@ class Stage1Engine:
         self._prog_disc_backward(self.p_d_fake_bwd_par, self.d_fake, self.G8, params=True, data=False)
         self.p_d_real_bwd_par = Program(self.ctx)
         self._prog_disc_backward(self.p_d_real_bwd_par, self.d_real, self.x8, params=True, data=False)
+
+        if self.mode == "wgan-gp":
+            self.p_gp = Program(self.ctx)
+            self._prog_gradient_penalty(self.p_gp)
+
+    def _prog_gradient_penalty(self, p):
+        """lambda * mean((||dD(xhat)/dxhat|| - 1)^2) and its gradient w.r.t. the critic parameters
+        (reference trainer.py:226-236; 4-D image variant: alpha per sample, norm over H*W*C).
+        Second backward pass = parameter gradient of the JVP of D along v = d(lambda*gp)/d(grad)."""
+        cfg, B = self.cfg, self.B
+        H, W, d = cfg.img_h, cfg.img_w, cfg.d_dim
+        dh = self.d_hat
+        per = H * W * 3
+        L = [self.conv[n] for n in self.n_d]
+        p.add("gp_interpolate", ptr(self.x), ptr(self.G), ptr(self.gp_alpha), B, per, ptr(self.xhat))
+        p.add("pack_f32", ptr(self.xhat), 3, 3, self.xhat8.ref())
+        self._prog_disc_forward(p, dh, self.xhat8)
+        self._prog_disc_backward(p, dh, self.xhat8, params=False, data=True)       # dlogits == 1 -> g_x = grad
+        p.add("gp_penalty", ptr(dh.g_x), B, per, float(self.lam), ptr(self.slopes), ptr(self.loss_gp), ptr(self.gp_v))
+        p.add("pack_f32", ptr(self.gp_v), 3, 3, self.gp_v8.ref())
+        # ---- tangent (JVP) forward along v
+        self.conv_fwd(p, L[0], self.gp_v8, act=ACT_NONE, bias=False, out_masked=dh.hd[0], mask_in=dh.m[0], mask_neg=0.2)
+        for i in (1, 2, 3):
+            hh, ww, c = H >> (i + 1), W >> (i + 1), d << i
+            sc = self.dp.view("Discriminator.BN%d.scale" % (i + 1))
+            self.conv_fwd(p, L[i], dh.hd[i - 1], act=ACT_NONE, bias=False, out_f32=dh.pd[i], out_f32_ps=c)
+            p.add("layernorm_jvp_fwd", ptr(dh.pre[i]), ptr(dh.pd[i]), B, hh, ww, c, ptr(dh.stats[i]), ptr(sc),
+                  ptr(dh.m[i]), 0.2, ptr(dh.tsums[i]), dh.hd[i].ref())
+        # ---- adjoint of S = sum_n flat(hdot4_n) . W_out
+        wo = self.dp.view("Discriminator.Output.W")
+        dwo = self.dp.gview("Discriminator.Output.W")
+        p.add("unpack_f32", dh.hd[3].ref(), ptr(dh.hd_flat), d * 8)
+        p.add("linear_bwd", ptr(dh.hd_flat), ptr(wo), ptr(self.ones_b), ptr(dh.hbar_flat), ptr(dwo), None, B,
+              self.d_flat, 1)
+        p.add("pack_f32", ptr(dh.hbar_flat), d * 8, d * 8, dh.hdbar[3].ref())
+        for i in (3, 2, 1):
+            hh, ww, c = H >> (i + 1), W >> (i + 1), d << i
+            sc = self.dp.view("Discriminator.BN%d.scale" % (i + 1))
+            dsc = self.dp.gview("Discriminator.BN%d.scale" % (i + 1))
+            dof = self.dp.gview("Discriminator.BN%d.offset" % (i + 1))
+            p.add("layernorm_jvp_bwd", dh.hdbar[i].ref(), ptr(dh.m[i]), 0.2, ptr(dh.pre[i]), ptr(dh.pd[i]),
+                  ptr(dh.stats[i]), ptr(sc), ptr(dh.tsums[i]), ptr(dh.asums[i]), ptr(dsc), dh.pdbar[i].ref(),
+                  ptr(dh.pbarT[i]))
+            # tangent-path conv adjoint
+            self.conv_wgrad(p, L[i], dh.hd[i - 1], dh.pdbar[i], bias=False)
+            if i > 1:
+                self.conv_dgrad(p, L[i], dh.pdbar[i], hh * 2, ww * 2, out=dh.hdbar[i - 1])
+            else:
+                self.conv_dgrad(p, L[i], dh.pdbar[i], hh * 2, ww * 2, out_masked=dh.pdbar[0], mask_in=dh.m[0], mask_neg=0.2)
+            # primal-path adjoint
+            if i == 3:
+                p.add("pack_f32", ptr(dh.pbarT[i]), c, c, dh.pbar[i].ref())
+            else:
+                p.add("norm_act_bwd_reduce", dh.hbar[i].ref(), ptr(dh.pre[i]), ptr(dh.stats[i]), ptr(dh.m[i]), 0.2,
+                      self.norm_mode, ptr(sc), ptr(dh.red[i]), ptr(dsc), ptr(dof))
+                p.add("norm_act_bwd_apply", dh.hbar[i].ref(), ptr(dh.pre[i]), ptr(dh.stats[i]), ptr(dh.m[i]), 0.2,
+                      self.norm_mode, ptr(sc), ptr(dh.red[i]), float(hh * ww * c), dh.pbarP[i].ref())
+                p.add("ew_combine", dh.pbar[i].ref(), dh.pbarP[i].ref(), None, None, ptr(dh.pbarT[i]), c, None, 0.0, 0)
+            self.conv_wgrad(p, L[i], dh.h[i - 1], dh.pbar[i])
+            if i > 1:
+                self.conv_dgrad(p, L[i], dh.pbar[i], hh * 2, ww * 2, out=dh.hbar[i - 1])
+            else:
+                self.conv_dgrad(p, L[i], dh.pbar[i], hh * 2, ww * 2, out_masked=dh.pbar[0], mask_in=dh.m[0], mask_neg=0.2)
+        self.conv_wgrad(p, L[0], self.xhat8, dh.pbar[0])
+        self.conv_wgrad(p, L[0], self.gp_v8, dh.pdbar[0], bias=False)
 
     def _prog_forward_generator(self, p):
         cfg, B = self.cfg, self.B
@@ -836,6 +936,10 @@ class Stage1Engine:
                           None, ptr(self.d_real.dlogits), ptr(self.d_fake.dlogits), s)
         self.p_d_real_bwd_par.run(s, timings)
         self.p_d_fake_bwd_par.run(s, timings)
+        if self.mode == "wgan-gp":
+            if not self.gp_alpha_fixed:
+                self.gp_alpha.uniform_(0.0, 1.0)     # alpha ~ U[0,1] per sample (trainer.py:226-230)
+            self.p_gp.run(s, timings)
 
     def g_step(self, timings=None):
         self.g_grads(timings)
@@ -846,9 +950,13 @@ class Stage1Engine:
         self._optim("d", torch.cuda.current_stream().cuda_stream)
 
     def losses(self):
-        """(g_gan, d_loss, L1) as Python floats -- a device->host read."""
+        """(g_gan, d_loss, L1) as Python floats -- a device->host read.  In wgan-gp mode d_loss includes
+        lambda * gradient_penalty of the last d_grads()."""
         lg = self.loss_gan.cpu()
-        return float(lg[0]), float(lg[1]), float(self.loss_l1.cpu()[0])
+        d_loss = float(lg[1])
+        if self.mode == "wgan-gp":
+            d_loss += self.lam * float(self.loss_gp.cpu()[0])
+        return float(lg[0]), d_loss, float(self.loss_l1.cpu()[0])
 
 
 def init_params(cfg, seed=1234):

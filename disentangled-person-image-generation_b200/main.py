@@ -1,0 +1,40 @@
+"""Entry point mirroring the reference's main.py:12-90: `--model` id -> trainer class, `--is_train` -> train()/test().
+Only the Stage-I Market-1501 class (--model=1, the BASELINE hot path) is implemented this round; the other ids
+raise NotImplementedError naming the reference class they would map to."""
+import os
+
+from .config import get_config
+
+_MODEL_CLASSES = {
+    1: "DPIG_Encoder_GAN_BodyROI_FgBg", 2: "DPIG_PoseRCV_AE_BodyROI", 3: "DPIG_Encoder_subSampleAppNetFgBg_GAN_BodyROI",
+    4: "DPIG_subnetSamplePoseRCV_GAN_BodyROI", 11: "DPIG_FourNetsFgBg_testOnly", 12: "DPIG_FourNetsFgBg_testOnlyCondition",
+    13: "DPIG_FourNetsFgBg_testOnlySampleFactor", 101: "DPIG_Encoder_GAN_BodyROI_256", 102: "DPIG_PoseRCV_AE_BodyROI_256",
+    103: "DPIG_Encoder_subSampleAppNet_GAN_BodyROI_256", 104: "DPIG_subnetSamplePoseRCV_GAN_BodyROI_256",
+    1001: "DPIG_ThreeNetsApp_testOnlyCondition_256", 1002: "DPIG_ThreeNetsApp_testOnlySampleFactor_256",
+}
+
+
+def main(config):
+    from . import trainer as T
+    if config.gpu > -1:
+        os.environ["CUDA_DEVICE_ORDER"] = "PCI_BUS_ID"
+        os.environ["CUDA_VISIBLE_DEVICES"] = str(config.gpu)
+    config.data_format = "NHWC"
+    name = _MODEL_CLASSES.get(config.model)
+    if name is None:
+        raise Exception("unknown --model=%r" % config.model)
+    cls = getattr(T, name, None)
+    if cls is None:
+        raise NotImplementedError("--model=%d (%s) is outside this round's hot path (SURVEY.md §8f)" % (config.model, name))
+    trainer = cls(config)
+    trainer.init_net()
+    if config.is_train:
+        trainer.train()
+    else:
+        trainer.test()
+    return trainer
+
+
+if __name__ == "__main__":
+    cfg, _ = get_config()
+    main(cfg)

@@ -219,6 +219,22 @@ int dpig_norm_act_bwd_apply(dpig_ctx* ctx, const dpig_tensor* dy, const float* x
                             const float* scale, const double* red, double count,
                             const dpig_tensor* dx, dpig_stream stream);
 
+/* Second-order LayerNorm pieces of the WGAN-GP penalty (trainer.py:226-236): the parameter gradient of the
+ * penalty is the gradient of the directional derivative (JVP) of D along v = d(lambda*gp)/d(grad).  Conv,
+ * LeakyReLU and Linear are piecewise linear -- their JVP / adjoint reuse the entries above -- LayerNorm is not.
+ *   jvp_fwd: hdot = lrelu'(mask) * gamma*rstd*(pdot - mean(pdot) - xhat*mean(xhat*pdot))
+ *            p, pdot: fp32 NHWC primal / tangent pre-norm conv outputs; stats from dpig_norm_act_fwd (LAYER);
+ *            tsums: fp64 [2][n] workspace, kept for jvp_bwd.
+ *   jvp_bwd: given hdot_bar, returns pdot_bar (split; adjoint of the tangent input), p_bar (fp32; adjoint of the
+ *            primal pre-norm input through xhat and sigma) and accumulates dscale.  asums: fp64 [3][n] workspace. */
+int dpig_layernorm_jvp_fwd(dpig_ctx* ctx, const float* p, const float* pdot, int32_t n, int32_t h, int32_t w_,
+                           int32_t c, const float* stats, const float* scale, const uint32_t* mask, float alpha,
+                           double* tsums, const dpig_tensor* hdot, dpig_stream stream);
+int dpig_layernorm_jvp_bwd(dpig_ctx* ctx, const dpig_tensor* hdot_bar, const uint32_t* mask, float alpha,
+                           const float* p, const float* pdot, const float* stats, const float* scale,
+                           const double* tsums, double* asums, float* dscale, const dpig_tensor* pdot_bar,
+                           float* p_bar, dpig_stream stream);
+
 /* ---- losses (trainer.py:217-252, 606-607) ---------------------------------------------------- */
 /* out[0] = mean|g-x|;  if dg != NULL: dg += weight * sign(g-x)/count  (fp32 images) */
 int dpig_loss_l1(dpig_ctx* ctx, const float* g, const float* x, int64_t count, float weight,

@@ -297,7 +297,7 @@ def stage1_forward(p, cfg, batch, mode="dcgan", gp_alpha=None, lam=10.0, taps=No
     d_fake = dcgan_discriminator(p, cfg, G, mode)
     g_gan, d_loss = T.gan_loss(mode, d_real, d_fake)
     out = dict(emb=emb, z=z, G=G, D_real=d_real, D_fake=d_fake)
-    if mode == "wgan-gp":
+    if mode == "wgan-gp" and gp_alpha is not None:
         gp, slopes, _ = T.gradient_penalty(lambda t: dcgan_discriminator(p, cfg, t, mode), x, G, gp_alpha)
         d_loss = d_loss + lam * gp
         out.update(gp=gp, slopes=slopes)
