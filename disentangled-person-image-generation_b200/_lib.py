@@ -65,6 +65,7 @@ _SIGNATURES = {
     "dpig_crop_and_resize_bwd": [_T, _P, _P, _P, _I, _P, _I, _I, _I, _I, _P],
     "dpig_linear_fwd": [_P, _P, _P, _P, _I, _I, _I, _I, _F, _P],
     "dpig_linear_bwd": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _P],
+    "dpig_add_f32": [_P, _P, _P, _L, _F, _F, _P],
     "dpig_act_bwd_f32": [_P, _P, _L, _F, _P],
     "dpig_norm_stats": [_P, _I, _I, _I, _I, _I, _P, _P],
     "dpig_norm_act_fwd": [_P, _I, _I, _I, _I, _I, _F, _P, _D, _P, _P, _I, _F, _P, _T, _P, _P],

@@ -471,3 +471,20 @@ extern "C" int dpig_embedding_assemble(dpig_ctx* ctx, float* fea, float* bg, con
   ctx->launches++;
   return check_launch(ctx, "embedding_assemble");
 }
+
+namespace dpig {
+__global__ void add_f32_kernel(float* out, const float* a, const float* b, long long count, float sa, float sb) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < count;
+       i += static_cast<long long>(gridDim.x) * blockDim.x)
+    out[i] = sa * a[i] + (b ? sb * b[i] : 0.f);
+}
+}  // namespace dpig
+
+extern "C" int dpig_add_f32(dpig_ctx* ctx, float* out, const float* a, const float* b, int64_t count, float sa, float sb,
+                            dpig_stream stream) {
+  DPIG_CHECK_CTX(ctx);
+  if (!out || !a) return set_error(ctx, DPIG_EINVAL, "add_f32: null argument");
+  add_f32_kernel<<<grid_for(count), 256, 0, static_cast<cudaStream_t>(stream)>>>(out, a, b, count, sa, sb);
+  ctx->launches++;
+  return check_launch(ctx, "add_f32");
+}

@@ -246,6 +246,9 @@ class Stage1Engine:
         self._keep = []
         self._build_params()
         self._build_buffers()
+        if mode in ("wgan", "lsgan"):      # TF RMSProp's 'rms' slot is initialised to ones
+            self.gp.v.fill_(1.0)
+            self.dp.v.fill_(1.0)
         self.t = {"g": 0, "d": 0}
         self.gp_alpha_fixed = False   # tests pin alpha to compare with the oracle
         self.g_lr = 2e-5
@@ -588,6 +591,8 @@ class Stage1Engine:
     def _build_programs(self):
         self.p_fwd_gen = Program(self.ctx)     # Encoder + U-Net forward (also the sampling path)
         self._prog_forward_generator(self.p_fwd_gen)
+        self.p_fwd_enc = Program(self.ctx)     # appearance encoder only (Stage-II real embeddings)
+        self._prog_forward_encoder(self.p_fwd_enc)
         self.p_bwd_gen = Program(self.ctx)     # g_G -> all Encoder+G parameter gradients
         self._prog_backward_generator(self.p_bwd_gen)
         self.p_d_fake_fwd = Program(self.ctx)
@@ -667,6 +672,15 @@ class Stage1Engine:
         self.conv_wgrad(p, L[0], self.gp_v8, dh.pdbar[0], bias=False)
 
     def _prog_forward_generator(self, p):
+        self._prog_forward_encoder(p)
+        # ---- generator (trainer.py:588-590, models.py:518-576)
+        self._prog_unet_forward(p)
+
+    def run_encoder(self, stream=None):
+        """Appearance-encoder forward only: fills self.emb [B, 352] for the current batch."""
+        self.p_fwd_enc.run(stream if stream is not None else torch.cuda.current_stream().cuda_stream)
+
+    def _prog_forward_encoder(self, p):
         cfg, B = self.cfg, self.B
         H, W, hn, rn, P = cfg.img_h, cfg.img_w, cfg.hidden, cfg.repeat_num, cfg.n_parts
         e0, e1, e2 = self.conv[self.n_e0], self.conv[self.n_e1], self.conv[self.n_e2]
@@ -690,8 +704,6 @@ class Stage1Engine:
               ACT_NONE, 0.0)
         p.add("embedding_assemble", ptr(self.fea), ptr(self.bg_fea), ptr(self.vis), B, P, cfg.part_z, cfg.part_z * 4,
               ptr(self.emb), 0)
-        # ---- generator (trainer.py:588-590, models.py:518-576)
-        self._prog_unet_forward(p)
 
     def _prog_unet_forward(self, p):
         cfg, B = self.cfg, self.B

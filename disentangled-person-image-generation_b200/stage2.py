@@ -1,0 +1,278 @@
+"""FC sampling nets and the Stage-II embedding-space adversarial step of the reference:
+
+    models.GaussianFCRes            models.py:474-486   noise -> residual MLP -> fake embedding
+    models.PoseEncoderFCRes         models.py:488-499   (same residual-MLP shape; built by FCStack)
+    WGAN_GP.FCDiscriminator         wgan_gp.py:399-405  LeakyReLU MLP critic on embeddings
+    DPIG_Encoder_subSampleAppNetFgBg_GAN_BodyROI        trainer.py:715-845 (--model=3): MODE='wgan',
+        RMSProp + weight clipping, g_optim then 5x(d_optim + clip) for the Fg and then the Bg factor.
+
+All layers are skinny fp32 GEMMs (dpig_linear_fwd/bwd); a tiny tape records forward calls and derives the
+backward program (linear / activation / residual add only).  The real embeddings come from the frozen Stage-I
+appearance encoder (engine.Stage1Engine.run_encoder()).
+"""
+import math
+from collections import OrderedDict
+
+import numpy as np
+import torch
+
+from ._lib import ACT_LRELU, ACT_NONE, ACT_RELU, GAN_MODES
+from .engine import ParamGroup, Program
+from .tensor import ptr
+
+
+class _Node:
+    def __init__(self, b, n, device):
+        self.data = torch.zeros((b, n), device=device)
+        self.grad = torch.zeros((b, n), device=device)
+        self.n = n
+
+
+class FCTape:
+    """Records y = act(x W + b) / y = a + b on [B, n] fp32 matrices and emits forward / backward programs."""
+
+    def __init__(self, ctx, group, batch, device):
+        self.ctx, self.group, self.B, self.device = ctx, group, batch, device
+        self.ops = []
+        self.nodes = []
+        self.scratch = {}
+
+    def node(self, n):
+        nd = _Node(self.B, n, self.device)
+        self.nodes.append(nd)
+        return nd
+
+    def linear(self, x, name_w, name_b, act=ACT_NONE, alpha=0.2):
+        w = self.group.view(name_w)
+        y = self.node(w.shape[1])
+        self.ops.append(("linear", x, y, name_w, name_b, act, alpha))
+        return y
+
+    def add(self, a, b):
+        y = self.node(a.n)
+        self.ops.append(("add", a, b, y))
+        return y
+
+    def forward_program(self):
+        p = Program(self.ctx)
+        for op in self.ops:
+            if op[0] == "linear":
+                _, x, y, nw, nb, act, alpha = op
+                w, b = self.group.view(nw), self.group.view(nb)
+                p.add("linear_fwd", ptr(x.data), ptr(w), ptr(b), ptr(y.data), self.B, w.shape[0], w.shape[1], act, alpha)
+            else:
+                _, a, b, y = op
+                p.add("add_f32", ptr(y.data), ptr(a.data), ptr(b.data), y.data.numel(), 1.0, 1.0)
+        return p
+
+    def backward_program(self, params=True):
+        """Expects out.grad filled by the caller; all other node grads are zeroed first.  Accumulates parameter
+        gradients when params=True; leaves d(loss)/d(node) in every node's .grad."""
+        p = Program(self.ctx)
+        out = self.ops[-1][2] if self.ops[-1][0] == "linear" else self.ops[-1][3]
+        zero = [nd for nd in self.nodes if nd is not out]
+        p.add_py(lambda s: [nd.grad.zero_() for nd in zero])
+        for op in reversed(self.ops):
+            if op[0] == "linear":
+                _, x, y, nw, nb, act, alpha = op
+                w = self.group.view(nw)
+                if act != ACT_NONE:
+                    p.add("act_bwd_f32", ptr(y.data), ptr(y.grad), y.grad.numel(), alpha if act == ACT_LRELU else 0.0)
+                need_dx = any(x is nd for nd in self.nodes)   # inputs outside the tape (noise) need no gradient
+                tmp = self.scratch.setdefault(x.n, torch.zeros((self.B, x.n), device=self.device))
+                p.add("linear_bwd", ptr(x.data), ptr(w), ptr(y.grad), ptr(tmp) if need_dx else None,
+                      ptr(self.group.gview(nw)) if params else None, ptr(self.group.gview(nb)) if params else None,
+                      self.B, w.shape[0], w.shape[1])
+                if need_dx:
+                    p.add("add_f32", ptr(x.grad), ptr(x.grad), ptr(tmp), x.grad.numel(), 1.0, 1.0)
+            else:
+                _, a, b, y = op
+                p.add("add_f32", ptr(a.grad), ptr(a.grad), ptr(y.grad), y.grad.numel(), 1.0, 1.0)
+                p.add("add_f32", ptr(b.grad), ptr(b.grad), ptr(y.grad), y.grad.numel(), 1.0, 1.0)
+        return p
+
+
+def fc_res_specs(prefix, in_dim, hidden, out_dim, repeat_num=4):
+    """slim variable names/shapes of GaussianFCRes / PoseEncoderFCRes inside scope `prefix`."""
+    specs, dims = [], [(in_dim, hidden)] + [(hidden, hidden)] * (2 * repeat_num) + [(hidden, out_dim)]
+    for i, (a, b) in enumerate(dims):
+        name = "%s/fully_connected%s" % (prefix, "" if i == 0 else "_%d" % i)
+        specs += [(name + "/weights", (a, b)), (name + "/biases", (b,))]
+    return specs
+
+
+def fc_critic_specs(name, in_dim, fc_dim=512, n_layers=3):
+    specs = [(name + "Discriminator.Input.Linear.W", (in_dim, fc_dim)), (name + "Discriminator.Input.Linear.b", (fc_dim,))]
+    for i in range(n_layers):
+        specs += [(name + "Discriminator.%d.Linear.W" % i, (fc_dim, fc_dim)), (name + "Discriminator.%d.Linear.b" % i, (fc_dim,))]
+    specs += [(name + "Discriminator.Out.W", (fc_dim, 1)), (name + "Discriminator.Out.b", (1,))]
+    return specs
+
+
+def init_stage2_params(fg_dim=224, bg_dim=128, seed=4321):
+    """Reference initialisers: slim xavier_uniform / zero bias for the Gaussian FC nets; tflib Linear 'he'
+    (LeakyReLULayer, wgan_gp.py:30-32) and glorot (Out) uniform for the critics (tflib/ops/linear.py:36-66)."""
+    rng = np.random.default_rng(seed)
+    p = OrderedDict()
+    for scope, dim, hid in (("Gaussian_FC_Fg/G_FC", fg_dim, 512), ("Gaussian_FC_Bg/G_FC", bg_dim, 256)):
+        for name, shape in fc_res_specs(scope, dim, hid, dim):
+            if name.endswith("weights"):
+                lim = math.sqrt(6.0 / (shape[0] + shape[1]))
+                p[name] = rng.uniform(-lim, lim, size=shape).astype(np.float32)
+            else:
+                p[name] = np.zeros(shape, np.float32)
+    for pre, dim in (("Fg_FCDis_", fg_dim), ("Bg_FCDis_", bg_dim)):
+        for name, shape in fc_critic_specs(pre, dim):
+            if name.endswith(".W"):
+                std = math.sqrt(2.0 / (shape[0] + shape[1])) if ".Out." in name else math.sqrt(2.0 / shape[0])
+                p[name] = rng.uniform(-std * math.sqrt(3), std * math.sqrt(3), size=shape).astype(np.float32)
+            else:
+                p[name] = np.zeros(shape, np.float32)
+    return p
+
+
+class _Factor:
+    """One factor (Fg or Bg): GaussianFCRes generator + FCDiscriminator critic with their optimiser state."""
+
+    def __init__(self, ctx, batch, dim, hidden, g_scope, d_name, device):
+        self.ctx, self.B, self.dim, self.device = ctx, batch, dim, device
+        self.g_scope, self.d_name = g_scope, d_name
+        self.gp = ParamGroup(fc_res_specs(g_scope, dim, hidden, dim), device)
+        self.dp = ParamGroup(fc_critic_specs(d_name, dim), device)
+        self.gp.v.fill_(1.0)   # TF RMSProp slot 'rms' starts at ones
+        self.dp.v.fill_(1.0)
+        # generator tape (models.py:474-486, activation_fn=LeakyReLU as passed by trainer.py:753-757)
+        t = self.gt = FCTape(ctx, self.gp, batch, device)
+        self.z = _Node(batch, dim, device)
+        names = [n for n, _ in fc_res_specs(g_scope, dim, hidden, dim)]
+        lay = [(names[2 * i], names[2 * i + 1]) for i in range(len(names) // 2)]
+        h = t.linear(self.z, *lay[0], act=ACT_LRELU)
+        for r in range(4):
+            res = h
+            a = t.linear(h, *lay[1 + 2 * r], act=ACT_LRELU)
+            b = t.linear(a, *lay[2 + 2 * r], act=ACT_LRELU)
+            h = t.add(res, b)
+        self.fake = t.linear(h, *lay[-1])
+        self.p_g_fwd = t.forward_program()
+        self.p_g_bwd = t.backward_program(params=True)
+        # critic tapes: one on the real embedding, one on the fake one (shared parameters)
+        self.real = _Node(batch, dim, device)
+        self.crit = {}
+        for key, inp in (("real", self.real), ("fake", self.fake)):
+            ct = FCTape(ctx, self.dp, batch, device)
+            dn = [n for n, _ in fc_critic_specs(d_name, dim)]
+            dl = [(dn[2 * i], dn[2 * i + 1]) for i in range(len(dn) // 2)]
+            x = _Node(batch, dim, device)
+            x.data = inp.data         # alias the input storage
+            ct.nodes.append(x)
+            hh = x
+            for wn, bn in dl[:-1]:
+                hh = ct.linear(hh, wn, bn, act=ACT_LRELU)
+            out = ct.linear(hh, *dl[-1])
+            self.crit[key] = dict(tape=ct, x=x, out=out, fwd=ct.forward_program(),
+                                  bwd_par=ct.backward_program(params=True), bwd_data=ct.backward_program(params=False))
+        self.loss = torch.zeros((2,), device=device)
+        self.t = {"g": 0, "d": 0}
+
+
+class Stage2Engine:
+    """--model=3 step on top of a (frozen) Stage-I engine: `g_step(factor)` / `d_step(factor)` with factor in
+    {'fg','bg'}; MODE 'wgan' (as shipped), 'lsgan' or 'dcgan' losses."""
+
+    def __init__(self, stage1, mode="wgan", g_lr=2e-5, d_lr=2e-5):
+        self.s1, self.ctx, self.mode, self.g_lr, self.d_lr = stage1, stage1.ctx, mode, g_lr, d_lr
+        self.gan_mode = GAN_MODES[mode]
+        cfg, B, dev = stage1.cfg, stage1.B, stage1.device
+        self.fg_dim = cfg.n_parts * cfg.part_z
+        self.bg_dim = cfg.part_z * 4
+        self.f = {"fg": _Factor(self.ctx, B, self.fg_dim, 512, "Gaussian_FC_Fg/G_FC", "Fg_FCDis_", dev),
+                  "bg": _Factor(self.ctx, B, self.bg_dim, 256, "Gaussian_FC_Bg/G_FC", "Bg_FCDis_", dev)}
+        self.B = B
+
+    def param_groups(self):
+        return [g for f in self.f.values() for g in (f.gp, f.dp)]
+
+    def load_params(self, params):
+        for grp in self.param_groups():
+            for name in grp.specs:
+                if name in params:
+                    grp.view(name).copy_(torch.as_tensor(np.asarray(params[name]), dtype=torch.float32).to(self.s1.device))
+
+    def get_params(self, grads=False):
+        out = OrderedDict()
+        for grp in self.param_groups():
+            for name in grp.specs:
+                out[name] = (grp.gview(name) if grads else grp.view(name)).detach().cpu().numpy().copy()
+        return out
+
+    def sample_noise(self, factor, z=None):
+        f = self.f[factor]
+        if z is None:
+            f.z.data.normal_(0.0, 0.2)      # tf.random_normal(z_shape, 0.0, 0.2)   models.py:477
+        else:
+            f.z.data.copy_(torch.as_tensor(z, dtype=torch.float32).to(self.s1.device))
+
+    def encode_real(self):
+        """Real embeddings of the current Stage-I batch (frozen encoder forward, trainer.py:737-741)."""
+        s = torch.cuda.current_stream().cuda_stream
+        self.s1.run_encoder(s)
+        self.f["fg"].real.data.copy_(self.s1.emb[:, :self.fg_dim])
+        self.f["bg"].real.data.copy_(self.s1.emb[:, self.fg_dim:])
+
+    def _optim(self, f, which, s):
+        grp = f.gp if which == "g" else f.dp
+        lr = self.g_lr if which == "g" else self.d_lr
+        f.t[which] += 1
+        if self.mode in ("wgan", "lsgan"):
+            clip = 0.01 if (self.mode == "wgan" and which == "d") else 0.0
+            self.ctx.rmsprop_step(ptr(grp.value), ptr(grp.grad), ptr(grp.v), grp.total, lr, 0.9, 1e-10, 1.0, clip, s)
+        else:
+            self.ctx.adam_step(ptr(grp.value), ptr(grp.grad), ptr(grp.m), ptr(grp.v), grp.total, lr, 0.5, 0.999, 1e-8,
+                               f.t[which], 1.0, s)
+
+    def g_grads(self, factor):
+        f = self.f[factor]
+        s = torch.cuda.current_stream().cuda_stream
+        f.gp.grad.zero_()
+        f.p_g_fwd.run(s)
+        c = f.crit["fake"]
+        c["fwd"].run(s)
+        self.ctx.loss_gan(self.gan_mode, None, ptr(c["out"].data), self.B, ptr(f.loss), ptr(c["out"].grad), None, None, s)
+        c["bwd_data"].run(s)
+        f.fake.grad.copy_(c["x"].grad)
+        f.p_g_bwd.run(s)
+
+    def d_grads(self, factor):
+        f = self.f[factor]
+        s = torch.cuda.current_stream().cuda_stream
+        f.dp.grad.zero_()
+        f.p_g_fwd.run(s)
+        cr, cf = f.crit["real"], f.crit["fake"]
+        cr["fwd"].run(s)
+        cf["fwd"].run(s)
+        self.ctx.loss_gan(self.gan_mode, ptr(cr["out"].data), ptr(cf["out"].data), self.B, ptr(f.loss), None,
+                          ptr(cr["out"].grad), ptr(cf["out"].grad), s)
+        cr["bwd_par"].run(s)
+        cf["bwd_par"].run(s)
+
+    def g_step(self, factor):
+        self.g_grads(factor)
+        self._optim(self.f[factor], "g", torch.cuda.current_stream().cuda_stream)
+
+    def d_step(self, factor):
+        self.d_grads(factor)
+        self._optim(self.f[factor], "d", torch.cuda.current_stream().cuda_stream)
+
+    def train_iteration(self, step, next_batch):
+        """trainer.py:821-845: per factor, one generator update (skipped at step 0) then CRITIC_ITERS critic updates
+        (+clip, fused into the RMSProp kernel), every optimiser call on a fresh batch / fresh noise."""
+        iters = 1 if self.mode in ("dcgan", "lsgan") else 5
+        for factor in ("fg", "bg"):
+            if step > 0:
+                self.sample_noise(factor)
+                self.g_step(factor)
+            for _ in range(iters):
+                self.s1.set_batch(next_batch())
+                self.encode_real()
+                self.sample_noise(factor)
+                self.d_step(factor)

@@ -186,6 +186,9 @@ int dpig_linear_fwd(dpig_ctx* ctx, const float* x, const float* w, const float* 
 /* dx[m,k] = dy[m,n] w[k,n]^T ; dw[k,n] += x^T dy ; db[n] += sum_m dy */
 int dpig_linear_bwd(dpig_ctx* ctx, const float* x, const float* w, const float* dy, float* dx,
                     float* dw, float* db, int32_t m, int32_t k, int32_t n, dpig_stream stream);
+/* out = sa*a + sb*b (b may be NULL): residual adds of the FC nets (models.py:483, 496, 509) */
+int dpig_add_f32(dpig_ctx* ctx, float* out, const float* a, const float* b, int64_t count, float sa, float sb,
+                 dpig_stream stream);
 /* dy *= (y > 0 ? 1 : neg) in place, for activated linear layers */
 int dpig_act_bwd_f32(dpig_ctx* ctx, const float* y, float* dy, int64_t count, float neg,
                      dpig_stream stream);

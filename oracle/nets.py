@@ -355,3 +355,44 @@ class Stage1Trainer:
         out, grads = stage1_grads(self.p, self.cfg, batch, "d", self.mode, gp_alpha)
         self._apply(grads, "d")
         return out, grads
+
+
+# --------------------------------------------------------------------------------- Stage-II (--model=3)
+def init_stage2_params(fg_dim=224, bg_dim=128, seed=4321, bias_noise=0.0):
+    """Parameters of the two GaussianFCRes nets (scopes Gaussian_FC_Fg / Gaussian_FC_Bg, trainer.py:752-758;
+    slim xavier_uniform) and the two FC critics (names 'Fg_FCDis_' / 'Bg_FCDis_', trainer.py:764-775; tflib Linear
+    'he' for the LeakyReLULayers wgan_gp.py:30-32, glorot for .Out, tflib/ops/linear.py:36-66)."""
+    rng = np.random.default_rng(seed)
+    p = OrderedDict()
+    for scope, dim, hid in (("Gaussian_FC_Fg/G_FC", fg_dim, 512), ("Gaussian_FC_Bg/G_FC", bg_dim, 256)):
+        s = _Scope(scope, p, rng)
+        s.fc(dim, hid)
+        for _ in range(8):
+            s.fc(hid, hid)
+        s.fc(hid, dim)
+    for name, dim in (("Fg_FCDis_", fg_dim), ("Bg_FCDis_", bg_dim)):
+        dims = [("Input", dim, 512)] + [(str(i), 512, 512) for i in range(3)]
+        for tag, a, b in dims:
+            std = math.sqrt(2.0 / a)
+            p[name + "Discriminator.%s.Linear.W" % tag] = rng.uniform(-std * math.sqrt(3), std * math.sqrt(3), size=(a, b)).astype(np.float32)
+            p[name + "Discriminator.%s.Linear.b" % tag] = np.zeros(b, np.float32)
+        std = math.sqrt(2.0 / (512 + 1))
+        p[name + "Discriminator.Out.W"] = rng.uniform(-std * math.sqrt(3), std * math.sqrt(3), size=(512, 1)).astype(np.float32)
+        p[name + "Discriminator.Out.b"] = np.zeros(1, np.float32)
+    if bias_noise > 0:
+        for k in p:
+            if k.endswith(("biases", ".b")):
+                p[k] = (p[k] + rng.normal(0, bias_noise, size=p[k].shape)).astype(np.float32)
+    return p
+
+
+def stage2_losses(p, factor, real, z, mode="wgan"):
+    """g_loss_embs / d_loss_embs of one factor (trainer.py:752-775): fake = GaussianFCRes(z) with
+    activation_fn=LeakyReLU; critic = FCDiscriminator on real and fake embeddings."""
+    scope = "Gaussian_FC_%s/G_FC" % ("Fg" if factor == "fg" else "Bg")
+    name = "Fg_FCDis_" if factor == "fg" else "Bg_FCDis_"
+    fake = gaussian_fc_res(p, z, repeat_num=4, prefix=scope, act=lambda t: T.leaky_relu(t, 0.2))
+    d_real = fc_discriminator(p, real, name=name)
+    d_fake = fc_discriminator(p, fake, name=name)
+    g_loss, d_loss = T.gan_loss(mode, d_real, d_fake)
+    return dict(fake=fake, d_real=d_real, d_fake=d_fake, g_loss=g_loss, d_loss=d_loss)
