@@ -31,7 +31,8 @@ def test_dcgan_discriminator_mirror(mode):
     out = net.DCGANDiscriminator(x.permute(0, 3, 1, 2).cuda(), input_dim=3)
     out2 = net.DCGANDiscriminator(x.permute(0, 3, 1, 2).cuda(), input_dim=3)          # same names -> same weights
     ref = nets.dcgan_discriminator(nets.to_torch(p), cfg, x.double(), mode)
-    assert out.shape == (3,) and torch.equal(out, out2)
+    # same names -> same weights; split-K fp32 atomics make the two runs equal only to rounding
+    assert out.shape == (3,) and torch.allclose(out, out2, atol=1e-5)
     assert float((out.double().cpu() - ref).abs().max()) < 1e-3
     assert len(lib.params_with_name("Discriminator.")) == len(p) + (6 if mode == "dcgan" else 0)  # + moving stats
     lib.delete_all_params()
