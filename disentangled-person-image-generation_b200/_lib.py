@@ -32,7 +32,8 @@ class ConvEpilogue(C.Structure):
     _fields_ = [("bias", C.c_void_p), ("act", C.c_int32), ("alpha", C.c_float),
                 ("addend", C.POINTER(Tensor)), ("mask_in", C.c_void_p), ("mask_neg", C.c_float),
                 ("mask_out", C.c_void_p), ("out", C.POINTER(Tensor)), ("out_masked", C.POINTER(Tensor)),
-                ("out_f32", C.c_void_p), ("out_f32_pix_stride", C.c_int64), ("upsample", C.c_int32)]
+                ("out_f32", C.c_void_p), ("out_f32_pix_stride", C.c_int64), ("upsample", C.c_int32),
+                ("class_bias", C.c_void_p)]
 
 
 _P = C.c_void_p
@@ -49,6 +50,10 @@ _SIGNATURES = {
     "dpig_conv2d_fwd": [_T, _P, _P, _I, _I, _I, _I, C.POINTER(ConvEpilogue), _P],
     "dpig_conv2d_bwd_data": [_T, _P, _P, _I, _I, _I, _I, _I, _I, C.POINTER(ConvEpilogue), _P],
     "dpig_conv2d_bwd_filter": [_T, _T, _I, _I, _I, _I, _I, _P, _P],
+    "dpig_conv2d_bwd_filter_rows": [_T, _T, _I, _I, _I, _I, _I, _P, _I, _P],
+    "dpig_weight_pack_rows": [_P, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P],
+    "dpig_stem_class_bias": [_P, _I, _I, _I, _I, _P, _P],
+    "dpig_stem_tap_sums": [_T, _P, _P, _P],
     "dpig_conv2d_small_fwd": [_P, _I, _I, _I, _I, _P, _P, _I, _I, _I, _I, _I, _F, _T, _P, _P, _P],
     "dpig_conv2d_small_bwd_data": [_P, _I, _I, _I, _I, _P, _I, _I, _I, _I, _I, _I, _P, _P],
     "dpig_conv2d_small_bwd_filter": [_P, _I, _I, _I, _I, _P, _I, _I, _I, _I, _P, _P],

@@ -48,6 +48,7 @@ struct ConvUmmaParams {
   int block_n, cout, stages;
   uint32_t a_tx_bytes, b_bytes, tmem_cols;
   const float* bias;
+  const float* class_bias;  // [N][9][cout]: per-image bias indexed by the pixel's border class (stem shortcut)
   int act;
   float alpha;
   int sh, sw, oh, ow, rep, out_H, out_W;
@@ -248,6 +249,11 @@ conv_umma_kernel(const __grid_constant__ ConvUmmaParams p) {
       const long long lpix = (static_cast<long long>(n) * p.Ho + h) * p.Wo + w;  // logical pixel
       const int py = h * p.sh + p.oh, px = w * p.sw + p.ow;
       const long long ppix = (static_cast<long long>(n) * p.out_H + py) * p.out_W + px;
+      const float* cbias = nullptr;
+      if (p.class_bias && valid) {
+        const int ch = h == 0 ? 0 : (h == p.Ho - 1 ? 2 : 1), cw = w == 0 ? 0 : (w == p.Wo - 1 ? 2 : 1);
+        cbias = p.class_bias + (static_cast<long long>(n) * 9 + ch * 3 + cw) * p.cout;
+      }
 
       ptx::mbar_wait(&tmem_full[acc], (j >> 1) & 1);
       ptx::tc_fence_after();
@@ -272,6 +278,7 @@ conv_umma_kernel(const __grid_constant__ ConvUmmaParams p) {
         for (int i = 0; i < 32; ++i) {
           float x = __uint_as_float(v[i]);
           if (p.bias && i < nvalid) x += __ldg(p.bias + cbase + i);
+          if (cbias && i < nvalid) x += __ldg(cbias + cbase + i);
           mbits |= (x > 0.f ? 1u : 0u) << i;
           if (p.act == DPIG_ACT_RELU) x = fmaxf(x, 0.f);
           else if (p.act == DPIG_ACT_LRELU) x = x > 0.f ? x : p.alpha * x;
@@ -370,6 +377,7 @@ struct WgradParams {
   int PW, PH, PN, tiles_w, tiles_h;
   int total_tiles, tiles_per_cta;
   int block_n, n_tiles, cin, cout, stages;
+  int cin_pitch;  // rows per tap in the HWIO gradient (>= cin when dw is a row-slice of a wider filter)
   uint32_t b_bytes, tmem_cols;
   float* dw;
 };
@@ -485,7 +493,7 @@ wgrad_umma_kernel(const __grid_constant__ WgradParams p) {
         ptx::tmem_ld_wait();
         const int cbase = nt * p.block_n + c0;
         if (ci < p.cin) {
-          float* o = p.dw + (static_cast<long long>(tap.wtap) * p.cin + ci) * p.cout + cbase;
+          float* o = p.dw + (static_cast<long long>(tap.wtap) * p.cin_pitch + ci) * p.cout + cbase;
 #pragma unroll
           for (int i = 0; i < 32; ++i)
             if (cbase + i < p.cout) atomicAdd(o + i, __uint_as_float(v[i]));
@@ -614,6 +622,7 @@ struct EpilogueGeom {
 static int fill_epilogue(dpig_ctx* ctx, ConvUmmaParams& P, const dpig_conv_epilogue* ep,
                          const EpilogueGeom& g, int n, int cout) {
   P.bias = ep->bias;
+  P.class_bias = ep->class_bias;
   P.act = ep->act;
   P.alpha = ep->alpha;
   P.sh = g.sh;
@@ -844,9 +853,23 @@ extern "C" int dpig_conv2d_bwd_data(dpig_ctx* ctx, const dpig_tensor* dy, const 
   return DPIG_OK;
 }
 
+static int wgrad_impl(dpig_ctx* ctx, const dpig_tensor* x, const dpig_tensor* dy, int32_t kh, int32_t kw,
+                      int32_t stride, int32_t cin, int32_t cout, float* dw, int32_t cin_pitch, dpig_stream stream);
+
 extern "C" int dpig_conv2d_bwd_filter(dpig_ctx* ctx, const dpig_tensor* x, const dpig_tensor* dy,
                                       int32_t kh, int32_t kw, int32_t stride, int32_t cin,
                                       int32_t cout, float* dw, dpig_stream stream) {
+  return wgrad_impl(ctx, x, dy, kh, kw, stride, cin, cout, dw, cin, stream);
+}
+
+extern "C" int dpig_conv2d_bwd_filter_rows(dpig_ctx* ctx, const dpig_tensor* x, const dpig_tensor* dy,
+                                           int32_t kh, int32_t kw, int32_t stride, int32_t cin, int32_t cout,
+                                           float* dw_rows, int32_t cin_total, dpig_stream stream) {
+  return wgrad_impl(ctx, x, dy, kh, kw, stride, cin, cout, dw_rows, cin_total, stream);
+}
+
+static int wgrad_impl(dpig_ctx* ctx, const dpig_tensor* x, const dpig_tensor* dy, int32_t kh, int32_t kw,
+                      int32_t stride, int32_t cin, int32_t cout, float* dw, int32_t cin_pitch, dpig_stream stream) {
   DPIG_CHECK_CTX(ctx);
   if (!x || !dy || !dw) return set_error(ctx, DPIG_EINVAL, "conv2d_bwd_filter: null argument");
   if (kh * kw > kMaxTaps || (stride != 1 && stride != 2))
@@ -862,6 +885,7 @@ extern "C" int dpig_conv2d_bwd_filter(dpig_ctx* ctx, const dpig_tensor* x, const
   memset(&P, 0, sizeof(P));
   P.planes = (x->lo && dy->lo && !ctx->fast_mode) ? 2 : 1;
   P.cin = cin;
+  P.cin_pitch = cin_pitch;
   P.cout = cout;
   const int c64 = (cout + 63) / 64 * 64;
   P.block_n = c64 <= 256 ? c64 : (c64 % 256 == 0 ? 256 : (c64 % 192 == 0 ? 192 : (c64 % 128 == 0 ? 128 : 64)));

@@ -187,6 +187,7 @@ bias_grad_kernel(TView g, const float* f32, long long f32_ps, float* db, int C, 
     const int ch = (cg0 + cg) * 8;
     float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     if (prow < rows && ch < C) {
+#pragma unroll 4
       for (long long p = p0 + prow; p < p1; p += rows) {
         if (f32) {
 #pragma unroll
@@ -238,11 +239,11 @@ __global__ void denorm_u8_kernel(const float* g, long long count, uint8_t* out) 
 // One tap at a time: w[tap][ci][co] -> fwd[tap][co][ci_pad] (transposed) and bwd[tap][ci][co_pad].
 __global__ void weight_pack_kernel(const float* w, int cin, int cout, int cin_pad, int cout_pad,
                                    __nv_bfloat16* fhi, __nv_bfloat16* flo, __nv_bfloat16* bhi,
-                                   __nv_bfloat16* blo) {
+                                   __nv_bfloat16* blo, int cin_total) {
   __shared__ float tile[32][33];
   const int tap = blockIdx.z;
   const int ci0 = blockIdx.y * 32, co0 = blockIdx.x * 32;
-  const float* wt = w + static_cast<long long>(tap) * cin * cout;
+  const float* wt = w + static_cast<long long>(tap) * cin_total * cout;
   for (int r = threadIdx.y; r < 32; r += blockDim.y) {
     const int ci = ci0 + r, co = co0 + threadIdx.x;
     const float v = (ci < cin && co < cout) ? wt[static_cast<long long>(ci) * cout + co] : 0.f;
@@ -430,9 +431,106 @@ extern "C" int dpig_weight_pack(dpig_ctx* ctx, const float* w_hwio, int32_t taps
   weight_pack_kernel<<<grid, block, 0, static_cast<cudaStream_t>(stream)>>>(
       w_hwio, cin, cout, cin_pad, cout_pad, static_cast<__nv_bfloat16*>(fwd_hi),
       static_cast<__nv_bfloat16*>(fwd_lo), static_cast<__nv_bfloat16*>(bwd_hi),
-      static_cast<__nv_bfloat16*>(bwd_lo));
+      static_cast<__nv_bfloat16*>(bwd_lo), cin);
   ctx->launches++;
   return check_launch(ctx, "weight_pack");
+}
+
+extern "C" int dpig_weight_pack_rows(dpig_ctx* ctx, const float* w_hwio, int32_t taps, int32_t cin_total, int32_t ci0,
+                                     int32_t cin, int32_t cout, int32_t cin_pad, int32_t cout_pad, void* fwd_hi,
+                                     void* fwd_lo, void* bwd_hi, void* bwd_lo, dpig_stream stream) {
+  DPIG_CHECK_CTX(ctx);
+  if (!w_hwio || cin_pad < cin || cout_pad < cout || ci0 + cin > cin_total)
+    return set_error(ctx, DPIG_EINVAL, "weight_pack_rows: bad argument");
+  dim3 grid((std::max(cout, cout_pad) + 31) / 32, (std::max(cin, cin_pad) + 31) / 32, taps);
+  dim3 block(32, 8);
+  weight_pack_kernel<<<grid, block, 0, static_cast<cudaStream_t>(stream)>>>(
+      w_hwio + static_cast<long long>(ci0) * cout, cin, cout, cin_pad, cout_pad, static_cast<__nv_bfloat16*>(fwd_hi),
+      static_cast<__nv_bfloat16*>(fwd_lo), static_cast<__nv_bfloat16*>(bwd_hi), static_cast<__nv_bfloat16*>(bwd_lo),
+      cin_total);
+  ctx->launches++;
+  return check_launch(ctx, "weight_pack_rows");
+}
+
+namespace dpig {
+// border class c = rh*3 + rw (r = 0 first, 1 interior, 2 last); tap (ky,kx) of a 3x3 SAME conv reads inside the
+// image for row class rh iff ky != 0 when rh == 0 and ky != 2 when rh == 2 (same for columns).
+__device__ __forceinline__ bool tap_valid(int cls, int tap, int H, int W) {
+  const int rh = cls / 3, rw = cls % 3, ky = tap / 3, kx = tap % 3;
+  (void)H;
+  (void)W;  // H, W >= 2 (checked by the callers): every pixel has exactly one row class and one column class
+  const bool vy = !((rh == 0 && ky == 0) || (rh == 2 && ky == 2));
+  const bool vx = !((rw == 0 && kx == 0) || (rw == 2 && kx == 2));
+  return vy && vx;
+}
+__global__ void stem_class_bias_kernel(const float* e, int N, int C, int H, int W, float* out) {
+  const int total = N * 9 * C;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int c = i % C, cls = (i / C) % 9, n = i / (9 * C);
+    float acc = 0.f;
+    for (int tap = 0; tap < 9; ++tap)
+      if (tap_valid(cls, tap, H, W)) acc += e[(static_cast<long long>(tap) * N + n) * C + c];
+    out[i] = acc;
+  }
+}
+// grid = (pixel chunks, N); 9 class bins per thread-channel kept in registers.
+__global__ void stem_class_sum_kernel(TView g, int C, int H, int W, int chunk, float* out) {
+  const int n = blockIdx.y;
+  const long long ppi = static_cast<long long>(H) * W;
+  const long long p0 = static_cast<long long>(blockIdx.x) * chunk;
+  const long long p1 = min(p0 + chunk, ppi);
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float acc[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    for (long long p = p0; p < p1; ++p) {
+      const int h = static_cast<int>(p / W), w = static_cast<int>(p % W);
+      const int cls = (h == 0 ? 0 : (h == H - 1 ? 2 : 1)) * 3 + (w == 0 ? 0 : (w == W - 1 ? 2 : 1));
+      const long long off = (n * ppi + p) * g.ps + c;
+      float v = __bfloat162float(g.hi[off]);
+      if (g.lo) v += __bfloat162float(g.lo[off]);
+#pragma unroll
+      for (int k = 0; k < 9; ++k) acc[k] += (k == cls) ? v : 0.f;
+    }
+#pragma unroll
+    for (int k = 0; k < 9; ++k)
+      if (acc[k] != 0.f) atomicAdd(out + (static_cast<long long>(n) * 9 + k) * C + c, acc[k]);
+  }
+}
+__global__ void stem_tap_sums_kernel(const float* cls_sums, int N, int C, int H, int W, float* taps) {
+  const int total = 9 * N * C;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int c = i % C, n = (i / C) % N, tap = i / (N * C);
+    float acc = 0.f;
+    for (int cls = 0; cls < 9; ++cls)
+      if (tap_valid(cls, tap, H, W)) acc += cls_sums[(static_cast<long long>(n) * 9 + cls) * C + c];
+    taps[i] = acc;
+  }
+}
+}  // namespace dpig
+
+extern "C" int dpig_stem_class_bias(dpig_ctx* ctx, const float* e_taps, int32_t n, int32_t cout, int32_t h, int32_t w_,
+                                    float* class_bias, dpig_stream stream) {
+  DPIG_CHECK_CTX(ctx);
+  if (!e_taps || !class_bias || h < 2 || w_ < 2) return set_error(ctx, DPIG_EINVAL, "stem_class_bias: bad argument");
+  const int total = n * 9 * cout;
+  stem_class_bias_kernel<<<(total + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(e_taps, n, cout, h, w_, class_bias);
+  ctx->launches++;
+  return check_launch(ctx, "stem_class_bias");
+}
+
+extern "C" int dpig_stem_tap_sums(dpig_ctx* ctx, const dpig_tensor* g, float* class_sums, float* tap_sums,
+                                  dpig_stream stream) {
+  DPIG_CHECK_CTX(ctx);
+  if (!g || !class_sums || !tap_sums || g->h < 2 || g->w < 2) return set_error(ctx, DPIG_EINVAL, "stem_tap_sums: bad argument");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  cudaMemsetAsync(class_sums, 0, sizeof(float) * g->n * 9 * g->c, s);
+  const long long ppi = static_cast<long long>(g->h) * g->w;
+  const int chunk = 64;
+  dim3 grid(static_cast<unsigned>((ppi + chunk - 1) / chunk), g->n);
+  stem_class_sum_kernel<<<grid, 128, 0, s>>>(view(g), g->c, g->h, g->w, chunk, class_sums);
+  const int total = 9 * g->n * g->c;
+  stem_tap_sums_kernel<<<(total + 255) / 256, 256, 0, s>>>(class_sums, g->n, g->c, g->h, g->w, tap_sums);
+  ctx->launches += 2;
+  return check_launch(ctx, "stem_tap_sums");
 }
 
 namespace dpig {

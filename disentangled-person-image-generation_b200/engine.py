@@ -306,8 +306,8 @@ class Stage1Engine:
         # ID_AE/G (models.py:518-576)
         sc, cc, fc_c = "ID_AE/G", [0], [0]
         self.gin_c = cfg.emb_dim + cfg.keypoints
-        self.gin_cpad = (self.gin_c + 63) // 64 * 64
-        self.n_gstem = conv(gspecs, sc, cc, 3, 1, self.gin_c, hn, cin_pad=self.gin_cpad)
+        self.pose_cpad = _pad8(cfg.keypoints)
+        self.n_gstem = conv(gspecs, sc, cc, 3, 1, self.gin_c, hn, need_bwd=False)
         self.n_genc = pyramid(sc, cc)
         self.n_gfc1 = fc(gspecs, sc, fc_c, self.bg_flat, cfg.z_num)
         self.n_gfc2 = fc(gspecs, sc, fc_c, cfg.z_num, self.fh * self.fw * hn)
@@ -347,6 +347,18 @@ class Stage1Engine:
         self.dp = ParamGroup(dspecs, dev)
         self.conv = OrderedDict()
         for name, s in self.layers.items():
+            if name == self.n_gstem:
+                # stem shortcut: the 352 embedding rows never reach the tensor cores (dpig_stem_class_bias);
+                # the packed operand holds the 18 pose rows only
+                lay = ConvLayer(self.gp, name + "/weights", name + "/biases", 3, 1, self.gin_c, hn, dev, False, True)
+                lay.small = False
+                lay.cin_pad = self.pose_cpad
+                lay.fwd = torch.zeros((2, 9, hn, self.pose_cpad), dtype=torch.bfloat16, device=dev)
+                lay.bwd = None
+                lay.stem = True
+                lay.flops_cin = cfg.keypoints   # executed work; the reference's algorithmic count has 370 channels
+                self.conv[name] = lay
+                continue
             if name.startswith("Discriminator"):
                 self.conv[name] = ConvLayer(self.dp, name + ".Filters", name + ".Biases", s["k"], s["stride"], s["cin"],
                                             s["cout"], dev, s["need_bwd"], s["small"], s["cin_pad"])
@@ -393,6 +405,11 @@ class Stage1Engine:
         for name, layer in self.conv.items():
             if layer.small or (name.startswith("Discriminator") != (which == "d")):
                 continue
+            if getattr(layer, "stem", False):
+                e = self.cfg.emb_dim
+                self.ctx.weight_pack_rows(ptr(layer.w), 9, layer.cin, e, layer.cin - e, layer.cout, layer.cin_pad,
+                                          layer.cout_pad, ptr(layer.fwd[0]), ptr(layer.fwd[1]), None, None, s)
+                continue
             self.ctx.weight_pack(ptr(layer.w), layer.k * layer.k, layer.cin, layer.cout, layer.cin_pad, layer.cout_pad,
                                  ptr(layer.fwd[0]), ptr(layer.fwd[1]),
                                  ptr(layer.bwd[0]) if layer.bwd is not None else None,
@@ -428,7 +445,12 @@ class Stage1Engine:
         self.bg_fea = torch.zeros((B, cfg.part_z * 4), device=dev)
         self.emb = torch.zeros((B, cfg.emb_dim), device=dev)
         # generator
-        self.gin = SplitTensor(B, H, W, self.gin_cpad, dev, zero=True)
+        self.gin = SplitTensor(B, H, W, self.pose_cpad, dev, zero=True)      # pose maps only (channels 0..17)
+        self.stem_e = torch.zeros((9, B, hn), device=dev)                    # E[tap][n][co] = emb . W[tap, :352]
+        self.stem_cb = torch.zeros((B, 9, hn), device=dev)                   # per-image border-class bias
+        self.stem_cls = torch.zeros((B, 9, hn), device=dev)
+        self.stem_ts = torch.zeros((9, B, hn), device=dev)
+        self.stem_tmp = torch.zeros((B, cfg.emb_dim), device=dev)
         self.g0 = SplitTensor(B, H, W, hn, dev)
         self.mg0 = _mask(B * H * W, hn, dev)
         # decoder concat buffers; the encoder skip outputs are slices of them
@@ -476,7 +498,6 @@ class Stage1Engine:
         self.g_dec_in_f32 = torch.zeros((B, self.fh * self.fw * hn), device=dev)
         self.g_z = torch.zeros((B, cfg.z_num), device=dev)
         self.g_gtop_f32 = torch.zeros((B, self.bg_flat), device=dev)
-        self.g_gin = SplitTensor(B, H, W, self.gin_cpad, dev)
         self.g_emb = torch.zeros((B, cfg.emb_dim), device=dev)
         # encoder backward
         self.g_fea = torch.zeros((P * B, cfg.part_z), device=dev)
@@ -531,8 +552,10 @@ class Stage1Engine:
 
     # -------------------------------------------------------------------------------- call helpers
     def _epilogue(self, prog, layer_bias, act, alpha, addend, mask_in, mask_neg, mask_out, out, out_masked, out_f32,
-                  out_f32_ps, upsample):
+                  out_f32_ps, upsample, class_bias=None):
         ep = _lib.ConvEpilogue()
+        if class_bias is not None:
+            ep.class_bias = class_bias.data_ptr()
         ep.bias = layer_bias.data_ptr() if layer_bias is not None else None
         ep.act = act
         ep.alpha = alpha
@@ -555,14 +578,15 @@ class Stage1Engine:
         return C.byref(ep)
 
     def conv_fwd(self, prog, layer, x, out=None, act=ACT_RELU, alpha=0.2, addend=None, mask_out=None, out_f32=None,
-                 out_f32_ps=0, upsample=1, bias=True, out_masked=None, mask_in=None, mask_neg=0.0):
+                 out_f32_ps=0, upsample=1, bias=True, out_masked=None, mask_in=None, mask_neg=0.0, class_bias=None):
         ep = self._epilogue(prog, layer.b if bias else None, act, alpha, addend, mask_in, mask_neg, mask_out, out,
-                            out_masked, out_f32, out_f32_ps, upsample)
+                            out_masked, out_f32, out_f32_ps, upsample, class_bias)
         assert x.c == layer.cin_pad, (layer.wname, x.c, layer.cin_pad)
         oh, ow = -(-x.h // layer.stride), -(-x.w // layer.stride)
         prog.add("conv2d_fwd", x.ref(), ptr(layer.fwd[0]), ptr(layer.fwd[1]), layer.k, layer.k, layer.stride, layer.cout, ep,
-                 flops=2.0 * x.n * oh * ow * layer.cout * layer.k * layer.k * layer.cin,
-                 tag="%s %dx%dx%dx%d->%d k%ds%d" % (layer.wname, x.n, x.h, x.w, layer.cin, layer.cout, layer.k, layer.stride))
+                 flops=2.0 * x.n * oh * ow * layer.cout * layer.k * layer.k * getattr(layer, "flops_cin", layer.cin),
+                 tag="%s %dx%dx%dx%d->%d k%ds%d" % (layer.wname, x.n, x.h, x.w, getattr(layer, "flops_cin", layer.cin),
+                                                    layer.cout, layer.k, layer.stride))
 
     def conv_dgrad(self, prog, layer, dy, in_h, in_w, out=None, out_masked=None, mask_in=None, mask_neg=0.0, addend=None,
                    out_f32=None, out_f32_ps=0):
@@ -708,11 +732,18 @@ class Stage1Engine:
     def _prog_unet_forward(self, p):
         cfg, B = self.cfg, self.B
         H, W, hn, rn = cfg.img_h, cfg.img_w, cfg.hidden, cfg.repeat_num
-        p.add("broadcast_embedding", ptr(self.emb), cfg.emb_dim, self.gin.ref())
-        pose_slice = self.gin.slice(cfg.emb_dim, cfg.keypoints)
+        # stem (models.py:528) on concat(tiled embedding, pose): the embedding channels are constant over space
+        # (trainer.py:588-590), so their 3x3 contribution is a per-image, per-border-class bias
+        stem = self.conv[self.n_gstem]
+        wt = stem.w.view(9, self.gin_c, hn)
+        for tap in range(9):
+            p.add("linear_fwd", ptr(self.emb), ptr(wt[tap]), None, ptr(self.stem_e[tap]), B, cfg.emb_dim, hn,
+                  ACT_NONE, 0.0)
+        p.add("stem_class_bias", ptr(self.stem_e), B, hn, H, W, ptr(self.stem_cb))
+        pose_slice = self.gin.slice(0, cfg.keypoints)
         self._keep.append(pose_slice)
         p.add("pose_rasterize", ptr(self.pose_rcv), B, cfg.keypoints, H, W, 4, pose_slice.ref(), None)
-        self.conv_fwd(p, self.conv[self.n_gstem], self.gin, out=self.g0, mask_out=self.mg0)
+        self.conv_fwd(p, stem, self.gin, out=self.g0, mask_out=self.mg0, class_bias=self.stem_cb)
         self.genc.forward(self, p)
         top = self.genc.y[rn - 1]
         p.add("unpack_f32", top.ref(), ptr(self.gtop_f32), hn * rn)
@@ -786,11 +817,19 @@ class Stage1Engine:
               None, 0.0, 0)
         self.genc.backward(self, p, skip_grads=skip)
         ls = self.conv[self.n_gstem]
-        self.conv_wgrad(p, ls, self.gin, self.genc.g_in)
-        self.conv_dgrad(p, ls, self.genc.g_in, H, W, out=self.g_gin)
-        gemb = self.g_gin.slice(0, cfg.emb_dim)
-        self._keep.append(gemb)
-        p.add("spatial_sum", gemb.ref(), ptr(self.g_emb))
+        gi = self.genc.g_in
+        e = cfg.emb_dim
+        wt = ls.w.view(9, self.gin_c, hn)
+        dwt = ls.dw.view(9, self.gin_c, hn)
+        # pose rows of the filter gradient on the tensor cores; embedding rows and d(emb) from per-tap sums of g
+        p.add("conv2d_bwd_filter_rows", self.gin.ref(), gi.ref(), 3, 3, 1, cfg.keypoints, hn, ptr(dwt[0, e:]), self.gin_c,
+              flops=2.0 * B * H * W * hn * 9 * cfg.keypoints, tag="%s pose rows" % ls.wname)
+        p.add("bias_grad", gi.ref(), ptr(ls.db))
+        p.add("stem_tap_sums", gi.ref(), ptr(self.stem_cls), ptr(self.stem_ts))
+        for tap in range(9):
+            p.add("linear_bwd", ptr(self.emb), ptr(wt[tap]), ptr(self.stem_ts[tap]), ptr(self.stem_tmp), ptr(dwt[tap]),
+                  None, B, e, hn)
+            p.add("add_f32", ptr(self.g_emb), ptr(self.stem_tmp), ptr(self.g_emb) if tap else None, B * e, 1.0, 1.0)
         # ---- appearance encoder
         p.add("embedding_assemble", ptr(self.g_fea), ptr(self.g_bg_fea), ptr(self.vis), B, P, cfg.part_z, cfg.part_z * 4,
               ptr(self.g_emb), 1)

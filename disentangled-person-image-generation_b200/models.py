@@ -81,7 +81,7 @@ def GeneratorCNN_ID_UAEAfterResidual(x, pose, input_channel, z_num, repeat_num, 
     if pose_rcv is None:
         # drop the rasterisation call and inject the given maps into the stem-input slice instead
         prog.calls = [c for c in prog.calls if c[0] != "pose_rasterize"]
-        sl = eng.gin.slice(eng.cfg.emb_dim, eng.cfg.keypoints)
+        sl = eng.gin.slice(0, eng.cfg.keypoints)
         sl.set_from_float(torch.as_tensor(pose, dtype=torch.float32).to(eng.device))
     prog.run(s)
     return eng.G.clone(), eng.z.clone(), _variables(eng, "ID_AE/G")

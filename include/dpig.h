@@ -76,6 +76,10 @@ typedef struct dpig_conv_epilogue {
   float* out_f32;
   int64_t out_f32_pix_stride;
   int32_t upsample;
+  /* optional fp32 [n][9][cout]: extra bias selected by the output pixel's border class
+   * (row class 0/1/2 = first/interior/last row) * 3 + column class -- the exact contribution of input channels
+   * that are constant over space (the broadcast embedding, trainer.py:588-590), see dpig_stem_class_bias. */
+  const float* class_bias;
 } dpig_conv_epilogue;
 
 /* ---- context ----------------------------------------------------------------------------- */
@@ -116,6 +120,27 @@ int dpig_conv2d_bwd_data(dpig_ctx* ctx, const dpig_tensor* dy, const void* wb_hi
 int dpig_conv2d_bwd_filter(dpig_ctx* ctx, const dpig_tensor* x, const dpig_tensor* dy, int32_t kh,
                            int32_t kw, int32_t stride, int32_t cin, int32_t cout, float* dw,
                            dpig_stream stream);
+
+/* Same as dpig_conv2d_bwd_filter for a ROW SLICE of a wider filter: dw_rows points at row ci0 of tap 0 of an
+ * HWIO gradient whose taps are cin_total rows apart; rows [0,cin) of the slice are accumulated. */
+int dpig_conv2d_bwd_filter_rows(dpig_ctx* ctx, const dpig_tensor* x, const dpig_tensor* dy, int32_t kh,
+                                int32_t kw, int32_t stride, int32_t cin, int32_t cout, float* dw_rows,
+                                int32_t cin_total, dpig_stream stream);
+/* dpig_weight_pack for input-channel rows [ci0, ci0+cin) of a filter with cin_total rows per tap. */
+int dpig_weight_pack_rows(dpig_ctx* ctx, const float* w_hwio, int32_t taps, int32_t cin_total, int32_t ci0,
+                          int32_t cin, int32_t cout, int32_t cin_pad, int32_t cout_pad, void* fwd_hi,
+                          void* fwd_lo, void* bwd_hi, void* bwd_lo, dpig_stream stream);
+
+/* Stem shortcut for spatially constant input channels (the tiled embedding of trainer.py:588-590 entering the
+ * 3x3 SAME stem conv models.py:528): with E[tap][n][co] = sum_ci emb[n,ci] * W[tap,ci,co] (9 small GEMMs),
+ *   class_bias[n][class][co] = sum over the taps that fall inside the image for that border class of E,
+ * which dpig_conv2d_fwd adds per pixel (dpig_conv_epilogue.class_bias): exact, 3.5 GMAC/image cheaper.
+ * Backward: class_sums[n][class][co] = sum of g over the pixels of each border class;
+ *   tap_sums[tap][n][co] = sum over classes where the tap is inside = sum_pixels valid(tap) g  -> dW, d_emb. */
+int dpig_stem_class_bias(dpig_ctx* ctx, const float* e_taps /* [9][n][cout] */, int32_t n, int32_t cout,
+                         int32_t h, int32_t w_, float* class_bias /* [n][9][cout] */, dpig_stream stream);
+int dpig_stem_tap_sums(dpig_ctx* ctx, const dpig_tensor* g, float* class_sums /* [n][9][c] workspace */,
+                       float* tap_sums /* [9][n][c] */, dpig_stream stream);
 
 /* CUDA-core fp32 convolutions for the 3-channel ends of the networks (image in, image out):
  * x, y, dy, dx are plain fp32 NHWC here; w is the fp32 HWIO master. */
