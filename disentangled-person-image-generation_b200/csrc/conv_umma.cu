@@ -111,6 +111,70 @@ __device__ __forceinline__ void store_split32(__nv_bfloat16* hi, __nv_bfloat16* 
   }
 }
 
+constexpr uint32_t kEpiBytesPerWarp = 4096;  // 32 pixel rows x (64 B hi + 64 B lo)  or  32 x 128 B fp32
+
+// Byte offset of 16-byte piece `piece` of row `row` in a warp-private staging tile; XOR swizzles keep both the
+// "thread = row" and the "4 (8) lanes per row" access patterns free of shared-memory bank conflicts.
+__device__ __forceinline__ uint32_t swz64(int row, int piece) {   // 64 B rows, 4 pieces
+  return row * 64 + ((piece ^ ((row >> 1) & 3)) << 4);
+}
+__device__ __forceinline__ uint32_t swz128(int row, int piece) {  // 128 B rows, 8 pieces
+  return row * 128 + ((piece ^ (row & 7)) << 4);
+}
+
+// thread's 32 channels -> staging rows (hi plane at +0, lo plane at +2048)
+__device__ __forceinline__ void epi_stage_split(uint8_t* stage, const float (&f)[32], int lane, bool with_lo) {
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    uint32_t h[4], l[4];
+#pragma unroll
+    for (int jj = 0; jj < 4; ++jj) {
+      __nv_bfloat16 h0, l0, h1, l1;
+      split_bf16(f[q * 8 + 2 * jj], h0, l0);
+      split_bf16(f[q * 8 + 2 * jj + 1], h1, l1);
+      h[jj] = pack2(h0, h1);
+      l[jj] = pack2(l0, l1);
+    }
+    *reinterpret_cast<uint4*>(stage + swz64(lane, q)) = make_uint4(h[0], h[1], h[2], h[3]);
+    if (with_lo) *reinterpret_cast<uint4*>(stage + 2048 + swz64(lane, q)) = make_uint4(l[0], l[1], l[2], l[3]);
+  }
+}
+
+// staging rows -> global: each instruction writes 8 pixel rows x 64 contiguous bytes per plane
+__device__ __forceinline__ void epi_scatter_rows(const uint8_t* stage, __nv_bfloat16* hi, __nv_bfloat16* lo,
+                                                 long long ps, int cbase, int pix, bool valid, int lane) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int q = 8 * i + (lane >> 2), pc = lane & 3;
+    const int pq = __shfl_sync(0xffffffffu, pix, q);
+    const int vq = __shfl_sync(0xffffffffu, static_cast<int>(valid), q);
+    if (vq) {
+      const long long off = static_cast<long long>(pq) * ps + cbase + pc * 8;
+      *reinterpret_cast<uint4*>(hi + off) = *reinterpret_cast<const uint4*>(stage + swz64(q, pc));
+      if (lo) *reinterpret_cast<uint4*>(lo + off) = *reinterpret_cast<const uint4*>(stage + 2048 + swz64(q, pc));
+    }
+  }
+}
+
+// global -> staging rows (residual / addend), same access shape as epi_scatter_rows
+__device__ __forceinline__ void epi_gather_rows(uint8_t* stage, const __nv_bfloat16* hi, const __nv_bfloat16* lo,
+                                                long long ps, int cbase, int pix, bool valid, int lane) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int q = 8 * i + (lane >> 2), pc = lane & 3;
+    const int pq = __shfl_sync(0xffffffffu, pix, q);
+    const int vq = __shfl_sync(0xffffffffu, static_cast<int>(valid), q);
+    uint4 a = make_uint4(0, 0, 0, 0), b = make_uint4(0, 0, 0, 0);
+    if (vq) {
+      const long long off = static_cast<long long>(pq) * ps + cbase + pc * 8;
+      a = __ldg(reinterpret_cast<const uint4*>(hi + off));
+      if (lo) b = __ldg(reinterpret_cast<const uint4*>(lo + off));
+    }
+    *reinterpret_cast<uint4*>(stage + swz64(q, pc)) = a;
+    if (lo) *reinterpret_cast<uint4*>(stage + 2048 + swz64(q, pc)) = b;
+  }
+}
+
 // Persistent: grid = min(#tiles, #SMs); CTA b processes tiles b, b+grid, ...  The smem pipeline runs
 // continuously across tiles and the fp32 accumulator is double-buffered in TMEM (2 x block_n columns), so
 // the epilogue of tile j overlaps the MMAs of tile j+1.
@@ -125,6 +189,7 @@ conv_umma_kernel(const __grid_constant__ ConvUmmaParams p) {
   uint64_t* tmem_full = empty + p.stages;   // [2]
   uint64_t* tmem_empty = tmem_full + 2;     // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  uint8_t* epi_smem = smem + p.stages * stage_bytes + 256;  // 4 x kEpiBytesPerWarp, 256 B past the barriers
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -230,13 +295,16 @@ conv_umma_kernel(const __grid_constant__ ConvUmmaParams p) {
       }
     }
   } else {
-    // ---------------- epilogue: 4 warps, thread = one accumulator row (= one output pixel)
+    // ---------------- epilogue: 4 warps, thread = one accumulator row (= one output pixel).
+    // Global traffic goes through a warp-private 4 KB staging tile so that every warp-level load / store
+    // touches whole 64 B (bf16 planes) or 128 B (fp32) pixel rows instead of 32 scattered 16 B pieces.
     const int lg = warp & 3;
     const int r = lg * 32 + lane;
     const int wl = r % p.BW;
     const int tq = r / p.BW;
     const int hl = tq % p.BH;
     const int nl = tq / p.BH;
+    uint8_t* stage = epi_smem + lg * kEpiBytesPerWarp;
     int j = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++j) {
       const int acc = j & 1;
@@ -246,9 +314,9 @@ conv_umma_kernel(const __grid_constant__ ConvUmmaParams p) {
       const int tn = pt / (p.tiles_w * p.tiles_h);
       const int w = tw * p.BW + wl, h = th * p.BH + hl, n = tn * p.BN + nl;
       const bool valid = (nl < p.BN) && (w < p.Wo) && (h < p.Ho) && (n < p.No);
-      const long long lpix = (static_cast<long long>(n) * p.Ho + h) * p.Wo + w;  // logical pixel
+      const int lpix = (n * p.Ho + h) * p.Wo + w;  // logical pixel (< 2^31 for every supported shape)
       const int py = h * p.sh + p.oh, px = w * p.sw + p.ow;
-      const long long ppix = (static_cast<long long>(n) * p.out_H + py) * p.out_W + px;
+      const int ppix = (n * p.out_H + py) * p.out_W + px;
       const float* cbias = nullptr;
       if (p.class_bias && valid) {
         const int ch = h == 0 ? 0 : (h == p.Ho - 1 ? 2 : 1), cw = w == 0 ? 0 : (w == p.Wo - 1 ? 2 : 1);
@@ -271,7 +339,8 @@ conv_umma_kernel(const __grid_constant__ ConvUmmaParams p) {
         }
         const int cbase = nt * p.block_n + c0;
         const int nvalid = min(32, p.cout - cbase);
-        if (!valid || nvalid <= 0) continue;
+        if (nvalid <= 0) continue;  // warp-uniform
+        const bool full32 = (nvalid == 32);
         float f[32];
         uint32_t mbits = 0;
 #pragma unroll
@@ -284,24 +353,23 @@ conv_umma_kernel(const __grid_constant__ ConvUmmaParams p) {
           else if (p.act == DPIG_ACT_LRELU) x = x > 0.f ? x : p.alpha * x;
           f[i] = x;
         }
-        const bool full32 = (nvalid == 32);
+        // ---- residual / addend
         if (p.add_hi) {
-          const long long off = ppix * p.add_ps + cbase;
           if (full32 && (p.add_ps % 8 == 0)) {
-            const uint4* ah = reinterpret_cast<const uint4*>(p.add_hi + off);
-            const uint4* al = p.add_lo ? reinterpret_cast<const uint4*>(p.add_lo + off) : nullptr;
+            epi_gather_rows(stage, p.add_hi, p.add_lo, p.add_ps, cbase, ppix, valid, lane);
+            __syncwarp();
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-              const uint4 a = __ldg(ah + q);
+              const uint4 a = *reinterpret_cast<const uint4*>(stage + swz64(lane, q));
               const uint32_t aw[4] = {a.x, a.y, a.z, a.w};
 #pragma unroll
               for (int jj = 0; jj < 4; ++jj) {
                 f[q * 8 + 2 * jj] += bf16_bits_to_float(aw[jj] & 0xFFFF);
                 f[q * 8 + 2 * jj + 1] += bf16_bits_to_float(aw[jj] >> 16);
               }
-              if (al) {
-                const uint4 b = __ldg(al + q);
-                const uint32_t bw[4] = {b.x, b.y, b.z, b.w};
+              if (p.add_lo) {
+                const uint4 b2 = *reinterpret_cast<const uint4*>(stage + 2048 + swz64(lane, q));
+                const uint32_t bw[4] = {b2.x, b2.y, b2.z, b2.w};
 #pragma unroll
                 for (int jj = 0; jj < 4; ++jj) {
                   f[q * 8 + 2 * jj] += bf16_bits_to_float(bw[jj] & 0xFFFF);
@@ -309,7 +377,9 @@ conv_umma_kernel(const __grid_constant__ ConvUmmaParams p) {
                 }
               }
             }
-          } else {
+            __syncwarp();
+          } else if (valid) {
+            const long long off = static_cast<long long>(ppix) * p.add_ps + cbase;
 #pragma unroll
             for (int i = 0; i < 32; ++i)
               if (i < nvalid) {
@@ -319,37 +389,67 @@ conv_umma_kernel(const __grid_constant__ ConvUmmaParams p) {
               }
           }
         }
-        if (p.mask_out) p.mask_out[lpix * p.mask_out_words + (cbase >> 5)] = mbits;
+        if (p.mask_out && valid) p.mask_out[static_cast<long long>(lpix) * p.mask_out_words + (cbase >> 5)] = mbits;
+        // ---- split-bf16 output
         if (p.out_hi) {
-          const bool vec = full32 && (p.out_ps % 8 == 0);
-          for (int dy = 0; dy < p.rep; ++dy)
-            for (int dx = 0; dx < p.rep; ++dx) {
-              const long long off = (ppix + static_cast<long long>(dy) * p.out_W + dx) * p.out_ps + cbase;
-              store_split32(p.out_hi, p.out_lo, off, f, nvalid, vec);
-            }
+          if (full32 && (p.out_ps % 8 == 0)) {
+            epi_stage_split(stage, f, lane, p.out_lo != nullptr);
+            __syncwarp();
+            for (int dy = 0; dy < p.rep; ++dy)
+              for (int dx = 0; dx < p.rep; ++dx)
+                epi_scatter_rows(stage, p.out_hi, p.out_lo, p.out_ps, cbase, ppix + dy * p.out_W + dx, valid, lane);
+            __syncwarp();
+          } else if (valid) {
+            for (int dy = 0; dy < p.rep; ++dy)
+              for (int dx = 0; dx < p.rep; ++dx)
+                store_split32(p.out_hi, p.out_lo,
+                              static_cast<long long>(ppix + dy * p.out_W + dx) * p.out_ps + cbase, f, nvalid, false);
+          }
         }
+        // ---- fp32 output
         if (p.out_f32) {
-          for (int dy = 0; dy < p.rep; ++dy)
-            for (int dx = 0; dx < p.rep; ++dx) {
-              float* o = p.out_f32 + (ppix + static_cast<long long>(dy) * p.out_W + dx) * p.out_f32_ps + cbase;
-              if (full32 && (p.out_f32_ps % 4 == 0)) {
+          if (full32 && (p.out_f32_ps % 4 == 0)) {
 #pragma unroll
-                for (int q = 0; q < 8; ++q)
-                  reinterpret_cast<float4*>(o)[q] =
-                      make_float4(f[4 * q], f[4 * q + 1], f[4 * q + 2], f[4 * q + 3]);
-              } else {
+            for (int q = 0; q < 8; ++q)
+              *reinterpret_cast<float4*>(stage + swz128(lane, q)) = make_float4(f[4 * q], f[4 * q + 1], f[4 * q + 2], f[4 * q + 3]);
+            __syncwarp();
+            for (int dy = 0; dy < p.rep; ++dy)
+              for (int dx = 0; dx < p.rep; ++dx) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                  const int q = 4 * i + (lane >> 3), pc = lane & 7;
+                  const int pq = __shfl_sync(0xffffffffu, ppix, q);
+                  const int vq = __shfl_sync(0xffffffffu, static_cast<int>(valid), q);
+                  if (vq)
+                    *reinterpret_cast<float4*>(p.out_f32 + static_cast<long long>(pq + dy * p.out_W + dx) * p.out_f32_ps + cbase + pc * 4) =
+                        *reinterpret_cast<const float4*>(stage + swz128(q, pc));
+                }
+              }
+            __syncwarp();
+          } else if (valid) {
+            for (int dy = 0; dy < p.rep; ++dy)
+              for (int dx = 0; dx < p.rep; ++dx) {
+                float* o = p.out_f32 + static_cast<long long>(ppix + dy * p.out_W + dx) * p.out_f32_ps + cbase;
 #pragma unroll
                 for (int i = 0; i < 32; ++i)
                   if (i < nvalid) o[i] = f[i];
               }
-            }
+          }
         }
+        // ---- second output multiplied by the incoming sign mask (backward of ReLU / LeakyReLU)
         if (p.out2_hi) {
-          const uint32_t mi = p.mask_in ? p.mask_in[ppix * p.mask_in_words + (cbase >> 5)] : 0xFFFFFFFFu;
+          uint32_t mi = 0xFFFFFFFFu;
+          if (p.mask_in && valid) mi = p.mask_in[static_cast<long long>(ppix) * p.mask_in_words + (cbase >> 5)];
 #pragma unroll
           for (int i = 0; i < 32; ++i) f[i] *= ((mi >> i) & 1u) ? 1.f : p.mask_neg;
-          const bool vec = full32 && (p.out2_ps % 8 == 0);
-          store_split32(p.out2_hi, p.out2_lo, ppix * p.out2_ps + cbase, f, nvalid, vec);
+          if (full32 && (p.out2_ps % 8 == 0)) {
+            epi_stage_split(stage, f, lane, p.out2_lo != nullptr);
+            __syncwarp();
+            epi_scatter_rows(stage, p.out2_hi, p.out2_lo, p.out2_ps, cbase, ppix, valid, lane);
+            __syncwarp();
+          } else if (valid) {
+            store_split32(p.out2_hi, p.out2_lo, static_cast<long long>(ppix) * p.out2_ps + cbase, f, nvalid, false);
+          }
         }
       }
     }
@@ -672,11 +772,12 @@ static int fill_epilogue(dpig_ctx* ctx, ConvUmmaParams& P, const dpig_conv_epilo
 static int launch_conv(dpig_ctx* ctx, ConvUmmaParams& P, cudaStream_t stream) {
   P.planes = ctx->fast_mode ? 1 : P.planes;
   const uint32_t stage_bytes = P.planes * (kABytes + P.b_bytes);
-  int stages = (ctx->max_smem_optin - 1024 - 256) / stage_bytes;
+  const uint32_t extra = 1024 + 256 + 4 * kEpiBytesPerWarp;  // alignment slack + barriers + epilogue staging
+  int stages = (ctx->max_smem_optin - static_cast<int>(extra)) / static_cast<int>(stage_bytes);
   if (stages > 6) stages = 6;
   if (stages < 2) return set_error(ctx, DPIG_EUNSUPPORTED, "conv tile does not fit shared memory");
   P.stages = stages;
-  const size_t smem = static_cast<size_t>(stages) * stage_bytes + 1024 + 256;
+  const size_t smem = static_cast<size_t>(stages) * stage_bytes + extra;
   static bool attr_set = false;
   if (!attr_set) {
     cudaFuncSetAttribute(conv_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->max_smem_optin);
@@ -902,8 +1003,25 @@ static int wgrad_impl(dpig_ctx* ctx, const dpig_tensor* x, const dpig_tensor* dy
   P.total_tiles = P.tiles_w * P.tiles_h * tiles_n;
   const int m_tiles = (cin + 127) / 128;
   const int base = m_tiles * P.n_tiles * kh * kw;
-  int ksplit = (3 * ctx->num_sms + base - 1) / base;
-  ksplit = std::max(1, std::min(ksplit, P.total_tiles));
+  // split-K so that the grid is as close as possible to (but not above) a whole number of waves of the
+  // 148 one-CTA-per-SM slots: a grid of 450 CTAs would run 4 rounds with the last one 4 % full.
+  int ksplit = 1;
+  {
+    double best = -1.0;
+    const int max_split = std::min(P.total_tiles, std::max(1, 4 * ctx->num_sms / base));
+    for (int ks = 1; ks <= max_split; ++ks) {
+      const int tpc = (P.total_tiles + ks - 1) / ks;
+      const int eff_ks = (P.total_tiles + tpc - 1) / tpc;
+      const int ctas = base * eff_ks;
+      const int rounds = (ctas + ctx->num_sms - 1) / ctx->num_sms;
+      // time ~ rounds * tiles-per-CTA (+ a fixed per-CTA cost of ~6 k-steps for prologue / atomics epilogue)
+      const double cost = static_cast<double>(rounds) * (tpc + 6);
+      if (best < 0 || cost < best) {
+        best = cost;
+        ksplit = eff_ks;
+      }
+    }
+  }
   P.tiles_per_cta = (P.total_tiles + ksplit - 1) / ksplit;
   ksplit = (P.total_tiles + P.tiles_per_cta - 1) / P.tiles_per_cta;
   P.dw = dw;
