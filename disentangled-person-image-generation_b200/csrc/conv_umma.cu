@@ -24,6 +24,7 @@
 //   Both operands are MN-major views of the same kind of TMA boxes (rows = pixels).
 //   One filter tap per CTA (blockIdx.y), split-K over pixel tiles (blockIdx.z), fp32 atomics.
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 #include "common.cuh"
@@ -111,6 +112,8 @@ __device__ __forceinline__ void store_split32(__nv_bfloat16* hi, __nv_bfloat16* 
   }
 }
 
+constexpr int kEpiWarps = 8;          // two epilogue warps per TMEM lane group: they take alternate 32-column chunks
+constexpr int kConvThreads = 64 + 32 * kEpiWarps;
 constexpr uint32_t kEpiBytesPerWarp = 4096;  // 32 pixel rows x (64 B hi + 64 B lo)  or  32 x 128 B fp32
 
 // Byte offset of 16-byte piece `piece` of row `row` in a warp-private staging tile; XOR swizzles keep both the
@@ -175,10 +178,130 @@ __device__ __forceinline__ void epi_gather_rows(uint8_t* stage, const __nv_bfloa
   }
 }
 
+// One 32-channel chunk of one accumulator row (pixel): bias / activation / residual / sign mask / outputs.
+// v[i] = raw fp32 accumulator of channel cbase+i; all 32 lanes of the warp call this together (the global traffic
+// is staged through the warp-private tile `stage`).
+__device__ __forceinline__ void epi_chunk(const ConvUmmaParams& p, uint8_t* stage, const uint32_t (&v)[32], int cbase,
+                                          bool valid, int lpix, int ppix, const float* cbias, int lane) {
+  const int nvalid = min(32, p.cout - cbase);
+  if (nvalid <= 0) return;  // warp-uniform
+  const bool full32 = (nvalid == 32);
+  float f[32];
+  uint32_t mbits = 0;
+#pragma unroll
+  for (int i = 0; i < 32; ++i) {
+    float x = __uint_as_float(v[i]);
+    if (p.bias && i < nvalid) x += __ldg(p.bias + cbase + i);
+    if (cbias && i < nvalid) x += __ldg(cbias + cbase + i);
+    mbits |= (x > 0.f ? 1u : 0u) << i;
+    if (p.act == DPIG_ACT_RELU) x = fmaxf(x, 0.f);
+    else if (p.act == DPIG_ACT_LRELU) x = x > 0.f ? x : p.alpha * x;
+    f[i] = x;
+  }
+  // ---- residual / addend
+  if (p.add_hi) {
+    if (full32 && (p.add_ps % 8 == 0)) {
+      epi_gather_rows(stage, p.add_hi, p.add_lo, p.add_ps, cbase, ppix, valid, lane);
+      __syncwarp();
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const uint4 a = *reinterpret_cast<const uint4*>(stage + swz64(lane, q));
+        const uint32_t aw[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) {
+          f[q * 8 + 2 * jj] += bf16_bits_to_float(aw[jj] & 0xFFFF);
+          f[q * 8 + 2 * jj + 1] += bf16_bits_to_float(aw[jj] >> 16);
+        }
+        if (p.add_lo) {
+          const uint4 b2 = *reinterpret_cast<const uint4*>(stage + 2048 + swz64(lane, q));
+          const uint32_t bw[4] = {b2.x, b2.y, b2.z, b2.w};
+#pragma unroll
+          for (int jj = 0; jj < 4; ++jj) {
+            f[q * 8 + 2 * jj] += bf16_bits_to_float(bw[jj] & 0xFFFF);
+            f[q * 8 + 2 * jj + 1] += bf16_bits_to_float(bw[jj] >> 16);
+          }
+        }
+      }
+      __syncwarp();
+    } else if (valid) {
+      const long long off = static_cast<long long>(ppix) * p.add_ps + cbase;
+#pragma unroll
+      for (int i = 0; i < 32; ++i)
+        if (i < nvalid) {
+          float a = __bfloat162float(p.add_hi[off + i]);
+          if (p.add_lo) a += __bfloat162float(p.add_lo[off + i]);
+          f[i] += a;
+        }
+    }
+  }
+  if (p.mask_out && valid) p.mask_out[static_cast<long long>(lpix) * p.mask_out_words + (cbase >> 5)] = mbits;
+  // ---- split-bf16 output
+  if (p.out_hi) {
+    if (full32 && (p.out_ps % 8 == 0)) {
+      epi_stage_split(stage, f, lane, p.out_lo != nullptr);
+      __syncwarp();
+      for (int dy = 0; dy < p.rep; ++dy)
+        for (int dx = 0; dx < p.rep; ++dx)
+          epi_scatter_rows(stage, p.out_hi, p.out_lo, p.out_ps, cbase, ppix + dy * p.out_W + dx, valid, lane);
+      __syncwarp();
+    } else if (valid) {
+      for (int dy = 0; dy < p.rep; ++dy)
+        for (int dx = 0; dx < p.rep; ++dx)
+          store_split32(p.out_hi, p.out_lo,
+                        static_cast<long long>(ppix + dy * p.out_W + dx) * p.out_ps + cbase, f, nvalid, false);
+    }
+  }
+  // ---- fp32 output
+  if (p.out_f32) {
+    if (full32 && (p.out_f32_ps % 4 == 0)) {
+#pragma unroll
+      for (int q = 0; q < 8; ++q)
+        *reinterpret_cast<float4*>(stage + swz128(lane, q)) = make_float4(f[4 * q], f[4 * q + 1], f[4 * q + 2], f[4 * q + 3]);
+      __syncwarp();
+      for (int dy = 0; dy < p.rep; ++dy)
+        for (int dx = 0; dx < p.rep; ++dx) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int q = 4 * i + (lane >> 3), pc = lane & 7;
+            const int pq = __shfl_sync(0xffffffffu, ppix, q);
+            const int vq = __shfl_sync(0xffffffffu, static_cast<int>(valid), q);
+            if (vq)
+              *reinterpret_cast<float4*>(p.out_f32 + static_cast<long long>(pq + dy * p.out_W + dx) * p.out_f32_ps + cbase + pc * 4) =
+                  *reinterpret_cast<const float4*>(stage + swz128(q, pc));
+          }
+        }
+      __syncwarp();
+    } else if (valid) {
+      for (int dy = 0; dy < p.rep; ++dy)
+        for (int dx = 0; dx < p.rep; ++dx) {
+          float* o = p.out_f32 + static_cast<long long>(ppix + dy * p.out_W + dx) * p.out_f32_ps + cbase;
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (i < nvalid) o[i] = f[i];
+        }
+    }
+  }
+  // ---- second output multiplied by the incoming sign mask (backward of ReLU / LeakyReLU)
+  if (p.out2_hi) {
+    uint32_t mi = 0xFFFFFFFFu;
+    if (p.mask_in && valid) mi = p.mask_in[static_cast<long long>(ppix) * p.mask_in_words + (cbase >> 5)];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) f[i] *= ((mi >> i) & 1u) ? 1.f : p.mask_neg;
+    if (full32 && (p.out2_ps % 8 == 0)) {
+      epi_stage_split(stage, f, lane, p.out2_lo != nullptr);
+      __syncwarp();
+      epi_scatter_rows(stage, p.out2_hi, p.out2_lo, p.out2_ps, cbase, ppix, valid, lane);
+      __syncwarp();
+    } else if (valid) {
+      store_split32(p.out2_hi, p.out2_lo, static_cast<long long>(ppix) * p.out2_ps + cbase, f, nvalid, false);
+    }
+  }
+}
+
 // Persistent: grid = min(#tiles, #SMs); CTA b processes tiles b, b+grid, ...  The smem pipeline runs
 // continuously across tiles and the fp32 accumulator is double-buffered in TMEM (2 x block_n columns), so
 // the epilogue of tile j overlaps the MMAs of tile j+1.
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(kConvThreads, 1)
 conv_umma_kernel(const __grid_constant__ ConvUmmaParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = align1024(smem_raw);
@@ -189,7 +312,7 @@ conv_umma_kernel(const __grid_constant__ ConvUmmaParams p) {
   uint64_t* tmem_full = empty + p.stages;   // [2]
   uint64_t* tmem_empty = tmem_full + 2;     // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
-  uint8_t* epi_smem = smem + p.stages * stage_bytes + 256;  // 4 x kEpiBytesPerWarp, 256 B past the barriers
+  uint8_t* epi_smem = smem + p.stages * stage_bytes + 256;  // kEpiWarps x kEpiBytesPerWarp, 256 B past the barriers
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -204,7 +327,7 @@ conv_umma_kernel(const __grid_constant__ ConvUmmaParams p) {
     }
     for (int a = 0; a < 2; ++a) {
       ptx::mbar_init(&tmem_full[a], 1);
-      ptx::mbar_init(&tmem_empty[a], 4);  // one arrive per epilogue warp
+      ptx::mbar_init(&tmem_empty[a], kEpiWarps);  // one arrive per epilogue warp
     }
     ptx::fence_barrier_init();
   }
@@ -298,13 +421,15 @@ conv_umma_kernel(const __grid_constant__ ConvUmmaParams p) {
     // ---------------- epilogue: 4 warps, thread = one accumulator row (= one output pixel).
     // Global traffic goes through a warp-private 4 KB staging tile so that every warp-level load / store
     // touches whole 64 B (bf16 planes) or 128 B (fp32) pixel rows instead of 32 scattered 16 B pieces.
-    const int lg = warp & 3;
+    const int lg = warp & 3;            // TMEM lane group this warp may read (hardware: warp id % 4)
+    const int ew = warp - 2;            // epilogue warp index 0..kEpiWarps-1
+    const int cpar = ew >> 2;           // which alternate 32-column chunks this warp takes
     const int r = lg * 32 + lane;
     const int wl = r % p.BW;
     const int tq = r / p.BW;
     const int hl = tq % p.BH;
     const int nl = tq / p.BH;
-    uint8_t* stage = epi_smem + lg * kEpiBytesPerWarp;
+    uint8_t* stage = epi_smem + ew * kEpiBytesPerWarp;
     int j = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++j) {
       const int acc = j & 1;
@@ -327,130 +452,26 @@ conv_umma_kernel(const __grid_constant__ ConvUmmaParams p) {
       ptx::tc_fence_after();
       const uint32_t tmem_acc = tmem_base + acc * p.block_n + (static_cast<uint32_t>(lg * 32) << 16);
 
-      for (int c0 = 0; c0 < p.block_n; c0 += 32) {
+      const int nchunks = p.block_n >> 5;
+      bool released = false;
+      for (int ci = cpar; ci < nchunks; ci += kEpiWarps / 4) {
+        const int c0 = ci << 5;
         uint32_t v[32];
         ptx::tmem_ld32(tmem_acc + c0, v);
         ptx::tmem_ld_wait();
-        if (c0 + 32 >= p.block_n) {
-          // last TMEM read of this tile: hand the accumulator stage back to the MMA warp
+        if (ci + kEpiWarps / 4 >= nchunks) {
+          // this warp's last TMEM read of the tile: hand the accumulator stage back to the MMA warp
           ptx::tc_fence_before();
           __syncwarp();
           if (lane == 0) ptx::mbar_arrive(&tmem_empty[acc]);
+          released = true;
         }
-        const int cbase = nt * p.block_n + c0;
-        const int nvalid = min(32, p.cout - cbase);
-        if (nvalid <= 0) continue;  // warp-uniform
-        const bool full32 = (nvalid == 32);
-        float f[32];
-        uint32_t mbits = 0;
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          float x = __uint_as_float(v[i]);
-          if (p.bias && i < nvalid) x += __ldg(p.bias + cbase + i);
-          if (cbias && i < nvalid) x += __ldg(cbias + cbase + i);
-          mbits |= (x > 0.f ? 1u : 0u) << i;
-          if (p.act == DPIG_ACT_RELU) x = fmaxf(x, 0.f);
-          else if (p.act == DPIG_ACT_LRELU) x = x > 0.f ? x : p.alpha * x;
-          f[i] = x;
-        }
-        // ---- residual / addend
-        if (p.add_hi) {
-          if (full32 && (p.add_ps % 8 == 0)) {
-            epi_gather_rows(stage, p.add_hi, p.add_lo, p.add_ps, cbase, ppix, valid, lane);
-            __syncwarp();
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const uint4 a = *reinterpret_cast<const uint4*>(stage + swz64(lane, q));
-              const uint32_t aw[4] = {a.x, a.y, a.z, a.w};
-#pragma unroll
-              for (int jj = 0; jj < 4; ++jj) {
-                f[q * 8 + 2 * jj] += bf16_bits_to_float(aw[jj] & 0xFFFF);
-                f[q * 8 + 2 * jj + 1] += bf16_bits_to_float(aw[jj] >> 16);
-              }
-              if (p.add_lo) {
-                const uint4 b2 = *reinterpret_cast<const uint4*>(stage + 2048 + swz64(lane, q));
-                const uint32_t bw[4] = {b2.x, b2.y, b2.z, b2.w};
-#pragma unroll
-                for (int jj = 0; jj < 4; ++jj) {
-                  f[q * 8 + 2 * jj] += bf16_bits_to_float(bw[jj] & 0xFFFF);
-                  f[q * 8 + 2 * jj + 1] += bf16_bits_to_float(bw[jj] >> 16);
-                }
-              }
-            }
-            __syncwarp();
-          } else if (valid) {
-            const long long off = static_cast<long long>(ppix) * p.add_ps + cbase;
-#pragma unroll
-            for (int i = 0; i < 32; ++i)
-              if (i < nvalid) {
-                float a = __bfloat162float(p.add_hi[off + i]);
-                if (p.add_lo) a += __bfloat162float(p.add_lo[off + i]);
-                f[i] += a;
-              }
-          }
-        }
-        if (p.mask_out && valid) p.mask_out[static_cast<long long>(lpix) * p.mask_out_words + (cbase >> 5)] = mbits;
-        // ---- split-bf16 output
-        if (p.out_hi) {
-          if (full32 && (p.out_ps % 8 == 0)) {
-            epi_stage_split(stage, f, lane, p.out_lo != nullptr);
-            __syncwarp();
-            for (int dy = 0; dy < p.rep; ++dy)
-              for (int dx = 0; dx < p.rep; ++dx)
-                epi_scatter_rows(stage, p.out_hi, p.out_lo, p.out_ps, cbase, ppix + dy * p.out_W + dx, valid, lane);
-            __syncwarp();
-          } else if (valid) {
-            for (int dy = 0; dy < p.rep; ++dy)
-              for (int dx = 0; dx < p.rep; ++dx)
-                store_split32(p.out_hi, p.out_lo,
-                              static_cast<long long>(ppix + dy * p.out_W + dx) * p.out_ps + cbase, f, nvalid, false);
-          }
-        }
-        // ---- fp32 output
-        if (p.out_f32) {
-          if (full32 && (p.out_f32_ps % 4 == 0)) {
-#pragma unroll
-            for (int q = 0; q < 8; ++q)
-              *reinterpret_cast<float4*>(stage + swz128(lane, q)) = make_float4(f[4 * q], f[4 * q + 1], f[4 * q + 2], f[4 * q + 3]);
-            __syncwarp();
-            for (int dy = 0; dy < p.rep; ++dy)
-              for (int dx = 0; dx < p.rep; ++dx) {
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                  const int q = 4 * i + (lane >> 3), pc = lane & 7;
-                  const int pq = __shfl_sync(0xffffffffu, ppix, q);
-                  const int vq = __shfl_sync(0xffffffffu, static_cast<int>(valid), q);
-                  if (vq)
-                    *reinterpret_cast<float4*>(p.out_f32 + static_cast<long long>(pq + dy * p.out_W + dx) * p.out_f32_ps + cbase + pc * 4) =
-                        *reinterpret_cast<const float4*>(stage + swz128(q, pc));
-                }
-              }
-            __syncwarp();
-          } else if (valid) {
-            for (int dy = 0; dy < p.rep; ++dy)
-              for (int dx = 0; dx < p.rep; ++dx) {
-                float* o = p.out_f32 + static_cast<long long>(ppix + dy * p.out_W + dx) * p.out_f32_ps + cbase;
-#pragma unroll
-                for (int i = 0; i < 32; ++i)
-                  if (i < nvalid) o[i] = f[i];
-              }
-          }
-        }
-        // ---- second output multiplied by the incoming sign mask (backward of ReLU / LeakyReLU)
-        if (p.out2_hi) {
-          uint32_t mi = 0xFFFFFFFFu;
-          if (p.mask_in && valid) mi = p.mask_in[static_cast<long long>(ppix) * p.mask_in_words + (cbase >> 5)];
-#pragma unroll
-          for (int i = 0; i < 32; ++i) f[i] *= ((mi >> i) & 1u) ? 1.f : p.mask_neg;
-          if (full32 && (p.out2_ps % 8 == 0)) {
-            epi_stage_split(stage, f, lane, p.out2_lo != nullptr);
-            __syncwarp();
-            epi_scatter_rows(stage, p.out2_hi, p.out2_lo, p.out2_ps, cbase, ppix, valid, lane);
-            __syncwarp();
-          } else if (valid) {
-            store_split32(p.out2_hi, p.out2_lo, static_cast<long long>(ppix) * p.out2_ps + cbase, f, nvalid, false);
-          }
-        }
+        epi_chunk(p, stage, v, nt * p.block_n + c0, valid, lpix, ppix, cbias, lane);
+      }
+      if (!released) {  // fewer chunks than epilogue warps per lane group (block_n == 32)
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&tmem_empty[acc]);
       }
     }
   }
@@ -772,7 +793,7 @@ static int fill_epilogue(dpig_ctx* ctx, ConvUmmaParams& P, const dpig_conv_epilo
 static int launch_conv(dpig_ctx* ctx, ConvUmmaParams& P, cudaStream_t stream) {
   P.planes = ctx->fast_mode ? 1 : P.planes;
   const uint32_t stage_bytes = P.planes * (kABytes + P.b_bytes);
-  const uint32_t extra = 1024 + 256 + 4 * kEpiBytesPerWarp;  // alignment slack + barriers + epilogue staging
+  const uint32_t extra = 1024 + 256 + kEpiWarps * kEpiBytesPerWarp;  // alignment slack + barriers + epilogue staging
   int stages = (ctx->max_smem_optin - static_cast<int>(extra)) / static_cast<int>(stage_bytes);
   if (stages > 6) stages = 6;
   if (stages < 2) return set_error(ctx, DPIG_EUNSUPPORTED, "conv tile does not fit shared memory");
@@ -787,7 +808,7 @@ static int launch_conv(dpig_ctx* ctx, ConvUmmaParams& P, cudaStream_t stream) {
   P.tmem_cols = 64;
   while (static_cast<int>(P.tmem_cols) < 2 * P.block_n) P.tmem_cols <<= 1;
   dim3 grid(std::min(total_tiles, ctx->num_sms));
-  conv_umma_kernel<<<grid, 192, smem, stream>>>(P);
+  conv_umma_kernel<<<grid, kConvThreads, smem, stream>>>(P);
   ctx->launches++;
   return check_launch(ctx, "conv_umma_kernel");
 }
