@@ -147,6 +147,10 @@ class Context:
     def last_error(self):
         return self.lib.dpig_last_error(self.handle).decode()
 
+    def set_fast_mode(self, fast):
+        """fast=True: single bf16 pass on the hi planes (NOT the parity mode)."""
+        self.call("ctx_set_fast_mode", int(bool(fast)))
+
     def launch_count(self):
         return int(self.lib.dpig_launch_count(self.handle))
 

@@ -1,0 +1,55 @@
+"""Dev tool (not a test): times single conv launches to separate mainloop from epilogue cost.
+   python tests/bench_conv_micro.py"""
+import ctypes as C
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import dpig_b200  # noqa: E402
+from dpig_b200 import _lib  # noqa: E402
+from dpig_b200.tensor import SplitTensor, ptr  # noqa: E402
+
+
+def run(ctx, n, h, w, cin, cout, k=3, mode="full", fast=False, iters=20):
+    s = torch.cuda.current_stream().cuda_stream
+    x = SplitTensor(n, h, w, cin, zero=True)
+    x.buf.normal_(0, 1)
+    wf = torch.randn((2, k * k, cout, cin), device="cuda").to(torch.bfloat16)
+    bias = torch.zeros(cout, device="cuda")
+    out = SplitTensor(n, h, w, cout)
+    res = SplitTensor(n, h, w, cout, zero=True)
+    mask = torch.zeros((n * h * w, cout // 32), dtype=torch.int32, device="cuda")
+    ep = _lib.ConvEpilogue()
+    ep.bias = bias.data_ptr()
+    ep.act = 1
+    ep.upsample = 1
+    if mode in ("full", "nores"):
+        ep.out = C.pointer(out.struct())
+        ep.mask_out = mask.data_ptr()
+    if mode == "full":
+        ep.addend = C.pointer(res.struct())
+    ctx.set_fast_mode(1 if fast else 0)
+    for _ in range(3):
+        ctx.conv2d_fwd(x.ref(), ptr(wf[0]), ptr(wf[1]), k, k, 1, cout, C.byref(ep), s)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        ctx.conv2d_fwd(x.ref(), ptr(wf[0]), ptr(wf[1]), k, k, 1, cout, C.byref(ep), s)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / iters
+    fl = 2.0 * n * h * w * cout * k * k * cin
+    ctx.set_fast_mode(0)
+    return ms, fl / ms / 1e9
+
+
+if __name__ == "__main__":
+    ctx = dpig_b200.Context(0)
+    for (n, h, w, cin, cout) in [(64, 128, 64, 128, 128), (64, 128, 64, 256, 256), (64, 64, 32, 512, 512), (448, 48, 48, 128, 128)]:
+        for mode in ("full", "nores", "none"):
+            for fast in (False, True):
+                ms, tf = run(ctx, n, h, w, cin, cout, mode=mode, fast=fast)
+                print("%4dx%3dx%3d %4d->%4d  epilogue=%-5s %-5s  %7.3f ms  %7.1f TFLOP/s (algorithmic)" % (
+                    n, h, w, cin, cout, mode, "1pass" if fast else "3pass", ms, tf), flush=True)
