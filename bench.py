@@ -37,6 +37,21 @@ def _peaks():
     return dict(hbm_gbs=6650.0, bf16_tflops=1400.0, source="fallback of B200_PROFILING.md (sustained)")
 
 
+def _ncu_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum of a representative conv_umma_kernel launch from the committed
+    `ncu --set full` capture (profiles/r01_ncu_full_summary.json); the live bench cannot run under ncu."""
+    path = os.path.join(ROOT, "profiles", "r01_ncu_full_summary.json")
+    try:
+        with open(path) as fh:
+            rows = json.load(fh)["conv_big_r01"]
+        r = max(rows, key=lambda x: x["time_us"])
+        return {"launch": "256->256 3x3 conv on 64x128x64 (ID_AE/G/Conv_27), grid %s" % r["grid"],
+                "dram_bytes": r["dram_read_bytes"] + r["dram_write_bytes"],
+                "algorithmic_bytes": 2 * 64 * 128 * 64 * 256 * 4, "source": "profiles/r01_ncu_full_summary.json"}
+    except Exception:
+        return None
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled every 200 ms DURING the timed region."""
 
@@ -246,7 +261,7 @@ def main():
         "kernel": "conv_umma_kernel (tcgen05 implicit-GEMM conv: forward + data-gradient launches)",
         "bound": "tensor", "achieved": ach, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
         "frac": ach / peaks["bf16_tflops"], "peak_source": peaks["source"] + " -- of measured",
-        "traffic": None,
+        "traffic": _ncu_traffic(),
         "note": "achieved = algorithmic conv FLOPs (2*pixels*Cout*k*k*Cin) / CUDA-event time of the launches; the "
                 "parity mode issues %d bf16 MMA passes per product, so executed tensor FLOPs = %dx algorithmic "
                 "(attainable frac <= 1/%d)" % (passes, passes, passes),

@@ -617,6 +617,8 @@ class Stage1Engine:
         self._prog_forward_generator(self.p_fwd_gen)
         self.p_fwd_enc = Program(self.ctx)     # appearance encoder only (Stage-II real embeddings)
         self._prog_forward_encoder(self.p_fwd_enc)
+        self.p_fwd_unet = Program(self.ctx)    # U-Net only, from self.emb / self.pose_rcv (sampling path, tester.py)
+        self._prog_unet_forward(self.p_fwd_unet)
         self.p_bwd_gen = Program(self.ctx)     # g_G -> all Encoder+G parameter gradients
         self._prog_backward_generator(self.p_bwd_gen)
         self.p_d_fake_fwd = Program(self.ctx)
@@ -703,6 +705,15 @@ class Stage1Engine:
     def run_encoder(self, stream=None):
         """Appearance-encoder forward only: fills self.emb [B, 352] for the current batch."""
         self.p_fwd_enc.run(stream if stream is not None else torch.cuda.current_stream().cuda_stream)
+
+    def run_unet(self, stream=None):
+        """U-Net forward from the embedding in self.emb and the keypoints in self.pose_rcv; fills self.G / self.G8."""
+        self.p_fwd_unet.run(stream if stream is not None else torch.cuda.current_stream().cuda_stream)
+
+    def score_generated(self, stream=None):
+        """DCGANDiscriminator logits of the current self.G (tester.py:568-571)."""
+        self.p_d_fake_fwd.run(stream if stream is not None else torch.cuda.current_stream().cuda_stream)
+        return self.d_fake.logits
 
     def _prog_forward_encoder(self, p):
         cfg, B = self.cfg, self.B

@@ -15,6 +15,7 @@ _MODEL_CLASSES = {
 
 
 def main(config):
+    from . import tester as TE
     from . import trainer as T
     if config.gpu > -1:
         os.environ["CUDA_DEVICE_ORDER"] = "PCI_BUS_ID"
@@ -23,7 +24,7 @@ def main(config):
     name = _MODEL_CLASSES.get(config.model)
     if name is None:
         raise Exception("unknown --model=%r" % config.model)
-    cls = getattr(T, name, None)
+    cls = getattr(T, name, None) or getattr(TE, name, None)
     if cls is None:
         raise NotImplementedError("--model=%d (%s) is outside this round's hot path (SURVEY.md §8f)" % (config.model, name))
     trainer = cls(config)

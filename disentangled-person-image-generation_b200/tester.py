@@ -1,0 +1,139 @@
+"""Sampling / inference call surface of the reference (--model=13):
+
+    class DPIG_FourNetsFgBg_testOnlySampleFactor      reference tester.py:419-613
+
+Forward only: appearance encoder -> sample-or-hold the Fg / Bg embeddings (GaussianFCRes nets) -> pose branch
+(PoseEncoderFCRes -> PoseDecoderFCRes; the decoder is fed the ENCODED REAL pose, quirk q7) -> keypoints to maps +
+radius-4 inflation -> U-Net -> denorm -> DCGANDiscriminator score.  Everything runs through the C ABI; PNG dumps and
+SSIM of the reference's generate()/test() are host-side I/O outside the hot path (results are returned as arrays and
+written as .npy)."""
+import os
+
+import numpy as np
+import torch
+
+from . import _lib, engine, stage2, synth
+from ._lib import ACT_LRELU, ACT_NONE
+from .tensor import ptr
+from .trainer import SyntheticLoader
+
+
+def pose_specs(keypoints=18):
+    specs = stage2.fc_res_specs("PoseAE/G_Pose_Encoder", keypoints * 3, 512, 32)
+    dec = [("PoseAE/G_Pose_Decoder", 32, 512)] + [("PoseAE/G_Pose_Decoder", 512, 512)] * 8 + \
+          [("PoseAE/G_Pose_Decoder", 512, keypoints * 2), ("PoseAE/G_Pose_Decoder", 512, keypoints)]
+    for i, (pre, a, b) in enumerate(dec):
+        name = "%s/fully_connected%s" % (pre, "" if i == 0 else "_%d" % i)
+        specs += [(name + "/weights", (a, b)), (name + "/biases", (b,))]
+    return specs
+
+
+class DPIG_FourNetsFgBg_testOnlySampleFactor(object):
+    def __init__(self, config, loader=None):
+        self.config = config
+        self.batch_size = config.batch_size
+        self.img_H, self.img_W = config.img_H, config.img_W
+        self.conv_hidden_num, self.z_num = config.conv_hidden_num, config.z_num
+        self.sample_fg, self.sample_bg, self.sample_pose = config.sample_fg, config.sample_bg, config.sample_pose
+        self.keypoint_num = 18
+        self.model_dir = config.model_dir or os.path.join(config.log_dir, "dpig_model%d" % config.model)
+        self.pretrained_path = config.pretrained_path
+        self.test_batch_num = 400        # tester.py:475
+        self.loader = loader or SyntheticLoader(self.batch_size, self.img_H, self.img_W, config.random_seed)
+        self.net_cfg = None
+
+    def init_net(self, net_cfg=None):
+        self.ctx = _lib.Context(0)
+        cfg = net_cfg or engine.NetConfig(img_h=self.img_H, img_w=self.img_W, hidden=self.conv_hidden_num, z_num=self.z_num)
+        self.cfg = cfg
+        dev = torch.device("cuda", 0)
+        B = self.batch_size
+        self.s1 = engine.Stage1Engine(self.ctx, cfg, B, mode="dcgan")
+        self.s1.load_params(engine.init_params(cfg, seed=self.config.random_seed))
+        self.s2 = stage2.Stage2Engine(self.s1, mode="wgan")
+        self.s2.load_params(stage2.init_stage2_params())
+        # pose auto-encoder tapes (models.py:488-515), activation_fn=LeakyReLU (tester.py:487, 495)
+        self.pp = engine.ParamGroup(pose_specs(self.keypoint_num), dev)
+        names = list(self.pp.specs)
+        lay = [(names[2 * i], names[2 * i + 1]) for i in range(len(names) // 2)]
+        enc, dec = lay[:10], lay[10:]
+        t = stage2.FCTape(self.ctx, self.pp, B, dev)
+        self.pose_in = stage2._Node(B, self.keypoint_num * 3, dev)
+        h = t.linear(self.pose_in, *enc[0], act=ACT_LRELU)
+        for r in range(4):
+            a = t.linear(h, *enc[1 + 2 * r], act=ACT_LRELU)
+            b = t.linear(a, *enc[2 + 2 * r], act=ACT_LRELU)
+            h = t.add(h, b)
+        self.pose_emb = t.linear(h, *enc[9])
+        h = t.linear(self.pose_emb, *dec[0])
+        for r in range(4):
+            a = t.linear(h, *dec[1 + 2 * r], act=ACT_LRELU)
+            b = t.linear(a, *dec[2 + 2 * r], act=ACT_LRELU)
+            h = t.add(h, b)
+        self.pose_coord = t.linear(h, *dec[9])
+        self.pose_vis_logit = t.linear(h, *dec[10])
+        self.p_pose = t.forward_program()
+        if self.pretrained_path:
+            with np.load(self.pretrained_path) as z:
+                self.load_params({k: z[k] for k in z.files})
+
+    def load_params(self, params):
+        """Parameters by TF variable name: Encoder/..., ID_AE/..., Discriminator.*, Gaussian_FC_Fg/..., Gaussian_FC_Bg/...,
+        PoseAE/... (the four partial checkpoints of tester.py:423-472 merged into one dict)."""
+        self.s1.load_params(params)
+        self.s2.load_params(params)
+        for name in self.pp.specs:
+            if name in params:
+                self.pp.view(name).copy_(torch.as_tensor(np.asarray(params[name]), dtype=torch.float32).cuda())
+
+    def generate(self, x_fixed, pose_fixed, pose_rcv_fixed, part_bbox_fixed, part_vis_fixed, root_path=None, path=None,
+                 idx=None, save=False, mask=None, z_fg=None, z_bg=None):
+        """Returns (G in [0,255] NHWC float32, G_pose_inflated_img, G_dis_score) like tester.py:573-613."""
+        s1, s2, cfg, B = self.s1, self.s2, self.cfg, self.batch_size
+        H, W = cfg.img_h, cfg.img_w
+        st = torch.cuda.current_stream().cuda_stream
+        if mask is None:
+            mask = np.ones((B, H, W, 1), np.float32)
+        s1.set_batch(dict(x=x_fixed, pose_rcv=pose_rcv_fixed, mask=mask, part_bbox=part_bbox_fixed, part_vis=part_vis_fixed))
+        # ---- pose branch (tester.py:477-505)
+        rcv = s1.pose_rcv
+        norm = torch.stack([rcv[:, :, 0] / float(H) * 2.0 - 1, rcv[:, :, 1] / float(W) * 2.0 - 1, rcv[:, :, 2]], dim=-1)
+        self.pose_in.data.copy_(norm.reshape(B, -1))
+        self.p_pose.run(st)
+        if self.sample_pose:
+            vis = torch.round(torch.sigmoid(self.pose_vis_logit.data))            # binaryRound (models.py:97-108)
+            g = torch.cat([self.pose_coord.data.reshape(B, self.keypoint_num, 2), vis[:, :, None]], dim=-1)
+        else:
+            g = norm[:1].expand(B, -1, -1)
+        R = torch.clamp((g[:, :, 0] + 1) / 2.0 * H, 0, H - 1)                      # utils.py:266-271
+        Cc = torch.clamp((g[:, :, 1] + 1) / 2.0 * W, 0, W - 1)
+        s1.pose_rcv.copy_(torch.stack([R, Cc, g[:, :, 2]], dim=-1))
+        # ---- appearance branch (tester.py:509-554)
+        s2.encode_real()
+        nfg = s2.fg_dim
+        for factor, z, sample in (("fg", z_fg, self.sample_fg), ("bg", z_bg, self.sample_bg)):
+            f = s2.f[factor]
+            s2.sample_noise(factor, z)
+            f.p_g_fwd.run(st)
+            sl = slice(0, nfg) if factor == "fg" else slice(nfg, None)
+            if sample:
+                s1.emb[:, sl].copy_(f.fake.data)
+            else:
+                s1.emb[:, sl].copy_(f.real.data[:1].expand(B, -1))
+        # ---- U-Net, denorm, critic score (tester.py:561-571)
+        s1.run_unet(st)
+        score = s1.score_generated(st)
+        G = torch.clamp((s1.G + 1.0) * 127.5, 0, 255)
+        pose_maps = s1.gin.slice(0, cfg.keypoints).hi.float()
+        pose_img = (pose_maps.amax(dim=-1, keepdim=True).expand(-1, -1, -1, 3) + 1) * 127.5
+        return G.cpu().numpy(), pose_img.cpu().numpy(), score.cpu().numpy()
+
+    def test(self, num_batches=None):
+        out_dir = os.path.join(self.model_dir, "test_result_SampleFg%rSampleBg%rSamplePose%r" % (
+            self.sample_fg, self.sample_bg, self.sample_pose))
+        os.makedirs(out_dir, exist_ok=True)
+        for i in range(num_batches or self.test_batch_num):
+            b = self.loader.next_batch()
+            G, pose_img, score = self.generate(b["x"], None, b["pose_rcv"], b["part_bbox"], b["part_vis"], mask=b["mask"])
+            np.save(os.path.join(out_dir, "G_%05d.npy" % i), G.astype(np.uint8))
+        return out_dir

@@ -396,3 +396,83 @@ def stage2_losses(p, factor, real, z, mode="wgan"):
     d_fake = fc_discriminator(p, fake, name=name)
     g_loss, d_loss = T.gan_loss(mode, d_real, d_fake)
     return dict(fake=fake, d_real=d_real, d_fake=d_fake, g_loss=g_loss, d_loss=d_loss)
+
+
+# --------------------------------------------------------------------------------- sampling (--model=13)
+def pose_encoder_fc_res(p, pose_rcv_norm, prefix="PoseAE/G_Pose_Encoder", repeat_num=4, act=None):
+    """models.PoseEncoderFCRes (models.py:488-499): residual MLP 54 -> 512 -> ... -> 32."""
+    act = act or (lambda t: T.leaky_relu(t, 0.2))
+    w = _Walker(prefix, p)
+    x = act(w.fc(pose_rcv_norm))
+    for _ in range(repeat_num):
+        res = x
+        x = act(w.fc(x))
+        x = act(w.fc(x))
+        x = res + x
+    return w.fc(x)
+
+
+def pose_decoder_fc_res(p, z, prefix="PoseAE/G_Pose_Decoder", repeat_num=4, act=None):
+    """models.PoseDecoderFCRes (models.py:501-515): first FC without activation, residual blocks, then the
+    coordinate head (no activation) and the visibility head sigmoid + binaryRound (models.py:97-108)."""
+    act = act or (lambda t: T.leaky_relu(t, 0.2))
+    w = _Walker(prefix, p)
+    x = w.fc(z)
+    for _ in range(repeat_num):
+        res = x
+        x = act(w.fc(x))
+        x = act(w.fc(x))
+        x = res + x
+    coord = w.fc(x)
+    vis = torch.round(torch.sigmoid(w.fc(x)))
+    return coord, vis
+
+
+def init_pose_params(keypoints=18, seed=777, bias_noise=0.0):
+    rng = np.random.default_rng(seed)
+    p = OrderedDict()
+    s = _Scope("PoseAE/G_Pose_Encoder", p, rng)
+    s.fc(keypoints * 3, 512)
+    for _ in range(8):
+        s.fc(512, 512)
+    s.fc(512, 32)
+    s = _Scope("PoseAE/G_Pose_Decoder", p, rng)
+    s.fc(32, 512)
+    for _ in range(8):
+        s.fc(512, 512)
+    s.fc(512, keypoints * 2)
+    s.fc(512, keypoints)
+    if bias_noise > 0:
+        for k in p:
+            if k.endswith("biases"):
+                p[k] = (p[k] + rng.normal(0, bias_noise, size=p[k].shape)).astype(np.float32)
+    return p
+
+
+def sample_factor_forward(p, cfg, batch, z_fg, z_bg, sample_fg, sample_bg, sample_pose, mode="dcgan"):
+    """DPIG_FourNetsFgBg_testOnlySampleFactor.build_model (tester.py:473-571): sample-or-hold each factor, decode the
+    (encoded real) pose when sample_pose (quirk q7), inflate, generate, denorm, score with D."""
+    x = batch["x"]
+    B, H, W = x.shape[0], cfg.img_h, cfg.img_w
+    rcv = batch["pose_rcv"]
+    norm = torch.stack([rcv[:, :, 0] / float(H) * 2.0 - 1, rcv[:, :, 1] / float(W) * 2.0 - 1, rcv[:, :, 2]], dim=-1)
+    pose_embs = pose_encoder_fc_res(p, norm.reshape(B, -1))
+    coord, vis = pose_decoder_fc_res(p, pose_embs)
+    if sample_pose:
+        g_rcv = torch.cat([coord.reshape(B, cfg.keypoints, 2), vis[:, :, None]], dim=-1)
+    else:
+        g_rcv = norm[:1].expand(B, -1, -1)
+    # coord2channel_simple_rcv(is_normalized=True) (utils.py:259-273): back to pixels, clamped into the image
+    R = torch.clamp((g_rcv[:, :, 0] + 1) / 2.0 * H, 0, H - 1)
+    C = torch.clamp((g_rcv[:, :, 1] + 1) / 2.0 * W, 0, W - 1)
+    pix = torch.stack([R, C, g_rcv[:, :, 2]], dim=-1)
+    pose_maps = T.pose_rasterize(pix, H, W, 4)
+    emb = encoder_fgbg(p, cfg, x, batch["mask"], batch["part_bbox"], batch["part_vis"])
+    nfg = cfg.n_parts * cfg.part_z
+    app_fg = gaussian_fc_res(p, z_fg, 4, "Gaussian_FC_Fg/G_FC", lambda t: T.leaky_relu(t, 0.2))
+    app_bg = gaussian_fc_res(p, z_bg, 4, "Gaussian_FC_Bg/G_FC", lambda t: T.leaky_relu(t, 0.2))
+    e_fg = app_fg if sample_fg else emb[:1, :nfg].expand(B, -1)
+    e_bg = app_bg if sample_bg else emb[:1, nfg:].expand(B, -1)
+    G, _ = unet_generator(p, cfg, torch.cat([e_fg, e_bg], dim=-1), pose_maps)
+    score = dcgan_discriminator(p, cfg, G, mode)
+    return dict(G=T.denorm_img(G), G_raw=G, score=score, pose_pix=pix, pose_maps=pose_maps)

@@ -1,0 +1,53 @@
+"""GPU parity of the sampling path (reference tester.py:419-613, --model=13) against the float64 oracle:
+sample-or-hold Fg / Bg / pose, pose auto-encoder, inflation, U-Net, denorm, critic score."""
+import argparse
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from oracle import nets  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("sample", [True, False])
+def test_sample_factor_forward(sample):
+    from dpig_b200 import config as cfgmod
+    from dpig_b200 import engine, synth, tester
+    B = 4
+    kw = dict(img_h=32, img_w=16, hidden=64, roi_size=12, d_dim=64)
+    conf, _ = cfgmod.get_config(["--model=13", "--is_train=False", "--batch_size=%d" % B, "--img_H=32", "--img_W=16",
+                                 "--conv_hidden_num=64", "--sample_fg=%s" % sample, "--sample_bg=%s" % sample,
+                                 "--sample_pose=%s" % sample])
+    t = tester.DPIG_FourNetsFgBg_testOnlySampleFactor(conf)
+    t.init_net(engine.NetConfig(**kw))
+    ocfg = nets.NetConfig(**kw)
+    params = dict(nets.init_params(ocfg, seed=11, bias_noise=0.05))
+    params.update(nets.init_stage2_params(seed=12, bias_noise=0.05))
+    params.update(nets.init_pose_params(seed=13, bias_noise=0.05))
+    t.load_params(params)
+    b = synth.make_batch(B, 32, 16, seed=21)
+    rng = np.random.default_rng(5)
+    z_fg = rng.normal(0, 0.2, size=(B, 224)).astype(np.float32)
+    z_bg = rng.normal(0, 0.2, size=(B, 128)).astype(np.float32)
+    G, pose_img, score = t.generate(b["x"], None, b["pose_rcv"], b["part_bbox"], b["part_vis"], mask=b["mask"],
+                                    z_fg=z_fg, z_bg=z_bg)
+    p = nets.to_torch(params, torch.float64)
+    ob = dict(x=torch.tensor(b["x"], dtype=torch.float64), mask=torch.tensor(b["mask"], dtype=torch.float64),
+              pose_rcv=torch.tensor(b["pose_rcv"], dtype=torch.float64),
+              part_bbox=torch.tensor(b["part_bbox"][:, :7]), part_vis=torch.tensor(b["part_vis"][:, :7]))
+    ref = nets.sample_factor_forward(p, ocfg, ob, torch.tensor(z_fg, dtype=torch.float64),
+                                     torch.tensor(z_bg, dtype=torch.float64), sample, sample, sample)
+    # keypoint pixels are truncated to ints by the rasteriser: compare the maps, then the image
+    maps = t.s1.gin.slice(0, 18).hi.float().cpu().double()
+    mism = float((maps != ref["pose_maps"]).double().mean())
+    assert mism < 2e-3, mism     # a decoded coordinate within 1e-5 of an integer may truncate differently
+    if mism == 0:
+        assert float(np.abs(G - ref["G"].numpy()).max()) < 0.2            # 1e-3 on [-1,1] == 0.13 on [0,255]
+        assert float(np.abs(score - ref["score"].numpy()).max()) < 1e-3
+    assert G.shape == (B, 32, 16, 3) and pose_img.shape == (B, 32, 16, 3) and score.shape == (B,)
+    assert G.min() >= 0 and G.max() <= 255
