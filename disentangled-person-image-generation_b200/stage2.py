@@ -55,6 +55,7 @@ class FCTape:
 
     def forward_program(self):
         p = Program(self.ctx)
+        p.keep.append((self.nodes, self.ops, self.group))   # programs hold raw pointers: pin the buffers' lifetime
         for op in self.ops:
             if op[0] == "linear":
                 _, x, y, nw, nb, act, alpha = op
@@ -69,6 +70,7 @@ class FCTape:
         """Expects out.grad filled by the caller; all other node grads are zeroed first.  Accumulates parameter
         gradients when params=True; leaves d(loss)/d(node) in every node's .grad."""
         p = Program(self.ctx)
+        p.keep.append((self.nodes, self.ops, self.group, self.scratch))
         out = self.ops[-1][2] if self.ops[-1][0] == "linear" else self.ops[-1][3]
         zero = [nd for nd in self.nodes if nd is not out]
         p.add_py(lambda s: [nd.grad.zero_() for nd in zero])

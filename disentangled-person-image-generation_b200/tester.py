@@ -57,7 +57,7 @@ class DPIG_FourNetsFgBg_testOnlySampleFactor(object):
         names = list(self.pp.specs)
         lay = [(names[2 * i], names[2 * i + 1]) for i in range(len(names) // 2)]
         enc, dec = lay[:10], lay[10:]
-        t = stage2.FCTape(self.ctx, self.pp, B, dev)
+        t = self.pose_tape = stage2.FCTape(self.ctx, self.pp, B, dev)
         self.pose_in = stage2._Node(B, self.keypoint_num * 3, dev)
         h = t.linear(self.pose_in, *enc[0], act=ACT_LRELU)
         for r in range(4):

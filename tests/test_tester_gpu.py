@@ -45,6 +45,10 @@ def test_sample_factor_forward(sample):
     # keypoint pixels are truncated to ints by the rasteriser: compare the maps, then the image
     maps = t.s1.gin.slice(0, 18).hi.float().cpu().double()
     mism = float((maps != ref["pose_maps"]).double().mean())
+    if mism >= 2e-3:
+        print("engine pose_rcv[0:2]:", t.s1.pose_rcv[0:2, :4].cpu().tolist())
+        print("oracle pose_pix[0:2]:", ref["pose_pix"][0:2, :4].tolist())
+        print("per-sample mismatch:", (maps != ref["pose_maps"]).double().mean(dim=(1, 2, 3)).tolist())
     assert mism < 2e-3, mism     # a decoded coordinate within 1e-5 of an integer may truncate differently
     if mism == 0:
         assert float(np.abs(G - ref["G"].numpy()).max()) < 0.2            # 1e-3 on [-1,1] == 0.13 on [0,255]
