@@ -53,12 +53,13 @@ def _ncu_traffic():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms DURING the timed region."""
+    """nvidia-smi clocks / throttle reasons sampled every 100 ms by one background process that runs for the whole
+    benchmark; window(t0, t1) summarises the samples that fall DURING a timed region (host timestamps)."""
 
     def __init__(self, index):
         self.index = index
         self.proc = None
-        self.lines = []
+        self.samples = []   # (host time, fields)
 
     def start(self):
         q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
@@ -66,23 +67,32 @@ class ClockSampler:
              "clocks_event_reasons.sw_power_cap")
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
-                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
+            t_end = time.time() + 5.0
+            while not self.samples and time.time() < t_end:   # first sample before anything is timed
+                time.sleep(0.05)
         except Exception:
             self.proc = None
 
     def _read(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.samples.append((time.time(), line.strip()))
 
     def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+
+    def window(self, t0, t1):
         if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
+            return {"sm_mhz": None, "sm_max_mhz": None, "samples": 0, "reasons": ["nvidia-smi unavailable"]}
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        rows = [ln for (t, ln) in self.samples if t0 <= t <= t1 + 0.15]
+        if not rows:   # region shorter than the sampling period: take the closest sample
+            rows = [min(self.samples, key=lambda s: abs(s[0] - 0.5 * (t0 + t1)))[1]] if self.samples else []
+        for ln in rows:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 7:
                 continue
@@ -151,7 +161,7 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=8)
+    ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--batch", type=int, default=64, help="images per GPU")
     ap.add_argument("--impl", default="dpig", choices=["dpig", "reference"])
@@ -212,10 +222,12 @@ def main():
         iteration(i, True)
     barrier()
 
+    sampler = ClockSampler(local)
+    sampler.start()
+
     def timed(host_io, timings_last=False):
-        sampler = ClockSampler(local)
-        sampler.start()
         barrier()
+        t_host0 = time.time()
         launches0 = ctx.launch_count()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         tl = []
@@ -224,7 +236,7 @@ def main():
             iteration(i, host_io, tl if (timings_last and i == K - 1) else None)
         e1.record()
         barrier()
-        clocks = sampler.stop()
+        clocks = sampler.window(t_host0, time.time())
         ms = torch.tensor([e0.elapsed_time(e1)], device="cuda", dtype=torch.float64)
         if dist:
             dist.all_reduce_max(ms)
@@ -232,6 +244,7 @@ def main():
 
     ms_dev, launches, clocks, tl = timed(False, timings_last=True)
     ms_e2e, _, clocks_e2e, _ = timed(True)
+    sampler.stop()
 
     # ---- roofline of the dominant kernel from the per-call events of the last timed iteration
     per = {}
