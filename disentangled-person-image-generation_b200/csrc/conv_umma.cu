@@ -66,6 +66,7 @@ struct ConvUmmaParams {
   const uint32_t* mask_in;
   int mask_in_words;
   float mask_neg;
+  float* colsum;  // [cout] += column sums (over pixels) of the masked output: the bias gradient of the layer below
 };
 
 __device__ __forceinline__ uint8_t* align1024(uint8_t* p) {
@@ -294,6 +295,26 @@ __device__ __forceinline__ void epi_chunk(const ConvUmmaParams& p, uint8_t* stag
       __syncwarp();
     } else if (valid) {
       store_split32(p.out2_hi, p.out2_lo, static_cast<long long>(ppix) * p.out2_ps + cbase, f, nvalid, false);
+    }
+    if (p.colsum) {
+      // bias gradient of the consuming layer = column sums of this masked gradient.  Transpose-reduce over the
+      // warp's 32 pixel rows in 31 shuffles: after step `off` every lane keeps the half of its values whose channel
+      // index has bit `off` equal to its lane-id bit, so lane l ends with the total of channel cbase + l.
+      if (!valid) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) f[i] = 0.f;
+      }
+#pragma unroll
+      for (int off = 16; off >= 1; off >>= 1) {
+        const bool upper = (lane & off) != 0;
+#pragma unroll
+        for (int i = 0; i < off; ++i) {
+          const float send = upper ? f[i] : f[i + off];
+          const float recv = __shfl_xor_sync(0xffffffffu, send, off);
+          f[i] = (upper ? f[i + off] : f[i]) + recv;
+        }
+      }
+      if (lane < nvalid) atomicAdd(p.colsum + cbase + lane, f[0]);
     }
   }
 }
@@ -785,6 +806,9 @@ static int fill_epilogue(dpig_ctx* ctx, ConvUmmaParams& P, const dpig_conv_epilo
   P.mask_in = ep->mask_in;
   P.mask_in_words = (cout + 31) / 32;
   P.mask_neg = ep->mask_neg;
+  P.colsum = ep->colsum_masked;
+  if (ep->colsum_masked && !ep->out_masked)
+    return set_error(ctx, DPIG_EINVAL, "colsum_masked needs out_masked");
   if (g.rep != 1 && (ep->addend || ep->out_masked))
     return set_error(ctx, DPIG_EUNSUPPORTED, "upsampling epilogue cannot take addend/out_masked");
   return DPIG_OK;

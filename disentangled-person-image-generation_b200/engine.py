@@ -157,6 +157,7 @@ class _Pyramid:
                 self.x_in.append(SplitTensor(n, hh // 2, ww // 2, c + hn, dev))
                 self.md.append(_mask(n * (hh // 2) * (ww // 2), c + hn, dev))
         self.in_mask = in_mask
+        self.in_layer = None   # ConvLayer producing the pyramid input (set by the owner when in_mask is used)
         # backward buffers
         self.g_y = [SplitTensor(n, d[0], d[1], d[2], dev) for d in self.dims]
         self.gb = [SplitTensor(n, d[0], d[1], d[2], dev) for d in self.dims]
@@ -188,23 +189,24 @@ class _Pyramid:
             hh, ww, c = self.dims[idx]
             if wgrad:
                 eng.conv_wgrad(prog, l2, self.a[idx], self.gb[idx])
-            eng.conv_dgrad(prog, l2, self.gb[idx], hh, ww, out_masked=self.ga[idx], mask_in=self.ma[idx])
+            eng.conv_dgrad(prog, l2, self.gb[idx], hh, ww, out_masked=self.ga[idx], mask_in=self.ma[idx], db_of=l1)
             if wgrad:
                 eng.conv_wgrad(prog, l1, self.x_in[idx], self.ga[idx])
             if idx > 0:
                 # x_in[idx] = relu(conv_s2(y[idx-1])): emit the masked gradient directly
-                eng.conv_dgrad(prog, l1, self.ga[idx], hh, ww, out_masked=self.gd[idx - 1], mask_in=self.md[idx - 1],
-                               addend=self.g_y[idx])
                 ls = self.layers[3 * (idx - 1) + 2]
+                eng.conv_dgrad(prog, l1, self.ga[idx], hh, ww, out_masked=self.gd[idx - 1], mask_in=self.md[idx - 1],
+                               addend=self.g_y[idx], db_of=ls)
                 if wgrad:
                     eng.conv_wgrad(prog, ls, self.y[idx - 1], self.gd[idx - 1])
                 ph, pw, pc = self.dims[idx - 1]
                 eng.conv_dgrad(prog, ls, self.gd[idx - 1], ph, pw, out=self.g_y[idx - 1], out_masked=self.gb[idx - 1],
-                               mask_in=self.mb[idx - 1], addend=skip_grads[idx - 1] if skip_grads else None)
+                               mask_in=self.mb[idx - 1], addend=skip_grads[idx - 1] if skip_grads else None,
+                               db_of=self.layers[3 * (idx - 1) + 1])
             else:
                 if self.in_mask is not None:
                     eng.conv_dgrad(prog, l1, self.ga[0], hh, ww, out_masked=self.g_in, mask_in=self.in_mask,
-                                   addend=self.g_y[0])
+                                   addend=self.g_y[0], db_of=self.in_layer)
                 else:
                     eng.conv_dgrad(prog, l1, self.ga[0], hh, ww, out=self.g_in, addend=self.g_y[0])
 
@@ -244,6 +246,8 @@ class Stage1Engine:
         self.norm_mode = NORM_LAYER if mode == "wgan-gp" else NORM_BATCH  # wgan_gp.py:34-40
         self.world = dist.world_size if dist is not None else 1
         self._keep = []
+        self._db_done = set()
+        self.fuse_bias_grad = True
         self._build_params()
         self._build_buffers()
         if mode in ("wgan", "lsgan"):      # TF RMSProp's 'rms' slot is initialised to ones
@@ -465,6 +469,7 @@ class Stage1Engine:
             y_slots[rn - 1 - idx] = self.cat[idx].slice(xc, c - xc)
         self.genc = _Pyramid(self, "genc", [self.conv[n] for n in self.n_genc], self.g0, B, H, W, y_slots=y_slots,
                              in_mask=self.mg0)
+        self.genc.in_layer = self.conv[self.n_gstem]
         self.gtop_f32 = torch.zeros((B, self.bg_flat), device=dev)
         self.z = torch.zeros((B, cfg.z_num), device=dev)
         self.dec_in_f32 = torch.zeros((B, self.fh * self.fw * hn), device=dev)
@@ -552,10 +557,12 @@ class Stage1Engine:
 
     # -------------------------------------------------------------------------------- call helpers
     def _epilogue(self, prog, layer_bias, act, alpha, addend, mask_in, mask_neg, mask_out, out, out_masked, out_f32,
-                  out_f32_ps, upsample, class_bias=None):
+                  out_f32_ps, upsample, class_bias=None, colsum=None):
         ep = _lib.ConvEpilogue()
         if class_bias is not None:
             ep.class_bias = class_bias.data_ptr()
+        if colsum is not None:
+            ep.colsum_masked = colsum.data_ptr()
         ep.bias = layer_bias.data_ptr() if layer_bias is not None else None
         ep.act = act
         ep.alpha = alpha
@@ -589,9 +596,15 @@ class Stage1Engine:
                                                     layer.cout, layer.k, layer.stride))
 
     def conv_dgrad(self, prog, layer, dy, in_h, in_w, out=None, out_masked=None, mask_in=None, mask_neg=0.0, addend=None,
-                   out_f32=None, out_f32_ps=0):
+                   out_f32=None, out_f32_ps=0, db_of=None):
+        """db_of: the ConvLayer whose output-gradient `out_masked` is; its bias gradient (column sums of out_masked)
+        is then accumulated by this kernel's epilogue and the later conv_wgrad(db_of, ., out_masked) skips bias_grad."""
+        colsum = None
+        if db_of is not None and out_masked is not None and self.fuse_bias_grad:
+            colsum = db_of.db
+            self._db_done.add((id(prog), id(out_masked), db_of.wname))
         ep = self._epilogue(prog, None, ACT_NONE, 0.0, addend, mask_in, mask_neg, None, out, out_masked, out_f32,
-                            out_f32_ps, 1)
+                            out_f32_ps, 1, colsum=colsum)
         assert dy.c == layer.cout_pad, (layer.wname, dy.c, layer.cout_pad)
         prog.add("conv2d_bwd_data", dy.ref(), ptr(layer.bwd[0]), ptr(layer.bwd[1]), layer.k, layer.k, layer.stride,
                  in_h, in_w, layer.cin, ep, flops=2.0 * dy.n * dy.h * dy.w * layer.cout * layer.k * layer.k * layer.cin,
@@ -601,7 +614,7 @@ class Stage1Engine:
         prog.add("conv2d_bwd_filter", x.ref(), dy.ref(), layer.k, layer.k, layer.stride, layer.cin, layer.cout,
                  ptr(layer.dw), flops=2.0 * dy.n * dy.h * dy.w * layer.cout * layer.k * layer.k * layer.cin,
                  tag="%s %dx%dx%dx%d->%d k%ds%d" % (layer.wname, x.n, x.h, x.w, layer.cin, layer.cout, layer.k, layer.stride))
-        if not bias:
+        if not bias or (id(prog), id(dy), layer.wname) in self._db_done:
             return
         if dy.c != layer.cout:  # channel-padded gradient (e.g. the 3-channel image gradient held in 8)
             dy = dy.slice(0, layer.cout)
@@ -787,7 +800,7 @@ class Stage1Engine:
         lo = self.conv[self.n_gout]
         self.conv_wgrad(p, lo, self.dec_y[rn - 1], self.g_G8)
         self.conv_dgrad(p, lo, self.g_G8, H, W, out=self.dec_gy[rn - 1], out_masked=self.dec_gb[rn - 1],
-                        mask_in=self.dec_mb[rn - 1])
+                        mask_in=self.dec_mb[rn - 1], db_of=self.conv[self.n_gdec[rn - 1][1]])
         for idx in range(rn - 1, -1, -1):
             names = self.n_gdec[idx]
             lvl = rn - 1 - idx
@@ -801,9 +814,9 @@ class Stage1Engine:
                 p.add("ew_combine", self.dec_gu[idx].ref(), gup.ref(), None, None, None, 0, ptr(self.dec_mu[idx]), 0.0, 1)
                 self.conv_wgrad(p, lu, self.dec_y[idx], self.dec_gu[idx])
                 self.conv_dgrad(p, lu, self.dec_gu[idx], hh, ww, out=self.dec_gy[idx], out_masked=self.dec_gb[idx],
-                                mask_in=self.dec_mb[idx])
+                                mask_in=self.dec_mb[idx], db_of=l2)
             self.conv_wgrad(p, l2, self.dec_a[idx], self.dec_gb[idx])
-            self.conv_dgrad(p, l2, self.dec_gb[idx], hh, ww, out_masked=self.dec_ga[idx], mask_in=self.dec_ma[idx])
+            self.conv_dgrad(p, l2, self.dec_gb[idx], hh, ww, out_masked=self.dec_ga[idx], mask_in=self.dec_ma[idx], db_of=l1)
             self.conv_wgrad(p, l1, self.cat[idx], self.dec_ga[idx])
             self.conv_dgrad(p, l1, self.dec_ga[idx], hh, ww, out=self.g_cat[idx], addend=self.dec_gy[idx])
         # ---- bottleneck FCs (models.py:543-555)
@@ -835,7 +848,8 @@ class Stage1Engine:
         # pose rows of the filter gradient on the tensor cores; embedding rows and d(emb) from per-tap sums of g
         p.add("conv2d_bwd_filter_rows", self.gin.ref(), gi.ref(), 3, 3, 1, cfg.keypoints, hn, ptr(dwt[0, e:]), self.gin_c,
               flops=2.0 * B * H * W * hn * 9 * cfg.keypoints, tag="%s pose rows" % ls.wname)
-        p.add("bias_grad", gi.ref(), ptr(ls.db))
+        if (id(p), id(gi), ls.wname) not in self._db_done:
+            p.add("bias_grad", gi.ref(), ptr(ls.db))
         p.add("stem_tap_sums", gi.ref(), ptr(self.stem_cls), ptr(self.stem_ts))
         for tap in range(9):
             p.add("linear_bwd", ptr(self.emb), ptr(wt[tap]), ptr(self.stem_ts[tap]), ptr(self.stem_tmp), ptr(dwt[tap]),
@@ -863,9 +877,9 @@ class Stage1Engine:
         p.add("ew_combine", self.g_xs_m.ref(), self.g_xs.ref(), None, None, None, 0, ptr(self.me2), 0.0, 0)
         e0, e1, e2 = self.conv[self.n_e0], self.conv[self.n_e1], self.conv[self.n_e2]
         self.conv_wgrad(p, e2, self.e1, self.g_xs_m)
-        self.conv_dgrad(p, e2, self.g_xs_m, H, W, out_masked=self.g_e1, mask_in=self.me1)
+        self.conv_dgrad(p, e2, self.g_xs_m, H, W, out_masked=self.g_e1, mask_in=self.me1, db_of=e1)
         self.conv_wgrad(p, e1, self.e0, self.g_e1)
-        self.conv_dgrad(p, e1, self.g_e1, H, W, out_masked=self.g_e0, mask_in=self.me0, addend=self.g_xs)
+        self.conv_dgrad(p, e1, self.g_e1, H, W, out_masked=self.g_e0, mask_in=self.me0, addend=self.g_xs, db_of=e0)
         self.conv_wgrad(p, e0, self.x8, self.g_e0)
 
     def _prog_disc_forward(self, p, dp, img):
@@ -920,7 +934,7 @@ class Stage1Engine:
             else:
                 # layer-1 output is a plain LeakyReLU: emit the masked gradient wrt its conv output
                 self.conv_dgrad(p, layer, dp.g_pre[i], hh * 2, ww * 2, out_masked=dp.g_pre[0], mask_in=dp.m[0],
-                                mask_neg=0.2)
+                                mask_neg=0.2, db_of=self.conv[self.n_d[0]] if params else None)
         l1 = self.conv[self.n_d[0]]
         if params:
             self.conv_wgrad(p, l1, img, dp.g_pre[0])

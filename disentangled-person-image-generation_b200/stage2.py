@@ -175,6 +175,71 @@ class _Factor:
                                   bwd_par=ct.backward_program(params=True), bwd_data=ct.backward_program(params=False))
         self.loss = torch.zeros((2,), device=device)
         self.t = {"g": 0, "d": 0}
+        self._build_gp(ctx, batch, dim, d_name, device)
+
+    def _build_gp(self, ctx, batch, dim, d_name, device):
+        """WGAN-GP on 2-D [B,F] inputs exactly as trainer.py:226-236 writes it: alpha [B,1], interpolates =
+        real + alpha*(fake-real), slopes = sqrt(sum_axis1 grad^2), gp = mean((slopes-1)^2).  The critic is a LeakyReLU
+        MLP (piecewise linear), so d(lambda*gp)/d(theta) is the parameter gradient of the JVP along
+        v = d(lambda*gp)/d(grad): tangent pass hdot_i = mask_i * (hdot_{i-1} W_i), then its adjoint (linear_bwd on the
+        tangent activations).  No primal-path term: the masks are locally constant."""
+        dn = [n for n, _ in fc_critic_specs(d_name, dim)]
+        self.gp_layers = [(dn[2 * i], dn[2 * i + 1]) for i in range(len(dn) // 2)]
+        ct = FCTape(ctx, self.dp, batch, device)
+        self.xhat = _Node(batch, dim, device)
+        ct.nodes.append(self.xhat)
+        hh = self.xhat
+        self.gp_h = []
+        for wn, bn in self.gp_layers[:-1]:
+            hh = ct.linear(hh, wn, bn, act=ACT_LRELU)
+            self.gp_h.append(hh)
+        self.gp_out = ct.linear(hh, *self.gp_layers[-1])
+        self.gp_tape = ct
+        self.gp_fwd = ct.forward_program()
+        self.gp_bwd_data = ct.backward_program(params=False)
+        self.gp_alpha = torch.zeros((batch,), device=device)
+        self.gp_alpha_fixed = False
+        self.gp_slopes = torch.zeros((batch,), device=device)
+        self.gp_loss = torch.zeros((1,), device=device)
+        self.gp_v = torch.zeros((batch, dim), device=device)
+        self.gp_ones = torch.ones((batch, 1), device=device)
+        widths = [self.dp.view(wn).shape[1] for wn, _ in self.gp_layers[:-1]]
+        self.gp_hd = [torch.zeros((batch, w), device=device) for w in widths]      # tangent activations
+        self.gp_hb = [torch.zeros((batch, w), device=device) for w in widths]      # their adjoints
+        self.gp_xb = torch.zeros((batch, dim), device=device)
+
+    def gp_program(self, lam):
+        """Program computing lambda*gp (into gp_loss) and accumulating its critic-parameter gradient."""
+        p = Program(self.ctx)
+        p.keep.append(self)
+        B, F = self.B, self.dim
+        p.add("gp_interpolate", ptr(self.real.data), ptr(self.fake.data), ptr(self.gp_alpha), B, F, ptr(self.xhat.data))
+        p.calls += self.gp_fwd.calls
+        p.add_py(lambda s: self.gp_out.grad.fill_(1.0))
+        p.calls += self.gp_bwd_data.calls
+        p.add("gp_penalty", ptr(self.xhat.grad), B, F, float(lam), ptr(self.gp_slopes), ptr(self.gp_loss), ptr(self.gp_v))
+        # tangent forward along v
+        prev = self.gp_v
+        for i, (wn, bn) in enumerate(self.gp_layers[:-1]):
+            w = self.dp.view(wn)
+            p.add("linear_fwd", ptr(prev), ptr(w), None, ptr(self.gp_hd[i]), B, w.shape[0], w.shape[1], ACT_NONE, 0.0)
+            p.add("act_bwd_f32", ptr(self.gp_h[i].data), ptr(self.gp_hd[i]), self.gp_hd[i].numel(), 0.2)
+            prev = self.gp_hd[i]
+        # adjoint of S = sum_n hdot_L(n) . W_out
+        wn, bn = self.gp_layers[-1]
+        w = self.dp.view(wn)
+        L = len(self.gp_hd)
+        p.add("linear_bwd", ptr(self.gp_hd[L - 1]), ptr(w), ptr(self.gp_ones), ptr(self.gp_hb[L - 1]),
+              ptr(self.dp.gview(wn)), None, B, w.shape[0], 1)
+        for i in range(L - 1, -1, -1):
+            wn, bn = self.gp_layers[i]
+            w = self.dp.view(wn)
+            p.add("act_bwd_f32", ptr(self.gp_h[i].data), ptr(self.gp_hb[i]), self.gp_hb[i].numel(), 0.2)
+            x_in = self.gp_hd[i - 1] if i > 0 else self.gp_v
+            dx = self.gp_hb[i - 1] if i > 0 else None
+            p.add("linear_bwd", ptr(x_in), ptr(w), ptr(self.gp_hb[i]), ptr(dx) if dx is not None else None,
+                  ptr(self.dp.gview(wn)), None, B, w.shape[0], w.shape[1])
+        return p
 
 
 class Stage2Engine:
@@ -190,6 +255,12 @@ class Stage2Engine:
         self.f = {"fg": _Factor(self.ctx, B, self.fg_dim, 512, "Gaussian_FC_Fg/G_FC", "Fg_FCDis_", dev),
                   "bg": _Factor(self.ctx, B, self.bg_dim, 256, "Gaussian_FC_Bg/G_FC", "Bg_FCDis_", dev)}
         self.B = B
+        self.lam = 10.0
+        if mode == "wgan-gp":
+            for f in self.f.values():
+                f.p_gp = f.gp_program(self.lam)
+                f.gp.v.zero_()     # Adam slots start at zero (RMSProp's start at one)
+                f.dp.v.zero_()
 
     def param_groups(self):
         return [g for f in self.f.values() for g in (f.gp, f.dp)]
@@ -229,7 +300,8 @@ class Stage2Engine:
             clip = 0.01 if (self.mode == "wgan" and which == "d") else 0.0
             self.ctx.rmsprop_step(ptr(grp.value), ptr(grp.grad), ptr(grp.v), grp.total, lr, 0.9, 1e-10, 1.0, clip, s)
         else:
-            self.ctx.adam_step(ptr(grp.value), ptr(grp.grad), ptr(grp.m), ptr(grp.v), grp.total, lr, 0.5, 0.999, 1e-8,
+            b2 = 0.9 if self.mode == "wgan-gp" else 0.999
+            self.ctx.adam_step(ptr(grp.value), ptr(grp.grad), ptr(grp.m), ptr(grp.v), grp.total, lr, 0.5, b2, 1e-8,
                                f.t[which], 1.0, s)
 
     def g_grads(self, factor):
@@ -256,6 +328,10 @@ class Stage2Engine:
                           ptr(cr["out"].grad), ptr(cf["out"].grad), s)
         cr["bwd_par"].run(s)
         cf["bwd_par"].run(s)
+        if self.mode == "wgan-gp":
+            if not f.gp_alpha_fixed:
+                f.gp_alpha.uniform_(0.0, 1.0)
+            f.p_gp.run(s)
 
     def g_step(self, factor):
         self.g_grads(factor)

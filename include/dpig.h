@@ -80,6 +80,9 @@ typedef struct dpig_conv_epilogue {
    * (row class 0/1/2 = first/interior/last row) * 3 + column class -- the exact contribution of input channels
    * that are constant over space (the broadcast embedding, trainer.py:588-590), see dpig_stem_class_bias. */
   const float* class_bias;
+  /* optional fp32 [cout]: += sum over pixels of out_masked -- the bias gradient of the layer that out_masked is the
+   * output-gradient of, fused here so that the gradient tensor is not re-read by dpig_bias_grad. */
+  float* colsum_masked;
 } dpig_conv_epilogue;
 
 /* ---- context ----------------------------------------------------------------------------- */

@@ -104,3 +104,34 @@ def test_stage2_iteration_runs():
     s2.train_iteration(1, lambda: synth.make_batch(s2.B, 32, 16, seed=100 + next(it)))
     torch.cuda.synchronize()
     assert all(np.isfinite(v).all() for v in s2.get_params().values())
+
+
+@pytest.mark.parametrize("factor", ["fg", "bg"])
+def test_stage2_wgan_gp_fc_critic(factor):
+    """Gradient penalty on [B,F] embeddings through the FC critic (trainer.py:226-236 as written for 2-D inputs):
+    the JVP/adjoint second pass vs torch double-backward."""
+    s1, s2, p1, p2, b, cfg = _setup(mode="wgan-gp")
+    s2.encode_real()
+    f = s2.f[factor]
+    rng = np.random.default_rng(19)
+    s2.sample_noise(factor, rng.normal(0, 0.2, size=(s2.B, f.dim)).astype(np.float32))
+    alpha = torch.tensor(rng.uniform(0, 1, size=s2.B))
+    f.gp_alpha.copy_(alpha.float().cuda())
+    f.gp_alpha_fixed = True
+    s2.d_grads(factor)
+    torch.cuda.synchronize()
+    got = s2.get_params(grads=True)
+    p = nets.to_torch(p2, torch.float64, requires_grad=True)
+    name = "Fg_FCDis_" if factor == "fg" else "Bg_FCDis_"
+    real = f.real.data.detach().double().cpu()
+    fake = f.fake.data.detach().double().cpu()
+    disc = lambda t: nets.fc_discriminator(p, t, name=name)  # noqa: E731
+    _, d_loss = T.gan_loss("wgan-gp", disc(real), disc(fake))
+    gp, slopes, _ = T.gradient_penalty(disc, real, fake, alpha)
+    dnames = [k for k in p if k.startswith(name)]
+    grads = torch.autograd.grad(d_loss + 10.0 * gp, [p[k] for k in dnames], allow_unused=True)
+    assert _rel(f.gp_slopes, slopes.detach()) < 1e-5
+    assert abs(float(f.gp_loss.cpu()[0]) - float(gp)) < 1e-5
+    for k, g in zip(dnames, grads):
+        if g is not None and float(g.abs().max()) > 1e-12:
+            assert _rel(got[k], g) < 2e-4, k
