@@ -1,6 +1,7 @@
 // Context management and error plumbing of libdpig.so (C ABI in include/dpig.h).
 #include <cstdarg>
 #include <cstdio>
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace dpig {
@@ -52,6 +53,9 @@ extern "C" int dpig_ctx_create(int device, dpig_ctx** out) {
     return DPIG_ECUDA;
   }
   ctx->encode_tiled = reinterpret_cast<decltype(ctx->encode_tiled)>(fn);
+  if (const char* e = getenv("DPIG_CONV_PAIR")) ctx->pair_mode = atoi(e);  // A/B switches for the conv tilings
+  if (const char* e = getenv("DPIG_CONV_DUAL")) ctx->dual_mode = atoi(e);
+  if (const char* e = getenv("DPIG_CONV_STAGES")) ctx->max_stages = atoi(e);
   *out = ctx;
   return DPIG_OK;
 }
@@ -65,6 +69,15 @@ extern "C" const char* dpig_last_error(const dpig_ctx* ctx) {
 extern "C" int dpig_ctx_set_fast_mode(dpig_ctx* ctx, int fast) {
   DPIG_CHECK_CTX(ctx);
   ctx->fast_mode = fast != 0;
+  return DPIG_OK;
+}
+
+extern "C" int dpig_ctx_set_conv_tiling(dpig_ctx* ctx, int pair_mode, int dual_mode) {
+  DPIG_CHECK_CTX(ctx);
+  if (pair_mode < 0 || pair_mode > 2 || dual_mode < 0 || dual_mode > 2)
+    return set_error(ctx, DPIG_EINVAL, "conv tiling modes must be 0, 1 or 2");
+  ctx->pair_mode = pair_mode;
+  ctx->dual_mode = dual_mode;
   return DPIG_OK;
 }
 

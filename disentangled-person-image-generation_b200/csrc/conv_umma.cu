@@ -47,6 +47,8 @@ struct ConvUmmaParams {
   int tiles_w, tiles_h, tiles_n;
   int Wo, Ho, No;
   int block_n, cout, stages;
+  int pair;  // 1: launched as 2-CTA clusters running cta_group::2 MMAs (b_bytes = this CTA's half of the B rows)
+  int dual;  // 1: one CTA computes two adjacent pixel tiles per weight tile (two accumulators; block_n <= 128)
   uint32_t a_tx_bytes, b_bytes, tmem_cols;
   const float* bias;
   const float* class_bias;  // [N][9][cout]: per-image bias indexed by the pixel's border class (stem shortcut)
@@ -322,12 +324,26 @@ __device__ __forceinline__ void epi_chunk(const ConvUmmaParams& p, uint8_t* stag
 // Persistent: grid = min(#tiles, #SMs); CTA b processes tiles b, b+grid, ...  The smem pipeline runs
 // continuously across tiles and the fp32 accumulator is double-buffered in TMEM (2 x block_n columns), so
 // the epilogue of tile j overlaps the MMAs of tile j+1.
+//
+// kPair: the grid is a list of 2-CTA clusters (one TPC each).  The pair computes two pixel tiles of the same output
+// channel block with ONE M=256 `cta_group::2` MMA stream issued by the leader (cluster rank 0): each CTA stages its
+// own 128 pixel rows of A and HALF of the weight rows (p.b_bytes is the per-CTA share), so the L2 -> SM operand
+// traffic per FLOP drops by a third (N=256) -- the single-CTA kernel is bound by that feed, not by the tensor pipe.
+//   full[s]        leader only; count 1 (leader's expect_tx covers both CTAs' bytes, peer TMAs signal it remotely)
+//   empty[s]       one per CTA; arrived by the leader's multicast tcgen05.commit
+//   tmem_full[a]   one per CTA; multicast commit after the last MMA of a tile
+//   tmem_empty[a]  leader only; count 2*kEpiWarps (peer epilogue warps arrive remotely)
+template <bool kPair>
+// 10 warps = 3+3+2+2 per SM sub-partition (16K registers each) caps the kernel at 168 registers per thread.
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv_umma_kernel(const __grid_constant__ ConvUmmaParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = align1024(smem_raw);
-  const uint32_t b_off = p.planes * kABytes;
-  const uint32_t stage_bytes = p.planes * (kABytes + p.b_bytes);
+  // dual: the stage holds the activation tiles of TWO adjacent pixel tiles next to one weight tile
+  // ([A0 hi, A0 lo, A1 hi, A1 lo, B hi, B lo]); a third fewer operand bytes per FLOP for narrow channel blocks.
+  const int nsub = (!kPair && p.dual) ? 2 : 1;
+  const uint32_t b_off = nsub * p.planes * kABytes;
+  const uint32_t stage_bytes = p.planes * (nsub * kABytes + p.b_bytes);
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + p.stages * stage_bytes);
   uint64_t* empty = full + p.stages;
   uint64_t* tmem_full = empty + p.stages;   // [2]
@@ -339,7 +355,12 @@ conv_umma_kernel(const __grid_constant__ ConvUmmaParams p) {
   const int lane = threadIdx.x & 31;
   const int pix_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
   const int n_tiles = (p.cout + p.block_n - 1) / p.block_n;
-  const int total_tiles = pix_tiles * n_tiles;
+  // work units: single CTA -> (pixel tile, channel block); pair -> (two adjacent pixel tiles, channel block)
+  const uint32_t rank = kPair ? ptx::cluster_ctarank() : 0u;
+  const int unit0 = kPair ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
+  const int unit_step = kPair ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
+  const int unit_pix_tiles = (kPair || nsub == 2) ? (pix_tiles + 1) / 2 : pix_tiles;
+  const int total_tiles = unit_pix_tiles * n_tiles;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.stages; ++s) {
@@ -348,20 +369,30 @@ conv_umma_kernel(const __grid_constant__ ConvUmmaParams p) {
     }
     for (int a = 0; a < 2; ++a) {
       ptx::mbar_init(&tmem_full[a], 1);
-      ptx::mbar_init(&tmem_empty[a], kEpiWarps);  // one arrive per epilogue warp
+      ptx::mbar_init(&tmem_empty[a], kPair ? 2 * kEpiWarps : kEpiWarps);  // one arrive per epilogue warp
     }
     ptx::fence_barrier_init();
   }
   if (warp == 1) {
-    switch (p.tmem_cols) {  // power of two >= 2 * block_n
-      case 64: ptx::tmem_alloc<64>(tmem_slot); break;
-      case 128: ptx::tmem_alloc<128>(tmem_slot); break;
-      case 256: ptx::tmem_alloc<256>(tmem_slot); break;
-      default: ptx::tmem_alloc<512>(tmem_slot); break;
+    if (kPair) {
+      switch (p.tmem_cols) {
+        case 64: ptx::tmem_alloc_pair<64>(tmem_slot); break;
+        case 128: ptx::tmem_alloc_pair<128>(tmem_slot); break;
+        case 256: ptx::tmem_alloc_pair<256>(tmem_slot); break;
+        default: ptx::tmem_alloc_pair<512>(tmem_slot); break;
+      }
+    } else {
+      switch (p.tmem_cols) {  // power of two >= 2 * block_n
+        case 64: ptx::tmem_alloc<64>(tmem_slot); break;
+        case 128: ptx::tmem_alloc<128>(tmem_slot); break;
+        case 256: ptx::tmem_alloc<256>(tmem_slot); break;
+        default: ptx::tmem_alloc<512>(tmem_slot); break;
+      }
     }
   }
   ptx::tc_fence_before();
-  __syncthreads();
+  if (kPair) ptx::cluster_sync();  // peer barriers must be initialised before any remote arrive / multicast commit
+  else __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const int steps_per_tile = p.num_taps * p.kchunks;
@@ -373,24 +404,45 @@ conv_umma_kernel(const __grid_constant__ ConvUmmaParams p) {
       for (int pl = 0; pl < p.planes; ++pl) ptx::prefetch_tmap(&p.b_map[pl]);
       int s = 0;
       uint32_t ph = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int pt = tile % pix_tiles, nt = tile / pix_tiles;
+      const int b_row0 = kPair ? static_cast<int>(rank) * (p.block_n >> 1) : 0;
+      for (int tile = unit0; tile < total_tiles; tile += unit_step) {
+        const int upt = tile % unit_pix_tiles, nt = tile / unit_pix_tiles;
+        // pt == pix_tiles for the odd tail of a pair / dual unit: an all-out-of-bounds (zero-filled) tile
+        const int pt = kPair ? 2 * upt + static_cast<int>(rank) : (nsub == 2 ? 2 * upt : upt);
         const int tw = pt % p.tiles_w;
         const int th = (pt / p.tiles_w) % p.tiles_h;
         const int tn = pt / (p.tiles_w * p.tiles_h);
         const int w0 = tw * p.BW, h0 = th * p.BH, n0 = tn * p.BN;
+        const int pt1 = pt + 1;  // second pixel tile of a dual unit
+        const int w1 = (pt1 % p.tiles_w) * p.BW, h1 = ((pt1 / p.tiles_w) % p.tiles_h) * p.BH;
+        const int n1 = (pt1 / (p.tiles_w * p.tiles_h)) * p.BN;
         for (int t = 0; t < p.num_taps; ++t) {
           const ConvTap tap = p.taps[t];
           for (int kc = 0; kc < p.kchunks; ++kc) {
             ptx::mbar_wait(&empty[s], ph ^ 1);
             uint8_t* st = smem + s * stage_bytes;
-            ptx::mbar_expect_tx(&full[s], p.planes * (p.a_tx_bytes + p.b_bytes));
+            if (kPair) {
+              const uint32_t lead_full = ptx::mapa_u32(ptx::smem_u32(&full[s]), 0);
+              if (rank == 0) ptx::mbar_expect_tx(&full[s], 2 * p.planes * (p.a_tx_bytes + p.b_bytes));
+              for (int pl = 0; pl < p.planes; ++pl)
+                ptx::tma_load_4d_pair(st + pl * kABytes, &p.a_map[tap.src][pl], lead_full, kc * 64, w0 + tap.dw,
+                                      h0 + tap.dh, n0);
+              for (int pl = 0; pl < p.planes; ++pl)
+                ptx::tma_load_3d_pair(st + b_off + pl * p.b_bytes, &p.b_map[pl], lead_full, kc * 64,
+                                      nt * p.block_n + b_row0, tap.wtap);
+            } else {
+            ptx::mbar_expect_tx(&full[s], p.planes * (nsub * p.a_tx_bytes + p.b_bytes));
             for (int pl = 0; pl < p.planes; ++pl)
               ptx::tma_load_4d(st + pl * kABytes, &p.a_map[tap.src][pl], &full[s], kc * 64, w0 + tap.dw,
                                h0 + tap.dh, n0);
+            if (nsub == 2)
+              for (int pl = 0; pl < p.planes; ++pl)
+                ptx::tma_load_4d(st + (p.planes + pl) * kABytes, &p.a_map[tap.src][pl], &full[s], kc * 64,
+                                 w1 + tap.dw, h1 + tap.dh, n1);
             for (int pl = 0; pl < p.planes; ++pl)
               ptx::tma_load_3d(st + b_off + pl * p.b_bytes, &p.b_map[pl], &full[s], kc * 64, nt * p.block_n,
                                tap.wtap);
+            }
             if (++s == p.stages) {
               s = 0;
               ph ^= 1;
@@ -400,16 +452,16 @@ conv_umma_kernel(const __grid_constant__ ConvUmmaParams p) {
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      const uint32_t idesc = ptx::make_idesc_bf16(128, p.block_n, 0, 0);
+    if (lane == 0 && rank == 0) {
+      const uint32_t idesc = ptx::make_idesc_bf16(kPair ? 256 : 128, p.block_n, 0, 0);
       int s = 0;
       uint32_t ph = 0;
       int j = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++j) {
+      for (int tile = unit0; tile < total_tiles; tile += unit_step, ++j) {
         const int acc = j & 1;
         ptx::mbar_wait(&tmem_empty[acc], ((j >> 1) & 1) ^ 1);
         ptx::tc_fence_after();
-        const uint32_t tmem_acc = tmem_base + acc * p.block_n;
+        const uint32_t tmem_acc = tmem_base + acc * nsub * p.block_n;
         for (int step = 0; step < steps_per_tile; ++step) {
           ptx::mbar_wait(&full[s], ph);
           ptx::tc_fence_after();
@@ -421,21 +473,44 @@ conv_umma_kernel(const __grid_constant__ ConvUmmaParams p) {
           for (int k = 0; k < 4; ++k) {
             const uint64_t da_hi = ptx::make_desc_sw128(a_hi + k * 32, 16, 1024);
             const uint64_t db_hi = ptx::make_desc_sw128(b_hi + k * 32, 16, 1024);
-            ptx::umma_bf16(tmem_acc, da_hi, db_hi, idesc, (step | k) ? 1u : 0u);
-            if (p.planes == 2) {
-              const uint64_t da_lo = ptx::make_desc_sw128(a_lo + k * 32, 16, 1024);
-              const uint64_t db_lo = ptx::make_desc_sw128(b_lo + k * 32, 16, 1024);
-              ptx::umma_bf16(tmem_acc, da_hi, db_lo, idesc, 1u);
-              ptx::umma_bf16(tmem_acc, da_lo, db_hi, idesc, 1u);
+            if (kPair) {
+              ptx::umma_bf16_pair(tmem_acc, da_hi, db_hi, idesc, (step | k) ? 1u : 0u);
+              if (p.planes == 2) {
+                const uint64_t da_lo = ptx::make_desc_sw128(a_lo + k * 32, 16, 1024);
+                const uint64_t db_lo = ptx::make_desc_sw128(b_lo + k * 32, 16, 1024);
+                ptx::umma_bf16_pair(tmem_acc, da_hi, db_lo, idesc, 1u);
+                ptx::umma_bf16_pair(tmem_acc, da_lo, db_hi, idesc, 1u);
+              }
+            } else {
+              ptx::umma_bf16(tmem_acc, da_hi, db_hi, idesc, (step | k) ? 1u : 0u);
+              if (p.planes == 2) {
+                const uint64_t da_lo = ptx::make_desc_sw128(a_lo + k * 32, 16, 1024);
+                const uint64_t db_lo = ptx::make_desc_sw128(b_lo + k * 32, 16, 1024);
+                ptx::umma_bf16(tmem_acc, da_hi, db_lo, idesc, 1u);
+                ptx::umma_bf16(tmem_acc, da_lo, db_hi, idesc, 1u);
+              }
+              if (nsub == 2) {  // second pixel tile: same weight descriptors, next accumulator
+                const uint32_t a1 = a_hi + p.planes * kABytes;
+                const uint64_t da1_hi = ptx::make_desc_sw128(a1 + k * 32, 16, 1024);
+                ptx::umma_bf16(tmem_acc + p.block_n, da1_hi, db_hi, idesc, (step | k) ? 1u : 0u);
+                if (p.planes == 2) {
+                  const uint64_t da1_lo = ptx::make_desc_sw128(a1 + kABytes + k * 32, 16, 1024);
+                  const uint64_t db_lo = ptx::make_desc_sw128(b_lo + k * 32, 16, 1024);
+                  ptx::umma_bf16(tmem_acc + p.block_n, da1_hi, db_lo, idesc, 1u);
+                  ptx::umma_bf16(tmem_acc + p.block_n, da1_lo, db_hi, idesc, 1u);
+                }
+              }
             }
           }
-          ptx::umma_commit(&empty[s]);
+          if (kPair) ptx::umma_commit_pair(&empty[s], 3);
+          else ptx::umma_commit(&empty[s]);
           if (++s == p.stages) {
             s = 0;
             ph ^= 1;
           }
         }
-        ptx::umma_commit(&tmem_full[acc]);
+        if (kPair) ptx::umma_commit_pair(&tmem_full[acc], 3);
+        else ptx::umma_commit(&tmem_full[acc]);
       }
     }
   } else {
@@ -451,61 +526,82 @@ conv_umma_kernel(const __grid_constant__ ConvUmmaParams p) {
     const int hl = tq % p.BH;
     const int nl = tq / p.BH;
     uint8_t* stage = epi_smem + ew * kEpiBytesPerWarp;
+    const uint32_t lead_tmem_empty[2] = {kPair ? ptx::mapa_u32(ptx::smem_u32(&tmem_empty[0]), 0) : 0u,
+                                         kPair ? ptx::mapa_u32(ptx::smem_u32(&tmem_empty[1]), 0) : 0u};
     int j = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++j) {
+    for (int tile = unit0; tile < total_tiles; tile += unit_step, ++j) {
       const int acc = j & 1;
-      const int pt = tile % pix_tiles, nt = tile / pix_tiles;
-      const int tw = pt % p.tiles_w;
-      const int th = (pt / p.tiles_w) % p.tiles_h;
-      const int tn = pt / (p.tiles_w * p.tiles_h);
-      const int w = tw * p.BW + wl, h = th * p.BH + hl, n = tn * p.BN + nl;
-      const bool valid = (nl < p.BN) && (w < p.Wo) && (h < p.Ho) && (n < p.No);
-      const int lpix = (n * p.Ho + h) * p.Wo + w;  // logical pixel (< 2^31 for every supported shape)
-      const int py = h * p.sh + p.oh, px = w * p.sw + p.ow;
-      const int ppix = (n * p.out_H + py) * p.out_W + px;
-      const float* cbias = nullptr;
-      if (p.class_bias && valid) {
-        const int ch = h == 0 ? 0 : (h == p.Ho - 1 ? 2 : 1), cw = w == 0 ? 0 : (w == p.Wo - 1 ? 2 : 1);
-        cbias = p.class_bias + (static_cast<long long>(n) * 9 + ch * 3 + cw) * p.cout;
-      }
-
+      const int upt = tile % unit_pix_tiles, nt = tile / unit_pix_tiles;
       ptx::mbar_wait(&tmem_full[acc], (j >> 1) & 1);
       ptx::tc_fence_after();
-      const uint32_t tmem_acc = tmem_base + acc * p.block_n + (static_cast<uint32_t>(lg * 32) << 16);
-
-      const int nchunks = p.block_n >> 5;
       bool released = false;
-      for (int ci = cpar; ci < nchunks; ci += kEpiWarps / 4) {
-        const int c0 = ci << 5;
-        uint32_t v[32];
-        ptx::tmem_ld32(tmem_acc + c0, v);
-        ptx::tmem_ld_wait();
-        if (ci + kEpiWarps / 4 >= nchunks) {
-          // this warp's last TMEM read of the tile: hand the accumulator stage back to the MMA warp
-          ptx::tc_fence_before();
-          __syncwarp();
-          if (lane == 0) ptx::mbar_arrive(&tmem_empty[acc]);
-          released = true;
+      for (int sub = 0; sub < nsub; ++sub) {
+        const int pt = kPair ? 2 * upt + static_cast<int>(rank) : (nsub == 2 ? 2 * upt + sub : upt);
+        const int tw = pt % p.tiles_w;
+        const int th = (pt / p.tiles_w) % p.tiles_h;
+        const int tn = pt / (p.tiles_w * p.tiles_h);
+        const int w = tw * p.BW + wl, h = th * p.BH + hl, n = tn * p.BN + nl;
+        const bool valid = (nl < p.BN) && (w < p.Wo) && (h < p.Ho) && (n < p.No);
+        const int lpix = (n * p.Ho + h) * p.Wo + w;  // logical pixel (< 2^31 for every supported shape)
+        const int py = h * p.sh + p.oh, px = w * p.sw + p.ow;
+        const int ppix = (n * p.out_H + py) * p.out_W + px;
+        const float* cbias = nullptr;
+        if (p.class_bias && valid) {
+          const int ch = h == 0 ? 0 : (h == p.Ho - 1 ? 2 : 1), cw = w == 0 ? 0 : (w == p.Wo - 1 ? 2 : 1);
+          cbias = p.class_bias + (static_cast<long long>(n) * 9 + ch * 3 + cw) * p.cout;
         }
-        epi_chunk(p, stage, v, nt * p.block_n + c0, valid, lpix, ppix, cbias, lane);
+        const uint32_t tmem_acc =
+            tmem_base + (acc * nsub + sub) * p.block_n + (static_cast<uint32_t>(lg * 32) << 16);
+
+        const int nchunks = p.block_n >> 5;
+        for (int ci = cpar; ci < nchunks; ci += kEpiWarps / 4) {
+          const int c0 = ci << 5;
+          uint32_t v[32];
+          ptx::tmem_ld32(tmem_acc + c0, v);
+          ptx::tmem_ld_wait();
+          if (sub == nsub - 1 && ci + kEpiWarps / 4 >= nchunks) {
+            // this warp's last TMEM read of the unit: hand the accumulator stage back to the MMA warp
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+              if (kPair) ptx::mbar_arrive_cluster(lead_tmem_empty[acc]);
+              else ptx::mbar_arrive(&tmem_empty[acc]);
+            }
+            released = true;
+          }
+          epi_chunk(p, stage, v, nt * p.block_n + c0, valid, lpix, ppix, cbias, lane);
+        }
       }
       if (!released) {  // fewer chunks than epilogue warps per lane group (block_n == 32)
         ptx::tc_fence_before();
         __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(&tmem_empty[acc]);
+        if (lane == 0) {
+          if (kPair) ptx::mbar_arrive_cluster(lead_tmem_empty[acc]);
+          else ptx::mbar_arrive(&tmem_empty[acc]);
+        }
       }
     }
   }
 
   ptx::tc_fence_before();
-  __syncthreads();
+  if (kPair) ptx::cluster_sync();  // the leader's MMAs read the peer's smem; nobody leaves before both are done
+  else __syncthreads();
   if (warp == 1) {
     ptx::tc_fence_after();
-    switch (p.tmem_cols) {
-      case 64: ptx::tmem_dealloc<64>(tmem_base); break;
-      case 128: ptx::tmem_dealloc<128>(tmem_base); break;
-      case 256: ptx::tmem_dealloc<256>(tmem_base); break;
-      default: ptx::tmem_dealloc<512>(tmem_base); break;
+    if (kPair) {
+      switch (p.tmem_cols) {
+        case 64: ptx::tmem_dealloc_pair<64>(tmem_base); break;
+        case 128: ptx::tmem_dealloc_pair<128>(tmem_base); break;
+        case 256: ptx::tmem_dealloc_pair<256>(tmem_base); break;
+        default: ptx::tmem_dealloc_pair<512>(tmem_base); break;
+      }
+    } else {
+      switch (p.tmem_cols) {
+        case 64: ptx::tmem_dealloc<64>(tmem_base); break;
+        case 128: ptx::tmem_dealloc<128>(tmem_base); break;
+        case 256: ptx::tmem_dealloc<256>(tmem_base); break;
+        default: ptx::tmem_dealloc<512>(tmem_base); break;
+      }
     }
   }
 }
@@ -757,6 +853,26 @@ static int tune_block_n(const dpig_ctx* ctx, int cout, int pix_tiles) {
   return bn;
 }
 
+// Two ways to let two adjacent pixel tiles share one weight tile (fewer operand bytes per FLOP; the single-tile
+// kernel is bound by the ~49 B/clk/SM operand feed, not by the tensor pipe):
+//   pair: a 2-CTA cluster runs cta_group::2 M=256 MMAs, each CTA stages half of the weight rows.  Measured on B200
+//         (profiles/r01_pair_vs_single.txt): wide channel blocks (N >= 192) gain 7-30 % and so do single-K-chunk
+//         layers; N = 128 blocks with a long K loop lose ~10 % to the cross-CTA handshake.
+//   dual: ONE CTA keeps two accumulators and stages both activation tiles next to one weight tile (block_n <= 128, so
+//         that 2 tiles x 2 TMEM buffers fit the 512 columns).
+// mode 0 never, 1 where it measured faster, 2 wherever legal (A/B runs, tests).
+static void choose_pair(const dpig_ctx* ctx, ConvUmmaParams& P) {
+  const int pix_tiles = P.tiles_w * P.tiles_h * P.tiles_n;
+  const int n_tiles = (P.cout + P.block_n - 1) / P.block_n;
+  const bool pair_legal = P.block_n >= 64 && P.block_n % 32 == 0 && pix_tiles >= 2 && ctx->num_sms >= 2;
+  const bool pair_wins = P.block_n >= 192 || P.kchunks == 1;
+  P.pair = (pair_legal && (ctx->pair_mode == 2 || (ctx->pair_mode == 1 && pair_wins))) ? 1 : 0;
+  P.b_bytes = (P.pair ? P.block_n / 2 : P.block_n) * 128;
+  const bool dual_legal = !P.pair && P.block_n <= 128 && pix_tiles >= 2;
+  const bool dual_wins = P.block_n >= 96 && P.kchunks >= 2 && ((pix_tiles + 1) / 2) * n_tiles >= ctx->num_sms;
+  P.dual = (dual_legal && (ctx->dual_mode == 2 || (ctx->dual_mode == 1 && dual_wins))) ? 1 : 0;
+}
+
 struct EpilogueGeom {
   int sh, sw, oh, ow, rep, out_H, out_W;
 };
@@ -816,24 +932,48 @@ static int fill_epilogue(dpig_ctx* ctx, ConvUmmaParams& P, const dpig_conv_epilo
 
 static int launch_conv(dpig_ctx* ctx, ConvUmmaParams& P, cudaStream_t stream) {
   P.planes = ctx->fast_mode ? 1 : P.planes;
-  const uint32_t stage_bytes = P.planes * (kABytes + P.b_bytes);
+  const int nsub = P.dual ? 2 : 1;
+  const uint32_t stage_bytes = P.planes * (nsub * kABytes + P.b_bytes);
   const uint32_t extra = 1024 + 256 + kEpiWarps * kEpiBytesPerWarp;  // alignment slack + barriers + epilogue staging
   int stages = (ctx->max_smem_optin - static_cast<int>(extra)) / static_cast<int>(stage_bytes);
   if (stages > 6) stages = 6;
   if (stages < 2) return set_error(ctx, DPIG_EUNSUPPORTED, "conv tile does not fit shared memory");
+  if (ctx->max_stages >= 2 && stages > ctx->max_stages) stages = ctx->max_stages;
   P.stages = stages;
   const size_t smem = static_cast<size_t>(stages) * stage_bytes + extra;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaFuncSetAttribute(conv_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->max_smem_optin);
+    cudaFuncSetAttribute(conv_umma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->max_smem_optin);
+    cudaFuncSetAttribute(conv_umma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->max_smem_optin);
     attr_set = true;
   }
-  const int total_tiles = P.tiles_w * P.tiles_h * P.tiles_n * ((P.cout + P.block_n - 1) / P.block_n);
+  const int pix_tiles = P.tiles_w * P.tiles_h * P.tiles_n;
+  const int n_tiles = (P.cout + P.block_n - 1) / P.block_n;
   P.tmem_cols = 64;
-  while (static_cast<int>(P.tmem_cols) < 2 * P.block_n) P.tmem_cols <<= 1;
-  dim3 grid(std::min(total_tiles, ctx->num_sms));
-  conv_umma_kernel<<<grid, kConvThreads, smem, stream>>>(P);
+  while (static_cast<int>(P.tmem_cols) < 2 * nsub * P.block_n) P.tmem_cols <<= 1;
   ctx->launches++;
+  if (P.pair) {
+    const int units = ((pix_tiles + 1) / 2) * n_tiles;
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(2 * std::min(units, ctx->num_sms / 2));
+    cfg.blockDim = dim3(kConvThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, conv_umma_kernel<true>, P);
+    if (e != cudaSuccess) return set_error(ctx, DPIG_ECUDA, "conv_umma_kernel<pair> launch: %s", cudaGetErrorString(e));
+    return check_launch(ctx, "conv_umma_kernel<pair>");
+  }
+  const int units = (P.dual ? (pix_tiles + 1) / 2 : pix_tiles) * n_tiles;
+  dim3 grid(std::min(units, ctx->num_sms));
+  conv_umma_kernel<false><<<grid, kConvThreads, smem, stream>>>(P);
   return check_launch(ctx, "conv_umma_kernel");
 }
 
@@ -872,7 +1012,7 @@ extern "C" int dpig_conv2d_fwd(dpig_ctx* ctx, const dpig_tensor* x, const void* 
   P.tiles_n = (x->n + b.bn - 1) / b.bn;
   P.a_tx_bytes = b.bw * b.bh * b.bn * 128;
   P.block_n = tune_block_n(ctx, cout, P.tiles_w * P.tiles_h * P.tiles_n);
-  P.b_bytes = P.block_n * 128;
+  choose_pair(ctx, P);
 
   int rc;
   P.num_taps = 0;
@@ -914,7 +1054,7 @@ extern "C" int dpig_conv2d_fwd(dpig_ctx* ctx, const dpig_tensor* x, const void* 
     uint64_t dims[3] = {static_cast<uint64_t>(cin_pad), static_cast<uint64_t>(cout),
                         static_cast<uint64_t>(kh * kw)};
     uint64_t strides[2] = {static_cast<uint64_t>(cin_pad) * 2, static_cast<uint64_t>(cin_pad) * cout * 2};
-    uint32_t box[3] = {64, static_cast<uint32_t>(P.block_n), 1};
+    uint32_t box[3] = {64, P.b_bytes / 128, 1};
     for (int pln = 0; pln < planes; ++pln)
       if ((rc = encode_map(ctx, &P.b_map[pln], pln ? wf_lo : wf_hi, 3, dims, strides, box))) return rc;
   }
@@ -961,7 +1101,7 @@ extern "C" int dpig_conv2d_bwd_data(dpig_ctx* ctx, const dpig_tensor* dy, const 
       P.tiles_n = (dy->n + b.bn - 1) / b.bn;
       P.a_tx_bytes = b.bw * b.bh * b.bn * 128;
       P.block_n = tune_block_n(ctx, cin, P.tiles_w * P.tiles_h * P.tiles_n);
-      P.b_bytes = P.block_n * 128;
+      choose_pair(ctx, P);
       P.num_taps = 0;
       for (int i = 0; i < kh; ++i)
         for (int j = 0; j < kw; ++j) {
@@ -988,7 +1128,7 @@ extern "C" int dpig_conv2d_bwd_data(dpig_ctx* ctx, const dpig_tensor* dy, const 
                             static_cast<uint64_t>(kh * kw)};
         uint64_t strides[2] = {static_cast<uint64_t>(cout_pad) * 2,
                                static_cast<uint64_t>(cout_pad) * cin * 2};
-        uint32_t box[3] = {64, static_cast<uint32_t>(P.block_n), 1};
+        uint32_t box[3] = {64, P.b_bytes / 128, 1};
         for (int pln = 0; pln < planes; ++pln)
           if ((rc = encode_map(ctx, &P.b_map[pln], pln ? wb_lo : wb_hi, 3, dims, strides, box))) return rc;
       }

@@ -46,10 +46,18 @@ def run(ctx, n, h, w, cin, cout, k=3, mode="full", fast=False, iters=20):
 
 
 if __name__ == "__main__":
-    ctx = dpig_b200.Context(0)
-    for (n, h, w, cin, cout) in [(64, 128, 64, 128, 128), (64, 128, 64, 256, 256), (64, 64, 32, 512, 512), (448, 48, 48, 128, 128)]:
-        for mode in ("full", "nores", "none"):
-            for fast in (False, True):
-                ms, tf = run(ctx, n, h, w, cin, cout, mode=mode, fast=fast)
-                print("%4dx%3dx%3d %4d->%4d  epilogue=%-5s %-5s  %7.3f ms  %7.1f TFLOP/s (algorithmic)" % (
-                    n, h, w, cin, cout, mode, "1pass" if fast else "3pass", ms, tf), flush=True)
+    shapes = [(64, 128, 64, 128, 128), (64, 128, 64, 256, 256), (64, 64, 32, 512, 512), (448, 48, 48, 128, 128),
+              (64, 32, 16, 640, 640)]
+    variants = [("single", (0, 0), "0"), ("single-2stage", (0, 0), "2"), ("pair", (2, 0), "0"), ("pair-2stage", (2, 0), "2"),
+                ("pair-3stage", (2, 0), "3")]
+    if len(sys.argv) > 1:
+        variants = [v for v in variants if v[0] in sys.argv[1:]]
+    for name, tiling, stages in variants:
+        os.environ["DPIG_CONV_STAGES"] = stages
+        ctx = dpig_b200.Context(0)
+        ctx.set_conv_tiling(*tiling)
+        for (n, h, w, cin, cout) in shapes:
+            for mode in ("full", "nores", "none"):
+                ms, tf = run(ctx, n, h, w, cin, cout, mode=mode, fast=False)
+                print("%-14s %4dx%3dx%3d %4d->%4d  epilogue=%-5s %7.3f ms  %7.1f TFLOP/s (algorithmic)" % (
+                    name, n, h, w, cin, cout, mode, ms, tf), flush=True)

@@ -145,12 +145,25 @@ CONV_FWD_CASES = [
     dict(n=1, h=128, w=64, cin=128, cout=128, k=3, stride=1, act="relu"),
     dict(n=2, h=16, w=8, cin=256, cout=3, k=3, stride=1, act="none", f32_out=True),
     dict(n=2, h=16, w=8, cin=370, cout=128, k=3, stride=1, act="relu", c_alloc_in=384),
+    # CTA-pair kernel: odd pixel-tile count (one all-padding tile), several units per cluster, N=192 halves
+    dict(n=3, h=16, w=8, cin=128, cout=128, k=3, stride=1, act="relu", residual=True),
+    dict(n=21, h=32, w=32, cin=64, cout=256, k=3, stride=1, act="relu", residual=True),
+    dict(n=7, h=16, w=8, cin=64, cout=384, k=3, stride=1, act="lrelu"),
 ]
 
 
+# plain single-tile kernel / 2-CTA cluster kernel / two-tiles-per-CTA kernel, each forced wherever the shape allows
+TILINGS = [(0, 0), (2, 0), (0, 2)]
+
+
+@pytest.mark.parametrize("tiling", TILINGS)
 @pytest.mark.parametrize("case", CONV_FWD_CASES)
-def test_conv2d_fwd(case):
-    info = run_conv_fwd(**case)
+def test_conv2d_fwd(case, tiling):
+    ctx().set_conv_tiling(*tiling)
+    try:
+        info = run_conv_fwd(**case)
+    finally:
+        ctx().set_conv_tiling(1, 1)
     assert info["err"] < 5e-5, info  # 3-pass split-bf16 vs float64 on identical (split-rounded) inputs
     assert info["mask_mismatch"] == 0, info
     if "err_f32" in info:
@@ -210,12 +223,19 @@ CONV_BWD_DATA_CASES = [
     dict(n=2, h=8, w=4, cin=192, cout=64, k=1, stride=1),
     dict(n=3, h=12, w=12, cin=256, cout=384, k=3, stride=2, masked=True),
     dict(n=2, h=16, w=8, cin=256, cout=3, k=3, stride=1),
+    dict(n=21, h=32, w=32, cin=256, cout=64, k=3, stride=1, addend=True, masked=True),
+    dict(n=3, h=16, w=8, cin=128, cout=128, k=3, stride=2, addend=True, masked=True),
 ]
 
 
+@pytest.mark.parametrize("tiling", TILINGS)
 @pytest.mark.parametrize("case", CONV_BWD_DATA_CASES)
-def test_conv2d_bwd_data(case):
-    info = run_conv_bwd_data(**case)
+def test_conv2d_bwd_data(case, tiling):
+    ctx().set_conv_tiling(*tiling)
+    try:
+        info = run_conv_bwd_data(**case)
+    finally:
+        ctx().set_conv_tiling(1, 1)
     assert info["err"] < 5e-5, info
     if "err_masked" in info:
         assert info["err_masked"] < 5e-5, info
