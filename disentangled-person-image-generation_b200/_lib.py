@@ -46,7 +46,7 @@ _D = C.c_double
 # name -> argtypes after the leading ctx pointer (all return int)
 _SIGNATURES = {
     "dpig_ctx_set_fast_mode": [C.c_int],
-    "dpig_ctx_set_conv_tiling": [C.c_int, C.c_int],
+    "dpig_ctx_set_pair_mode": [C.c_int],
     "dpig_weight_pack": [_P, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P],
     "dpig_conv2d_fwd": [_T, _P, _P, _I, _I, _I, _I, C.POINTER(ConvEpilogue), _P],
     "dpig_conv2d_bwd_data": [_T, _P, _P, _I, _I, _I, _I, _I, _I, C.POINTER(ConvEpilogue), _P],
@@ -152,9 +152,9 @@ class Context:
         """fast=True: single bf16 pass on the hi planes (NOT the parity mode)."""
         self.call("ctx_set_fast_mode", int(bool(fast)))
 
-    def set_conv_tiling(self, pair_mode=1, dual_mode=1):
-        """pair_mode: 2-CTA cluster kernel, dual_mode: two pixel tiles per CTA; 0 never, 1 where faster, 2 always."""
-        self.call("ctx_set_conv_tiling", int(pair_mode), int(dual_mode))
+    def set_pair_mode(self, mode):
+        """2-CTA cluster conv kernel: 0 never, 1 where it measured faster (default), 2 wherever the shape allows."""
+        self.call("ctx_set_pair_mode", int(mode))
 
     def launch_count(self):
         return int(self.lib.dpig_launch_count(self.handle))

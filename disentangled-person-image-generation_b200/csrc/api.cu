@@ -54,7 +54,6 @@ extern "C" int dpig_ctx_create(int device, dpig_ctx** out) {
   }
   ctx->encode_tiled = reinterpret_cast<decltype(ctx->encode_tiled)>(fn);
   if (const char* e = getenv("DPIG_CONV_PAIR")) ctx->pair_mode = atoi(e);  // A/B switches for the conv tilings
-  if (const char* e = getenv("DPIG_CONV_DUAL")) ctx->dual_mode = atoi(e);
   if (const char* e = getenv("DPIG_CONV_STAGES")) ctx->max_stages = atoi(e);
   *out = ctx;
   return DPIG_OK;
@@ -72,12 +71,10 @@ extern "C" int dpig_ctx_set_fast_mode(dpig_ctx* ctx, int fast) {
   return DPIG_OK;
 }
 
-extern "C" int dpig_ctx_set_conv_tiling(dpig_ctx* ctx, int pair_mode, int dual_mode) {
+extern "C" int dpig_ctx_set_pair_mode(dpig_ctx* ctx, int mode) {
   DPIG_CHECK_CTX(ctx);
-  if (pair_mode < 0 || pair_mode > 2 || dual_mode < 0 || dual_mode > 2)
-    return set_error(ctx, DPIG_EINVAL, "conv tiling modes must be 0, 1 or 2");
-  ctx->pair_mode = pair_mode;
-  ctx->dual_mode = dual_mode;
+  if (mode < 0 || mode > 2) return set_error(ctx, DPIG_EINVAL, "pair mode must be 0, 1 or 2");
+  ctx->pair_mode = mode;
   return DPIG_OK;
 }
 

@@ -48,7 +48,6 @@ struct ConvUmmaParams {
   int Wo, Ho, No;
   int block_n, cout, stages;
   int pair;  // 1: launched as 2-CTA clusters running cta_group::2 MMAs (b_bytes = this CTA's half of the B rows)
-  int dual;  // 1: one CTA computes two adjacent pixel tiles per weight tile (two accumulators; block_n <= 128)
   uint32_t a_tx_bytes, b_bytes, tmem_cols;
   const float* bias;
   const float* class_bias;  // [N][9][cout]: per-image bias indexed by the pixel's border class (stem shortcut)
@@ -339,11 +338,8 @@ __global__ void __launch_bounds__(kConvThreads, 1)
 conv_umma_kernel(const __grid_constant__ ConvUmmaParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = align1024(smem_raw);
-  // dual: the stage holds the activation tiles of TWO adjacent pixel tiles next to one weight tile
-  // ([A0 hi, A0 lo, A1 hi, A1 lo, B hi, B lo]); a third fewer operand bytes per FLOP for narrow channel blocks.
-  const int nsub = (!kPair && p.dual) ? 2 : 1;
-  const uint32_t b_off = nsub * p.planes * kABytes;
-  const uint32_t stage_bytes = p.planes * (nsub * kABytes + p.b_bytes);
+  const uint32_t b_off = p.planes * kABytes;
+  const uint32_t stage_bytes = p.planes * (kABytes + p.b_bytes);
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + p.stages * stage_bytes);
   uint64_t* empty = full + p.stages;
   uint64_t* tmem_full = empty + p.stages;   // [2]
@@ -359,7 +355,7 @@ conv_umma_kernel(const __grid_constant__ ConvUmmaParams p) {
   const uint32_t rank = kPair ? ptx::cluster_ctarank() : 0u;
   const int unit0 = kPair ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
   const int unit_step = kPair ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
-  const int unit_pix_tiles = (kPair || nsub == 2) ? (pix_tiles + 1) / 2 : pix_tiles;
+  const int unit_pix_tiles = kPair ? (pix_tiles + 1) / 2 : pix_tiles;
   const int total_tiles = unit_pix_tiles * n_tiles;
 
   if (threadIdx.x == 0) {
@@ -407,15 +403,12 @@ conv_umma_kernel(const __grid_constant__ ConvUmmaParams p) {
       const int b_row0 = kPair ? static_cast<int>(rank) * (p.block_n >> 1) : 0;
       for (int tile = unit0; tile < total_tiles; tile += unit_step) {
         const int upt = tile % unit_pix_tiles, nt = tile / unit_pix_tiles;
-        // pt == pix_tiles for the odd tail of a pair / dual unit: an all-out-of-bounds (zero-filled) tile
-        const int pt = kPair ? 2 * upt + static_cast<int>(rank) : (nsub == 2 ? 2 * upt : upt);
+        // pt == pix_tiles for the odd tail of a pair: an all-out-of-bounds (zero-filled) tile
+        const int pt = kPair ? 2 * upt + static_cast<int>(rank) : upt;
         const int tw = pt % p.tiles_w;
         const int th = (pt / p.tiles_w) % p.tiles_h;
         const int tn = pt / (p.tiles_w * p.tiles_h);
         const int w0 = tw * p.BW, h0 = th * p.BH, n0 = tn * p.BN;
-        const int pt1 = pt + 1;  // second pixel tile of a dual unit
-        const int w1 = (pt1 % p.tiles_w) * p.BW, h1 = ((pt1 / p.tiles_w) % p.tiles_h) * p.BH;
-        const int n1 = (pt1 / (p.tiles_w * p.tiles_h)) * p.BN;
         for (int t = 0; t < p.num_taps; ++t) {
           const ConvTap tap = p.taps[t];
           for (int kc = 0; kc < p.kchunks; ++kc) {
@@ -431,14 +424,10 @@ conv_umma_kernel(const __grid_constant__ ConvUmmaParams p) {
                 ptx::tma_load_3d_pair(st + b_off + pl * p.b_bytes, &p.b_map[pl], lead_full, kc * 64,
                                       nt * p.block_n + b_row0, tap.wtap);
             } else {
-            ptx::mbar_expect_tx(&full[s], p.planes * (nsub * p.a_tx_bytes + p.b_bytes));
+            ptx::mbar_expect_tx(&full[s], p.planes * (p.a_tx_bytes + p.b_bytes));
             for (int pl = 0; pl < p.planes; ++pl)
               ptx::tma_load_4d(st + pl * kABytes, &p.a_map[tap.src][pl], &full[s], kc * 64, w0 + tap.dw,
                                h0 + tap.dh, n0);
-            if (nsub == 2)
-              for (int pl = 0; pl < p.planes; ++pl)
-                ptx::tma_load_4d(st + (p.planes + pl) * kABytes, &p.a_map[tap.src][pl], &full[s], kc * 64,
-                                 w1 + tap.dw, h1 + tap.dh, n1);
             for (int pl = 0; pl < p.planes; ++pl)
               ptx::tma_load_3d(st + b_off + pl * p.b_bytes, &p.b_map[pl], &full[s], kc * 64, nt * p.block_n,
                                tap.wtap);
@@ -461,7 +450,7 @@ conv_umma_kernel(const __grid_constant__ ConvUmmaParams p) {
         const int acc = j & 1;
         ptx::mbar_wait(&tmem_empty[acc], ((j >> 1) & 1) ^ 1);
         ptx::tc_fence_after();
-        const uint32_t tmem_acc = tmem_base + acc * nsub * p.block_n;
+        const uint32_t tmem_acc = tmem_base + acc * p.block_n;
         for (int step = 0; step < steps_per_tile; ++step) {
           ptx::mbar_wait(&full[s], ph);
           ptx::tc_fence_after();
@@ -488,17 +477,6 @@ conv_umma_kernel(const __grid_constant__ ConvUmmaParams p) {
                 const uint64_t db_lo = ptx::make_desc_sw128(b_lo + k * 32, 16, 1024);
                 ptx::umma_bf16(tmem_acc, da_hi, db_lo, idesc, 1u);
                 ptx::umma_bf16(tmem_acc, da_lo, db_hi, idesc, 1u);
-              }
-              if (nsub == 2) {  // second pixel tile: same weight descriptors, next accumulator
-                const uint32_t a1 = a_hi + p.planes * kABytes;
-                const uint64_t da1_hi = ptx::make_desc_sw128(a1 + k * 32, 16, 1024);
-                ptx::umma_bf16(tmem_acc + p.block_n, da1_hi, db_hi, idesc, (step | k) ? 1u : 0u);
-                if (p.planes == 2) {
-                  const uint64_t da1_lo = ptx::make_desc_sw128(a1 + kABytes + k * 32, 16, 1024);
-                  const uint64_t db_lo = ptx::make_desc_sw128(b_lo + k * 32, 16, 1024);
-                  ptx::umma_bf16(tmem_acc + p.block_n, da1_hi, db_lo, idesc, 1u);
-                  ptx::umma_bf16(tmem_acc + p.block_n, da1_lo, db_hi, idesc, 1u);
-                }
               }
             }
           }
@@ -532,45 +510,43 @@ conv_umma_kernel(const __grid_constant__ ConvUmmaParams p) {
     for (int tile = unit0; tile < total_tiles; tile += unit_step, ++j) {
       const int acc = j & 1;
       const int upt = tile % unit_pix_tiles, nt = tile / unit_pix_tiles;
+      const int pt = kPair ? 2 * upt + static_cast<int>(rank) : upt;
+      const int tw = pt % p.tiles_w;
+      const int th = (pt / p.tiles_w) % p.tiles_h;
+      const int tn = pt / (p.tiles_w * p.tiles_h);
+      const int w = tw * p.BW + wl, h = th * p.BH + hl, n = tn * p.BN + nl;
+      const bool valid = (nl < p.BN) && (w < p.Wo) && (h < p.Ho) && (n < p.No);
+      const int lpix = (n * p.Ho + h) * p.Wo + w;  // logical pixel (< 2^31 for every supported shape)
+      const int py = h * p.sh + p.oh, px = w * p.sw + p.ow;
+      const int ppix = (n * p.out_H + py) * p.out_W + px;
+      const float* cbias = nullptr;
+      if (p.class_bias && valid) {
+        const int ch = h == 0 ? 0 : (h == p.Ho - 1 ? 2 : 1), cw = w == 0 ? 0 : (w == p.Wo - 1 ? 2 : 1);
+        cbias = p.class_bias + (static_cast<long long>(n) * 9 + ch * 3 + cw) * p.cout;
+      }
+
       ptx::mbar_wait(&tmem_full[acc], (j >> 1) & 1);
       ptx::tc_fence_after();
-      bool released = false;
-      for (int sub = 0; sub < nsub; ++sub) {
-        const int pt = kPair ? 2 * upt + static_cast<int>(rank) : (nsub == 2 ? 2 * upt + sub : upt);
-        const int tw = pt % p.tiles_w;
-        const int th = (pt / p.tiles_w) % p.tiles_h;
-        const int tn = pt / (p.tiles_w * p.tiles_h);
-        const int w = tw * p.BW + wl, h = th * p.BH + hl, n = tn * p.BN + nl;
-        const bool valid = (nl < p.BN) && (w < p.Wo) && (h < p.Ho) && (n < p.No);
-        const int lpix = (n * p.Ho + h) * p.Wo + w;  // logical pixel (< 2^31 for every supported shape)
-        const int py = h * p.sh + p.oh, px = w * p.sw + p.ow;
-        const int ppix = (n * p.out_H + py) * p.out_W + px;
-        const float* cbias = nullptr;
-        if (p.class_bias && valid) {
-          const int ch = h == 0 ? 0 : (h == p.Ho - 1 ? 2 : 1), cw = w == 0 ? 0 : (w == p.Wo - 1 ? 2 : 1);
-          cbias = p.class_bias + (static_cast<long long>(n) * 9 + ch * 3 + cw) * p.cout;
-        }
-        const uint32_t tmem_acc =
-            tmem_base + (acc * nsub + sub) * p.block_n + (static_cast<uint32_t>(lg * 32) << 16);
+      const uint32_t tmem_acc = tmem_base + acc * p.block_n + (static_cast<uint32_t>(lg * 32) << 16);
 
-        const int nchunks = p.block_n >> 5;
-        for (int ci = cpar; ci < nchunks; ci += kEpiWarps / 4) {
-          const int c0 = ci << 5;
-          uint32_t v[32];
-          ptx::tmem_ld32(tmem_acc + c0, v);
-          ptx::tmem_ld_wait();
-          if (sub == nsub - 1 && ci + kEpiWarps / 4 >= nchunks) {
-            // this warp's last TMEM read of the unit: hand the accumulator stage back to the MMA warp
-            ptx::tc_fence_before();
-            __syncwarp();
-            if (lane == 0) {
-              if (kPair) ptx::mbar_arrive_cluster(lead_tmem_empty[acc]);
-              else ptx::mbar_arrive(&tmem_empty[acc]);
-            }
-            released = true;
+      const int nchunks = p.block_n >> 5;
+      bool released = false;
+      for (int ci = cpar; ci < nchunks; ci += kEpiWarps / 4) {
+        const int c0 = ci << 5;
+        uint32_t v[32];
+        ptx::tmem_ld32(tmem_acc + c0, v);
+        ptx::tmem_ld_wait();
+        if (ci + kEpiWarps / 4 >= nchunks) {
+          // this warp's last TMEM read of the tile: hand the accumulator stage back to the MMA warp
+          ptx::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            if (kPair) ptx::mbar_arrive_cluster(lead_tmem_empty[acc]);
+            else ptx::mbar_arrive(&tmem_empty[acc]);
           }
-          epi_chunk(p, stage, v, nt * p.block_n + c0, valid, lpix, ppix, cbias, lane);
+          released = true;
         }
+        epi_chunk(p, stage, v, nt * p.block_n + c0, valid, lpix, ppix, cbias, lane);
       }
       if (!released) {  // fewer chunks than epilogue warps per lane group (block_n == 32)
         ptx::tc_fence_before();
@@ -853,24 +829,20 @@ static int tune_block_n(const dpig_ctx* ctx, int cout, int pix_tiles) {
   return bn;
 }
 
-// Two ways to let two adjacent pixel tiles share one weight tile (fewer operand bytes per FLOP; the single-tile
-// kernel is bound by the ~49 B/clk/SM operand feed, not by the tensor pipe):
-//   pair: a 2-CTA cluster runs cta_group::2 M=256 MMAs, each CTA stages half of the weight rows.  Measured on B200
-//         (profiles/r01_pair_vs_single.txt): wide channel blocks (N >= 192) gain 7-30 % and so do single-K-chunk
-//         layers; N = 128 blocks with a long K loop lose ~10 % to the cross-CTA handshake.
-//   dual: ONE CTA keeps two accumulators and stages both activation tiles next to one weight tile (block_n <= 128, so
-//         that 2 tiles x 2 TMEM buffers fit the 512 columns).
+// CTA pairs: a 2-CTA cluster runs cta_group::2 M=256 MMAs over two adjacent pixel tiles, each CTA staging half of the
+// weight rows (fewer operand bytes per FLOP; the single-CTA kernel is bound by the ~49 B/clk/SM operand feed, not by
+// the tensor pipe).  Measured on B200 (profiles/r01_pair_vs_single.txt): channel blocks wider than 128 gain 7-30 %
+// and so do single-K-chunk layers; N = 128 blocks with a long K loop lose 4-10 % to the cross-CTA handshake.
+// A single-CTA variant with two accumulators per CTA ("dual", two activation tiles next to one weight tile) was also
+// built and measured: +11 % on the bare main loop at N = 128 but slower with the real epilogue, and its extra
+// registers cost the plain kernel 6-20 %; it was removed again (measurement history).
 // mode 0 never, 1 where it measured faster, 2 wherever legal (A/B runs, tests).
 static void choose_pair(const dpig_ctx* ctx, ConvUmmaParams& P) {
   const int pix_tiles = P.tiles_w * P.tiles_h * P.tiles_n;
-  const int n_tiles = (P.cout + P.block_n - 1) / P.block_n;
-  const bool pair_legal = P.block_n >= 64 && P.block_n % 32 == 0 && pix_tiles >= 2 && ctx->num_sms >= 2;
-  const bool pair_wins = P.block_n >= 192 || P.kchunks == 1;
-  P.pair = (pair_legal && (ctx->pair_mode == 2 || (ctx->pair_mode == 1 && pair_wins))) ? 1 : 0;
+  const bool legal = P.block_n >= 64 && P.block_n % 32 == 0 && pix_tiles >= 2 && ctx->num_sms >= 2;
+  const bool wins = P.block_n > 128 || P.kchunks == 1;
+  P.pair = (legal && (ctx->pair_mode == 2 || (ctx->pair_mode == 1 && wins))) ? 1 : 0;
   P.b_bytes = (P.pair ? P.block_n / 2 : P.block_n) * 128;
-  const bool dual_legal = !P.pair && P.block_n <= 128 && pix_tiles >= 2;
-  const bool dual_wins = P.block_n >= 96 && P.kchunks >= 2 && ((pix_tiles + 1) / 2) * n_tiles >= ctx->num_sms;
-  P.dual = (dual_legal && (ctx->dual_mode == 2 || (ctx->dual_mode == 1 && dual_wins))) ? 1 : 0;
 }
 
 struct EpilogueGeom {
@@ -932,8 +904,7 @@ static int fill_epilogue(dpig_ctx* ctx, ConvUmmaParams& P, const dpig_conv_epilo
 
 static int launch_conv(dpig_ctx* ctx, ConvUmmaParams& P, cudaStream_t stream) {
   P.planes = ctx->fast_mode ? 1 : P.planes;
-  const int nsub = P.dual ? 2 : 1;
-  const uint32_t stage_bytes = P.planes * (nsub * kABytes + P.b_bytes);
+  const uint32_t stage_bytes = P.planes * (kABytes + P.b_bytes);
   const uint32_t extra = 1024 + 256 + kEpiWarps * kEpiBytesPerWarp;  // alignment slack + barriers + epilogue staging
   int stages = (ctx->max_smem_optin - static_cast<int>(extra)) / static_cast<int>(stage_bytes);
   if (stages > 6) stages = 6;
@@ -950,7 +921,7 @@ static int launch_conv(dpig_ctx* ctx, ConvUmmaParams& P, cudaStream_t stream) {
   const int pix_tiles = P.tiles_w * P.tiles_h * P.tiles_n;
   const int n_tiles = (P.cout + P.block_n - 1) / P.block_n;
   P.tmem_cols = 64;
-  while (static_cast<int>(P.tmem_cols) < 2 * nsub * P.block_n) P.tmem_cols <<= 1;
+  while (static_cast<int>(P.tmem_cols) < 2 * P.block_n) P.tmem_cols <<= 1;
   ctx->launches++;
   if (P.pair) {
     const int units = ((pix_tiles + 1) / 2) * n_tiles;
@@ -971,8 +942,7 @@ static int launch_conv(dpig_ctx* ctx, ConvUmmaParams& P, cudaStream_t stream) {
     if (e != cudaSuccess) return set_error(ctx, DPIG_ECUDA, "conv_umma_kernel<pair> launch: %s", cudaGetErrorString(e));
     return check_launch(ctx, "conv_umma_kernel<pair>");
   }
-  const int units = (P.dual ? (pix_tiles + 1) / 2 : pix_tiles) * n_tiles;
-  dim3 grid(std::min(units, ctx->num_sms));
+  dim3 grid(std::min(pix_tiles * n_tiles, ctx->num_sms));
   conv_umma_kernel<false><<<grid, kConvThreads, smem, stream>>>(P);
   return check_launch(ctx, "conv_umma_kernel");
 }

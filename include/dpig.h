@@ -91,12 +91,11 @@ void dpig_ctx_destroy(dpig_ctx* ctx);
 const char* dpig_last_error(const dpig_ctx* ctx);
 /* fast=1: single bf16 pass on the hi planes only (NOT the parity mode; ~1e-2 relative). */
 int dpig_ctx_set_fast_mode(dpig_ctx* ctx, int fast);
-/* How the conv kernel lets two adjacent pixel tiles share one weight tile:
- *   pair_mode: 2-CTA clusters running tcgen05 cta_group::2 (M=256) MMAs, each CTA staging half of the weight rows;
- *   dual_mode: one CTA with two accumulators and both activation tiles staged next to one weight tile.
- * Each: 0 never, 1 where it measured faster (default), 2 wherever the shape allows.  Results are identical in every
- * mode (same products, same fp32 accumulation order per output element). */
-int dpig_ctx_set_conv_tiling(dpig_ctx* ctx, int pair_mode, int dual_mode);
+/* conv kernels as 2-CTA clusters (tcgen05 cta_group::2, M=256 MMAs over two adjacent pixel tiles, each CTA staging
+ * half of the weight rows): 0 never, 1 where it measured faster (default; wide channel blocks and single-K-chunk
+ * layers), 2 wherever the shape allows.  Results are identical in every mode (same products, same fp32 accumulation
+ * order per output element). */
+int dpig_ctx_set_pair_mode(dpig_ctx* ctx, int mode);
 /* number of kernels this ctx has launched so far (bench.py's gpu_launches). */
 unsigned long long dpig_launch_count(const dpig_ctx* ctx);
 const char* dpig_version(void);

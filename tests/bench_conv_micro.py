@@ -48,14 +48,14 @@ def run(ctx, n, h, w, cin, cout, k=3, mode="full", fast=False, iters=20):
 if __name__ == "__main__":
     shapes = [(64, 128, 64, 128, 128), (64, 128, 64, 256, 256), (64, 64, 32, 512, 512), (448, 48, 48, 128, 128),
               (64, 32, 16, 640, 640)]
-    variants = [("single", (0, 0), "0"), ("single-2stage", (0, 0), "2"), ("pair", (2, 0), "0"), ("pair-2stage", (2, 0), "2"),
-                ("pair-3stage", (2, 0), "3")]
+    variants = [("single", 0, "0"), ("single-2stage", 0, "2"), ("pair", 2, "0"), ("pair-2stage", 2, "2"),
+                ("pair-3stage", 2, "3")]
     if len(sys.argv) > 1:
         variants = [v for v in variants if v[0] in sys.argv[1:]]
     for name, tiling, stages in variants:
         os.environ["DPIG_CONV_STAGES"] = stages
         ctx = dpig_b200.Context(0)
-        ctx.set_conv_tiling(*tiling)
+        ctx.set_pair_mode(tiling)
         for (n, h, w, cin, cout) in shapes:
             for mode in ("full", "nores", "none"):
                 ms, tf = run(ctx, n, h, w, cin, cout, mode=mode, fast=False)
