@@ -48,6 +48,8 @@ struct ConvUmmaParams {
   int Wo, Ho, No;
   int block_n, cout, stages;
   int pair;  // 1: launched as 2-CTA clusters running cta_group::2 MMAs (b_bytes = this CTA's half of the B rows)
+  // hi and lo planes fetched by ONE TMA instruction (map slot [..][0] then has a trailing "plane" dimension)
+  int a_merged, b_merged;
   uint32_t a_tx_bytes, b_bytes, tmem_cols;
   const float* bias;
   const float* class_bias;  // [N][9][cout]: per-image bias indexed by the pixel's border class (stem shortcut)
@@ -417,20 +419,32 @@ conv_umma_kernel(const __grid_constant__ ConvUmmaParams p) {
             if (kPair) {
               const uint32_t lead_full = ptx::mapa_u32(ptx::smem_u32(&full[s]), 0);
               if (rank == 0) ptx::mbar_expect_tx(&full[s], 2 * p.planes * (p.a_tx_bytes + p.b_bytes));
-              for (int pl = 0; pl < p.planes; ++pl)
-                ptx::tma_load_4d_pair(st + pl * kABytes, &p.a_map[tap.src][pl], lead_full, kc * 64, w0 + tap.dw,
-                                      h0 + tap.dh, n0);
-              for (int pl = 0; pl < p.planes; ++pl)
-                ptx::tma_load_3d_pair(st + b_off + pl * p.b_bytes, &p.b_map[pl], lead_full, kc * 64,
-                                      nt * p.block_n + b_row0, tap.wtap);
+              if (p.a_merged)
+                ptx::tma_load_5d_pair(st, &p.a_map[tap.src][0], lead_full, kc * 64, w0 + tap.dw, h0 + tap.dh, n0, 0);
+              else
+                for (int pl = 0; pl < p.planes; ++pl)
+                  ptx::tma_load_4d_pair(st + pl * kABytes, &p.a_map[tap.src][pl], lead_full, kc * 64, w0 + tap.dw,
+                                        h0 + tap.dh, n0);
+              if (p.b_merged)
+                ptx::tma_load_4d_pair(st + b_off, &p.b_map[0], lead_full, kc * 64, nt * p.block_n + b_row0, tap.wtap, 0);
+              else
+                for (int pl = 0; pl < p.planes; ++pl)
+                  ptx::tma_load_3d_pair(st + b_off + pl * p.b_bytes, &p.b_map[pl], lead_full, kc * 64,
+                                        nt * p.block_n + b_row0, tap.wtap);
             } else {
             ptx::mbar_expect_tx(&full[s], p.planes * (p.a_tx_bytes + p.b_bytes));
-            for (int pl = 0; pl < p.planes; ++pl)
-              ptx::tma_load_4d(st + pl * kABytes, &p.a_map[tap.src][pl], &full[s], kc * 64, w0 + tap.dw,
-                               h0 + tap.dh, n0);
-            for (int pl = 0; pl < p.planes; ++pl)
-              ptx::tma_load_3d(st + b_off + pl * p.b_bytes, &p.b_map[pl], &full[s], kc * 64, nt * p.block_n,
-                               tap.wtap);
+            if (p.a_merged)
+              ptx::tma_load_5d(st, &p.a_map[tap.src][0], &full[s], kc * 64, w0 + tap.dw, h0 + tap.dh, n0, 0);
+            else
+              for (int pl = 0; pl < p.planes; ++pl)
+                ptx::tma_load_4d(st + pl * kABytes, &p.a_map[tap.src][pl], &full[s], kc * 64, w0 + tap.dw,
+                                 h0 + tap.dh, n0);
+            if (p.b_merged)
+              ptx::tma_load_4d(st + b_off, &p.b_map[0], &full[s], kc * 64, nt * p.block_n, tap.wtap, 0);
+            else
+              for (int pl = 0; pl < p.planes; ++pl)
+                ptx::tma_load_3d(st + b_off + pl * p.b_bytes, &p.b_map[pl], &full[s], kc * 64, nt * p.block_n,
+                                 tap.wtap);
             }
             if (++s == p.stages) {
               s = 0;
@@ -756,8 +770,9 @@ static int encode_map(dpig_ctx* ctx, CUtensorMap* map, const void* base, int ran
 
 // Activation view -> 4-D map over (C, W', H', N) where W'/H' are either the full grid or one
 // parity class of it (step = 2, offset = parity).
+// plane_stride_bytes > 0 appends a 5th "plane" dimension of extent 2 (hi, lo) fetched by the same box.
 static int act_map(dpig_ctx* ctx, CUtensorMap* map, const void* plane, const dpig_tensor* t,
-                   int step, int py, int px, int box_w, int box_h, int box_n) {
+                   int step, int py, int px, int box_w, int box_h, int box_n, long long plane_stride_bytes = 0) {
   const uint64_t ps = static_cast<uint64_t>(t->pix_stride);
   const int W2 = (t->w - px + step - 1) / step;
   const int H2 = (t->h - py + step - 1) / step;
@@ -767,12 +782,25 @@ static int act_map(dpig_ctx* ctx, CUtensorMap* map, const void* plane, const dpi
   uint32_t box[4] = {64, static_cast<uint32_t>(box_w), static_cast<uint32_t>(box_h),
                      static_cast<uint32_t>(box_n)};
   const char* base = static_cast<const char*>(plane) + (static_cast<uint64_t>(py) * t->w + px) * ps * 2;
+  if (plane_stride_bytes > 0) {
+    uint64_t dims5[5] = {dims[0], dims[1], dims[2], dims[3], 2};
+    uint64_t strides4[4] = {strides[0], strides[1], strides[2], static_cast<uint64_t>(plane_stride_bytes)};
+    uint32_t box5[5] = {box[0], box[1], box[2], box[3], 2};
+    return encode_map(ctx, map, base, 5, dims5, strides4, box5);
+  }
   return encode_map(ctx, map, base, 4, dims, strides, box);
 }
 
 struct Box {
   int bw, bh, bn;
 };
+
+// Byte distance lo - hi when both planes can be addressed by one tensor map (same allocation, 16 B granular), else 0.
+static long long plane_stride(const void* hi, const void* lo) {
+  if (!hi || !lo) return 0;
+  const long long d = static_cast<const char*>(lo) - static_cast<const char*>(hi);
+  return (d > 0 && d % 16 == 0 && d < (1ll << 40)) ? d : 0;
+}
 // Pick the pixel box (<= max_rows rows) with the best tile utilisation.
 static Box choose_box(int W, int H, int N, int max_rows, bool pow2_exact) {
   Box best{1, 1, 1};
@@ -1005,16 +1033,22 @@ extern "C" int dpig_conv2d_fwd(dpig_ctx* ctx, const dpig_tensor* x, const void* 
       used[t.src] = true;
       P.taps[P.num_taps++] = t;
     }
+  // one TMA instruction per operand and stage when hi / lo sit in one allocation and the box fills the 16 KB slot
+  const long long a_ps = (planes == 2 && ctx->merge_planes && P.a_tx_bytes == kABytes) ? plane_stride(x->hi, x->lo) : 0;
+  const long long b_ps = (planes == 2 && ctx->merge_planes) ? plane_stride(wf_hi, wf_lo) : 0;
+  P.a_merged = a_ps > 0;
+  P.b_merged = b_ps > 0;
   int first_used = -1;
   for (int s = 0; s < 4; ++s) {
     if (!used[s]) continue;
     if (first_used < 0) first_used = s;
-    for (int pln = 0; pln < planes; ++pln) {
+    for (int pln = 0; pln < (P.a_merged ? 1 : planes); ++pln) {
       const void* plane = pln ? x->lo : x->hi;
       if ((rc = act_map(ctx, &P.a_map[s][pln], plane, x, stride, stride == 1 ? 0 : s / 2,
-                        stride == 1 ? 0 : s % 2, b.bw, b.bh, b.bn)))
+                        stride == 1 ? 0 : s % 2, b.bw, b.bh, b.bn, a_ps)))
         return rc;
     }
+    if (P.a_merged) P.a_map[s][1] = P.a_map[s][0];  // slot [1] is only prefetched
   }
   for (int s = 0; s < 4; ++s)  // unused slots alias a valid map (they are only prefetched)
     if (!used[s])
@@ -1025,8 +1059,16 @@ extern "C" int dpig_conv2d_fwd(dpig_ctx* ctx, const dpig_tensor* x, const void* 
                         static_cast<uint64_t>(kh * kw)};
     uint64_t strides[2] = {static_cast<uint64_t>(cin_pad) * 2, static_cast<uint64_t>(cin_pad) * cout * 2};
     uint32_t box[3] = {64, P.b_bytes / 128, 1};
-    for (int pln = 0; pln < planes; ++pln)
-      if ((rc = encode_map(ctx, &P.b_map[pln], pln ? wf_lo : wf_hi, 3, dims, strides, box))) return rc;
+    if (P.b_merged) {
+      uint64_t dims4[4] = {dims[0], dims[1], dims[2], 2};
+      uint64_t strides3[3] = {strides[0], strides[1], static_cast<uint64_t>(b_ps)};
+      uint32_t box4[4] = {box[0], box[1], 1, 2};
+      if ((rc = encode_map(ctx, &P.b_map[0], wf_hi, 4, dims4, strides3, box4))) return rc;
+      P.b_map[1] = P.b_map[0];
+    } else {
+      for (int pln = 0; pln < planes; ++pln)
+        if ((rc = encode_map(ctx, &P.b_map[pln], pln ? wf_lo : wf_hi, 3, dims, strides, box))) return rc;
+    }
   }
   EpilogueGeom g{up, up, 0, 0, up, OH * up, OW * up};
   if ((rc = fill_epilogue(ctx, P, ep, g, x->n, cout))) return rc;
@@ -1087,9 +1129,18 @@ extern "C" int dpig_conv2d_bwd_data(dpig_ctx* ctx, const dpig_tensor* dy, const 
         }
       if (P.num_taps == 0)
         return set_error(ctx, DPIG_EUNSUPPORTED, "conv2d_bwd_data: parity class without taps");
+      const long long a_ps =
+          (planes == 2 && ctx->merge_planes && P.a_tx_bytes == kABytes) ? plane_stride(dy->hi, dy->lo) : 0;
+      const long long b_ps = (planes == 2 && ctx->merge_planes) ? plane_stride(wb_hi, wb_lo) : 0;
+      P.a_merged = a_ps > 0;
+      P.b_merged = b_ps > 0;
       for (int pln = 0; pln < planes; ++pln) {
-        if ((rc = act_map(ctx, &P.a_map[0][pln], pln ? dy->lo : dy->hi, dy, 1, 0, 0, b.bw, b.bh, b.bn)))
-          return rc;
+        if (pln == 0 || !P.a_merged) {
+          if ((rc = act_map(ctx, &P.a_map[0][pln], pln ? dy->lo : dy->hi, dy, 1, 0, 0, b.bw, b.bh, b.bn, a_ps)))
+            return rc;
+        } else {
+          P.a_map[0][1] = P.a_map[0][0];
+        }
         for (int s = 1; s < 4; ++s) P.a_map[s][pln] = P.a_map[0][pln];
       }
       {
@@ -1099,8 +1150,16 @@ extern "C" int dpig_conv2d_bwd_data(dpig_ctx* ctx, const dpig_tensor* dy, const 
         uint64_t strides[2] = {static_cast<uint64_t>(cout_pad) * 2,
                                static_cast<uint64_t>(cout_pad) * cin * 2};
         uint32_t box[3] = {64, P.b_bytes / 128, 1};
-        for (int pln = 0; pln < planes; ++pln)
-          if ((rc = encode_map(ctx, &P.b_map[pln], pln ? wb_lo : wb_hi, 3, dims, strides, box))) return rc;
+        if (P.b_merged) {
+          uint64_t dims4[4] = {dims[0], dims[1], dims[2], 2};
+          uint64_t strides3[3] = {strides[0], strides[1], static_cast<uint64_t>(b_ps)};
+          uint32_t box4[4] = {box[0], box[1], 1, 2};
+          if ((rc = encode_map(ctx, &P.b_map[0], wb_hi, 4, dims4, strides3, box4))) return rc;
+          P.b_map[1] = P.b_map[0];
+        } else {
+          for (int pln = 0; pln < planes; ++pln)
+            if ((rc = encode_map(ctx, &P.b_map[pln], pln ? wb_lo : wb_hi, 3, dims, strides, box))) return rc;
+        }
       }
       EpilogueGeom g{stride, stride, py, px, 1, in_h, in_w};
       if ((rc = fill_epilogue(ctx, P, ep, g, dy->n, cin))) return rc;

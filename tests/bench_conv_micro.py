@@ -48,16 +48,21 @@ def run(ctx, n, h, w, cin, cout, k=3, mode="full", fast=False, iters=20):
 if __name__ == "__main__":
     shapes = [(64, 128, 64, 128, 128), (64, 128, 64, 256, 256), (64, 64, 32, 512, 512), (448, 48, 48, 128, 128),
               (64, 32, 16, 640, 640)]
-    variants = [("single", 0, "0"), ("single-2stage", 0, "2"), ("pair", 2, "0"), ("pair-2stage", 2, "2"),
-                ("pair-3stage", 2, "3")]
+    variants = [("single", 0, {}), ("single-nomerge", 0, {"DPIG_CONV_MERGE": "0"}), ("pair", 2, {}),
+                ("pair-nomerge", 2, {"DPIG_CONV_MERGE": "0"}), ("single-2stage", 0, {"DPIG_CONV_STAGES": "2"})]
     if len(sys.argv) > 1:
         variants = [v for v in variants if v[0] in sys.argv[1:]]
-    for name, tiling, stages in variants:
-        os.environ["DPIG_CONV_STAGES"] = stages
+    if os.environ.get("MICRO_SHAPES"):  # e.g. MICRO_SHAPES=0,1 MICRO_MODES=none (profiling one launch under ncu)
+        shapes = [shapes[int(i)] for i in os.environ["MICRO_SHAPES"].split(",")]
+    modes = os.environ.get("MICRO_MODES", "full,nores,none").split(",")
+    for name, tiling, env in variants:
+        for k in ("DPIG_CONV_STAGES", "DPIG_CONV_MERGE"):
+            os.environ.pop(k, None)
+        os.environ.update(env)
         ctx = dpig_b200.Context(0)
         ctx.set_pair_mode(tiling)
         for (n, h, w, cin, cout) in shapes:
-            for mode in ("full", "nores", "none"):
+            for mode in modes:
                 ms, tf = run(ctx, n, h, w, cin, cout, mode=mode, fast=False)
                 print("%-14s %4dx%3dx%3d %4d->%4d  epilogue=%-5s %7.3f ms  %7.1f TFLOP/s (algorithmic)" % (
                     name, n, h, w, cin, cout, mode, ms, tf), flush=True)
