@@ -562,7 +562,7 @@ extern "C" int dpig_embedding_assemble(dpig_ctx* ctx, float* fea, float* bg, con
                                        int32_t parts, int32_t part_z, int32_t bg_z, float* emb, int32_t backward,
                                        dpig_stream stream) {
   DPIG_CHECK_CTX(ctx);
-  if (!fea || !bg || !vis || !emb) return set_error(ctx, DPIG_EINVAL, "embedding_assemble: null argument");
+  if (!fea || (!bg && bg_z > 0) || !vis || !emb) return set_error(ctx, DPIG_EINVAL, "embedding_assemble: null argument");
   const int total = batch * (parts * part_z + bg_z);
   emb_assemble_kernel<<<(total + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(
       fea, bg, vis, batch, parts, part_z, bg_z, emb, backward);

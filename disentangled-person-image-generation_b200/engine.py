@@ -29,14 +29,36 @@ def _pad8(c):
 
 
 class NetConfig:
-    """Shapes of the Stage-I Market-1501 graph (reference config.py:23-25, trainer.py:74-75, 576-582)."""
+    """Shapes of the Stage-I graphs.
+
+    Market-1501 128x64, --model=1 (reference config.py:23-25, trainer.py:74-75, 576-582): Fg/Bg two-branch encoder
+    (models.py:390-471), ROI pyramid and U-Net `repeat_num` levels deep, D applied to x and to G in separate calls.
+    DeepFashion 256x256, --model=101 (reference trainer_256.py:31-68) = NetConfig.deepfashion(): `fgbg=False`
+    (models.GeneratorCNN_ID_Encoder_BodyROIVis, models.py:328-388: no mask, no background branch), ROI pyramid
+    `repeat_num+1` levels on 64x64 crops, U-Net `repeat_num-1` levels, D applied once to concat([x, G]) (`d_joint`:
+    joint batch statistics; the logits are split in half afterwards)."""
 
     def __init__(self, img_h=128, img_w=64, hidden=128, z_num=64, roi_size=48, n_parts=7, part_z=32,
-                 keypoints=18, d_dim=64, repeat_num=None):
+                 keypoints=18, d_dim=64, repeat_num=None, fgbg=True, enc_repeat=None, unet_repeat=None, d_joint=False):
         self.img_h, self.img_w, self.hidden, self.z_num = img_h, img_w, hidden, z_num
         self.roi_size, self.n_parts, self.part_z, self.keypoints, self.d_dim = roi_size, n_parts, part_z, keypoints, d_dim
         self.repeat_num = repeat_num if repeat_num is not None else int(math.log2(img_h)) - 2
-        self.emb_dim = n_parts * part_z + 4 * part_z
+        self.fgbg, self.d_joint = fgbg, d_joint
+        self.enc_repeat = enc_repeat if enc_repeat is not None else self.repeat_num
+        self.unet_repeat = unet_repeat if unet_repeat is not None else self.repeat_num
+        self.emb_dim = n_parts * part_z + (4 * part_z if fgbg else 0)
+        # rows of D's Linear: tf.reshape(output, [-1, 8*4*8*dim]) (wgan_gp.py:433) is hard-wired to the 128x64 geometry,
+        # so a 256x256 image yields 8 rows (= 8 logits) of 64 channels each (SURVEY.md q5); reduced test geometries whose
+        # whole map is smaller keep one row per image
+        self.d_row = min(8 * 4 * 8 * d_dim, (img_h // 16) * (img_w // 16) * 8 * d_dim)
+        self.d_rows = (img_h // 16) * (img_w // 16) * 8 * d_dim // self.d_row
+
+    @classmethod
+    def deepfashion(cls, img_h=256, img_w=256, hidden=128, roi_size=64, **kw):
+        """--model=101 (trainer_256.py:40-55): encoder repeat_num+1 levels, roi 64, U-Net repeat_num-1 levels."""
+        rn = int(math.log2(img_h)) - 2
+        return cls(img_h=img_h, img_w=img_w, hidden=hidden, roi_size=roi_size, repeat_num=rn, fgbg=False,
+                   enc_repeat=rn + 1, unet_repeat=rn - 1, d_joint=True, **kw)
 
 
 # ------------------------------------------------------------------------------------- parameters
@@ -137,9 +159,9 @@ def _mask(pixels, c, device):
 class _Pyramid:
     """`repeat_num` levels of {conv, conv, +res, [conv/s2]} (models.py:421-429, 454-462, 530-539)."""
 
-    def __init__(self, eng, prefix, layers, x_in, n, h, w, y_slots=None, in_mask=None):
+    def __init__(self, eng, prefix, layers, x_in, n, h, w, rn, y_slots=None, in_mask=None):
         cfg = eng.cfg
-        hn, rn = cfg.hidden, cfg.repeat_num
+        hn = cfg.hidden
         dev = eng.device
         self.layers = layers  # 3*rn - 1 ConvLayers in creation order
         self.n, self.rn = n, rn
@@ -214,11 +236,14 @@ class _Pyramid:
 class _DiscPass:
     """Activations of one DCGANDiscriminator application (wgan_gp.py:407-440)."""
 
-    def __init__(self, eng, n):
+    def __init__(self, eng, n, segs=1):
+        """n images in `segs` equal groups (2 = concat([x, G]), trainer_256.py:61-63).  The Linear sees
+        cfg.d_rows rows per image; row (group g, row r, image b) of flat / logits sits at (g*d_rows + r)*(n/segs) + b,
+        so the logits of each group are contiguous (tf.split(D_z, 2), trainer_256.py:66)."""
         cfg, dev = eng.cfg, eng.device
         d = cfg.d_dim
         H, W = cfg.img_h, cfg.img_w
-        self.n = n
+        self.n, self.segs = n, segs
         self.h = [SplitTensor(n, H >> (i + 1), W >> (i + 1), d << i, dev) for i in range(4)]   # activated outputs
         self.m = [_mask(n * (H >> (i + 1)) * (W >> (i + 1)), d << i, dev) for i in range(4)]
         self.pre = [None] + [torch.zeros((n, H >> (i + 1), W >> (i + 1), d << i), device=dev) for i in (1, 2, 3)]
@@ -226,15 +251,27 @@ class _DiscPass:
         self.sums = [None] + [torch.zeros((2, g), dtype=torch.float64, device=dev) for g in self.groups[1:]]
         self.stats = [None] + [torch.zeros((2, g), device=dev) for g in self.groups[1:]]
         self.red = [None] + [torch.zeros((2, g), dtype=torch.float64, device=dev) for g in self.groups[1:]]
-        flat = (H >> 4) * (W >> 4) * 8 * d
-        self.flat = torch.zeros((n, flat), device=dev)
-        self.logits = torch.zeros((n,), device=dev)
+        rows = n * cfg.d_rows
+        self.flat = torch.zeros((rows, cfg.d_row), device=dev)
+        self.logits = torch.zeros((rows,), device=dev)
         # backward
-        self.dlogits = torch.zeros((n,), device=dev)
-        self.g_flat = torch.zeros((n, flat), device=dev)
+        self.dlogits = torch.zeros((rows,), device=dev)
+        self.g_flat = torch.zeros((rows, cfg.d_row), device=dev)
         self.g_h = [SplitTensor(n, H >> (i + 1), W >> (i + 1), d << i, dev) for i in range(4)]  # grad wrt activated
         self.g_pre = [SplitTensor(n, H >> (i + 1), W >> (i + 1), d << i, dev) for i in range(4)]  # grad wrt conv out
         self.g_x = torch.zeros((n, H, W, 3), device=dev)
+
+
+class _DiscHalf:
+    """One half of a joint discriminator pass (views of its logits / logit gradients / image gradient)."""
+
+    def __init__(self, dp, half):
+        rows = dp.logits.numel() // 2
+        n = dp.n // 2
+        self.n = n
+        self.logits = dp.logits[half * rows:(half + 1) * rows]
+        self.dlogits = dp.dlogits[half * rows:(half + 1) * rows]
+        self.g_x = dp.g_x[half * n:(half + 1) * n]
 
 
 class Stage1Engine:
@@ -245,6 +282,9 @@ class Stage1Engine:
         self.gan_mode = GAN_MODES[mode]
         self.norm_mode = NORM_LAYER if mode == "wgan-gp" else NORM_BATCH  # wgan_gp.py:34-40
         self.world = dist.world_size if dist is not None else 1
+        if mode == "wgan-gp" and (cfg.d_joint or cfg.d_rows != 1):
+            # the reference's 256x256 trainers hard-wire MODE='dcgan' (trainer_256.py:28)
+            raise _lib.DpigError("wgan-gp is built for the 128x64 graph only (one logit per image, separate D calls)")
         self._keep = []
         self._db_done = set()
         self.fuse_bias_grad = True
@@ -262,7 +302,7 @@ class Stage1Engine:
     # -------------------------------------------------------------------------------- parameters
     def _build_params(self):
         cfg, dev = self.cfg, self.device
-        hn, rn = cfg.hidden, cfg.repeat_num
+        hn, rn, ern = cfg.hidden, cfg.unet_repeat, cfg.enc_repeat
         gspecs, dspecs = [], []
         self.layers = OrderedDict()
 
@@ -284,13 +324,13 @@ class Stage1Engine:
             group_specs.append((name + "/biases", (cout,)))
             return name
 
-        def pyramid(scope, cc):
+        def pyramid(scope, cc, levels):
             names = []
-            for idx in range(rn):
+            for idx in range(levels):
                 c = hn * (idx + 1)
                 names.append(conv(gspecs, scope, cc, 3, 1, c, c))
                 names.append(conv(gspecs, scope, cc, 3, 1, c, c))
-                if idx < rn - 1:
+                if idx < levels - 1:
                     names.append(conv(gspecs, scope, cc, 3, 2, c, hn * (idx + 2)))
             return names
 
@@ -299,21 +339,23 @@ class Stage1Engine:
         self.n_e0 = conv(gspecs, sc, cc, 3, 1, 3, hn, need_bwd=False)
         self.n_e1 = conv(gspecs, sc, cc, 3, 1, hn, hn)
         self.n_e2 = conv(gspecs, sc, cc, 3, 1, hn, hn)
-        self.n_roi = pyramid(sc, cc)
-        roi_f = cfg.roi_size >> (rn - 1)
-        self.roi_flat = roi_f * roi_f * hn * rn
+        self.n_roi = pyramid(sc, cc, ern)
+        roi_f = cfg.roi_size >> (ern - 1)
+        self.roi_flat = roi_f * roi_f * hn * ern
         self.n_roi_fc = fc(gspecs, sc, fc_c, self.roi_flat, cfg.part_z)
-        self.n_bg = pyramid(sc, cc)
+        if cfg.fgbg:   # background branch of the two-branch encoder (models.py:454-464)
+            self.n_bg = pyramid(sc, cc, ern)
+            self.bg_flat = (cfg.img_h >> (ern - 1)) * (cfg.img_w >> (ern - 1)) * hn * ern
+            self.n_bg_fc = fc(gspecs, sc, fc_c, self.bg_flat, cfg.part_z * 4)
         self.fh, self.fw = cfg.img_h >> (rn - 1), cfg.img_w >> (rn - 1)
-        self.bg_flat = self.fh * self.fw * hn * rn
-        self.n_bg_fc = fc(gspecs, sc, fc_c, self.bg_flat, cfg.part_z * 4)
+        self.gtop_flat = self.fh * self.fw * hn * rn
         # ID_AE/G (models.py:518-576)
         sc, cc, fc_c = "ID_AE/G", [0], [0]
         self.gin_c = cfg.emb_dim + cfg.keypoints
         self.pose_cpad = _pad8(cfg.keypoints)
         self.n_gstem = conv(gspecs, sc, cc, 3, 1, self.gin_c, hn, need_bwd=False)
-        self.n_genc = pyramid(sc, cc)
-        self.n_gfc1 = fc(gspecs, sc, fc_c, self.bg_flat, cfg.z_num)
+        self.n_genc = pyramid(sc, cc, rn)
+        self.n_gfc1 = fc(gspecs, sc, fc_c, self.gtop_flat, cfg.z_num)
         self.n_gfc2 = fc(gspecs, sc, fc_c, cfg.z_num, self.fh * self.fw * hn)
         self.n_gdec = []
         self.dec_c = []
@@ -343,7 +385,7 @@ class Stage1Engine:
             self.layers[name] = dict(k=5, stride=2, cin=chans[i], cout=chans[i + 1], small=False, need_bwd=True,
                                      cin_pad=None)
             self.n_d.append(name)
-        self.d_flat = (cfg.img_h // 16) * (cfg.img_w // 16) * 8 * d
+        self.d_flat = cfg.d_row
         dspecs.append(("Discriminator.Output.W", (self.d_flat, 1)))
         dspecs.append(("Discriminator.Output.b", (1,)))
 
@@ -374,7 +416,7 @@ class Stage1Engine:
             self.dp.view("Discriminator.BN%d.scale" % i).fill_(1.0)
         # the D output weight is kept NHWC-flattened internally; TF order (c-major) at the API boundary
         hw = (cfg.img_h // 16) * (cfg.img_w // 16)
-        self._dperm = torch.arange(self.d_flat, device=dev).view(8 * d, hw).t().reshape(-1)  # nhwc idx -> nchw idx
+        self._dperm = torch.arange(self.d_flat, device=dev).view(8 * d // cfg.d_rows, hw).t().reshape(-1)  # nhwc idx -> nchw idx
 
     def param_names(self):
         return list(self.gp.specs) + list(self.dp.specs)
@@ -422,11 +464,15 @@ class Stage1Engine:
     # -------------------------------------------------------------------------------- buffers
     def _build_buffers(self):
         cfg, dev, B = self.cfg, self.device, self.B
-        H, W, hn, rn = cfg.img_h, cfg.img_w, cfg.hidden, cfg.repeat_num
+        H, W, hn, rn, ern = cfg.img_h, cfg.img_w, cfg.hidden, cfg.unet_repeat, cfg.enc_repeat
         P = cfg.n_parts
         # inputs (device copies of one batch)
         self.x = torch.zeros((B, H, W, 3), device=dev)
-        self.x8 = SplitTensor(B, H, W, 8, dev, zero=True)   # image as a channel-padded split tensor (TMA operand)
+        if cfg.d_joint:   # concat([x, G]) (trainer_256.py:61): x and G are the two halves of one buffer
+            self.pair8 = SplitTensor(2 * B, H, W, 8, dev, zero=True)
+            self.x8 = self.pair8.batch_slice(0, B)
+        else:
+            self.x8 = SplitTensor(B, H, W, 8, dev, zero=True)   # image as a channel-padded split tensor (TMA operand)
         self.pose_rcv = torch.zeros((B, cfg.keypoints, 3), device=dev)
         self.fg_mask = torch.zeros((B, H, W), device=dev)
         self.boxes = torch.zeros((P * B, 4), device=dev)
@@ -439,14 +485,17 @@ class Stage1Engine:
         self.me1 = _mask(B * H * W, hn, dev)
         self.xs = SplitTensor(B, H, W, hn, dev)
         self.me2 = _mask(B * H * W, hn, dev)
-        self.x_bg = SplitTensor(B, H, W, hn, dev)
         self.rois = SplitTensor(P * B, cfg.roi_size, cfg.roi_size, hn, dev)
-        self.roi_pyr = _Pyramid(self, "roi", [self.conv[n] for n in self.n_roi], self.rois, P * B, cfg.roi_size, cfg.roi_size)
-        self.bg_pyr = _Pyramid(self, "bg", [self.conv[n] for n in self.n_bg], self.x_bg, B, H, W)
+        self.roi_pyr = _Pyramid(self, "roi", [self.conv[n] for n in self.n_roi], self.rois, P * B, cfg.roi_size,
+                                cfg.roi_size, ern)
         self.roi_flat_f32 = torch.zeros((P * B, self.roi_flat), device=dev)
         self.fea = torch.zeros((P * B, cfg.part_z), device=dev)
-        self.bg_flat_f32 = torch.zeros((B, self.bg_flat), device=dev)
-        self.bg_fea = torch.zeros((B, cfg.part_z * 4), device=dev)
+        self.bg_z = cfg.part_z * 4 if cfg.fgbg else 0
+        if cfg.fgbg:
+            self.x_bg = SplitTensor(B, H, W, hn, dev)
+            self.bg_pyr = _Pyramid(self, "bg", [self.conv[n] for n in self.n_bg], self.x_bg, B, H, W, ern)
+            self.bg_flat_f32 = torch.zeros((B, self.bg_flat), device=dev)
+        self.bg_fea = torch.zeros((B, max(self.bg_z, 1)), device=dev)
         self.emb = torch.zeros((B, cfg.emb_dim), device=dev)
         # generator
         self.gin = SplitTensor(B, H, W, self.pose_cpad, dev, zero=True)      # pose maps only (channels 0..17)
@@ -467,10 +516,10 @@ class Stage1Engine:
         for idx in range(rn):
             xc, c = self.dec_c[idx]
             y_slots[rn - 1 - idx] = self.cat[idx].slice(xc, c - xc)
-        self.genc = _Pyramid(self, "genc", [self.conv[n] for n in self.n_genc], self.g0, B, H, W, y_slots=y_slots,
+        self.genc = _Pyramid(self, "genc", [self.conv[n] for n in self.n_genc], self.g0, B, H, W, rn, y_slots=y_slots,
                              in_mask=self.mg0)
         self.genc.in_layer = self.conv[self.n_gstem]
-        self.gtop_f32 = torch.zeros((B, self.bg_flat), device=dev)
+        self.gtop_f32 = torch.zeros((B, self.gtop_flat), device=dev)
         self.z = torch.zeros((B, cfg.z_num), device=dev)
         self.dec_in_f32 = torch.zeros((B, self.fh * self.fw * hn), device=dev)
         self.dec_a, self.dec_y, self.dec_ma, self.dec_mb, self.dec_mu = [], [], [], [], []
@@ -485,7 +534,7 @@ class Stage1Engine:
             if idx < rn - 1:
                 self.dec_mu.append(_mask(B * hh * ww, self.dec_c[idx + 1][0], dev))
         self.G = torch.zeros((B, H, W, 3), device=dev)
-        self.G8 = SplitTensor(B, H, W, 8, dev, zero=True)
+        self.G8 = self.pair8.batch_slice(B, B) if cfg.d_joint else SplitTensor(B, H, W, 8, dev, zero=True)
         # generator backward
         self.g_G = torch.zeros((B, H, W, 3), device=dev)
         self.g_G8 = SplitTensor(B, H, W, 8, dev, zero=True)
@@ -502,22 +551,27 @@ class Stage1Engine:
                 self.dec_gu.append(SplitTensor(B, hh, ww, self.dec_c[idx + 1][0], dev))
         self.g_dec_in_f32 = torch.zeros((B, self.fh * self.fw * hn), device=dev)
         self.g_z = torch.zeros((B, cfg.z_num), device=dev)
-        self.g_gtop_f32 = torch.zeros((B, self.bg_flat), device=dev)
+        self.g_gtop_f32 = torch.zeros((B, self.gtop_flat), device=dev)
         self.g_emb = torch.zeros((B, cfg.emb_dim), device=dev)
         # encoder backward
         self.g_fea = torch.zeros((P * B, cfg.part_z), device=dev)
-        self.g_bg_fea = torch.zeros((B, cfg.part_z * 4), device=dev)
+        self.g_bg_fea = torch.zeros((B, max(self.bg_z, 1)), device=dev)
         self.g_roi_flat = torch.zeros((P * B, self.roi_flat), device=dev)
-        self.g_bg_flat = torch.zeros((B, self.bg_flat), device=dev)
         self.g_crop = torch.zeros((B, H, W, hn), device=dev)
-        self.g_xbg_s = SplitTensor(B, H, W, hn, dev)
+        if cfg.fgbg:
+            self.g_bg_flat = torch.zeros((B, self.bg_flat), device=dev)
+            self.g_xbg_s = SplitTensor(B, H, W, hn, dev)
         self.g_xs = SplitTensor(B, H, W, hn, dev)
         self.g_xs_m = SplitTensor(B, H, W, hn, dev)
         self.g_e1 = SplitTensor(B, H, W, hn, dev)
         self.g_e0 = SplitTensor(B, H, W, hn, dev)
         # discriminator passes
-        self.d_real = _DiscPass(self, B)
-        self.d_fake = _DiscPass(self, B)
+        if cfg.d_joint:
+            self.d_pair = _DiscPass(self, 2 * B, segs=2)
+            self.d_real, self.d_fake = _DiscHalf(self.d_pair, 0), _DiscHalf(self.d_pair, 1)
+        else:
+            self.d_real = _DiscPass(self, B)
+            self.d_fake = _DiscPass(self, B)
         if self.mode == "wgan-gp":
             self._build_gp_buffers()
         # losses: [g_gan, d_loss], [L1], gp
@@ -634,6 +688,14 @@ class Stage1Engine:
         self._prog_unet_forward(self.p_fwd_unet)
         self.p_bwd_gen = Program(self.ctx)     # g_G -> all Encoder+G parameter gradients
         self._prog_backward_generator(self.p_bwd_gen)
+        if self.cfg.d_joint:
+            self.p_d_pair_fwd = Program(self.ctx)
+            self._prog_disc_forward(self.p_d_pair_fwd, self.d_pair, self.pair8)
+            self.p_d_pair_bwd_data = Program(self.ctx)   # G step: gradient w.r.t. the image halves (the G half is used)
+            self._prog_disc_backward(self.p_d_pair_bwd_data, self.d_pair, self.pair8, params=False, data=True)
+            self.p_d_pair_bwd_par = Program(self.ctx)    # D step
+            self._prog_disc_backward(self.p_d_pair_bwd_par, self.d_pair, self.pair8, params=True, data=False)
+            return
         self.p_d_fake_fwd = Program(self.ctx)
         self._prog_disc_forward(self.p_d_fake_fwd, self.d_fake, self.G8)
         self.p_d_real_fwd = Program(self.ctx)
@@ -725,37 +787,41 @@ class Stage1Engine:
 
     def score_generated(self, stream=None):
         """DCGANDiscriminator logits of the current self.G (tester.py:568-571)."""
+        if self.cfg.d_joint:
+            raise _lib.DpigError("score_generated: the joint-D (256x256) graph scores concat([x, G]) only")
         self.p_d_fake_fwd.run(stream if stream is not None else torch.cuda.current_stream().cuda_stream)
         return self.d_fake.logits
 
     def _prog_forward_encoder(self, p):
         cfg, B = self.cfg, self.B
-        H, W, hn, rn, P = cfg.img_h, cfg.img_w, cfg.hidden, cfg.repeat_num, cfg.n_parts
+        H, W, hn, rn, P = cfg.img_h, cfg.img_w, cfg.hidden, cfg.enc_repeat, cfg.n_parts
         e0, e1, e2 = self.conv[self.n_e0], self.conv[self.n_e1], self.conv[self.n_e2]
-        # ---- encoder (models.py:396-471)
+        # ---- encoder (models.py:396-471; without the mask / background branch: models.py:334-384)
         p.add("pack_f32", ptr(self.x), 3, 3, self.x8.ref())
         self.conv_fwd(p, e0, self.x8, out=self.e0, mask_out=self.me0)
         self.conv_fwd(p, e1, self.e0, out=self.e1, mask_out=self.me1)
         self.conv_fwd(p, e2, self.e1, out=self.xs, addend=self.e0, mask_out=self.me2)
-        p.add("mask_split", self.xs.ref(), ptr(self.fg_mask), None, self.x_bg.ref())
-        p.add("crop_and_resize_fwd", self.xs.ref(), ptr(self.fg_mask), ptr(self.boxes), ptr(self.box_ind), P * B,
-              self.rois.ref())
+        if cfg.fgbg:
+            p.add("mask_split", self.xs.ref(), ptr(self.fg_mask), None, self.x_bg.ref())
+        p.add("crop_and_resize_fwd", self.xs.ref(), ptr(self.fg_mask) if cfg.fgbg else None, ptr(self.boxes),
+              ptr(self.box_ind), P * B, self.rois.ref())
         self.roi_pyr.forward(self, p)
         p.add("unpack_f32", self.roi_pyr.y[rn - 1].ref(), ptr(self.roi_flat_f32), hn * rn)
         w, b, _, _ = self._linear(self.gp, self.n_roi_fc)
         p.add("linear_fwd", ptr(self.roi_flat_f32), ptr(w), ptr(b), ptr(self.fea), P * B, self.roi_flat, cfg.part_z,
               ACT_NONE, 0.0)
-        self.bg_pyr.forward(self, p)
-        p.add("unpack_f32", self.bg_pyr.y[rn - 1].ref(), ptr(self.bg_flat_f32), hn * rn)
-        w, b, _, _ = self._linear(self.gp, self.n_bg_fc)
-        p.add("linear_fwd", ptr(self.bg_flat_f32), ptr(w), ptr(b), ptr(self.bg_fea), B, self.bg_flat, cfg.part_z * 4,
-              ACT_NONE, 0.0)
-        p.add("embedding_assemble", ptr(self.fea), ptr(self.bg_fea), ptr(self.vis), B, P, cfg.part_z, cfg.part_z * 4,
+        if cfg.fgbg:
+            self.bg_pyr.forward(self, p)
+            p.add("unpack_f32", self.bg_pyr.y[rn - 1].ref(), ptr(self.bg_flat_f32), hn * rn)
+            w, b, _, _ = self._linear(self.gp, self.n_bg_fc)
+            p.add("linear_fwd", ptr(self.bg_flat_f32), ptr(w), ptr(b), ptr(self.bg_fea), B, self.bg_flat, self.bg_z,
+                  ACT_NONE, 0.0)
+        p.add("embedding_assemble", ptr(self.fea), ptr(self.bg_fea), ptr(self.vis), B, P, cfg.part_z, self.bg_z,
               ptr(self.emb), 0)
 
     def _prog_unet_forward(self, p):
         cfg, B = self.cfg, self.B
-        H, W, hn, rn = cfg.img_h, cfg.img_w, cfg.hidden, cfg.repeat_num
+        H, W, hn, rn = cfg.img_h, cfg.img_w, cfg.hidden, cfg.unet_repeat
         # stem (models.py:528) on concat(tiled embedding, pose): the embedding channels are constant over space
         # (trainer.py:588-590), so their 3x3 contribution is a per-image, per-border-class bias
         stem = self.conv[self.n_gstem]
@@ -772,7 +838,7 @@ class Stage1Engine:
         top = self.genc.y[rn - 1]
         p.add("unpack_f32", top.ref(), ptr(self.gtop_f32), hn * rn)
         w, b, _, _ = self._linear(self.gp, self.n_gfc1)
-        p.add("linear_fwd", ptr(self.gtop_f32), ptr(w), ptr(b), ptr(self.z), B, self.bg_flat, cfg.z_num, ACT_NONE, 0.0)
+        p.add("linear_fwd", ptr(self.gtop_f32), ptr(w), ptr(b), ptr(self.z), B, self.gtop_flat, cfg.z_num, ACT_NONE, 0.0)
         w, b, _, _ = self._linear(self.gp, self.n_gfc2)
         p.add("linear_fwd", ptr(self.z), ptr(w), ptr(b), ptr(self.dec_in_f32), B, cfg.z_num, self.fh * self.fw * hn,
               ACT_NONE, 0.0)
@@ -794,7 +860,7 @@ class Stage1Engine:
     def _prog_backward_generator(self, p):
         """Consumes self.g_G (fp32 grad wrt the generated image) and accumulates all Encoder+G param grads."""
         cfg, B = self.cfg, self.B
-        H, W, hn, rn, P = cfg.img_h, cfg.img_w, cfg.hidden, cfg.repeat_num, cfg.n_parts
+        H, W, hn, rn, ern, P = cfg.img_h, cfg.img_w, cfg.hidden, cfg.unet_repeat, cfg.enc_repeat, cfg.n_parts
         p.add("pack_f32", ptr(self.g_G), 3, 3, self.g_G8.ref())
         # ---- decoder
         lo = self.conv[self.n_gout]
@@ -828,7 +894,7 @@ class Stage1Engine:
               self.fh * self.fw * hn)
         w, b, dw, db = self._linear(self.gp, self.n_gfc1)
         p.add("linear_bwd", ptr(self.gtop_f32), ptr(w), ptr(self.g_z), ptr(self.g_gtop_f32), ptr(dw), ptr(db), B,
-              self.bg_flat, cfg.z_num)
+              self.gtop_flat, cfg.z_num)
         # ---- U-Net encoder: top gradient = FC path + skip path
         skip = []
         for lvl in range(rn):
@@ -856,24 +922,27 @@ class Stage1Engine:
                   None, B, e, hn)
             p.add("add_f32", ptr(self.g_emb), ptr(self.stem_tmp), ptr(self.g_emb) if tap else None, B * e, 1.0, 1.0)
         # ---- appearance encoder
-        p.add("embedding_assemble", ptr(self.g_fea), ptr(self.g_bg_fea), ptr(self.vis), B, P, cfg.part_z, cfg.part_z * 4,
+        p.add("embedding_assemble", ptr(self.g_fea), ptr(self.g_bg_fea), ptr(self.vis), B, P, cfg.part_z, self.bg_z,
               ptr(self.g_emb), 1)
         w, b, dw, db = self._linear(self.gp, self.n_roi_fc)
         p.add("linear_bwd", ptr(self.roi_flat_f32), ptr(w), ptr(self.g_fea), ptr(self.g_roi_flat), ptr(dw), ptr(db), P * B,
               self.roi_flat, cfg.part_z)
-        p.add("pack_f32", ptr(self.g_roi_flat), hn * rn, hn * rn, self.roi_pyr.g_y[rn - 1].ref())
+        p.add("pack_f32", ptr(self.g_roi_flat), hn * ern, hn * ern, self.roi_pyr.g_y[ern - 1].ref())
         self.roi_pyr.backward(self, p)
         p.add_py(lambda s: self.g_crop.zero_())
-        p.add("crop_and_resize_bwd", self.roi_pyr.g_in.ref(), ptr(self.fg_mask), ptr(self.boxes), ptr(self.box_ind), P * B,
-              ptr(self.g_crop), B, H, W, hn)
-        w, b, dw, db = self._linear(self.gp, self.n_bg_fc)
-        p.add("linear_bwd", ptr(self.bg_flat_f32), ptr(w), ptr(self.g_bg_fea), ptr(self.g_bg_flat), ptr(dw), ptr(db), B,
-              self.bg_flat, cfg.part_z * 4)
-        p.add("pack_f32", ptr(self.g_bg_flat), hn * rn, hn * rn, self.bg_pyr.g_y[rn - 1].ref())
-        self.bg_pyr.backward(self, p)
-        # g_xs = g_crop (already * m) + g_xbg * (1 - m)      (models.py:402-403)
-        p.add("mask_split", self.bg_pyr.g_in.ref(), ptr(self.fg_mask), None, self.g_xbg_s.ref())
-        p.add("ew_combine", self.g_xs.ref(), self.g_xbg_s.ref(), None, None, ptr(self.g_crop), hn, None, 0.0, 0)
+        p.add("crop_and_resize_bwd", self.roi_pyr.g_in.ref(), ptr(self.fg_mask) if cfg.fgbg else None, ptr(self.boxes),
+              ptr(self.box_ind), P * B, ptr(self.g_crop), B, H, W, hn)
+        if cfg.fgbg:
+            w, b, dw, db = self._linear(self.gp, self.n_bg_fc)
+            p.add("linear_bwd", ptr(self.bg_flat_f32), ptr(w), ptr(self.g_bg_fea), ptr(self.g_bg_flat), ptr(dw), ptr(db), B,
+                  self.bg_flat, self.bg_z)
+            p.add("pack_f32", ptr(self.g_bg_flat), hn * ern, hn * ern, self.bg_pyr.g_y[ern - 1].ref())
+            self.bg_pyr.backward(self, p)
+            # g_xs = g_crop (already * m) + g_xbg * (1 - m)      (models.py:402-403)
+            p.add("mask_split", self.bg_pyr.g_in.ref(), ptr(self.fg_mask), None, self.g_xbg_s.ref())
+            p.add("ew_combine", self.g_xs.ref(), self.g_xbg_s.ref(), None, None, ptr(self.g_crop), hn, None, 0.0, 0)
+        else:
+            p.add("pack_f32", ptr(self.g_crop), hn, hn, self.g_xs.ref())
         p.add("ew_combine", self.g_xs_m.ref(), self.g_xs.ref(), None, None, None, 0, ptr(self.me2), 0.0, 0)
         e0, e1, e2 = self.conv[self.n_e0], self.conv[self.n_e1], self.conv[self.n_e2]
         self.conv_wgrad(p, e2, self.e1, self.g_xs_m)
@@ -899,10 +968,27 @@ class Stage1Engine:
             of = self.dp.view("Discriminator.BN%d.offset" % (i + 1))
             p.add("norm_act_fwd", ptr(dp.pre[i]), n, hh, ww, c, self.norm_mode, 1e-5, ptr(dp.sums[i]), count, ptr(sc),
                   ptr(of), ACT_LRELU, 0.2, ptr(dp.stats[i]), dp.h[i].ref(), ptr(dp.m[i]))
-        p.add("unpack_f32", dp.h[3].ref(), ptr(dp.flat), d * 8)
+        for view, rows in self._disc_rows(dp, dp.h[3], dp.flat):
+            p.add("unpack_f32", view.ref(), ptr(rows), view.c)
         w = self.dp.view("Discriminator.Output.W")
         b = self.dp.view("Discriminator.Output.b")
-        p.add("linear_fwd", ptr(dp.flat), ptr(w), ptr(b), ptr(dp.logits), n, self.d_flat, 1, ACT_NONE, 0.0)
+        p.add("linear_fwd", ptr(dp.flat), ptr(w), ptr(b), ptr(dp.logits), n * cfg.d_rows, self.d_flat, 1, ACT_NONE, 0.0)
+
+    def _disc_rows(self, dp, t, flat):
+        """(view of the last feature map, rows of the Linear input it fills): the whole map when every image is one
+        row; else, per image group g and row r, the channel block [r*C/R, (r+1)*C/R) of that group's images
+        (NCHW flatten + reshape [-1, 16384], wgan_gp.py:433) -> rows (g*R + r)*n_g .. +n_g."""
+        R = self.cfg.d_rows
+        if R == 1:
+            return [(t, flat)]
+        out = []
+        ng, cpr = dp.n // dp.segs, t.c // R
+        for g in range(dp.segs):
+            for r in range(R):
+                v = t.batch_slice(g * ng, ng).slice(r * cpr, cpr)
+                self._keep.append(v)
+                out.append((v, flat[(g * R + r) * ng:(g * R + r + 1) * ng]))
+        return out
 
     def _prog_disc_backward(self, p, dp, img, params, data):
         """dp.dlogits -> parameter grads (params=True) and/or the gradient w.r.t. the input image (data=True)."""
@@ -912,8 +998,9 @@ class Stage1Engine:
         dw = self.dp.gview("Discriminator.Output.W")
         db = self.dp.gview("Discriminator.Output.b")
         p.add("linear_bwd", ptr(dp.flat), ptr(w), ptr(dp.dlogits), ptr(dp.g_flat), ptr(dw) if params else None,
-              ptr(db) if params else None, n, self.d_flat, 1)
-        p.add("pack_f32", ptr(dp.g_flat), d * 8, d * 8, dp.g_h[3].ref())
+              ptr(db) if params else None, n * cfg.d_rows, self.d_flat, 1)
+        for view, rows in self._disc_rows(dp, dp.g_h[3], dp.g_flat):
+            p.add("pack_f32", ptr(rows), view.c, view.c, view.ref())
         for i in (3, 2, 1):
             layer = self.conv[self.n_d[i]]
             hh, ww, c = H >> (i + 1), W >> (i + 1), d << i
@@ -953,7 +1040,8 @@ class Stage1Engine:
 
         self.x.copy_(dev(batch["x"]))
         self.pose_rcv.copy_(dev(batch["pose_rcv"]))
-        self.fg_mask.copy_(dev(batch["mask"]).reshape(B, cfg.img_h, cfg.img_w))
+        if cfg.fgbg:
+            self.fg_mask.copy_(dev(batch["mask"]).reshape(B, cfg.img_h, cfg.img_w))
         bb = dev(batch["part_bbox"])[:, :P, :]                      # [B,P,4] pixels (y1,x1,y2,x2)
         scale = torch.tensor([cfg.img_h, cfg.img_w, cfg.img_h, cfg.img_w], dtype=torch.float32, device=self.device)
         self.boxes.copy_((bb / scale).permute(1, 0, 2).reshape(P * B, 4))   # ROI i of image b -> row i*B+b
@@ -964,11 +1052,24 @@ class Stage1Engine:
         s = torch.cuda.current_stream().cuda_stream
         self.p_fwd_gen.run(s)
         if with_disc:
-            self.p_d_real_fwd.run(s)
-            self.p_d_fake_fwd.run(s)
-            self.ctx.loss_gan(self.gan_mode, ptr(self.d_real.logits), ptr(self.d_fake.logits), self.B, ptr(self.loss_gan),
-                              None, None, None, s)
+            self._disc_fwd(s, None, real=True)
+            self.ctx.loss_gan(self.gan_mode, ptr(self.d_real.logits), ptr(self.d_fake.logits), self.n_logits,
+                              ptr(self.loss_gan), None, None, None, s)
             self.ctx.loss_l1(ptr(self.G), ptr(self.x), self.G.numel(), 20.0, ptr(self.loss_l1), None, s)
+
+    @property
+    def n_logits(self):
+        """logits per D application on B images (8 per image on the 256x256 graph)."""
+        return self.B * self.cfg.d_rows
+
+    def _disc_fwd(self, s, timings, real):
+        """D on G (and on x when `real`); the joint graph always sees concat([x, G]) (trainer_256.py:61-63)."""
+        if self.cfg.d_joint:
+            self.p_d_pair_fwd.run(s, timings)
+            return
+        if real:
+            self.p_d_real_fwd.run(s, timings)
+        self.p_d_fake_fwd.run(s, timings)
 
     def _optim(self, which, s):
         grp = self.gp if which == "g" else self.dp
@@ -991,12 +1092,15 @@ class Stage1Engine:
         s = torch.cuda.current_stream().cuda_stream
         self.gp.grad.zero_()
         self.p_fwd_gen.run(s, timings)
-        self.p_d_fake_fwd.run(s, timings)
-        self.ctx.loss_gan(self.gan_mode, None, ptr(self.d_fake.logits), self.B, ptr(self.loss_gan),
+        self._disc_fwd(s, timings, real=False)
+        self.ctx.loss_gan(self.gan_mode, None, ptr(self.d_fake.logits), self.n_logits, ptr(self.loss_gan),
                           ptr(self.d_fake.dlogits), None, None, s)
-        if self.world > 1:
-            pass  # batch-mean losses: per-rank grads are means over the local shard; summed then scaled by 1/world
-        self.p_d_fake_bwd_data.run(s, timings)
+        # batch-mean losses: per-rank grads are means over the local shard; summed then scaled by 1/world in _optim
+        if self.cfg.d_joint:
+            self.d_real.dlogits.zero_()   # g_loss does not depend on D(x), but x shares the batch statistics with G
+            self.p_d_pair_bwd_data.run(s, timings)
+        else:
+            self.p_d_fake_bwd_data.run(s, timings)
         self.g_G.copy_(self.d_fake.g_x)
         self.ctx.loss_l1(ptr(self.G), ptr(self.x), self.G.numel(), 20.0, ptr(self.loss_l1), ptr(self.g_G), s)
         self.p_bwd_gen.run(s, timings)
@@ -1006,12 +1110,14 @@ class Stage1Engine:
         s = torch.cuda.current_stream().cuda_stream
         self.dp.grad.zero_()
         self.p_fwd_gen.run(s, timings)
-        self.p_d_real_fwd.run(s, timings)
-        self.p_d_fake_fwd.run(s, timings)
-        self.ctx.loss_gan(self.gan_mode, ptr(self.d_real.logits), ptr(self.d_fake.logits), self.B, ptr(self.loss_gan),
-                          None, ptr(self.d_real.dlogits), ptr(self.d_fake.dlogits), s)
-        self.p_d_real_bwd_par.run(s, timings)
-        self.p_d_fake_bwd_par.run(s, timings)
+        self._disc_fwd(s, timings, real=True)
+        self.ctx.loss_gan(self.gan_mode, ptr(self.d_real.logits), ptr(self.d_fake.logits), self.n_logits,
+                          ptr(self.loss_gan), None, ptr(self.d_real.dlogits), ptr(self.d_fake.dlogits), s)
+        if self.cfg.d_joint:
+            self.p_d_pair_bwd_par.run(s, timings)
+        else:
+            self.p_d_real_bwd_par.run(s, timings)
+            self.p_d_fake_bwd_par.run(s, timings)
         if self.mode == "wgan-gp":
             if not self.gp_alpha_fixed:
                 self.gp_alpha.uniform_(0.0, 1.0)     # alpha ~ U[0,1] per sample (trainer.py:226-230)
@@ -1041,7 +1147,7 @@ def init_params(cfg, seed=1234):
     discriminator convs / linear -> U(+-0.02*sqrt(3)) (wgan_gp.py:411-413, tflib/ops/conv2d.py:56-80),
     zero biases, norm scale 1 / offset 0 (tflib/ops/batchnorm.py:23-24)."""
     rng = np.random.default_rng(seed)
-    hn, rn = cfg.hidden, cfg.repeat_num
+    hn, rn, ern = cfg.hidden, cfg.unet_repeat, cfg.enc_repeat
     p = OrderedDict()
 
     def xavier(shape, fan_in, fan_out):
@@ -1064,12 +1170,12 @@ def init_params(cfg, seed=1234):
             p[name + "/weights"] = xavier((cin, cout), cin, cout)
             p[name + "/biases"] = np.zeros(cout, np.float32)
 
-        def pyramid(self):
-            for idx in range(rn):
+        def pyramid(self, levels):
+            for idx in range(levels):
                 c = hn * (idx + 1)
                 self.conv(3, c, c)
                 self.conv(3, c, c)
-                if idx < rn - 1:
+                if idx < levels - 1:
                     self.conv(3, c, hn * (idx + 2))
 
     fh, fw = cfg.img_h >> (rn - 1), cfg.img_w >> (rn - 1)
@@ -1077,14 +1183,15 @@ def init_params(cfg, seed=1234):
     s.conv(3, 3, hn)
     s.conv(3, hn, hn)
     s.conv(3, hn, hn)
-    s.pyramid()
-    rf = cfg.roi_size >> (rn - 1)
-    s.fc(rf * rf * hn * rn, cfg.part_z)
-    s.pyramid()
-    s.fc(fh * fw * hn * rn, cfg.part_z * 4)
+    s.pyramid(ern)
+    rf = cfg.roi_size >> (ern - 1)
+    s.fc(rf * rf * hn * ern, cfg.part_z)
+    if cfg.fgbg:
+        s.pyramid(ern)
+        s.fc((cfg.img_h >> (ern - 1)) * (cfg.img_w >> (ern - 1)) * hn * ern, cfg.part_z * 4)
     s = Scope("ID_AE/G")
     s.conv(3, cfg.emb_dim + cfg.keypoints, hn)
-    s.pyramid()
+    s.pyramid(rn)
     s.fc(fh * fw * hn * rn, cfg.z_num)
     s.fc(cfg.z_num, fh * fw * hn)
     x_c = hn
@@ -1107,7 +1214,7 @@ def init_params(cfg, seed=1234):
         if i >= 1:
             p["Discriminator.BN%d.offset" % (i + 1)] = np.zeros(chans[i + 1], np.float32)
             p["Discriminator.BN%d.scale" % (i + 1)] = np.ones(chans[i + 1], np.float32)
-    d_in = (cfg.img_h // 16) * (cfg.img_w // 16) * 8 * d
+    d_in = cfg.d_row
     p["Discriminator.Output.W"] = rng.uniform(-lim, lim, size=(d_in, 1)).astype(np.float32)
     p["Discriminator.Output.b"] = np.zeros(1, np.float32)
     return p

@@ -3,12 +3,15 @@
 CPU restatement of the reference's hot-path graphs built on oracle/tf_ops.py:
 
   encoder_fgbg      <- models.GeneratorCNN_ID_Encoder_BodyROIVis_FgBgFeaTwoBranch   models.py:390-471
+  encoder_roi       <- models.GeneratorCNN_ID_Encoder_BodyROIVis (DeepFashion)      models.py:328-388
   unet_generator    <- models.GeneratorCNN_ID_UAEAfterResidual                      models.py:518-576
   dcgan_discriminator <- WGAN_GP.DCGANDiscriminator                                 wgan_gp.py:407-440
   fc_discriminator  <- WGAN_GP.FCDiscriminator                                      wgan_gp.py:399-405
   gaussian_fc_res   <- models.GaussianFCRes                                         models.py:474-486
   Stage-I model (--model=1) forward, losses and the g_optim / d_optim updates
                     <- trainer.DPIG_Encoder_GAN_BodyROI_FgBg.build_model / train    trainer.py:567-625, 336-347
+  DeepFashion 256x256 Stage-I model (--model=101): NetConfig.deepfashion()
+                    <- trainer_256.DPIG_Encoder_GAN_BodyROI_256.build_model         trainer_256.py:31-93
 
 Parameters live in a dict keyed by the reference's TensorFlow variable names (slim auto-numbering
 `Conv`, `Conv_1`, ... / `fully_connected`, `fully_connected_1` inside `Encoder/G_encoder` and
@@ -25,14 +28,35 @@ from . import tf_ops as T
 
 
 class NetConfig:
-    """Shapes of the Stage-I Market-1501 graph (config.py:23-25, trainer.py:74-75, 576-582)."""
+    """Shapes of the Stage-I graphs.
+
+    Market-1501 128x64, --model=1 (config.py:23-25, trainer.py:74-75, 576-582): Fg/Bg two-branch encoder,
+    ROI pyramid and U-Net both `repeat_num` levels deep, D applied to x and G in separate calls.
+    DeepFashion 256x256, --model=101 (trainer_256.py:31-68): `fgbg=False` (models.GeneratorCNN_ID_Encoder_BodyROIVis,
+    no mask, no background branch), ROI pyramid `repeat_num+1` levels on 64x64 crops, U-Net `repeat_num-1` levels,
+    D applied once to concat([x, G]) (`d_joint`: joint batch statistics, logits split in half afterwards)."""
 
     def __init__(self, img_h=128, img_w=64, hidden=128, z_num=64, roi_size=48, n_parts=7, part_z=32,
-                 keypoints=18, d_dim=64, repeat_num=None):
+                 keypoints=18, d_dim=64, repeat_num=None, fgbg=True, enc_repeat=None, unet_repeat=None, d_joint=False):
         self.img_h, self.img_w, self.hidden, self.z_num = img_h, img_w, hidden, z_num
         self.roi_size, self.n_parts, self.part_z, self.keypoints, self.d_dim = roi_size, n_parts, part_z, keypoints, d_dim
         self.repeat_num = repeat_num if repeat_num is not None else int(math.log2(img_h)) - 2  # trainer.py:75
-        self.emb_dim = n_parts * part_z + 4 * part_z  # 7*32 + 128 = 352 (models.py:464-468)
+        self.fgbg, self.d_joint = fgbg, d_joint
+        self.enc_repeat = enc_repeat if enc_repeat is not None else self.repeat_num
+        self.unet_repeat = unet_repeat if unet_repeat is not None else self.repeat_num
+        # 7*32 + 128 = 352 (models.py:464-468); 7*32 = 224 without the background branch (models.py:384)
+        self.emb_dim = n_parts * part_z + (4 * part_z if fgbg else 0)
+        # D's Linear reads rows of 8*4*8*dim features: `tf.reshape(output, [-1, 8*4*8*dim])` (wgan_gp.py:433) is
+        # hard-wired to the 128x64 geometry, so a 256x256 image yields 8 rows = 8 logits (SURVEY.md q5).  Reduced test
+        # geometries whose whole map is smaller than that keep one row per image.
+        self.d_row = min(8 * 4 * 8 * d_dim, (img_h // 16) * (img_w // 16) * 8 * d_dim)
+
+    @classmethod
+    def deepfashion(cls, img_h=256, img_w=256, hidden=128, roi_size=64, **kw):
+        """--model=101 (trainer_256.py:40-55): encoder repeat_num+1 levels, roi 64, U-Net repeat_num-1 levels."""
+        rn = int(math.log2(img_h)) - 2
+        return cls(img_h=img_h, img_w=img_w, hidden=hidden, roi_size=roi_size, repeat_num=rn, fgbg=False,
+                   enc_repeat=rn + 1, unet_repeat=rn - 1, d_joint=True, **kw)
 
 
 # --------------------------------------------------------------------------------- parameters
@@ -70,28 +94,30 @@ def init_params(cfg, seed=1234, bias_noise=0.0):
     bias_noise > 0 perturbs biases / norm params so tests exercise them."""
     rng = np.random.default_rng(seed)
     p = OrderedDict()
-    hn, rn = cfg.hidden, cfg.repeat_num
-    # ---- Encoder/G_encoder (models.py:390-471), creation order = slim numbering
+    hn, ern, rn = cfg.hidden, cfg.enc_repeat, cfg.unet_repeat
+    # ---- Encoder/G_encoder (models.py:390-471 / 328-388), creation order = slim numbering
     s = _Scope("Encoder/G_encoder", p, rng)
     s.conv(3, 3, hn)
     s.conv(3, hn, hn)
     s.conv(3, hn, hn)
-    for idx in range(rn):
+    for idx in range(ern):
         c = hn * (idx + 1)
         s.conv(3, c, c)
         s.conv(3, c, c)
-        if idx < rn - 1:
+        if idx < ern - 1:
             s.conv(3, c, hn * (idx + 2))
-    roi_final = cfg.roi_size >> (rn - 1)
-    s.fc(roi_final * roi_final * hn * rn, cfg.part_z)
-    for idx in range(rn):
-        c = hn * (idx + 1)
-        s.conv(3, c, c)
-        s.conv(3, c, c)
-        if idx < rn - 1:
-            s.conv(3, c, hn * (idx + 2))
+    roi_final = cfg.roi_size >> (ern - 1)
+    s.fc(roi_final * roi_final * hn * ern, cfg.part_z)
+    if cfg.fgbg:
+        for idx in range(ern):
+            c = hn * (idx + 1)
+            s.conv(3, c, c)
+            s.conv(3, c, c)
+            if idx < ern - 1:
+                s.conv(3, c, hn * (idx + 2))
+        bh, bw = cfg.img_h >> (ern - 1), cfg.img_w >> (ern - 1)
+        s.fc(bh * bw * hn * ern, cfg.part_z * 4)
     fh, fw = cfg.img_h >> (rn - 1), cfg.img_w >> (rn - 1)
-    s.fc(fh * fw * hn * rn, cfg.part_z * 4)
     # ---- ID_AE/G (models.py:518-576)
     s = _Scope("ID_AE/G", p, rng)
     s.conv(3, cfg.emb_dim + cfg.keypoints, hn)
@@ -124,7 +150,7 @@ def init_params(cfg, seed=1234, bias_noise=0.0):
         if i >= 1:
             p["Discriminator.BN%d.offset" % (i + 1)] = np.zeros(chans[i + 1], np.float32)
             p["Discriminator.BN%d.scale" % (i + 1)] = np.ones(chans[i + 1], np.float32)
-    d_in = (cfg.img_h // 16) * (cfg.img_w // 16) * 8 * d  # == 8*4*8*dim at 128x64 (wgan_gp.py:433-434)
+    d_in = cfg.d_row  # 8*4*8*dim (wgan_gp.py:433-434)
     p["Discriminator.Output.W"] = rng.uniform(-lim, lim, size=(d_in, 1)).astype(np.float32)
     p["Discriminator.Output.b"] = np.zeros(1, np.float32)
     if bias_noise > 0:
@@ -205,15 +231,48 @@ def encoder_fgbg(p, cfg, x, fg_mask, roi_bbox, roi_vis, taps=None):
         boxes = torch.stack([bb[:, 0] / float(H), bb[:, 1] / float(W), bb[:, 2] / float(H), bb[:, 3] / float(W)], dim=1)
         rois.append(T.crop_and_resize(x_fg, boxes, torch.arange(B), (cfg.roi_size, cfg.roi_size)))
     body = _tap(taps, "rois", torch.cat(rois, dim=0))
-    body = _pyramid(w, body, cfg.hidden, cfg.repeat_num, taps, "roi")
+    body = _pyramid(w, body, cfg.hidden, cfg.enc_repeat, taps, "roi")
     body = w.fc(body.reshape(body.shape[0], -1))
     feats = list(torch.split(body, B, dim=0))
     for i in range(cfg.n_parts):
         feats[i] = feats[i] * roi_vis[:, i:i + 1].to(x.dtype)
-    bg = _pyramid(w, x_bg, cfg.hidden, cfg.repeat_num, taps, "bg")
+    bg = _pyramid(w, x_bg, cfg.hidden, cfg.enc_repeat, taps, "bg")
     bg = w.fc(bg.reshape(B, -1))
     feats.append(bg)
     return torch.cat(feats, dim=-1)
+
+
+def encoder_roi(p, cfg, x, roi_bbox, roi_vis, taps=None):
+    """models.GeneratorCNN_ID_Encoder_BodyROIVis (models.py:328-388; the DeepFashion encoder, trainer_256.py:40-41):
+    same stem / residual block / 7 ROI crops / shared pyramid / FC / visibility gating as the two-branch encoder,
+    but the crops are taken from the unmasked feature map and there is no background branch.
+    Returns the [B, n_parts*part_z] embedding."""
+    w = _Walker("Encoder/G_encoder", p)
+    B, H, W, _ = x.shape
+    x = w.conv(x)
+    res = x
+    x = w.conv(x)
+    x = w.conv(x)
+    x = _tap(taps, "xs", x + res)
+    rois = []
+    for i in range(cfg.n_parts):
+        bb = roi_bbox[:, i, :].to(x.dtype)
+        boxes = torch.stack([bb[:, 0] / float(H), bb[:, 1] / float(W), bb[:, 2] / float(H), bb[:, 3] / float(W)], dim=1)
+        rois.append(T.crop_and_resize(x, boxes, torch.arange(B), (cfg.roi_size, cfg.roi_size)))
+    body = _tap(taps, "rois", torch.cat(rois, dim=0))
+    body = _pyramid(w, body, cfg.hidden, cfg.enc_repeat, taps, "roi")
+    body = w.fc(body.reshape(body.shape[0], -1))
+    feats = list(torch.split(body, B, dim=0))
+    for i in range(cfg.n_parts):
+        feats[i] = feats[i] * roi_vis[:, i:i + 1].to(x.dtype)
+    return torch.cat(feats, dim=-1)
+
+
+def encoder(p, cfg, batch, taps=None):
+    """The appearance encoder the config selects (trainer.py:581 / trainer_256.py:40)."""
+    if cfg.fgbg:
+        return encoder_fgbg(p, cfg, batch["x"], batch["mask"], batch["part_bbox"], batch["part_vis"], taps)
+    return encoder_roi(p, cfg, batch["x"], batch["part_bbox"], batch["part_vis"], taps)
 
 
 def unet_generator(p, cfg, emb, pose, taps=None):
@@ -222,7 +281,7 @@ def unet_generator(p, cfg, emb, pose, taps=None):
     w = _Walker("ID_AE/G", p)
     B = emb.shape[0]
     H, W = pose.shape[1], pose.shape[2]
-    hn, rn = cfg.hidden, cfg.repeat_num
+    hn, rn = cfg.hidden, cfg.unet_repeat
     emb_rep = emb[:, None, None, :].expand(B, H, W, emb.shape[1])
     x = torch.cat([emb_rep, pose], dim=3)
     x = _tap(taps, "g0", w.conv(x))
@@ -261,7 +320,9 @@ def dcgan_discriminator(p, cfg, x_nhwc, mode="dcgan"):
         h = T.conv2d_same(h, p["Discriminator.%d.Filters" % i], p["Discriminator.%d.Biases" % i], 2)
         h = norm(h, p["Discriminator.BN%d.scale" % i], p["Discriminator.BN%d.offset" % i])
         h = T.leaky_relu(h)
-    flat = h.permute(0, 3, 1, 2).reshape(h.shape[0], -1)  # NCHW flatten: index = c*(h*w) + y*w + x
+    # NCHW flatten (index = c*(h*w) + y*w + x), then tf.reshape(output, [-1, 8*4*8*dim]) (wgan_gp.py:433): one row per
+    # image at 128x64; at 256x256 the 16x16x512 map becomes 8 rows per image (64 channels each), i.e. 8 logits (q5)
+    flat = h.permute(0, 3, 1, 2).reshape(-1, cfg.d_row)
     out = flat @ p["Discriminator.Output.W"] + p["Discriminator.Output.b"]
     return out.reshape(-1)
 
@@ -291,10 +352,14 @@ def stage1_forward(p, cfg, batch, mode="dcgan", gp_alpha=None, lam=10.0, taps=No
     """build_model of --model=1 (trainer.py:568-625).  batch: dict x, pose, mask, part_bbox, part_vis.
     Returns dict with emb, z, G, D_real, D_fake, g_loss (incl. 20*L1), d_loss, L1."""
     x = batch["x"]
-    emb = encoder_fgbg(p, cfg, x, batch["mask"], batch["part_bbox"], batch["part_vis"], taps)
+    emb = encoder(p, cfg, batch, taps)
     G, z = unet_generator(p, cfg, emb, batch["pose"], taps)
-    d_real = dcgan_discriminator(p, cfg, x, mode)
-    d_fake = dcgan_discriminator(p, cfg, G, mode)
+    if cfg.d_joint:   # trainer_256.py:61-66: one call on concat([x, G]) (joint batch statistics), then tf.split(D_z, 2)
+        d_both = dcgan_discriminator(p, cfg, torch.cat([x, G], dim=0), mode)
+        d_real, d_fake = d_both[:d_both.shape[0] // 2], d_both[d_both.shape[0] // 2:]
+    else:             # trainer.py:601-602: two calls
+        d_real = dcgan_discriminator(p, cfg, x, mode)
+        d_fake = dcgan_discriminator(p, cfg, G, mode)
     g_gan, d_loss = T.gan_loss(mode, d_real, d_fake)
     out = dict(emb=emb, z=z, G=G, D_real=d_real, D_fake=d_fake)
     if mode == "wgan-gp" and gp_alpha is not None:
@@ -467,7 +532,7 @@ def sample_factor_forward(p, cfg, batch, z_fg, z_bg, sample_fg, sample_bg, sampl
     C = torch.clamp((g_rcv[:, :, 1] + 1) / 2.0 * W, 0, W - 1)
     pix = torch.stack([R, C, g_rcv[:, :, 2]], dim=-1)
     pose_maps = T.pose_rasterize(pix, H, W, 4)
-    emb = encoder_fgbg(p, cfg, x, batch["mask"], batch["part_bbox"], batch["part_vis"])
+    emb = encoder(p, cfg, batch)
     nfg = cfg.n_parts * cfg.part_z
     app_fg = gaussian_fc_res(p, z_fg, 4, "Gaussian_FC_Fg/G_FC", lambda t: T.leaky_relu(t, 0.2))
     app_bg = gaussian_fc_res(p, z_bg, 4, "Gaussian_FC_Bg/G_FC", lambda t: T.leaky_relu(t, 0.2))

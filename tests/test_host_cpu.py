@@ -67,11 +67,54 @@ def test_engine_and_oracle_agree_on_parameter_names_and_shapes():
         b = nets.init_params(nets.NetConfig(**kw))
         assert list(a.keys()) == list(b.keys())
         assert all(a[k].shape == b[k].shape for k in a)
+    # DeepFashion graph (--model=101): no background branch, 7 / 5 levels, hard-wired 16384-wide D rows
+    for kw in (dict(), dict(img_h=128, img_w=128, hidden=64, roi_size=32)):
+        ec, oc = engine.NetConfig.deepfashion(**kw), nets.NetConfig.deepfashion(**kw)
+        a, b = engine.init_params(ec), nets.init_params(oc)
+        assert list(a.keys()) == list(b.keys())
+        assert all(a[k].shape == b[k].shape for k in a)
+        assert (ec.d_row, ec.d_rows, ec.emb_dim) == (oc.d_row, ec.d_rows, oc.emb_dim)
+    ec = engine.NetConfig.deepfashion()
+    assert (ec.enc_repeat, ec.unet_repeat, ec.emb_dim, ec.d_row, ec.d_rows) == (7, 5, 224, 16384, 8)
+    a = engine.init_params(ec)
+    assert a["Encoder/G_encoder/Conv_22/weights"].shape == (3, 3, 896, 896)      # last ROI level (1x1 pixel maps)
+    assert a["Encoder/G_encoder/fully_connected/weights"].shape == (896, 32)
+    assert a["ID_AE/G/Conv/weights"].shape == (3, 3, 224 + 18, 128)
+    assert a["ID_AE/G/fully_connected/weights"].shape == (16 * 16 * 640, 64)
+    assert "Encoder/G_encoder/fully_connected_1/weights" not in a
     p = engine.init_params(engine.NetConfig())
     w = p["ID_AE/G/Conv_5/weights"]
     lim = np.sqrt(6.0 / (9 * w.shape[2] + 9 * w.shape[3]))       # slim xavier_uniform
     assert np.abs(w).max() <= lim and np.abs(w).max() > 0.95 * lim
     assert np.abs(p["Discriminator.2.Filters"]).max() <= 0.02 * np.sqrt(3.0) + 1e-7
+
+
+def test_launch_programs_record_without_a_device():
+    """Host logic of the engine: buffer geometry and the recorded C-ABI call lists of every graph variant are built
+    on the CPU (no kernel runs; the context handle is absent), so shape / wiring errors surface without a GPU."""
+    from dpig_b200 import _lib, engine
+
+    class NoDeviceCtx:
+        lib, handle = _lib.load(), None
+
+    cases = [(engine.NetConfig(img_h=32, img_w=16, hidden=64, roi_size=12), "dcgan"),
+             (engine.NetConfig(img_h=32, img_w=16, hidden=64, roi_size=12), "wgan-gp"),
+             (engine.NetConfig.deepfashion(img_h=128, img_w=128, hidden=64, roi_size=32), "dcgan")]
+    for cfg, mode in cases:
+        eng = engine.Stage1Engine(NoDeviceCtx(), cfg, 2, mode=mode, device="cpu")
+        names = [c[0] for c in eng.p_bwd_gen.calls]
+        n_conv = sum(1 for v in eng.conv.values() if not v.wname.startswith("Discriminator"))
+        # every Encoder / G convolution gets exactly one filter-gradient launch (the stem's pose rows use _rows)
+        assert names.count("conv2d_bwd_filter") + names.count("conv2d_bwd_filter_rows") == n_conv
+        if cfg.d_joint:
+            assert eng.d_pair.n == 4 and eng.d_real.logits.numel() == 2 * cfg.d_rows == 4
+            assert eng.d_fake.logits.data_ptr() == eng.d_pair.logits.data_ptr() + 4 * 4
+            assert [c[0] for c in eng.p_d_pair_fwd.calls].count("unpack_f32") == 2 * cfg.d_rows
+        else:
+            assert [c[0] for c in eng.p_d_fake_fwd.calls].count("unpack_f32") == 1
+    import pytest
+    with pytest.raises(_lib.DpigError):
+        engine.Stage1Engine(NoDeviceCtx(), cases[2][0], 2, mode="wgan-gp", device="cpu")
 
 
 def test_synthetic_batch_shapes_and_box_rule():

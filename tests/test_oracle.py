@@ -125,3 +125,63 @@ def test_small_stage1_forward_and_grads():
     out, grads = nets.stage1_grads(p, cfg, batch, "d", mode="wgan-gp", gp_alpha=torch.tensor([0.3, 0.8], dtype=torch.float64))
     assert math.isfinite(float(out["d_loss"])) and float(out["gp"]) >= 0
     assert all(g is not None for g in grads.values())
+
+
+def test_deepfashion_encoder_is_the_fg_branch_without_mask():
+    """models.py:328-388 vs 390-471: with an all-ones mask the Fg branch of the two-branch encoder sees the same
+    feature map as the DeepFashion encoder, and both number their shared layers identically (slim auto-naming)."""
+    from dpig_b200 import synth
+    kw = dict(img_h=32, img_w=16, hidden=8, roi_size=12)
+    c2 = nets.NetConfig(**kw)
+    c1 = nets.NetConfig(fgbg=False, **kw)
+    assert c1.emb_dim == 7 * 32 and c2.emb_dim == 7 * 32 + 128
+    p = nets.to_torch(nets.init_params(c2, seed=5, bias_noise=0.05))
+    b = synth.make_batch(2, 32, 16, seed=9)
+    x = torch.tensor(b["x"], dtype=torch.float64)
+    bb, vis = torch.tensor(b["part_bbox"][:, :7]), torch.tensor(b["part_vis"][:, :7])
+    e2 = nets.encoder_fgbg(p, c2, x, torch.ones(2, 32, 16, 1, dtype=torch.float64), bb, vis)
+    e1 = nets.encoder_roi(p, c1, x, bb, vis)
+    assert e1.shape == (2, 224)
+    assert (e1 - e2[:, :224]).abs().max() < 1e-12
+
+
+def test_discriminator_row_quirk_on_large_images():
+    """wgan_gp.py:433 `tf.reshape(output, [-1, 8*4*8*dim])` after the NCHW transpose: a map with R times the
+    128x64 element count becomes R rows per image, row r = channels [r*C/R, (r+1)*C/R) over all pixels."""
+    cfg = nets.NetConfig.deepfashion(img_h=128, img_w=128, hidden=8, roi_size=32, d_dim=8)
+    assert cfg.d_row == 8 * 4 * 8 * 8 and (128 // 16) * (128 // 16) * 64 // cfg.d_row == 2
+    p = nets.to_torch(nets.init_params(cfg, seed=3, bias_noise=0.1))
+    g = torch.Generator().manual_seed(1)
+    x = torch.rand((3, 128, 128, 3), generator=g, dtype=torch.float64) * 2 - 1
+    out = nets.dcgan_discriminator(p, cfg, x, "dcgan")
+    assert out.shape == (6,)
+    # explicit restatement of the last two lines with numpy indexing
+    h = T.leaky_relu(T.conv2d_same(x, p["Discriminator.1.Filters"], p["Discriminator.1.Biases"], 2))
+    for i in (2, 3, 4):
+        h = T.conv2d_same(h, p["Discriminator.%d.Filters" % i], p["Discriminator.%d.Biases" % i], 2)
+        h = T.leaky_relu(T.batchnorm_train(h, p["Discriminator.BN%d.scale" % i], p["Discriminator.BN%d.offset" % i]))
+    hn = h.numpy()                                            # [3, 8, 8, 64]
+    w = p["Discriminator.Output.W"].numpy().reshape(32, 64)   # row index = c' * 64 + (y*8 + x)
+    ref = np.zeros(6)
+    for n in range(3):
+        for r in range(2):
+            blk = hn[n, :, :, r * 32:(r + 1) * 32].reshape(64, 32)     # [pixel, c']
+            ref[n * 2 + r] = (blk.T * w).sum() + float(p["Discriminator.Output.b"][0])
+    assert np.abs(out.numpy() - ref).max() < 1e-10
+
+
+def test_joint_discriminator_call_shares_batch_statistics():
+    """trainer_256.py:61-66: D(concat([x, G])) then tf.split -- differs from two separate calls (trainer.py:601-602)
+    exactly by the BatchNorm statistics."""
+    cfg = nets.NetConfig.deepfashion(img_h=64, img_w=64, hidden=8, roi_size=16, d_dim=8)
+    p = nets.to_torch(nets.init_params(cfg, seed=3, bias_noise=0.1))
+    g = torch.Generator().manual_seed(2)
+    x = torch.rand((2, 64, 64, 3), generator=g, dtype=torch.float64) * 2 - 1
+    y = torch.rand((2, 64, 64, 3), generator=g, dtype=torch.float64) - 0.5
+    joint = nets.dcgan_discriminator(p, cfg, torch.cat([x, y]), "dcgan")
+    sep = torch.cat([nets.dcgan_discriminator(p, cfg, x, "dcgan"), nets.dcgan_discriminator(p, cfg, y, "dcgan")])
+    assert joint.shape == sep.shape and (joint - sep).abs().max() > 1e-3
+    # LayerNorm (wgan-gp) is per sample: there the two agree
+    j2 = nets.dcgan_discriminator(p, cfg, torch.cat([x, y]), "wgan-gp")
+    s2 = torch.cat([nets.dcgan_discriminator(p, cfg, x, "wgan-gp"), nets.dcgan_discriminator(p, cfg, y, "wgan-gp")])
+    assert (j2 - s2).abs().max() < 1e-12
