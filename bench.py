@@ -25,6 +25,7 @@ sys.path.insert(0, ROOT)
 
 METRIC = "images/sec (G+D step) Market-1501 128x64"
 WORKLOAD = "Stage-I Fg/Bg/Pose reconstruction (--model=1, dcgan loss), Market-1501 128x64, batch=64 per GPU"
+WORKLOAD_DF = "Stage-I DeepFashion 256x256 (--model=101, trainer_256.py path, dcgan loss), batch=%d per GPU"
 
 
 def _peaks():
@@ -163,7 +164,9 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--batch", type=int, default=64, help="images per GPU")
+    ap.add_argument("--batch", type=int, default=0, help="images per GPU (default 64; 32 for --workload df256)")
+    ap.add_argument("--workload", default="market", choices=["market", "df256"],
+                    help="market = BASELINE.json configs[1] (the headline); df256 = configs[3], reported on request")
     ap.add_argument("--impl", default="dpig", choices=["dpig", "reference"])
     ap.add_argument("--mode", default="dcgan")
     ap.add_argument("--fast", action="store_true", help="single bf16 pass (NOT parity mode; labelled)")
@@ -189,7 +192,9 @@ def main():
     ctx = dpig_b200.Context(local)
     if args.fast:
         ctx.set_fast_mode(1)
-    cfg = engine.NetConfig()
+    cfg = engine.NetConfig.deepfashion() if args.workload == "df256" else engine.NetConfig()
+    args.batch = args.batch or (32 if args.workload == "df256" else 64)
+    workload = WORKLOAD_DF % args.batch if args.workload == "df256" else WORKLOAD
     eng = engine.Stage1Engine(ctx, cfg, args.batch, mode=args.mode, dist=dist, device="cuda:%d" % local)
     eng.load_params(engine.init_params(cfg, seed=1234))  # identical on every rank (same seed)
 
@@ -290,11 +295,12 @@ def main():
         value = n_img * K / (ms_dev * 1e-3)
         e2e_v = n_img * K / (ms_e2e * 1e-3)
         line = {
-            "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": K, "warmup": W,
+            "metric": METRIC if args.workload == "market" else METRIC.replace("Market-1501 128x64", "DeepFashion 256x256"),
+            "value": value, "unit": "images/s", "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms_dev / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16 hi/lo split x3 MMA, fp32 accumulate (fp32-equivalent)" if not args.fast else "bf16 (fast mode, NOT parity)",
             "data": "synthetic",
-            "config": {"workload": WORKLOAD, "global_batch": n_img, "parallelism": "dp%d" % world,
+            "config": {"workload": workload, "global_batch": n_img, "parallelism": "dp%d" % world,
                        "l2": "working set per iteration (>8 GB of activations) exceeds the 126 MB L2; no flush needed",
                        "schedule": "1 g_optim + 1 d_optim per iteration, separate batches (trainer.py:336-347)"},
             "clocks": clocks,
@@ -303,7 +309,7 @@ def main():
             "gpu_launches": launches,
             "roofline": roofline,
         }
-        if world == 1 and not args.no_cpu_baseline:
+        if world == 1 and not args.no_cpu_baseline and args.workload == "market":
             line["cpu_baseline"] = cpu_baseline()
         print(json.dumps(line), flush=True)
     if dist:

@@ -64,12 +64,15 @@ class DPIG_Encoder_GAN_BodyROI_FgBg(object):
         self.test_dir_name = "test_result"
 
     # ------------------------------------------------------------------ build
+    def _net_config(self):
+        return engine.NetConfig(img_h=self.img_H, img_w=self.img_W, hidden=self.conv_hidden_num, z_num=self.z_num)
+
     def init_net(self):
         """build_model + session setup of the reference (trainer.py:177-215, 568-625)."""
         os.makedirs(self.model_dir, exist_ok=True)
         device = self.dist.local_rank if self.dist is not None else 0
         self.ctx = _lib.Context(device)
-        cfg = engine.NetConfig(img_h=self.img_H, img_w=self.img_W, hidden=self.conv_hidden_num, z_num=self.z_num)
+        cfg = self._net_config()
         self.net = engine.Stage1Engine(self.ctx, cfg, self.batch_size, mode=self.gan_mode, dist=self.dist,
                                        device="cuda:%d" % device)
         self.net.g_lr, self.net.d_lr = self.g_lr, self.d_lr

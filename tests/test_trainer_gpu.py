@@ -1,0 +1,48 @@
+"""GPU tests of the reference's call surface: `main.py --model=N` -> trainer class -> init_net() / train() / test()
+(reference main.py:12-90, trainer.py:326-366, trainer_256.py:95-134) driving the engine for a few steps."""
+import json
+import os
+import sys
+
+import numpy as np
+import pytest
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+pytestmark = pytest.mark.gpu
+
+
+def _run(tmp_path, model, extra):
+    import dpig_b200  # noqa: F401
+    from dpig_b200 import config as C
+    from dpig_b200 import main as M
+    argv = ["--model=%d" % model, "--is_train=True", "--batch_size=2", "--max_step=3", "--log_step=2", "--gpu=-1",
+            "--model_dir=%s" % tmp_path, "--conv_hidden_num=64", "--an_unknown_flag=1"] + extra
+    cfg, unparsed = C.get_config(argv)
+    assert unparsed == ["--an_unknown_flag=1"]          # config.py:96 parse_known_args
+    return M.main(cfg)
+
+
+@pytest.mark.parametrize("model,extra,cls", [
+    (1, ["--img_H=32", "--img_W=16"], "DPIG_Encoder_GAN_BodyROI_FgBg"),
+    (101, ["--img_H=128", "--img_W=128", "--dataset=DF_train_data"], "DPIG_Encoder_GAN_BodyROI_256"),
+])
+def test_main_trains_and_generates(tmp_path, model, extra, cls):
+    tr = _run(tmp_path, model, extra)
+    assert type(tr).__name__ == cls
+    recs = [json.loads(ln) for ln in open(os.path.join(str(tmp_path), "summary.jsonl"))]
+    assert [r["step"] for r in recs] == [0, 1] and all(np.isfinite(r["loss/g_loss"]) for r in recs)
+    assert set(recs[0]) >= {"loss/L1Loss", "loss/g_loss_only", "loss/g_loss", "loss/d_loss", "misc/g_lr", "misc/d_lr"}
+    b = tr.loader.next_batch()
+    g = tr.generate(b["x"], b["x"], b["pose_rcv"], b["part_bbox"], b["part_vis"], mask=b["mask"])
+    assert g.shape == b["x"].shape and g.dtype == np.uint8
+    path = tr.save(2)
+    with np.load(path) as z:
+        assert "Encoder/G_encoder/Conv/weights" in z.files and "Discriminator.Output.W" in z.files
+        if model == 101:
+            assert z["Discriminator.Output.W"].shape == (16384, 1) and "Encoder/G_encoder/fully_connected_1/weights" not in z.files
+
+
+def test_main_rejects_unbuilt_models(tmp_path):
+    with pytest.raises(NotImplementedError):
+        _run(tmp_path, 104, [])
