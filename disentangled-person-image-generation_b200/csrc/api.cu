@@ -54,6 +54,8 @@ extern "C" int dpig_ctx_create(int device, dpig_ctx** out) {
   }
   ctx->encode_tiled = reinterpret_cast<decltype(ctx->encode_tiled)>(fn);
   if (const char* e = getenv("DPIG_CONV_PAIR")) ctx->pair_mode = atoi(e);  // A/B switches for the conv tilings
+  if (const char* e = getenv("DPIG_WGRAD_GROUP")) ctx->wgrad_group = atoi(e);
+  if (const char* e = getenv("DPIG_WGRAD_PX")) ctx->wgrad_px = atoi(e);
   if (const char* e = getenv("DPIG_CONV_STAGES")) ctx->max_stages = atoi(e);
   if (const char* e = getenv("DPIG_CONV_MERGE")) ctx->merge_planes = atoi(e) != 0;
   *out = ctx;

@@ -597,6 +597,11 @@ conv_umma_kernel(const __grid_constant__ ConvUmmaParams p) {
 }
 
 // ------------------------------------------------------------------------------------- wgrad
+// Both operands stream from L2 (every pixel is read once per tap and output-channel tile), and the chip-wide L2 -> SM
+// throughput (~43 B/clk/SM) is what bounds this kernel: one tap with a 256-wide channel block needs 64 B per MMA clock.
+// A CTA therefore owns a GROUP of filter taps (p.group taps, one fp32 accumulator each in TMEM): the dy tile of a
+// pixel step is loaded once and multiplied with the tap-shifted x tiles of every tap of the group
+// (2 taps x 256 columns: 43 B/clk; 3 taps x 128 columns: 57 B/clk instead of 85).
 struct WgradParams {
   CUtensorMap x_map[4][2];
   CUtensorMap dy_map[2];
@@ -606,6 +611,10 @@ struct WgradParams {
   int total_tiles, tiles_per_cta;
   int block_n, n_tiles, cin, cout, stages;
   int cin_pitch;  // rows per tap in the HWIO gradient (>= cin when dw is a row-slice of a wider filter)
+  int num_taps, group;      // taps per CTA (accumulators), blockIdx.y = tap group
+  int px;                   // pixels (GEMM K) per pipeline step: 32 or 64
+  int x_grouped, dy_grouped;  // operand fetched by ONE 5-D TMA per plane (64-channel groups as the 5th box dimension)
+  uint32_t a_bytes;         // one x tile of one plane: 2 boxes of px rows x 128 B
   uint32_t b_bytes, tmem_cols;
   float* dw;
 };
@@ -614,8 +623,10 @@ __global__ void __launch_bounds__(192, 1)
 wgrad_umma_kernel(const __grid_constant__ WgradParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = align1024(smem_raw);
-  const uint32_t b_off = p.planes * kABytes;
-  const uint32_t stage_bytes = p.planes * (kABytes + p.b_bytes);
+  // stage layout: [tap 0: x hi | x lo] ... [tap group-1: x hi | x lo] [dy hi | dy lo]
+  const uint32_t box_bytes = p.px * 128;
+  const uint32_t b_off = p.group * p.planes * p.a_bytes;
+  const uint32_t stage_bytes = p.planes * (p.group * p.a_bytes + p.b_bytes);
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + p.stages * stage_bytes);
   uint64_t* empty = full + p.stages;
   uint64_t* tmem_full = empty + p.stages;
@@ -625,7 +636,8 @@ wgrad_umma_kernel(const __grid_constant__ WgradParams p) {
   const int lane = threadIdx.x & 31;
   const int nt = blockIdx.x % p.n_tiles;  // output-channel tile
   const int mt = blockIdx.x / p.n_tiles;  // input-channel tile (128 wide)
-  const ConvTap tap = p.taps[blockIdx.y];
+  const int tap0 = blockIdx.y * p.group;
+  const int ntap = min(p.group, p.num_taps - tap0);
   const int tile_begin = blockIdx.z * p.tiles_per_cta;
   const int tile_end = min(tile_begin + p.tiles_per_cta, p.total_tiles);
   const int nsteps = tile_end - tile_begin;
@@ -642,7 +654,8 @@ wgrad_umma_kernel(const __grid_constant__ WgradParams p) {
     switch (p.tmem_cols) {
       case 64: ptx::tmem_alloc<64>(tmem_slot); break;
       case 128: ptx::tmem_alloc<128>(tmem_slot); break;
-      default: ptx::tmem_alloc<256>(tmem_slot); break;
+      case 256: ptx::tmem_alloc<256>(tmem_slot); break;
+      default: ptx::tmem_alloc<512>(tmem_slot); break;
     }
   }
   ptx::tc_fence_before();
@@ -663,15 +676,32 @@ wgrad_umma_kernel(const __grid_constant__ WgradParams p) {
           const int w0 = tw * p.PW, h0 = th * p.PH, n0 = tn * p.PN;
           ptx::mbar_wait(&empty[s], ph ^ 1);
           uint8_t* st = smem + s * stage_bytes;
-          ptx::mbar_expect_tx(&full[s], p.planes * (kABytes + p.b_bytes));
-          for (int pl = 0; pl < p.planes; ++pl)
-            for (int j = 0; j < 2; ++j)
-              ptx::tma_load_4d(st + pl * kABytes + j * 8192, &p.x_map[tap.src][pl], &full[s],
-                               mt * 128 + j * 64, w0 + tap.dw, h0 + tap.dh, n0);
-          for (int pl = 0; pl < p.planes; ++pl)
-            for (int j = 0; j < nboxes_b; ++j)
-              ptx::tma_load_4d(st + b_off + pl * p.b_bytes + j * 8192, &p.dy_map[pl], &full[s],
-                               nt * p.block_n + j * 64, w0, h0, n0);
+          ptx::mbar_expect_tx(&full[s], p.planes * (ntap * p.a_bytes + p.b_bytes));
+          // (the kernel is sensitive to the NUMBER of TMA instructions per step, ~200 clk each on one issuing thread:
+          //  a 64-channel box per instruction made 12 per step and capped it at ~55 % of the MMA rate)
+          for (int pl = 0; pl < p.planes; ++pl) {
+            if (p.dy_grouped) {
+              ptx::tma_load_5d(st + b_off + pl * p.b_bytes, &p.dy_map[pl], &full[s], 0, w0, h0, n0,
+                               nt * nboxes_b);
+            } else {
+              for (int j = 0; j < nboxes_b; ++j)
+                ptx::tma_load_4d(st + b_off + pl * p.b_bytes + j * box_bytes, &p.dy_map[pl], &full[s],
+                                 nt * p.block_n + j * 64, w0, h0, n0);
+            }
+          }
+          for (int i = 0; i < ntap; ++i) {
+            const ConvTap tap = p.taps[tap0 + i];
+            for (int pl = 0; pl < p.planes; ++pl) {
+              uint8_t* dst = st + (i * p.planes + pl) * p.a_bytes;
+              if (p.x_grouped) {
+                ptx::tma_load_5d(dst, &p.x_map[tap.src][pl], &full[s], 0, w0 + tap.dw, h0 + tap.dh, n0, mt * 2);
+              } else {
+                for (int j = 0; j < 2; ++j)
+                  ptx::tma_load_4d(dst + j * box_bytes, &p.x_map[tap.src][pl], &full[s], mt * 128 + j * 64,
+                                   w0 + tap.dw, h0 + tap.dh, n0);
+              }
+            }
+          }
           if (++s == p.stages) {
             s = 0;
             ph ^= 1;
@@ -681,25 +711,29 @@ wgrad_umma_kernel(const __grid_constant__ WgradParams p) {
     } else if (warp == 1) {
       if (lane == 0) {
         const uint32_t idesc = ptx::make_idesc_bf16(128, p.block_n, 1, 1);
+        const int ksteps = p.px / 16;  // 16 pixels (K) per MMA = 2 KB of rows
         int s = 0;
         uint32_t ph = 0;
         for (int step = 0; step < nsteps; ++step) {
           ptx::mbar_wait(&full[s], ph);
           ptx::tc_fence_after();
-          const uint32_t a_hi = ptx::smem_u32(smem + s * stage_bytes);
-          const uint32_t a_lo = a_hi + kABytes;
-          const uint32_t b_hi = a_hi + b_off;
+          const uint32_t st = ptx::smem_u32(smem + s * stage_bytes);
+          const uint32_t b_hi = st + b_off;
           const uint32_t b_lo = b_hi + p.b_bytes;
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {  // 16 pixels (K) per MMA = 2 KB of rows
-            const uint64_t da_hi = ptx::make_desc_sw128(a_hi + k * 2048, 8192, 1024);
-            const uint64_t db_hi = ptx::make_desc_sw128(b_hi + k * 2048, 8192, 1024);
-            ptx::umma_bf16(tmem_base, da_hi, db_hi, idesc, (step | k) ? 1u : 0u);
-            if (p.planes == 2) {
-              const uint64_t da_lo = ptx::make_desc_sw128(a_lo + k * 2048, 8192, 1024);
-              const uint64_t db_lo = ptx::make_desc_sw128(b_lo + k * 2048, 8192, 1024);
-              ptx::umma_bf16(tmem_base, da_hi, db_lo, idesc, 1u);
-              ptx::umma_bf16(tmem_base, da_lo, db_hi, idesc, 1u);
+          for (int i = 0; i < ntap; ++i) {
+            const uint32_t a_hi = st + i * p.planes * p.a_bytes;
+            const uint32_t a_lo = a_hi + p.a_bytes;
+            const uint32_t acc = tmem_base + i * p.block_n;
+            for (int k = 0; k < ksteps; ++k) {
+              const uint64_t da_hi = ptx::make_desc_sw128(a_hi + k * 2048, box_bytes, 1024);
+              const uint64_t db_hi = ptx::make_desc_sw128(b_hi + k * 2048, box_bytes, 1024);
+              ptx::umma_bf16(acc, da_hi, db_hi, idesc, (step | k) ? 1u : 0u);
+              if (p.planes == 2) {
+                const uint64_t da_lo = ptx::make_desc_sw128(a_lo + k * 2048, box_bytes, 1024);
+                const uint64_t db_lo = ptx::make_desc_sw128(b_lo + k * 2048, box_bytes, 1024);
+                ptx::umma_bf16(acc, da_hi, db_lo, idesc, 1u);
+                ptx::umma_bf16(acc, da_lo, db_hi, idesc, 1u);
+              }
             }
           }
           ptx::umma_commit(&empty[s]);
@@ -715,16 +749,19 @@ wgrad_umma_kernel(const __grid_constant__ WgradParams p) {
       const int ci = mt * 128 + lg * 32 + lane;
       ptx::mbar_wait(tmem_full, 0);
       ptx::tc_fence_after();
-      for (int c0 = 0; c0 < p.block_n; c0 += 32) {
-        uint32_t v[32];
-        ptx::tmem_ld32(tmem_base + (static_cast<uint32_t>(lg * 32) << 16) + c0, v);
-        ptx::tmem_ld_wait();
-        const int cbase = nt * p.block_n + c0;
-        if (ci < p.cin) {
-          float* o = p.dw + (static_cast<long long>(tap.wtap) * p.cin_pitch + ci) * p.cout + cbase;
+      for (int i = 0; i < ntap; ++i) {
+        const int wtap = p.taps[tap0 + i].wtap;
+        for (int c0 = 0; c0 < p.block_n; c0 += 32) {
+          uint32_t v[32];
+          ptx::tmem_ld32(tmem_base + (static_cast<uint32_t>(lg * 32) << 16) + i * p.block_n + c0, v);
+          ptx::tmem_ld_wait();
+          const int cbase = nt * p.block_n + c0;
+          if (ci < p.cin) {
+            float* o = p.dw + (static_cast<long long>(wtap) * p.cin_pitch + ci) * p.cout + cbase;
 #pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (cbase + i < p.cout) atomicAdd(o + i, __uint_as_float(v[i]));
+            for (int j = 0; j < 32; ++j)
+              if (cbase + j < p.cout) atomicAdd(o + j, __uint_as_float(v[j]));
+          }
         }
       }
     }
@@ -737,7 +774,8 @@ wgrad_umma_kernel(const __grid_constant__ WgradParams p) {
     switch (p.tmem_cols) {
       case 64: ptx::tmem_dealloc<64>(tmem_base); break;
       case 128: ptx::tmem_dealloc<128>(tmem_base); break;
-      default: ptx::tmem_dealloc<256>(tmem_base); break;
+      case 256: ptx::tmem_dealloc<256>(tmem_base); break;
+      default: ptx::tmem_dealloc<512>(tmem_base); break;
     }
   }
 }
@@ -772,7 +810,8 @@ static int encode_map(dpig_ctx* ctx, CUtensorMap* map, const void* base, int ran
 // parity class of it (step = 2, offset = parity).
 // plane_stride_bytes > 0 appends a 5th "plane" dimension of extent 2 (hi, lo) fetched by the same box.
 static int act_map(dpig_ctx* ctx, CUtensorMap* map, const void* plane, const dpig_tensor* t,
-                   int step, int py, int px, int box_w, int box_h, int box_n, long long plane_stride_bytes = 0) {
+                   int step, int py, int px, int box_w, int box_h, int box_n, long long plane_stride_bytes = 0,
+                   int cgroups = 0) {
   const uint64_t ps = static_cast<uint64_t>(t->pix_stride);
   const int W2 = (t->w - px + step - 1) / step;
   const int H2 = (t->h - py + step - 1) / step;
@@ -786,6 +825,14 @@ static int act_map(dpig_ctx* ctx, CUtensorMap* map, const void* plane, const dpi
     uint64_t dims5[5] = {dims[0], dims[1], dims[2], dims[3], 2};
     uint64_t strides4[4] = {strides[0], strides[1], strides[2], static_cast<uint64_t>(plane_stride_bytes)};
     uint32_t box5[5] = {box[0], box[1], box[2], box[3], 2};
+    return encode_map(ctx, map, base, 5, dims5, strides4, box5);
+  }
+  if (cgroups > 0) {
+    // 5th dimension = 64-channel group (128 B apart): one instruction fetches `cgroups` swizzled 64-channel boxes,
+    // laid out one after the other in shared memory (t->c must be a multiple of 64)
+    uint64_t dims5[5] = {64, dims[1], dims[2], dims[3], static_cast<uint64_t>(t->c / 64)};
+    uint64_t strides4[4] = {strides[0], strides[1], strides[2], 128};
+    uint32_t box5[5] = {64, box[1], box[2], box[3], static_cast<uint32_t>(cgroups)};
     return encode_map(ctx, map, base, 5, dims5, strides4, box5);
   }
   return encode_map(ctx, map, base, 4, dims, strides, box);
@@ -1205,9 +1252,27 @@ static int wgrad_impl(dpig_ctx* ctx, const dpig_tensor* x, const dpig_tensor* dy
   const int c64 = (cout + 63) / 64 * 64;
   P.block_n = c64 <= 256 ? c64 : (c64 % 256 == 0 ? 256 : (c64 % 192 == 0 ? 192 : (c64 % 128 == 0 ? 128 : 64)));
   P.n_tiles = (cout + P.block_n - 1) / P.block_n;
-  P.b_bytes = P.block_n * 128;
-  P.tmem_cols = pow2_cols(P.block_n) < 64 ? 64 : pow2_cols(P.block_n);
-  Box b = choose_box(OW, OH, x->n, 64, true);
+  // taps per CTA: as many fp32 accumulators as fit the 512 TMEM columns, balanced over the filter taps
+  // (3x3: 2+2+2+2+1 for 256-wide blocks, 3+3+3 for <= 128-wide blocks); ctx->wgrad_group 0 = auto, else forced.
+  const int ntaps_total = kh * kw;
+  int group = P.block_n > 128 ? 2 : 3;
+  if (ctx->wgrad_group > 0) group = std::min(ctx->wgrad_group, 512 / P.block_n);
+  group = std::max(1, std::min(group, ntaps_total));
+  P.group = group;
+  P.num_taps = ntaps_total;
+  const int tap_groups = (ntaps_total + group - 1) / group;
+  uint32_t cols = pow2_cols(group * P.block_n);
+  P.tmem_cols = cols < 64 ? 64 : cols;
+  // pixels per pipeline step: 64 when >= 2 stages of (group x tiles + dy tile) fit, else 32
+  const int planes_w = (x->lo && dy->lo && !ctx->fast_mode) ? 2 : 1;
+  P.px = 64;
+  if ((ctx->max_smem_optin - 1024 - 256) / (planes_w * (group * 2 * 64 * 128 + P.block_n * 64 * 2)) < 2) P.px = 32;
+  if (ctx->wgrad_px == 32 || ctx->wgrad_px == 64) P.px = ctx->wgrad_px;
+  P.x_grouped = (x->c % 64 == 0 && ctx->merge_planes) ? 1 : 0;
+  P.dy_grouped = (dy->c % 64 == 0 && ctx->merge_planes) ? 1 : 0;
+  P.a_bytes = 2 * P.px * 128;
+  P.b_bytes = (P.block_n / 64) * P.px * 128;
+  Box b = choose_box(OW, OH, x->n, P.px, true);
   P.PW = b.bw;
   P.PH = b.bh;
   P.PN = b.bn;
@@ -1216,20 +1281,20 @@ static int wgrad_impl(dpig_ctx* ctx, const dpig_tensor* x, const dpig_tensor* dy
   const int tiles_n = (x->n + b.bn - 1) / b.bn;
   P.total_tiles = P.tiles_w * P.tiles_h * tiles_n;
   const int m_tiles = (cin + 127) / 128;
-  const int base = m_tiles * P.n_tiles * kh * kw;
+  const int base = m_tiles * P.n_tiles * tap_groups;
   // split-K so that the grid is as close as possible to (but not above) a whole number of waves of the
   // 148 one-CTA-per-SM slots: a grid of 450 CTAs would run 4 rounds with the last one 4 % full.
   int ksplit = 1;
   {
     double best = -1.0;
     const int max_split = std::min(P.total_tiles, std::max(1, 4 * ctx->num_sms / base));
+    const int fixed = 6 * 64 / P.px;   // per-CTA prologue / atomics epilogue, in pipeline steps
     for (int ks = 1; ks <= max_split; ++ks) {
       const int tpc = (P.total_tiles + ks - 1) / ks;
       const int eff_ks = (P.total_tiles + tpc - 1) / tpc;
       const int ctas = base * eff_ks;
       const int rounds = (ctas + ctx->num_sms - 1) / ctx->num_sms;
-      // time ~ rounds * tiles-per-CTA (+ a fixed per-CTA cost of ~6 k-steps for prologue / atomics epilogue)
-      const double cost = static_cast<double>(rounds) * (tpc + 6);
+      const double cost = static_cast<double>(rounds) * (tpc + fixed);
       if (best < 0 || cost < best) {
         best = cost;
         ksplit = eff_ks;
@@ -1265,13 +1330,15 @@ static int wgrad_impl(dpig_ctx* ctx, const dpig_tensor* x, const dpig_tensor* dy
     if (!used[s]) continue;
     for (int pln = 0; pln < P.planes; ++pln)
       if ((rc = act_map(ctx, &P.x_map[s][pln], pln ? x->lo : x->hi, x, stride, stride == 1 ? 0 : s / 2,
-                        stride == 1 ? 0 : s % 2, b.bw, b.bh, b.bn)))
+                        stride == 1 ? 0 : s % 2, b.bw, b.bh, b.bn, 0, P.x_grouped ? 2 : 0)))
         return rc;
   }
   for (int pln = 0; pln < P.planes; ++pln)
-    if ((rc = act_map(ctx, &P.dy_map[pln], pln ? dy->lo : dy->hi, dy, 1, 0, 0, b.bw, b.bh, b.bn))) return rc;
+    if ((rc = act_map(ctx, &P.dy_map[pln], pln ? dy->lo : dy->hi, dy, 1, 0, 0, b.bw, b.bh, b.bn, 0,
+                      P.dy_grouped ? P.block_n / 64 : 0)))
+      return rc;
 
-  const uint32_t stage_bytes = P.planes * (kABytes + P.b_bytes);
+  const uint32_t stage_bytes = P.planes * (P.group * P.a_bytes + P.b_bytes);
   int stages = (ctx->max_smem_optin - 1024 - 256) / stage_bytes;
   if (stages > 6) stages = 6;
   if (stages < 2) return set_error(ctx, DPIG_EUNSUPPORTED, "wgrad tile does not fit shared memory");
@@ -1282,7 +1349,7 @@ static int wgrad_impl(dpig_ctx* ctx, const dpig_tensor* x, const dpig_tensor* dy
     cudaFuncSetAttribute(wgrad_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->max_smem_optin);
     attr_set = true;
   }
-  dim3 grid(m_tiles * P.n_tiles, kh * kw, ksplit);
+  dim3 grid(m_tiles * P.n_tiles, tap_groups, ksplit);
   wgrad_umma_kernel<<<grid, 192, smem, static_cast<cudaStream_t>(stream)>>>(P);
   ctx->launches++;
   return check_launch(ctx, "wgrad_umma_kernel");
