@@ -597,11 +597,14 @@ conv_umma_kernel(const __grid_constant__ ConvUmmaParams p) {
 }
 
 // ------------------------------------------------------------------------------------- wgrad
-// Both operands stream from L2 (every pixel is read once per tap and output-channel tile), and the chip-wide L2 -> SM
-// throughput (~43 B/clk/SM) is what bounds this kernel: one tap with a 256-wide channel block needs 64 B per MMA clock.
-// A CTA therefore owns a GROUP of filter taps (p.group taps, one fp32 accumulator each in TMEM): the dy tile of a
-// pixel step is loaded once and multiplied with the tap-shifted x tiles of every tap of the group
-// (2 taps x 256 columns: 43 B/clk; 3 taps x 128 columns: 57 B/clk instead of 85).
+// A CTA owns a GROUP of filter taps (p.group taps, one fp32 accumulator each in TMEM): the dy tile of a pixel step
+// is loaded once and multiplied with the tap-shifted x tiles of every tap of the group, which cuts the L2 -> SM bytes
+// per FLOP (2 taps x 256 columns: 43 B per MMA clock instead of 64).  Measured on B200 (profiles/r01_wgrad_ab.txt) the
+// kernel was NOT bound by those bytes but by the number of TMA instructions per step (12 x ~200 clk on the one issuing
+// thread): fetching all 64-channel boxes of an operand plane with ONE 5-D TMA (4 per step) took the 256-wide layers
+// from 440 to 477 TFLOP/s algorithmic (= the tensor peak at 3 passes) and the 128-wide ones from 280 to 349; with
+// that, groups of 2 / 3 taps measured 0-8 % slower than one tap per CTA (32-pixel steps are needed to fit two
+// stages), so the default group is 1 and the grouping stays available as a tuning knob (DPIG_WGRAD_GROUP).
 struct WgradParams {
   CUtensorMap x_map[4][2];
   CUtensorMap dy_map[2];
@@ -1252,10 +1255,9 @@ static int wgrad_impl(dpig_ctx* ctx, const dpig_tensor* x, const dpig_tensor* dy
   const int c64 = (cout + 63) / 64 * 64;
   P.block_n = c64 <= 256 ? c64 : (c64 % 256 == 0 ? 256 : (c64 % 192 == 0 ? 192 : (c64 % 128 == 0 ? 128 : 64)));
   P.n_tiles = (cout + P.block_n - 1) / P.block_n;
-  // taps per CTA: as many fp32 accumulators as fit the 512 TMEM columns, balanced over the filter taps
-  // (3x3: 2+2+2+2+1 for 256-wide blocks, 3+3+3 for <= 128-wide blocks); ctx->wgrad_group 0 = auto, else forced.
+  // taps per CTA (one fp32 accumulator each; at most 512 TMEM columns): 1 by default, see the kernel's header
   const int ntaps_total = kh * kw;
-  int group = P.block_n > 128 ? 2 : 3;
+  int group = 1;
   if (ctx->wgrad_group > 0) group = std::min(ctx->wgrad_group, 512 / P.block_n);
   group = std::max(1, std::min(group, ntaps_total));
   P.group = group;
