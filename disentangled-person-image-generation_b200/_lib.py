@@ -81,6 +81,7 @@ _SIGNATURES = {
     "dpig_layernorm_jvp_bwd": [_T, _P, _F, _P, _P, _P, _P, _P, _P, _P, _T, _P, _P],
     "dpig_loss_l1": [_P, _P, _L, _F, _P, _P, _P],
     "dpig_loss_gan": [_I, _P, _P, _I, _P, _P, _P, _P, _P],
+    "dpig_pose_ae_loss": [_P, _P, _P, _I, _I, _F, _P, _P, _P, _P, _P],
     "dpig_gp_interpolate": [_P, _P, _P, _I, _L, _P, _P],
     "dpig_gp_penalty": [_P, _I, _L, _F, _P, _P, _P, _P],
     "dpig_adam_step": [_P, _P, _P, _P, _L, _F, _F, _F, _F, _I, _F, _P],

@@ -80,6 +80,37 @@ __global__ void gan_loss_kernel(int mode, const float* dr, const float* df, int 
   }
 }
 
+// Pose auto-encoder reconstruction loss (trainer.py:638-660, models.py:97-108, 501-515): single block.
+//   vis = round(sigmoid(logit)) with the straight-through gradient of binaryRound,
+//   G_rcv[b,k,:] = (coord[b,2k], coord[b,2k+1], vis[b,k]),  loss = mean((target - G_rcv)^2) over B*K*3.
+__global__ void pose_ae_loss_kernel(const float* target, const float* coord, const float* logit, int B, int K,
+                                    float weight, float* out, float* dcoord, float* dlogit, float* g_rcv) {
+  __shared__ float sh[32];
+  const int total = B * K;
+  const float inv = 1.0f / static_cast<float>(total * 3);
+  float acc = 0.f;
+  for (int i = threadIdx.x; i < total; i += blockDim.x) {
+    const float* t = target + 3 * i;
+    const float r = coord[2 * i], c = coord[2 * i + 1];
+    const float sg = sigm(logit[i]);
+    const float v = rintf(sg);  // tf.round: half to even
+    const float dr = r - t[0], dc = c - t[1], dv = v - t[2];
+    acc += dr * dr + dc * dc + dv * dv;
+    if (dcoord) {
+      dcoord[2 * i] = weight * 2.f * dr * inv;
+      dcoord[2 * i + 1] = weight * 2.f * dc * inv;
+    }
+    if (dlogit) dlogit[i] = weight * 2.f * dv * inv * sg * (1.f - sg);
+    if (g_rcv) {
+      g_rcv[3 * i] = r;
+      g_rcv[3 * i + 1] = c;
+      g_rcv[3 * i + 2] = v;
+    }
+  }
+  const float s = block_sum(acc, sh);
+  if (threadIdx.x == 0) out[0] = s * inv;
+}
+
 __global__ void gp_interp_kernel(const float* x, const float* g, const float* alpha, long long per, long long total,
                                  float* xhat) {
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
@@ -201,6 +232,17 @@ extern "C" int dpig_loss_gan(dpig_ctx* ctx, int32_t mode, const float* d_real, c
                                                                      d_real_d, d_fake_d);
   ctx->launches++;
   return check_launch(ctx, "loss_gan");
+}
+
+extern "C" int dpig_pose_ae_loss(dpig_ctx* ctx, const float* target, const float* coord, const float* vis_logit,
+                                 int32_t batch, int32_t keypoints, float weight, float* out, float* d_coord,
+                                 float* d_vis_logit, float* g_rcv, dpig_stream stream) {
+  DPIG_CHECK_CTX(ctx);
+  if (!target || !coord || !vis_logit || !out) return set_error(ctx, DPIG_EINVAL, "pose_ae_loss: null argument");
+  pose_ae_loss_kernel<<<1, 256, 0, static_cast<cudaStream_t>(stream)>>>(target, coord, vis_logit, batch, keypoints,
+                                                                     weight, out, d_coord, d_vis_logit, g_rcv);
+  ctx->launches++;
+  return check_launch(ctx, "pose_ae_loss");
 }
 
 extern "C" int dpig_gp_interpolate(dpig_ctx* ctx, const float* x, const float* g, const float* alpha, int32_t n,

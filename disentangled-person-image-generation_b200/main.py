@@ -1,5 +1,5 @@
 """Entry point mirroring the reference's main.py:12-90: `--model` id -> trainer class, `--is_train` -> train()/test().
-Implemented: --model=1 (Stage-I Market-1501, the BASELINE hot path), --model=3 / 13 (tester.py), --model=101
+Implemented: --model=1 (Stage-I Market-1501, the BASELINE hot path), --model=2 / 3 / 4 (trainer_sub.py), 13 (tester.py), 101
 (Stage-I DeepFashion 256x256); the other ids raise NotImplementedError naming the reference class they map to."""
 import os
 
@@ -18,6 +18,7 @@ def main(config):
     from . import tester as TE
     from . import trainer as T
     from . import trainer_256 as T256
+    from . import trainer_sub as TS
     if config.gpu > -1:
         os.environ["CUDA_DEVICE_ORDER"] = "PCI_BUS_ID"
         os.environ["CUDA_VISIBLE_DEVICES"] = str(config.gpu)
@@ -25,7 +26,7 @@ def main(config):
     name = _MODEL_CLASSES.get(config.model)
     if name is None:
         raise Exception("unknown --model=%r" % config.model)
-    cls = getattr(T256, name, None) or getattr(T, name, None) or getattr(TE, name, None)   # main.py:4-6 import order (q9)
+    cls = getattr(T256, name, None) or getattr(T, name, None) or getattr(TS, name, None) or getattr(TE, name, None)   # main.py:4-6 import order (q9)
     if cls is None:
         raise NotImplementedError("--model=%d (%s) is outside this round's hot path (SURVEY.md §8f)" % (config.model, name))
     trainer = cls(config)

@@ -66,13 +66,15 @@ class FCTape:
                 p.add("add_f32", ptr(y.data), ptr(a.data), ptr(b.data), y.data.numel(), 1.0, 1.0)
         return p
 
-    def backward_program(self, params=True):
-        """Expects out.grad filled by the caller; all other node grads are zeroed first.  Accumulates parameter
-        gradients when params=True; leaves d(loss)/d(node) in every node's .grad."""
+    def backward_program(self, params=True, outs=None):
+        """Expects the .grad of the output node(s) filled by the caller (`outs`, default: the last op's output); all
+        other node grads are zeroed first.  Accumulates parameter gradients when params=True; leaves d(loss)/d(node)
+        in every node's .grad."""
         p = Program(self.ctx)
         p.keep.append((self.nodes, self.ops, self.group, self.scratch))
-        out = self.ops[-1][2] if self.ops[-1][0] == "linear" else self.ops[-1][3]
-        zero = [nd for nd in self.nodes if nd is not out]
+        if outs is None:
+            outs = [self.ops[-1][2] if self.ops[-1][0] == "linear" else self.ops[-1][3]]
+        zero = [nd for nd in self.nodes if not any(nd is o for o in outs)]
         p.add_py(lambda s: [nd.grad.zero_() for nd in zero])
         for op in reversed(self.ops):
             if op[0] == "linear":
@@ -111,25 +113,38 @@ def fc_critic_specs(name, in_dim, fc_dim=512, n_layers=3):
     return specs
 
 
+def _init_specs(rng, specs, p):
+    """Reference initialisers by variable kind: slim xavier_uniform / zero bias (`.../weights`, `.../biases`); tflib Linear
+    'he' for the critic's LeakyReLULayers (wgan_gp.py:30-32) and glorot for `.Out.` (tflib/ops/linear.py:36-66)."""
+    for name, shape in specs:
+        if name.endswith("weights"):
+            lim = math.sqrt(6.0 / (shape[0] + shape[1]))
+            p[name] = rng.uniform(-lim, lim, size=shape).astype(np.float32)
+        elif name.endswith(".W"):
+            std = math.sqrt(2.0 / (shape[0] + shape[1])) if ".Out." in name else math.sqrt(2.0 / shape[0])
+            p[name] = rng.uniform(-std * math.sqrt(3), std * math.sqrt(3), size=shape).astype(np.float32)
+        else:
+            p[name] = np.zeros(shape, np.float32)
+    return p
+
+
 def init_stage2_params(fg_dim=224, bg_dim=128, seed=4321):
-    """Reference initialisers: slim xavier_uniform / zero bias for the Gaussian FC nets; tflib Linear 'he'
-    (LeakyReLULayer, wgan_gp.py:30-32) and glorot (Out) uniform for the critics (tflib/ops/linear.py:36-66)."""
+    """Gaussian_FC_Fg / Gaussian_FC_Bg samplers and their critics 'Fg_FCDis_' / 'Bg_FCDis_' (trainer.py:752-775)."""
     rng = np.random.default_rng(seed)
     p = OrderedDict()
     for scope, dim, hid in (("Gaussian_FC_Fg/G_FC", fg_dim, 512), ("Gaussian_FC_Bg/G_FC", bg_dim, 256)):
-        for name, shape in fc_res_specs(scope, dim, hid, dim):
-            if name.endswith("weights"):
-                lim = math.sqrt(6.0 / (shape[0] + shape[1]))
-                p[name] = rng.uniform(-lim, lim, size=shape).astype(np.float32)
-            else:
-                p[name] = np.zeros(shape, np.float32)
+        _init_specs(rng, fc_res_specs(scope, dim, hid, dim), p)
     for pre, dim in (("Fg_FCDis_", fg_dim), ("Bg_FCDis_", bg_dim)):
-        for name, shape in fc_critic_specs(pre, dim):
-            if name.endswith(".W"):
-                std = math.sqrt(2.0 / (shape[0] + shape[1])) if ".Out." in name else math.sqrt(2.0 / shape[0])
-                p[name] = rng.uniform(-std * math.sqrt(3), std * math.sqrt(3), size=shape).astype(np.float32)
-            else:
-                p[name] = np.zeros(shape, np.float32)
+        _init_specs(rng, fc_critic_specs(pre, dim), p)
+    return p
+
+
+def init_factor_params(factor, seed=4321):
+    """Random-init parameters of one sampler + critic pair (e.g. PoseGaussian/G_FC + 'Pose_emb_', trainer.py:893-905)."""
+    rng = np.random.default_rng(seed)
+    p = OrderedDict()
+    for grp in (factor.gp, factor.dp):
+        _init_specs(rng, [(n, sp[2]) for n, sp in grp.specs.items()], p)
     return p
 
 
@@ -242,20 +257,119 @@ class _Factor:
         return p
 
 
+def pose_ae_specs(keypoints=18):
+    """slim variable names / shapes of PoseEncoderFCRes + PoseDecoderFCRes inside scope PoseAE (models.py:488-515;
+    trainer.py:637-651): encoder 54 -> 512 -> 4 residual blocks -> 32; decoder 32 -> 512 -> 4 blocks -> (36 | 18)."""
+    specs = fc_res_specs("PoseAE/G_Pose_Encoder", keypoints * 3, 512, 32)
+    dec = [(32, 512)] + [(512, 512)] * 8 + [(512, keypoints * 2), (512, keypoints)]
+    for i, (a, b) in enumerate(dec):
+        name = "PoseAE/G_Pose_Decoder/fully_connected%s" % ("" if i == 0 else "_%d" % i)
+        specs += [(name + "/weights", (a, b)), (name + "/biases", (b,))]
+    return specs
+
+
+def init_pose_ae_params(keypoints=18, seed=777):
+    rng = np.random.default_rng(seed)
+    p = OrderedDict()
+    for name, shape in pose_ae_specs(keypoints):
+        if name.endswith("weights"):
+            lim = math.sqrt(6.0 / (shape[0] + shape[1]))
+            p[name] = rng.uniform(-lim, lim, size=shape).astype(np.float32)
+        else:
+            p[name] = np.zeros(shape, np.float32)
+    return p
+
+
+class PoseAE:
+    """The pose auto-encoder as one FC tape: pose_in [B,54] (normalised r,c,v) -> pose_emb [B,32] -> (coord [B,36],
+    vis_logit [B,18]).  `decoder_in` lets the decoder read another [B,32] node (the sampled embedding of --model=4)."""
+
+    def __init__(self, ctx, batch, device, keypoints=18, group=None, encoder=True, decoder_from=None):
+        self.ctx, self.B, self.K = ctx, batch, keypoints
+        self.group = group or ParamGroup(pose_ae_specs(keypoints), device)
+        names = list(self.group.specs)
+        lay = [(names[2 * i], names[2 * i + 1]) for i in range(len(names) // 2)]
+        enc, dec = lay[:10], lay[10:]
+        t = self.tape = FCTape(ctx, self.group, batch, device)
+        if encoder:
+            self.pose_in = _Node(batch, keypoints * 3, device)
+            h = t.linear(self.pose_in, *enc[0], act=ACT_LRELU)
+            for r in range(4):
+                a = t.linear(h, *enc[1 + 2 * r], act=ACT_LRELU)
+                b = t.linear(a, *enc[2 + 2 * r], act=ACT_LRELU)
+                h = t.add(h, b)
+            self.pose_emb = t.linear(h, *enc[9])
+            src = self.pose_emb
+        else:
+            src = decoder_from
+        h = t.linear(src, *dec[0])
+        for r in range(4):
+            a = t.linear(h, *dec[1 + 2 * r], act=ACT_LRELU)
+            b = t.linear(a, *dec[2 + 2 * r], act=ACT_LRELU)
+            h = t.add(h, b)
+        self.coord = t.linear(h, *dec[9])
+        self.vis_logit = t.linear(h, *dec[10])
+        self.p_fwd = t.forward_program()
+        self.p_bwd = t.backward_program(params=True, outs=[self.coord, self.vis_logit])
+        self.loss = torch.zeros((1,), device=device)
+        self.g_rcv = torch.zeros((batch, keypoints, 3), device=device)
+        self.t = 0
+
+    def load_params(self, params):
+        for name in self.group.specs:
+            if name in params:
+                self.group.view(name).copy_(torch.as_tensor(np.asarray(params[name]), dtype=torch.float32).to(
+                    self.group.value.device))
+
+    def get_params(self, grads=False):
+        return OrderedDict((n, (self.group.gview(n) if grads else self.group.view(n)).detach().cpu().numpy().copy())
+                           for n in self.group.specs)
+
+    @staticmethod
+    def normalise(pose_rcv, img_h, img_w):
+        """(row, col, visible) pixels -> [-1,1] x [-1,1] x {0,1} (trainer.py:639-644)."""
+        return torch.stack([pose_rcv[:, :, 0] / float(img_h) * 2.0 - 1, pose_rcv[:, :, 1] / float(img_w) * 2.0 - 1,
+                            pose_rcv[:, :, 2]], dim=-1)
+
+    def grads(self, weight=20.0):
+        """Forward + reconstruct_loss (trainer.py:658) + backward of loss*weight w.r.t. all PoseAE parameters."""
+        s = torch.cuda.current_stream().cuda_stream
+        self.group.grad.zero_()
+        self.p_fwd.run(s)
+        self.ctx.pose_ae_loss(ptr(self.pose_in.data), ptr(self.coord.data), ptr(self.vis_logit.data), self.B, self.K,
+                              float(weight), ptr(self.loss), ptr(self.coord.grad), ptr(self.vis_logit.grad),
+                              ptr(self.g_rcv), s)
+        self.p_bwd.run(s)
+
+    def step(self, lr, weight=20.0):
+        """g_optim of --model=2: Adam(lr, beta1=0.5) on reconstruct_loss*20 (trainer.py:662-664)."""
+        self.grads(weight)
+        self.t += 1
+        g = self.group
+        self.ctx.adam_step(ptr(g.value), ptr(g.grad), ptr(g.m), ptr(g.v), g.total, lr, 0.5, 0.999, 1e-8, self.t, 1.0,
+                           torch.cuda.current_stream().cuda_stream)
+
+
 class Stage2Engine:
     """--model=3 step on top of a (frozen) Stage-I engine: `g_step(factor)` / `d_step(factor)` with factor in
     {'fg','bg'}; MODE 'wgan' (as shipped), 'lsgan' or 'dcgan' losses."""
 
-    def __init__(self, stage1, mode="wgan", g_lr=2e-5, d_lr=2e-5):
-        self.s1, self.ctx, self.mode, self.g_lr, self.d_lr = stage1, stage1.ctx, mode, g_lr, d_lr
+    def __init__(self, stage1, mode="wgan", g_lr=2e-5, d_lr=2e-5, factors=None):
+        self.s1, self.mode, self.g_lr, self.d_lr = stage1, mode, g_lr, d_lr
         self.gan_mode = GAN_MODES[mode]
-        cfg, B, dev = stage1.cfg, stage1.B, stage1.device
-        self.fg_dim = cfg.n_parts * cfg.part_z
-        self.bg_dim = cfg.part_z * 4
-        self.f = {"fg": _Factor(self.ctx, B, self.fg_dim, 512, "Gaussian_FC_Fg/G_FC", "Fg_FCDis_", dev),
-                  "bg": _Factor(self.ctx, B, self.bg_dim, 256, "Gaussian_FC_Bg/G_FC", "Bg_FCDis_", dev)}
-        self.B = B
         self.lam = 10.0
+        if factors is not None:      # custom factor set (the pose sampler of --model=4); no Stage-I engine needed
+            self.f = factors
+            first = next(iter(factors.values()))
+            self.ctx, self.B = first.ctx, first.B
+        else:
+            self.ctx = stage1.ctx
+            cfg, B, dev = stage1.cfg, stage1.B, stage1.device
+            self.fg_dim = cfg.n_parts * cfg.part_z
+            self.bg_dim = cfg.part_z * 4
+            self.f = {"fg": _Factor(self.ctx, B, self.fg_dim, 512, "Gaussian_FC_Fg/G_FC", "Fg_FCDis_", dev),
+                      "bg": _Factor(self.ctx, B, self.bg_dim, 256, "Gaussian_FC_Bg/G_FC", "Bg_FCDis_", dev)}
+            self.B = B
         if mode == "wgan-gp":
             for f in self.f.values():
                 f.p_gp = f.gp_program(self.lam)
@@ -269,7 +383,7 @@ class Stage2Engine:
         for grp in self.param_groups():
             for name in grp.specs:
                 if name in params:
-                    grp.view(name).copy_(torch.as_tensor(np.asarray(params[name]), dtype=torch.float32).to(self.s1.device))
+                    grp.view(name).copy_(torch.as_tensor(np.asarray(params[name]), dtype=torch.float32).to(grp.value.device))
 
     def get_params(self, grads=False):
         out = OrderedDict()
@@ -283,7 +397,7 @@ class Stage2Engine:
         if z is None:
             f.z.data.normal_(0.0, 0.2)      # tf.random_normal(z_shape, 0.0, 0.2)   models.py:477
         else:
-            f.z.data.copy_(torch.as_tensor(z, dtype=torch.float32).to(self.s1.device))
+            f.z.data.copy_(torch.as_tensor(z, dtype=torch.float32).to(f.z.data.device))
 
     def encode_real(self):
         """Real embeddings of the current Stage-I batch (frozen encoder forward, trainer.py:737-741)."""

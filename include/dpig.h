@@ -280,6 +280,13 @@ int dpig_loss_l1(dpig_ctx* ctx, const float* g, const float* x, int64_t count, f
 int dpig_loss_gan(dpig_ctx* ctx, int32_t mode, const float* d_real, const float* d_fake,
                   int32_t count, float* out, float* d_fake_g, float* d_real_d, float* d_fake_d,
                   dpig_stream stream);
+/* Pose auto-encoder loss of --model=2 (trainer.py:638-660): vis = binaryRound(sigmoid(vis_logit)) (models.py:97-108,
+ * 512-513; straight-through gradient), G_rcv[b,k] = (coord[b,2k], coord[b,2k+1], vis[b,k]) (written to g_rcv, optional),
+ * out[0] = mean((target - G_rcv)^2) over batch*keypoints*3; d_coord / d_vis_logit (optional) receive
+ * weight * d(out)/d(.) (the trainer minimises reconstruct_loss * 20, trainer.py:663). */
+int dpig_pose_ae_loss(dpig_ctx* ctx, const float* target, const float* coord, const float* vis_logit, int32_t batch,
+                      int32_t keypoints, float weight, float* out, float* d_coord, float* d_vis_logit, float* g_rcv,
+                      dpig_stream stream);
 /* WGAN-GP pieces (trainer.py:226-236).  xhat = x + alpha[n]*(g - x) */
 int dpig_gp_interpolate(dpig_ctx* ctx, const float* x, const float* g, const float* alpha,
                         int32_t n, int64_t per_sample, float* xhat, dpig_stream stream);

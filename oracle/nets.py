@@ -454,8 +454,11 @@ def init_stage2_params(fg_dim=224, bg_dim=128, seed=4321, bias_noise=0.0):
 def stage2_losses(p, factor, real, z, mode="wgan"):
     """g_loss_embs / d_loss_embs of one factor (trainer.py:752-775): fake = GaussianFCRes(z) with
     activation_fn=LeakyReLU; critic = FCDiscriminator on real and fake embeddings."""
-    scope = "Gaussian_FC_%s/G_FC" % ("Fg" if factor == "fg" else "Bg")
-    name = "Fg_FCDis_" if factor == "fg" else "Bg_FCDis_"
+    if factor == "pose":     # --model=4: PoseGaussian sampler, critic 'Pose_emb_' (trainer.py:893-910)
+        scope, name = "PoseGaussian/G_FC", "Pose_emb_"
+    else:
+        scope = "Gaussian_FC_%s/G_FC" % ("Fg" if factor == "fg" else "Bg")
+        name = "Fg_FCDis_" if factor == "fg" else "Bg_FCDis_"
     fake = gaussian_fc_res(p, z, repeat_num=4, prefix=scope, act=lambda t: T.leaky_relu(t, 0.2))
     d_real = fc_discriminator(p, real, name=name)
     d_fake = fc_discriminator(p, fake, name=name)
@@ -491,6 +494,27 @@ def pose_decoder_fc_res(p, z, prefix="PoseAE/G_Pose_Decoder", repeat_num=4, act=
     coord = w.fc(x)
     vis = torch.round(torch.sigmoid(w.fc(x)))
     return coord, vis
+
+
+def pose_ae_loss(p, pose_rcv_norm):
+    """reconstruct_loss of --model=2 (trainer.py:638-658): encode, decode, G_pose_rcv = (coord, binaryRound(sigmoid))
+    with the straight-through gradient of binaryRound (models.py:97-108: Round -> Identity), mean squared error over
+    [B,18,3].  Returns (loss, G_pose_rcv)."""
+    B, K = pose_rcv_norm.shape[0], pose_rcv_norm.shape[1]
+    z = pose_encoder_fc_res(p, pose_rcv_norm.reshape(B, -1))
+    act = lambda t: T.leaky_relu(t, 0.2)  # noqa: E731
+    w = _Walker("PoseAE/G_Pose_Decoder", p)
+    x = w.fc(z)
+    for _ in range(4):
+        res = x
+        x = act(w.fc(x))
+        x = act(w.fc(x))
+        x = res + x
+    coord = w.fc(x)
+    sg = torch.sigmoid(w.fc(x))
+    vis = sg + (torch.round(sg) - sg).detach()
+    g = torch.cat([coord.reshape(B, K, 2), vis[:, :, None]], dim=-1)
+    return ((pose_rcv_norm - g) ** 2).mean(), g
 
 
 def init_pose_params(keypoints=18, seed=777, bias_noise=0.0):
