@@ -92,7 +92,7 @@ _SIGNATURES = {
 }
 
 EXPORTS = sorted(list(_SIGNATURES) + ["dpig_ctx_create", "dpig_ctx_destroy", "dpig_last_error",
-                                      "dpig_launch_count", "dpig_version"])
+                                      "dpig_launch_count", "dpig_version", "dpig_crc32c"])
 
 _lib = None
 

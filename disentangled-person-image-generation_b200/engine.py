@@ -446,6 +446,55 @@ class Stage1Engine:
                 out[name] = t.cpu().numpy()
         return out
 
+    def get_state(self):
+        """Everything tf.train.Saver would write for this graph (trainer.py:365-366): the variables plus the optimiser
+        slots under TensorFlow's slot names (`<var>/Adam` = m, `<var>/Adam_1` = v; RMSProp: `<var>/RMSProp` = ms) and the
+        optimisers' step counters as beta-power accumulators (`beta1_power`, `beta2_power` for g_optim; `_1` for d_optim).
+        `Discriminator.BNk.moving_mean / moving_variance` are exported at their never-updated initial values (q4)."""
+        out = self.get_params()
+        rms = self.mode in ("wgan", "lsgan")
+        b2 = 0.9 if self.mode == "wgan-gp" else 0.999
+        for which, grp, suffix in (("g", self.gp, ""), ("d", self.dp, "_1")):
+            for name in grp.specs:
+                off, n, shape = grp.specs[name]
+                m, v = grp.m[off:off + n].view(shape), grp.v[off:off + n].view(shape)
+                if name == "Discriminator.Output.W":
+                    inv = torch.empty_like(self._dperm)
+                    inv[self._dperm] = torch.arange(self.d_flat, device=self.device)
+                    m, v = m.reshape(-1)[inv].reshape(-1, 1), v.reshape(-1)[inv].reshape(-1, 1)
+                if rms:
+                    out[name + "/RMSProp"] = v.cpu().numpy().copy()
+                else:
+                    out[name + "/Adam"] = m.cpu().numpy().copy()
+                    out[name + "/Adam_1"] = v.cpu().numpy().copy()
+            if not rms:
+                out["beta1_power" + suffix] = np.float32(0.5 ** (self.t[which] + 1))
+                out["beta2_power" + suffix] = np.float32(b2 ** (self.t[which] + 1))
+        for i in (2, 3, 4):
+            c = self.cfg.d_dim << (i - 1)
+            out["Discriminator.BN%d.moving_mean" % i] = np.zeros(c, np.float32)
+            out["Discriminator.BN%d.moving_variance" % i] = np.ones(c, np.float32)
+        return out
+
+    def load_state(self, state):
+        """Inverse of get_state(): variables by name (missing names keep their value), optimiser slots and step counters
+        when present (a full `--ckpt_path` restore resumes Adam exactly, trainer.py:211-213)."""
+        self.load_params(state)
+        rms = self.mode in ("wgan", "lsgan")
+        b2 = 0.9 if self.mode == "wgan-gp" else 0.999
+        for which, grp, suffix in (("g", self.gp, ""), ("d", self.dp, "_1")):
+            for name in grp.specs:
+                off, n, shape = grp.specs[name]
+                for slot, arena in ((("/RMSProp", grp.v),) if rms else (("/Adam", grp.m), ("/Adam_1", grp.v))):
+                    if name + slot in state:
+                        t = torch.as_tensor(np.asarray(state[name + slot]), dtype=torch.float32).to(self.device)
+                        if name == "Discriminator.Output.W":
+                            t = t.reshape(-1)[self._dperm].reshape(-1, 1)
+                        arena[off:off + n].view(shape).copy_(t.reshape(shape))
+            key = "beta2_power" + suffix
+            if not rms and key in state and 0.0 < float(state[key]) < 1.0:
+                self.t[which] = max(0, int(round(math.log(float(state[key])) / math.log(b2))) - 1)
+
     def pack_weights(self, which, stream=None):
         s = stream if stream is not None else torch.cuda.current_stream().cuda_stream
         for name, layer in self.conv.items():

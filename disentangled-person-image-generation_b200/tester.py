@@ -12,7 +12,7 @@ import os
 import numpy as np
 import torch
 
-from . import _lib, engine, stage2, synth
+from . import _lib, engine, stage2, synth, tf_checkpoint
 from ._lib import ACT_LRELU, ACT_NONE
 from .tensor import ptr
 from .trainer import SyntheticLoader
@@ -73,9 +73,12 @@ class DPIG_FourNetsFgBg_testOnlySampleFactor(object):
         self.pose_coord = t.linear(h, *dec[9])
         self.pose_vis_logit = t.linear(h, *dec[10])
         self.p_pose = t.forward_program()
-        if self.pretrained_path:
-            with np.load(self.pretrained_path) as z:
-                self.load_params({k: z[k] for k in z.files})
+        # the four partial restores of tester.py:423-472 (Encoder+ID_AE, Gaussian_FC_*, PoseAE, Discriminator.): any of
+        # --pretrained_path, --pretrained_appSample_path, --pretrained_poseAE_path (TensorFlow V2 checkpoints or .npz)
+        for path in (self.pretrained_path, getattr(self.config, "pretrained_appSample_path", None),
+                     getattr(self.config, "pretrained_poseAE_path", None)):
+            if path:
+                self.load_params(tf_checkpoint.load_any(path))
 
     def load_params(self, params):
         """Parameters by TF variable name: Encoder/..., ID_AE/..., Discriminator.*, Gaussian_FC_Fg/..., Gaussian_FC_Bg/...,

@@ -7,9 +7,10 @@
 is replaced by engine.Stage1Engine (static launch programs over the C ABI).  Scalar names of the summaries are
 kept (`loss/L1Loss`, `loss/g_loss`, ...) and written as JSON lines instead of TF event files.
 
-Not reproduced this round: the TFRecord input pipeline (datasets/market1501.py) -- batches come from
-synth.make_batch unless a loader object with `next_batch()` is supplied -- and tf.train.Saver checkpoints
-(parameters are saved as .npz keyed by the TF variable names).
+Checkpoints are TensorFlow V2 bundles written / read without TensorFlow (tf_checkpoint.py), keyed by the reference's
+variable names, so `--pretrained_path` / `--ckpt_path` accept the reference's checkpoints and vice versa.
+Not reproduced: the TFRecord input pipeline (datasets/market1501.py) -- batches come from synth.make_batch unless a
+loader object with `next_batch()` is supplied.
 """
 import json
 import os
@@ -18,7 +19,7 @@ import time
 import numpy as np
 import torch
 
-from . import _lib, engine, synth
+from . import _lib, engine, synth, tf_checkpoint
 from .tensor import ptr
 
 
@@ -76,12 +77,13 @@ class DPIG_Encoder_GAN_BodyROI_FgBg(object):
         self.net = engine.Stage1Engine(self.ctx, cfg, self.batch_size, mode=self.gan_mode, dist=self.dist,
                                        device="cuda:%d" % device)
         self.net.g_lr, self.net.d_lr = self.g_lr, self.d_lr
-        params = engine.init_params(cfg, seed=self.config.random_seed)
-        for path in (self.pretrained_path, self.ckpt_path):     # partial / full restore by variable name
-            if path:
-                with np.load(path) as z:
-                    params.update({k: z[k] for k in z.files if k in params})
-        self.net.load_params(params)
+        self.net.load_params(engine.init_params(cfg, seed=self.config.random_seed))
+        # tf.train.Saver restores (trainer.py:180-213): --pretrained_path = the Encoder + ID_AE scopes only,
+        # --ckpt_path = everything incl. the optimiser slots.  TensorFlow V2 checkpoints (prefix or directory) or .npz.
+        if self.pretrained_path:
+            self.net.load_params(tf_checkpoint.load_any(self.pretrained_path, scopes=["Encoder", "ID_AE"]))
+        if self.ckpt_path:
+            self.net.load_state(tf_checkpoint.load_any(self.ckpt_path))
         self._log = open(os.path.join(self.model_dir, "summary.jsonl"), "a")
 
     # ------------------------------------------------------------------ train
@@ -114,9 +116,12 @@ class DPIG_Encoder_GAN_BodyROI_FgBg(object):
         torch.cuda.synchronize()
 
     def save(self, step):
-        path = os.path.join(self.model_dir, "model.ckpt-%d.npz" % step)
-        np.savez(path, **self.net.get_params())
-        return path
+        """saver.save(sess, model_dir/model.ckpt, global_step=step) (trainer.py:365-366): a TensorFlow V2 checkpoint
+        (model.ckpt-<step>.index / .data-00000-of-00001 + the `checkpoint` state file) readable by the reference."""
+        state = self.net.get_state()
+        state["step"] = np.int32(step)
+        state["g_lr"], state["d_lr"] = np.float32(self.net.g_lr), np.float32(self.net.d_lr)
+        return tf_checkpoint.save_checkpoint(os.path.join(self.model_dir, "model.ckpt-%d" % step), state)
 
     # ------------------------------------------------------------------ inference
     def generate(self, x, x_target, pose, part_bbox, part_vis, root_path=None, path=None, idx=None, save=False,

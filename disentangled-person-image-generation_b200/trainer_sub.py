@@ -12,7 +12,7 @@
 
 `__init__(config)`, `init_net()`, `train()`, `test()`, `generate(...)` keep the reference's meaning; every FC layer runs
 through the C ABI (dpig_linear_fwd/bwd, dpig_pose_ae_loss, dpig_loss_gan, dpig_rmsprop_step / dpig_adam_step).
-Checkpoints are .npz files keyed by the TF variable names (partial restores by scope as in trainer.py:180-213).
+Checkpoints are TensorFlow V2 bundles (tf_checkpoint.py) keyed by the TF variable names; restores are by name.
 """
 import json
 import os
@@ -21,18 +21,24 @@ import time
 import numpy as np
 import torch
 
-from . import _lib, engine, stage2
+from . import _lib, engine, stage2, tf_checkpoint
 from .tensor import ptr
 from .trainer import DPIG_Encoder_GAN_BodyROI_FgBg
 
 
 def _load_npz(paths):
+    """Variables of every given checkpoint (TensorFlow V2 prefix / directory or .npz), later paths winning."""
     out = {}
     for path in paths:
         if path:
-            with np.load(path) as z:
-                out.update({k: z[k] for k in z.files})
+            out.update(tf_checkpoint.load_any(path))
     return out
+
+
+def _save(model_dir, step, tensors):
+    tensors = dict(tensors)
+    tensors["step"] = np.int32(step)
+    return tf_checkpoint.save_checkpoint(os.path.join(model_dir, "model.ckpt-%d" % step), tensors)
 
 
 class DPIG_PoseRCV_AE_BodyROI(DPIG_Encoder_GAN_BodyROI_FgBg):
@@ -74,9 +80,7 @@ class DPIG_PoseRCV_AE_BodyROI(DPIG_Encoder_GAN_BodyROI_FgBg):
         torch.cuda.synchronize()
 
     def save(self, step):
-        path = os.path.join(self.model_dir, "model.ckpt-%d.npz" % step)
-        np.savez(path, **self.pose_ae.get_params())
-        return path
+        return _save(self.model_dir, step, self.pose_ae.get_params())
 
     def generate(self, pose_rcv):
         """Reconstructed keypoints G_pose_rcv [B,18,3] (normalised r, c and the binary visibility)."""
@@ -135,11 +139,9 @@ class DPIG_Encoder_subSampleAppNetFgBg_GAN_BodyROI(DPIG_Encoder_GAN_BodyROI_FgBg
         torch.cuda.synchronize()
 
     def save(self, step):
-        path = os.path.join(self.model_dir, "model.ckpt-%d.npz" % step)
         d = self.net.get_params()
         d.update(self.s2.get_params())
-        np.savez(path, **d)
-        return path
+        return _save(self.model_dir, step, d)
 
     def generate(self, x, x_target, pose, part_bbox, part_vis, root_path=None, path=None, idx=None, save=False,
                  mask=None, z_fg=None, z_bg=None):
@@ -225,11 +227,9 @@ class DPIG_subnetSamplePoseRCV_GAN_BodyROI(DPIG_PoseRCV_AE_BodyROI):
         torch.cuda.synchronize()
 
     def save(self, step):
-        path = os.path.join(self.model_dir, "model.ckpt-%d.npz" % step)
         d = self.pose_ae.get_params()
         d.update(self.s2.get_params())
-        np.savez(path, **d)
-        return path
+        return _save(self.model_dir, step, d)
 
     def sample_pose_rcv(self, z=None):
         """G_pose_rcv [B,18,3]: noise -> PoseGaussian -> PoseDecoderFCRes -> (r, c in [-1,1], binary visibility)."""

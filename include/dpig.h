@@ -316,6 +316,12 @@ int dpig_pose_rasterize(dpig_ctx* ctx, const float* rcv, int32_t n, int32_t k, i
                         int32_t w_, int32_t radius, const dpig_tensor* out, float* out_f32,
                         dpig_stream stream);
 
+/* ---- host utility ------------------------------------------------------------------------------ */
+/* CRC-32C (Castagnoli) of a HOST buffer, chained through `crc` (start with 0): the checksum TensorFlow's checkpoint
+ * format stores per tensor and per index block (tf.train.Saver, reference trainer.py:180-213, 365-366); used by the
+ * TensorFlow-free checkpoint reader / writer tf_checkpoint.py.  No context, no device work. */
+uint32_t dpig_crc32c(uint32_t crc, const void* data, size_t n);
+
 #ifdef __cplusplus
 }
 #endif

@@ -103,8 +103,9 @@ def test_main_model2_pose_autoencoder(tmp_path):
     assert all(np.isfinite(r["loss/reconstruct_loss"]) for r in recs)
     g = tr.generate(tr.loader.next_batch()["pose_rcv"])
     assert g.shape == (4, 18, 3) and set(np.unique(g[:, :, 2])) <= {0.0, 1.0}
-    with np.load(tr.save(2)) as z:
-        assert "PoseAE/G_Pose_Encoder/fully_connected/weights" in z.files and len(z.files) == 42
+    from dpig_b200 import tf_checkpoint
+    z = tf_checkpoint.load_checkpoint(tr.save(2))
+    assert "PoseAE/G_Pose_Encoder/fully_connected/weights" in z and len(z) == 42 + 1 and int(z["step"]) == 2
 
 
 def test_main_model3_appearance_samplers(tmp_path):
@@ -134,5 +135,6 @@ def test_main_model4_pose_sampler(tmp_path):
     b = tr.loader.next_batch()
     g = tr.generate(b["x"], b["x"], b["pose_rcv"], b["part_bbox"], part_vis=b["part_vis"], mask=b["mask"])
     assert g.shape == (4, 32, 16, 3) and g.dtype == np.uint8
-    with np.load(tr.save(2)) as z:
-        assert "PoseGaussian/G_FC/fully_connected/weights" in z.files and "Pose_emb_Discriminator.Out.W" in z.files
+    from dpig_b200 import tf_checkpoint
+    z = tf_checkpoint.CheckpointReader(tr.save(2))
+    assert z.has_tensor("PoseGaussian/G_FC/fully_connected/weights") and z.has_tensor("Pose_emb_Discriminator.Out.W")

@@ -36,11 +36,25 @@ def test_main_trains_and_generates(tmp_path, model, extra, cls):
     b = tr.loader.next_batch()
     g = tr.generate(b["x"], b["x"], b["pose_rcv"], b["part_bbox"], b["part_vis"], mask=b["mask"])
     assert g.shape == b["x"].shape and g.dtype == np.uint8
-    path = tr.save(2)
-    with np.load(path) as z:
-        assert "Encoder/G_encoder/Conv/weights" in z.files and "Discriminator.Output.W" in z.files
-        if model == 101:
-            assert z["Discriminator.Output.W"].shape == (16384, 1) and "Encoder/G_encoder/fully_connected_1/weights" not in z.files
+    # saver.save -> TensorFlow V2 checkpoint; a second trainer resumes from it (--ckpt_path) incl. the Adam slots
+    from dpig_b200 import tf_checkpoint
+    prefix = tr.save(2)
+    z = tf_checkpoint.CheckpointReader(prefix)
+    assert z.has_tensor("Encoder/G_encoder/Conv/weights") and z.has_tensor("Discriminator.Output.W")
+    assert z.has_tensor("ID_AE/G/Conv_3/weights/Adam_1") and z.has_tensor("beta1_power_1") and int(z.get_tensor("step")) == 2
+    if model == 101:
+        assert z.get_variable_to_shape_map()["Discriminator.Output.W"] == [16384, 1]
+        assert not z.has_tensor("Encoder/G_encoder/fully_connected_1/weights")
+    import copy
+    from dpig_b200 import main as M
+    cfg2 = copy.copy(tr.config)
+    cfg2.ckpt_path, cfg2.max_step, cfg2.model_dir = str(tmp_path), 0, str(tmp_path / "resumed")
+    tr2 = M.main(cfg2)
+    a, b2 = tr.net.get_state(), tr2.net.get_state()
+    assert set(a) == set(b2)
+    for k in a:
+        assert np.array_equal(np.asarray(a[k]), np.asarray(b2[k])), k
+    assert tr2.net.t == tr.net.t
 
 
 def test_main_rejects_unbuilt_models(tmp_path):
