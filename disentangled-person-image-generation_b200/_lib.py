@@ -58,6 +58,9 @@ _SIGNATURES = {
     "dpig_conv2d_small_fwd": [_P, _I, _I, _I, _I, _P, _P, _I, _I, _I, _I, _I, _F, _T, _P, _P, _P],
     "dpig_conv2d_small_bwd_data": [_P, _I, _I, _I, _I, _P, _I, _I, _I, _I, _I, _I, _P, _P],
     "dpig_conv2d_small_bwd_filter": [_P, _I, _I, _I, _I, _P, _I, _I, _I, _I, _P, _P],
+    "dpig_im2col_small": [_T, _I, _I, _I, _I, _I, _T, _P],
+    "dpig_col2im_small": [_P, _L, _I, _I, _I, _I, _I, _I, _P, _P, _L, _T, _P],
+    "dpig_permute_taps": [_P, _P, _I, _I, _I, _I, _P],
     "dpig_bias_grad": [_T, _P, _P],
     "dpig_bias_grad_f32": [_P, _L, _I, _P, _P],
     "dpig_ew_combine": [_T, _T, _T, _T, _P, _L, _P, _F, _I, _P],

@@ -117,6 +117,34 @@ class ConvLayer:
         return self.group.gview(self.bname)
 
 
+class PatchLayer:
+    """A convolution whose 3-channel side has been folded into the channel dimension (csrc/patch.cu), seen as a 1x1
+    layer by conv_fwd / conv_wgrad: `master` is the fp32 [cin][cout] matrix the bf16 operand copy is packed from --
+    for a cin = 3 layer the HWIO filter itself ([k*k*3][cout]), for the cout = 3 layer a re-laid copy."""
+
+    def __init__(self, base, cin, cout, device, master=None, cout_launch=None):
+        self.base, self.group, self.wname, self.bname = base, base.group, base.wname, base.bname
+        self.k, self.stride, self.cin, self.rows = 1, 1, cin, cout
+        # cout_launch > cout: the conv is launched with zero-padded output columns so that its epilogue takes the
+        # whole-32-channel (coalesced) path; the extra weight rows stay zero
+        self.cout = cout_launch or cout
+        self.flops_cout = cout
+        self.cin_pad, self.cout_pad = _pad8(cin), _pad8(self.cout)
+        self.small, self.bwd = False, None
+        self.fwd = torch.zeros((2, 1, self.cout, self.cin_pad), dtype=torch.bfloat16, device=device)
+        self.master = master        # None: base.w
+
+    w = property(lambda self: self.base.w)
+    b = property(lambda self: self.base.b)
+    dw = property(lambda self: self.base.dw)
+    db = property(lambda self: self.base.db)
+
+    def pack(self, ctx, stream):
+        src = self.master if self.master is not None else self.base.w
+        ctx.weight_pack(ptr(src), 1, self.cin, self.rows, self.cin_pad, _pad8(self.rows), ptr(self.fwd[0]),
+                        ptr(self.fwd[1]), None, None, stream)
+
+
 class Program:
     """A recorded list of C-ABI calls; run() replays it on the given stream."""
 
@@ -244,6 +272,7 @@ class _DiscPass:
         d = cfg.d_dim
         H, W = cfg.img_h, cfg.img_w
         self.n, self.segs = n, segs
+        self.patch = SplitTensor(n, H >> 1, W >> 1, _pad8(5 * 5 * 3), dev)   # im2col of the image (layer 1 as a 1x1 GEMM)
         self.h = [SplitTensor(n, H >> (i + 1), W >> (i + 1), d << i, dev) for i in range(4)]   # activated outputs
         self.m = [_mask(n * (H >> (i + 1)) * (W >> (i + 1)), d << i, dev) for i in range(4)]
         self.pre = [None] + [torch.zeros((n, H >> (i + 1), W >> (i + 1), d << i), device=dev) for i in (1, 2, 3)]
@@ -411,6 +440,15 @@ class Stage1Engine:
             else:
                 self.conv[name] = ConvLayer(self.gp, name + "/weights", name + "/biases", s["k"], s["stride"], s["cin"],
                                             s["cout"], dev, s["need_bwd"], s["small"], s["cin_pad"])
+        # 3-channel ends as 1x1 contractions over (tap, channel) patches (csrc/patch.cu)
+        e0, d1, go = self.conv[self.n_e0], self.conv[self.n_d[0]], self.conv[self.n_gout]
+        self.e0_patch = PatchLayer(e0, 9 * 3, hn, dev)
+        self.d1_patch = PatchLayer(d1, 25 * 3, d, dev)
+        self.gout_wf = torch.zeros((go.cin, 27), device=dev)      # [ci][tap*3+co]  forward: 1x1 conv to 27 tap channels
+        self.gout_wd = torch.zeros((27, go.cin), device=dev)      # [tap*3+co][ci]  data gradient: 1x1 conv from dy patches
+        self.gout_dwv = torch.zeros((go.cin, 27), device=dev)     # filter gradient in the forward layout
+        self.gout_f = PatchLayer(go, go.cin, 27, dev, master=self.gout_wf, cout_launch=32)
+        self.gout_d = PatchLayer(go, 27, go.cin, dev, master=self.gout_wd)
         # BN / LN scale defaults to one
         for i in (2, 3, 4):
             self.dp.view("Discriminator.BN%d.scale" % i).fill_(1.0)
@@ -509,6 +547,15 @@ class Stage1Engine:
                                  ptr(layer.fwd[0]), ptr(layer.fwd[1]),
                                  ptr(layer.bwd[0]) if layer.bwd is not None else None,
                                  ptr(layer.bwd[1]) if layer.bwd is not None else None, s)
+        if which == "d":
+            self.d1_patch.pack(self.ctx, s)
+        else:
+            self.e0_patch.pack(self.ctx, s)
+            go = self.gout_f.base
+            self.ctx.permute_taps(ptr(go.w), ptr(self.gout_wf), 9, go.cin, 3, 0, s)
+            self.ctx.permute_taps(ptr(go.w), ptr(self.gout_wd), 9, go.cin, 3, 1, s)
+            self.gout_f.pack(self.ctx, s)
+            self.gout_d.pack(self.ctx, s)
 
     # -------------------------------------------------------------------------------- buffers
     def _build_buffers(self):
@@ -528,6 +575,7 @@ class Stage1Engine:
         self.box_ind = (torch.arange(P * B, device=dev, dtype=torch.int32) % B).contiguous()
         self.vis = torch.zeros((B, P), device=dev)
         # encoder
+        self.x_patch = SplitTensor(B, H, W, _pad8(27), dev)     # im2col of the image: the stem as a 1x1 GEMM
         self.e0 = SplitTensor(B, H, W, hn, dev)
         self.me0 = _mask(B * H * W, hn, dev)
         self.e1 = SplitTensor(B, H, W, hn, dev)
@@ -583,6 +631,8 @@ class Stage1Engine:
             if idx < rn - 1:
                 self.dec_mu.append(_mask(B * hh * ww, self.dec_c[idx + 1][0], dev))
         self.G = torch.zeros((B, H, W, 3), device=dev)
+        self.gout_y = torch.zeros((B, H, W, 32), device=dev)    # per-tap partial outputs of the 256 -> 3 conv
+        self.gG_patch = SplitTensor(B, H, W, 32, dev)           # transposed patches of dL/dG
         self.G8 = self.pair8.batch_slice(B, B) if cfg.d_joint else SplitTensor(B, H, W, 8, dev, zero=True)
         # generator backward
         self.g_G = torch.zeros((B, H, W, 3), device=dev)
@@ -637,6 +687,7 @@ class Stage1Engine:
         self.xhat8 = SplitTensor(B, H, W, 8, dev, zero=True)
         self.gp_v = torch.zeros((B, H, W, 3), device=dev)
         self.gp_v8 = SplitTensor(B, H, W, 8, dev, zero=True)
+        self.gp_v_patch = SplitTensor(B, H >> 1, W >> 1, _pad8(75), dev)
         self.slopes = torch.zeros((B,), device=dev)
         self.ones_b = torch.ones((B,), device=dev)
         dh = self.d_hat = _DiscPass(self, B)
@@ -694,7 +745,8 @@ class Stage1Engine:
         assert x.c == layer.cin_pad, (layer.wname, x.c, layer.cin_pad)
         oh, ow = -(-x.h // layer.stride), -(-x.w // layer.stride)
         prog.add("conv2d_fwd", x.ref(), ptr(layer.fwd[0]), ptr(layer.fwd[1]), layer.k, layer.k, layer.stride, layer.cout, ep,
-                 flops=2.0 * x.n * oh * ow * layer.cout * layer.k * layer.k * getattr(layer, "flops_cin", layer.cin),
+                 flops=2.0 * x.n * oh * ow * getattr(layer, "flops_cout", layer.cout) * layer.k * layer.k *
+                 getattr(layer, "flops_cin", layer.cin),
                  tag="%s %dx%dx%dx%d->%d k%ds%d" % (layer.wname, x.n, x.h, x.w, getattr(layer, "flops_cin", layer.cin),
                                                     layer.cout, layer.k, layer.stride))
 
@@ -776,7 +828,9 @@ class Stage1Engine:
         p.add("gp_penalty", ptr(dh.g_x), B, per, float(self.lam), ptr(self.slopes), ptr(self.loss_gp), ptr(self.gp_v))
         p.add("pack_f32", ptr(self.gp_v), 3, 3, self.gp_v8.ref())
         # ---- tangent (JVP) forward along v
-        self.conv_fwd(p, L[0], self.gp_v8, act=ACT_NONE, bias=False, out_masked=dh.hd[0], mask_in=dh.m[0], mask_neg=0.2)
+        p.add("im2col_small", self.gp_v8.ref(), 3, 5, 5, 2, 0, self.gp_v_patch.ref())
+        self.conv_fwd(p, self.d1_patch, self.gp_v_patch, act=ACT_NONE, bias=False, out_masked=dh.hd[0], mask_in=dh.m[0],
+                      mask_neg=0.2)
         for i in (1, 2, 3):
             hh, ww, c = H >> (i + 1), W >> (i + 1), d << i
             sc = self.dp.view("Discriminator.BN%d.scale" % (i + 1))
@@ -818,8 +872,8 @@ class Stage1Engine:
                 self.conv_dgrad(p, L[i], dh.pbar[i], hh * 2, ww * 2, out=dh.hbar[i - 1])
             else:
                 self.conv_dgrad(p, L[i], dh.pbar[i], hh * 2, ww * 2, out_masked=dh.pbar[0], mask_in=dh.m[0], mask_neg=0.2)
-        self.conv_wgrad(p, L[0], self.xhat8, dh.pbar[0])
-        self.conv_wgrad(p, L[0], self.gp_v8, dh.pdbar[0], bias=False)
+        self.conv_wgrad(p, self.d1_patch, dh.patch, dh.pbar[0])
+        self.conv_wgrad(p, self.d1_patch, self.gp_v_patch, dh.pdbar[0], bias=False)
 
     def _prog_forward_generator(self, p):
         self._prog_forward_encoder(p)
@@ -847,7 +901,8 @@ class Stage1Engine:
         e0, e1, e2 = self.conv[self.n_e0], self.conv[self.n_e1], self.conv[self.n_e2]
         # ---- encoder (models.py:396-471; without the mask / background branch: models.py:334-384)
         p.add("pack_f32", ptr(self.x), 3, 3, self.x8.ref())
-        self.conv_fwd(p, e0, self.x8, out=self.e0, mask_out=self.me0)
+        p.add("im2col_small", self.x8.ref(), 3, 3, 3, 1, 0, self.x_patch.ref())
+        self.conv_fwd(p, self.e0_patch, self.x_patch, out=self.e0, mask_out=self.me0)
         self.conv_fwd(p, e1, self.e0, out=self.e1, mask_out=self.me1)
         self.conv_fwd(p, e2, self.e1, out=self.xs, addend=self.e0, mask_out=self.me2)
         if cfg.fgbg:
@@ -903,8 +958,10 @@ class Stage1Engine:
                 up = self.cat[idx + 1].slice(0, self.dec_c[idx + 1][0])
                 self._keep.append(up)
                 self.conv_fwd(p, self.conv[names[2]], self.dec_y[idx], out=up, mask_out=self.dec_mu[idx], upsample=2)
-        self.conv_fwd(p, self.conv[self.n_gout], self.dec_y[rn - 1], act=ACT_NONE, out=self.G8, out_f32=self.G,
-                      out_f32_ps=3)
+        # 256 -> 3 output conv (models.py:573): 1x1 conv to 27 tap channels, then the col2im gather adds the bias
+        self.conv_fwd(p, self.gout_f, self.dec_y[rn - 1], act=ACT_NONE, bias=False, out_f32=self.gout_y, out_f32_ps=32)
+        p.add("col2im_small", ptr(self.gout_y), 32, B, H, W, 3, 3, 3, ptr(self.conv[self.n_gout].b), ptr(self.G), 3,
+              self.G8.ref())
 
     def _prog_backward_generator(self, p):
         """Consumes self.g_G (fp32 grad wrt the generated image) and accumulates all Encoder+G param grads."""
@@ -913,9 +970,26 @@ class Stage1Engine:
         p.add("pack_f32", ptr(self.g_G), 3, 3, self.g_G8.ref())
         # ---- decoder
         lo = self.conv[self.n_gout]
-        self.conv_wgrad(p, lo, self.dec_y[rn - 1], self.g_G8)
-        self.conv_dgrad(p, lo, self.g_G8, H, W, out=self.dec_gy[rn - 1], out_masked=self.dec_gb[rn - 1],
-                        mask_in=self.dec_mb[rn - 1], db_of=self.conv[self.n_gdec[rn - 1][1]])
+        p.add("im2col_small", self.g_G8.ref(), 3, 3, 3, 1, 1, self.gG_patch.ref())
+        fl = 2.0 * B * H * W * 27 * lo.cin
+        tag = "%s %dx%dx%dx%d->3 k3s1 (patch form)" % (lo.wname, B, H, W, lo.cin)
+        # filter gradient in the [ci][tap*3+co] layout, folded back into HWIO; bias gradient from dL/dG itself
+        p.add_py(lambda s: self.gout_dwv.zero_())
+        p.add("conv2d_bwd_filter", self.dec_y[rn - 1].ref(), self.gG_patch.ref(), 1, 1, 1, lo.cin, 27, ptr(self.gout_dwv),
+              flops=fl, tag=tag)
+        p.add("permute_taps", ptr(self.gout_dwv), ptr(lo.dw), 9, lo.cin, 3, 2)
+        g3 = self.g_G8.slice(0, 3)
+        self._keep.append(g3)
+        p.add("bias_grad", g3.ref(), ptr(lo.db))
+        # data gradient: 1x1 conv from the 27 patch channels of dL/dG
+        db_of = self.conv[self.n_gdec[rn - 1][1]]
+        colsum = db_of.db if self.fuse_bias_grad else None
+        if colsum is not None:
+            self._db_done.add((id(p), id(self.dec_gb[rn - 1]), db_of.wname))
+        ep = self._epilogue(p, None, ACT_NONE, 0.0, None, self.dec_mb[rn - 1], 0.0, None, self.dec_gy[rn - 1],
+                            self.dec_gb[rn - 1], None, 0, 1, colsum=colsum)
+        p.add("conv2d_fwd", self.gG_patch.ref(), ptr(self.gout_d.fwd[0]), ptr(self.gout_d.fwd[1]), 1, 1, 1, lo.cin, ep,
+              flops=fl, tag="dgrad " + tag)
         for idx in range(rn - 1, -1, -1):
             names = self.n_gdec[idx]
             lvl = rn - 1 - idx
@@ -998,13 +1072,13 @@ class Stage1Engine:
         self.conv_dgrad(p, e2, self.g_xs_m, H, W, out_masked=self.g_e1, mask_in=self.me1, db_of=e1)
         self.conv_wgrad(p, e1, self.e0, self.g_e1)
         self.conv_dgrad(p, e1, self.g_e1, H, W, out_masked=self.g_e0, mask_in=self.me0, addend=self.g_xs, db_of=e0)
-        self.conv_wgrad(p, e0, self.x8, self.g_e0)
+        self.conv_wgrad(p, self.e0_patch, self.x_patch, self.g_e0)
 
     def _prog_disc_forward(self, p, dp, img):
         cfg = self.cfg
         H, W, d, n = cfg.img_h, cfg.img_w, cfg.d_dim, dp.n
-        l1 = self.conv[self.n_d[0]]
-        self.conv_fwd(p, l1, img, out=dp.h[0], act=ACT_LRELU, alpha=0.2, mask_out=dp.m[0])
+        p.add("im2col_small", img.ref(), 3, 5, 5, 2, 0, dp.patch.ref())
+        self.conv_fwd(p, self.d1_patch, dp.patch, out=dp.h[0], act=ACT_LRELU, alpha=0.2, mask_out=dp.m[0])
         for i in (1, 2, 3):
             layer = self.conv[self.n_d[i]]
             hh, ww, c = H >> (i + 1), W >> (i + 1), d << i
@@ -1073,7 +1147,7 @@ class Stage1Engine:
                                 mask_neg=0.2, db_of=self.conv[self.n_d[0]] if params else None)
         l1 = self.conv[self.n_d[0]]
         if params:
-            self.conv_wgrad(p, l1, img, dp.g_pre[0])
+            self.conv_wgrad(p, self.d1_patch, dp.patch, dp.g_pre[0])
         if data:
             self.conv_dgrad(p, l1, dp.g_pre[0], H, W, out_f32=dp.g_x, out_f32_ps=3)
 

@@ -165,6 +165,24 @@ int dpig_conv2d_small_bwd_filter(dpig_ctx* ctx, const float* x, int32_t n, int32
                                  int32_t cin, const float* dy, int32_t kh, int32_t kw,
                                  int32_t stride, int32_t cout, float* dw, dpig_stream stream);
 
+/* The 3-channel ends as dense 1x1 contractions (patch.cu).  (tap, channel) pairs of the 3-channel side become channels:
+ *   dpig_im2col_small:  out[n,oy,ox,(i*kw+j)*c_src + c] = src[n, oy*s+i-pt, ox*s+j-pl, c]  (0 outside; SAME padding);
+ *                       transposed=1 (stride 1): src[n, oy-(i-pt), ox-(j-pl), c] -- the patches of an output gradient.
+ *                       c_src leading channels of src are used; out->c >= kh*kw*c_src, remaining channels are zero.
+ *     cin = 3 layers (models.py:396; wgan_gp.py:419):  conv = dpig_conv2d_fwd(patches, k=1) on the same HWIO filter read
+ *     as [kh*kw*3][cout];  filter gradient = dpig_conv2d_bwd_filter(patches, dy, k=1).
+ *   dpig_col2im_small:  out[n,y,x,co] = bias[co] + sum_taps Y[n, y+i-pt, x+j-pl, (i*kw+j)*cout + co] for the cout = 3
+ *     output conv (models.py:573) computed as Y = dpig_conv2d_fwd(x, k=1) with the filter re-laid by
+ *   dpig_permute_taps:  mode 0 dst[ci][tap*cout+co] = src[tap][ci][co]; mode 1 dst[tap*cout+co][ci] = src[tap][ci][co];
+ *                       mode 2 dst[tap][ci][co] += src[ci][tap*cout+co]  (fp32 filters / filter gradients). */
+int dpig_im2col_small(dpig_ctx* ctx, const dpig_tensor* src, int32_t c_src, int32_t kh, int32_t kw, int32_t stride,
+                      int32_t transposed, const dpig_tensor* out, dpig_stream stream);
+int dpig_col2im_small(dpig_ctx* ctx, const float* y, int64_t y_pix_stride, int32_t n, int32_t h, int32_t w_, int32_t kh,
+                      int32_t kw, int32_t cout, const float* bias, float* out_f32, int64_t out_f32_pix_stride,
+                      const dpig_tensor* out, dpig_stream stream);
+int dpig_permute_taps(dpig_ctx* ctx, const float* src, float* dst, int32_t taps, int32_t cin, int32_t cout, int32_t mode,
+                      dpig_stream stream);
+
 /* db[c] += sum over pixels of dy (bias gradient of bias_add). */
 int dpig_bias_grad(dpig_ctx* ctx, const dpig_tensor* dy, float* db, dpig_stream stream);
 int dpig_bias_grad_f32(dpig_ctx* ctx, const float* dy, int64_t pixels, int32_t c, float* db,

@@ -54,6 +54,8 @@ if __name__ == "__main__":
         variants = [v for v in variants if v[0] in sys.argv[1:]]
     if os.environ.get("MICRO_SHAPES"):  # e.g. MICRO_SHAPES=0,1 MICRO_MODES=none (profiling one launch under ncu)
         shapes = [shapes[int(i)] for i in os.environ["MICRO_SHAPES"].split(",")]
+    if os.environ.get("MICRO_SHAPE"):   # explicit "n,h,w,cin,cout[,k]"
+        shapes = [tuple(int(v) for v in os.environ["MICRO_SHAPE"].split(","))]
     modes = os.environ.get("MICRO_MODES", "full,nores,none").split(",")
     for name, tiling, env in variants:
         for k in ("DPIG_CONV_STAGES", "DPIG_CONV_MERGE"):
@@ -61,8 +63,10 @@ if __name__ == "__main__":
         os.environ.update(env)
         ctx = dpig_b200.Context(0)
         ctx.set_pair_mode(tiling)
-        for (n, h, w, cin, cout) in shapes:
+        for shp in shapes:
+            n, h, w, cin, cout = shp[:5]
+            kk = shp[5] if len(shp) > 5 else 3
             for mode in modes:
-                ms, tf = run(ctx, n, h, w, cin, cout, mode=mode, fast=False)
+                ms, tf = run(ctx, n, h, w, cin, cout, k=kk, mode=mode, fast=False, iters=int(os.environ.get("MICRO_ITERS", "20")))
                 print("%-14s %4dx%3dx%3d %4d->%4d  epilogue=%-5s %7.3f ms  %7.1f TFLOP/s (algorithmic)" % (
                     name, n, h, w, cin, cout, mode, ms, tf), flush=True)

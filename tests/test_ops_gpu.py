@@ -515,3 +515,102 @@ if __name__ == "__main__":
             import traceback
             traceback.print_exc()
             print("test_norm_act", mode, "FAILED", repr(e)[:300], flush=True)
+
+
+# ------------------------------------------------------------------------------------------ 3-channel ends as 1x1 GEMMs
+@pytest.mark.parametrize("case", [dict(n=2, h=16, w=8, k=3, stride=1, cout=128), dict(n=3, h=32, w=16, k=5, stride=2, cout=64),
+                                  dict(n=2, h=7, w=5, k=3, stride=2, cout=32)])
+def test_patch_form_of_3_channel_input_conv(case):
+    """cin = 3 (models.py:396, wgan_gp.py:419): im2col -> 1x1 conv on the SAME HWIO filter, and its filter gradient,
+    against the float64 oracle convolution."""
+    import ctypes as C
+    _lib, SplitTensor, ptr, split_ref = _imports()
+    n, h, w, k, stride, cout = (case[x] for x in ("n", "h", "w", "k", "stride", "cout"))
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn((n, h, w, 3), generator=g)
+    wt = torch.randn((k, k, 3, cout), generator=g) / np.sqrt(k * k * 3)
+    bias = torch.randn((cout,), generator=g) * 0.1
+    oh, ow = -(-h // stride), -(-w // stride)
+    kp = (k * k * 3 + 7) // 8 * 8
+    xs = padded_split(x)                                   # [n,h,w,8]
+    patches = SplitTensor(n, oh, ow, kp, zero=False)
+    ctx().im2col_small(xs.ref(), 3, k, k, stride, 0, patches.ref(), stream())
+    # the filter read as a 1x1 conv with k*k*3 input channels
+    w1 = wt.reshape(1, 1, k * k * 3, cout).cuda().contiguous()
+    f, _ = pack_weights(w1, cin_pad=kp)
+    out = SplitTensor(n, oh, ow, cout, zero=True)
+    ep = _lib.ConvEpilogue()
+    bd = bias.cuda()
+    ep.bias = bd.data_ptr()
+    ep.act = 1
+    ep.upsample = 1
+    ep.out = C.pointer(out.struct())
+    ctx().conv2d_fwd(patches.ref(), ptr(f[0]), ptr(f[1]), 1, 1, 1, cout, C.byref(ep), stream())
+    dy = torch.randn((n, oh, ow, cout), generator=g)
+    dys = padded_split(dy)
+    dw = torch.zeros((k, k, 3, cout), device="cuda")
+    ctx().conv2d_bwd_filter(patches.ref(), dys.ref(), 1, 1, 1, k * k * 3, cout, ptr(dw), stream())
+    torch.cuda.synchronize()
+    wv = split_ref(wt).double().requires_grad_(True)
+    y = T.conv2d_same(split_ref(x).double(), wv, bias.double(), stride)
+    assert rel_err(out.float(), torch.relu(y).detach()) < 2e-5
+    gw, = torch.autograd.grad(y, wv, split_ref(dy).double())
+    assert rel_err(dw, gw) < 2e-5
+    assert float(patches.float()[..., k * k * 3:].abs().max()) == 0.0 if kp > k * k * 3 else True
+
+
+def test_patch_form_of_3_channel_output_conv():
+    """cout = 3 (models.py:573): 1x1 conv to 27 tap-channels + col2im gather; data / filter gradients through the
+    transposed patches of dy -- against the float64 oracle convolution and its autograd."""
+    import ctypes as C
+    _lib, SplitTensor, ptr, split_ref = _imports()
+    n, h, w, cin, k, cout = 2, 16, 8, 256, 3, 3
+    g = torch.Generator().manual_seed(6)
+    x = torch.randn((n, h, w, cin), generator=g)
+    wt = torch.randn((k, k, cin, cout), generator=g) / np.sqrt(k * k * cin)
+    bias = torch.randn((cout,), generator=g) * 0.1
+    dy = torch.randn((n, h, w, cout), generator=g)
+    taps, J = k * k, k * k * cout
+    xs = SplitTensor.from_float(x.cuda())
+    wd = wt.cuda().contiguous()
+    # ---- forward
+    wf = torch.zeros((cin, J), device="cuda")
+    ctx().permute_taps(ptr(wd), ptr(wf), taps, cin, cout, 0, stream())
+    f, _ = pack_weights(wf.reshape(1, 1, cin, J).contiguous())
+    ybuf = torch.zeros((n, h, w, 32), device="cuda")
+    ep = _lib.ConvEpilogue()
+    ep.act = 0
+    ep.upsample = 1
+    ep.out_f32 = ybuf.data_ptr()
+    ep.out_f32_pix_stride = 32
+    ctx().conv2d_fwd(xs.ref(), ptr(f[0]), ptr(f[1]), 1, 1, 1, J, C.byref(ep), stream())
+    out32 = torch.zeros((n, h, w, cout), device="cuda")
+    out8 = SplitTensor(n, h, w, 8, zero=False)
+    bd = bias.cuda()
+    ctx().col2im_small(ptr(ybuf), 32, n, h, w, k, k, cout, ptr(bd), ptr(out32), cout, out8.ref(), stream())
+    # ---- gradients
+    dys = padded_split(dy)
+    dp = SplitTensor(n, h, w, 32, zero=False)
+    ctx().im2col_small(dys.ref(), cout, k, k, 1, 1, dp.ref(), stream())
+    wdg = torch.zeros((J, cin), device="cuda")
+    ctx().permute_taps(ptr(wd), ptr(wdg), taps, cin, cout, 1, stream())
+    fd, _ = pack_weights(wdg.reshape(1, 1, J, cin).contiguous(), cin_pad=32)
+    dx = SplitTensor(n, h, w, cin, zero=True)
+    ep2 = _lib.ConvEpilogue()
+    ep2.act = 0
+    ep2.upsample = 1
+    ep2.out = C.pointer(dx.struct())
+    ctx().conv2d_fwd(dp.ref(), ptr(fd[0]), ptr(fd[1]), 1, 1, 1, cin, C.byref(ep2), stream())
+    dwv = torch.zeros((cin, J), device="cuda")
+    ctx().conv2d_bwd_filter(xs.ref(), dp.ref(), 1, 1, 1, cin, J, ptr(dwv), stream())
+    dw = torch.full((k, k, cin, cout), 0.5, device="cuda")            # mode 2 accumulates
+    ctx().permute_taps(ptr(dwv), ptr(dw), taps, cin, cout, 2, stream())
+    torch.cuda.synchronize()
+    xv = split_ref(x).double().requires_grad_(True)
+    wv = split_ref(wt).double().requires_grad_(True)
+    y = T.conv2d_same(xv, wv, bias.double(), 1)
+    gx, gw = torch.autograd.grad(y, [xv, wv], split_ref(dy).double())
+    assert rel_err(out32, y.detach()) < 2e-5
+    assert rel_err(out8.float()[..., :3], y.detach()) < 2e-5 and float(out8.float()[..., 3:].abs().max()) == 0.0
+    assert rel_err(dx.float(), gx) < 2e-5
+    assert rel_err(dw - 0.5, gw) < 2e-5
