@@ -192,11 +192,35 @@ __device__ __forceinline__ void epi_chunk(const ConvUmmaParams& p, uint8_t* stag
   const bool full32 = (nvalid == 32);
   float f[32];
   uint32_t mbits = 0;
+  // bias of the chunk's 32 channels: ONE coalesced load per warp, broadcast by shuffles.  (32 predicated scalar loads,
+  // each followed by its dependent add, cost ~10k clk per chunk on the long scoreboard -- half of the whole tile time
+  // of every short-K layer, profiles/r01_epilogue_bias_ncu.txt.)
+  float bl = 0.f;
+  if (p.bias && lane < nvalid) bl = __ldg(p.bias + cbase + lane);
+#pragma unroll
+  for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]) + __shfl_sync(0xffffffffu, bl, i);
+  if (cbias) {  // per-pixel (border class) bias row: vector loads, issued back to back
+    if (full32) {
+      const float4* cb4 = reinterpret_cast<const float4*>(cbias + cbase);
+      float4 t[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) t[q] = __ldg(cb4 + q);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        f[4 * q] += t[q].x;
+        f[4 * q + 1] += t[q].y;
+        f[4 * q + 2] += t[q].z;
+        f[4 * q + 3] += t[q].w;
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 32; ++i)
+        if (i < nvalid) f[i] += __ldg(cbias + cbase + i);
+    }
+  }
 #pragma unroll
   for (int i = 0; i < 32; ++i) {
-    float x = __uint_as_float(v[i]);
-    if (p.bias && i < nvalid) x += __ldg(p.bias + cbase + i);
-    if (cbias && i < nvalid) x += __ldg(cbias + cbase + i);
+    float x = f[i];
     mbits |= (x > 0.f ? 1u : 0u) << i;
     if (p.act == DPIG_ACT_RELU) x = fmaxf(x, 0.f);
     else if (p.act == DPIG_ACT_LRELU) x = x > 0.f ? x : p.alpha * x;
