@@ -163,22 +163,32 @@ __device__ __forceinline__ void epi_scatter_rows(const uint8_t* stage, __nv_bflo
   }
 }
 
-// global -> staging rows (residual / addend), same access shape as epi_scatter_rows
+// global -> staging rows (residual / addend), same access shape as epi_scatter_rows.  All eight 16-byte loads are
+// issued before the first staging store: in program order (load, load, store) x 4 the compiler kept each store behind
+// its loads and the next loads behind the store, i.e. four exposed global latencies per chunk (30 % of all stall
+// samples of a 128-channel residual layer, profiles/r01_epilogue_ncu.txt).
 __device__ __forceinline__ void epi_gather_rows(uint8_t* stage, const __nv_bfloat16* hi, const __nv_bfloat16* lo,
                                                 long long ps, int cbase, int pix, bool valid, int lane) {
+  uint4 a[4], b[4];
+  const int pc = lane & 3;
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    const int q = 8 * i + (lane >> 2), pc = lane & 3;
+    const int q = 8 * i + (lane >> 2);
     const int pq = __shfl_sync(0xffffffffu, pix, q);
     const int vq = __shfl_sync(0xffffffffu, static_cast<int>(valid), q);
-    uint4 a = make_uint4(0, 0, 0, 0), b = make_uint4(0, 0, 0, 0);
+    a[i] = make_uint4(0, 0, 0, 0);
+    b[i] = make_uint4(0, 0, 0, 0);
     if (vq) {
       const long long off = static_cast<long long>(pq) * ps + cbase + pc * 8;
-      a = __ldg(reinterpret_cast<const uint4*>(hi + off));
-      if (lo) b = __ldg(reinterpret_cast<const uint4*>(lo + off));
+      a[i] = __ldg(reinterpret_cast<const uint4*>(hi + off));
+      if (lo) b[i] = __ldg(reinterpret_cast<const uint4*>(lo + off));
     }
-    *reinterpret_cast<uint4*>(stage + swz64(q, pc)) = a;
-    if (lo) *reinterpret_cast<uint4*>(stage + 2048 + swz64(q, pc)) = b;
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int q = 8 * i + (lane >> 2);
+    *reinterpret_cast<uint4*>(stage + swz64(q, pc)) = a[i];
+    if (lo) *reinterpret_cast<uint4*>(stage + 2048 + swz64(q, pc)) = b[i];
   }
 }
 
