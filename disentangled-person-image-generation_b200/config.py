@@ -63,7 +63,7 @@ def build_parser():
     misc.add_argument("--gan_mode", type=str, default="dcgan", choices=["dcgan", "wgan", "wgan-gp", "lsgan"],
                       help="loss / critic-norm mode of wgan_gp.WGAN_GP (the shipped Stage-I trainer hard-codes dcgan)")
     misc.add_argument("--synthetic_data", type=str2bool, default=True,
-                      help="draw synthetic batches (the TFRecord pipeline is not part of this round)")
+                      help="true: synthetic batches (no dataset ships here); false: read the TFRecord pair files under <data_dir>/<dataset> (datasets.py)")
     return p
 
 

@@ -15,7 +15,7 @@ import torch
 from . import _lib, engine, stage2, synth, tf_checkpoint
 from ._lib import ACT_LRELU, ACT_NONE
 from .tensor import ptr
-from .trainer import SyntheticLoader
+from .trainer import SyntheticLoader, make_loader
 
 
 def pose_specs(keypoints=18):
@@ -39,7 +39,7 @@ class DPIG_FourNetsFgBg_testOnlySampleFactor(object):
         self.model_dir = config.model_dir or os.path.join(config.log_dir, "dpig_model%d" % config.model)
         self.pretrained_path = config.pretrained_path
         self.test_batch_num = 400        # tester.py:475
-        self.loader = loader or SyntheticLoader(self.batch_size, self.img_H, self.img_W, config.random_seed)
+        self.loader = loader or make_loader(config, self.batch_size, self.img_H, self.img_W)
         self.net_cfg = None
 
     def init_net(self, net_cfg=None):

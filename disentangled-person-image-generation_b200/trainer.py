@@ -9,8 +9,9 @@ kept (`loss/L1Loss`, `loss/g_loss`, ...) and written as JSON lines instead of TF
 
 Checkpoints are TensorFlow V2 bundles written / read without TensorFlow (tf_checkpoint.py), keyed by the reference's
 variable names, so `--pretrained_path` / `--ckpt_path` accept the reference's checkpoints and vice versa.
-Not reproduced: the TFRecord input pipeline (datasets/market1501.py) -- batches come from synth.make_batch unless a
-loader object with `next_batch()` is supplied.
+Input: `--synthetic_data=false` reads the reference's TFRecord pair files under `<data_dir>/<dataset>` through
+datasets.TFRecordPairLoader (datasets/market1501.py + _load_batch_pair_pose, without TensorFlow); otherwise batches come
+from synth.make_batch, or from any loader object with `next_batch()` that is supplied.
 """
 import json
 import os
@@ -19,7 +20,7 @@ import time
 import numpy as np
 import torch
 
-from . import _lib, engine, synth, tf_checkpoint
+from . import _lib, datasets, engine, synth, tf_checkpoint
 from .tensor import ptr
 
 
@@ -35,13 +36,31 @@ class SyntheticLoader:
         return synth.make_batch(self.batch_size, self.img_h, self.img_w, seed=self.seed + self.i)
 
 
+def make_loader(config, batch_size, img_h, img_w):
+    """trainer.py:35-42 / 1049-1055: dataset name -> market1501 / deepfashion get_split('train' | 'test', data_path) with
+    data_path = <data_dir>/<dataset> (utils.py:136).  `--synthetic_data=true` (default here: no dataset ships) draws
+    synthetic batches of the same shapes instead."""
+    if getattr(config, "synthetic_data", True):
+        return SyntheticLoader(batch_size, img_h, img_w, config.random_seed)
+    name = config.dataset.lower()
+    if "market" in name:
+        data_name = "Market1501"
+    elif "deepfashion" in name or "df" in name:
+        data_name = "DeepFashion"
+    else:
+        raise Exception("dataset %r: expected a Market-1501 or DeepFashion TFRecord directory" % config.dataset)
+    data_path = getattr(config, "data_path", None) or os.path.join(config.data_dir, config.dataset)
+    return datasets.get_split("train" if config.is_train else "test", data_path, data_name=data_name,
+                              batch_size=batch_size, seed=config.random_seed)
+
+
 class DPIG_Encoder_GAN_BodyROI_FgBg(object):
     def __init__(self, config, loader=None, dist=None):
         self._common_init(config)
         self.D_arch = config.D_arch
         self.part_num = 37
         self.keypoint_num = 18
-        self.loader = loader or SyntheticLoader(self.batch_size, self.img_H, self.img_W, config.random_seed)
+        self.loader = loader or make_loader(config, self.batch_size, self.img_H, self.img_W)
         self.dist = dist
         self.net = None
 
