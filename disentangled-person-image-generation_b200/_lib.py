@@ -89,6 +89,8 @@ _SIGNATURES = {
     "dpig_gp_penalty": [_P, _I, _L, _F, _P, _P, _P, _P],
     "dpig_adam_step": [_P, _P, _P, _P, _L, _F, _F, _F, _F, _I, _F, _P],
     "dpig_rmsprop_step": [_P, _P, _P, _L, _F, _F, _F, _F, _F, _P],
+    "dpig_adam_step_dev": [_P, _P, _P, _P, _L, _P, _F, _F, _F, _F, _P],
+    "dpig_rmsprop_step_dev": [_P, _P, _P, _L, _P, _F, _F, _F, _F, _P],
     "dpig_clip": [_P, _L, _F, _F, _P],
     "dpig_denorm_u8": [_P, _L, _P, _P],
     "dpig_pose_rasterize": [_P, _I, _I, _I, _I, _I, _T, _P, _P],
@@ -140,6 +142,7 @@ class Context:
                             "this library has no CPU or other-GPU fallback" % (device, rc))
         self.handle = h
         self.device = device
+        self.replayed_launches = 0
 
     def __del__(self):
         try:
@@ -161,7 +164,9 @@ class Context:
         self.call("ctx_set_pair_mode", int(mode))
 
     def launch_count(self):
-        return int(self.lib.dpig_launch_count(self.handle))
+        """Kernels launched through this context, including the kernels of replayed CUDA graphs (the library counts a
+        launch when it is issued or captured; every replay adds the captured count, see engine.StepGraph)."""
+        return int(self.lib.dpig_launch_count(self.handle)) + self.replayed_launches
 
     def call(self, name, *args):
         rc = getattr(self.lib, "dpig_" + name)(self.handle, *args)

@@ -59,6 +59,7 @@ extern "C" int dpig_ctx_create(int device, dpig_ctx** out) {
   if (const char* e = getenv("DPIG_WGRAD_PX")) ctx->wgrad_px = atoi(e);
   if (const char* e = getenv("DPIG_CONV_STAGES")) ctx->max_stages = atoi(e);
   if (const char* e = getenv("DPIG_CONV_MERGE")) ctx->merge_planes = atoi(e) != 0;
+  if (const char* e = getenv("DPIG_DGRAD_MERGE")) ctx->dgrad_merge = atoi(e) != 0;
   *out = ctx;
   return DPIG_OK;
 }

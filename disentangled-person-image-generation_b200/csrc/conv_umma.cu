@@ -43,6 +43,12 @@ struct ConvUmmaParams {
   CUtensorMap b_map[2];
   ConvTap taps[kMaxTaps];
   int num_taps, planes, kchunks;
+  // Parity classes of a stride-2 data gradient merged into ONE launch: a work unit runs its pixel tile once per class,
+  // back to back (taps [cls_tap0[c], cls_tap0[c+1]), output offset (cls_oh[c], cls_ow[c])).  The same dy region then
+  // feeds all four classes from L2 while the four interleaved quarters of the dx region are written close in time;
+  // every unit carries all kh*kw taps, so the static tile schedule stays balanced.  nclass = 1 otherwise.
+  int nclass;
+  int16_t cls_tap0[5], cls_oh[4], cls_ow[4];
   int BW, BH, BN;
   int tiles_w, tiles_h, tiles_n;
   int Wo, Ho, No;
@@ -195,8 +201,9 @@ __device__ __forceinline__ void epi_gather_rows(uint8_t* stage, const __nv_bfloa
 // One 32-channel chunk of one accumulator row (pixel): bias / activation / residual / sign mask / outputs.
 // v[i] = raw fp32 accumulator of channel cbase+i; all 32 lanes of the warp call this together (the global traffic
 // is staged through the warp-private tile `stage`).
+// colsum: lane l's running total of channel cbase + l of the masked output (see the flush in the kernel).
 __device__ __forceinline__ void epi_chunk(const ConvUmmaParams& p, uint8_t* stage, const uint32_t (&v)[32], int cbase,
-                                          bool valid, int lpix, int ppix, const float* cbias, int lane) {
+                                          bool valid, int lpix, int ppix, const float* cbias, int lane, float& colsum) {
   const int nvalid = min(32, p.cout - cbase);
   if (nvalid <= 0) return;  // warp-uniform
   const bool full32 = (nvalid == 32);
@@ -351,7 +358,7 @@ __device__ __forceinline__ void epi_chunk(const ConvUmmaParams& p, uint8_t* stag
           f[i] = (upper ? f[i + off] : f[i]) + recv;
         }
       }
-      if (lane < nvalid) atomicAdd(p.colsum + cbase + lane, f[0]);
+      colsum += f[0];
     }
   }
 }
@@ -427,7 +434,6 @@ conv_umma_kernel(const __grid_constant__ ConvUmmaParams p) {
   else __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const int steps_per_tile = p.num_taps * p.kchunks;
 
   if (warp == 0) {
     if (lane == 0) {
@@ -445,7 +451,7 @@ conv_umma_kernel(const __grid_constant__ ConvUmmaParams p) {
         const int th = (pt / p.tiles_w) % p.tiles_h;
         const int tn = pt / (p.tiles_w * p.tiles_h);
         const int w0 = tw * p.BW, h0 = th * p.BH, n0 = tn * p.BN;
-        for (int t = 0; t < p.num_taps; ++t) {
+        for (int t = 0; t < p.num_taps; ++t) {   // all classes of the unit, in class order (taps are sorted by class)
           const ConvTap tap = p.taps[t];
           for (int kc = 0; kc < p.kchunks; ++kc) {
             ptx::mbar_wait(&empty[s], ph ^ 1);
@@ -494,11 +500,13 @@ conv_umma_kernel(const __grid_constant__ ConvUmmaParams p) {
       int s = 0;
       uint32_t ph = 0;
       int j = 0;
-      for (int tile = unit0; tile < total_tiles; tile += unit_step, ++j) {
+      for (int tile = unit0; tile < total_tiles; tile += unit_step)
+      for (int cls = 0; cls < p.nclass; ++cls, ++j) {
         const int acc = j & 1;
         ptx::mbar_wait(&tmem_empty[acc], ((j >> 1) & 1) ^ 1);
         ptx::tc_fence_after();
         const uint32_t tmem_acc = tmem_base + acc * p.block_n;
+        const int steps_per_tile = (p.cls_tap0[cls + 1] - p.cls_tap0[cls]) * p.kchunks;
         for (int step = 0; step < steps_per_tile; ++step) {
           ptx::mbar_wait(&full[s], ph);
           ptx::tc_fence_after();
@@ -554,10 +562,32 @@ conv_umma_kernel(const __grid_constant__ ConvUmmaParams p) {
     uint8_t* stage = epi_smem + ew * kEpiBytesPerWarp;
     const uint32_t lead_tmem_empty[2] = {kPair ? ptx::mapa_u32(ptx::smem_u32(&tmem_empty[0]), 0) : 0u,
                                          kPair ? ptx::mapa_u32(ptx::smem_u32(&tmem_empty[1]), 0) : 0u};
+    // Bias-gradient column sums stay in registers across all tiles of one channel block (a warp owns at most four
+    // 32-channel chunks of it; lane l holds channel chunk*32 + l) and reach global memory with one atomic per channel
+    // when the block changes / at the end.  One atomic per chunk and 32 pixel rows (the first version) put
+    // pixels/32 same-address fp32 atomics on every channel: ~1.3 clk each at the L2, 0.6 ms on a 1 M-pixel layer --
+    // it made every short-K data gradient (stride-2 parity classes, 1x1) atomic-bound instead of tensor-bound.
+    float cs0 = 0.f, cs1 = 0.f, cs2 = 0.f, cs3 = 0.f;
+    int cs_nt = -1;
+    auto flush_colsum = [&]() {
+      if (p.colsum == nullptr || cs_nt < 0) return;
+      const float cs[4] = {cs0, cs1, cs2, cs3};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int c = cs_nt * p.block_n + ((cpar + k * (kEpiWarps / 4)) << 5) + lane;
+        if (cpar + k * (kEpiWarps / 4) < (p.block_n >> 5) && c < p.cout) atomicAdd(p.colsum + c, cs[k]);
+      }
+      cs0 = cs1 = cs2 = cs3 = 0.f;
+    };
     int j = 0;
-    for (int tile = unit0; tile < total_tiles; tile += unit_step, ++j) {
+    for (int tile = unit0; tile < total_tiles; tile += unit_step)
+    for (int cls = 0; cls < p.nclass; ++cls, ++j) {
       const int acc = j & 1;
       const int upt = tile % unit_pix_tiles, nt = tile / unit_pix_tiles;
+      if (nt != cs_nt) {
+        flush_colsum();
+        cs_nt = nt;
+      }
       const int pt = kPair ? 2 * upt + static_cast<int>(rank) : upt;
       const int tw = pt % p.tiles_w;
       const int th = (pt / p.tiles_w) % p.tiles_h;
@@ -565,7 +595,7 @@ conv_umma_kernel(const __grid_constant__ ConvUmmaParams p) {
       const int w = tw * p.BW + wl, h = th * p.BH + hl, n = tn * p.BN + nl;
       const bool valid = (nl < p.BN) && (w < p.Wo) && (h < p.Ho) && (n < p.No);
       const int lpix = (n * p.Ho + h) * p.Wo + w;  // logical pixel (< 2^31 for every supported shape)
-      const int py = h * p.sh + p.oh, px = w * p.sw + p.ow;
+      const int py = h * p.sh + p.cls_oh[cls], px = w * p.sw + p.cls_ow[cls];
       const int ppix = (n * p.out_H + py) * p.out_W + px;
       const float* cbias = nullptr;
       if (p.class_bias && valid) {
@@ -594,7 +624,13 @@ conv_umma_kernel(const __grid_constant__ ConvUmmaParams p) {
           }
           released = true;
         }
-        epi_chunk(p, stage, v, nt * p.block_n + c0, valid, lpix, ppix, cbias, lane);
+        float csum = 0.f;
+        epi_chunk(p, stage, v, nt * p.block_n + c0, valid, lpix, ppix, cbias, lane, csum);
+        const int k = (ci - cpar) / (kEpiWarps / 4);   // this warp's k-th chunk of the block
+        cs0 += k == 0 ? csum : 0.f;
+        cs1 += k == 1 ? csum : 0.f;
+        cs2 += k == 2 ? csum : 0.f;
+        cs3 += k == 3 ? csum : 0.f;
       }
       if (!released) {  // fewer chunks than epilogue warps per lane group (block_n == 32)
         ptx::tc_fence_before();
@@ -605,6 +641,7 @@ conv_umma_kernel(const __grid_constant__ ConvUmmaParams p) {
         }
       }
     }
+    flush_colsum();
   }
 
   ptx::tc_fence_before();
@@ -1154,6 +1191,9 @@ extern "C" int dpig_conv2d_fwd(dpig_ctx* ctx, const dpig_tensor* x, const void* 
         if ((rc = encode_map(ctx, &P.b_map[pln], pln ? wf_lo : wf_hi, 3, dims, strides, box))) return rc;
     }
   }
+  P.nclass = 1;
+  P.cls_tap0[0] = 0;
+  P.cls_tap0[1] = static_cast<int16_t>(P.num_taps);
   EpilogueGeom g{up, up, 0, 0, up, OH * up, OW * up};
   if ((rc = fill_epilogue(ctx, P, ep, g, x->n, cout))) return rc;
   return launch_conv(ctx, P, static_cast<cudaStream_t>(stream));
@@ -1175,30 +1215,40 @@ extern "C" int dpig_conv2d_bwd_data(dpig_ctx* ctx, const dpig_tensor* dy, const 
   if (ep->upsample > 1) return set_error(ctx, DPIG_EUNSUPPORTED, "conv2d_bwd_data: no upsample");
   const int pt = same_pad_before(in_h, kh, stride), pl = same_pad_before(in_w, kw, stride);
   int rc;
-  for (int py = 0; py < stride; ++py)
-    for (int px = 0; px < stride; ++px) {
-      const int GH = (in_h - py + stride - 1) / stride, GW = (in_w - px + stride - 1) / stride;
-      if (GH <= 0 || GW <= 0) continue;
-      ConvUmmaParams P;
-      memset(&P, 0, sizeof(P));
-      P.planes = (dy->lo && wb_lo) ? 2 : 1;
-      const int planes = ctx->fast_mode ? 1 : P.planes;
-      P.kchunks = (dy->c + 63) / 64;
-      P.Wo = GW;
-      P.Ho = GH;
-      P.No = dy->n;
-      P.cout = cin;
-      Box b = choose_box(GW, GH, dy->n, 128, false);
-      P.BW = b.bw;
-      P.BH = b.bh;
-      P.BN = b.bn;
-      P.tiles_w = (GW + b.bw - 1) / b.bw;
-      P.tiles_h = (GH + b.bh - 1) / b.bh;
-      P.tiles_n = (dy->n + b.bn - 1) / b.bn;
-      P.a_tx_bytes = b.bw * b.bh * b.bn * 128;
-      P.block_n = tune_block_n(ctx, cin, P.tiles_w * P.tiles_h * P.tiles_n);
-      choose_pair(ctx, P);
-      P.num_taps = 0;
+  // Stride 2: the four parity classes of dx share one launch when they have the same grid (even in_h, in_w), see
+  // ConvUmmaParams::nclass; otherwise (and with DPIG_DGRAD_MERGE=0) one launch per class.
+  const bool merged = stride == 2 && ctx->dgrad_merge && in_h % 2 == 0 && in_w % 2 == 0;
+  const int nlaunch = merged ? 1 : stride * stride;
+  for (int li = 0; li < nlaunch; ++li) {
+    const int py0 = merged ? 0 : li / stride, px0 = merged ? 0 : li % stride;
+    const int GH = (in_h - py0 + stride - 1) / stride, GW = (in_w - px0 + stride - 1) / stride;
+    if (GH <= 0 || GW <= 0) continue;
+    ConvUmmaParams P;
+    memset(&P, 0, sizeof(P));
+    P.planes = (dy->lo && wb_lo) ? 2 : 1;
+    const int planes = ctx->fast_mode ? 1 : P.planes;
+    P.kchunks = (dy->c + 63) / 64;
+    P.Wo = GW;
+    P.Ho = GH;
+    P.No = dy->n;
+    P.cout = cin;
+    Box b = choose_box(GW, GH, dy->n, 128, false);
+    P.BW = b.bw;
+    P.BH = b.bh;
+    P.BN = b.bn;
+    P.tiles_w = (GW + b.bw - 1) / b.bw;
+    P.tiles_h = (GH + b.bh - 1) / b.bh;
+    P.tiles_n = (dy->n + b.bn - 1) / b.bn;
+    P.a_tx_bytes = b.bw * b.bh * b.bn * 128;
+    P.block_n = tune_block_n(ctx, cin, P.tiles_w * P.tiles_h * P.tiles_n);
+    choose_pair(ctx, P);
+    P.num_taps = 0;
+    P.nclass = merged ? stride * stride : 1;
+    for (int c = 0; c < P.nclass; ++c) {
+      const int py = merged ? c / stride : py0, px = merged ? c % stride : px0;
+      P.cls_tap0[c] = static_cast<int16_t>(P.num_taps);
+      P.cls_oh[c] = static_cast<int16_t>(py);
+      P.cls_ow[c] = static_cast<int16_t>(px);
       for (int i = 0; i < kh; ++i)
         for (int j = 0; j < kw; ++j) {
           // dx[s*a+py] gets dy[(s*a + py + pt - i)/s] when divisible
@@ -1211,44 +1261,46 @@ extern "C" int dpig_conv2d_bwd_data(dpig_ctx* ctx, const dpig_tensor* dy, const 
           t.wtap = i * kw + j;
           P.taps[P.num_taps++] = t;
         }
-      if (P.num_taps == 0)
+      if (P.num_taps == P.cls_tap0[c])
         return set_error(ctx, DPIG_EUNSUPPORTED, "conv2d_bwd_data: parity class without taps");
-      const long long a_ps =
-          (planes == 2 && ctx->merge_planes && P.a_tx_bytes == kABytes) ? plane_stride(dy->hi, dy->lo) : 0;
-      const long long b_ps = (planes == 2 && ctx->merge_planes) ? plane_stride(wb_hi, wb_lo) : 0;
-      P.a_merged = a_ps > 0;
-      P.b_merged = b_ps > 0;
-      for (int pln = 0; pln < planes; ++pln) {
-        if (pln == 0 || !P.a_merged) {
-          if ((rc = act_map(ctx, &P.a_map[0][pln], pln ? dy->lo : dy->hi, dy, 1, 0, 0, b.bw, b.bh, b.bn, a_ps)))
-            return rc;
-        } else {
-          P.a_map[0][1] = P.a_map[0][0];
-        }
-        for (int s = 1; s < 4; ++s) P.a_map[s][pln] = P.a_map[0][pln];
-      }
-      {
-        const int cout_pad = dy->c;
-        uint64_t dims[3] = {static_cast<uint64_t>(cout_pad), static_cast<uint64_t>(cin),
-                            static_cast<uint64_t>(kh * kw)};
-        uint64_t strides[2] = {static_cast<uint64_t>(cout_pad) * 2,
-                               static_cast<uint64_t>(cout_pad) * cin * 2};
-        uint32_t box[3] = {64, P.b_bytes / 128, 1};
-        if (P.b_merged) {
-          uint64_t dims4[4] = {dims[0], dims[1], dims[2], 2};
-          uint64_t strides3[3] = {strides[0], strides[1], static_cast<uint64_t>(b_ps)};
-          uint32_t box4[4] = {box[0], box[1], 1, 2};
-          if ((rc = encode_map(ctx, &P.b_map[0], wb_hi, 4, dims4, strides3, box4))) return rc;
-          P.b_map[1] = P.b_map[0];
-        } else {
-          for (int pln = 0; pln < planes; ++pln)
-            if ((rc = encode_map(ctx, &P.b_map[pln], pln ? wb_lo : wb_hi, 3, dims, strides, box))) return rc;
-        }
-      }
-      EpilogueGeom g{stride, stride, py, px, 1, in_h, in_w};
-      if ((rc = fill_epilogue(ctx, P, ep, g, dy->n, cin))) return rc;
-      if ((rc = launch_conv(ctx, P, static_cast<cudaStream_t>(stream)))) return rc;
     }
+    P.cls_tap0[P.nclass] = static_cast<int16_t>(P.num_taps);
+    const long long a_ps =
+        (planes == 2 && ctx->merge_planes && P.a_tx_bytes == kABytes) ? plane_stride(dy->hi, dy->lo) : 0;
+    const long long b_ps = (planes == 2 && ctx->merge_planes) ? plane_stride(wb_hi, wb_lo) : 0;
+    P.a_merged = a_ps > 0;
+    P.b_merged = b_ps > 0;
+    for (int pln = 0; pln < planes; ++pln) {
+      if (pln == 0 || !P.a_merged) {
+        if ((rc = act_map(ctx, &P.a_map[0][pln], pln ? dy->lo : dy->hi, dy, 1, 0, 0, b.bw, b.bh, b.bn, a_ps)))
+          return rc;
+      } else {
+        P.a_map[0][1] = P.a_map[0][0];
+      }
+      for (int s = 1; s < 4; ++s) P.a_map[s][pln] = P.a_map[0][pln];
+    }
+    {
+      const int cout_pad = dy->c;
+      uint64_t dims[3] = {static_cast<uint64_t>(cout_pad), static_cast<uint64_t>(cin),
+                          static_cast<uint64_t>(kh * kw)};
+      uint64_t strides[2] = {static_cast<uint64_t>(cout_pad) * 2,
+                             static_cast<uint64_t>(cout_pad) * cin * 2};
+      uint32_t box[3] = {64, P.b_bytes / 128, 1};
+      if (P.b_merged) {
+        uint64_t dims4[4] = {dims[0], dims[1], dims[2], 2};
+        uint64_t strides3[3] = {strides[0], strides[1], static_cast<uint64_t>(b_ps)};
+        uint32_t box4[4] = {box[0], box[1], 1, 2};
+        if ((rc = encode_map(ctx, &P.b_map[0], wb_hi, 4, dims4, strides3, box4))) return rc;
+        P.b_map[1] = P.b_map[0];
+      } else {
+        for (int pln = 0; pln < planes; ++pln)
+          if ((rc = encode_map(ctx, &P.b_map[pln], pln ? wb_lo : wb_hi, 3, dims, strides, box))) return rc;
+      }
+    }
+    EpilogueGeom g{stride, stride, py0, px0, 1, in_h, in_w};
+    if ((rc = fill_epilogue(ctx, P, ep, g, dy->n, cin))) return rc;
+    if ((rc = launch_conv(ctx, P, static_cast<cudaStream_t>(stream)))) return rc;
+  }
   return DPIG_OK;
 }
 

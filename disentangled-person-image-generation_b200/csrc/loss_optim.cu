@@ -145,10 +145,35 @@ __global__ void gp_finish_kernel(const float* grad, const float* slopes, int n, 
   }
 }
 
-__global__ void adam_kernel(float* p, const float* g, float* m, float* v, long long count, float lr_t, float b1,
-                            float b2, float eps, float gs) {
-  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < count;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+// lr_dev (optional): the step size is read from device memory instead of the launch argument, so that a captured
+// CUDA graph of the whole optimiser step can be replayed while Adam's bias-corrected lr_t changes every step.
+// 16-byte accesses on the 4-aligned body (28 B/param of HBM traffic is the whole cost of this kernel), scalar tail.
+__global__ void adam_kernel(float* p, const float* g, float* m, float* v, long long count, float lr_arg,
+                            const float* lr_dev, float b1, float b2, float eps, float gs, int vec) {
+  const float lr_t = lr_dev ? __ldg(lr_dev) : lr_arg;
+  const long long n4 = vec ? count >> 2 : 0;
+  const long long tid = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  const long long nth = static_cast<long long>(gridDim.x) * blockDim.x;
+  float4* p4 = reinterpret_cast<float4*>(p);
+  const float4* g4 = reinterpret_cast<const float4*>(g);
+  float4* m4 = reinterpret_cast<float4*>(m);
+  float4* v4 = reinterpret_cast<float4*>(v);
+  for (long long i = tid; i < n4; i += nth) {
+    const float4 gv = g4[i];
+    float4 mv = m4[i], vv = v4[i], pv = p4[i];
+    const float ga[4] = {gv.x * gs, gv.y * gs, gv.z * gs, gv.w * gs};
+    float ma[4] = {mv.x, mv.y, mv.z, mv.w}, va[4] = {vv.x, vv.y, vv.z, vv.w}, pa[4] = {pv.x, pv.y, pv.z, pv.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      ma[j] = b1 * ma[j] + (1.f - b1) * ga[j];
+      va[j] = b2 * va[j] + (1.f - b2) * ga[j] * ga[j];
+      pa[j] -= lr_t * ma[j] / (sqrtf(va[j]) + eps);
+    }
+    m4[i] = make_float4(ma[0], ma[1], ma[2], ma[3]);
+    v4[i] = make_float4(va[0], va[1], va[2], va[3]);
+    p4[i] = make_float4(pa[0], pa[1], pa[2], pa[3]);
+  }
+  for (long long i = (n4 << 2) + tid; i < count; i += nth) {
     const float gi = g[i] * gs;
     const float mi = b1 * m[i] + (1.f - b1) * gi;
     const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
@@ -158,8 +183,9 @@ __global__ void adam_kernel(float* p, const float* g, float* m, float* v, long l
   }
 }
 
-__global__ void rmsprop_kernel(float* p, const float* g, float* ms, long long count, float lr, float decay,
-                               float eps, float gs, float clip) {
+__global__ void rmsprop_kernel(float* p, const float* g, float* ms, long long count, float lr_arg, const float* lr_dev,
+                               float decay, float eps, float gs, float clip) {
+  const float lr = lr_dev ? __ldg(lr_dev) : lr_arg;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < count;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
     const float gi = g[i] * gs;
@@ -267,26 +293,56 @@ extern "C" int dpig_gp_penalty(dpig_ctx* ctx, const float* grad, int32_t n, int6
   return check_launch(ctx, "gp_penalty");
 }
 
+static bool aligned16(const void* a, const void* b, const void* c, const void* d) {
+  return ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) | reinterpret_cast<uintptr_t>(c) |
+           reinterpret_cast<uintptr_t>(d)) & 15) == 0;
+}
+
 extern "C" int dpig_adam_step(dpig_ctx* ctx, float* p, const float* g, float* m, float* v, int64_t count, float lr,
                               float beta1, float beta2, float eps, int32_t t, float grad_scale, dpig_stream stream) {
   DPIG_CHECK_CTX(ctx);
   if (!p || !g || !m || !v || t < 1) return set_error(ctx, DPIG_EINVAL, "adam_step: bad argument");
   const double lr_t = static_cast<double>(lr) * sqrt(1.0 - pow(static_cast<double>(beta2), t)) /
                       (1.0 - pow(static_cast<double>(beta1), t));
+  // the vector body needs 16-byte aligned arrays; otherwise everything goes through the scalar loop
   adam_kernel<<<gridn(count), 256, 0, static_cast<cudaStream_t>(stream)>>>(p, g, m, v, count, static_cast<float>(lr_t),
-                                                                           beta1, beta2, eps, grad_scale);
+                                                                           nullptr, beta1, beta2, eps, grad_scale,
+                                                                           aligned16(p, g, m, v) ? 1 : 0);
   ctx->launches++;
   return check_launch(ctx, "adam_step");
+}
+
+extern "C" int dpig_adam_step_dev(dpig_ctx* ctx, float* p, const float* g, float* m, float* v, int64_t count,
+                                  const float* lr_t_dev, float beta1, float beta2, float eps, float grad_scale,
+                                  dpig_stream stream) {
+  DPIG_CHECK_CTX(ctx);
+  if (!p || !g || !m || !v || !lr_t_dev) return set_error(ctx, DPIG_EINVAL, "adam_step_dev: null argument");
+  adam_kernel<<<gridn(count), 256, 0, static_cast<cudaStream_t>(stream)>>>(p, g, m, v, count, 0.f, lr_t_dev, beta1,
+                                                                           beta2, eps, grad_scale,
+                                                                           aligned16(p, g, m, v) ? 1 : 0);
+  ctx->launches++;
+  return check_launch(ctx, "adam_step_dev");
 }
 
 extern "C" int dpig_rmsprop_step(dpig_ctx* ctx, float* p, const float* g, float* ms, int64_t count, float lr,
                                  float decay, float eps, float grad_scale, float clip, dpig_stream stream) {
   DPIG_CHECK_CTX(ctx);
   if (!p || !g || !ms) return set_error(ctx, DPIG_EINVAL, "rmsprop_step: null argument");
-  rmsprop_kernel<<<gridn(count), 256, 0, static_cast<cudaStream_t>(stream)>>>(p, g, ms, count, lr, decay, eps,
+  rmsprop_kernel<<<gridn(count), 256, 0, static_cast<cudaStream_t>(stream)>>>(p, g, ms, count, lr, nullptr, decay, eps,
                                                                               grad_scale, clip);
   ctx->launches++;
   return check_launch(ctx, "rmsprop_step");
+}
+
+extern "C" int dpig_rmsprop_step_dev(dpig_ctx* ctx, float* p, const float* g, float* ms, int64_t count,
+                                     const float* lr_dev, float decay, float eps, float grad_scale, float clip,
+                                     dpig_stream stream) {
+  DPIG_CHECK_CTX(ctx);
+  if (!p || !g || !ms || !lr_dev) return set_error(ctx, DPIG_EINVAL, "rmsprop_step_dev: null argument");
+  rmsprop_kernel<<<gridn(count), 256, 0, static_cast<cudaStream_t>(stream)>>>(p, g, ms, count, 0.f, lr_dev, decay, eps,
+                                                                              grad_scale, clip);
+  ctx->launches++;
+  return check_launch(ctx, "rmsprop_step_dev");
 }
 
 extern "C" int dpig_clip(dpig_ctx* ctx, float* p, int64_t count, float lo, float hi, dpig_stream stream) {

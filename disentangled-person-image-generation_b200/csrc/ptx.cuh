@@ -100,6 +100,40 @@ __device__ __forceinline__ void tma_load_5d(void* dst, const CUtensorMap* m, uin
       : "memory");
 }
 
+// TMA store: shared::cta -> global tile (out-of-bounds parts of the box are not written), tracked by bulk async-groups
+// of the issuing thread.
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* m, const void* src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(m)),
+               "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit_group() {
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+// all bulk groups of this thread have finished READING their shared-memory source (the buffer may be rewritten)
+__device__ __forceinline__ void bulk_wait_group_read0() {
+  asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_wait_group0() {
+  asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+// named barrier among `count` threads (ids 1..15; 0 is __syncthreads)
+__device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t count) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
+// explicit shared-space 16-byte accesses (a generic-pointer ST/LD goes through the long scoreboard)
+__device__ __forceinline__ void sts128(uint32_t saddr, uint4 v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
+               : "memory");
+}
+__device__ __forceinline__ uint4 lds128(uint32_t saddr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(saddr)
+               : "memory");
+  return v;
+}
+
 // ---- CTA-pair (cta_group::2) variants: a cluster of two CTAs on one TPC runs one M=256 MMA; each CTA stages its own
 // 128 rows of A and half of the B rows, and every TMA completion is signalled on the LEADER CTA's mbarrier
 // (`bar_cluster` = shared::cluster address obtained with mapa).

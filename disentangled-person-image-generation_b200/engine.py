@@ -14,6 +14,7 @@ parameters, their gradients and the optimiser slots are flat fp32 arenas (one NC
 """
 import ctypes as C
 import math
+import os
 from collections import OrderedDict
 
 import numpy as np
@@ -323,6 +324,17 @@ class Stage1Engine:
             self.gp.v.fill_(1.0)
             self.dp.v.fill_(1.0)
         self.t = {"g": 0, "d": 0}
+        # step size of the next optimiser call, in device memory (dpig_adam_step_dev / dpig_rmsprop_step_dev): lets one
+        # captured CUDA graph serve every step although Adam's bias-corrected lr_t changes with t
+        self.lr_dev = {"g": torch.zeros(1, dtype=torch.float32, device=self.device),
+                       "d": torch.zeros(1, dtype=torch.float32, device=self.device)}
+        # whole-step CUDA graphs (forward + backward + update + weight re-pack = ~220 launches replayed by one
+        # cudaGraphLaunch): on by default on one GPU; with torch.distributed the NCCL exchanges would have to be
+        # captured too, opt in with DPIG_GRAPHS=2.  DPIG_GRAPHS=0 switches them off.
+        gmode = int(os.environ.get("DPIG_GRAPHS", "1"))
+        self.use_graphs = gmode >= 2 or (gmode == 1 and dist is None)
+        self._graphs = {}
+        self._eager_steps = {"g": 0, "d": 0}
         self.gp_alpha_fixed = False   # tests pin alpha to compare with the oracle
         self.g_lr = 2e-5
         self.d_lr = 2e-5
@@ -1194,21 +1206,63 @@ class Stage1Engine:
             self.p_d_real_fwd.run(s, timings)
         self.p_d_fake_fwd.run(s, timings)
 
+    def _step_size(self, which):
+        """The scalar the update kernel multiplies with: TF Adam's lr_t = lr*sqrt(1-b2^t)/(1-b1^t) (float64 on the
+        host, like dpig_adam_step) or the plain RMSProp lr."""
+        lr = float(np.float32(self.g_lr if which == "g" else self.d_lr))
+        if self.mode in ("wgan", "lsgan"):
+            return lr
+        b2 = float(np.float32(0.9 if self.mode == "wgan-gp" else 0.999))   # the betas reach the C entry as fp32
+        t = self.t[which]
+        return lr * math.sqrt(1.0 - b2 ** t) / (1.0 - 0.5 ** t)
+
     def _optim(self, which, s):
+        """All-reduce (N > 1), update, re-pack of the bf16 operand copies.  Reads the step size from self.lr_dev."""
         grp = self.gp if which == "g" else self.dp
-        lr = self.g_lr if which == "g" else self.d_lr
         if self.dist is not None:
             self.dist.all_reduce_sum(grp.grad)
         gs = 1.0 / self.world
-        self.t[which] += 1
         if self.mode in ("wgan", "lsgan"):
             clip = 0.01 if (self.mode == "wgan" and which == "d") else 0.0
-            self.ctx.rmsprop_step(ptr(grp.value), ptr(grp.grad), ptr(grp.v), grp.total, lr, 0.9, 1e-10, gs, clip, s)
+            self.ctx.rmsprop_step_dev(ptr(grp.value), ptr(grp.grad), ptr(grp.v), grp.total, ptr(self.lr_dev[which]), 0.9,
+                                      1e-10, gs, clip, s)
         else:
             b2 = 0.9 if self.mode == "wgan-gp" else 0.999
-            self.ctx.adam_step(ptr(grp.value), ptr(grp.grad), ptr(grp.m), ptr(grp.v), grp.total, lr, 0.5, b2, 1e-8,
-                               self.t[which], gs, s)
+            self.ctx.adam_step_dev(ptr(grp.value), ptr(grp.grad), ptr(grp.m), ptr(grp.v), grp.total,
+                                   ptr(self.lr_dev[which]), 0.5, b2, 1e-8, gs, s)
         self.pack_weights(which, s)
+
+    def _step(self, which, timings):
+        """One optimiser call.  The first two calls of each kind run eagerly (they also set the kernels' launch
+        attributes and warm NCCL); the third is captured into a CUDA graph while it runs, later calls replay it.
+        Per-launch timing (timings is not None) always runs eagerly."""
+        grads = self.g_grads if which == "g" else self.d_grads
+        self.t[which] += 1
+        self.lr_dev[which].fill_(self._step_size(which))      # a fill kernel on the current stream: ordered before the step
+        if not self.use_graphs or timings is not None:
+            grads(timings)
+            self._optim(which, torch.cuda.current_stream().cuda_stream)
+            return
+        g = self._graphs.get(which)
+        if g is None:
+            if self._eager_steps[which] < 2:
+                self._eager_steps[which] += 1
+                grads(None)
+                self._optim(which, torch.cuda.current_stream().cuda_stream)
+                return
+            graph = torch.cuda.CUDAGraph()
+            n0 = self.ctx.launch_count()
+            with torch.cuda.graph(graph):
+                grads(None)
+                self._optim(which, torch.cuda.current_stream().cuda_stream)
+            g = self._graphs[which] = (graph, self.ctx.launch_count() - n0)
+        g[0].replay()
+        self.ctx.replayed_launches += g[1]
+
+    def drop_graphs(self):
+        """Forget the captured step graphs (after anything that changes what a step launches: fast mode, pair mode,
+        a pinned GP alpha ...); the next steps re-capture."""
+        self._graphs = {}
 
     def g_grads(self, timings=None):
         """Forward + backward of g_loss = gan(D(G)) + 20*L1 w.r.t. Encoder+G (trainer.py:605-607, 622-624)."""
@@ -1247,12 +1301,10 @@ class Stage1Engine:
             self.p_gp.run(s, timings)
 
     def g_step(self, timings=None):
-        self.g_grads(timings)
-        self._optim("g", torch.cuda.current_stream().cuda_stream)
+        self._step("g", timings)
 
     def d_step(self, timings=None):
-        self.d_grads(timings)
-        self._optim("d", torch.cuda.current_stream().cuda_stream)
+        self._step("d", timings)
 
     def losses(self):
         """(g_gan, d_loss, L1) as Python floats -- a device->host read.  In wgan-gp mode d_loss includes

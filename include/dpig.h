@@ -322,6 +322,15 @@ int dpig_adam_step(dpig_ctx* ctx, float* p, const float* g, float* m, float* v, 
 /* TF RMSPropOptimizer (decay .9, momentum 0, eps 1e-10, ms initialised to ones) + optional clip */
 int dpig_rmsprop_step(dpig_ctx* ctx, float* p, const float* g, float* ms, int64_t count, float lr,
                       float decay, float eps, float grad_scale, float clip, dpig_stream stream);
+/* Graph-replayable forms: the step size is read from device memory at run time (lr_t_dev[0] = the bias-corrected
+ * Adam step lr*sqrt(1-b2^t)/(1-b1^t) of trainer.py:119-123 computed by the host; lr_dev[0] = the RMSProp lr), so one
+ * captured CUDA graph of "forward + backward + update" serves every step while t and the halved lr change. */
+int dpig_adam_step_dev(dpig_ctx* ctx, float* p, const float* g, float* m, float* v, int64_t count,
+                       const float* lr_t_dev, float beta1, float beta2, float eps, float grad_scale,
+                       dpig_stream stream);
+int dpig_rmsprop_step_dev(dpig_ctx* ctx, float* p, const float* g, float* ms, int64_t count,
+                          const float* lr_dev, float decay, float eps, float grad_scale, float clip,
+                          dpig_stream stream);
 int dpig_clip(dpig_ctx* ctx, float* p, int64_t count, float lo, float hi, dpig_stream stream);
 
 /* ---- image / pose ends (utils.py:88-89, 259-318) ---------------------------------------------- */

@@ -200,6 +200,9 @@ def run_conv_bwd_data(n, h, w, cin, cout, k, stride, addend=False, masked=False,
         ep.mask_in = mask_dev.data_ptr()
         ep.mask_neg = 0.2
         ep.out_masked = C.pointer(out2.struct())
+        # bias gradient of the layer below = column sums of the masked gradient, accumulated (+=) by the epilogue
+        colsum = torch.full((cin,), 0.5, device="cuda")
+        ep.colsum_masked = colsum.data_ptr()
     ep.upsample = 1
     ctx().conv2d_bwd_data(dys.ref(), ptr(b[0]), ptr(b[1]), k, k, stride, h, w, cin, C.byref(ep), stream())
     torch.cuda.synchronize()
@@ -213,6 +216,7 @@ def run_conv_bwd_data(n, h, w, cin, cout, k, stride, addend=False, masked=False,
     if masked:
         gm = gx * torch.where(mbits.bool(), 1.0, 0.2)
         info["err_masked"] = rel_err(out2.float(), gm)
+        info["err_colsum"] = rel_err(colsum.cpu() - 0.5, gm.sum(dim=(0, 1, 2)))
     return info
 
 
@@ -225,6 +229,9 @@ CONV_BWD_DATA_CASES = [
     dict(n=2, h=16, w=8, cin=256, cout=3, k=3, stride=1),
     dict(n=21, h=32, w=32, cin=256, cout=64, k=3, stride=1, addend=True, masked=True),
     dict(n=3, h=16, w=8, cin=128, cout=128, k=3, stride=2, addend=True, masked=True),
+    # odd input size: the four parity classes have different grids -> one launch per class (no merged launch)
+    dict(n=2, h=15, w=9, cin=64, cout=128, k=3, stride=2, addend=True, masked=True),
+    dict(n=40, h=32, w=16, cin=128, cout=256, k=3, stride=2, masked=True),   # many units per CTA, merged classes
 ]
 
 
@@ -239,6 +246,37 @@ def test_conv2d_bwd_data(case, tiling):
     assert info["err"] < 5e-5, info
     if "err_masked" in info:
         assert info["err_masked"] < 5e-5, info
+        assert info["err_colsum"] < 2e-4, info   # fp32 sums over up to 21k pixels, minus the 0.5 it started from
+
+
+def test_conv2d_bwd_data_merged_classes_equal_separate_launches(monkeypatch):
+    """Stride-2 data gradient: one launch running the four parity classes per pixel tile (default) against four
+    launches (DPIG_DGRAD_MERGE=0) -- same taps, same accumulation order per output, so the results are bit-identical."""
+    import ctypes as C
+    import dpig_b200
+    _lib, SplitTensor, ptr, split_ref = _imports()
+    outs = []
+    for merge in ("1", "0"):
+        monkeypatch.setenv("DPIG_DGRAD_MERGE", merge)
+        c = dpig_b200.Context(0)
+        g = torch.Generator().manual_seed(11)
+        n, h, w, cin, cout, k = 5, 32, 16, 128, 256, 5
+        dy = torch.randn((n, h // 2, w // 2, cout), generator=g)
+        wt = torch.randn((k, k, cin, cout), generator=g) * 0.05
+        dys = padded_split(dy)
+        _, b = pack_weights(wt.cuda().contiguous(), cout_pad=dys.c)
+        out = SplitTensor(n, h, w, cin, zero=True)
+        ep = _lib.ConvEpilogue()
+        ep.act = 0
+        ep.out = C.pointer(out.struct())
+        ep.upsample = 1
+        n0 = c.launch_count()
+        c.conv2d_bwd_data(dys.ref(), ptr(b[0]), ptr(b[1]), k, k, 2, h, w, cin, C.byref(ep), stream())
+        torch.cuda.synchronize()
+        outs.append((out.float().cpu(), c.launch_count() - n0))
+    assert outs[0][1] == 1 and outs[1][1] == 4
+    assert torch.equal(outs[0][0], outs[1][0])
+    assert float(outs[0][0].abs().max()) > 0.1
 
 
 def run_conv_bwd_filter(n, h, w, cin, cout, k, stride, seed=2):
@@ -464,6 +502,35 @@ def test_adam_and_pose():
         T.adam_step(pr, gr.double(), mr, vr, 2e-5, t)
     # fp32 parameters of magnitude ~3 quantise at 2.4e-7; the three updates are 2e-5 each
     assert float((pd.cpu().double() - pr).abs().max()) < 5e-7
+    # graph-replayable form: step size from device memory; vector body + scalar tail (1003 = 4*250 + 3) and an
+    # unaligned view (scalar loop only) give the bits of the scalar-argument entry
+    import math
+    for off in (0, 1):
+        q = torch.randn((1004,), generator=g)[off:off + 1003]
+        gq = torch.randn((1004,), generator=g)[off:off + 1003]
+        a = [t_.cuda() for t_ in (q.clone(), torch.zeros(1003), torch.zeros(1003))]
+        bfull = [torch.zeros(1004, device="cuda") for _ in range(3)]
+        bv = [t_[off:off + 1003] for t_ in bfull]
+        bv[0].copy_(q)
+        gfull = torch.zeros(1004, device="cuda")
+        gv = gfull[off:off + 1003]
+        gv.copy_(gq)
+        ga = gq.cuda()
+        lr_t = torch.tensor([float(np.float32(2e-5)) * math.sqrt(1.0 - float(np.float32(0.999)) ** 2) / (1.0 - 0.5 ** 2)], dtype=torch.float32).cuda()
+        ctx().adam_step(ptr(a[0]), ptr(ga), ptr(a[1]), ptr(a[2]), 1003, 2e-5, 0.5, 0.999, 1e-8, 2, 0.5, stream())
+        ctx().adam_step_dev(ptr(bv[0]), ptr(gv), ptr(bv[1]), ptr(bv[2]), 1003, ptr(lr_t), 0.5, 0.999, 1e-8, 0.5, stream())
+        torch.cuda.synchronize()
+        for x_, y_ in zip(a, bv):
+            assert torch.equal(x_, y_)
+    r1 = torch.randn((777,), generator=g).cuda()
+    r2 = r1.clone()
+    gr_ = torch.randn((777,), generator=g).cuda()
+    ms1, ms2 = torch.ones(777, device="cuda"), torch.ones(777, device="cuda")
+    lr_d = torch.tensor([5e-5], dtype=torch.float32).cuda()
+    ctx().rmsprop_step(ptr(r1), ptr(gr_), ptr(ms1), 777, 5e-5, 0.9, 1e-10, 1.0, 0.01, stream())
+    ctx().rmsprop_step_dev(ptr(r2), ptr(gr_), ptr(ms2), 777, ptr(lr_d), 0.9, 1e-10, 1.0, 0.01, stream())
+    torch.cuda.synchronize()
+    assert torch.equal(r1, r2) and torch.equal(ms1, ms2)
     assert rel_err(pd.cpu().double() - p.double(), pr - p.double()) < 2e-2
     from dpig_b200 import synth
     batch = synth.make_batch(3, 128, 64, seed=5)
