@@ -20,6 +20,7 @@ struct dpig_ctx {
   bool fast_mode = false;  // hi-plane only (single bf16 MMA pass); NOT the parity mode
   int pair_mode = 1;       // conv kernels as 2-CTA clusters (cta_group::2): 0 never, 1 where it wins, 2 wherever legal
   bool merge_planes = true;  // fetch hi+lo with one TMA instruction where the layout allows (DPIG_CONV_MERGE=0 disables)
+  bool epi_tma = true;       // split-bf16 conv outputs leave the SM as TMA tensor stores (DPIG_EPI_TMA=0: per-lane stores)
   bool dgrad_merge = true;   // stride-2 data gradients: the four parity classes in one launch (DPIG_DGRAD_MERGE=0: four)
   int wgrad_group = 0;     // filter taps per wgrad CTA: 0 = default (1); DPIG_WGRAD_GROUP
   int wgrad_px = 0;        // pixels per wgrad pipeline step: 0 = auto, 32 / 64 forced; DPIG_WGRAD_PX

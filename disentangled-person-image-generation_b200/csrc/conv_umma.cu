@@ -76,6 +76,11 @@ struct ConvUmmaParams {
   int mask_in_words;
   float mask_neg;
   float* colsum;  // [cout] += column sums (over pixels) of the masked output: the bias gradient of the layer below
+  // TMA tensor-store maps of the split-bf16 outputs, [index][plane hi / lo]; index = parity class of a merged stride-2
+  // data gradient, or 2x2 replica of the fused upsample, else 0.  Box {32 channels, BW, BH, BN}, SWIZZLE_64B.
+  CUtensorMap out_map[4][2];
+  CUtensorMap out2_map[4][2];
+  int out_tma, out2_tma;
 };
 
 __device__ __forceinline__ uint8_t* align1024(uint8_t* p) {
@@ -124,19 +129,30 @@ __device__ __forceinline__ void store_split32(__nv_bfloat16* hi, __nv_bfloat16* 
 
 constexpr int kEpiWarps = 8;          // two epilogue warps per TMEM lane group: they take alternate 32-column chunks
 constexpr int kConvThreads = 64 + 32 * kEpiWarps;
-constexpr uint32_t kEpiBytesPerWarp = 4096;  // 32 pixel rows x (64 B hi + 64 B lo)  or  32 x 128 B fp32
+// Epilogue staging in shared memory.  The eight epilogue warps form two SETS (the warps taking the even / the odd
+// 32-column chunks; each set holds one warp per TMEM lane group = all 128 pixel rows of the tile).  One 16 KB buffer per
+// set: [hi plane: 128 rows x 64 B][lo plane: 128 rows x 64 B]; warp lg owns rows lg*32 .. lg*32+31 of both planes.
+// 16-byte piece q of row r sits at r*64 + ((q ^ ((r >> 1) & 3)) << 4): that is TMA's SWIZZLE_64B pattern (buffers are
+// 1024-byte aligned), so the same buffer is bank-conflict free for "thread = row" accesses AND a valid source box
+// {32 channels, BW, BH, BN} of a TMA tensor store -- the split-bf16 outputs leave the SM as two bulk tensor stores per
+// chunk issued by one thread (TMA clips at the tensor edge and walks the parity-strided outputs of stride-2 gradients /
+// the 2x2 replicas of the fused upsample) instead of 8 shuffles + 8 predicated 16-byte stores per lane.  Measured before
+// the change (tests/bench_dgrad_micro.py, profiles/r01_dgrad_epilogue_micro.txt): every split output cost ~2.6k clk per
+// chunk and warp -- short-K layers (stride-2 parity classes, 1x1) ran at the epilogue's speed, not the tensor pipe's.
+constexpr uint32_t kEpiSetBytes = 16384, kEpiLoOff = 8192;
+constexpr uint32_t kEpiBytes = 2 * kEpiSetBytes;
 
-// Byte offset of 16-byte piece `piece` of row `row` in a warp-private staging tile; XOR swizzles keep both the
-// "thread = row" and the "4 (8) lanes per row" access patterns free of shared-memory bank conflicts.
-__device__ __forceinline__ uint32_t swz64(int row, int piece) {   // 64 B rows, 4 pieces
+// Byte offset of 16-byte piece `piece` of row `row` (relative to the warp's first row; warps start 2048 B apart).
+__device__ __forceinline__ uint32_t swz64(int row, int piece) {   // 64 B rows, 4 pieces (split-bf16 planes)
   return row * 64 + ((piece ^ ((row >> 1) & 3)) << 4);
 }
-__device__ __forceinline__ uint32_t swz128(int row, int piece) {  // 128 B rows, 8 pieces
-  return row * 128 + ((piece ^ (row & 7)) << 4);
+// fp32 staging (128 B rows, warp-private, never a TMA source): rows 0-15 in the warp's hi slot, 16-31 in its lo slot
+__device__ __forceinline__ uint32_t swz128(int row, int piece) {
+  return ((row & 16) ? kEpiLoOff : 0u) + (row & 15) * 128 + ((piece ^ (row & 7)) << 4);
 }
 
-// thread's 32 channels -> staging rows (hi plane at +0, lo plane at +2048)
-__device__ __forceinline__ void epi_stage_split(uint8_t* stage, const float (&f)[32], int lane, bool with_lo) {
+// thread's 32 channels -> its staging row (hi plane at +0, lo plane at +kEpiLoOff)
+__device__ __forceinline__ void epi_stage_split(uint32_t st, const float (&f)[32], int lane, bool with_lo) {
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
     uint32_t h[4], l[4];
@@ -148,13 +164,14 @@ __device__ __forceinline__ void epi_stage_split(uint8_t* stage, const float (&f)
       h[jj] = pack2(h0, h1);
       l[jj] = pack2(l0, l1);
     }
-    *reinterpret_cast<uint4*>(stage + swz64(lane, q)) = make_uint4(h[0], h[1], h[2], h[3]);
-    if (with_lo) *reinterpret_cast<uint4*>(stage + 2048 + swz64(lane, q)) = make_uint4(l[0], l[1], l[2], l[3]);
+    ptx::sts128(st + swz64(lane, q), make_uint4(h[0], h[1], h[2], h[3]));
+    if (with_lo) ptx::sts128(st + kEpiLoOff + swz64(lane, q), make_uint4(l[0], l[1], l[2], l[3]));
   }
 }
 
-// staging rows -> global: each instruction writes 8 pixel rows x 64 contiguous bytes per plane
-__device__ __forceinline__ void epi_scatter_rows(const uint8_t* stage, __nv_bfloat16* hi, __nv_bfloat16* lo,
+// staging rows -> global without TMA (outputs whose layout TMA cannot address): each instruction writes 8 pixel rows
+// x 64 contiguous bytes per plane
+__device__ __forceinline__ void epi_scatter_rows(uint32_t st, __nv_bfloat16* hi, __nv_bfloat16* lo,
                                                  long long ps, int cbase, int pix, bool valid, int lane) {
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
@@ -163,8 +180,8 @@ __device__ __forceinline__ void epi_scatter_rows(const uint8_t* stage, __nv_bflo
     const int vq = __shfl_sync(0xffffffffu, static_cast<int>(valid), q);
     if (vq) {
       const long long off = static_cast<long long>(pq) * ps + cbase + pc * 8;
-      *reinterpret_cast<uint4*>(hi + off) = *reinterpret_cast<const uint4*>(stage + swz64(q, pc));
-      if (lo) *reinterpret_cast<uint4*>(lo + off) = *reinterpret_cast<const uint4*>(stage + 2048 + swz64(q, pc));
+      *reinterpret_cast<uint4*>(hi + off) = ptx::lds128(st + swz64(q, pc));
+      if (lo) *reinterpret_cast<uint4*>(lo + off) = ptx::lds128(st + kEpiLoOff + swz64(q, pc));
     }
   }
 }
@@ -173,7 +190,7 @@ __device__ __forceinline__ void epi_scatter_rows(const uint8_t* stage, __nv_bflo
 // issued before the first staging store: in program order (load, load, store) x 4 the compiler kept each store behind
 // its loads and the next loads behind the store, i.e. four exposed global latencies per chunk (30 % of all stall
 // samples of a 128-channel residual layer, profiles/r01_epilogue_ncu.txt).
-__device__ __forceinline__ void epi_gather_rows(uint8_t* stage, const __nv_bfloat16* hi, const __nv_bfloat16* lo,
+__device__ __forceinline__ void epi_gather_rows(uint32_t st, const __nv_bfloat16* hi, const __nv_bfloat16* lo,
                                                 long long ps, int cbase, int pix, bool valid, int lane) {
   uint4 a[4], b[4];
   const int pc = lane & 3;
@@ -193,22 +210,44 @@ __device__ __forceinline__ void epi_gather_rows(uint8_t* stage, const __nv_bfloa
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const int q = 8 * i + (lane >> 2);
-    *reinterpret_cast<uint4*>(stage + swz64(q, pc)) = a[i];
-    if (lo) *reinterpret_cast<uint4*>(stage + 2048 + swz64(q, pc)) = b[i];
+    ptx::sts128(st + swz64(q, pc), a[i]);
+    if (lo) ptx::sts128(st + kEpiLoOff + swz64(q, pc), b[i]);
   }
 }
 
+// What an epilogue warp knows about the tile it is draining.
+struct EpiTile {
+  int w0, h0, n0;     // origin of the pixel box in the (class) output grid = TMA store coordinates
+  int cls;            // parity class (merged stride-2 data gradient), else 0
+  uint32_t set_base;  // shared address of the warp set's staging buffer
+  uint32_t bar_id;    // named barrier of the set (4 warps)
+  bool leader;        // the one thread of the set that issues / tracks the TMA stores
+};
+
 // One 32-channel chunk of one accumulator row (pixel): bias / activation / residual / sign mask / outputs.
-// v[i] = raw fp32 accumulator of channel cbase+i; all 32 lanes of the warp call this together (the global traffic
-// is staged through the warp-private tile `stage`).
-// colsum: lane l's running total of channel cbase + l of the masked output (see the flush in the kernel).
-__device__ __forceinline__ void epi_chunk(const ConvUmmaParams& p, uint8_t* stage, const uint32_t (&v)[32], int cbase,
-                                          bool valid, int lpix, int ppix, const float* cbias, int lane, float& colsum) {
+// v[i] = raw fp32 accumulator of channel cbase+i; all 32 lanes of the warp, and all four warps of the set, call this
+// together.  colsum: lane l's running total of channel cbase + l of the masked output (see the flush in the kernel).
+__device__ __forceinline__ void epi_chunk(const ConvUmmaParams& p, const EpiTile& t, uint32_t st,
+                                          const uint32_t (&v)[32], int cbase, bool valid, int lpix, int ppix,
+                                          const float* cbias, int lane, float& colsum) {
   const int nvalid = min(32, p.cout - cbase);
-  if (nvalid <= 0) return;  // warp-uniform
+  if (nvalid <= 0) return;  // uniform over the warp set
   const bool full32 = (nvalid == 32);
+  // The set's buffer may still be read by the TMA stores of the previous chunk: whoever writes staging rows next first
+  // lets the leader wait for those reads and tells the other warps (every condition below is uniform over the set).
+  bool pending = p.out_tma || p.out2_tma;
+  auto acquire = [&]() {
+    if (pending) {
+      if (t.leader) ptx::bulk_wait_group_read0();
+      ptx::named_bar_sync(t.bar_id, 128);
+      pending = false;
+    }
+  };
   float f[32];
   uint32_t mbits = 0;
+  // sign mask of the consuming activation (second output): loaded first, used last
+  uint32_t mi = 0xFFFFFFFFu;
+  if (p.out2_hi && p.mask_in && valid) mi = __ldg(p.mask_in + static_cast<long long>(ppix) * p.mask_in_words + (cbase >> 5));
   // bias of the chunk's 32 channels: ONE coalesced load per warp, broadcast by shuffles.  (32 predicated scalar loads,
   // each followed by its dependent add, cost ~10k clk per chunk on the long scoreboard -- half of the whole tile time
   // of every short-K layer, profiles/r01_epilogue_bias_ncu.txt.)
@@ -219,15 +258,15 @@ __device__ __forceinline__ void epi_chunk(const ConvUmmaParams& p, uint8_t* stag
   if (cbias) {  // per-pixel (border class) bias row: vector loads, issued back to back
     if (full32) {
       const float4* cb4 = reinterpret_cast<const float4*>(cbias + cbase);
-      float4 t[8];
+      float4 tt[8];
 #pragma unroll
-      for (int q = 0; q < 8; ++q) t[q] = __ldg(cb4 + q);
+      for (int q = 0; q < 8; ++q) tt[q] = __ldg(cb4 + q);
 #pragma unroll
       for (int q = 0; q < 8; ++q) {
-        f[4 * q] += t[q].x;
-        f[4 * q + 1] += t[q].y;
-        f[4 * q + 2] += t[q].z;
-        f[4 * q + 3] += t[q].w;
+        f[4 * q] += tt[q].x;
+        f[4 * q + 1] += tt[q].y;
+        f[4 * q + 2] += tt[q].z;
+        f[4 * q + 3] += tt[q].w;
       }
     } else {
 #pragma unroll
@@ -246,11 +285,12 @@ __device__ __forceinline__ void epi_chunk(const ConvUmmaParams& p, uint8_t* stag
   // ---- residual / addend
   if (p.add_hi) {
     if (full32 && (p.add_ps % 8 == 0)) {
-      epi_gather_rows(stage, p.add_hi, p.add_lo, p.add_ps, cbase, ppix, valid, lane);
+      acquire();
+      epi_gather_rows(st, p.add_hi, p.add_lo, p.add_ps, cbase, ppix, valid, lane);
       __syncwarp();
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
-        const uint4 a = *reinterpret_cast<const uint4*>(stage + swz64(lane, q));
+        const uint4 a = ptx::lds128(st + swz64(lane, q));
         const uint32_t aw[4] = {a.x, a.y, a.z, a.w};
 #pragma unroll
         for (int jj = 0; jj < 4; ++jj) {
@@ -258,7 +298,7 @@ __device__ __forceinline__ void epi_chunk(const ConvUmmaParams& p, uint8_t* stag
           f[q * 8 + 2 * jj + 1] += bf16_bits_to_float(aw[jj] >> 16);
         }
         if (p.add_lo) {
-          const uint4 b2 = *reinterpret_cast<const uint4*>(stage + 2048 + swz64(lane, q));
+          const uint4 b2 = ptx::lds128(st + kEpiLoOff + swz64(lane, q));
           const uint32_t bw[4] = {b2.x, b2.y, b2.z, b2.w};
 #pragma unroll
           for (int jj = 0; jj < 4; ++jj) {
@@ -282,12 +322,26 @@ __device__ __forceinline__ void epi_chunk(const ConvUmmaParams& p, uint8_t* stag
   if (p.mask_out && valid) p.mask_out[static_cast<long long>(lpix) * p.mask_out_words + (cbase >> 5)] = mbits;
   // ---- split-bf16 output
   if (p.out_hi) {
-    if (full32 && (p.out_ps % 8 == 0)) {
-      epi_stage_split(stage, f, lane, p.out_lo != nullptr);
+    if (full32 && p.out_tma) {
+      acquire();
+      epi_stage_split(st, f, lane, p.out_lo != nullptr);
+      ptx::fence_proxy_async();   // generic-proxy writes of the rows -> visible to the async proxy
+      ptx::named_bar_sync(t.bar_id, 128);
+      if (t.leader) {
+        for (int r = 0; r < p.rep * p.rep; ++r) {   // rep = 2: the four replicas of the fused nearest-neighbour upsample
+          ptx::tma_store_4d(&p.out_map[t.cls + r][0], t.set_base, cbase, t.w0, t.h0, t.n0);
+          if (p.out_lo) ptx::tma_store_4d(&p.out_map[t.cls + r][1], t.set_base + kEpiLoOff, cbase, t.w0, t.h0, t.n0);
+        }
+        ptx::bulk_commit_group();
+      }
+      pending = true;
+    } else if (full32 && (p.out_ps % 8 == 0)) {
+      acquire();
+      epi_stage_split(st, f, lane, p.out_lo != nullptr);
       __syncwarp();
       for (int dy = 0; dy < p.rep; ++dy)
         for (int dx = 0; dx < p.rep; ++dx)
-          epi_scatter_rows(stage, p.out_hi, p.out_lo, p.out_ps, cbase, ppix + dy * p.out_W + dx, valid, lane);
+          epi_scatter_rows(st, p.out_hi, p.out_lo, p.out_ps, cbase, ppix + dy * p.out_W + dx, valid, lane);
       __syncwarp();
     } else if (valid) {
       for (int dy = 0; dy < p.rep; ++dy)
@@ -299,9 +353,11 @@ __device__ __forceinline__ void epi_chunk(const ConvUmmaParams& p, uint8_t* stag
   // ---- fp32 output
   if (p.out_f32) {
     if (full32 && (p.out_f32_ps % 4 == 0)) {
+      acquire();
 #pragma unroll
       for (int q = 0; q < 8; ++q)
-        *reinterpret_cast<float4*>(stage + swz128(lane, q)) = make_float4(f[4 * q], f[4 * q + 1], f[4 * q + 2], f[4 * q + 3]);
+        ptx::sts128(st + swz128(lane, q), make_uint4(__float_as_uint(f[4 * q]), __float_as_uint(f[4 * q + 1]),
+                                                     __float_as_uint(f[4 * q + 2]), __float_as_uint(f[4 * q + 3])));
       __syncwarp();
       for (int dy = 0; dy < p.rep; ++dy)
         for (int dx = 0; dx < p.rep; ++dx) {
@@ -311,8 +367,8 @@ __device__ __forceinline__ void epi_chunk(const ConvUmmaParams& p, uint8_t* stag
             const int pq = __shfl_sync(0xffffffffu, ppix, q);
             const int vq = __shfl_sync(0xffffffffu, static_cast<int>(valid), q);
             if (vq)
-              *reinterpret_cast<float4*>(p.out_f32 + static_cast<long long>(pq + dy * p.out_W + dx) * p.out_f32_ps + cbase + pc * 4) =
-                  *reinterpret_cast<const float4*>(stage + swz128(q, pc));
+              *reinterpret_cast<uint4*>(p.out_f32 + static_cast<long long>(pq + dy * p.out_W + dx) * p.out_f32_ps + cbase + pc * 4) =
+                  ptx::lds128(st + swz128(q, pc));
           }
         }
       __syncwarp();
@@ -328,14 +384,24 @@ __device__ __forceinline__ void epi_chunk(const ConvUmmaParams& p, uint8_t* stag
   }
   // ---- second output multiplied by the incoming sign mask (backward of ReLU / LeakyReLU)
   if (p.out2_hi) {
-    uint32_t mi = 0xFFFFFFFFu;
-    if (p.mask_in && valid) mi = p.mask_in[static_cast<long long>(ppix) * p.mask_in_words + (cbase >> 5)];
 #pragma unroll
     for (int i = 0; i < 32; ++i) f[i] *= ((mi >> i) & 1u) ? 1.f : p.mask_neg;
-    if (full32 && (p.out2_ps % 8 == 0)) {
-      epi_stage_split(stage, f, lane, p.out2_lo != nullptr);
+    if (full32 && p.out2_tma) {
+      acquire();
+      epi_stage_split(st, f, lane, p.out2_lo != nullptr);
+      ptx::fence_proxy_async();
+      ptx::named_bar_sync(t.bar_id, 128);
+      if (t.leader) {
+        ptx::tma_store_4d(&p.out2_map[t.cls][0], t.set_base, cbase, t.w0, t.h0, t.n0);
+        if (p.out2_lo) ptx::tma_store_4d(&p.out2_map[t.cls][1], t.set_base + kEpiLoOff, cbase, t.w0, t.h0, t.n0);
+        ptx::bulk_commit_group();
+      }
+      pending = true;
+    } else if (full32 && (p.out2_ps % 8 == 0)) {
+      acquire();
+      epi_stage_split(st, f, lane, p.out2_lo != nullptr);
       __syncwarp();
-      epi_scatter_rows(stage, p.out2_hi, p.out2_lo, p.out2_ps, cbase, ppix, valid, lane);
+      epi_scatter_rows(st, p.out2_hi, p.out2_lo, p.out2_ps, cbase, ppix, valid, lane);
       __syncwarp();
     } else if (valid) {
       store_split32(p.out2_hi, p.out2_lo, static_cast<long long>(ppix) * p.out2_ps + cbase, f, nvalid, false);
@@ -344,6 +410,7 @@ __device__ __forceinline__ void epi_chunk(const ConvUmmaParams& p, uint8_t* stag
       // bias gradient of the consuming layer = column sums of this masked gradient.  Transpose-reduce over the
       // warp's 32 pixel rows in 31 shuffles: after step `off` every lane keeps the half of its values whose channel
       // index has bit `off` equal to its lane-id bit, so lane l ends with the total of channel cbase + l.
+      // (Runs while the TMA store of the rows above drains.)
       if (!valid) {
 #pragma unroll
         for (int i = 0; i < 32; ++i) f[i] = 0.f;
@@ -383,12 +450,12 @@ conv_umma_kernel(const __grid_constant__ ConvUmmaParams p) {
   uint8_t* smem = align1024(smem_raw);
   const uint32_t b_off = p.planes * kABytes;
   const uint32_t stage_bytes = p.planes * (kABytes + p.b_bytes);
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + p.stages * stage_bytes);
+  uint8_t* epi_smem = smem + p.stages * stage_bytes;        // 2 x kEpiSetBytes, 1024-byte aligned (TMA store source)
+  uint64_t* full = reinterpret_cast<uint64_t*>(epi_smem + kEpiBytes);
   uint64_t* empty = full + p.stages;
   uint64_t* tmem_full = empty + p.stages;   // [2]
   uint64_t* tmem_empty = tmem_full + 2;     // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
-  uint8_t* epi_smem = smem + p.stages * stage_bytes + 256;  // kEpiWarps x kEpiBytesPerWarp, 256 B past the barriers
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -559,7 +626,11 @@ conv_umma_kernel(const __grid_constant__ ConvUmmaParams p) {
     const int tq = r / p.BW;
     const int hl = tq % p.BH;
     const int nl = tq / p.BH;
-    uint8_t* stage = epi_smem + ew * kEpiBytesPerWarp;
+    EpiTile et;
+    et.set_base = ptx::smem_u32(epi_smem) + cpar * kEpiSetBytes;
+    et.bar_id = 1 + cpar;
+    et.leader = (lg == 0 && lane == 0);
+    const uint32_t st = et.set_base + lg * 2048;   // this warp's 32 rows of the hi plane
     const uint32_t lead_tmem_empty[2] = {kPair ? ptx::mapa_u32(ptx::smem_u32(&tmem_empty[0]), 0) : 0u,
                                          kPair ? ptx::mapa_u32(ptx::smem_u32(&tmem_empty[1]), 0) : 0u};
     // Bias-gradient column sums stay in registers across all tiles of one channel block (a warp owns at most four
@@ -593,6 +664,10 @@ conv_umma_kernel(const __grid_constant__ ConvUmmaParams p) {
       const int th = (pt / p.tiles_w) % p.tiles_h;
       const int tn = pt / (p.tiles_w * p.tiles_h);
       const int w = tw * p.BW + wl, h = th * p.BH + hl, n = tn * p.BN + nl;
+      et.w0 = tw * p.BW;
+      et.h0 = th * p.BH;
+      et.n0 = tn * p.BN;
+      et.cls = cls;
       const bool valid = (nl < p.BN) && (w < p.Wo) && (h < p.Ho) && (n < p.No);
       const int lpix = (n * p.Ho + h) * p.Wo + w;  // logical pixel (< 2^31 for every supported shape)
       const int py = h * p.sh + p.cls_oh[cls], px = w * p.sw + p.cls_ow[cls];
@@ -625,7 +700,7 @@ conv_umma_kernel(const __grid_constant__ ConvUmmaParams p) {
           released = true;
         }
         float csum = 0.f;
-        epi_chunk(p, stage, v, nt * p.block_n + c0, valid, lpix, ppix, cbias, lane, csum);
+        epi_chunk(p, et, st, v, nt * p.block_n + c0, valid, lpix, ppix, cbias, lane, csum);
         const int k = (ci - cpar) / (kEpiWarps / 4);   // this warp's k-th chunk of the block
         cs0 += k == 0 ? csum : 0.f;
         cs1 += k == 1 ? csum : 0.f;
@@ -642,6 +717,7 @@ conv_umma_kernel(const __grid_constant__ ConvUmmaParams p) {
       }
     }
     flush_colsum();
+    if (et.leader) ptx::bulk_wait_group0();   // the last TMA stores read this CTA's shared memory
   }
 
   ptx::tc_fence_before();
@@ -856,7 +932,8 @@ wgrad_umma_kernel(const __grid_constant__ WgradParams p) {
 
 // ------------------------------------------------------------------------------------- host
 static int encode_map(dpig_ctx* ctx, CUtensorMap* map, const void* base, int rank,
-                      const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box) {
+                      const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box,
+                      CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B) {
   cuuint64_t gdim[5];
   cuuint64_t gstr[4];
   cuuint32_t bdim[5];
@@ -874,7 +951,7 @@ static int encode_map(dpig_ctx* ctx, CUtensorMap* map, const void* base, int ran
   if (reinterpret_cast<uintptr_t>(base) % 16) return set_error(ctx, DPIG_EINVAL, "tensor map: base not 16B aligned");
   CUresult r = ctx->encode_tiled(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(base),
                                  gdim, gstr, bdim, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                                 CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                 swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return set_error(ctx, DPIG_ECUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
   return DPIG_OK;
@@ -998,6 +1075,56 @@ struct EpilogueGeom {
   int sh, sw, oh, ow, rep, out_H, out_W;
 };
 
+// TMA tensor-store maps of one split-bf16 output: per index (parity class / upsample replica) a 4-D view (C, W', H', N)
+// of the pixels {oy + step*h', ox + step*w'}, box {32 channels, BW, BH, BN}, SWIZZLE_64B (the staging layout of the
+// epilogue).  *use = 0 when the layout cannot be addressed by TMA (the epilogue then scatters rows itself).
+static int store_maps(dpig_ctx* ctx, CUtensorMap (*maps)[2], int* use, const dpig_tensor* t, const ConvUmmaParams& P,
+                      const EpilogueGeom& g, bool replicas) {
+  *use = 0;
+  if (!ctx->epi_tma || t->pix_stride % 8 || t->c < 32 || P.cout < 32) return DPIG_OK;
+  if (reinterpret_cast<uintptr_t>(t->hi) % 16 || reinterpret_cast<uintptr_t>(t->lo) % 16) return DPIG_OK;
+  const int step = g.sh;
+  int nidx = 1;
+  int oy[4] = {g.oh, 0, 0, 0}, ox[4] = {g.ow, 0, 0, 0};
+  if (P.nclass > 1) {
+    nidx = P.nclass;
+    for (int c = 0; c < nidx; ++c) {
+      oy[c] = P.cls_oh[c];
+      ox[c] = P.cls_ow[c];
+    }
+  } else if (g.rep > 1) {
+    if (!replicas || g.rep != 2) return DPIG_OK;
+    nidx = 4;
+    for (int r = 0; r < 4; ++r) {
+      oy[r] = r / 2;
+      ox[r] = r % 2;
+    }
+  }
+  const uint64_t ps = static_cast<uint64_t>(t->pix_stride);
+  for (int i = 0; i < nidx; ++i) {
+    const int W2 = (t->w - ox[i] + step - 1) / step, H2 = (t->h - oy[i] + step - 1) / step;
+    if (W2 <= 0 || H2 <= 0) return DPIG_OK;
+    uint64_t dims[4] = {static_cast<uint64_t>(t->c), static_cast<uint64_t>(W2), static_cast<uint64_t>(H2),
+                        static_cast<uint64_t>(t->n)};
+    uint64_t strides[3] = {ps * 2 * step, ps * 2 * t->w * step, ps * 2 * t->w * t->h};
+    uint32_t box[4] = {32, static_cast<uint32_t>(P.BW), static_cast<uint32_t>(P.BH), static_cast<uint32_t>(P.BN)};
+    for (int pln = 0; pln < 2; ++pln) {
+      const void* plane = pln ? t->lo : t->hi;
+      if (!plane) {
+        maps[i][1] = maps[i][0];
+        continue;
+      }
+      const char* base = static_cast<const char*>(plane) + (static_cast<uint64_t>(oy[i]) * t->w + ox[i]) * ps * 2;
+      int rc = encode_map(ctx, &maps[i][pln], base, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_64B);
+      if (rc) return rc;
+    }
+  }
+  for (int i = nidx; i < 4; ++i)
+    for (int pln = 0; pln < 2; ++pln) maps[i][pln] = maps[0][pln];
+  *use = 1;
+  return DPIG_OK;
+}
+
 static int fill_epilogue(dpig_ctx* ctx, ConvUmmaParams& P, const dpig_conv_epilogue* ep,
                          const EpilogueGeom& g, int n, int cout) {
   P.bias = ep->bias;
@@ -1023,12 +1150,14 @@ static int fill_epilogue(dpig_ctx* ctx, ConvUmmaParams& P, const dpig_conv_epilo
     P.out_hi = static_cast<__nv_bfloat16*>(ep->out->hi);
     P.out_lo = static_cast<__nv_bfloat16*>(ep->out->lo);
     P.out_ps = ep->out->pix_stride;
+    if ((rc = store_maps(ctx, P.out_map, &P.out_tma, ep->out, P, g, true))) return rc;
   }
   if (ep->out_masked) {
     if ((rc = chk(ep->out_masked, "out_masked"))) return rc;
     P.out2_hi = static_cast<__nv_bfloat16*>(ep->out_masked->hi);
     P.out2_lo = static_cast<__nv_bfloat16*>(ep->out_masked->lo);
     P.out2_ps = ep->out_masked->pix_stride;
+    if ((rc = store_maps(ctx, P.out2_map, &P.out2_tma, ep->out_masked, P, g, false))) return rc;
   }
   if (ep->addend) {
     if ((rc = chk(ep->addend, "addend"))) return rc;
@@ -1054,7 +1183,7 @@ static int fill_epilogue(dpig_ctx* ctx, ConvUmmaParams& P, const dpig_conv_epilo
 static int launch_conv(dpig_ctx* ctx, ConvUmmaParams& P, cudaStream_t stream) {
   P.planes = ctx->fast_mode ? 1 : P.planes;
   const uint32_t stage_bytes = P.planes * (kABytes + P.b_bytes);
-  const uint32_t extra = 1024 + 256 + kEpiWarps * kEpiBytesPerWarp;  // alignment slack + barriers + epilogue staging
+  const uint32_t extra = 1024 + 256 + kEpiBytes;  // alignment slack + barriers + epilogue staging
   int stages = (ctx->max_smem_optin - static_cast<int>(extra)) / static_cast<int>(stage_bytes);
   if (stages > 6) stages = 6;
   if (stages < 2) return set_error(ctx, DPIG_EUNSUPPORTED, "conv tile does not fit shared memory");
