@@ -61,6 +61,8 @@ extern "C" int dpig_ctx_create(int device, dpig_ctx** out) {
   if (const char* e = getenv("DPIG_CONV_MERGE")) ctx->merge_planes = atoi(e) != 0;
   if (const char* e = getenv("DPIG_DGRAD_MERGE")) ctx->dgrad_merge = atoi(e) != 0;
   if (const char* e = getenv("DPIG_EPI_TMA")) ctx->epi_tma = atoi(e) != 0;
+  if (const char* e = getenv("DPIG_WGRAD_PAIR")) ctx->wgrad_pair = atoi(e) != 0;
+  if (const char* e = getenv("DPIG_WIDE_B")) ctx->wide_b = atoi(e) != 0;
   *out = ctx;
   return DPIG_OK;
 }

@@ -53,6 +53,12 @@ struct ConvUmmaParams {
   int tiles_w, tiles_h, tiles_n;
   int Wo, Ho, No;
   int block_n, cout, stages;
+  // wide-B form of the three split-bf16 passes (single-CTA kernel, block_n <= 128): the hi and lo weight rows sit back
+  // to back in a stage, so ONE N = 2*block_n MMA computes A_hi*B_hi | A_hi*B_lo into two column ranges of the
+  // accumulator and a second N = block_n MMA adds A_lo*B_hi; the epilogue sums the two ranges.  Same tensor time, but
+  // the A_hi tile is read from shared memory once instead of twice: 20 KB instead of 24 KB per 16-deep K slice of a
+  // 128-wide tile, whose MMA rate is capped by the 128 B/clk shared-memory port.
+  int wide_b;
   int pair;  // 1: launched as 2-CTA clusters running cta_group::2 MMAs (b_bytes = this CTA's half of the B rows)
   // hi and lo planes fetched by ONE TMA instruction (map slot [..][0] then has a trailing "plane" dimension)
   int a_merged, b_merged;
@@ -442,7 +448,9 @@ __device__ __forceinline__ void epi_chunk(const ConvUmmaParams& p, const EpiTile
 //   empty[s]       one per CTA; arrived by the leader's multicast tcgen05.commit
 //   tmem_full[a]   one per CTA; multicast commit after the last MMA of a tile
 //   tmem_empty[a]  leader only; count 2*kEpiWarps (peer epilogue warps arrive remotely)
-template <bool kPair>
+// kWide: the wide-B form of the three passes (ConvUmmaParams::wide_b), single-CTA kernel only; a template parameter so
+// that the second TMEM read of its epilogue costs the other variants no registers.
+template <bool kPair, bool kWide>
 // 10 warps = 3+3+2+2 per SM sub-partition (16K registers each) caps the kernel at 168 registers per thread.
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv_umma_kernel(const __grid_constant__ ConvUmmaParams p) {
@@ -564,6 +572,8 @@ conv_umma_kernel(const __grid_constant__ ConvUmmaParams p) {
   } else if (warp == 1) {
     if (lane == 0 && rank == 0) {
       const uint32_t idesc = ptx::make_idesc_bf16(kPair ? 256 : 128, p.block_n, 0, 0);
+      const uint32_t idesc_wide = ptx::make_idesc_bf16(128, 2 * p.block_n, 0, 0);
+      const uint32_t acc_cols = kWide ? 2 * p.block_n : p.block_n;
       int s = 0;
       uint32_t ph = 0;
       int j = 0;
@@ -572,7 +582,7 @@ conv_umma_kernel(const __grid_constant__ ConvUmmaParams p) {
         const int acc = j & 1;
         ptx::mbar_wait(&tmem_empty[acc], ((j >> 1) & 1) ^ 1);
         ptx::tc_fence_after();
-        const uint32_t tmem_acc = tmem_base + acc * p.block_n;
+        const uint32_t tmem_acc = tmem_base + acc * acc_cols;
         const int steps_per_tile = (p.cls_tap0[cls + 1] - p.cls_tap0[cls]) * p.kchunks;
         for (int step = 0; step < steps_per_tile; ++step) {
           ptx::mbar_wait(&full[s], ph);
@@ -593,6 +603,11 @@ conv_umma_kernel(const __grid_constant__ ConvUmmaParams p) {
                 ptx::umma_bf16_pair(tmem_acc, da_hi, db_lo, idesc, 1u);
                 ptx::umma_bf16_pair(tmem_acc, da_lo, db_hi, idesc, 1u);
               }
+            } else if (kWide) {
+              // rows [0, block_n) of the B slot are the hi weights, rows [block_n, 2*block_n) the lo weights
+              const uint64_t da_lo = ptx::make_desc_sw128(a_lo + k * 32, 16, 1024);
+              ptx::umma_bf16(tmem_acc, da_hi, db_hi, idesc_wide, (step | k) ? 1u : 0u);
+              ptx::umma_bf16(tmem_acc, da_lo, db_hi, idesc, 1u);
             } else {
               ptx::umma_bf16(tmem_acc, da_hi, db_hi, idesc, (step | k) ? 1u : 0u);
               if (p.planes == 2) {
@@ -680,7 +695,7 @@ conv_umma_kernel(const __grid_constant__ ConvUmmaParams p) {
 
       ptx::mbar_wait(&tmem_full[acc], (j >> 1) & 1);
       ptx::tc_fence_after();
-      const uint32_t tmem_acc = tmem_base + acc * p.block_n + (static_cast<uint32_t>(lg * 32) << 16);
+      const uint32_t tmem_acc = tmem_base + acc * (kWide ? 2 * p.block_n : p.block_n) + (static_cast<uint32_t>(lg * 32) << 16);
 
       const int nchunks = p.block_n >> 5;
       bool released = false;
@@ -688,7 +703,15 @@ conv_umma_kernel(const __grid_constant__ ConvUmmaParams p) {
         const int c0 = ci << 5;
         uint32_t v[32];
         ptx::tmem_ld32(tmem_acc + c0, v);
-        ptx::tmem_ld_wait();
+        if (kWide) {   // second column range: the A_hi * B_lo products
+          uint32_t v2[32];
+          ptx::tmem_ld32(tmem_acc + p.block_n + c0, v2);
+          ptx::tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) + __uint_as_float(v2[i]));
+        } else {
+          ptx::tmem_ld_wait();
+        }
         if (ci + kEpiWarps / 4 >= nchunks) {
           // this warp's last TMEM read of the tile: hand the accumulator stage back to the MMA warp
           ptx::tc_fence_before();
@@ -759,24 +782,34 @@ struct WgradParams {
   int planes;
   int PW, PH, PN, tiles_w, tiles_h;
   int total_tiles, tiles_per_cta;
-  int block_n, n_tiles, cin, cout, stages;
+  int block_n, n_tiles, m_tiles, cin, cout, stages;
   int cin_pitch;  // rows per tap in the HWIO gradient (>= cin when dw is a row-slice of a wider filter)
   int num_taps, group;      // taps per CTA (accumulators), blockIdx.y = tap group
   int px;                   // pixels (GEMM K) per pipeline step: 32 or 64
   int x_grouped, dy_grouped;  // operand fetched by ONE 5-D TMA per plane (64-channel groups as the 5th box dimension)
+  int wide_b;               // single-CTA, one tap, block_n <= 128: dy hi|lo as one N = 2*block_n operand (see ConvUmmaParams)
   uint32_t a_bytes;         // one x tile of one plane: 2 boxes of px rows x 128 B
   uint32_t b_bytes, tmem_cols;
   float* dw;
 };
 
+// kPair: 2-CTA clusters running ONE M=256 `cta_group::2` MMA stream (issued by cluster rank 0).  The two CTAs take two
+// work units (filter tap x 128-input-channel tile) that share the dy tile: each stages its own tap-shifted x tile (its
+// 128 rows of D) and HALF of the dy channels, so the L2 -> SM operand bytes per MMA clock drop from 62 to 42 B (block_n =
+// 256) -- the single-CTA kernel sits at the ~49 B/clk/SM feed limit -- and three 64 KB stages fit where two 96 KB ones
+// did.  Units are paired over (tap, channel tile), so 128-input-channel layers pair two taps.  Barriers as in the conv
+// pair kernel: full[s] on the leader (its expect_tx covers both CTAs' bytes, the peer's TMAs signal it remotely),
+// empty[s] / tmem_full in each CTA, arrived by the leader's multicast commits.
+template <bool kPair>
 __global__ void __launch_bounds__(192, 1)
 wgrad_umma_kernel(const __grid_constant__ WgradParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = align1024(smem_raw);
-  // stage layout: [tap 0: x hi | x lo] ... [tap group-1: x hi | x lo] [dy hi | dy lo]
+  // stage layout: [tap 0: x hi | x lo] ... [tap group-1: x hi | x lo] [dy hi | dy lo]   (pair: this CTA's half of dy)
   const uint32_t box_bytes = p.px * 128;
+  const uint32_t b_bytes = kPair ? p.b_bytes / 2 : p.b_bytes;
   const uint32_t b_off = p.group * p.planes * p.a_bytes;
-  const uint32_t stage_bytes = p.planes * (p.group * p.a_bytes + p.b_bytes);
+  const uint32_t stage_bytes = p.planes * (p.group * p.a_bytes + b_bytes);
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + p.stages * stage_bytes);
   uint64_t* empty = full + p.stages;
   uint64_t* tmem_full = empty + p.stages;
@@ -784,10 +817,27 @@ wgrad_umma_kernel(const __grid_constant__ WgradParams p) {
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int nt = blockIdx.x % p.n_tiles;  // output-channel tile
-  const int mt = blockIdx.x / p.n_tiles;  // input-channel tile (128 wide)
-  const int tap0 = blockIdx.y * p.group;
-  const int ntap = min(p.group, p.num_taps - tap0);
+  const uint32_t rank = kPair ? ptx::cluster_ctarank() : 0u;
+  int nt, mt, tap0, ntap;
+  bool active = true;
+  if (kPair) {
+    const int pi = static_cast<int>(blockIdx.x >> 1);
+    nt = pi % p.n_tiles;
+    const int units = p.num_taps * p.m_tiles;
+    int unit = 2 * (pi / p.n_tiles) + static_cast<int>(rank);
+    if (unit >= units) {   // odd unit count: the last cluster's second CTA mirrors its partner and writes nothing
+      unit = units - 1;
+      active = false;
+    }
+    tap0 = unit / p.m_tiles;
+    mt = unit % p.m_tiles;
+    ntap = 1;
+  } else {
+    nt = blockIdx.x % p.n_tiles;  // output-channel tile
+    mt = blockIdx.x / p.n_tiles;  // input-channel tile (128 wide)
+    tap0 = blockIdx.y * p.group;
+    ntap = min(p.group, p.num_taps - tap0);
+  }
   const int tile_begin = blockIdx.z * p.tiles_per_cta;
   const int tile_end = min(tile_begin + p.tiles_per_cta, p.total_tiles);
   const int nsteps = tile_end - tile_begin;
@@ -801,18 +851,30 @@ wgrad_umma_kernel(const __grid_constant__ WgradParams p) {
     ptx::fence_barrier_init();
   }
   if (warp == 1) {
-    switch (p.tmem_cols) {
-      case 64: ptx::tmem_alloc<64>(tmem_slot); break;
-      case 128: ptx::tmem_alloc<128>(tmem_slot); break;
-      case 256: ptx::tmem_alloc<256>(tmem_slot); break;
-      default: ptx::tmem_alloc<512>(tmem_slot); break;
+    if (kPair) {
+      switch (p.tmem_cols) {
+        case 64: ptx::tmem_alloc_pair<64>(tmem_slot); break;
+        case 128: ptx::tmem_alloc_pair<128>(tmem_slot); break;
+        case 256: ptx::tmem_alloc_pair<256>(tmem_slot); break;
+        default: ptx::tmem_alloc_pair<512>(tmem_slot); break;
+      }
+    } else {
+      switch (p.tmem_cols) {
+        case 64: ptx::tmem_alloc<64>(tmem_slot); break;
+        case 128: ptx::tmem_alloc<128>(tmem_slot); break;
+        case 256: ptx::tmem_alloc<256>(tmem_slot); break;
+        default: ptx::tmem_alloc<512>(tmem_slot); break;
+      }
     }
   }
   ptx::tc_fence_before();
-  __syncthreads();
+  if (kPair) ptx::cluster_sync();  // peer barriers must be initialised before any remote arrive / multicast commit
+  else __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const int nboxes_b = p.block_n / 64;
+  const int nboxes_cta = kPair ? nboxes_b / 2 : nboxes_b;   // dy boxes staged by this CTA
+  const int box0_b = nt * nboxes_b + (kPair ? static_cast<int>(rank) * nboxes_cta : 0);
 
   if (nsteps > 0) {
     if (warp == 0) {
@@ -826,6 +888,16 @@ wgrad_umma_kernel(const __grid_constant__ WgradParams p) {
           const int w0 = tw * p.PW, h0 = th * p.PH, n0 = tn * p.PN;
           ptx::mbar_wait(&empty[s], ph ^ 1);
           uint8_t* st = smem + s * stage_bytes;
+          if (kPair) {
+            const uint32_t lead_full = ptx::mapa_u32(ptx::smem_u32(&full[s]), 0);
+            if (rank == 0) ptx::mbar_expect_tx(&full[s], 2 * p.planes * (p.a_bytes + b_bytes));
+            const ConvTap tap = p.taps[tap0];
+            for (int pl = 0; pl < p.planes; ++pl) {
+              ptx::tma_load_5d_pair(st + b_off + pl * b_bytes, &p.dy_map[pl], lead_full, 0, w0, h0, n0, box0_b);
+              ptx::tma_load_5d_pair(st + pl * p.a_bytes, &p.x_map[tap.src][pl], lead_full, 0, w0 + tap.dw, h0 + tap.dh,
+                                    n0, mt * 2);
+            }
+          } else {
           ptx::mbar_expect_tx(&full[s], p.planes * (ntap * p.a_bytes + p.b_bytes));
           // (the kernel is sensitive to the NUMBER of TMA instructions per step, ~200 clk each on one issuing thread:
           //  a 64-channel box per instruction made 12 per step and capped it at ~55 % of the MMA rate)
@@ -852,6 +924,7 @@ wgrad_umma_kernel(const __grid_constant__ WgradParams p) {
               }
             }
           }
+          }
           if (++s == p.stages) {
             s = 0;
             ph ^= 1;
@@ -859,8 +932,9 @@ wgrad_umma_kernel(const __grid_constant__ WgradParams p) {
         }
       }
     } else if (warp == 1) {
-      if (lane == 0) {
-        const uint32_t idesc = ptx::make_idesc_bf16(128, p.block_n, 1, 1);
+      if (lane == 0 && rank == 0) {
+        const uint32_t idesc = ptx::make_idesc_bf16(kPair ? 256 : 128, p.block_n, 1, 1);
+        const uint32_t idesc_wide = ptx::make_idesc_bf16(128, 2 * p.block_n, 1, 1);
         const int ksteps = p.px / 16;  // 16 pixels (K) per MMA = 2 KB of rows
         int s = 0;
         uint32_t ph = 0;
@@ -869,7 +943,7 @@ wgrad_umma_kernel(const __grid_constant__ WgradParams p) {
           ptx::tc_fence_after();
           const uint32_t st = ptx::smem_u32(smem + s * stage_bytes);
           const uint32_t b_hi = st + b_off;
-          const uint32_t b_lo = b_hi + p.b_bytes;
+          const uint32_t b_lo = b_hi + b_bytes;
           for (int i = 0; i < ntap; ++i) {
             const uint32_t a_hi = st + i * p.planes * p.a_bytes;
             const uint32_t a_lo = a_hi + p.a_bytes;
@@ -877,22 +951,39 @@ wgrad_umma_kernel(const __grid_constant__ WgradParams p) {
             for (int k = 0; k < ksteps; ++k) {
               const uint64_t da_hi = ptx::make_desc_sw128(a_hi + k * 2048, box_bytes, 1024);
               const uint64_t db_hi = ptx::make_desc_sw128(b_hi + k * 2048, box_bytes, 1024);
-              ptx::umma_bf16(acc, da_hi, db_hi, idesc, (step | k) ? 1u : 0u);
-              if (p.planes == 2) {
+              if (kPair) {
+                ptx::umma_bf16_pair(acc, da_hi, db_hi, idesc, (step | k) ? 1u : 0u);
+                if (p.planes == 2) {
+                  const uint64_t da_lo = ptx::make_desc_sw128(a_lo + k * 2048, box_bytes, 1024);
+                  const uint64_t db_lo = ptx::make_desc_sw128(b_lo + k * 2048, box_bytes, 1024);
+                  ptx::umma_bf16_pair(acc, da_hi, db_lo, idesc, 1u);
+                  ptx::umma_bf16_pair(acc, da_lo, db_hi, idesc, 1u);
+                }
+              } else if (p.wide_b) {
+                // the lo boxes of dy follow the hi boxes in the stage: atoms 0.. = hi channels, then the lo channels
                 const uint64_t da_lo = ptx::make_desc_sw128(a_lo + k * 2048, box_bytes, 1024);
-                const uint64_t db_lo = ptx::make_desc_sw128(b_lo + k * 2048, box_bytes, 1024);
-                ptx::umma_bf16(acc, da_hi, db_lo, idesc, 1u);
+                ptx::umma_bf16(acc, da_hi, db_hi, idesc_wide, (step | k) ? 1u : 0u);
                 ptx::umma_bf16(acc, da_lo, db_hi, idesc, 1u);
+              } else {
+                ptx::umma_bf16(acc, da_hi, db_hi, idesc, (step | k) ? 1u : 0u);
+                if (p.planes == 2) {
+                  const uint64_t da_lo = ptx::make_desc_sw128(a_lo + k * 2048, box_bytes, 1024);
+                  const uint64_t db_lo = ptx::make_desc_sw128(b_lo + k * 2048, box_bytes, 1024);
+                  ptx::umma_bf16(acc, da_hi, db_lo, idesc, 1u);
+                  ptx::umma_bf16(acc, da_lo, db_hi, idesc, 1u);
+                }
               }
             }
           }
-          ptx::umma_commit(&empty[s]);
+          if (kPair) ptx::umma_commit_pair(&empty[s], 3);
+          else ptx::umma_commit(&empty[s]);
           if (++s == p.stages) {
             s = 0;
             ph ^= 1;
           }
         }
-        ptx::umma_commit(tmem_full);
+        if (kPair) ptx::umma_commit_pair(tmem_full, 3);
+        else ptx::umma_commit(tmem_full);
       }
     } else {
       const int lg = warp & 3;
@@ -904,9 +995,17 @@ wgrad_umma_kernel(const __grid_constant__ WgradParams p) {
         for (int c0 = 0; c0 < p.block_n; c0 += 32) {
           uint32_t v[32];
           ptx::tmem_ld32(tmem_base + (static_cast<uint32_t>(lg * 32) << 16) + i * p.block_n + c0, v);
-          ptx::tmem_ld_wait();
+          if (p.wide_b) {
+            uint32_t v2[32];
+            ptx::tmem_ld32(tmem_base + (static_cast<uint32_t>(lg * 32) << 16) + p.block_n + c0, v2);
+            ptx::tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(v2[j]));
+          } else {
+            ptx::tmem_ld_wait();
+          }
           const int cbase = nt * p.block_n + c0;
-          if (ci < p.cin) {
+          if (active && ci < p.cin) {
             float* o = p.dw + (static_cast<long long>(wtap) * p.cin_pitch + ci) * p.cout + cbase;
 #pragma unroll
             for (int j = 0; j < 32; ++j)
@@ -918,14 +1017,24 @@ wgrad_umma_kernel(const __grid_constant__ WgradParams p) {
   }
 
   ptx::tc_fence_before();
-  __syncthreads();
+  if (kPair) ptx::cluster_sync();  // the leader's MMAs read the peer's smem; nobody leaves before both are done
+  else __syncthreads();
   if (warp == 1) {
     ptx::tc_fence_after();
-    switch (p.tmem_cols) {
-      case 64: ptx::tmem_dealloc<64>(tmem_base); break;
-      case 128: ptx::tmem_dealloc<128>(tmem_base); break;
-      case 256: ptx::tmem_dealloc<256>(tmem_base); break;
-      default: ptx::tmem_dealloc<512>(tmem_base); break;
+    if (kPair) {
+      switch (p.tmem_cols) {
+        case 64: ptx::tmem_dealloc_pair<64>(tmem_base); break;
+        case 128: ptx::tmem_dealloc_pair<128>(tmem_base); break;
+        case 256: ptx::tmem_dealloc_pair<256>(tmem_base); break;
+        default: ptx::tmem_dealloc_pair<512>(tmem_base); break;
+      }
+    } else {
+      switch (p.tmem_cols) {
+        case 64: ptx::tmem_dealloc<64>(tmem_base); break;
+        case 128: ptx::tmem_dealloc<128>(tmem_base); break;
+        case 256: ptx::tmem_dealloc<256>(tmem_base); break;
+        default: ptx::tmem_dealloc<512>(tmem_base); break;
+      }
     }
   }
 }
@@ -1069,6 +1178,7 @@ static void choose_pair(const dpig_ctx* ctx, ConvUmmaParams& P) {
   const bool wins = P.block_n > 128 || P.kchunks == 1;
   P.pair = (legal && (ctx->pair_mode == 2 || (ctx->pair_mode == 1 && wins))) ? 1 : 0;
   P.b_bytes = (P.pair ? P.block_n / 2 : P.block_n) * 128;
+  P.wide_b = (!P.pair && ctx->wide_b && !ctx->fast_mode && P.planes == 2 && P.block_n <= 128 && P.block_n % 8 == 0) ? 1 : 0;
 }
 
 struct EpilogueGeom {
@@ -1192,14 +1302,15 @@ static int launch_conv(dpig_ctx* ctx, ConvUmmaParams& P, cudaStream_t stream) {
   const size_t smem = static_cast<size_t>(stages) * stage_bytes + extra;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaFuncSetAttribute(conv_umma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->max_smem_optin);
-    cudaFuncSetAttribute(conv_umma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->max_smem_optin);
+    cudaFuncSetAttribute(conv_umma_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->max_smem_optin);
+    cudaFuncSetAttribute(conv_umma_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->max_smem_optin);
+    cudaFuncSetAttribute(conv_umma_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->max_smem_optin);
     attr_set = true;
   }
   const int pix_tiles = P.tiles_w * P.tiles_h * P.tiles_n;
   const int n_tiles = (P.cout + P.block_n - 1) / P.block_n;
   P.tmem_cols = 64;
-  while (static_cast<int>(P.tmem_cols) < 2 * P.block_n) P.tmem_cols <<= 1;
+  while (static_cast<int>(P.tmem_cols) < (P.wide_b ? 4 : 2) * P.block_n) P.tmem_cols <<= 1;
   ctx->launches++;
   if (P.pair) {
     const int units = ((pix_tiles + 1) / 2) * n_tiles;
@@ -1216,12 +1327,13 @@ static int launch_conv(dpig_ctx* ctx, ConvUmmaParams& P, cudaStream_t stream) {
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, conv_umma_kernel<true>, P);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, conv_umma_kernel<true, false>, P);
     if (e != cudaSuccess) return set_error(ctx, DPIG_ECUDA, "conv_umma_kernel<pair> launch: %s", cudaGetErrorString(e));
     return check_launch(ctx, "conv_umma_kernel<pair>");
   }
   dim3 grid(std::min(pix_tiles * n_tiles, ctx->num_sms));
-  conv_umma_kernel<false><<<grid, kConvThreads, smem, stream>>>(P);
+  if (P.wide_b) conv_umma_kernel<false, true><<<grid, kConvThreads, smem, stream>>>(P);
+  else conv_umma_kernel<false, false><<<grid, kConvThreads, smem, stream>>>(P);
   return check_launch(ctx, "conv_umma_kernel");
 }
 
@@ -1498,7 +1610,14 @@ static int wgrad_impl(dpig_ctx* ctx, const dpig_tensor* x, const dpig_tensor* dy
   const int tiles_n = (x->n + b.bn - 1) / b.bn;
   P.total_tiles = P.tiles_w * P.tiles_h * tiles_n;
   const int m_tiles = (cin + 127) / 128;
-  const int base = m_tiles * P.n_tiles * tap_groups;
+  P.m_tiles = m_tiles;
+  // CTA pairs (see the kernel): two (tap, channel-tile) units per cluster sharing one dy tile, half of it staged by each
+  // (measured, profiles/r01_wgrad_pair_ab.txt: 256-wide blocks gain 17-21 %, 128 -> 128 layers lose 2-4 %)
+  const bool pair = ctx->wgrad_pair && group == 1 && P.px == 64 && P.x_grouped && P.dy_grouped && P.block_n % 128 == 0 &&
+                    !(P.block_n == 128 && cin <= 128) && ntaps_total * m_tiles >= 2 && ctx->num_sms >= 2;
+  P.wide_b = (!pair && ctx->wide_b && group == 1 && P.planes == 2 && P.block_n <= 128) ? 1 : 0;
+  if (P.wide_b) P.tmem_cols = std::max<uint32_t>(64, pow2_cols(2 * P.block_n));
+  const int base = pair ? 2 * ((ntaps_total * m_tiles + 1) / 2) * P.n_tiles : m_tiles * P.n_tiles * tap_groups;
   // split-K so that the grid is as close as possible to (but not above) a whole number of waves of the
   // 148 one-CTA-per-SM slots: a grid of 450 CTAs would run 4 rounds with the last one 4 % full.
   int ksplit = 1;
@@ -1552,10 +1671,10 @@ static int wgrad_impl(dpig_ctx* ctx, const dpig_tensor* x, const dpig_tensor* dy
   }
   for (int pln = 0; pln < P.planes; ++pln)
     if ((rc = act_map(ctx, &P.dy_map[pln], pln ? dy->lo : dy->hi, dy, 1, 0, 0, b.bw, b.bh, b.bn, 0,
-                      P.dy_grouped ? P.block_n / 64 : 0)))
+                      P.dy_grouped ? P.block_n / (pair ? 128 : 64) : 0)))
       return rc;
 
-  const uint32_t stage_bytes = P.planes * (P.group * P.a_bytes + P.b_bytes);
+  const uint32_t stage_bytes = P.planes * (P.group * P.a_bytes + (pair ? P.b_bytes / 2 : P.b_bytes));
   int stages = (ctx->max_smem_optin - 1024 - 256) / stage_bytes;
   if (stages > 6) stages = 6;
   if (stages < 2) return set_error(ctx, DPIG_EUNSUPPORTED, "wgrad tile does not fit shared memory");
@@ -1563,11 +1682,30 @@ static int wgrad_impl(dpig_ctx* ctx, const dpig_tensor* x, const dpig_tensor* dy
   const size_t smem = static_cast<size_t>(stages) * stage_bytes + 1024 + 256;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaFuncSetAttribute(wgrad_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->max_smem_optin);
+    cudaFuncSetAttribute(wgrad_umma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->max_smem_optin);
+    cudaFuncSetAttribute(wgrad_umma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->max_smem_optin);
     attr_set = true;
   }
-  dim3 grid(m_tiles * P.n_tiles, tap_groups, ksplit);
-  wgrad_umma_kernel<<<grid, 192, smem, static_cast<cudaStream_t>(stream)>>>(P);
   ctx->launches++;
+  if (pair) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(base, 1, ksplit);
+    cfg.blockDim = dim3(192);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = static_cast<cudaStream_t>(stream);
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, wgrad_umma_kernel<true>, P);
+    if (e != cudaSuccess) return set_error(ctx, DPIG_ECUDA, "wgrad_umma_kernel<pair> launch: %s", cudaGetErrorString(e));
+    return check_launch(ctx, "wgrad_umma_kernel<pair>");
+  }
+  dim3 grid(m_tiles * P.n_tiles, tap_groups, ksplit);
+  wgrad_umma_kernel<false><<<grid, 192, smem, static_cast<cudaStream_t>(stream)>>>(P);
   return check_launch(ctx, "wgrad_umma_kernel");
 }

@@ -305,6 +305,11 @@ CONV_BWD_FILTER_CASES = [
     dict(n=2, h=16, w=8, cin=256, cout=3, k=3, stride=1),
     dict(n=2, h=16, w=8, cin=370, cout=128, k=3, stride=1),
     dict(n=1, h=128, w=64, cin=128, cout=128, k=3, stride=1),
+    # CTA-pair kernel: even / odd numbers of (tap, channel tile) units, two output-channel tiles, split-K over many tiles
+    dict(n=2, h=16, w=8, cin=256, cout=256, k=3, stride=1),
+    dict(n=3, h=12, w=12, cin=384, cout=512, k=3, stride=1),
+    dict(n=9, h=32, w=32, cin=256, cout=128, k=3, stride=1),
+    dict(n=4, h=16, w=16, cin=128, cout=256, k=1, stride=1),
 ]
 
 
