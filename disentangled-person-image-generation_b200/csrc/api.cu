@@ -63,6 +63,8 @@ extern "C" int dpig_ctx_create(int device, dpig_ctx** out) {
   if (const char* e = getenv("DPIG_EPI_TMA")) ctx->epi_tma = atoi(e) != 0;
   if (const char* e = getenv("DPIG_WGRAD_PAIR")) ctx->wgrad_pair = atoi(e) != 0;
   if (const char* e = getenv("DPIG_WIDE_B")) ctx->wide_b = atoi(e) != 0;
+  if (const char* e = getenv("DPIG_EPI_BUFS")) ctx->epi_bufs = atoi(e);
+  if (const char* e = getenv("DPIG_TUNE_SMALL")) ctx->tune_small = atoi(e);
   *out = ctx;
   return DPIG_OK;
 }

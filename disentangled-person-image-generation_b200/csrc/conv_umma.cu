@@ -87,6 +87,7 @@ struct ConvUmmaParams {
   CUtensorMap out_map[4][2];
   CUtensorMap out2_map[4][2];
   int out_tma, out2_tma;
+  int epi_bufs;  // staging buffers per warp set (1 or 2), used alternately by successive TMA stores
 };
 
 __device__ __forceinline__ uint8_t* align1024(uint8_t* p) {
@@ -145,8 +146,11 @@ constexpr int kConvThreads = 64 + 32 * kEpiWarps;
 // the 2x2 replicas of the fused upsample) instead of 8 shuffles + 8 predicated 16-byte stores per lane.  Measured before
 // the change (tests/bench_dgrad_micro.py, profiles/r01_dgrad_epilogue_micro.txt): every split output cost ~2.6k clk per
 // chunk and warp -- short-K layers (stride-2 parity classes, 1x1) ran at the epilogue's speed, not the tensor pipe's.
+// With shared memory to spare a set gets TWO such buffers and alternates between them: a TMA store queues behind the
+// producer's in-flight loads and needs ~2k clk until its source is free again, which a single buffer exposes on every
+// chunk of a layer with two outputs or a short K loop.
 constexpr uint32_t kEpiSetBytes = 16384, kEpiLoOff = 8192;
-constexpr uint32_t kEpiBytes = 2 * kEpiSetBytes;
+constexpr uint32_t kEpiBytes = 2 * kEpiSetBytes;   // both sets, one buffer each
 
 // Byte offset of 16-byte piece `piece` of row `row` (relative to the warp's first row; warps start 2048 B apart).
 __device__ __forceinline__ uint32_t swz64(int row, int piece) {   // 64 B rows, 4 pieces (split-bf16 planes)
@@ -225,28 +229,36 @@ __device__ __forceinline__ void epi_gather_rows(uint32_t st, const __nv_bfloat16
 struct EpiTile {
   int w0, h0, n0;     // origin of the pixel box in the (class) output grid = TMA store coordinates
   int cls;            // parity class (merged stride-2 data gradient), else 0
-  uint32_t set_base;  // shared address of the warp set's staging buffer
+  uint32_t set_base;  // shared address of the warp set's staging buffer 0 (buffer 1 is kEpiBytes further)
   uint32_t bar_id;    // named barrier of the set (4 warps)
   bool leader;        // the one thread of the set that issues / tracks the TMA stores
+  uint32_t phase;     // TMA-store phases issued so far by the set: the next staging rows go to buffer phase % bufs
+  bool pending;       // stores issued since the last acquire may still be reading the buffer about to be written
 };
 
 // One 32-channel chunk of one accumulator row (pixel): bias / activation / residual / sign mask / outputs.
 // v[i] = raw fp32 accumulator of channel cbase+i; all 32 lanes of the warp, and all four warps of the set, call this
 // together.  colsum: lane l's running total of channel cbase + l of the masked output (see the flush in the kernel).
-__device__ __forceinline__ void epi_chunk(const ConvUmmaParams& p, const EpiTile& t, uint32_t st,
+__device__ __forceinline__ void epi_chunk(const ConvUmmaParams& p, EpiTile& t, uint32_t st0,
                                           const uint32_t (&v)[32], int cbase, bool valid, int lpix, int ppix,
                                           const float* cbias, int lane, float& colsum) {
   const int nvalid = min(32, p.cout - cbase);
   if (nvalid <= 0) return;  // uniform over the warp set
   const bool full32 = (nvalid == 32);
-  // The set's buffer may still be read by the TMA stores of the previous chunk: whoever writes staging rows next first
+  // The buffer about to be written may still be read by an earlier TMA store: whoever writes staging rows next first
   // lets the leader wait for those reads and tells the other warps (every condition below is uniform over the set).
-  bool pending = p.out_tma || p.out2_tma;
+  uint32_t st = st0, set_buf = t.set_base;
   auto acquire = [&]() {
-    if (pending) {
-      if (t.leader) ptx::bulk_wait_group_read0();
+    const uint32_t boff = (p.epi_bufs == 2 && (t.phase & 1)) ? kEpiBytes : 0u;
+    st = st0 + boff;
+    set_buf = t.set_base + boff;
+    if (t.pending) {
+      if (t.leader) {
+        if (p.epi_bufs == 2) ptx::bulk_wait_group_read1();
+        else ptx::bulk_wait_group_read0();
+      }
       ptx::named_bar_sync(t.bar_id, 128);
-      pending = false;
+      t.pending = false;
     }
   };
   float f[32];
@@ -335,12 +347,13 @@ __device__ __forceinline__ void epi_chunk(const ConvUmmaParams& p, const EpiTile
       ptx::named_bar_sync(t.bar_id, 128);
       if (t.leader) {
         for (int r = 0; r < p.rep * p.rep; ++r) {   // rep = 2: the four replicas of the fused nearest-neighbour upsample
-          ptx::tma_store_4d(&p.out_map[t.cls + r][0], t.set_base, cbase, t.w0, t.h0, t.n0);
-          if (p.out_lo) ptx::tma_store_4d(&p.out_map[t.cls + r][1], t.set_base + kEpiLoOff, cbase, t.w0, t.h0, t.n0);
+          ptx::tma_store_4d(&p.out_map[t.cls + r][0], set_buf, cbase, t.w0, t.h0, t.n0);
+          if (p.out_lo) ptx::tma_store_4d(&p.out_map[t.cls + r][1], set_buf + kEpiLoOff, cbase, t.w0, t.h0, t.n0);
         }
         ptx::bulk_commit_group();
       }
-      pending = true;
+      t.phase++;
+      t.pending = true;
     } else if (full32 && (p.out_ps % 8 == 0)) {
       acquire();
       epi_stage_split(st, f, lane, p.out_lo != nullptr);
@@ -398,11 +411,12 @@ __device__ __forceinline__ void epi_chunk(const ConvUmmaParams& p, const EpiTile
       ptx::fence_proxy_async();
       ptx::named_bar_sync(t.bar_id, 128);
       if (t.leader) {
-        ptx::tma_store_4d(&p.out2_map[t.cls][0], t.set_base, cbase, t.w0, t.h0, t.n0);
-        if (p.out2_lo) ptx::tma_store_4d(&p.out2_map[t.cls][1], t.set_base + kEpiLoOff, cbase, t.w0, t.h0, t.n0);
+        ptx::tma_store_4d(&p.out2_map[t.cls][0], set_buf, cbase, t.w0, t.h0, t.n0);
+        if (p.out2_lo) ptx::tma_store_4d(&p.out2_map[t.cls][1], set_buf + kEpiLoOff, cbase, t.w0, t.h0, t.n0);
         ptx::bulk_commit_group();
       }
-      pending = true;
+      t.phase++;
+      t.pending = true;
     } else if (full32 && (p.out2_ps % 8 == 0)) {
       acquire();
       epi_stage_split(st, f, lane, p.out2_lo != nullptr);
@@ -458,8 +472,8 @@ conv_umma_kernel(const __grid_constant__ ConvUmmaParams p) {
   uint8_t* smem = align1024(smem_raw);
   const uint32_t b_off = p.planes * kABytes;
   const uint32_t stage_bytes = p.planes * (kABytes + p.b_bytes);
-  uint8_t* epi_smem = smem + p.stages * stage_bytes;        // 2 x kEpiSetBytes, 1024-byte aligned (TMA store source)
-  uint64_t* full = reinterpret_cast<uint64_t*>(epi_smem + kEpiBytes);
+  uint8_t* epi_smem = smem + p.stages * stage_bytes;        // epi_bufs x kEpiBytes, 1024-byte aligned (TMA store source)
+  uint64_t* full = reinterpret_cast<uint64_t*>(epi_smem + p.epi_bufs * kEpiBytes);
   uint64_t* empty = full + p.stages;
   uint64_t* tmem_full = empty + p.stages;   // [2]
   uint64_t* tmem_empty = tmem_full + 2;     // [2]
@@ -645,6 +659,8 @@ conv_umma_kernel(const __grid_constant__ ConvUmmaParams p) {
     et.set_base = ptx::smem_u32(epi_smem) + cpar * kEpiSetBytes;
     et.bar_id = 1 + cpar;
     et.leader = (lg == 0 && lane == 0);
+    et.phase = 0;
+    et.pending = false;
     const uint32_t st = et.set_base + lg * 2048;   // this warp's 32 rows of the hi plane
     const uint32_t lead_tmem_empty[2] = {kPair ? ptx::mapa_u32(ptx::smem_u32(&tmem_empty[0]), 0) : 0u,
                                          kPair ? ptx::mapa_u32(ptx::smem_u32(&tmem_empty[1]), 0) : 0u};
@@ -1157,11 +1173,39 @@ static int pick_block_n(int cout) {
   return best;
 }
 
-// Few-pixel layers (8x4, 3x3 maps): trade operand reuse for parallelism until the persistent grid fills the SMs.
-static int tune_block_n(const dpig_ctx* ctx, int cout, int pix_tiles) {
-  int bn = pick_block_n(cout);
-  while (bn >= 128 && (bn / 2) % 32 == 0 && pix_tiles * ((cout + bn - 1) / bn) < ctx->num_sms) bn /= 2;
-  return bn;
+// Few-pixel layers (8x4, 3x3 maps; fewer work units than SMs at the widest channel block): pick the channel block by
+// a cost model instead of the widest one.  Per K step (64 channels of one tap) a CTA needs 32 KB of activations plus
+// block_n x 256 B of weights through the ~49 B/clk/SM L2 -> SM feed and 12 MMAs of block_n/2 clk (1.45x that below
+// N = 256, where the shared-memory port caps the MMA rate); a unit costs steps x max(feed, MMA), a launch
+// ceil(units / SMs) unit times.  Narrow blocks buy parallelism but re-fetch the activation tile once per block: the
+// old rule (halve until the grid fills the SMs) went down to N = 64 and ran two half-empty rounds at 3x the bytes.
+static int tune_block_n(const dpig_ctx* ctx, int cout, int pix_tiles, int steps) {
+  const int widest = pick_block_n(cout);
+  if (ctx->tune_small == 0 || pix_tiles * ((cout + widest - 1) / widest) >= ctx->num_sms) return widest;
+  if (ctx->tune_small == 2) {   // the old rule, kept for A/B runs
+    int bn = widest;
+    while (bn >= 128 && (bn / 2) % 32 == 0 && pix_tiles * ((cout + bn - 1) / bn) < ctx->num_sms) bn /= 2;
+    return bn;
+  }
+  const int c32 = (cout + 31) / 32 * 32;
+  int best = widest;
+  double best_cost = -1.0;
+  for (int bn = 32; bn <= 256; bn += 32) {
+    if (c32 % bn) continue;
+    const int n_tiles = c32 / bn;
+    const bool pair = bn >= 64 && pix_tiles >= 2 && ctx->pair_mode >= 1 && (bn > 128 || (steps > 0 && ctx->pair_mode == 2));
+    const double feed = (32768.0 + (pair ? bn / 2 : bn) * 256.0) / 49.0;
+    const double mma = 12.0 * (bn / 2) * (bn < 256 ? 1.45 : 1.0);
+    const double unit = steps * std::max(feed, mma) + 2500.0 + (bn / 32) * 600.0;
+    const int units = pair ? ((pix_tiles + 1) / 2) * n_tiles : pix_tiles * n_tiles;
+    const int slots = pair ? ctx->num_sms / 2 : ctx->num_sms;
+    const double cost = ((units + slots - 1) / slots) * unit;
+    if (best_cost < 0 || cost < best_cost - 1e-9 || (cost < best_cost + 1e-9 && bn > best)) {
+      best_cost = cost;
+      best = bn;
+    }
+  }
+  return best;
 }
 
 // CTA pairs: a 2-CTA cluster runs cta_group::2 M=256 MMAs over two adjacent pixel tiles, each CTA staging half of the
@@ -1293,11 +1337,24 @@ static int fill_epilogue(dpig_ctx* ctx, ConvUmmaParams& P, const dpig_conv_epilo
 static int launch_conv(dpig_ctx* ctx, ConvUmmaParams& P, cudaStream_t stream) {
   P.planes = ctx->fast_mode ? 1 : P.planes;
   const uint32_t stage_bytes = P.planes * (kABytes + P.b_bytes);
-  const uint32_t extra = 1024 + 256 + kEpiBytes;  // alignment slack + barriers + epilogue staging
+  uint32_t extra = 1024 + 256 + kEpiBytes;  // alignment slack + barriers + epilogue staging
   int stages = (ctx->max_smem_optin - static_cast<int>(extra)) / static_cast<int>(stage_bytes);
   if (stages > 6) stages = 6;
   if (stages < 2) return set_error(ctx, DPIG_EUNSUPPORTED, "conv tile does not fit shared memory");
   if (ctx->max_stages >= 2 && stages > ctx->max_stages) stages = ctx->max_stages;
+  // Second staging buffer per warp set: free when it costs no pipeline stage; at the price of the third stage where
+  // the epilogue, not the K loop, sets the pace (two outputs per chunk, or a K loop of a few steps per tile).
+  P.epi_bufs = 1;
+  if (ctx->epi_bufs != 1 && (P.out_tma || P.out2_tma)) {
+    const int stages2 = std::min(6, (ctx->max_smem_optin - static_cast<int>(extra + kEpiBytes)) / static_cast<int>(stage_bytes));
+    const int steps = P.num_taps * P.kchunks / std::max(1, P.nclass);
+    const bool heavy = (P.out_tma && P.out2_tma) || steps <= 4;
+    if (stages2 >= stages || (stages2 >= 2 && (heavy || ctx->epi_bufs == 2))) {
+      P.epi_bufs = 2;
+      stages = std::min(stages, stages2);
+      extra += kEpiBytes;
+    }
+  }
   P.stages = stages;
   const size_t smem = static_cast<size_t>(stages) * stage_bytes + extra;
   static bool attr_set = false;
@@ -1371,7 +1428,7 @@ extern "C" int dpig_conv2d_fwd(dpig_ctx* ctx, const dpig_tensor* x, const void* 
   P.tiles_h = (OH + b.bh - 1) / b.bh;
   P.tiles_n = (x->n + b.bn - 1) / b.bn;
   P.a_tx_bytes = b.bw * b.bh * b.bn * 128;
-  P.block_n = tune_block_n(ctx, cout, P.tiles_w * P.tiles_h * P.tiles_n);
+  P.block_n = tune_block_n(ctx, cout, P.tiles_w * P.tiles_h * P.tiles_n, kh * kw * P.kchunks);
   choose_pair(ctx, P);
 
   int rc;
@@ -1481,7 +1538,7 @@ extern "C" int dpig_conv2d_bwd_data(dpig_ctx* ctx, const dpig_tensor* dy, const 
     P.tiles_h = (GH + b.bh - 1) / b.bh;
     P.tiles_n = (dy->n + b.bn - 1) / b.bn;
     P.a_tx_bytes = b.bw * b.bh * b.bn * 128;
-    P.block_n = tune_block_n(ctx, cin, P.tiles_w * P.tiles_h * P.tiles_n);
+    P.block_n = tune_block_n(ctx, cin, P.tiles_w * P.tiles_h * P.tiles_n, kh * kw * P.kchunks / (merged ? 1 : stride * stride));
     choose_pair(ctx, P);
     P.num_taps = 0;
     P.nclass = merged ? stride * stride : 1;

@@ -115,6 +115,10 @@ __device__ __forceinline__ void bulk_commit_group() {
 __device__ __forceinline__ void bulk_wait_group_read0() {
   asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
 }
+// ... all but the most recent one (two staging buffers used alternately)
+__device__ __forceinline__ void bulk_wait_group_read1() {
+  asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+}
 __device__ __forceinline__ void bulk_wait_group0() {
   asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
