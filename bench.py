@@ -41,16 +41,20 @@ def _peaks():
 def _ncu_traffic():
     """dram__bytes_read.sum + dram__bytes_write.sum of a representative conv_umma_kernel launch from the committed
     `ncu --set full` capture (profiles/r01_ncu_full_summary.json); the live bench cannot run under ncu."""
-    path = os.path.join(ROOT, "profiles", "r01_ncu_full_summary.json")
-    try:
-        with open(path) as fh:
-            rows = json.load(fh)["conv_big_r01"]
-        r = max(rows, key=lambda x: x["time_us"])
-        return {"launch": "256->256 3x3 conv on 64x128x64 (ID_AE/G/Conv_27), grid %s" % r["grid"],
-                "dram_bytes": r["dram_read_bytes"] + r["dram_write_bytes"],
-                "algorithmic_bytes": 2 * 64 * 128 * 64 * 256 * 4, "source": "profiles/r01_ncu_full_summary.json"}
-    except Exception:
-        return None
+    for name, key in (("r01_ncu_full_summary_v3.json", "conv_fwd_256.ncu-rep"), ("r01_ncu_full_summary.json", "conv_big_r01")):
+        try:
+            with open(os.path.join(ROOT, "profiles", name)) as fh:
+                rows = json.load(fh)[key]
+            r = max(rows, key=lambda x: x.get("time_ns", x.get("time_us", 0)))
+            # v3 capture: the residual layer (input + addend read, output written: 3 tensors); v1: no addend (2 tensors)
+            tensors = 3 if "v3" in name else 2
+            return {"launch": "256->256 3x3 conv%s on 64x128x64 (ID_AE/G/Conv_27/28), grid %s" % (
+                        " + residual add" if tensors == 3 else "", r["grid"]),
+                    "dram_bytes": r["dram_read_bytes"] + r["dram_write_bytes"],
+                    "algorithmic_bytes": tensors * 64 * 128 * 64 * 256 * 4, "source": "profiles/" + name}
+        except Exception:
+            continue
+    return None
 
 
 class ClockSampler:

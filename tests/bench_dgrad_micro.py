@@ -15,7 +15,7 @@ from dpig_b200.tensor import SplitTensor, ptr  # noqa: E402
 # n, in_h, in_w, cin (dx channels), cout (dy channels), k, stride
 SHAPES = [(448, 48, 48, 128, 256, 3, 2), (64, 64, 32, 128, 256, 3, 2), (64, 64, 32, 512, 128, 1, 1),
           (448, 48, 48, 128, 128, 3, 1), (64, 128, 64, 256, 256, 3, 1)]
-VARIANTS = ["out", "masked", "masked+colsum", "out+masked", "out+masked+colsum", "full"]
+VARIANTS = ["out", "masked", "masked+colsum", "out+masked", "out+masked+colsum", "full"]   # + "wgrad": the filter gradient
 
 
 def run(ctx, shape, variant, iters=10):
@@ -43,6 +43,11 @@ def run(ctx, shape, variant, iters=10):
     if variant == "full":
         ep.addend = C.pointer(add.struct())
     call = lambda: ctx.conv2d_bwd_data(dy.ref(), ptr(wb[0]), ptr(wb[1]), k, k, stride, h, w, cin, C.byref(ep), s)
+    if variant == "wgrad":
+        x = SplitTensor(n, h, w, cin, zero=True)
+        x.buf.normal_(0, 1)
+        dw = torch.zeros((k, k, cin, cout), device="cuda")
+        call = lambda: ctx.conv2d_bwd_filter(x.ref(), dy.ref(), k, k, stride, cin, cout, ptr(dw), s)
     for _ in range(2 if iters > 1 else 0):
         call()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
