@@ -93,6 +93,7 @@ _SIGNATURES = {
     "dpig_rmsprop_step_dev": [_P, _P, _P, _L, _P, _F, _F, _F, _F, _P],
     "dpig_clip": [_P, _L, _F, _F, _P],
     "dpig_denorm_u8": [_P, _L, _P, _P],
+    "dpig_ssim_gray_u8": [_P, _P, _I, _I, _I, _P, _P],
     "dpig_pose_rasterize": [_P, _I, _I, _I, _I, _I, _T, _P, _P],
 }
 

@@ -15,7 +15,7 @@ LIB = os.path.join(HERE, "libdpig.so")
 STAMP = os.path.join(HERE, "build", "stamp.txt")
 
 SOURCES = ["api.cu", "conv_umma.cu", "conv_simt.cu", "elementwise.cu", "crop_resize.cu", "linear.cu",
-           "norm.cu", "loss_optim.cu", "patch.cu"]
+           "norm.cu", "loss_optim.cu", "patch.cu", "image_metrics.cu"]
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC"]

@@ -4,15 +4,16 @@
 
 Forward only: appearance encoder -> sample-or-hold the Fg / Bg embeddings (GaussianFCRes nets) -> pose branch
 (PoseEncoderFCRes -> PoseDecoderFCRes; the decoder is fed the ENCODED REAL pose, quirk q7) -> keypoints to maps +
-radius-4 inflation -> U-Net -> denorm -> DCGANDiscriminator score.  Everything runs through the C ABI; PNG dumps and
-SSIM of the reference's generate()/test() are host-side I/O outside the hot path (results are returned as arrays and
-written as .npy)."""
+radius-4 inflation -> U-Net -> denorm -> DCGANDiscriminator score.  Everything numeric runs through the C ABI, incl. the
+per-sample SSIM of generate() (dpig_ssim_gray_u8) and the uint8 conversion; test() writes the reference's result
+directories (x, x_target, G, pose, pose_target, G_pose, mask, mask_target -- the input of score.py) through
+outputs.ResultWriter, PNG encoding batched over host threads."""
 import os
 
 import numpy as np
 import torch
 
-from . import _lib, engine, stage2, synth, tf_checkpoint
+from . import _lib, engine, outputs, stage2, synth, tf_checkpoint
 from ._lib import ACT_LRELU, ACT_NONE
 from .tensor import ptr
 from .trainer import SyntheticLoader, make_loader
@@ -129,14 +130,60 @@ class DPIG_FourNetsFgBg_testOnlySampleFactor(object):
         G = torch.clamp((s1.G + 1.0) * 127.5, 0, 255)
         pose_maps = s1.gin.slice(0, cfg.keypoints).hi.float()
         pose_img = (pose_maps.amax(dim=-1, keepdim=True).expand(-1, -1, -1, 3) + 1) * 127.5
-        return G.cpu().numpy(), pose_img.cpu().numpy(), score.cpu().numpy()
+        # ---- SSIM(G, x) per sample on the uint8 images (tester.py:236-241), on the device
+        self.last_ssim = self.ssim_G_x(st)
+        G_np, pose_np = G.cpu().numpy(), pose_img.cpu().numpy()
+        if save and root_path is not None:                       # tester.py:242-252
+            ssim_mean = float(np.mean(self.last_ssim))
+            outputs.save_image(G_np, path or os.path.join(root_path, "%s_G_ssim%s.png" % (idx, ssim_mean)))
+            outputs.save_image(pose_np, os.path.join(root_path, "%s_G_pose_inflated_reLoss%s.png" % (idx, 0.0)))
+        return G_np, pose_np, score.cpu().numpy()
+
+    def ssim_G_x(self, stream=None):
+        """skimage-style SSIM between the generated and the input images of the current batch, per sample [B]."""
+        s1, B = self.s1, self.batch_size
+        st = stream if stream is not None else torch.cuda.current_stream().cuda_stream
+        H, W = self.cfg.img_h, self.cfg.img_w
+        g8 = torch.empty((B, H, W, 3), dtype=torch.uint8, device=s1.device)
+        x8 = torch.empty((B, H, W, 3), dtype=torch.uint8, device=s1.device)
+        out = torch.empty((B,), dtype=torch.float32, device=s1.device)
+        self.ctx.denorm_u8(ptr(s1.G), s1.G.numel(), ptr(g8), st)
+        self.ctx.denorm_u8(ptr(s1.x), s1.x.numel(), ptr(x8), st)
+        self.ctx.ssim_gray_u8(ptr(g8), ptr(x8), B, H, W, ptr(out), st)
+        return out.cpu().numpy()
+
+    def _pose_max_img(self, pose_rcv):
+        """(amax over the 18 inflated keypoint maps + 1) * 127.5 (tester.py:175-176) for a [B,18,3] keypoint array."""
+        B, H, W = self.batch_size, self.cfg.img_h, self.cfg.img_w
+        rcv = torch.as_tensor(np.asarray(pose_rcv, np.float32)).to(self.s1.device)
+        maps = torch.empty((B, H, W, self.keypoint_num), dtype=torch.float32, device=self.s1.device)
+        self.ctx.pose_rasterize(ptr(rcv), B, self.keypoint_num, H, W, 4, None, ptr(maps),
+                                torch.cuda.current_stream().cuda_stream)
+        return ((maps.amax(dim=-1) + 1.0) * 127.5).cpu().numpy()
 
     def test(self, num_batches=None):
+        """tester.py:138-202: the eight per-sample PNG directories + the sample sheets of the first batch."""
         out_dir = os.path.join(self.model_dir, "test_result_SampleFg%rSampleBg%rSamplePose%r" % (
             self.sample_fg, self.sample_bg, self.sample_pose))
-        os.makedirs(out_dir, exist_ok=True)
+        wr = outputs.ResultWriter(out_dir)
+        B = self.batch_size
         for i in range(num_batches or self.test_batch_num):
             b = self.loader.next_batch()
-            G, pose_img, score = self.generate(b["x"], None, b["pose_rcv"], b["part_bbox"], b["part_vis"], mask=b["mask"])
-            np.save(os.path.join(out_dir, "G_%05d.npy" % i), G.astype(np.uint8))
+            G, G_pose, score = self.generate(b["x"], None, b["pose_rcv"], b["part_bbox"], b["part_vis"], mask=b["mask"],
+                                             root_path=out_dir, idx=i, save=i < 4)
+            x255 = (np.asarray(b["x"]) + 1.0) * 127.5                         # unprocess_image (tester.py:207)
+            xt255 = (np.asarray(b.get("x_target", b["x"])) + 1.0) * 127.5
+            mask255 = np.asarray(b["mask"]) * 255.0
+            maskt255 = np.asarray(b.get("mask_target", b["mask"])) * 255.0
+            p = self._pose_max_img(b["pose_rcv"])
+            pt = self._pose_max_img(b.get("pose_rcv_target", b["pose_rcv"]))
+            wr.add_batch(i, B, x255, xt255, G, p, pt, G_pose, mask255, maskt255, np.asarray(score).reshape(-1))
+            if i == 0:
+                wr.add_grid(x255, "x_fixed.png")
+                wr.add_grid(xt255, "x_target_fixed.png")
+                wr.add_grid(mask255, "mask_fixed.png")
+                wr.add_grid(maskt255, "mask_target_fixed.png")
+                wr.add_grid(p[..., None], "pose_fixed.png")
+                wr.add_grid(pt[..., None], "pose_target_fixed.png")
+        self.files_written = wr.close()
         return out_dir

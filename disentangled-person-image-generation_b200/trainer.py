@@ -20,7 +20,7 @@ import time
 import numpy as np
 import torch
 
-from . import _lib, datasets, engine, synth, tf_checkpoint
+from . import _lib, datasets, engine, outputs, synth, tf_checkpoint
 from .tensor import ptr
 
 
@@ -153,9 +153,19 @@ class DPIG_Encoder_GAN_BodyROI_FgBg(object):
         self.net.set_batch(dict(x=np.asarray(x, np.float32), pose_rcv=np.asarray(pose, np.float32), mask=mask,
                                 part_bbox=np.asarray(part_bbox), part_vis=np.asarray(part_vis, np.float32)))
         self.net.forward(with_disc=False)
+        st = torch.cuda.current_stream().cuda_stream
         out = torch.empty((B, self.img_H, self.img_W, 3), dtype=torch.uint8, device=self.net.device)
-        self.ctx.denorm_u8(ptr(self.net.G), self.net.G.numel(), ptr(out), torch.cuda.current_stream().cuda_stream)
-        return out.cpu().numpy()
+        self.ctx.denorm_u8(ptr(self.net.G), self.net.G.numel(), ptr(out), st)
+        # per-sample SSIM(G, x) on the uint8 images (trainer.py:516-521), computed on the device
+        x8 = torch.empty_like(out)
+        ssim = torch.empty((B,), dtype=torch.float32, device=self.net.device)
+        self.ctx.denorm_u8(ptr(self.net.x), self.net.x.numel(), ptr(x8), st)
+        self.ctx.ssim_gray_u8(ptr(out), ptr(x8), B, self.img_H, self.img_W, ptr(ssim), st)
+        self.last_ssim = ssim.cpu().numpy()
+        G = out.cpu().numpy()
+        if save and (path is not None or root_path is not None):   # trainer.py:522-525
+            outputs.save_image(G, path or os.path.join(root_path, "%s_G_ssim%s.png" % (idx, float(self.last_ssim.mean()))))
+        return G
 
     def test(self):
         """Reconstruction pass over the loader (tester-style): writes G as .npy batches under model_dir/test_result."""

@@ -337,6 +337,12 @@ int dpig_clip(dpig_ctx* ctx, float* p, int64_t count, float lo, float hi, dpig_s
 /* u8 = clip((g+1)*127.5, 0, 255) */
 int dpig_denorm_u8(dpig_ctx* ctx, const float* g, int64_t count, uint8_t* out,
                    dpig_stream stream);
+/* SSIM of generate() (trainer.py:514-526, tester.py:236-241) on the device: a, b uint8 [n,h,w,3] (a = the generated
+ * image, b = the input image); out[i] = skimage.measure.compare_ssim(rgb2gray(a[i]), rgb2gray(b[i]),
+ * data_range = gray(b[i]).max() - gray(b[i]).min()) with scikit-image's defaults (7x7 uniform window, K1 .01, K2 .03,
+ * sample covariance, float64). */
+int dpig_ssim_gray_u8(dpig_ctx* ctx, const uint8_t* a, const uint8_t* b, int32_t n, int32_t h, int32_t w,
+                      float* out, dpig_stream stream);
 /* rcv: fp32 [n][k][3] (row, col, visible) -> {-1,+1} maps [n,h,w,k] dilated by the radius-4 disc
  * of tf_poseInflate; written as a split tensor slice (hi plane only is needed). */
 int dpig_pose_rasterize(dpig_ctx* ctx, const float* rcv, int32_t n, int32_t k, int32_t h,
