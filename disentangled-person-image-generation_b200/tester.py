@@ -108,22 +108,16 @@ class DPIG_FourNetsFgBg_testOnlySampleFactor(object):
             vis = torch.round(torch.sigmoid(self.pose_vis_logit.data))            # binaryRound (models.py:97-108)
             g = torch.cat([self.pose_coord.data.reshape(B, self.keypoint_num, 2), vis[:, :, None]], dim=-1)
         else:
-            g = norm[:1].expand(B, -1, -1)
+            g = self._held_pose(norm)
         R = torch.clamp((g[:, :, 0] + 1) / 2.0 * H, 0, H - 1)                      # utils.py:266-271
         Cc = torch.clamp((g[:, :, 1] + 1) / 2.0 * W, 0, W - 1)
         s1.pose_rcv.copy_(torch.stack([R, Cc, g[:, :, 2]], dim=-1))
         # ---- appearance branch (tester.py:509-554)
         s2.encode_real()
-        nfg = s2.fg_dim
-        for factor, z, sample in (("fg", z_fg, self.sample_fg), ("bg", z_bg, self.sample_bg)):
-            f = s2.f[factor]
+        for factor, z in (("fg", z_fg), ("bg", z_bg)):
             s2.sample_noise(factor, z)
-            f.p_g_fwd.run(st)
-            sl = slice(0, nfg) if factor == "fg" else slice(nfg, None)
-            if sample:
-                s1.emb[:, sl].copy_(f.fake.data)
-            else:
-                s1.emb[:, sl].copy_(f.real.data[:1].expand(B, -1))
+            s2.f[factor].p_g_fwd.run(st)
+        self._fill_embedding()
         # ---- U-Net, denorm, critic score (tester.py:561-571)
         s1.run_unet(st)
         score = s1.score_generated(st)
@@ -138,6 +132,23 @@ class DPIG_FourNetsFgBg_testOnlySampleFactor(object):
             outputs.save_image(G_np, path or os.path.join(root_path, "%s_G_ssim%s.png" % (idx, ssim_mean)))
             outputs.save_image(pose_np, os.path.join(root_path, "%s_G_pose_inflated_reLoss%s.png" % (idx, 0.0)))
         return G_np, pose_np, score.cpu().numpy()
+
+    def _held_pose(self, norm):
+        """sample_pose=False: the first sample's real pose for the whole batch (tester.py:500-503)."""
+        return norm[:1].expand(self.batch_size, -1, -1)
+
+    def _fill_embedding(self):
+        """Which appearance factors reach the U-Net (tester.py:540-554): a sampled factor takes the GaussianFCRes
+        output, a held one the first sample's encoder embedding tiled over the batch."""
+        s1, s2, B = self.s1, self.s2, self.batch_size
+        nfg = s2.fg_dim
+        for factor, sample in (("fg", self.sample_fg), ("bg", self.sample_bg)):
+            f = s2.f[factor]
+            sl = slice(0, nfg) if factor == "fg" else slice(nfg, None)
+            if sample:
+                s1.emb[:, sl].copy_(f.fake.data)
+            else:
+                s1.emb[:, sl].copy_(f.real.data[:1].expand(B, -1))
 
     def ssim_G_x(self, stream=None):
         """skimage-style SSIM between the generated and the input images of the current batch, per sample [B]."""
@@ -187,3 +198,147 @@ class DPIG_FourNetsFgBg_testOnlySampleFactor(object):
                 wr.add_grid(pt[..., None], "pose_target_fixed.png")
         self.files_written = wr.close()
         return out_dir
+
+
+class DPIG_FourNetsFgBg_testOnly(DPIG_FourNetsFgBg_testOnlySampleFactor):
+    """--model=11 (tester.py:256-417): the same four networks with the `--sample_app` / `--one_app_per_batch` switches
+    instead of per-factor ones.
+      sample_app:        embedding = [Gaussian_FC_Fg(z) (its first row tiled if one_app_per_batch), Gaussian_FC_Bg(z)]
+      otherwise:         the encoder embedding; with one_app_per_batch the first sample's Fg part tiled, own Bg parts
+      sample_pose=False: every sample keeps its OWN real pose (tester.py:349-351), unlike model 13."""
+
+    def __init__(self, config, loader=None):
+        super().__init__(config, loader=loader)
+        self.sample_app = getattr(config, "sample_app", False)
+        self.one_app_per_batch = getattr(config, "one_app_per_batch", False)
+        self.test_batch_num = 400
+
+    def _held_pose(self, norm):
+        return norm
+
+    def _fill_embedding(self):
+        s1, s2, B = self.s1, self.s2, self.batch_size
+        nfg = s2.fg_dim
+        fg, bg = s2.f["fg"], s2.f["bg"]
+        if self.sample_app:
+            s1.emb[:, :nfg].copy_(fg.fake.data[:1].expand(B, -1) if self.one_app_per_batch else fg.fake.data)
+            s1.emb[:, nfg:].copy_(bg.fake.data)
+        else:
+            s1.emb[:, :nfg].copy_(fg.real.data[:1].expand(B, -1) if self.one_app_per_batch else fg.real.data)
+            s1.emb[:, nfg:].copy_(bg.real.data)
+
+    def test(self, num_batches=None):
+        out = super().test(num_batches)
+        return out
+
+
+class DPIG_FourNetsFgBg_testOnlyCondition(object):
+    """--model=12 (tester.py:616-773): pose-conditioned generation.  Encoder(x, mask, part boxes) -> embedding -> U-Net
+    driven by the TARGET pose maps -> G, critic score of G; SSIM against x_target; result directories without G_pose and
+    with plain `%05d.png` names for G (tester.py:752)."""
+    deepfashion = False
+
+    def __init__(self, config, loader=None):
+        self.config = config
+        self.batch_size = config.batch_size
+        self.img_H, self.img_W = config.img_H, config.img_W
+        self.conv_hidden_num, self.z_num = config.conv_hidden_num, config.z_num
+        self.keypoint_num = 18
+        self.model_dir = config.model_dir or os.path.join(config.log_dir, "dpig_model%d" % config.model)
+        self.pretrained_path, self.ckpt_path = config.pretrained_path, config.ckpt_path
+        self.test_batch_num = 600        # tester.py:650
+        self.test_dir_name = "test_samples_result_ROI7_Condition_TargetPose_%dx%d" % (self.test_batch_num, self.batch_size)
+        self.loader = loader or make_loader(config, self.batch_size, self.img_H, self.img_W)
+
+    def init_net(self, net_cfg=None):
+        self.ctx = _lib.Context(0)
+        if net_cfg is None:
+            net_cfg = (engine.NetConfig.deepfashion(img_h=self.img_H, img_w=self.img_W, hidden=self.conv_hidden_num)
+                       if self.deepfashion else
+                       engine.NetConfig(img_h=self.img_H, img_w=self.img_W, hidden=self.conv_hidden_num, z_num=self.z_num))
+        self.cfg = net_cfg
+        self.s1 = engine.Stage1Engine(self.ctx, net_cfg, self.batch_size, mode="dcgan")
+        self.s1.load_params(engine.init_params(net_cfg, seed=self.config.random_seed))
+        # saverPart = Encoder + ID_AE + Discriminator. (tester.py:619-623); --ckpt_path restores everything
+        if self.pretrained_path:
+            self.s1.load_params(tf_checkpoint.load_any(self.pretrained_path, scopes=["Encoder", "ID_AE", "Discriminator."]))
+        if self.ckpt_path:
+            self.s1.load_params(tf_checkpoint.load_any(self.ckpt_path))
+
+    def load_params(self, params):
+        self.s1.load_params(params)
+
+    def generate(self, x_fixed, x_target_fixed, pose_rcv_target_fixed, mask_fixed, part_bbox_fixed, part_vis_fixed,
+                 root_path=None, path=None, idx=None, save=True):
+        """(G in [0,255] NHWC float32, critic score [B]) like tester.py:688-702; the target pose is given as keypoints
+        (pose_peaks_1_rcv) and rasterised + inflated on the device (the reference feeds the ready maps)."""
+        s1, B = self.s1, self.batch_size
+        H, W = self.cfg.img_h, self.cfg.img_w
+        st = torch.cuda.current_stream().cuda_stream
+        if mask_fixed is None:
+            mask_fixed = np.ones((B, H, W, 1), np.float32)
+        s1.set_batch(dict(x=x_fixed, pose_rcv=pose_rcv_target_fixed, mask=mask_fixed, part_bbox=part_bbox_fixed,
+                          part_vis=part_vis_fixed))
+        s1.forward(with_disc=False)
+        score = s1.score_generated(st) if not self.deepfashion else torch.zeros((B,), device=s1.device)
+        G = torch.clamp((s1.G + 1.0) * 127.5, 0, 255)
+        # SSIM against the TARGET image (tester.py:692-697)
+        g8 = torch.empty((B, H, W, 3), dtype=torch.uint8, device=s1.device)
+        t8 = torch.empty_like(g8)
+        xt = torch.as_tensor(np.asarray(x_target_fixed, np.float32)).to(s1.device).contiguous()
+        out = torch.empty((B,), dtype=torch.float32, device=s1.device)
+        self.ctx.denorm_u8(ptr(s1.G), s1.G.numel(), ptr(g8), st)
+        self.ctx.denorm_u8(ptr(xt), xt.numel(), ptr(t8), st)
+        self.ctx.ssim_gray_u8(ptr(g8), ptr(t8), B, H, W, ptr(out), st)
+        self.last_ssim = out.cpu().numpy()
+        G_np = G.cpu().numpy()
+        if save and (path is not None or root_path is not None):
+            outputs.save_image(G_np, path or os.path.join(root_path, "%s_G_ssim%s.png" % (idx, float(self.last_ssim.mean()))))
+        return G_np, score.reshape(-1).cpu().numpy()
+
+    def _pose_max_img(self, pose_rcv):
+        B, H, W = self.batch_size, self.cfg.img_h, self.cfg.img_w
+        rcv = torch.as_tensor(np.asarray(pose_rcv, np.float32)).to(self.s1.device)
+        maps = torch.empty((B, H, W, self.keypoint_num), dtype=torch.float32, device=self.s1.device)
+        self.ctx.pose_rasterize(ptr(rcv), B, self.keypoint_num, H, W, 4, None, ptr(maps),
+                                torch.cuda.current_stream().cuda_stream)
+        return ((maps.amax(dim=-1) + 1.0) * 127.5).cpu().numpy()
+
+    def test(self, num_batches=None):
+        """tester.py:704-773."""
+        out_dir = os.path.join(self.model_dir, self.test_dir_name)
+        wr = outputs.ResultWriter(out_dir)
+        B = self.batch_size
+        for i in range(num_batches or self.test_batch_num):
+            b = self.loader.next_batch()
+            xt = b.get("x_target", b["x"])
+            G, score = self.generate(b["x"], xt, b.get("pose_rcv_target", b["pose_rcv"]), b.get("mask"), b["part_bbox"],
+                                     b["part_vis"], root_path=out_dir, idx=i, save=(i == 0))
+            x255, xt255 = (np.asarray(b["x"]) + 1.0) * 127.5, (np.asarray(xt) + 1.0) * 127.5
+            mask = np.asarray(b["mask"]) if "mask" in b else np.zeros((B, self.cfg.img_h, self.cfg.img_w, 1), np.float32)
+            maskt = np.asarray(b.get("mask_target", mask))
+            p, pt = self._pose_max_img(b["pose_rcv"]), self._pose_max_img(b.get("pose_rcv_target", b["pose_rcv"]))
+            for j in range(B):
+                idx = i * B + j
+                for d, arr in (("x", x255[j]), ("x_target", xt255[j]), ("G", G[j]), ("pose", p[j]), ("pose_target", pt[j]),
+                               ("mask", np.squeeze(mask[j] * 255.0)), ("mask_target", np.squeeze(maskt[j] * 255.0))):
+                    wr._submit(arr, "%s/%s/%05d.png" % (out_dir, d, idx))
+            if i == 0:
+                wr.add_grid(x255, "x_fixed.png")
+                wr.add_grid(xt255, "x_target_fixed.png")
+                wr.add_grid(mask * 255.0, "mask_fixed.png")
+                wr.add_grid(maskt * 255.0, "mask_target_fixed.png")
+                wr.add_grid(p[..., None], "pose_fixed.png")
+                wr.add_grid(pt[..., None], "pose_target_fixed.png")
+        self.files_written = wr.close()
+        return out_dir
+
+
+class DPIG_ThreeNetsApp_testOnlyCondition_256(DPIG_FourNetsFgBg_testOnlyCondition):
+    """--model=1001 (tester.py:775-915): the DeepFashion 256x256 form -- encoder without mask / background branch
+    (GeneratorCNN_ID_Encoder_BodyROIVis, roi 64), 5-level U-Net, no critic in the graph."""
+    deepfashion = True
+
+    def __init__(self, config, loader=None):
+        super().__init__(config, loader=loader)
+        self.test_dir_name = "test_result_ROI7_Condition_TargetPose_%dx%d" % (self.test_batch_num, self.batch_size)

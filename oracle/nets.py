@@ -565,3 +565,43 @@ def sample_factor_forward(p, cfg, batch, z_fg, z_bg, sample_fg, sample_bg, sampl
     G, _ = unet_generator(p, cfg, torch.cat([e_fg, e_bg], dim=-1), pose_maps)
     score = dcgan_discriminator(p, cfg, G, mode)
     return dict(G=T.denorm_img(G), G_raw=G, score=score, pose_pix=pix, pose_maps=pose_maps)
+
+
+def four_nets_forward(p, cfg, batch, z_fg, z_bg, sample_app, one_app_per_batch, sample_pose, mode="dcgan"):
+    """DPIG_FourNetsFgBg_testOnly.build_model (tester.py:323-417, --model=11): `sample_app` replaces the whole
+    appearance embedding by the two GaussianFCRes outputs (the Fg row of sample 0 tiled when `one_app_per_batch`),
+    otherwise the encoder embedding is kept (first sample's Fg part tiled when `one_app_per_batch`); without
+    `sample_pose` every sample keeps its own real pose (tester.py:349-351)."""
+    x = batch["x"]
+    B, H, W = x.shape[0], cfg.img_h, cfg.img_w
+    rcv = batch["pose_rcv"]
+    norm = torch.stack([rcv[:, :, 0] / float(H) * 2.0 - 1, rcv[:, :, 1] / float(W) * 2.0 - 1, rcv[:, :, 2]], dim=-1)
+    coord, vis = pose_decoder_fc_res(p, pose_encoder_fc_res(p, norm.reshape(B, -1)))
+    g_rcv = torch.cat([coord.reshape(B, cfg.keypoints, 2), vis[:, :, None]], dim=-1) if sample_pose else norm
+    R = torch.clamp((g_rcv[:, :, 0] + 1) / 2.0 * H, 0, H - 1)
+    C = torch.clamp((g_rcv[:, :, 1] + 1) / 2.0 * W, 0, W - 1)
+    pix = torch.stack([R, C, g_rcv[:, :, 2]], dim=-1)
+    pose_maps = T.pose_rasterize(pix, H, W, 4)
+    emb = encoder(p, cfg, batch)
+    nfg = cfg.n_parts * cfg.part_z
+    lrelu = lambda t: T.leaky_relu(t, 0.2)
+    if sample_app:
+        fg = gaussian_fc_res(p, z_fg, 4, "Gaussian_FC_Fg/G_FC", lrelu)
+        bg = gaussian_fc_res(p, z_bg, 4, "Gaussian_FC_Bg/G_FC", lrelu)
+    else:
+        fg, bg = emb[:, :nfg], emb[:, nfg:]
+    if one_app_per_batch:
+        fg = fg[:1].expand(B, -1)
+    G, _ = unet_generator(p, cfg, torch.cat([fg, bg], dim=-1), pose_maps)
+    score = dcgan_discriminator(p, cfg, G, mode)
+    return dict(G=T.denorm_img(G), G_raw=G, score=score, pose_pix=pix, pose_maps=pose_maps)
+
+
+def condition_forward(p, cfg, batch, pose_rcv_target, mode="dcgan"):
+    """DPIG_FourNetsFgBg_testOnlyCondition.build_model (tester.py:657-686, --model=12; _256 form tester.py:815-836):
+    appearance of x, TARGET pose maps (rasterised + inflated keypoints of the second image of the pair)."""
+    pose_t = T.pose_rasterize(pose_rcv_target, cfg.img_h, cfg.img_w, 4)
+    emb = encoder(p, cfg, batch)
+    G, _ = unet_generator(p, cfg, emb, pose_t)
+    score = None if cfg.d_joint else dcgan_discriminator(p, cfg, G, mode)
+    return dict(G=T.denorm_img(G), G_raw=G, score=score, pose_maps=pose_t)

@@ -55,3 +55,99 @@ def test_sample_factor_forward(sample):
         assert float(np.abs(score - ref["score"].numpy()).max()) < 1e-3
     assert G.shape == (B, 32, 16, 3) and pose_img.shape == (B, 32, 16, 3) and score.shape == (B,)
     assert G.min() >= 0 and G.max() <= 255
+
+
+def _four_nets(cls_name, argv, B=4):
+    from dpig_b200 import config as cfgmod
+    from dpig_b200 import engine, tester
+    kw = dict(img_h=32, img_w=16, hidden=64, roi_size=12, d_dim=64)
+    conf, _ = cfgmod.get_config(["--is_train=False", "--batch_size=%d" % B, "--img_H=32", "--img_W=16",
+                                 "--conv_hidden_num=64"] + argv)
+    t = getattr(tester, cls_name)(conf)
+    t.init_net(engine.NetConfig(**kw))
+    ocfg = nets.NetConfig(**kw)
+    params = dict(nets.init_params(ocfg, seed=11, bias_noise=0.05))
+    params.update(nets.init_stage2_params(seed=12, bias_noise=0.05))
+    params.update(nets.init_pose_params(seed=13, bias_noise=0.05))
+    t.load_params(params)
+    return t, ocfg, nets.to_torch(params, torch.float64)
+
+
+@pytest.mark.parametrize("sample_app,one_app", [(True, False), (True, True), (False, True), (False, False)])
+def test_four_nets_test_only_model11(sample_app, one_app):
+    """--model=11 (tester.py:256-417): sample_app / one_app_per_batch switches; every sample keeps its own pose."""
+    from dpig_b200 import synth
+    B = 4
+    t, ocfg, p = _four_nets("DPIG_FourNetsFgBg_testOnly", ["--model=11", "--sample_app=%s" % sample_app,
+                                                           "--one_app_per_batch=%s" % one_app, "--sample_pose=False"], B)
+    b = synth.make_batch(B, 32, 16, seed=23)
+    rng = np.random.default_rng(6)
+    z_fg = rng.normal(0, 0.2, size=(B, 224)).astype(np.float32)
+    z_bg = rng.normal(0, 0.2, size=(B, 128)).astype(np.float32)
+    G, pose_img, score = t.generate(b["x"], None, b["pose_rcv"], b["part_bbox"], b["part_vis"], mask=b["mask"], z_fg=z_fg,
+                                    z_bg=z_bg)
+    ob = dict(x=torch.tensor(b["x"], dtype=torch.float64), mask=torch.tensor(b["mask"], dtype=torch.float64),
+              pose_rcv=torch.tensor(b["pose_rcv"], dtype=torch.float64),
+              part_bbox=torch.tensor(b["part_bbox"][:, :7]), part_vis=torch.tensor(b["part_vis"][:, :7]))
+    ref = nets.four_nets_forward(p, ocfg, ob, torch.tensor(z_fg, dtype=torch.float64), torch.tensor(z_bg, dtype=torch.float64),
+                                 sample_app, one_app, False)
+    maps = t.s1.gin.slice(0, 18).hi.float().cpu().double()
+    assert float((maps != ref["pose_maps"]).double().mean()) == 0.0      # integer keypoints: exact
+    assert float(np.abs(G - ref["G"].numpy()).max()) < 0.2               # 1e-3 on [-1,1] == 0.13 on [0,255]
+    assert float(np.abs(score - ref["score"].numpy()).max()) < 1e-3
+
+
+def test_condition_model12_matches_oracle_and_writes_results(tmp_path):
+    """--model=12 (tester.py:616-773): appearance of x, target pose; SSIM against x_target; result directories."""
+    from dpig_b200 import synth
+    B = 4
+    t, ocfg, p = _four_nets("DPIG_FourNetsFgBg_testOnlyCondition", ["--model=12", "--model_dir=%s" % tmp_path], B)
+    b = synth.make_batch(B, 32, 16, seed=31)
+    bt = synth.make_batch(B, 32, 16, seed=32)
+    G, score = t.generate(b["x"], bt["x"], bt["pose_rcv"], b["mask"], b["part_bbox"], b["part_vis"], save=False)
+    ob = dict(x=torch.tensor(b["x"], dtype=torch.float64), mask=torch.tensor(b["mask"], dtype=torch.float64),
+              part_bbox=torch.tensor(b["part_bbox"][:, :7]), part_vis=torch.tensor(b["part_vis"][:, :7]))
+    ref = nets.condition_forward(p, ocfg, ob, torch.tensor(bt["pose_rcv"], dtype=torch.float64))
+    assert float(np.abs(G - ref["G"].numpy()).max()) < 0.2
+    assert float(np.abs(score - ref["score"].numpy()).max()) < 1e-3
+    from oracle import image_metrics as im
+    G8 = np.clip(G, 0, 255).astype(np.uint8)
+    t8 = np.clip((bt["x"] + 1.0) * 127.5, 0, 255).astype(np.uint8)
+    assert np.allclose(t.last_ssim, im.ssim_generate(G8, t8), atol=5e-6)
+
+    class PairLoader:
+        def next_batch(self):
+            d = dict(b)
+            d.update(x_target=bt["x"], pose_rcv_target=bt["pose_rcv"], mask_target=bt["mask"])
+            return d
+    t.loader = PairLoader()
+    out_dir = t.test(num_batches=2)
+    for d in ("x", "x_target", "G", "pose", "pose_target", "mask", "mask_target"):
+        assert sorted(os.listdir(os.path.join(out_dir, d)))[:2] == ["00000.png", "00001.png"], d
+        assert len(os.listdir(os.path.join(out_dir, d))) == 2 * B
+    assert len(os.listdir(os.path.join(out_dir, "G_pose"))) == 0          # model 12 writes no G_pose files
+    assert any(f.startswith("0_G_ssim") for f in os.listdir(out_dir))
+
+
+def test_condition_256_model1001_matches_oracle():
+    """--model=1001 (tester.py:775-915): DeepFashion form (no mask / Bg branch, no critic in the graph), small geometry."""
+    from dpig_b200 import config as cfgmod
+    from dpig_b200 import engine, synth, tester
+    B = 2
+    kw = dict(img_h=128, img_w=128, hidden=64, roi_size=32)          # DF_SMALL of tests/test_df256_gpu.py
+    conf, _ = cfgmod.get_config(["--model=1001", "--is_train=False", "--batch_size=%d" % B, "--img_H=128", "--img_W=128",
+                                 "--conv_hidden_num=64"])
+    t = tester.DPIG_ThreeNetsApp_testOnlyCondition_256(conf)
+    ecfg = engine.NetConfig.deepfashion(**kw)
+    t.init_net(ecfg)
+    ocfg = nets.NetConfig.deepfashion(**kw)
+    params = nets.init_params(ocfg, seed=17, bias_noise=0.05)
+    t.load_params(params)
+    b = synth.make_batch(B, 128, 128, seed=41)
+    bt = synth.make_batch(B, 128, 128, seed=42)
+    G, score = t.generate(b["x"], bt["x"], bt["pose_rcv"], None, b["part_bbox"], b["part_vis"], save=False)
+    ob = dict(x=torch.tensor(b["x"], dtype=torch.float64), mask=torch.tensor(b["mask"], dtype=torch.float64),
+              part_bbox=torch.tensor(b["part_bbox"][:, :7]), part_vis=torch.tensor(b["part_vis"][:, :7]))
+    ref = nets.condition_forward(nets.to_torch(params, torch.float64), ocfg, ob, torch.tensor(bt["pose_rcv"], dtype=torch.float64))
+    assert float(np.abs(G - ref["G"].numpy()).max()) < 0.2
+    assert (score == 0).all()
