@@ -22,6 +22,7 @@ struct dpig_ctx {
   bool merge_planes = true;  // fetch hi+lo with one TMA instruction where the layout allows (DPIG_CONV_MERGE=0 disables)
   bool epi_tma = true;       // split-bf16 conv outputs leave the SM as TMA tensor stores (DPIG_EPI_TMA=0: per-lane stores)
   bool dgrad_merge = true;   // stride-2 data gradients: the four parity classes in one launch (DPIG_DGRAD_MERGE=0: four)
+  bool add_prefetch = true;  // L2 prefetch of a tile's residual rows ahead of the epilogue (DPIG_ADD_PREFETCH=0: off)
   int tune_small = 1;        // channel block of few-pixel layers: 1 cost model, 2 the old halving rule, 0 always the widest (DPIG_TUNE_SMALL)
   int epi_bufs = 0;          // epilogue staging buffers per warp set: 0 auto, 1 always one, 2 two wherever two stages still fit (DPIG_EPI_BUFS)
   bool wide_b = true;        // hi|lo weight rows as one N = 2*block_n MMA operand for block_n <= 128 (DPIG_WIDE_B=0: three N = block_n MMAs)

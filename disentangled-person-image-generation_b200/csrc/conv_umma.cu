@@ -88,6 +88,7 @@ struct ConvUmmaParams {
   CUtensorMap out2_map[4][2];
   int out_tma, out2_tma;
   int epi_bufs;  // staging buffers per warp set (1 or 2), used alternately by successive TMA stores
+  int add_prefetch;  // pull the residual rows of a tile into L2 before its accumulator is awaited
 };
 
 __device__ __forceinline__ uint8_t* align1024(uint8_t* p) {
@@ -269,10 +270,15 @@ __device__ __forceinline__ void epi_chunk(const ConvUmmaParams& p, EpiTile& t, u
   // bias of the chunk's 32 channels: ONE coalesced load per warp, broadcast by shuffles.  (32 predicated scalar loads,
   // each followed by its dependent add, cost ~10k clk per chunk on the long scoreboard -- half of the whole tile time
   // of every short-K layer, profiles/r01_epilogue_bias_ncu.txt.)
-  float bl = 0.f;
-  if (p.bias && lane < nvalid) bl = __ldg(p.bias + cbase + lane);
+  if (p.bias) {
+    float bl = 0.f;
+    if (lane < nvalid) bl = __ldg(p.bias + cbase + lane);
 #pragma unroll
-  for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]) + __shfl_sync(0xffffffffu, bl, i);
+    for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]) + __shfl_sync(0xffffffffu, bl, i);
+  } else {   // data gradients carry no bias: no shuffles
+#pragma unroll
+    for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
+  }
   if (cbias) {  // per-pixel (border class) bias row: vector loads, issued back to back
     if (full32) {
       const float4* cb4 = reinterpret_cast<const float4*>(cbias + cbase);
@@ -292,13 +298,15 @@ __device__ __forceinline__ void epi_chunk(const ConvUmmaParams& p, EpiTile& t, u
         if (i < nvalid) f[i] += __ldg(cbias + cbase + i);
     }
   }
+  if (p.mask_out || p.act != DPIG_ACT_NONE) {
 #pragma unroll
-  for (int i = 0; i < 32; ++i) {
-    float x = f[i];
-    mbits |= (x > 0.f ? 1u : 0u) << i;
-    if (p.act == DPIG_ACT_RELU) x = fmaxf(x, 0.f);
-    else if (p.act == DPIG_ACT_LRELU) x = x > 0.f ? x : p.alpha * x;
-    f[i] = x;
+    for (int i = 0; i < 32; ++i) {
+      float x = f[i];
+      mbits |= (x > 0.f ? 1u : 0u) << i;
+      if (p.act == DPIG_ACT_RELU) x = fmaxf(x, 0.f);
+      else if (p.act == DPIG_ACT_LRELU) x = x > 0.f ? x : p.alpha * x;
+      f[i] = x;
+    }
   }
   // ---- residual / addend
   if (p.add_hi) {
@@ -709,6 +717,17 @@ conv_umma_kernel(const __grid_constant__ ConvUmmaParams p) {
         cbias = p.class_bias + (static_cast<long long>(n) * 9 + ch * 3 + cw) * p.cout;
       }
 
+      // The residual rows of this tile are gathered chunk by chunk further down, each gather an exposed global-load
+      // latency (12 % of all stall samples of a two-output data gradient, profiles/r01_dgrad_epilogue_micro.txt):
+      // pull them into L2 now, while the tile's MMAs are still running.
+      if (p.add_prefetch && p.add_hi && valid && cpar == 0) {
+        const long long e0 = static_cast<long long>(ppix) * p.add_ps + nt * p.block_n;
+        const int ne = min(p.block_n, p.cout - nt * p.block_n);
+        for (int e = 0; e < ne; e += 64) {
+          ptx::prefetch_l2(p.add_hi + e0 + e);
+          if (p.add_lo) ptx::prefetch_l2(p.add_lo + e0 + e);
+        }
+      }
       ptx::mbar_wait(&tmem_full[acc], (j >> 1) & 1);
       ptx::tc_fence_after();
       const uint32_t tmem_acc = tmem_base + acc * (kWide ? 2 * p.block_n : p.block_n) + (static_cast<uint32_t>(lg * 32) << 16);
@@ -1318,6 +1337,7 @@ static int fill_epilogue(dpig_ctx* ctx, ConvUmmaParams& P, const dpig_conv_epilo
     P.add_hi = static_cast<const __nv_bfloat16*>(ep->addend->hi);
     P.add_lo = static_cast<const __nv_bfloat16*>(ep->addend->lo);
     P.add_ps = ep->addend->pix_stride;
+    P.add_prefetch = ctx->add_prefetch ? 1 : 0;
   }
   P.out_f32 = ep->out_f32;
   P.out_f32_ps = ep->out_f32_pix_stride;

@@ -122,6 +122,9 @@ __device__ __forceinline__ void bulk_wait_group_read1() {
 __device__ __forceinline__ void bulk_wait_group0() {
   asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
+__device__ __forceinline__ void prefetch_l2(const void* p) {
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
 // named barrier among `count` threads (ids 1..15; 0 is __syncthreads)
 __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t count) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
