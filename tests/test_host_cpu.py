@@ -117,6 +117,54 @@ def test_launch_programs_record_without_a_device():
         engine.Stage1Engine(NoDeviceCtx(), cases[2][0], 2, mode="wgan-gp", device="cpu")
 
 
+def test_step_size_and_overlap_slice_host_logic(monkeypatch):
+    """Host logic of the data-parallel / graph-replay step: the device-side step size equals TF-Adam's lr_t computed the
+    way dpig_adam_step does (float32 lr and betas, float64 arithmetic), and the all-reduce that overlaps the encoder's
+    backward covers exactly the ID_AE parameters (one contiguous, 64-padded block of the generator arena) and is issued
+    right before the appearance encoder's backward."""
+    import math
+    from dpig_b200 import _lib, engine
+
+    class NoDeviceCtx:
+        lib, handle = _lib.load(), None
+
+    class FakeDist:
+        world_size, local_rank, rank = 2, 0, 0
+        calls = []
+
+        def all_reduce_sum(self, t):
+            self.calls.append(t.numel())
+
+    cfg = engine.NetConfig(img_h=32, img_w=16, hidden=64, roi_size=12)
+    eng = engine.Stage1Engine(NoDeviceCtx(), cfg, 2, mode="dcgan", device="cpu")
+    assert eng.use_graphs and not eng.overlap_comm                      # one GPU: graphs on, nothing to overlap
+    eng.g_lr, eng.t["g"] = 2e-5, 3
+    lr32, b2 = float(np.float32(2e-5)), float(np.float32(0.999))
+    assert eng._step_size("g") == lr32 * math.sqrt(1.0 - b2 ** 3) / (1.0 - 0.5 ** 3)
+    eng_w = engine.Stage1Engine(NoDeviceCtx(), cfg, 2, mode="wgan", device="cpu")
+    eng_w.d_lr = 5e-5
+    assert eng_w._step_size("d") == float(np.float32(5e-5))             # RMSProp: the plain lr
+    assert not any(c[0] is None and i > 0 and eng.p_bwd_gen.calls[i + 1][0] == "embedding_assemble"
+                   for i, c in enumerate(eng.p_bwd_gen.calls[:-1]))     # no hook without torch.distributed
+
+    monkeypatch.setenv("DPIG_GRAPHS", "1")
+    d = engine.Stage1Engine(NoDeviceCtx(), cfg, 2, mode="dcgan", dist=FakeDist(), device="cpu")
+    assert d.overlap_comm and not d.use_graphs                          # N > 1: eager lists unless DPIG_GRAPHS=2
+    lo, hi = d._idae_range()
+    assert lo % 64 == 0 and hi % 64 == 0 and 0 < lo < hi <= d.gp.total
+    for name, (off, n, _) in d.gp.specs.items():
+        assert (lo <= off and off + n <= hi) == name.startswith("ID_AE/"), name
+    names = [c[0] for c in d.p_bwd_gen.calls]
+    k = names.index("embedding_assemble")
+    assert names[k - 1] is None                                         # the python hook that starts the early all-reduce
+    # every ID_AE filter gradient is launched before the hook
+    idae_layers = sum(1 for v in d.conv.values() if v.wname.startswith("ID_AE/"))
+    before = names[:k].count("conv2d_bwd_filter") + names[:k].count("conv2d_bwd_filter_rows")
+    assert before == idae_layers, (before, idae_layers)
+    monkeypatch.setenv("DPIG_OVERLAP", "0")
+    assert not engine.Stage1Engine(NoDeviceCtx(), cfg, 2, mode="dcgan", dist=FakeDist(), device="cpu").overlap_comm
+
+
 def test_synthetic_batch_shapes_and_box_rule():
     from dpig_b200 import synth
     b = synth.make_batch(3, 128, 64, seed=7)
