@@ -10,19 +10,22 @@
 // conv kernel (forward and data-gradient):
 //   GEMM M = a box of <=128 output pixels (BW x BH x BN), N = block_n output channels,
 //   K = (filter taps) x (input channels in chunks of 64).
-//   A tile  : one 4-D TMA box of the NHWC activation per (tap, chunk); the tap shift is applied to
-//             the box coordinates and TMA's out-of-bounds zero fill *is* the SAME padding.
+//   A tile  : one TMA box of the NHWC activation per (tap, chunk), hi and lo planes in one instruction; the tap shift is
+//             applied to the box coordinates and TMA's out-of-bounds zero fill *is* the SAME padding.
 //             Stride-2 convs read one of four parity views of the input (src index), so every
 //             load is a plain dense box.
-//   B tile  : 3-D TMA box of the packed weights [tap][n][k] (K-major).
+//   B tile  : TMA box of the packed weights [tap][n][k] (K-major), hi rows then lo rows.
 //   both land in 128B-swizzled shared memory and are consumed by tcgen05.mma via descriptors.
-//   Warp roles: warp0 = TMA producer, warp1 = MMA issuer (+TMEM alloc), warps2..5 = epilogue
-//   (tcgen05.ld -> bias/act/residual/mask -> split-bf16 stores).
+//   Warp roles: warp0 = TMA producer, warp1 = MMA issuer (+TMEM alloc), warps2..9 = epilogue
+//   (tcgen05.ld -> bias/act/residual/mask -> split-bf16 rows staged in smem -> TMA tensor stores).
+//   Variants: <pair> 2-CTA clusters with cta_group::2 M=256 MMAs; <wide> hi|lo weight rows as one N = 2*block_n operand;
+//   stride-2 data gradients run their four parity classes in one launch (ConvUmmaParams::nclass).
 //
 // wgrad kernel (filter gradient):
 //   GEMM M = 128 input channels, N = block_n output channels, K = pixels (64 per step).
 //   Both operands are MN-major views of the same kind of TMA boxes (rows = pixels).
-//   One filter tap per CTA (blockIdx.y), split-K over pixel tiles (blockIdx.z), fp32 atomics.
+//   One filter tap per CTA, split-K over pixel tiles (blockIdx.z), fp32 atomics into the HWIO gradient;
+//   <pair>: two (tap, channel-tile) units per 2-CTA cluster share one dy tile (M=256 cta_group::2 MMAs).
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
@@ -652,9 +655,8 @@ conv_umma_kernel(const __grid_constant__ ConvUmmaParams p) {
       }
     }
   } else {
-    // ---------------- epilogue: 4 warps, thread = one accumulator row (= one output pixel).
-    // Global traffic goes through a warp-private 4 KB staging tile so that every warp-level load / store
-    // touches whole 64 B (bf16 planes) or 128 B (fp32) pixel rows instead of 32 scattered 16 B pieces.
+    // ---------------- epilogue: 8 warps in two sets, thread = one accumulator row (= one output pixel).
+    // Output rows are staged in the set's shared-memory buffer(s) and leave as TMA tensor stores (see kEpiSetBytes).
     const int lg = warp & 3;            // TMEM lane group this warp may read (hardware: warp id % 4)
     const int ew = warp - 2;            // epilogue warp index 0..kEpiWarps-1
     const int cpar = ew >> 2;           // which alternate 32-column chunks this warp takes
