@@ -185,3 +185,52 @@ def test_joint_discriminator_call_shares_batch_statistics():
     j2 = nets.dcgan_discriminator(p, cfg, torch.cat([x, y]), "wgan-gp")
     s2 = torch.cat([nets.dcgan_discriminator(p, cfg, x, "wgan-gp"), nets.dcgan_discriminator(p, cfg, y, "wgan-gp")])
     assert (j2 - s2).abs().max() < 1e-12
+
+
+def test_ops_against_scipy_as_a_third_implementation():
+    """The oracle's TF-semantics ops against scipy routines that were written by neither of us (the reference's
+    TensorFlow is not installable, so independent agreement is the available evidence):
+      * SAME stride-1 / stride-2 cross-correlation == scipy.signal.correlate2d on the explicitly padded image
+        (pad_before = pad_total // 2, the extra row / column at the bottom / right), subsampled by the stride;
+      * crop_and_resize == scipy.ndimage.map_coordinates(order=1) at TF's sample positions
+        y1*(H-1) + i*(y2-y1)*(H-1)/(c-1), with zeros outside the image;
+      * sigmoid cross-entropy == -l*log(sigmoid z) - (1-l)*log(1 - sigmoid z) via scipy.special.expit / log1p."""
+    from scipy import ndimage, signal, special
+    g = torch.Generator().manual_seed(3)
+    # --- convolution
+    for (H, W, k, s) in ((9, 7, 3, 1), (8, 6, 3, 2), (9, 7, 5, 2), (6, 6, 1, 1)):
+        x = torch.randn((1, H, W, 2), generator=g, dtype=torch.float64)
+        w = torch.randn((k, k, 2, 3), generator=g, dtype=torch.float64)
+        y = T.conv2d_same(x, w, None, s)[0].numpy()
+        oh, ow = -(-H // s), -(-W // s)
+        ph, pw = max((oh - 1) * s + k - H, 0), max((ow - 1) * s + k - W, 0)
+        xp = np.pad(x[0].numpy(), ((ph // 2, ph - ph // 2), (pw // 2, pw - pw // 2), (0, 0)))
+        ref = np.zeros((oh, ow, 3))
+        for co in range(3):
+            for ci in range(2):
+                full = signal.correlate2d(xp[:, :, ci], w[:, :, ci, co].numpy(), mode="valid")
+                ref[:, :, co] += full[::s, ::s][:oh, :ow]
+        assert np.abs(y - ref).max() < 1e-12, (H, W, k, s)
+    # --- crop_and_resize
+    H, W, c = 12, 9, 5
+    img = torch.randn((2, H, W, 3), generator=g, dtype=torch.float64)
+    boxes = torch.tensor([[0.1, 0.2, 0.8, 0.9], [0.0, 0.0, 1.0, 1.0], [-0.2, 0.3, 1.3, 0.6]], dtype=torch.float64)
+    ind = torch.tensor([0, 1, 1])
+    out = T.crop_and_resize(img, boxes, ind, (c, c)).numpy()
+    for b in range(3):
+        y1, x1, y2, x2 = boxes[b].tolist()
+        ys = y1 * (H - 1) + np.arange(c) * (y2 - y1) * (H - 1) / (c - 1)
+        xs = x1 * (W - 1) + np.arange(c) * (x2 - x1) * (W - 1) / (c - 1)
+        yy, xx = np.meshgrid(ys, xs, indexing="ij")
+        inside = (yy >= 0) & (yy <= H - 1) & (xx >= 0) & (xx <= W - 1)
+        for ch in range(3):
+            ref = ndimage.map_coordinates(img[int(ind[b]), :, :, ch].numpy(), [yy, xx], order=1, mode="nearest")
+            assert np.abs(out[b, :, :, ch] - np.where(inside, ref, 0.0)).max() < 1e-12, b
+    # --- sigmoid cross-entropy
+    z = torch.tensor([-30.0, -2.0, 0.0, 0.5, 40.0], dtype=torch.float64)
+    for lab in (0.0, 1.0):
+        with np.errstate(divide="ignore", invalid="ignore"):      # expit saturates at +-40: those entries are skipped
+            ref = -lab * np.log(special.expit(z.numpy())) - (1 - lab) * np.log1p(-special.expit(z.numpy()))
+        got = T.sigmoid_ce(z, torch.full_like(z, lab)).numpy()
+        ok = np.isfinite(ref)
+        assert np.allclose(got[ok], ref[ok], rtol=1e-10, atol=1e-12)
