@@ -3,6 +3,9 @@ flags tolerated (`parse_known_args`, config.py:96) so that run_market_*.sh comma
 Flags the reference parses but never reads (optimizer, gamma, lambda_k, L1Loss_weight, interpolate_*, ...)
 are accepted and likewise ignored."""
 import argparse
+import json
+import os
+from datetime import datetime
 
 
 def str2bool(v):
@@ -71,3 +74,35 @@ def get_config(argv=None):
     config, unparsed = build_parser().parse_known_args(argv)
     config.data_format = "NHWC"   # main.py:18 overrides config.py:97-101
     return config, unparsed
+
+
+def prepare_dirs(config):
+    """utils.prepare_dirs_and_logger (utils.py:110-141) minus the logging handler: `--load_path` inside `--log_dir` IS the
+    model directory, otherwise it names it (prefixed with the dataset unless it already starts with it); without it the
+    name is <dataset>_<MMDD_HHMMSS>.  An explicit `--model_dir` (what run_market_*.sh pass) wins.  Also sets
+    `config.data_path = <data_dir>/<dataset>` (utils.py:136) and creates the log / model directories."""
+    model_name = None
+    if config.load_path:
+        if config.load_path.startswith(config.log_dir):
+            config.model_dir = config.load_path
+        elif config.load_path.startswith(config.dataset):
+            model_name = config.load_path
+        else:
+            model_name = "%s_%s" % (config.dataset, config.load_path)
+    else:
+        model_name = "%s_%s" % (config.dataset, datetime.now().strftime("%m%d_%H%M%S"))
+    config.model_name = model_name
+    if getattr(config, "model_dir", None) is None:
+        config.model_dir = os.path.join(config.log_dir, model_name)
+    config.data_path = os.path.join(config.data_dir, config.dataset)
+    for path in (config.log_dir, config.model_dir):
+        os.makedirs(path, exist_ok=True)
+    return config
+
+
+def save_config(config):
+    """utils.save_config (utils.py:146-154): the parsed flags as <model_dir>/params.json."""
+    param_path = os.path.join(config.model_dir, "params.json")
+    with open(param_path, "w") as fp:
+        json.dump(config.__dict__, fp, indent=4, sort_keys=True)
+    return param_path

@@ -4,7 +4,7 @@ Implemented: --model=1 (Stage-I Market-1501, the BASELINE hot path), --model=2 /
 raise NotImplementedError naming the reference class they map to."""
 import os
 
-from .config import get_config
+from .config import get_config, prepare_dirs, save_config
 
 _MODEL_CLASSES = {
     1: "DPIG_Encoder_GAN_BodyROI_FgBg", 2: "DPIG_PoseRCV_AE_BodyROI", 3: "DPIG_Encoder_subSampleAppNetFgBg_GAN_BodyROI",
@@ -20,6 +20,7 @@ def main(config):
     from . import trainer as T
     from . import trainer_256 as T256
     from . import trainer_sub as TS
+    prepare_dirs(config)            # main.py:13 prepare_dirs_and_logger
     if config.gpu > -1:
         os.environ["CUDA_DEVICE_ORDER"] = "PCI_BUS_ID"
         os.environ["CUDA_VISIBLE_DEVICES"] = str(config.gpu)
@@ -41,4 +42,6 @@ def main(config):
 
 if __name__ == "__main__":
     cfg, _ = get_config()
+    prepare_dirs(cfg)
+    save_config(cfg)                # main.py:88-90
     main(cfg)

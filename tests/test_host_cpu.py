@@ -165,6 +165,27 @@ def test_step_size_and_overlap_slice_host_logic(monkeypatch):
     assert not engine.Stage1Engine(NoDeviceCtx(), cfg, 2, mode="dcgan", dist=FakeDist(), device="cpu").overlap_comm
 
 
+def test_prepare_dirs_and_save_config_follow_the_reference(tmp_path):
+    """utils.prepare_dirs_and_logger / save_config (utils.py:110-154): model directory naming and params.json."""
+    import json
+    from dpig_b200 import config as C
+    log = str(tmp_path / "logs")
+    cfg, _ = C.get_config(["--dataset=Market_train_data", "--log_dir=%s" % log, "--data_dir=%s" % (tmp_path / "data")])
+    C.prepare_dirs(cfg)
+    assert re.fullmatch(r"Market_train_data_\d{4}_\d{6}", cfg.model_name) and cfg.model_dir == os.path.join(log, cfg.model_name)
+    assert cfg.data_path == os.path.join(str(tmp_path / "data"), "Market_train_data") and os.path.isdir(cfg.model_dir)
+    cfg, _ = C.get_config(["--dataset=Market_train_data", "--log_dir=%s" % log, "--load_path=run7"])
+    assert C.prepare_dirs(cfg).model_dir == os.path.join(log, "Market_train_data_run7")
+    cfg, _ = C.get_config(["--dataset=Market_train_data", "--log_dir=%s" % log, "--load_path=Market_train_data_x"])
+    assert C.prepare_dirs(cfg).model_dir == os.path.join(log, "Market_train_data_x")
+    cfg, _ = C.get_config(["--dataset=Market_train_data", "--log_dir=%s" % log, "--load_path=%s/abc" % log])
+    assert C.prepare_dirs(cfg).model_dir == "%s/abc" % log
+    cfg, _ = C.get_config(["--dataset=D", "--log_dir=%s" % log, "--model_dir=%s" % (tmp_path / "explicit"), "--model=13"])
+    assert C.prepare_dirs(cfg).model_dir == str(tmp_path / "explicit")           # run_market_*.sh pass --model_dir
+    params = json.load(open(C.save_config(cfg)))
+    assert params["model"] == 13 and params["data_format"] == "NHWC" and params["model_dir"] == cfg.model_dir
+
+
 def test_synthetic_batch_shapes_and_box_rule():
     from dpig_b200 import synth
     b = synth.make_batch(3, 128, 64, seed=7)
