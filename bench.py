@@ -292,6 +292,8 @@ def main():
                 "parity mode issues %d bf16 MMA passes per product, so executed tensor FLOPs = %dx algorithmic "
                 "(attainable frac <= 1/%d)" % (passes, passes, passes),
         "mma_passes": passes, "frac_executed": passes * ach / peaks["bf16_tflops"],
+        "timing": "per-launch CUDA events on the launching stream in one extra iteration replayed launch by launch right "
+                  "after the timed regions (the timed steps themselves are whole-step CUDA graph replays on one GPU)",
         "launches_per_iteration": conv_n, "share_of_iteration": conv_ms / iter_ms if iter_ms else None,
         "wgrad_kernel": {"achieved": (wg[1] / (wg[2] * 1e-3) / 1e12) if wg[2] > 0 else 0.0, "unit": "TFLOP/s",
                          "launches_per_iteration": wg[0], "share_of_iteration": wg[2] / iter_ms if iter_ms else None},
