@@ -1,7 +1,8 @@
 """Entry point mirroring the reference's main.py:12-90: `--model` id -> trainer class, `--is_train` -> train()/test().
 Implemented: --model=1 (Stage-I Market-1501, the BASELINE hot path), --model=2 / 3 / 4 (trainer_sub.py), 11 / 12 / 13 and
-1001 (tester.py), 101 (Stage-I DeepFashion 256x256); the other ids (102-104, 1002: the DeepFashion sub-network stages)
-raise NotImplementedError naming the reference class they map to."""
+1001 (tester.py), 101 / 102 (trainer_256.py: Stage-I DeepFashion 256x256 and its pose auto-encoder stage); the other ids
+(103, 104, 1002: the DeepFashion samplers on the BodyROI encoder) raise NotImplementedError naming the reference class
+they map to."""
 import os
 
 from .config import get_config, prepare_dirs, save_config

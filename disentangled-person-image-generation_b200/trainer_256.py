@@ -10,6 +10,7 @@ MODE is hard-wired to 'dcgan' (trainer_256.py:28).
 """
 from . import engine
 from .trainer import DPIG_Encoder_GAN_BodyROI_FgBg
+from .trainer_sub import DPIG_PoseRCV_AE_BodyROI
 
 
 class DPIG_Encoder_GAN_BodyROI_256(DPIG_Encoder_GAN_BodyROI_FgBg):
@@ -20,3 +21,10 @@ class DPIG_Encoder_GAN_BodyROI_256(DPIG_Encoder_GAN_BodyROI_FgBg):
     def _net_config(self):
         return engine.NetConfig.deepfashion(img_h=self.img_H, img_w=self.img_W, hidden=self.conv_hidden_num,
                                             z_num=self.z_num)
+
+
+class DPIG_PoseRCV_AE_BodyROI_256(DPIG_PoseRCV_AE_BodyROI):
+    """--model=102 (trainer_256.py:404-509): the pose auto-encoder stage on DeepFashion keypoints.  The graph and the
+    step are those of --model=2 (trainer.py:626-708; the two build_model / train bodies differ only in commented-out
+    preview code): PoseEncoderFCRes -> PoseDecoderFCRes on (r / img_H, c / img_W, v) normalised to [-1, 1] with the
+    256 x 256 image size of the flags, loss mean((pose - G_pose)^2) * 20, Adam(beta1 = .5) on the PoseAE variables."""
