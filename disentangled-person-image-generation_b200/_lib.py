@@ -33,7 +33,8 @@ class ConvEpilogue(C.Structure):
                 ("addend", C.POINTER(Tensor)), ("mask_in", C.c_void_p), ("mask_neg", C.c_float),
                 ("mask_out", C.c_void_p), ("out", C.POINTER(Tensor)), ("out_masked", C.POINTER(Tensor)),
                 ("out_f32", C.c_void_p), ("out_f32_pix_stride", C.c_int64), ("upsample", C.c_int32),
-                ("class_bias", C.c_void_p), ("colsum_masked", C.c_void_p)]
+                ("class_bias", C.c_void_p), ("colsum_masked", C.c_void_p), ("stat_sums", C.c_void_p),
+                ("stat_mode", C.c_int32)]
 
 
 _P = C.c_void_p

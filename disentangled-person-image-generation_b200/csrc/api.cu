@@ -66,6 +66,7 @@ extern "C" int dpig_ctx_create(int device, dpig_ctx** out) {
   if (const char* e = getenv("DPIG_EPI_BUFS")) ctx->epi_bufs = atoi(e);
   if (const char* e = getenv("DPIG_TUNE_SMALL")) ctx->tune_small = atoi(e);
   if (const char* e = getenv("DPIG_ADD_PREFETCH")) ctx->add_prefetch = atoi(e) != 0;
+  if (const char* e = getenv("DPIG_CROP_GATHER")) ctx->crop_gather = atoi(e) != 0;
   *out = ctx;
   return DPIG_OK;
 }

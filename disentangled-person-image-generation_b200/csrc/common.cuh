@@ -29,6 +29,7 @@ struct dpig_ctx {
   bool wgrad_pair = true;    // filter-gradient kernel as 2-CTA clusters (cta_group::2) where the shape allows (DPIG_WGRAD_PAIR=0: never)
   int wgrad_group = 0;     // filter taps per wgrad CTA: 0 = default (1); DPIG_WGRAD_GROUP
   int wgrad_px = 0;        // pixels per wgrad pipeline step: 0 = auto, 32 / 64 forced; DPIG_WGRAD_PX
+  bool crop_gather = true;  // crop_and_resize image gradient in gather form (DPIG_CROP_GATHER=0: atomic scatter)
   int max_stages = 0;      // >= 2: cap on the conv smem pipeline depth (DPIG_CONV_STAGES, tuning experiments)
   unsigned long long launches = 0;
 };

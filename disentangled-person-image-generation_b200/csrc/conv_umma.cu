@@ -85,6 +85,10 @@ struct ConvUmmaParams {
   int mask_in_words;
   float mask_neg;
   float* colsum;  // [cout] += column sums (over pixels) of the masked output: the bias gradient of the layer below
+  // raw normalisation sums of pre = acc + bias (dpig_conv_epilogue::stat_sums): [2][stat_groups] fp64, per output channel
+  // (stat_mode DPIG_NORM_BATCH) or per image (DPIG_NORM_LAYER)
+  double* stat_sums;
+  int stat_mode, stat_groups;
   // TMA tensor-store maps of the split-bf16 outputs, [index][plane hi / lo]; index = parity class of a merged stride-2
   // data gradient, or 2x2 replica of the fused upsample, else 0.  Box {32 channels, BW, BH, BN}, SWIZZLE_64B.
   CUtensorMap out_map[4][2];
@@ -229,6 +233,23 @@ __device__ __forceinline__ void epi_gather_rows(uint32_t st, const __nv_bfloat16
   }
 }
 
+// Column sums over the warp's 32 rows (lane = row, f = the row's 32 channels), transposed: lane l returns the total of
+// channel l.  31 shuffles: after step `off` every lane keeps the half of its values whose channel index has bit `off`
+// equal to its lane-id bit.  Destroys f.
+__device__ __forceinline__ float warp_colsum32(float (&f)[32], int lane) {
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) {
+    const bool upper = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < off; ++i) {
+      const float send = upper ? f[i] : f[i + off];
+      const float recv = __shfl_xor_sync(0xffffffffu, send, off);
+      f[i] = (upper ? f[i + off] : f[i]) + recv;
+    }
+  }
+  return f[0];
+}
+
 // What an epilogue warp knows about the tile it is draining.
 struct EpiTile {
   int w0, h0, n0;     // origin of the pixel box in the (class) output grid = TMA store coordinates
@@ -245,7 +266,7 @@ struct EpiTile {
 // together.  colsum: lane l's running total of channel cbase + l of the masked output (see the flush in the kernel).
 __device__ __forceinline__ void epi_chunk(const ConvUmmaParams& p, EpiTile& t, uint32_t st0,
                                           const uint32_t (&v)[32], int cbase, bool valid, int lpix, int ppix,
-                                          const float* cbias, int lane, float& colsum) {
+                                          const float* cbias, int lane, float& colsum, float& sqsum) {
   const int nvalid = min(32, p.cout - cbase);
   if (nvalid <= 0) return;  // uniform over the warp set
   const bool full32 = (nvalid == 32);
@@ -446,17 +467,33 @@ __device__ __forceinline__ void epi_chunk(const ConvUmmaParams& p, EpiTile& t, u
 #pragma unroll
         for (int i = 0; i < 32; ++i) f[i] = 0.f;
       }
+      colsum += warp_colsum32(f, lane);
+    }
+  }
+  // ---- raw normalisation sums of pre = acc + bias (act = none, no addend: f still holds pre).  Runs last, while the
+  // stores above drain.  Batch mode: per-channel totals of the warp's 32 rows (lane l = channel cbase + l);
+  // layer mode: this row's totals over the chunk's channels (the caller reduces rows of one image).
+  if (p.stat_sums) {
+    if (!valid) {
 #pragma unroll
-      for (int off = 16; off >= 1; off >>= 1) {
-        const bool upper = (lane & off) != 0;
+      for (int i = 0; i < 32; ++i) f[i] = 0.f;
+    }
+    if (p.stat_mode == DPIG_NORM_BATCH) {
+      float q[32];
 #pragma unroll
-        for (int i = 0; i < off; ++i) {
-          const float send = upper ? f[i] : f[i + off];
-          const float recv = __shfl_xor_sync(0xffffffffu, send, off);
-          f[i] = (upper ? f[i + off] : f[i]) + recv;
+      for (int i = 0; i < 32; ++i) q[i] = f[i] * f[i];
+      sqsum += warp_colsum32(q, lane);
+      colsum += warp_colsum32(f, lane);
+    } else {
+      float a = 0.f, b = 0.f;
+#pragma unroll
+      for (int i = 0; i < 32; ++i)
+        if (i < nvalid) {
+          a += f[i];
+          b = fmaf(f[i], f[i], b);
         }
-      }
-      colsum += f[0];
+      colsum += a;
+      sqsum += b;
     }
   }
 }
@@ -679,17 +716,31 @@ conv_umma_kernel(const __grid_constant__ ConvUmmaParams p) {
     // when the block changes / at the end.  One atomic per chunk and 32 pixel rows (the first version) put
     // pixels/32 same-address fp32 atomics on every channel: ~1.3 clk each at the L2, 0.6 ms on a 1 M-pixel layer --
     // it made every short-K data gradient (stride-2 parity classes, 1x1) atomic-bound instead of tensor-bound.
+    // The per-channel normalisation sums of a batch-norm conv (stat_sums, never together with colsum) use the same
+    // registers plus four for the squares; they reach memory as fp64 atomics, one per channel, warp and channel block.
     float cs0 = 0.f, cs1 = 0.f, cs2 = 0.f, cs3 = 0.f;
+    float qs0 = 0.f, qs1 = 0.f, qs2 = 0.f, qs3 = 0.f;
     int cs_nt = -1;
+    const bool stat_batch = p.stat_sums != nullptr && p.stat_mode == DPIG_NORM_BATCH;
+    const bool stat_layer = p.stat_sums != nullptr && p.stat_mode != DPIG_NORM_BATCH;
     auto flush_colsum = [&]() {
-      if (p.colsum == nullptr || cs_nt < 0) return;
+      if ((p.colsum == nullptr && !stat_batch) || cs_nt < 0) return;
       const float cs[4] = {cs0, cs1, cs2, cs3};
+      const float qs[4] = {qs0, qs1, qs2, qs3};
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         const int c = cs_nt * p.block_n + ((cpar + k * (kEpiWarps / 4)) << 5) + lane;
-        if (cpar + k * (kEpiWarps / 4) < (p.block_n >> 5) && c < p.cout) atomicAdd(p.colsum + c, cs[k]);
+        if (cpar + k * (kEpiWarps / 4) < (p.block_n >> 5) && c < p.cout) {
+          if (stat_batch) {
+            atomicAdd(p.stat_sums + c, static_cast<double>(cs[k]));
+            atomicAdd(p.stat_sums + p.stat_groups + c, static_cast<double>(qs[k]));
+          } else {
+            atomicAdd(p.colsum + c, cs[k]);
+          }
+        }
       }
       cs0 = cs1 = cs2 = cs3 = 0.f;
+      qs0 = qs1 = qs2 = qs3 = 0.f;
     };
     int j = 0;
     for (int tile = unit0; tile < total_tiles; tile += unit_step)
@@ -759,13 +810,44 @@ conv_umma_kernel(const __grid_constant__ ConvUmmaParams p) {
           }
           released = true;
         }
-        float csum = 0.f;
-        epi_chunk(p, et, st, v, nt * p.block_n + c0, valid, lpix, ppix, cbias, lane, csum);
-        const int k = (ci - cpar) / (kEpiWarps / 4);   // this warp's k-th chunk of the block
-        cs0 += k == 0 ? csum : 0.f;
-        cs1 += k == 1 ? csum : 0.f;
-        cs2 += k == 2 ? csum : 0.f;
-        cs3 += k == 3 ? csum : 0.f;
+        float csum = 0.f, qsum = 0.f;
+        epi_chunk(p, et, st, v, nt * p.block_n + c0, valid, lpix, ppix, cbias, lane, csum, qsum);
+        if (stat_layer) {   // this row's sums over the chunk's channels: collected per tile (cs0 / qs0), flushed below
+          cs0 += csum;
+          qs0 += qsum;
+        } else {
+          const int k = (ci - cpar) / (kEpiWarps / 4);   // this warp's k-th chunk of the block
+          cs0 += k == 0 ? csum : 0.f;
+          cs1 += k == 1 ? csum : 0.f;
+          cs2 += k == 2 ? csum : 0.f;
+          cs3 += k == 3 ? csum : 0.f;
+          qs0 += k == 0 ? qsum : 0.f;
+          qs1 += k == 1 ? qsum : 0.f;
+          qs2 += k == 2 ? qsum : 0.f;
+          qs3 += k == 3 ? qsum : 0.f;
+        }
+      }
+      if (stat_layer) {
+        // per-sample sums: rows of one image reduce inside the warp when the whole warp sits in one image (the usual
+        // case: >= 32 pixels per image and tile), else every row adds its own share
+        const int n_first = __shfl_sync(0xffffffffu, n, 0);
+        const bool uniform = __all_sync(0xffffffffu, !valid || n == n_first) && __shfl_sync(0xffffffffu, static_cast<int>(valid), 0);
+        if (uniform) {
+          float a = cs0, b = qs0;
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) {
+            a += __shfl_xor_sync(0xffffffffu, a, o);
+            b += __shfl_xor_sync(0xffffffffu, b, o);
+          }
+          if (lane == 0) {
+            atomicAdd(p.stat_sums + n_first, static_cast<double>(a));
+            atomicAdd(p.stat_sums + p.stat_groups + n_first, static_cast<double>(b));
+          }
+        } else if (valid) {
+          atomicAdd(p.stat_sums + n, static_cast<double>(cs0));
+          atomicAdd(p.stat_sums + p.stat_groups + n, static_cast<double>(qs0));
+        }
+        cs0 = qs0 = 0.f;
       }
       if (!released) {  // fewer chunks than epilogue warps per lane group (block_n == 32)
         ptx::tc_fence_before();
@@ -1351,6 +1433,15 @@ static int fill_epilogue(dpig_ctx* ctx, ConvUmmaParams& P, const dpig_conv_epilo
   P.colsum = ep->colsum_masked;
   if (ep->colsum_masked && !ep->out_masked)
     return set_error(ctx, DPIG_EINVAL, "colsum_masked needs out_masked");
+  P.stat_sums = ep->stat_sums;
+  P.stat_mode = ep->stat_mode;
+  P.stat_groups = ep->stat_mode == DPIG_NORM_BATCH ? cout : n;
+  if (ep->stat_sums) {
+    if (ep->stat_mode != DPIG_NORM_BATCH && ep->stat_mode != DPIG_NORM_LAYER)
+      return set_error(ctx, DPIG_EUNSUPPORTED, "stat_sums: batch (per channel) or layer (per sample) statistics only");
+    if (ep->act != DPIG_ACT_NONE || ep->addend || ep->out_masked || ep->colsum_masked || g.rep != 1 || P.nclass != 1)
+      return set_error(ctx, DPIG_EINVAL, "stat_sums needs a plain conv epilogue (act none, no addend / out_masked / upsample)");
+  }
   if (g.rep != 1 && (ep->addend || ep->out_masked))
     return set_error(ctx, DPIG_EUNSUPPORTED, "upsampling epilogue cannot take addend/out_masked");
   return DPIG_OK;
@@ -1390,6 +1481,7 @@ static int launch_conv(dpig_ctx* ctx, ConvUmmaParams& P, cudaStream_t stream) {
   const int n_tiles = (P.cout + P.block_n - 1) / P.block_n;
   P.tmem_cols = 64;
   while (static_cast<int>(P.tmem_cols) < (P.wide_b ? 4 : 2) * P.block_n) P.tmem_cols <<= 1;
+  if (P.stat_sums) cudaMemsetAsync(P.stat_sums, 0, sizeof(double) * 2 * P.stat_groups, stream);
   ctx->launches++;
   if (P.pair) {
     const int units = ((pix_tiles + 1) / 2) * n_tiles;

@@ -137,6 +137,115 @@ __global__ void crop_resize_bwd_kernel(const __nv_bfloat16* ghi, const __nv_bflo
   }
 }
 
+// Gather form of the image gradient: thread = (image pixel, 8 channels) sums every crop sample whose bilinear footprint
+// covers the pixel -- no atomics (the scatter form above issues 4 fp32 atomics per gradient element and ran at 10 % of
+// the HBM roofline), no zero fill of the 0.27 GB gradient image, a fixed summation order (boxes ascending, crop rows,
+// crop columns), one 32-byte store per thread.
+//   The sample position of crop row y is in_y(y) = a + y*hs (sample_coords); it touches image rows floor(in_y) with weight
+//   1 - frac and ceil(in_y) with weight frac.  The candidate rows for image row Y are those with in_y in (Y-1, Y+1): the
+//   range is bracketed from the affine map (one row of slack) and every candidate re-evaluates in_y with the forward
+//   kernel's expression, so both directions agree on floor / ceil bit for bit.
+// A block serves one image; its boxes (box_ind[b] == n) are compacted in ascending order into shared memory, kCropListCap
+// at a time.
+constexpr int kCropListCap = 256;
+
+__device__ __forceinline__ void cand_range(float a, float hs, int crop, int Y, int& lo, int& hi) {
+  if (crop <= 1) {
+    lo = hi = 0;
+    return;
+  }
+  if (hs == 0.f) {
+    lo = 0;
+    hi = crop - 1;
+    return;
+  }
+  float t0 = (static_cast<float>(Y) - 1.f - a) / hs, t1 = (static_cast<float>(Y) + 1.f - a) / hs;
+  if (t0 > t1) {
+    const float t = t0;
+    t0 = t1;
+    t1 = t;
+  }
+  t0 = fminf(fmaxf(floorf(t0) - 1.f, 0.f), static_cast<float>(crop));       // clamp before the int conversion
+  t1 = fminf(fmaxf(ceilf(t1) + 1.f, -1.f), static_cast<float>(crop - 1));
+  lo = static_cast<int>(t0);
+  hi = static_cast<int>(t1);
+}
+
+__global__ void __launch_bounds__(256)
+crop_resize_bwd_gather_kernel(const __nv_bfloat16* ghi, const __nv_bfloat16* glo, long long gps, const float* mask,
+                              const float* boxes, const int* box_ind, int nbox, CropGeom g, float* gimg) {
+  __shared__ int s_list[kCropListCap];
+  __shared__ int s_cnt, s_next;
+  const int n = blockIdx.y;
+  const int C8 = g.C / 8;
+  const long long item = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;   // (pixel of image n, channel group)
+  const bool live = item < static_cast<long long>(g.H) * g.W * C8;
+  const int c = static_cast<int>(item % C8) * 8;
+  const int pin = static_cast<int>(item / C8);
+  const int X = pin % g.W, Y = pin / g.W;
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  int scanned = 0;
+  while (scanned < nbox) {
+    if (threadIdx.x < 32) {   // ordered compaction of this image's boxes, 32 candidates per round
+      int cnt = 0, b0 = scanned;
+      for (; b0 < nbox; b0 += 32) {
+        const int b = b0 + threadIdx.x;
+        const bool hit = b < nbox && box_ind[b] == n;
+        const unsigned m = __ballot_sync(0xffffffffu, hit);
+        const int k = __popc(m);
+        if (cnt + k > kCropListCap) break;
+        if (hit) s_list[cnt + __popc(m & ((1u << threadIdx.x) - 1u))] = b;
+        cnt += k;
+      }
+      if (threadIdx.x == 0) {
+        s_cnt = cnt;
+        s_next = b0 < nbox ? b0 : nbox;
+      }
+    }
+    __syncthreads();
+    const int cnt = s_cnt;
+    scanned = s_next;
+    if (live) {
+      for (int k = 0; k < cnt; ++k) {
+        const int b = s_list[k];
+        const float* box = boxes + 4 * b;
+        const float y1 = box[0], x1 = box[1], y2 = box[2], x2 = box[3];
+        const float hs = (g.CH > 1) ? (y2 - y1) * (g.H - 1) / (g.CH - 1) : 0.f;
+        const float ws = (g.CW > 1) ? (x2 - x1) * (g.W - 1) / (g.CW - 1) : 0.f;
+        int ylo, yhi, xlo, xhi;
+        cand_range((g.CH > 1) ? y1 * (g.H - 1) : 0.5f * (y1 + y2) * (g.H - 1), hs, g.CH, Y, ylo, yhi);
+        cand_range((g.CW > 1) ? x1 * (g.W - 1) : 0.5f * (x1 + x2) * (g.W - 1), ws, g.CW, X, xlo, xhi);
+        for (int y = ylo; y <= yhi; ++y) {
+          const float in_y = (g.CH > 1) ? y1 * (g.H - 1) + y * hs : 0.5f * (y1 + y2) * (g.H - 1);
+          if (in_y < 0.f || in_y > g.H - 1) continue;
+          const int t = static_cast<int>(floorf(in_y)), bo = static_cast<int>(ceilf(in_y));
+          if (t != Y && bo != Y) continue;
+          const float yl = in_y - t;
+          const float wy = (t == Y ? 1.f - yl : 0.f) + (bo == Y ? yl : 0.f);
+          for (int x = xlo; x <= xhi; ++x) {
+            const float in_x = (g.CW > 1) ? x1 * (g.W - 1) + x * ws : 0.5f * (x1 + x2) * (g.W - 1);
+            if (in_x < 0.f || in_x > g.W - 1) continue;
+            const int l = static_cast<int>(floorf(in_x)), r = static_cast<int>(ceilf(in_x));
+            if (l != X && r != X) continue;
+            const float xl = in_x - l;
+            const float wx = (l == X ? 1.f - xl : 0.f) + (r == X ? xl : 0.f);
+            const long long opix = (static_cast<long long>(b) * g.CH + y) * g.CW + x;
+            ld8_split(ghi, glo, opix * gps + c, 1.f, wy * wx, acc);
+          }
+        }
+      }
+    }
+    __syncthreads();
+  }
+  if (live) {
+    const long long pix = static_cast<long long>(n) * g.H * g.W + pin;
+    const float m = mask ? mask[pix] : 1.f;
+    float4* o = reinterpret_cast<float4*>(gimg + pix * g.C + c);
+    o[0] = make_float4(acc[0] * m, acc[1] * m, acc[2] * m, acc[3] * m);
+    o[1] = make_float4(acc[4] * m, acc[5] * m, acc[6] * m, acc[7] * m);
+  }
+}
+
 }  // namespace dpig
 using namespace dpig;
 
@@ -168,6 +277,17 @@ extern "C" int dpig_crop_and_resize_bwd(dpig_ctx* ctx, const dpig_tensor* grad, 
   if (!grad || !boxes || !box_ind || !grad_image || grad->n != nbox || grad->c != c)
     return set_error(ctx, DPIG_EINVAL, "crop_and_resize_bwd: bad argument");
   CropGeom g{n, h, w_, c, grad->h, grad->w};
+  if (ctx->crop_gather && c % 8 == 0 && grad->pix_stride % 8 == 0 && reinterpret_cast<uintptr_t>(grad_image) % 16 == 0 &&
+      n <= 65535) {
+    // gather form: grad_image is overwritten (the zero fill the scatter form needs is harmless but not required)
+    const long long items = static_cast<long long>(h) * w_ * (c / 8);
+    dim3 grid2(static_cast<unsigned>((items + 255) / 256), n);
+    crop_resize_bwd_gather_kernel<<<grid2, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const __nv_bfloat16*>(grad->hi), static_cast<const __nv_bfloat16*>(grad->lo), grad->pix_stride, mask,
+        boxes, box_ind, nbox, g, grad_image);
+    ctx->launches++;
+    return check_launch(ctx, "crop_resize_bwd_gather");
+  }
   const long long total = static_cast<long long>(nbox) * g.CH * g.CW * g.C;
   long long grid = (total + 255) / 256;
   if (grid > 148 * 32) grid = 148 * 32;

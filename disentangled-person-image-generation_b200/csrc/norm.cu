@@ -71,11 +71,33 @@ __global__ void norm_finalize_kernel(const double* sums, int groups, double coun
   stats[groups + g] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
 }
 
-// thread = (pixel, 32-channel word)
+// thread = (pixel, 32-channel word).  kFused: (mean, rstd) of every group are derived from the raw fp64 sums by each
+// block into shared memory (<= kMaxFusedGroups groups: 2 fp64 divisions + a square root per group and block), block 0
+// also writes them to `stats` for the backward pass -- one launch instead of finalize + apply.
+constexpr int kMaxFusedGroups = 2048;
+template <bool kFused>
 __global__ void norm_act_fwd_kernel(const float* x, int N, long long ppi, int C, int mode, int groups,
-                                    const float* stats, const float* scale, const float* offset, int act,
-                                    float alpha, __nv_bfloat16* ohi, __nv_bfloat16* olo, long long ops,
-                                    uint32_t* mask_out) {
+                                    const double* sums, double count, float eps, float* stats, const float* scale,
+                                    const float* offset, int act, float alpha, __nv_bfloat16* ohi,
+                                    __nv_bfloat16* olo, long long ops, uint32_t* mask_out) {
+  extern __shared__ float s_stats[];   // kFused: [2][groups]
+  const float* st = stats;
+  if (kFused) {
+    for (int g = threadIdx.x; g < groups; g += blockDim.x) {
+      const double mean = sums[g] / count;
+      double var = sums[groups + g] / count - mean * mean;
+      if (var < 0) var = 0;
+      const float m = static_cast<float>(mean), r = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+      s_stats[g] = m;
+      s_stats[groups + g] = r;
+      if (blockIdx.x == 0) {
+        stats[g] = m;
+        stats[groups + g] = r;
+      }
+    }
+    __syncthreads();
+    st = s_stats;
+  }
   const int words = C / 32;
   const long long total = static_cast<long long>(N) * ppi * words;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
@@ -84,18 +106,43 @@ __global__ void norm_act_fwd_kernel(const float* x, int N, long long ppi, int C,
     const long long pix = i / words;
     const int n = static_cast<int>(pix / ppi);
     uint32_t bits = 0;
-#pragma unroll 4
-    for (int j = 0; j < 32; ++j) {
-      const int c = wd * 32 + j;
-      const int g = group_of(mode, n, c, C);
-      float v = (x[pix * C + c] - stats[g]) * stats[groups + g] * scale[c] + offset[c];
-      if (v > 0.f) bits |= 1u << j;
-      if (act == DPIG_ACT_RELU) v = fmaxf(v, 0.f);
-      else if (act == DPIG_ACT_LRELU) v = v > 0.f ? v : alpha * v;
-      __nv_bfloat16 h, l;
-      split_bf16(v, h, l);
-      ohi[pix * ops + c] = h;
-      if (olo) olo[pix * ops + c] = l;
+    const float4* x4 = reinterpret_cast<const float4*>(x + pix * C + wd * 32);
+    uint4* oh4 = reinterpret_cast<uint4*>(ohi + pix * ops + wd * 32);
+    uint4* ol4 = olo ? reinterpret_cast<uint4*>(olo + pix * ops + wd * 32) : nullptr;
+    const bool vec = (ops % 8 == 0);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {     // 8 channels per round: two 16-byte loads, one 16-byte store per plane
+      const float4 a = __ldg(x4 + 2 * q), b = __ldg(x4 + 2 * q + 1);
+      const float in[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+      uint32_t hw[4], lw[4];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const int j = q * 8 + e;
+        const int c = wd * 32 + j;
+        const int g = group_of(mode, n, c, C);
+        float v = (in[e] - st[g]) * st[groups + g] * __ldg(scale + c) + __ldg(offset + c);
+        if (v > 0.f) bits |= 1u << j;
+        if (act == DPIG_ACT_RELU) v = fmaxf(v, 0.f);
+        else if (act == DPIG_ACT_LRELU) v = v > 0.f ? v : alpha * v;
+        __nv_bfloat16 h, l;
+        split_bf16(v, h, l);
+        if (vec) {
+          if (e & 1) {
+            hw[e >> 1] |= static_cast<uint32_t>(__bfloat16_as_ushort(h)) << 16;
+            lw[e >> 1] |= static_cast<uint32_t>(__bfloat16_as_ushort(l)) << 16;
+          } else {
+            hw[e >> 1] = __bfloat16_as_ushort(h);
+            lw[e >> 1] = __bfloat16_as_ushort(l);
+          }
+        } else {
+          ohi[pix * ops + c] = h;
+          if (olo) olo[pix * ops + c] = l;
+        }
+      }
+      if (vec) {
+        oh4[q] = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+        if (ol4) ol4[q] = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+      }
     }
     if (mask_out) mask_out[pix * words + wd] = bits;
   }
@@ -225,14 +272,23 @@ extern "C" int dpig_norm_act_fwd(dpig_ctx* ctx, const float* x, int32_t n, int32
     return set_error(ctx, DPIG_EINVAL, "norm_act_fwd: bad argument (c must be a multiple of 32)");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const int groups = groups_of(mode, n, c);
-  norm_finalize_kernel<<<(groups + 127) / 128, 128, 0, s>>>(sums, groups, count, eps, stats);
   const long long ppi = static_cast<long long>(h) * w_;
   const long long total = static_cast<long long>(n) * ppi * (c / 32);
   long long grid = (total + 127) / 128;
-  if (grid > 148 * 32) grid = 148 * 32;
-  norm_act_fwd_kernel<<<static_cast<int>(grid), 128, 0, s>>>(
-      x, n, ppi, c, mode, groups, stats, scale, offset, act, alpha, static_cast<__nv_bfloat16*>(out->hi),
-      static_cast<__nv_bfloat16*>(out->lo), out->pix_stride, mask_out);
+  if (grid > 148 * 16) grid = 148 * 16;
+  if (reinterpret_cast<uintptr_t>(out->hi) % 16 || (out->lo && reinterpret_cast<uintptr_t>(out->lo) % 16))
+    return set_error(ctx, DPIG_EINVAL, "norm_act_fwd: output planes must be 16-byte aligned");
+  if (groups <= kMaxFusedGroups) {
+    norm_act_fwd_kernel<true><<<static_cast<int>(grid), 128, sizeof(float) * 2 * groups, s>>>(
+        x, n, ppi, c, mode, groups, sums, count, eps, stats, scale, offset, act, alpha,
+        static_cast<__nv_bfloat16*>(out->hi), static_cast<__nv_bfloat16*>(out->lo), out->pix_stride, mask_out);
+    ctx->launches += 1;
+    return check_launch(ctx, "norm_act_fwd");
+  }
+  norm_finalize_kernel<<<(groups + 127) / 128, 128, 0, s>>>(sums, groups, count, eps, stats);
+  norm_act_fwd_kernel<false><<<static_cast<int>(grid), 128, 0, s>>>(
+      x, n, ppi, c, mode, groups, sums, count, eps, stats, scale, offset, act, alpha,
+      static_cast<__nv_bfloat16*>(out->hi), static_cast<__nv_bfloat16*>(out->lo), out->pix_stride, mask_out);
   ctx->launches += 2;
   return check_launch(ctx, "norm_act_fwd");
 }

@@ -123,14 +123,14 @@ class PatchLayer:
     layer by conv_fwd / conv_wgrad: `master` is the fp32 [cin][cout] matrix the bf16 operand copy is packed from --
     for a cin = 3 layer the HWIO filter itself ([k*k*3][cout]), for the cout = 3 layer a re-laid copy."""
 
-    def __init__(self, base, cin, cout, device, master=None, cout_launch=None):
+    def __init__(self, base, cin, cout, device, master=None, cout_launch=None, cin_pad=None):
         self.base, self.group, self.wname, self.bname = base, base.group, base.wname, base.bname
         self.k, self.stride, self.cin, self.rows = 1, 1, cin, cout
         # cout_launch > cout: the conv is launched with zero-padded output columns so that its epilogue takes the
         # whole-32-channel (coalesced) path; the extra weight rows stay zero
         self.cout = cout_launch or cout
         self.flops_cout = cout
-        self.cin_pad, self.cout_pad = _pad8(cin), _pad8(self.cout)
+        self.cin_pad, self.cout_pad = cin_pad or _pad8(cin), _pad8(self.cout)
         self.small, self.bwd = False, None
         self.fwd = torch.zeros((2, 1, self.cout, self.cin_pad), dtype=torch.bfloat16, device=device)
         self.master = master        # None: base.w
@@ -445,12 +445,7 @@ class Stage1Engine:
                 # stem shortcut: the 352 embedding rows never reach the tensor cores (dpig_stem_class_bias);
                 # the packed operand holds the 18 pose rows only
                 lay = ConvLayer(self.gp, name + "/weights", name + "/biases", 3, 1, self.gin_c, hn, dev, False, True)
-                lay.small = False
-                lay.cin_pad = self.pose_cpad
-                lay.fwd = torch.zeros((2, 9, hn, self.pose_cpad), dtype=torch.bfloat16, device=dev)
-                lay.bwd = None
-                lay.stem = True
-                lay.flops_cin = cfg.keypoints   # executed work; the reference's algorithmic count has 370 channels
+                lay.stem = True                 # no packed copies of its own: the pose rows run in patch form (below)
                 self.conv[name] = lay
                 continue
             if name.startswith("Discriminator"):
@@ -468,6 +463,14 @@ class Stage1Engine:
         self.gout_dwv = torch.zeros((go.cin, 27), device=dev)     # filter gradient in the forward layout
         self.gout_f = PatchLayer(go, go.cin, 27, dev, master=self.gout_wf, cout_launch=32)
         self.gout_d = PatchLayer(go, 27, go.cin, dev, master=self.gout_wd)
+        # pose rows of the U-Net stem (18 of its 370 input channels; the 352 embedding rows are the class-bias shortcut):
+        # as a 3x3 conv every filter tap spent a whole 64-deep K chunk on 18 channels (45 TFLOP/s); with the 9 taps folded
+        # into the channel dimension it is a 1x1 contraction over K = 9*18 = 162 (3 chunks instead of 9) and its filter
+        # gradient one M = 2x128-row GEMM instead of nine
+        kp = 9 * cfg.keypoints
+        self.stem_wp = torch.zeros((kp, hn), device=dev)       # [tap*18 + c][co] = W[tap][352 + c][co]
+        self.stem_dwp = torch.zeros((kp, hn), device=dev)
+        self.stem_patch = PatchLayer(self.conv[self.n_gstem], kp, hn, dev, master=self.stem_wp, cin_pad=(kp + 63) // 64 * 64)
         # BN / LN scale defaults to one
         for i in (2, 3, 4):
             self.dp.view("Discriminator.BN%d.scale" % i).fill_(1.0)
@@ -558,9 +561,6 @@ class Stage1Engine:
             if layer.small or (name.startswith("Discriminator") != (which == "d")):
                 continue
             if getattr(layer, "stem", False):
-                e = self.cfg.emb_dim
-                self.ctx.weight_pack_rows(ptr(layer.w), 9, layer.cin, e, layer.cin - e, layer.cout, layer.cin_pad,
-                                          layer.cout_pad, ptr(layer.fwd[0]), ptr(layer.fwd[1]), None, None, s)
                 continue
             self.ctx.weight_pack(ptr(layer.w), layer.k * layer.k, layer.cin, layer.cout, layer.cin_pad, layer.cout_pad,
                                  ptr(layer.fwd[0]), ptr(layer.fwd[1]),
@@ -570,6 +570,11 @@ class Stage1Engine:
             self.d1_patch.pack(self.ctx, s)
         else:
             self.e0_patch.pack(self.ctx, s)
+            stem = self.conv[self.n_gstem]
+            # (a torch copy on the current stream: every caller passes the current stream, like the add_py steps)
+            self.stem_wp.copy_(stem.w.view(9, self.gin_c, self.cfg.hidden)[:, self.cfg.emb_dim:, :]
+                               .reshape(self.stem_wp.shape))
+            self.stem_patch.pack(self.ctx, s)
             go = self.gout_f.base
             self.ctx.permute_taps(ptr(go.w), ptr(self.gout_wf), 9, go.cin, 3, 0, s)
             self.ctx.permute_taps(ptr(go.w), ptr(self.gout_wd), 9, go.cin, 3, 1, s)
@@ -615,6 +620,7 @@ class Stage1Engine:
         self.emb = torch.zeros((B, cfg.emb_dim), device=dev)
         # generator
         self.gin = SplitTensor(B, H, W, self.pose_cpad, dev, zero=True)      # pose maps only (channels 0..17)
+        self.pose_patch = SplitTensor(B, H, W, self.stem_patch.cin_pad, dev, zero=True)   # their 3x3 patches [tap*18 + c]
         self.stem_e = torch.zeros((9, B, hn), device=dev)                    # E[tap][n][co] = emb . W[tap, :352]
         self.stem_cb = torch.zeros((B, 9, hn), device=dev)                   # per-image border-class bias
         self.stem_cls = torch.zeros((B, 9, hn), device=dev)
@@ -730,8 +736,11 @@ class Stage1Engine:
 
     # -------------------------------------------------------------------------------- call helpers
     def _epilogue(self, prog, layer_bias, act, alpha, addend, mask_in, mask_neg, mask_out, out, out_masked, out_f32,
-                  out_f32_ps, upsample, class_bias=None, colsum=None):
+                  out_f32_ps, upsample, class_bias=None, colsum=None, stat_sums=None, stat_mode=0):
         ep = _lib.ConvEpilogue()
+        if stat_sums is not None:
+            ep.stat_sums = stat_sums.data_ptr()
+            ep.stat_mode = stat_mode
         if class_bias is not None:
             ep.class_bias = class_bias.data_ptr()
         if colsum is not None:
@@ -758,9 +767,11 @@ class Stage1Engine:
         return C.byref(ep)
 
     def conv_fwd(self, prog, layer, x, out=None, act=ACT_RELU, alpha=0.2, addend=None, mask_out=None, out_f32=None,
-                 out_f32_ps=0, upsample=1, bias=True, out_masked=None, mask_in=None, mask_neg=0.0, class_bias=None):
+                 out_f32_ps=0, upsample=1, bias=True, out_masked=None, mask_in=None, mask_neg=0.0, class_bias=None,
+                 stat_sums=None, stat_mode=0):
         ep = self._epilogue(prog, layer.b if bias else None, act, alpha, addend, mask_in, mask_neg, mask_out, out,
-                            out_masked, out_f32, out_f32_ps, upsample, class_bias)
+                            out_masked, out_f32, out_f32_ps, upsample, class_bias, stat_sums=stat_sums,
+                            stat_mode=stat_mode)
         assert x.c == layer.cin_pad, (layer.wname, x.c, layer.cin_pad)
         oh, ow = -(-x.h // layer.stride), -(-x.w // layer.stride)
         prog.add("conv2d_fwd", x.ref(), ptr(layer.fwd[0]), ptr(layer.fwd[1]), layer.k, layer.k, layer.stride, layer.cout, ep,
@@ -956,7 +967,8 @@ class Stage1Engine:
         pose_slice = self.gin.slice(0, cfg.keypoints)
         self._keep.append(pose_slice)
         p.add("pose_rasterize", ptr(self.pose_rcv), B, cfg.keypoints, H, W, 4, pose_slice.ref(), None)
-        self.conv_fwd(p, stem, self.gin, out=self.g0, mask_out=self.mg0, class_bias=self.stem_cb)
+        p.add("im2col_small", self.gin.ref(), cfg.keypoints, 3, 3, 1, 0, self.pose_patch.ref())
+        self.conv_fwd(p, self.stem_patch, self.pose_patch, out=self.g0, mask_out=self.mg0, class_bias=self.stem_cb)
         self.genc.forward(self, p)
         top = self.genc.y[rn - 1]
         p.add("unpack_f32", top.ref(), ptr(self.gtop_f32), hn * rn)
@@ -1054,8 +1066,10 @@ class Stage1Engine:
         wt = ls.w.view(9, self.gin_c, hn)
         dwt = ls.dw.view(9, self.gin_c, hn)
         # pose rows of the filter gradient on the tensor cores; embedding rows and d(emb) from per-tap sums of g
-        p.add("conv2d_bwd_filter_rows", self.gin.ref(), gi.ref(), 3, 3, 1, cfg.keypoints, hn, ptr(dwt[0, e:]), self.gin_c,
-              flops=2.0 * B * H * W * hn * 9 * cfg.keypoints, tag="%s pose rows" % ls.wname)
+        p.add_py(lambda s: self.stem_dwp.zero_())
+        p.add("conv2d_bwd_filter", self.pose_patch.ref(), gi.ref(), 1, 1, 1, 9 * cfg.keypoints, hn, ptr(self.stem_dwp),
+              flops=2.0 * B * H * W * hn * 9 * cfg.keypoints, tag="%s pose rows (patch form)" % ls.wname)
+        p.add_py(lambda s: dwt[:, e:, :].add_(self.stem_dwp.view(9, cfg.keypoints, hn)))
         if (id(p), id(gi), ls.wname) not in self._db_done:
             p.add("bias_grad", gi.ref(), ptr(ls.db))
         p.add("stem_tap_sums", gi.ref(), ptr(self.stem_cls), ptr(self.stem_ts))
@@ -1073,7 +1087,8 @@ class Stage1Engine:
               self.roi_flat, cfg.part_z)
         p.add("pack_f32", ptr(self.g_roi_flat), hn * ern, hn * ern, self.roi_pyr.g_y[ern - 1].ref())
         self.roi_pyr.backward(self, p)
-        p.add_py(lambda s: self.g_crop.zero_())
+        if int(os.environ.get("DPIG_CROP_GATHER", "1")) == 0:      # the atomic scatter form accumulates; the gather form overwrites
+            p.add_py(lambda s: self.g_crop.zero_())
         p.add("crop_and_resize_bwd", self.roi_pyr.g_in.ref(), ptr(self.fg_mask) if cfg.fgbg else None, ptr(self.boxes),
               ptr(self.box_ind), P * B, ptr(self.g_crop), B, H, W, hn)
         if cfg.fgbg:
@@ -1103,8 +1118,10 @@ class Stage1Engine:
         for i in (1, 2, 3):
             layer = self.conv[self.n_d[i]]
             hh, ww, c = H >> (i + 1), W >> (i + 1), d << i
-            self.conv_fwd(p, layer, dp.h[i - 1], act=ACT_NONE, out_f32=dp.pre[i], out_f32_ps=c)
-            p.add("norm_stats", ptr(dp.pre[i]), n, hh, ww, c, self.norm_mode, ptr(dp.sums[i]))
+            # conv + bias with the raw normalisation sums (sum x, sum x^2 per channel / per sample) emitted by the conv
+            # epilogue, then ONE normalise + LeakyReLU pass: 2 launches per block (wgan_gp.py:417-431)
+            self.conv_fwd(p, layer, dp.h[i - 1], act=ACT_NONE, out_f32=dp.pre[i], out_f32_ps=c,
+                          stat_sums=dp.sums[i], stat_mode=self.norm_mode)
             count = float(hh * ww * c) if self.norm_mode == NORM_LAYER else float(n * hh * ww * self.world)
             if self.norm_mode == NORM_BATCH and self.dist is not None:
                 p.add_py(lambda s, t=dp.sums[i]: self.dist.all_reduce_sum(t))

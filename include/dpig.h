@@ -83,6 +83,14 @@ typedef struct dpig_conv_epilogue {
   /* optional fp32 [cout]: += sum over pixels of out_masked -- the bias gradient of the layer that out_masked is the
    * output-gradient of, fused here so that the gradient tensor is not re-read by dpig_bias_grad. */
   float* colsum_masked;
+  /* optional fp64 [2][groups]: raw sums (sum x, sum x^2) of pre = acc + bias, accumulated by the epilogue so that the
+   * normalisation that follows the conv (wgan_gp.py:417-431: Conv2D -> Batchnorm / Layernorm -> LeakyReLU) needs no
+   * separate statistics pass over the conv output.  stat_mode DPIG_NORM_BATCH: groups = cout (per channel over
+   * N,H,W; tflib/ops/batchnorm.py:29-30); DPIG_NORM_LAYER: groups = n (per sample over C,H,W; layernorm.py:6-20).
+   * The buffer is zeroed by the call.  Needs act = DPIG_ACT_NONE and no addend / out_masked.  These raw sums are what
+   * data-parallel ranks all-reduce for sync-BN before dpig_norm_act_fwd. */
+  double* stat_sums;
+  int32_t stat_mode;
 } dpig_conv_epilogue;
 
 /* ---- context ----------------------------------------------------------------------------- */
@@ -224,7 +232,10 @@ int dpig_embedding_assemble(dpig_ctx* ctx, float* fea, float* bg, const float* v
 int dpig_crop_and_resize_fwd(dpig_ctx* ctx, const dpig_tensor* image, const float* mask,
                              const float* boxes, const int32_t* box_ind, int32_t nbox,
                              const dpig_tensor* out, dpig_stream stream);
-/* grad_image (fp32 NHWC, dense, zero-initialised by caller) += CropAndResizeGradImage(grad). */
+/* grad_image (fp32 NHWC, dense) = CropAndResizeGradImage(grad) (* mask).  Gather form: every image pixel sums the crop
+ * samples whose bilinear footprint covers it, in a fixed order -- no atomics, run-to-run identical, grad_image is
+ * overwritten.  (DPIG_CROP_GATHER=0 selects the older atomic scatter form, which ACCUMULATES into a caller-zeroed
+ * grad_image.) */
 int dpig_crop_and_resize_bwd(dpig_ctx* ctx, const dpig_tensor* grad, const float* mask,
                              const float* boxes, const int32_t* box_ind, int32_t nbox,
                              float* grad_image, int32_t n, int32_t h, int32_t w_, int32_t c,

@@ -170,6 +170,64 @@ def test_conv2d_fwd(case, tiling):
         assert info["err_f32"] < 5e-5, info
 
 
+CONV_STAT_CASES = [
+    # the discriminator's conv -> norm blocks (wgan_gp.py:417-431) and shapes that stress the tiling: several images per
+    # tile (8x4 maps: a warp's rows span images), ragged pixel tiles, two channel blocks / CTA pairs
+    dict(n=4, h=32, w=16, cin=64, cout=128, k=5, stride=2),
+    dict(n=6, h=16, w=8, cin=128, cout=256, k=5, stride=2),
+    dict(n=5, h=8, w=4, cin=256, cout=512, k=5, stride=2),
+    dict(n=3, h=12, w=10, cin=64, cout=96, k=3, stride=1),
+]
+
+
+@pytest.mark.parametrize("tiling", TILINGS)
+@pytest.mark.parametrize("mode", ["batch", "layer"])
+@pytest.mark.parametrize("case", CONV_STAT_CASES)
+def test_conv2d_fwd_stat_emission(case, mode, tiling):
+    """dpig_conv_epilogue::stat_sums: the raw sums (sum x, sum x^2 of conv + bias) per channel (Batchnorm,
+    tflib/ops/batchnorm.py:29-30) or per sample (Layernorm, layernorm.py:6-20) leave the conv epilogue; checked against
+    the float64 sums of the oracle convolution and against dpig_norm_stats on the kernel's own fp32 output."""
+    _lib, SplitTensor, ptr, split_ref = _imports()
+    import ctypes as C
+    n, h, w, cin, cout, k, stride = (case[x] for x in ("n", "h", "w", "cin", "cout", "k", "stride"))
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn((n, h, w, cin), generator=g)
+    wt = torch.randn((k, k, cin, cout), generator=g) / np.sqrt(k * k * cin)
+    bias = torch.randn((cout,), generator=g) * 0.5
+    oh, ow = -(-h // stride), -(-w // stride)
+    xs = padded_split(x)
+    f, _ = pack_weights(wt.cuda().contiguous(), cin_pad=xs.c)
+    bd = bias.cuda()
+    md = {"layer": 0, "batch": 1}[mode]
+    groups = n if mode == "layer" else cout
+    out32 = torch.zeros((n, oh, ow, cout), device="cuda")
+    sums = torch.full((2, groups), 123.0, dtype=torch.float64, device="cuda")    # the call zeroes it
+    ep = _lib.ConvEpilogue()
+    ep.bias = bd.data_ptr()
+    ep.act = 0
+    ep.out_f32 = out32.data_ptr()
+    ep.out_f32_pix_stride = cout
+    ep.upsample = 1
+    ep.stat_sums = sums.data_ptr()
+    ep.stat_mode = md
+    ctx().set_pair_mode(tiling)
+    try:
+        ctx().conv2d_fwd(xs.ref(), ptr(f[0]), ptr(f[1]), k, k, stride, cout, C.byref(ep), stream())
+    finally:
+        ctx().set_pair_mode(1)
+    torch.cuda.synchronize()
+    pre = T.conv2d_same(split_ref(x).double(), split_ref(wt).double(), bias.double(), stride)
+    dims = (1, 2, 3) if mode == "layer" else (0, 1, 2)
+    ref = torch.stack([pre.sum(dim=dims), (pre * pre).sum(dim=dims)])
+    assert rel_err(out32, pre) < 5e-5
+    assert rel_err(sums[0], ref[0]) < 2e-5 and rel_err(sums[1], ref[1]) < 2e-5, (sums.cpu(), ref)
+    if cout % 32 == 0:
+        sums2 = torch.zeros_like(sums)
+        ctx().norm_stats(ptr(out32), n, oh, ow, cout, md, ptr(sums2), stream())
+        torch.cuda.synchronize()
+        assert rel_err(sums, sums2) < 2e-6
+
+
 def run_conv_bwd_data(n, h, w, cin, cout, k, stride, addend=False, masked=False, seed=1):
     _lib, SplitTensor, ptr, split_ref = _imports()
     import ctypes as C
@@ -379,6 +437,44 @@ def test_crop_and_resize():
     gi, = torch.autograd.grad(ref, iv, split_ref(gy).double())
     gi = gi * m[..., None].double()
     assert rel_err(gimg, gi) < 2e-5
+
+
+def test_crop_and_resize_bwd_gather_many_boxes():
+    """Gather form of CropAndResizeGradImage: more boxes on one image than one shared-memory list holds (256), boxes
+    that up- and down-sample, degenerate (invisible-part) boxes [0,0,1,1] px and boxes reaching outside the image
+    (extrapolated samples carry no gradient); against autograd through the float64 oracle."""
+    _lib, SplitTensor, ptr, split_ref = _imports()
+    g = torch.Generator().manual_seed(41)
+    n, h, w, c, cs = 3, 24, 16, 16, 5
+    nb = 700
+    y1 = torch.randint(-2, h - 2, (nb,), generator=g).float()
+    x1 = torch.randint(-2, w - 2, (nb,), generator=g).float()
+    y2 = y1 + torch.randint(0, h, (nb,), generator=g).float()
+    x2 = x1 + torch.randint(0, w, (nb,), generator=g).float()
+    # a last sample exactly on the image edge (y2 == h: in_y == H-1) is valid or extrapolated depending on one rounding
+    # of in_y -- float32 here, float64 in the oracle -- so the test keeps off that knife edge
+    y2[y2 == h] = h - 1
+    x2[x2 == w] = w - 1
+    px = torch.stack([y1, x1, y2, x2], dim=1)
+    px[::17] = torch.tensor([0.0, 0.0, 1.0, 1.0])
+    boxes = torch.stack([px[:, 0] / h, px[:, 1] / w, px[:, 2] / h, px[:, 3] / w], dim=1)
+    ind = torch.randint(0, n, (nb,), generator=g).to(torch.int32)
+    ind[:400] = 1                                   # > 256 boxes on image 1
+    m = (torch.rand((n, h, w), generator=g) > 0.3).float()
+    iv = torch.zeros((n, h, w, c), dtype=torch.float64, requires_grad=True)
+    ref = T.crop_and_resize(iv, boxes.double(), ind, (cs, cs))
+    gy = torch.randn((nb, cs, cs, c), generator=g)
+    gys = SplitTensor.from_float(gy.cuda())
+    gimg = torch.full((n, h, w, c), 7.0, device="cuda")          # overwritten, not accumulated into
+    ctx().crop_and_resize_bwd(gys.ref(), ptr(m.cuda()), ptr(boxes.cuda()), ptr(ind.cuda()), nb, ptr(gimg), n, h, w, c,
+                              stream())
+    gi, = torch.autograd.grad(ref, iv, split_ref(gy).double())
+    gi = gi * m[..., None].double()
+    assert rel_err(gimg, gi) < 2e-5
+    again = torch.zeros_like(gimg)
+    ctx().crop_and_resize_bwd(gys.ref(), ptr(m.cuda()), ptr(boxes.cuda()), ptr(ind.cuda()), nb, ptr(again), n, h, w, c,
+                              stream())
+    assert torch.equal(gimg, again)                 # fixed summation order: bit-identical run to run
 
 
 def test_linear():
