@@ -66,7 +66,7 @@ class NetConfig:
 class ParamGroup:
     """Flat fp32 arenas (value, grad, Adam m / v) with named views."""
 
-    def __init__(self, specs, device):
+    def __init__(self, specs, device, slots=True):
         self.specs = OrderedDict()
         off = 0
         for name, shape in specs:
@@ -75,9 +75,11 @@ class ParamGroup:
             off += (n + 63) // 64 * 64
         self.total = off
         self.value = torch.zeros(off, device=device)
-        self.grad = torch.zeros(off, device=device)
-        self.m = torch.zeros(off, device=device)
-        self.v = torch.zeros(off, device=device)
+        # forward-only engines keep no gradient / optimiser arenas (one shared dummy element keeps the views valid)
+        n = off if slots else 1
+        self.grad = torch.zeros(n, device=device)
+        self.m = torch.zeros(n, device=device)
+        self.v = torch.zeros(n, device=device)
 
     def view(self, name, arena=None):
         off, n, shape = self.specs[name]
@@ -209,6 +211,8 @@ class _Pyramid:
                 self.md.append(_mask(n * (hh // 2) * (ww // 2), c + hn, dev))
         self.in_mask = in_mask
         self.in_layer = None   # ConvLayer producing the pyramid input (set by the owner when in_mask is used)
+        if not eng.training:      # forward-only engine (sampling, tester.py): no gradient buffers
+            return
         # backward buffers
         self.g_y = [SplitTensor(n, d[0], d[1], d[2], dev) for d in self.dims]
         self.gb = [SplitTensor(n, d[0], d[1], d[2], dev) for d in self.dims]
@@ -284,6 +288,8 @@ class _DiscPass:
         rows = n * cfg.d_rows
         self.flat = torch.zeros((rows, cfg.d_row), device=dev)
         self.logits = torch.zeros((rows,), device=dev)
+        if not eng.training:
+            return
         # backward
         self.dlogits = torch.zeros((rows,), device=dev)
         self.g_flat = torch.zeros((rows, cfg.d_row), device=dev)
@@ -300,14 +306,18 @@ class _DiscHalf:
         n = dp.n // 2
         self.n = n
         self.logits = dp.logits[half * rows:(half + 1) * rows]
-        self.dlogits = dp.dlogits[half * rows:(half + 1) * rows]
-        self.g_x = dp.g_x[half * n:(half + 1) * n]
+        if hasattr(dp, "dlogits"):
+            self.dlogits = dp.dlogits[half * rows:(half + 1) * rows]
+            self.g_x = dp.g_x[half * n:(half + 1) * n]
 
 
 class Stage1Engine:
-    def __init__(self, ctx, cfg, batch, mode="dcgan", lam=10.0, dist=None, device="cuda"):
-        """dist: optional object with all_reduce_sum(tensor) and world_size (data-parallel hooks)."""
+    def __init__(self, ctx, cfg, batch, mode="dcgan", lam=10.0, dist=None, device="cuda", inference=False):
+        """dist: optional object with all_reduce_sum(tensor) and world_size (data-parallel hooks).
+        inference: forward-only engine (tester.py: sampling at batch 512) -- no gradient buffers, no backward programs,
+        no optimiser slots: ~1/2 of the activation memory of a training engine, none of its parameter-sized slots."""
         self.ctx, self.cfg, self.B, self.mode, self.lam, self.dist = ctx, cfg, int(batch), mode, lam, dist
+        self.training = not inference
         self.device = torch.device(device)
         self.gan_mode = GAN_MODES[mode]
         self.norm_mode = NORM_LAYER if mode == "wgan-gp" else NORM_BATCH  # wgan_gp.py:34-40
@@ -437,8 +447,8 @@ class Stage1Engine:
         dspecs.append(("Discriminator.Output.W", (self.d_flat, 1)))
         dspecs.append(("Discriminator.Output.b", (1,)))
 
-        self.gp = ParamGroup(gspecs, dev)
-        self.dp = ParamGroup(dspecs, dev)
+        self.gp = ParamGroup(gspecs, dev, slots=self.training)
+        self.dp = ParamGroup(dspecs, dev, slots=self.training)
         self.conv = OrderedDict()
         for name, s in self.layers.items():
             if name == self.n_gstem:
@@ -450,10 +460,10 @@ class Stage1Engine:
                 continue
             if name.startswith("Discriminator"):
                 self.conv[name] = ConvLayer(self.dp, name + ".Filters", name + ".Biases", s["k"], s["stride"], s["cin"],
-                                            s["cout"], dev, s["need_bwd"], s["small"], s["cin_pad"])
+                                            s["cout"], dev, s["need_bwd"] and self.training, s["small"], s["cin_pad"])
             else:
                 self.conv[name] = ConvLayer(self.gp, name + "/weights", name + "/biases", s["k"], s["stride"], s["cin"],
-                                            s["cout"], dev, s["need_bwd"], s["small"], s["cin_pad"])
+                                            s["cout"], dev, s["need_bwd"] and self.training, s["small"], s["cin_pad"])
         # 3-channel ends as 1x1 contractions over (tap, channel) patches (csrc/patch.cu)
         e0, d1, go = self.conv[self.n_e0], self.conv[self.n_d[0]], self.conv[self.n_gout]
         self.e0_patch = PatchLayer(e0, 9 * 3, hn, dev)
@@ -657,9 +667,29 @@ class Stage1Engine:
                 self.dec_mu.append(_mask(B * hh * ww, self.dec_c[idx + 1][0], dev))
         self.G = torch.zeros((B, H, W, 3), device=dev)
         self.gout_y = torch.zeros((B, H, W, 32), device=dev)    # per-tap partial outputs of the 256 -> 3 conv
-        self.gG_patch = SplitTensor(B, H, W, 32, dev)           # transposed patches of dL/dG
         self.G8 = self.pair8.batch_slice(B, B) if cfg.d_joint else SplitTensor(B, H, W, 8, dev, zero=True)
+        if self.training:
+            self._build_backward_buffers()
+        # discriminator passes
+        if cfg.d_joint:
+            self.d_pair = _DiscPass(self, 2 * B, segs=2)
+            self.d_real, self.d_fake = _DiscHalf(self.d_pair, 0), _DiscHalf(self.d_pair, 1)
+        else:
+            self.d_real = _DiscPass(self, B)
+            self.d_fake = _DiscPass(self, B)
+        if self.mode == "wgan-gp" and self.training:
+            self._build_gp_buffers()
+        # losses: [g_gan, d_loss], [L1], gp
+        self.loss_gan = torch.zeros((2,), device=dev)
+        self.loss_l1 = torch.zeros((1,), device=dev)
+        self.loss_gp = torch.zeros((1,), device=dev)
+
+    def _build_backward_buffers(self):
+        cfg, dev, B = self.cfg, self.device, self.B
+        H, W, hn, rn, ern = cfg.img_h, cfg.img_w, cfg.hidden, cfg.unet_repeat, cfg.enc_repeat
+        P = cfg.n_parts
         # generator backward
+        self.gG_patch = SplitTensor(B, H, W, 32, dev)           # transposed patches of dL/dG
         self.g_G = torch.zeros((B, H, W, 3), device=dev)
         self.g_G8 = SplitTensor(B, H, W, 8, dev, zero=True)
         self.g_cat, self.dec_gy, self.dec_gb, self.dec_ga, self.dec_gu = [], [], [], [], []
@@ -689,19 +719,6 @@ class Stage1Engine:
         self.g_xs_m = SplitTensor(B, H, W, hn, dev)
         self.g_e1 = SplitTensor(B, H, W, hn, dev)
         self.g_e0 = SplitTensor(B, H, W, hn, dev)
-        # discriminator passes
-        if cfg.d_joint:
-            self.d_pair = _DiscPass(self, 2 * B, segs=2)
-            self.d_real, self.d_fake = _DiscHalf(self.d_pair, 0), _DiscHalf(self.d_pair, 1)
-        else:
-            self.d_real = _DiscPass(self, B)
-            self.d_fake = _DiscPass(self, B)
-        if self.mode == "wgan-gp":
-            self._build_gp_buffers()
-        # losses: [g_gan, d_loss], [L1], gp
-        self.loss_gan = torch.zeros((2,), device=dev)
-        self.loss_l1 = torch.zeros((1,), device=dev)
-        self.loss_gp = torch.zeros((1,), device=dev)
 
     def _build_gp_buffers(self):
         """Interpolates, critic pass on them, tangent (JVP) and adjoint buffers of the gradient penalty."""
@@ -807,6 +824,8 @@ class Stage1Engine:
         prog.add("bias_grad", dy.ref(), ptr(layer.db))
 
     def _linear(self, grp, name):
+        if not self.training:
+            return grp.view(name + "/weights"), grp.view(name + "/biases"), None, None
         return grp.view(name + "/weights"), grp.view(name + "/biases"), grp.gview(name + "/weights"), grp.gview(name + "/biases")
 
     # -------------------------------------------------------------------------------- programs
@@ -817,11 +836,14 @@ class Stage1Engine:
         self._prog_forward_encoder(self.p_fwd_enc)
         self.p_fwd_unet = Program(self.ctx)    # U-Net only, from self.emb / self.pose_rcv (sampling path, tester.py)
         self._prog_unet_forward(self.p_fwd_unet)
-        self.p_bwd_gen = Program(self.ctx)     # g_G -> all Encoder+G parameter gradients
-        self._prog_backward_generator(self.p_bwd_gen)
+        if self.training:
+            self.p_bwd_gen = Program(self.ctx)     # g_G -> all Encoder+G parameter gradients
+            self._prog_backward_generator(self.p_bwd_gen)
         if self.cfg.d_joint:
             self.p_d_pair_fwd = Program(self.ctx)
             self._prog_disc_forward(self.p_d_pair_fwd, self.d_pair, self.pair8)
+            if not self.training:
+                return
             self.p_d_pair_bwd_data = Program(self.ctx)   # G step: gradient w.r.t. the image halves (the G half is used)
             self._prog_disc_backward(self.p_d_pair_bwd_data, self.d_pair, self.pair8, params=False, data=True)
             self.p_d_pair_bwd_par = Program(self.ctx)    # D step
@@ -831,6 +853,8 @@ class Stage1Engine:
         self._prog_disc_forward(self.p_d_fake_fwd, self.d_fake, self.G8)
         self.p_d_real_fwd = Program(self.ctx)
         self._prog_disc_forward(self.p_d_real_fwd, self.d_real, self.x8)
+        if not self.training:
+            return
         self.p_d_fake_bwd_data = Program(self.ctx)   # G step: gradient w.r.t. the generated image only
         self._prog_disc_backward(self.p_d_fake_bwd_data, self.d_fake, self.G8, params=False, data=True)
         self.p_d_fake_bwd_par = Program(self.ctx)    # D step
@@ -1298,6 +1322,11 @@ class Stage1Engine:
         self.pack_weights(which, s)
 
     def _step(self, which, timings):
+        if not self.training:
+            raise _lib.DpigError("this engine was built forward-only (inference=True): no optimiser steps")
+        return self._step_impl(which, timings)
+
+    def _step_impl(self, which, timings):
         """One optimiser call.  The first two calls of each kind run eagerly (they also set the kernels' launch
         attributes and warm NCCL); the third is captured into a CUDA graph while it runs, later calls replay it.
         Per-launch timing (timings is not None) always runs eagerly."""

@@ -49,7 +49,7 @@ class DPIG_FourNetsFgBg_testOnlySampleFactor(object):
         self.cfg = cfg
         dev = torch.device("cuda", 0)
         B = self.batch_size
-        self.s1 = engine.Stage1Engine(self.ctx, cfg, B, mode="dcgan")
+        self.s1 = engine.Stage1Engine(self.ctx, cfg, B, mode="dcgan", inference=True)
         self.s1.load_params(engine.init_params(cfg, seed=self.config.random_seed))
         self.s2 = stage2.Stage2Engine(self.s1, mode="wgan")
         self.s2.load_params(stage2.init_stage2_params())
@@ -257,7 +257,7 @@ class DPIG_FourNetsFgBg_testOnlyCondition(object):
                        if self.deepfashion else
                        engine.NetConfig(img_h=self.img_H, img_w=self.img_W, hidden=self.conv_hidden_num, z_num=self.z_num))
         self.cfg = net_cfg
-        self.s1 = engine.Stage1Engine(self.ctx, net_cfg, self.batch_size, mode="dcgan")
+        self.s1 = engine.Stage1Engine(self.ctx, net_cfg, self.batch_size, mode="dcgan", inference=True)
         self.s1.load_params(engine.init_params(net_cfg, seed=self.config.random_seed))
         # saverPart = Encoder + ID_AE + Discriminator. (tester.py:619-623); --ckpt_path restores everything
         if self.pretrained_path:

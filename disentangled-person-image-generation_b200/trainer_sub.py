@@ -102,7 +102,7 @@ class DPIG_Encoder_subSampleAppNetFgBg_GAN_BodyROI(DPIG_Encoder_GAN_BodyROI_FgBg
         assert self.batch_size > 0 and self.batch_size % 2 == 0, "batch should be Even and >0"   # trainer.py:777
         self.ctx = _lib.Context(0)
         cfg = self._net_config()
-        self.net = engine.Stage1Engine(self.ctx, cfg, self.batch_size, mode="dcgan")
+        self.net = engine.Stage1Engine(self.ctx, cfg, self.batch_size, mode="dcgan", inference=True)
         params = engine.init_params(cfg, seed=self.config.random_seed)
         loaded = _load_npz([self.pretrained_path, self.ckpt_path])        # Encoder + ID_AE restored, frozen (trainer.py:180-183)
         params.update({k: v for k, v in loaded.items() if k in params})
@@ -248,7 +248,7 @@ class DPIG_subnetSamplePoseRCV_GAN_BodyROI(DPIG_PoseRCV_AE_BodyROI):
         B, H, W = self.batch_size, self.img_H, self.img_W
         if self.net is None:
             cfg = self._net_config()
-            self.net = engine.Stage1Engine(self.ctx, cfg, B, mode="dcgan")
+            self.net = engine.Stage1Engine(self.ctx, cfg, B, mode="dcgan", inference=True)
             p1 = engine.init_params(cfg, seed=self.config.random_seed)
             p1.update({k: v for k, v in _load_npz([self.pretrained_path]).items() if k in p1})
             self.net.load_params(p1)

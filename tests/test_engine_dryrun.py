@@ -1,0 +1,106 @@
+"""CPU dry run of the engine's host logic: every launch program of Stage1Engine is RECORDED (buffers allocated on the
+CPU, no kernel is called -- the library has no CPU path) and each recorded C-ABI call is checked against the ctypes
+signature of include/dpig.h: arity and argument types.  Catches host-side breakage (a renamed buffer, a missing
+argument, a program that references a gradient buffer in forward-only mode) without a GPU; the numerics are the
+`-m gpu` tests' business."""
+import ctypes as C
+import os
+import sys
+
+import pytest
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+from dpig_b200 import _lib, engine  # noqa: E402
+
+
+class DryContext:
+    """Stands in for _lib.Context where no device exists: the library is loaded (symbols resolve), nothing is launched."""
+
+    def __init__(self):
+        self.lib = _lib.load()
+        self.handle = None
+        self.replayed_launches = 0
+
+    def launch_count(self):
+        return 0
+
+    def last_error(self):
+        return ""
+
+
+def _check_program(prog):
+    n = 0
+    for name, fn, args, flops, tag in prog.calls:
+        if name is None:
+            continue
+        want = fn.argtypes[1:-1]          # minus ctx, minus the trailing stream
+        assert len(args) == len(want), ("dpig_" + name, len(args), len(want))
+        for i, (a, t) in enumerate(zip(args, want)):
+            try:
+                t.from_param(a)
+            except (TypeError, C.ArgumentError) as e:      # pragma: no cover - the message is the point
+                raise AssertionError("dpig_%s argument %d: %r does not convert to %s (%s)" % (name, i, a, t, e))
+        n += 1
+    return n
+
+
+SMALL = dict(img_h=32, img_w=16, hidden=64, roi_size=12, d_dim=64)
+
+
+@pytest.mark.parametrize("mode", ["dcgan", "wgan-gp", "wgan"])
+def test_training_programs_record(mode):
+    eng = engine.Stage1Engine(DryContext(), engine.NetConfig(**SMALL), 2, mode=mode, device="cpu")
+    progs = [eng.p_fwd_gen, eng.p_fwd_enc, eng.p_fwd_unet, eng.p_bwd_gen, eng.p_d_fake_fwd, eng.p_d_real_fwd,
+             eng.p_d_fake_bwd_data, eng.p_d_fake_bwd_par, eng.p_d_real_bwd_par]
+    if mode == "wgan-gp":
+        progs.append(eng.p_gp)
+    assert sum(_check_program(p) for p in progs) > 150
+    # conv + norm + LeakyReLU of the critic (wgan_gp.py:417-431): the conv epilogue emits the statistics, so a block is
+    # two launches (conv, normalise-and-activate); no separate statistics pass
+    names = [c[0] for c in eng.p_d_fake_fwd.calls if c[0]]
+    assert "norm_stats" not in names
+    assert names.count("conv2d_fwd") == 4 and names.count("norm_act_fwd") == 3
+
+
+def test_deepfashion_joint_programs_record():
+    cfg = engine.NetConfig.deepfashion(img_h=64, img_w=64, hidden=64, roi_size=16)
+    eng = engine.Stage1Engine(DryContext(), cfg, 2, mode="dcgan", device="cpu")
+    for p in (eng.p_fwd_gen, eng.p_bwd_gen, eng.p_d_pair_fwd, eng.p_d_pair_bwd_data, eng.p_d_pair_bwd_par):
+        assert _check_program(p) > 0
+
+
+def test_forward_only_engine_has_no_gradient_state():
+    """inference=True (tester.py sampling at batch 512): forward programs only, no gradient / optimiser arenas."""
+    cfg = engine.NetConfig(**SMALL)
+    eng = engine.Stage1Engine(DryContext(), cfg, 4, mode="dcgan", device="cpu", inference=True)
+    for p in (eng.p_fwd_gen, eng.p_fwd_enc, eng.p_fwd_unet, eng.p_d_fake_fwd, eng.p_d_real_fwd):
+        assert _check_program(p) > 0
+    assert not hasattr(eng, "p_bwd_gen") and not hasattr(eng, "g_cat") and not hasattr(eng.d_fake, "g_x")
+    assert eng.gp.grad.numel() == 1 and eng.gp.m.numel() == 1
+    with pytest.raises(_lib.DpigError):
+        eng.g_step()
+    full = engine.Stage1Engine(DryContext(), cfg, 4, mode="dcgan", device="cpu")
+
+    def nbytes(e):
+        seen, total = set(), 0
+        stack = [e]
+        while stack:
+            o = stack.pop()
+            if id(o) in seen:
+                continue
+            seen.add(id(o))
+            if hasattr(o, "untyped_storage"):
+                st = o.untyped_storage()
+                if st.data_ptr() not in seen:
+                    seen.add(st.data_ptr())
+                    total += st.nbytes()
+            elif isinstance(o, (list, tuple)):
+                stack.extend(o)
+            elif isinstance(o, dict):
+                stack.extend(o.values())
+            elif hasattr(o, "__dict__") and type(o).__module__.startswith("dpig_b200"):
+                stack.extend(vars(o).values())
+        return total
+
+    assert nbytes(eng) < 0.6 * nbytes(full)

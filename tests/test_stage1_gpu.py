@@ -77,6 +77,36 @@ def check_forward(small, batch=2, mode="dcgan"):
     return rep
 
 
+def check_forward_batch64(batch=64, rows=(0, 21, 42, 63)):
+    """BASELINE.json configs[1] -- the configuration bench.py is quoted on: full 128x64 graph, batch 64.  The generator is
+    per-image (models.py:390-576), so the float64 oracle runs the Encoder + U-Net on a subset of rows; the critic
+    normalises with the statistics of the whole batch (tflib/ops/batchnorm.py:29-30), so the oracle critic is run on all
+    64 real and all 64 generated images (the engine's G, so that both sides evaluate D at the same point)."""
+    eng, cfg, p, ob = _setup(False, batch)
+    eng.forward(with_disc=True)
+    torch.cuda.synchronize()
+    rows = list(rows)
+    sub = {k: v[rows] for k, v in ob.items()}
+    with torch.no_grad():
+        ref = nets.stage1_forward(p, cfg, sub, "dcgan")
+        Gc = eng.G.detach().double().cpu()
+        d_real = nets.dcgan_discriminator(p, cfg, ob["x"], "dcgan")
+        d_fake = nets.dcgan_discriminator(p, cfg, Gc, "dcgan")
+        g_gan, d_loss = T.gan_loss("dcgan", d_real, d_fake)
+        l1 = (Gc - ob["x"]).abs().mean()
+    rep = dict(emb=_maxabs(eng.emb[rows], ref["emb"]), z=_maxabs(eng.z[rows], ref["z"]), G=_maxabs(eng.G[rows], ref["G"]),
+               D_real=_maxabs(eng.d_real.logits, d_real.reshape(-1)), D_fake=_maxabs(eng.d_fake.logits, d_fake.reshape(-1)))
+    e_gan, e_d, e_l1 = eng.losses()
+    rep.update(g_gan=abs(e_gan - float(g_gan)), d_loss=abs(e_d - float(d_loss)), L1=abs(e_l1 - float(l1)))
+    return rep
+
+
+def test_stage1_forward_batch64():
+    rep = check_forward_batch64()
+    for k in ("emb", "z", "G", "D_real", "D_fake", "g_gan", "d_loss", "L1"):
+        assert rep[k] < TOL_ABS, rep
+
+
 def check_grads(small, which, batch=2, mode="dcgan"):
     eng, cfg, p, ob = _setup(small, batch, mode)
     (eng.g_grads if which == "g" else eng.d_grads)()

@@ -57,6 +57,48 @@ def test_sample_factor_forward(sample):
     assert G.min() >= 0 and G.max() <= 255
 
 
+def test_sample_factor_forward_batch512_full_geometry():
+    """BASELINE.json configs[4]: sampling (tester.py:573-613, --model=13) at 128x64, batch 512, through a forward-only
+    engine (inference=True: no gradient buffers; a training engine at this batch would need ~150 GB).  The generator is
+    per-sample, so the float64 oracle runs on a subset of rows; the critic score normalises with the statistics of the
+    WHOLE batch (tflib/ops/batchnorm.py:29-30, quirk q4), so the oracle critic is run on all 512 generated images."""
+    from dpig_b200 import config as cfgmod
+    from dpig_b200 import synth, tester
+    B, rows = 512, [0, 255, 511]
+    conf, _ = cfgmod.get_config(["--model=13", "--is_train=False", "--batch_size=%d" % B, "--sample_fg=True",
+                                 "--sample_bg=True", "--sample_pose=True"])
+    t = tester.DPIG_FourNetsFgBg_testOnlySampleFactor(conf)
+    t.init_net()
+    assert not t.s1.training
+    ocfg = nets.NetConfig()
+    params = dict(nets.init_params(ocfg, seed=11, bias_noise=0.05))
+    params.update(nets.init_stage2_params(seed=12, bias_noise=0.05))
+    params.update(nets.init_pose_params(seed=13, bias_noise=0.05))
+    t.load_params(params)
+    b = synth.make_batch(B, ocfg.img_h, ocfg.img_w, seed=27)
+    rng = np.random.default_rng(8)
+    z_fg = rng.normal(0, 0.2, size=(B, 224)).astype(np.float32)
+    z_bg = rng.normal(0, 0.2, size=(B, 128)).astype(np.float32)
+    G, pose_img, score = t.generate(b["x"], None, b["pose_rcv"], b["part_bbox"], b["part_vis"], mask=b["mask"],
+                                    z_fg=z_fg, z_bg=z_bg)
+    assert G.shape == (B, 128, 64, 3) and score.shape == (B,) and np.isfinite(G).all() and np.isfinite(score).all()
+    p = nets.to_torch(params, torch.float64)
+    ob = dict(x=torch.tensor(b["x"][rows], dtype=torch.float64), mask=torch.tensor(b["mask"][rows], dtype=torch.float64),
+              pose_rcv=torch.tensor(b["pose_rcv"][rows], dtype=torch.float64),
+              part_bbox=torch.tensor(b["part_bbox"][rows][:, :7]), part_vis=torch.tensor(b["part_vis"][rows][:, :7]))
+    with torch.no_grad():
+        ref = nets.sample_factor_forward(p, ocfg, ob, torch.tensor(z_fg[rows], dtype=torch.float64),
+                                         torch.tensor(z_bg[rows], dtype=torch.float64), True, True, True)
+        maps = t.s1.gin.slice(0, 18).hi.float()[rows].cpu().double()
+        same = (maps == ref["pose_maps"]).reshape(len(rows), -1).all(dim=1)       # see test_sample_factor_forward
+        assert int(same.sum()) >= 2, same
+        Ge = t.s1.G.detach().cpu().double()
+        err = (Ge[rows] - ref["G_raw"] if "G_raw" in ref else (torch.clamp((Ge[rows] + 1) * 127.5, 0, 255) - ref["G"]) / 127.5)
+        assert float(err[same].abs().max()) < 1e-3, float(err[same].abs().max())   # north-star bound, pre-denorm scale
+        ref_score = nets.dcgan_discriminator(p, ocfg, Ge, "dcgan").reshape(-1)
+    assert float(np.abs(score.reshape(-1) - ref_score.numpy()).max()) < 1e-3
+
+
 def _four_nets(cls_name, argv, B=4):
     from dpig_b200 import config as cfgmod
     from dpig_b200 import engine, tester

@@ -32,9 +32,59 @@ def run(dist, overlap, graphs):
     return eng, init
 
 
+def oracle_parity(dist):
+    """N ranks x 2 images against the float64 oracle on the GLOBAL batch of 2N (sync-BN over NCCL): critic logits,
+    d_loss and the all-reduced BatchNorm-scale gradients (reference trainer.py:601-605, tflib/ops/batchnorm.py:29-30).
+    The same comparison runs in tests/test_dp_gpu.py with thread-simulated ranks on one GPU."""
+    import torch.distributed as td
+    from oracle import nets
+    from oracle import tf_ops as T
+    os.environ["DPIG_OVERLAP"], os.environ["DPIG_GRAPHS"] = "1", "0"
+    kw = dict(img_h=32, img_w=16, hidden=64, roi_size=12, d_dim=64)
+    ocfg, cfg = nets.NetConfig(**kw), engine.NetConfig(**kw)
+    params = nets.init_params(ocfg, seed=77, bias_noise=0.05)
+    B = 2 * dist.world_size
+    gb = synth.make_batch(B, 32, 16, seed=321)
+    eng = engine.Stage1Engine(dpig_b200.Context(dist.local_rank), cfg, 2, mode="dcgan", dist=dist,
+                              device="cuda:%d" % dist.local_rank)
+    eng.load_params(params)
+    eng.set_batch(ddp.shard(gb, dist.rank, dist.world_size))
+    eng.d_grads()
+    grad = eng.dp.grad.clone()
+    dist.all_reduce_sum(grad)
+    grad /= dist.world_size
+    gather = lambda t: (lambda out: (td.all_gather(out, t.contiguous()), torch.cat(out))[1])(  # noqa: E731
+        [torch.empty_like(t) for _ in range(dist.world_size)])
+    lr, lf, G = gather(eng.d_real.logits), gather(eng.d_fake.logits), gather(eng.G)
+    dl = torch.tensor([eng.losses()[1]], device=G.device)
+    dist.all_reduce_sum(dl)
+    ok = True
+    if dist.rank == 0:
+        p = nets.to_torch(params, torch.float64, requires_grad=True)
+        d_real = nets.dcgan_discriminator(p, ocfg, torch.tensor(gb["x"], dtype=torch.float64), "dcgan")
+        d_fake = nets.dcgan_discriminator(p, ocfg, G.double().cpu(), "dcgan")
+        _, d_loss = T.gan_loss("dcgan", d_real, d_fake)
+        names = ["Discriminator.BN%d.scale" % i for i in (2, 3, 4)]
+        gs = torch.autograd.grad(d_loss, [p[k] for k in names])
+        e_log = max(float((lr.double().cpu() - d_real.detach().reshape(-1)).abs().max()),
+                    float((lf.double().cpu() - d_fake.detach().reshape(-1)).abs().max()))
+        e_loss = abs(float(dl[0]) / dist.world_size - float(d_loss))
+        e_g = 0.0
+        for k, g in zip(names, gs):
+            off, n, _ = eng.dp.specs[k]
+            e_g = max(e_g, float((grad[off:off + n].double().cpu() - g).norm() / g.norm()))
+        ok = e_log < 1e-3 and e_loss < 1e-3 and e_g < 1e-3
+        print("ddp_check oracle parity (global batch %d over %d ranks): logits %.2e d_loss %.2e BN-scale grads %.2e -> %s"
+              % (B, dist.world_size, e_log, e_loss, e_g, "OK" if ok else "FAIL"), flush=True)
+    flag = torch.tensor([1.0 if ok else 0.0], device=G.device)
+    dist.broadcast(flag, 0)
+    return bool(flag[0] > 0)
+
+
 def main():
     dist = ddp.Dist()
     torch.cuda.set_device(dist.local_rank)
+    parity_ok = oracle_parity(dist)
     results = {}
     for name, overlap, graphs in (("overlap", "1", "1"), ("plain", "0", "1"), ("graphs", "1", "2")):
         eng, init = run(dist, overlap, graphs)
@@ -52,7 +102,7 @@ def main():
             d = np.median(np.abs(results[name][0][k].astype(np.float64) - base_p[k]))
             moved = np.median(np.abs(base_p[k].astype(np.float64) - init[k]))
             worst = max(worst, d / max(moved, 1e-12))
-    ok = ok and worst < 0.5 and results["graphs"][3] and results["overlap"][4] and not results["plain"][4]
+    ok = ok and parity_ok and worst < 0.5 and results["graphs"][3] and results["overlap"][4] and not results["plain"][4]
     if dist.rank == 0:
         print("ddp_check ranks_identical=%s worst_median_diff/moved=%.3f graphs_captured=%s -> %s" % (
             [r[2] for r in results.values()], worst, results["graphs"][3], "OK" if ok else "FAIL"), flush=True)
