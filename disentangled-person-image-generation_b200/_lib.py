@@ -96,6 +96,7 @@ _SIGNATURES = {
     "dpig_denorm_u8": [_P, _L, _P, _P],
     "dpig_ssim_gray_u8": [_P, _P, _I, _I, _I, _P, _P],
     "dpig_pose_rasterize": [_P, _I, _I, _I, _I, _I, _T, _P, _P],
+    "dpig_pose_patch": [_P, _I, _I, _I, _I, _I, _I, _I, _T, _P],
 }
 
 EXPORTS = sorted(list(_SIGNATURES) + ["dpig_ctx_create", "dpig_ctx_destroy", "dpig_last_error",

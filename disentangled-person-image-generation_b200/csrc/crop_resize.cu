@@ -149,17 +149,25 @@ __global__ void crop_resize_bwd_kernel(const __nv_bfloat16* ghi, const __nv_bflo
 // at a time.
 constexpr int kCropListCap = 256;
 
-__device__ __forceinline__ void cand_range(float a, float hs, int crop, int Y, int& lo, int& hi) {
+struct CropBoxAffine {   // per box of the block's image: sample position = a + index * s, and the pixels it can touch
+  float ay, hs, ax, ws, rhs, rws;
+  int b;
+  short ymin, ymax, xmin, xmax;
+};
+
+// candidate crop indices whose sample position lies within one pixel of Y (one index of slack on both sides; every
+// candidate is re-checked with the forward kernel's expression)
+__device__ __forceinline__ void cand_range(float a, float s, float rs, int crop, int Y, int& lo, int& hi) {
   if (crop <= 1) {
     lo = hi = 0;
     return;
   }
-  if (hs == 0.f) {
+  if (s == 0.f) {
     lo = 0;
     hi = crop - 1;
     return;
   }
-  float t0 = (static_cast<float>(Y) - 1.f - a) / hs, t1 = (static_cast<float>(Y) + 1.f - a) / hs;
+  float t0 = (static_cast<float>(Y) - 1.f - a) * rs, t1 = (static_cast<float>(Y) + 1.f - a) * rs;
   if (t0 > t1) {
     const float t = t0;
     t0 = t1;
@@ -175,6 +183,7 @@ __global__ void __launch_bounds__(256)
 crop_resize_bwd_gather_kernel(const __nv_bfloat16* ghi, const __nv_bfloat16* glo, long long gps, const float* mask,
                               const float* boxes, const int* box_ind, int nbox, CropGeom g, float* gimg) {
   __shared__ int s_list[kCropListCap];
+  __shared__ CropBoxAffine s_box[kCropListCap];
   __shared__ int s_cnt, s_next;
   const int n = blockIdx.y;
   const int C8 = g.C / 8;
@@ -205,16 +214,36 @@ crop_resize_bwd_gather_kernel(const __nv_bfloat16* ghi, const __nv_bfloat16* glo
     __syncthreads();
     const int cnt = s_cnt;
     scanned = s_next;
+    for (int k = threadIdx.x; k < cnt; k += blockDim.x) {   // the affine sample maps of the boxes, once per block
+      const int b = s_list[k];
+      const float* box = boxes + 4 * b;
+      const float y1 = box[0], x1 = box[1], y2 = box[2], x2 = box[3];
+      CropBoxAffine q;
+      q.b = b;
+      q.hs = (g.CH > 1) ? (y2 - y1) * (g.H - 1) / (g.CH - 1) : 0.f;
+      q.ws = (g.CW > 1) ? (x2 - x1) * (g.W - 1) / (g.CW - 1) : 0.f;
+      q.ay = (g.CH > 1) ? y1 * (g.H - 1) : 0.5f * (y1 + y2) * (g.H - 1);
+      q.ax = (g.CW > 1) ? x1 * (g.W - 1) : 0.5f * (x1 + x2) * (g.W - 1);
+      q.rhs = q.hs != 0.f ? 1.f / q.hs : 0.f;
+      q.rws = q.ws != 0.f ? 1.f / q.ws : 0.f;
+      const float ye = q.ay + (g.CH - 1) * q.hs, xe = q.ax + (g.CW - 1) * q.ws;   // last sample (first: ay / ax)
+      q.ymin = static_cast<short>(fminf(fmaxf(floorf(fminf(q.ay, ye)) - 1.f, 0.f), 32767.f));
+      q.ymax = static_cast<short>(fminf(fmaxf(ceilf(fmaxf(q.ay, ye)) + 1.f, -1.f), static_cast<float>(g.H - 1)));
+      q.xmin = static_cast<short>(fminf(fmaxf(floorf(fminf(q.ax, xe)) - 1.f, 0.f), 32767.f));
+      q.xmax = static_cast<short>(fminf(fmaxf(ceilf(fmaxf(q.ax, xe)) + 1.f, -1.f), static_cast<float>(g.W - 1)));
+      s_box[k] = q;
+    }
+    __syncthreads();
     if (live) {
       for (int k = 0; k < cnt; ++k) {
-        const int b = s_list[k];
-        const float* box = boxes + 4 * b;
+        const CropBoxAffine& q = s_box[k];
+        if (Y < q.ymin || Y > q.ymax || X < q.xmin || X > q.xmax) continue;   // most boxes miss most pixels
+        const float* box = boxes + 4 * q.b;
         const float y1 = box[0], x1 = box[1], y2 = box[2], x2 = box[3];
-        const float hs = (g.CH > 1) ? (y2 - y1) * (g.H - 1) / (g.CH - 1) : 0.f;
-        const float ws = (g.CW > 1) ? (x2 - x1) * (g.W - 1) / (g.CW - 1) : 0.f;
+        const float hs = q.hs, ws = q.ws;
         int ylo, yhi, xlo, xhi;
-        cand_range((g.CH > 1) ? y1 * (g.H - 1) : 0.5f * (y1 + y2) * (g.H - 1), hs, g.CH, Y, ylo, yhi);
-        cand_range((g.CW > 1) ? x1 * (g.W - 1) : 0.5f * (x1 + x2) * (g.W - 1), ws, g.CW, X, xlo, xhi);
+        cand_range(q.ay, hs, q.rhs, g.CH, Y, ylo, yhi);
+        cand_range(q.ax, ws, q.rws, g.CW, X, xlo, xhi);
         for (int y = ylo; y <= yhi; ++y) {
           const float in_y = (g.CH > 1) ? y1 * (g.H - 1) + y * hs : 0.5f * (y1 + y2) * (g.H - 1);
           if (in_y < 0.f || in_y > g.H - 1) continue;
@@ -229,7 +258,7 @@ crop_resize_bwd_gather_kernel(const __nv_bfloat16* ghi, const __nv_bfloat16* glo
             if (l != X && r != X) continue;
             const float xl = in_x - l;
             const float wx = (l == X ? 1.f - xl : 0.f) + (r == X ? xl : 0.f);
-            const long long opix = (static_cast<long long>(b) * g.CH + y) * g.CW + x;
+            const long long opix = (static_cast<long long>(q.b) * g.CH + y) * g.CW + x;
             ld8_split(ghi, glo, opix * gps + c, 1.f, wy * wx, acc);
           }
         }

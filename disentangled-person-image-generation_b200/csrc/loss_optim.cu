@@ -229,6 +229,55 @@ __global__ void pose_raster_kernel(const float* rcv, int N, int K, int H, int W,
   }
 }
 
+// The 3x3 (kh x kw) SAME-padded patches of the inflated pose maps straight from the keypoints: out[n,y,x,(i*kw+j)*K + k] =
+// map_k(y + i - pt, x + j - pl), 0 outside the image (the conv's zero padding) and in the pad channels.  The U-Net stem
+// reads the pose channels in this patch form (one 1x1 contraction over K = 9*18 instead of nine 64-deep K chunks of
+// 18 channels); building the patches from the 18 keypoints costs no read of the maps at all.
+// thread = (pixel, tap): the 18 keypoints of one neighbour pixel -> K bf16 values per plane, 4-byte stores (a tap's K
+// channels start at byte tap*2K: 4-byte aligned for even K).  No per-element index arithmetic: the first version
+// (thread = 8 patch channels, c / K and c % K per element) was instruction-bound at 0.5 ms per call.
+__global__ void pose_patch_kernel(const float* rcv, int N, int K, int H, int W, int radius, int kh, int kw, int pt,
+                                  int pl, __nv_bfloat16* ohi, __nv_bfloat16* olo, long long ops, int Cp) {
+  const int taps = kh * kw;
+  const int tail = Cp - taps * K;                      // pad channels, zeroed by the last tap's thread
+  const long long total = static_cast<long long>(N) * H * W * taps;
+  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int tap = static_cast<int>(idx % taps);
+    const long long pix = idx / taps;
+    const int x = static_cast<int>(pix % W);
+    const int y = static_cast<int>((pix / W) % H);
+    const int n = static_cast<int>(pix / (static_cast<long long>(W) * H));
+    const int yy = y + tap / kw - pt, xx = x + tap % kw - pl;
+    const bool in_img = yy >= 0 && yy < H && xx >= 0 && xx < W;
+    const float* q = rcv + static_cast<long long>(n) * K * 3;
+    uint32_t* oh = reinterpret_cast<uint32_t*>(ohi + pix * ops + tap * K);
+    uint32_t* ol = olo ? reinterpret_cast<uint32_t*>(olo + pix * ops + tap * K) : nullptr;
+    for (int k = 0; k < K; k += 2) {
+      uint32_t hw = 0, lw = 0;
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        if (in_img && k + e < K) {
+          const float* qq = q + (k + e) * 3;
+          const int dr = yy - static_cast<int>(__ldg(qq)), dc = xx - static_cast<int>(__ldg(qq + 1));
+          const bool inside = (dr * dr + dc * dc <= radius * radius);
+          const float v = (inside ? fminf(__ldg(qq + 2), 1.f) : 0.f) * 2.f - 1.f;     // as pose_raster_kernel
+          const __nv_bfloat16 hb = __float2bfloat16_rn(v);
+          hw |= static_cast<uint32_t>(__bfloat16_as_ushort(hb)) << (16 * e);
+          lw |= static_cast<uint32_t>(__bfloat16_as_ushort(__float2bfloat16_rn(v - __bfloat162float(hb)))) << (16 * e);
+        }
+      }
+      oh[k >> 1] = hw;
+      if (ol) ol[k >> 1] = lw;
+    }
+    if (tap == taps - 1)
+      for (int t = 0; t < tail; t += 2) {
+        oh[(K + t) >> 1] = 0u;
+        if (ol) ol[(K + t) >> 1] = 0u;
+      }
+  }
+}
+
 static inline int gridn(long long total, int block = 256, int cap = 148 * 16) {
   long long g = (total + block - 1) / block;
   if (g > cap) g = cap;
@@ -364,4 +413,21 @@ extern "C" int dpig_pose_rasterize(dpig_ctx* ctx, const float* rcv, int32_t n, i
       out ? static_cast<__nv_bfloat16*>(out->lo) : nullptr, out ? out->pix_stride : 0, out_f32);
   ctx->launches++;
   return check_launch(ctx, "pose_rasterize");
+}
+
+extern "C" int dpig_pose_patch(dpig_ctx* ctx, const float* rcv, int32_t n, int32_t k, int32_t h, int32_t w_,
+                               int32_t radius, int32_t kh, int32_t kw, const dpig_tensor* out, dpig_stream stream) {
+  DPIG_CHECK_CTX(ctx);
+  if (!rcv || !out || !out->hi) return set_error(ctx, DPIG_EINVAL, "pose_patch: null argument");
+  if (k % 2) return set_error(ctx, DPIG_EUNSUPPORTED, "pose_patch: an even number of keypoint channels is required");
+  if (out->n != n || out->h != h || out->w != w_ || out->c < kh * kw * k || out->c % 8 || out->pix_stride % 8 ||
+      reinterpret_cast<uintptr_t>(out->hi) % 16 || (out->lo && reinterpret_cast<uintptr_t>(out->lo) % 16))
+    return set_error(ctx, DPIG_EINVAL, "pose_patch: output must be [%d,%d,%d,>=%d] with channels / stride multiples of 8",
+                     n, h, w_, kh * kw * k);
+  const long long total = static_cast<long long>(n) * h * w_ * kh * kw;
+  pose_patch_kernel<<<gridn(total), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      rcv, n, k, h, w_, radius, kh, kw, same_pad_before(h, kh, 1), same_pad_before(w_, kw, 1),
+      static_cast<__nv_bfloat16*>(out->hi), static_cast<__nv_bfloat16*>(out->lo), out->pix_stride, out->c);
+  ctx->launches++;
+  return check_launch(ctx, "pose_patch");
 }

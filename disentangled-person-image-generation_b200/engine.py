@@ -991,7 +991,7 @@ class Stage1Engine:
         pose_slice = self.gin.slice(0, cfg.keypoints)
         self._keep.append(pose_slice)
         p.add("pose_rasterize", ptr(self.pose_rcv), B, cfg.keypoints, H, W, 4, pose_slice.ref(), None)
-        p.add("im2col_small", self.gin.ref(), cfg.keypoints, 3, 3, 1, 0, self.pose_patch.ref())
+        p.add("pose_patch", ptr(self.pose_rcv), B, cfg.keypoints, H, W, 4, 3, 3, self.pose_patch.ref())
         self.conv_fwd(p, self.stem_patch, self.pose_patch, out=self.g0, mask_out=self.mg0, class_bias=self.stem_cb)
         self.genc.forward(self, p)
         top = self.genc.y[rn - 1]

@@ -11,6 +11,7 @@ backward program (linear / activation / residual add only).  The real embeddings
 appearance encoder (engine.Stage1Engine.run_encoder()).
 """
 import math
+import os
 from collections import OrderedDict
 
 import numpy as np
@@ -354,10 +355,19 @@ class Stage2Engine:
     """--model=3 step on top of a (frozen) Stage-I engine: `g_step(factor)` / `d_step(factor)` with factor in
     {'fg','bg'}; MODE 'wgan' (as shipped), 'lsgan' or 'dcgan' losses."""
 
-    def __init__(self, stage1, mode="wgan", g_lr=2e-5, d_lr=2e-5, factors=None):
+    def __init__(self, stage1, mode="wgan", g_lr=2e-5, d_lr=2e-5, factors=None, dist=None):
+        """dist: data-parallel hooks (ddp.Dist): the FC gradients are all-reduced before every optimiser call; the FC
+        nets carry no batch-coupled normalisation (models.py:474-486, wgan_gp.py:399-405), so that is the only exchange."""
         self.s1, self.mode, self.g_lr, self.d_lr = stage1, mode, g_lr, d_lr
         self.gan_mode = GAN_MODES[mode]
         self.lam = 10.0
+        self.dist = dist
+        self.world = dist.world_size if dist is not None else 1
+        # whole-call CUDA graphs of train_iteration's optimiser calls (a critic call = frozen-encoder forward, ~100
+        # launches, + ~70 small FC launches + the update): same switch as Stage1Engine (DPIG_GRAPHS)
+        gmode = int(os.environ.get("DPIG_GRAPHS", "1"))
+        self.use_graphs = gmode >= 2 or (gmode == 1 and dist is None)
+        self._graphs, self._eager_calls, self._lr_dev = {}, {}, {}
         if factors is not None:      # custom factor set (the pose sampler of --model=4); no Stage-I engine needed
             self.f = factors
             first = next(iter(factors.values()))
@@ -410,13 +420,74 @@ class Stage2Engine:
         grp = f.gp if which == "g" else f.dp
         lr = self.g_lr if which == "g" else self.d_lr
         f.t[which] += 1
+        if self.dist is not None:
+            self.dist.all_reduce_sum(grp.grad)
+        gs = 1.0 / self.world
         if self.mode in ("wgan", "lsgan"):
             clip = 0.01 if (self.mode == "wgan" and which == "d") else 0.0
-            self.ctx.rmsprop_step(ptr(grp.value), ptr(grp.grad), ptr(grp.v), grp.total, lr, 0.9, 1e-10, 1.0, clip, s)
+            self.ctx.rmsprop_step(ptr(grp.value), ptr(grp.grad), ptr(grp.v), grp.total, lr, 0.9, 1e-10, gs, clip, s)
         else:
             b2 = 0.9 if self.mode == "wgan-gp" else 0.999
             self.ctx.adam_step(ptr(grp.value), ptr(grp.grad), ptr(grp.m), ptr(grp.v), grp.total, lr, 0.5, b2, 1e-8,
-                               f.t[which], 1.0, s)
+                               f.t[which], gs, s)
+
+    def _optim_dev(self, f, which, lr_dev, s):
+        """_optim with the step size read from device memory (dpig_*_step_dev): what a captured graph replays."""
+        grp = f.gp if which == "g" else f.dp
+        if self.dist is not None:
+            self.dist.all_reduce_sum(grp.grad)
+        gs = 1.0 / self.world
+        if self.mode in ("wgan", "lsgan"):
+            clip = 0.01 if (self.mode == "wgan" and which == "d") else 0.0
+            self.ctx.rmsprop_step_dev(ptr(grp.value), ptr(grp.grad), ptr(grp.v), grp.total, ptr(lr_dev), 0.9, 1e-10, gs,
+                                      clip, s)
+        else:
+            b2 = 0.9 if self.mode == "wgan-gp" else 0.999
+            self.ctx.adam_step_dev(ptr(grp.value), ptr(grp.grad), ptr(grp.m), ptr(grp.v), grp.total, ptr(lr_dev), 0.5,
+                                   b2, 1e-8, gs, s)
+
+    def _step_size(self, f, which):
+        lr = float(np.float32(self.g_lr if which == "g" else self.d_lr))
+        if self.mode in ("wgan", "lsgan"):
+            return lr
+        b2 = float(np.float32(0.9 if self.mode == "wgan-gp" else 0.999))
+        t = f.t[which]
+        return lr * math.sqrt(1.0 - b2 ** t) / (1.0 - 0.5 ** t)
+
+    def _call(self, factor, which):
+        """One optimiser call of train_iteration on the Stage-I batch already in HBM: fresh noise, gradients, update
+        (a critic call first runs the frozen encoder on the batch).  The first two calls of a kind run eagerly, the
+        third is captured into a CUDA graph while it runs, later ones replay it; the step size is a device scalar."""
+        f = self.f[factor]
+        key = (factor, which)
+        lr_dev = self._lr_dev.get(key)
+        if lr_dev is None:
+            lr_dev = self._lr_dev[key] = torch.zeros(1, dtype=torch.float32, device=f.loss.device)
+        f.t[which] += 1
+        lr_dev.fill_(self._step_size(f, which))
+
+        def body():
+            s = torch.cuda.current_stream().cuda_stream
+            if which == "d" and self.s1 is not None:
+                self.encode_real()
+            self.sample_noise(factor)
+            (self.g_grads if which == "g" else self.d_grads)(factor)
+            self._optim_dev(f, which, lr_dev, s)
+
+        if not self.use_graphs:
+            return body()
+        g = self._graphs.get(key)
+        if g is None:
+            if self._eager_calls.get(key, 0) < 2:
+                self._eager_calls[key] = self._eager_calls.get(key, 0) + 1
+                return body()
+            graph = torch.cuda.CUDAGraph()
+            n0 = self.ctx.launch_count()
+            with torch.cuda.graph(graph):
+                body()
+            g = self._graphs[key] = (graph, self.ctx.launch_count() - n0)
+        g[0].replay()
+        self.ctx.replayed_launches += g[1]
 
     def g_grads(self, factor):
         f = self.f[factor]
@@ -461,10 +532,7 @@ class Stage2Engine:
         iters = 1 if self.mode in ("dcgan", "lsgan") else 5
         for factor in ("fg", "bg"):
             if step > 0:
-                self.sample_noise(factor)
-                self.g_step(factor)
+                self._call(factor, "g")
             for _ in range(iters):
                 self.s1.set_batch(next_batch())
-                self.encode_real()
-                self.sample_noise(factor)
-                self.d_step(factor)
+                self._call(factor, "d")

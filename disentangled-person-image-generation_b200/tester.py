@@ -99,6 +99,21 @@ class DPIG_FourNetsFgBg_testOnlySampleFactor(object):
         if mask is None:
             mask = np.ones((B, H, W, 1), np.float32)
         s1.set_batch(dict(x=x_fixed, pose_rcv=pose_rcv_fixed, mask=mask, part_bbox=part_bbox_fixed, part_vis=part_vis_fixed))
+        G, pose_img, score, ssim = self.generate_on_device(z_fg, z_bg)
+        self.last_ssim = ssim.cpu().numpy()
+        G_np, pose_np = G.cpu().numpy(), pose_img.cpu().numpy()
+        if save and root_path is not None:                       # tester.py:242-252
+            ssim_mean = float(np.mean(self.last_ssim))
+            outputs.save_image(G_np, path or os.path.join(root_path, "%s_G_ssim%s.png" % (idx, ssim_mean)))
+            outputs.save_image(pose_np, os.path.join(root_path, "%s_G_pose_inflated_reLoss%s.png" % (idx, 0.0)))
+        return G_np, pose_np, score.cpu().numpy()
+
+    def generate_on_device(self, z_fg=None, z_bg=None):
+        """The device half of generate() for the batch already in HBM (Stage1Engine.set_batch): returns DEVICE tensors
+        (G in [0,255] NHWC float32, inflated-pose image, critic score [B], per-sample SSIM(G, x) [B])."""
+        s1, s2, cfg, B = self.s1, self.s2, self.cfg, self.batch_size
+        H, W = cfg.img_h, cfg.img_w
+        st = torch.cuda.current_stream().cuda_stream
         # ---- pose branch (tester.py:477-505)
         rcv = s1.pose_rcv
         norm = torch.stack([rcv[:, :, 0] / float(H) * 2.0 - 1, rcv[:, :, 1] / float(W) * 2.0 - 1, rcv[:, :, 2]], dim=-1)
@@ -125,13 +140,7 @@ class DPIG_FourNetsFgBg_testOnlySampleFactor(object):
         pose_maps = s1.gin.slice(0, cfg.keypoints).hi.float()
         pose_img = (pose_maps.amax(dim=-1, keepdim=True).expand(-1, -1, -1, 3) + 1) * 127.5
         # ---- SSIM(G, x) per sample on the uint8 images (tester.py:236-241), on the device
-        self.last_ssim = self.ssim_G_x(st)
-        G_np, pose_np = G.cpu().numpy(), pose_img.cpu().numpy()
-        if save and root_path is not None:                       # tester.py:242-252
-            ssim_mean = float(np.mean(self.last_ssim))
-            outputs.save_image(G_np, path or os.path.join(root_path, "%s_G_ssim%s.png" % (idx, ssim_mean)))
-            outputs.save_image(pose_np, os.path.join(root_path, "%s_G_pose_inflated_reLoss%s.png" % (idx, 0.0)))
-        return G_np, pose_np, score.cpu().numpy()
+        return G, pose_img, score, self.ssim_G_x(st, to_host=False)
 
     def _held_pose(self, norm):
         """sample_pose=False: the first sample's real pose for the whole batch (tester.py:500-503)."""
@@ -150,7 +159,7 @@ class DPIG_FourNetsFgBg_testOnlySampleFactor(object):
             else:
                 s1.emb[:, sl].copy_(f.real.data[:1].expand(B, -1))
 
-    def ssim_G_x(self, stream=None):
+    def ssim_G_x(self, stream=None, to_host=True):
         """skimage-style SSIM between the generated and the input images of the current batch, per sample [B]."""
         s1, B = self.s1, self.batch_size
         st = stream if stream is not None else torch.cuda.current_stream().cuda_stream
@@ -161,7 +170,7 @@ class DPIG_FourNetsFgBg_testOnlySampleFactor(object):
         self.ctx.denorm_u8(ptr(s1.G), s1.G.numel(), ptr(g8), st)
         self.ctx.denorm_u8(ptr(s1.x), s1.x.numel(), ptr(x8), st)
         self.ctx.ssim_gray_u8(ptr(g8), ptr(x8), B, H, W, ptr(out), st)
-        return out.cpu().numpy()
+        return out.cpu().numpy() if to_host else out
 
     def _pose_max_img(self, pose_rcv):
         """(amax over the 18 inflated keypoint maps + 1) * 127.5 (tester.py:175-176) for a [B,18,3] keypoint array."""

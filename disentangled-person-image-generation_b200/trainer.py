@@ -106,9 +106,11 @@ class DPIG_Encoder_GAN_BodyROI_FgBg(object):
         self._log = open(os.path.join(self.model_dir, "summary.jsonl"), "a")
 
     # ------------------------------------------------------------------ train
-    def train(self):
+    def train(self, on_step=None):
         """The step loop of trainer.py:336-366: G update (skipped at global step 0), then disc_ITERS critic updates,
-        each on its own batch; lr halving every lr_update_step; parameter dump every 30*log_step."""
+        each on its own batch; lr halving every lr_update_step; parameter dump every 30*log_step.
+        on_step(step, trainer): optional hook called after the optimiser calls of every step (bench.py reads the losses
+        there; the reference's loop fetches nothing between summaries)."""
         net = self.net
         disc_iters = 1 if self.gan_mode in ("dcgan", "lsgan") else 5   # wgan_gp.CRITIC_ITERS = 5 (wgan_gp.py:113)
         t0 = time.time()
@@ -119,6 +121,8 @@ class DPIG_Encoder_GAN_BodyROI_FgBg(object):
             for _ in range(disc_iters):
                 net.set_batch(self.loader.next_batch())
                 net.d_step()
+            if on_step is not None:
+                on_step(step, self)
             if step == 0 or step % self.log_step == self.log_step - 1:
                 net.set_batch(self.loader.next_batch())
                 net.forward(with_disc=True)

@@ -100,25 +100,31 @@ class DPIG_Encoder_subSampleAppNetFgBg_GAN_BodyROI(DPIG_Encoder_GAN_BodyROI_FgBg
     def init_net(self):
         os.makedirs(self.model_dir, exist_ok=True)
         assert self.batch_size > 0 and self.batch_size % 2 == 0, "batch should be Even and >0"   # trainer.py:777
-        self.ctx = _lib.Context(0)
+        device = self.dist.local_rank if self.dist is not None else 0
+        self.ctx = _lib.Context(device)
         cfg = self._net_config()
-        self.net = engine.Stage1Engine(self.ctx, cfg, self.batch_size, mode="dcgan", inference=True)
+        # the frozen Stage-I networks run forward only (trainer.py:737-741: no gradient reaches the Encoder / ID_AE scopes)
+        self.net = engine.Stage1Engine(self.ctx, cfg, self.batch_size, mode="dcgan", inference=True,
+                                       device="cuda:%d" % device)
         params = engine.init_params(cfg, seed=self.config.random_seed)
         loaded = _load_npz([self.pretrained_path, self.ckpt_path])        # Encoder + ID_AE restored, frozen (trainer.py:180-183)
         params.update({k: v for k, v in loaded.items() if k in params})
         self.net.load_params(params)
-        self.s2 = stage2.Stage2Engine(self.net, mode="wgan", g_lr=self.g_lr, d_lr=self.d_lr)   # MODE='wgan' trainer.py:720-725
+        self.s2 = stage2.Stage2Engine(self.net, mode="wgan", g_lr=self.g_lr, d_lr=self.d_lr,   # MODE='wgan' trainer.py:720-725
+                                      dist=self.dist)
         p2 = stage2.init_stage2_params(seed=self.config.random_seed)
         p2.update({k: v for k, v in loaded.items() if k in p2})
         self.s2.load_params(p2)
         self._log = open(os.path.join(self.model_dir, "summary.jsonl"), "a")
 
-    def train(self):
+    def train(self, on_step=None):
         """trainer.py:812-867: per step and factor one g_optim (step > 0) and CRITIC_ITERS x (d_optim + clip)."""
         t0 = time.time()
         for step in range(self.start_step, self.max_step):
             self.s2.g_lr, self.s2.d_lr = self.g_lr, self.d_lr
             self.s2.train_iteration(step, self.loader.next_batch)
+            if on_step is not None:
+                on_step(step, self)
             if step == 0 or step % self.log_step == self.log_step - 1:
                 rec = {"step": step, "misc/g_lr": self.g_lr, "misc/d_lr": self.d_lr, "wall_s": time.time() - t0}
                 for factor in ("fg", "bg"):

@@ -359,6 +359,12 @@ int dpig_ssim_gray_u8(dpig_ctx* ctx, const uint8_t* a, const uint8_t* b, int32_t
 int dpig_pose_rasterize(dpig_ctx* ctx, const float* rcv, int32_t n, int32_t k, int32_t h,
                         int32_t w_, int32_t radius, const dpig_tensor* out, float* out_f32,
                         dpig_stream stream);
+/* The kh x kw SAME-padded (stride 1) patches of those maps, built straight from the keypoints:
+ * out[n,y,x,(i*kw + j)*k + c] = map_c(y + i - pad, x + j - pad), 0 outside the image and in the pad channels
+ * (out->c >= kh*kw*k).  Input of the U-Net stem's pose rows in patch form (models.py:520-528: the 18 pose channels of
+ * concat([emb, pose]) under the 3x3 stem conv, as ONE 1x1 contraction over kh*kw*k channels). */
+int dpig_pose_patch(dpig_ctx* ctx, const float* rcv, int32_t n, int32_t k, int32_t h, int32_t w_,
+                    int32_t radius, int32_t kh, int32_t kw, const dpig_tensor* out, dpig_stream stream);
 
 /* ---- host utility ------------------------------------------------------------------------------ */
 /* CRC-32C (Castagnoli) of a HOST buffer, chained through `crc` (start with 0): the checksum TensorFlow's checkpoint

@@ -447,16 +447,16 @@ def test_crop_and_resize_bwd_gather_many_boxes():
     g = torch.Generator().manual_seed(41)
     n, h, w, c, cs = 3, 24, 16, 16, 5
     nb = 700
-    y1 = torch.randint(-2, h - 2, (nb,), generator=g).float()
-    x1 = torch.randint(-2, w - 2, (nb,), generator=g).float()
-    y2 = y1 + torch.randint(0, h, (nb,), generator=g).float()
-    x2 = x1 + torch.randint(0, w, (nb,), generator=g).float()
-    # a last sample exactly on the image edge (y2 == h: in_y == H-1) is valid or extrapolated depending on one rounding
-    # of in_y -- float32 here, float64 in the oracle -- so the test keeps off that knife edge
-    y2[y2 == h] = h - 1
-    x2[x2 == w] = w - 1
+    # fractional box corners: with integer corners whole rows of samples land EXACTLY on the image border (in_y == 0 or
+    # H-1), where one rounding of in_y -- float32 here, float64 in the oracle -- decides valid vs extrapolated
+    y1 = torch.rand((nb,), generator=g) * h - 2
+    x1 = torch.rand((nb,), generator=g) * w - 2
+    y2 = y1 + torch.rand((nb,), generator=g) * h
+    x2 = x1 + torch.rand((nb,), generator=g) * w
     px = torch.stack([y1, x1, y2, x2], dim=1)
     px[::17] = torch.tensor([0.0, 0.0, 1.0, 1.0])
+    px[5] = torch.tensor([18.3, 12.1, 4.2, 1.4])        # flipped box (y2 < y1, x2 < x1)
+    px[6] = torch.tensor([7.3, 2.1, 7.3, 11.4])         # zero height: every crop row samples the same image row
     boxes = torch.stack([px[:, 0] / h, px[:, 1] / w, px[:, 2] / h, px[:, 3] / w], dim=1)
     ind = torch.randint(0, n, (nb,), generator=g).to(torch.int32)
     ind[:400] = 1                                   # > 256 boxes on image 1
@@ -466,15 +466,38 @@ def test_crop_and_resize_bwd_gather_many_boxes():
     gy = torch.randn((nb, cs, cs, c), generator=g)
     gys = SplitTensor.from_float(gy.cuda())
     gimg = torch.full((n, h, w, c), 7.0, device="cuda")          # overwritten, not accumulated into
-    ctx().crop_and_resize_bwd(gys.ref(), ptr(m.cuda()), ptr(boxes.cuda()), ptr(ind.cuda()), nb, ptr(gimg), n, h, w, c,
-                              stream())
+    md, bd, idd = m.cuda(), boxes.cuda(), ind.cuda()          # (kept alive: the kernel reads them after this line)
+    ctx().crop_and_resize_bwd(gys.ref(), ptr(md), ptr(bd), ptr(idd), nb, ptr(gimg), n, h, w, c, stream())
     gi, = torch.autograd.grad(ref, iv, split_ref(gy).double())
     gi = gi * m[..., None].double()
     assert rel_err(gimg, gi) < 2e-5
     again = torch.zeros_like(gimg)
-    ctx().crop_and_resize_bwd(gys.ref(), ptr(m.cuda()), ptr(boxes.cuda()), ptr(ind.cuda()), nb, ptr(again), n, h, w, c,
-                              stream())
+    ctx().crop_and_resize_bwd(gys.ref(), ptr(md), ptr(bd), ptr(idd), nb, ptr(again), n, h, w, c, stream())
     assert torch.equal(gimg, again)                 # fixed summation order: bit-identical run to run
+
+
+def test_pose_patch_matches_rasterised_maps():
+    """dpig_pose_patch: the 3x3 SAME patches of the inflated keypoint maps (utils.py:259-318) built straight from the
+    keypoints == the oracle's rasterised maps, zero-padded and unfolded (bit-exact: the values are -1 / +1 / 0)."""
+    _lib, SplitTensor, ptr, split_ref = _imports()
+    rng = np.random.default_rng(9)
+    n, k, h, w = 3, 18, 32, 16
+    rcv = np.zeros((n, k, 3), np.float32)
+    rcv[:, :, 0] = rng.uniform(0, h - 1, size=(n, k))
+    rcv[:, :, 1] = rng.uniform(0, w - 1, size=(n, k))
+    rcv[:, :, 2] = (rng.uniform(size=(n, k)) < 0.8)
+    rcv[0, 0] = [0.0, 0.0, 1.0]
+    rcv[0, 1] = [h - 1, w - 1, 1.0]
+    rd = torch.from_numpy(rcv).cuda()
+    out = SplitTensor(n, h, w, 192)
+    out.buf.fill_(3.0)                                   # every element is written, pad channels included
+    ctx().pose_patch(ptr(rd), n, k, h, w, 4, 3, 3, out.ref(), stream())
+    torch.cuda.synchronize()
+    maps = T.pose_rasterize(torch.from_numpy(rcv).double(), h, w)            # [n,h,w,18] in {-1,+1}
+    pad = torch.nn.functional.pad(maps, (0, 0, 1, 1, 1, 1))                   # zero padding = the conv's SAME padding
+    ref = torch.cat([pad[:, i:i + h, j:j + w, :] for i in range(3) for j in range(3)], dim=-1)
+    assert torch.equal(out.hi.float().cpu()[..., :162].double(), ref)
+    assert float(out.hi.float().abs().cpu()[..., 162:].max()) == 0.0 and float(out.lo.float().abs().max()) == 0.0
 
 
 def test_linear():
