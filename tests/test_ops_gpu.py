@@ -500,6 +500,47 @@ def test_pose_patch_matches_rasterised_maps():
     assert float(out.hi.float().abs().cpu()[..., 162:].max()) == 0.0 and float(out.lo.float().abs().max()) == 0.0
 
 
+def test_kernels_match_tf_known_answers():
+    """The CUDA kernels against TensorFlow's own unit-test vectors (tests/golden/tf_known_answers.py: conv_ops_test SAME
+    cases incl. the bottom/right-padded stride-3 one, crop_and_resize_op_test bilinear cases).  Small integers: exact."""
+    import ctypes as C
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    import tf_known_answers as KA
+    _lib, SplitTensor, ptr, split_ref = _imports()
+    for case in KA.CONV2D:
+        name, _, _, stride, padding, expected = case
+        if padding != "SAME" or stride > 2:        # the kernels implement SAME, stride 1 / 2 (all the reference uses)
+            continue
+        x, w = KA.conv2d_inputs(case)
+        xs = padded_split(torch.tensor(x, dtype=torch.float32))
+        wt = torch.zeros((w.shape[0], w.shape[1], xs.c, w.shape[3]))
+        wt[:, :, :w.shape[2], :] = torch.tensor(w, dtype=torch.float32)
+        f, _ = pack_weights(wt.cuda().contiguous(), cin_pad=xs.c)
+        n, h, wd, _ = x.shape
+        oh, ow, co = -(-h // stride), -(-wd // stride), w.shape[3]
+        out32 = torch.zeros((n, oh, ow, co), device="cuda")
+        ep = _lib.ConvEpilogue()
+        ep.act = 0
+        ep.out_f32 = out32.data_ptr()
+        ep.out_f32_pix_stride = co
+        ep.upsample = 1
+        ctx().conv2d_fwd(xs.ref(), ptr(f[0]), ptr(f[1]), w.shape[0], w.shape[1], stride, co, C.byref(ep), stream())
+        torch.cuda.synchronize()
+        assert out32.cpu().reshape(-1).tolist() == expected, name
+    for name, img, boxes, ind, crop, ev, expected in KA.CROP_AND_RESIZE:
+        image = torch.tensor(img, dtype=torch.float32)[None, :, :, None].repeat(1, 1, 1, 8)     # 8 identical channels
+        ims = SplitTensor.from_float(image.cuda())
+        bd = torch.tensor(boxes, dtype=torch.float32).cuda()
+        idd = torch.tensor(ind, dtype=torch.int32).cuda()
+        out = SplitTensor(len(boxes), crop[0], crop[1], 8, zero=True)
+        ctx().crop_and_resize_fwd(ims.ref(), None, ptr(bd), ptr(idd), len(boxes), out.ref(), stream())
+        torch.cuda.synchronize()
+        got = out.float().cpu()
+        want = torch.tensor(expected, dtype=torch.float32)
+        for ch in (0, 7):
+            assert torch.allclose(got[..., ch], want, atol=1e-6, rtol=0), (name, got[..., ch])
+
+
 def test_linear():
     _lib, SplitTensor, ptr, _ = _imports()
     g = torch.Generator().manual_seed(5)
