@@ -65,8 +65,9 @@ def build_parser():
     # additions of this implementation (not in the reference)
     misc.add_argument("--gan_mode", type=str, default="dcgan", choices=["dcgan", "wgan", "wgan-gp", "lsgan"],
                       help="loss / critic-norm mode of wgan_gp.WGAN_GP (the shipped Stage-I trainer hard-codes dcgan)")
-    misc.add_argument("--synthetic_data", type=str2bool, default=True,
-                      help="true: synthetic batches (no dataset ships here); false: read the TFRecord pair files under <data_dir>/<dataset> (datasets.py)")
+    misc.add_argument("--synthetic_data", type=str2bool, default=None,
+                      help="unset: read the TFRecord pair files under <data_dir>/<dataset> when they exist, else synthetic batches "
+                           "with a warning; true / false force either (datasets.py, trainer.make_loader)")
     return p
 
 

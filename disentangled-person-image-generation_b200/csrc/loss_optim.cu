@@ -1,6 +1,7 @@
 // Losses and optimisers of the Stage-I/II trainers, restating the TensorFlow-1.4 formulas the reference
 // calls:  L1 reconstruction (trainer.py:606-607, 622), GAN losses incl. the WGAN-GP interpolation and
 // penalty (trainer.py:217-252), Adam / RMSProp(+clip) (trainer.py:116-149).  All HBM-bound fp32.
+#include <algorithm>
 #include "common.cuh"
 
 namespace dpig {
@@ -233,48 +234,55 @@ __global__ void pose_raster_kernel(const float* rcv, int N, int K, int H, int W,
 // map_k(y + i - pt, x + j - pl), 0 outside the image (the conv's zero padding) and in the pad channels.  The U-Net stem
 // reads the pose channels in this patch form (one 1x1 contraction over K = 9*18 instead of nine 64-deep K chunks of
 // 18 channels); building the patches from the 18 keypoints costs no read of the maps at all.
-// thread = (pixel, tap): the 18 keypoints of one neighbour pixel -> K bf16 values per plane, 4-byte stores (a tap's K
-// channels start at byte tap*2K: 4-byte aligned for even K).  No per-element index arithmetic: the first version
-// (thread = 8 patch channels, c / K and c % K per element) was instruction-bound at 0.5 ms per call.
-__global__ void pose_patch_kernel(const float* rcv, int N, int K, int H, int W, int radius, int kh, int kw, int pt,
-                                  int pl, __nv_bfloat16* ohi, __nv_bfloat16* olo, long long ops, int Cp) {
-  const int taps = kh * kw;
-  const int tail = Cp - taps * K;                      // pad channels, zeroed by the last tap's thread
-  const long long total = static_cast<long long>(N) * H * W * taps;
-  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
-       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int tap = static_cast<int>(idx % taps);
-    const long long pix = idx / taps;
-    const int x = static_cast<int>(pix % W);
-    const int y = static_cast<int>((pix / W) % H);
-    const int n = static_cast<int>(pix / (static_cast<long long>(W) * H));
-    const int yy = y + tap / kw - pt, xx = x + tap % kw - pl;
-    const bool in_img = yy >= 0 && yy < H && xx >= 0 && xx < W;
-    const float* q = rcv + static_cast<long long>(n) * K * 3;
-    uint32_t* oh = reinterpret_cast<uint32_t*>(ohi + pix * ops + tap * K);
-    uint32_t* ol = olo ? reinterpret_cast<uint32_t*>(olo + pix * ops + tap * K) : nullptr;
-    for (int k = 0; k < K; k += 2) {
-      uint32_t hw = 0, lw = 0;
+// thread = (pixel, 8 patch channels): one 16-byte store per plane, consecutive lanes write consecutive 16-byte pieces
+// (a pixel's patch row is 24 pieces).  K and the tap grid are compile-time constants so that c / K, c % K, tap / KW cost a
+// multiply-shift: with run-time divisors this kernel was instruction-bound (0.5 ms per call), and a (pixel, tap) thread
+// layout with 4-byte stores at a 36-byte stride was bound by its 8x store-sector amplification (0.57 ms).
+// The (row, col, visible) triples of the image's keypoints are decoded once per block into shared memory.
+template <int K, int KH, int KW>
+__global__ void __launch_bounds__(256)
+pose_patch_kernel(const float* rcv, int N, int H, int W, int radius, int pt, int pl, __nv_bfloat16* ohi,
+                  __nv_bfloat16* olo, long long ops, int Cp, int blocks_per_image) {
+  __shared__ int s_r[K], s_c[K];
+  __shared__ float s_v[K];
+  const int n = blockIdx.x / blocks_per_image;
+  if (threadIdx.x < K) {
+    const float* q = rcv + (static_cast<long long>(n) * K + threadIdx.x) * 3;
+    s_r[threadIdx.x] = static_cast<int>(q[0]);     // tf.to_int32 truncates
+    s_c[threadIdx.x] = static_cast<int>(q[1]);
+    s_v[threadIdx.x] = fminf(q[2], 1.f) * 2.f - 1.f;
+  }
+  __syncthreads();
+  const int G8 = Cp / 8;
+  const int r2 = radius * radius;
+  const int items = H * W * G8;
+  for (int it = (blockIdx.x % blocks_per_image) * blockDim.x + threadIdx.x; it < items;
+       it += blocks_per_image * blockDim.x) {
+    const int g = it % G8;
+    const int pin = it / G8;
+    const int x = pin % W, y = pin / W;
+    uint32_t h[4] = {0, 0, 0, 0}, l[4] = {0, 0, 0, 0};
 #pragma unroll
-      for (int e = 0; e < 2; ++e) {
-        if (in_img && k + e < K) {
-          const float* qq = q + (k + e) * 3;
-          const int dr = yy - static_cast<int>(__ldg(qq)), dc = xx - static_cast<int>(__ldg(qq + 1));
-          const bool inside = (dr * dr + dc * dc <= radius * radius);
-          const float v = (inside ? fminf(__ldg(qq + 2), 1.f) : 0.f) * 2.f - 1.f;     // as pose_raster_kernel
+    for (int e = 0; e < 8; ++e) {
+      const int c = g * 8 + e;
+      uint16_t hv = 0, lv = 0;
+      if (c < KH * KW * K) {
+        const int tap = c / K, k = c % K;
+        const int yy = y + tap / KW - pt, xx = x + tap % KW - pl;
+        if (yy >= 0 && yy < H && xx >= 0 && xx < W) {
+          const int dr = yy - s_r[k], dc = xx - s_c[k];
+          const float v = (dr * dr + dc * dc <= r2) ? s_v[k] : -1.f;           // as pose_raster_kernel
           const __nv_bfloat16 hb = __float2bfloat16_rn(v);
-          hw |= static_cast<uint32_t>(__bfloat16_as_ushort(hb)) << (16 * e);
-          lw |= static_cast<uint32_t>(__bfloat16_as_ushort(__float2bfloat16_rn(v - __bfloat162float(hb)))) << (16 * e);
+          hv = __bfloat16_as_ushort(hb);
+          lv = __bfloat16_as_ushort(__float2bfloat16_rn(v - __bfloat162float(hb)));
         }
       }
-      oh[k >> 1] = hw;
-      if (ol) ol[k >> 1] = lw;
+      h[e >> 1] |= static_cast<uint32_t>(hv) << ((e & 1) * 16);
+      l[e >> 1] |= static_cast<uint32_t>(lv) << ((e & 1) * 16);
     }
-    if (tap == taps - 1)
-      for (int t = 0; t < tail; t += 2) {
-        oh[(K + t) >> 1] = 0u;
-        if (ol) ol[(K + t) >> 1] = 0u;
-      }
+    const long long o = (static_cast<long long>(n) * H * W + pin) * ops + g * 8;
+    *reinterpret_cast<uint4*>(ohi + o) = make_uint4(h[0], h[1], h[2], h[3]);
+    if (olo) *reinterpret_cast<uint4*>(olo + o) = make_uint4(l[0], l[1], l[2], l[3]);
   }
 }
 
@@ -419,15 +427,20 @@ extern "C" int dpig_pose_patch(dpig_ctx* ctx, const float* rcv, int32_t n, int32
                                int32_t radius, int32_t kh, int32_t kw, const dpig_tensor* out, dpig_stream stream) {
   DPIG_CHECK_CTX(ctx);
   if (!rcv || !out || !out->hi) return set_error(ctx, DPIG_EINVAL, "pose_patch: null argument");
-  if (k % 2) return set_error(ctx, DPIG_EUNSUPPORTED, "pose_patch: an even number of keypoint channels is required");
+  if (k != 18 || kh != 3 || kw != 3)
+    return set_error(ctx, DPIG_EUNSUPPORTED, "pose_patch: built for the reference's 18 keypoints under a 3x3 stem (got %d, %dx%d)",
+                     k, kh, kw);
   if (out->n != n || out->h != h || out->w != w_ || out->c < kh * kw * k || out->c % 8 || out->pix_stride % 8 ||
       reinterpret_cast<uintptr_t>(out->hi) % 16 || (out->lo && reinterpret_cast<uintptr_t>(out->lo) % 16))
     return set_error(ctx, DPIG_EINVAL, "pose_patch: output must be [%d,%d,%d,>=%d] with channels / stride multiples of 8",
                      n, h, w_, kh * kw * k);
-  const long long total = static_cast<long long>(n) * h * w_ * kh * kw;
-  pose_patch_kernel<<<gridn(total), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      rcv, n, k, h, w_, radius, kh, kw, same_pad_before(h, kh, 1), same_pad_before(w_, kw, 1),
-      static_cast<__nv_bfloat16*>(out->hi), static_cast<__nv_bfloat16*>(out->lo), out->pix_stride, out->c);
+  const long long items = static_cast<long long>(h) * w_ * (out->c / 8);
+  int bpi = static_cast<int>((items + 255) / 256);
+  const int cap = std::max(1, 148 * 16 / std::max(1, n));    // grid ~ a few waves of the 148 SMs
+  if (bpi > cap) bpi = cap;
+  pose_patch_kernel<18, 3, 3><<<n * bpi, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      rcv, n, h, w_, radius, same_pad_before(h, kh, 1), same_pad_before(w_, kw, 1),
+      static_cast<__nv_bfloat16*>(out->hi), static_cast<__nv_bfloat16*>(out->lo), out->pix_stride, out->c, bpi);
   ctx->launches++;
   return check_launch(ctx, "pose_patch");
 }

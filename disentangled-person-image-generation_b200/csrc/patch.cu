@@ -17,9 +17,14 @@ namespace dpig {
 
 // out[n, oy, ox, (i*kw + j)*cs + c] = src[n, oy*s + i - pt, ox*s + j - pl, c]   (transposed: y - (i - pt), x - (j - pl))
 // One thread per (pixel, group of 8 output channels): 16-byte stores per plane.
+// CS / KW > 0: compile-time source channel count / filter width (k / cs, tap / kw become multiply-shifts; with run-time
+// divisors the kernel is bound by its ~16 integer divisions per thread, not by memory).
+template <int CS, int KW>
 __global__ void im2col_small_kernel(const __nv_bfloat16* shi, const __nv_bfloat16* slo, long long sps, int N, int H,
-                                    int W, int cs, int kh, int kw, int stride, int pt, int pl, int transposed, int OH,
+                                    int W, int cs_rt, int kh, int kw_rt, int stride, int pt, int pl, int transposed, int OH,
                                     int OW, __nv_bfloat16* ohi, __nv_bfloat16* olo, long long ops, int Kp) {
+  const int cs = CS > 0 ? CS : cs_rt;
+  const int kw = KW > 0 ? KW : kw_rt;
   const int K8 = Kp / 8;
   const int kvalid = kh * kw * cs;
   const long long total = static_cast<long long>(N) * OH * OW * K8;
@@ -131,10 +136,15 @@ extern "C" int dpig_im2col_small(dpig_ctx* ctx, const dpig_tensor* src, int32_t 
     return set_error(ctx, DPIG_EINVAL, "im2col_small: output is not [%d,%d,%d,.]", src->n, OH, OW);
   const int pt = same_pad_before(src->h, kh, stride), pl = same_pad_before(src->w, kw, stride);
   const long long total = static_cast<long long>(out->n) * OH * OW * (out->c / 8);
-  im2col_small_kernel<<<grid_for(total), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const __nv_bfloat16*>(src->hi), static_cast<const __nv_bfloat16*>(src->lo), src->pix_stride, src->n,
-      src->h, src->w, c_src, kh, kw, stride, pt, pl, transposed, OH, OW, static_cast<__nv_bfloat16*>(out->hi),
-      static_cast<__nv_bfloat16*>(out->lo), out->pix_stride, out->c);
+  auto launch = [&](auto kern) {
+    kern<<<grid_for(total), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const __nv_bfloat16*>(src->hi), static_cast<const __nv_bfloat16*>(src->lo), src->pix_stride, src->n,
+        src->h, src->w, c_src, kh, kw, stride, pt, pl, transposed, OH, OW, static_cast<__nv_bfloat16*>(out->hi),
+        static_cast<__nv_bfloat16*>(out->lo), out->pix_stride, out->c);
+  };
+  if (c_src == 3 && kw == 3) launch(im2col_small_kernel<3, 3>);        // the image under the 3x3 stems / output conv
+  else if (c_src == 3 && kw == 5) launch(im2col_small_kernel<3, 5>);   // the image under the critic's 5x5 first layer
+  else launch(im2col_small_kernel<0, 0>);
   ctx->launches++;
   return check_launch(ctx, "im2col_small");
 }

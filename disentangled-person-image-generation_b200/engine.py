@@ -540,6 +540,9 @@ class Stage1Engine:
             if not rms:
                 out["beta1_power" + suffix] = np.float32(0.5 ** (self.t[which] + 1))
                 out["beta2_power" + suffix] = np.float32(b2 ** (self.t[which] + 1))
+            # the float32 beta powers underflow (0.999^t at t ~ 104k, 0.5^t at t ~ 150): the step counter itself travels
+            # too, under a name no TensorFlow graph reads (a reference restore ignores it)
+            out["dpig_step_count" + suffix] = np.int64(self.t[which])
         for i in (2, 3, 4):
             c = self.cfg.d_dim << (i - 1)
             out["Discriminator.BN%d.moving_mean" % i] = np.zeros(c, np.float32)
@@ -561,9 +564,26 @@ class Stage1Engine:
                         if name == "Discriminator.Output.W":
                             t = t.reshape(-1)[self._dperm].reshape(-1, 1)
                         arena[off:off + n].view(shape).copy_(t.reshape(shape))
-            key = "beta2_power" + suffix
-            if not rms and key in state and 0.0 < float(state[key]) < 1.0:
-                self.t[which] = max(0, int(round(math.log(float(state[key])) / math.log(b2))) - 1)
+            self.t[which] = self._restored_step_count(state, suffix, b2, rms, self.t[which])
+
+    @staticmethod
+    def _restored_step_count(state, suffix, b2, rms, default):
+        """Adam's t of a restored optimiser: the explicit counter when this implementation wrote the checkpoint, else
+        recovered from TensorFlow's beta-power accumulators in float64 (beta2_power = b2^(t+1) while it has not
+        underflowed in float32, then beta1_power); powers that have underflowed to 0 mean t is so large that the bias
+        correction is 1 to float32 precision, which any large t reproduces."""
+        if "dpig_step_count" + suffix in state:
+            return int(np.asarray(state["dpig_step_count" + suffix]))
+        if rms:
+            return default
+        for key, base in (("beta2_power" + suffix, b2), ("beta1_power" + suffix, 0.5)):
+            if key in state:
+                v = float(np.asarray(state[key], dtype=np.float64))
+                if 0.0 < v < 1.0:
+                    return max(0, int(round(math.log(v) / math.log(float(base)))) - 1)
+                if v == 0.0:
+                    return 1 << 24
+        return default
 
     def pack_weights(self, which, stream=None):
         s = stream if stream is not None else torch.cuda.current_stream().cuda_stream

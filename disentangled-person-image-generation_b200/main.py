@@ -32,7 +32,16 @@ def main(config):
     cls = getattr(T256, name, None) or getattr(T, name, None) or getattr(TS, name, None) or getattr(TE, name, None)   # main.py:4-6 import order (q9)
     if cls is None:
         raise NotImplementedError("--model=%d (%s) is outside this round's hot path (SURVEY.md §8f)" % (config.model, name))
-    trainer = cls(config)
+    # one process per GPU under torchrun (WORLD_SIZE > 1): data-parallel hooks for the trainers that take them
+    dist = None
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        import inspect
+        if "dist" in inspect.signature(cls.__init__).parameters:
+            from . import ddp
+            dist = ddp.Dist()
+    trainer = cls(config, dist=dist) if dist is not None else cls(config)
+    if getattr(config, "model_dir", None) and os.path.isdir(config.model_dir) and (dist is None or dist.rank == 0):
+        save_config(config)         # again: now with synthetic_data_effective (which loader the run really uses)
     trainer.init_net()
     if config.is_train:
         trainer.train()

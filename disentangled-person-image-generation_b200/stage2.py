@@ -326,6 +326,29 @@ class PoseAE:
         return OrderedDict((n, (self.group.gview(n) if grads else self.group.view(n)).detach().cpu().numpy().copy())
                            for n in self.group.specs)
 
+    def get_state(self):
+        """Variables + Adam slots (`<var>/Adam`, `<var>/Adam_1`) + step counter of the --model=2 optimiser."""
+        out = self.get_params()
+        g = self.group
+        for name, (off, n, shape) in g.specs.items():
+            out[name + "/Adam"] = g.m[off:off + n].view(shape).detach().cpu().numpy().copy()
+            out[name + "/Adam_1"] = g.v[off:off + n].view(shape).detach().cpu().numpy().copy()
+        out["beta1_power"] = np.float32(0.5 ** (self.t + 1))
+        out["beta2_power"] = np.float32(0.999 ** (self.t + 1))
+        out["dpig_step_count"] = np.int64(self.t)
+        return out
+
+    def load_state(self, state):
+        from .engine import Stage1Engine
+        self.load_params(state)
+        g = self.group
+        for name, (off, n, shape) in g.specs.items():
+            for slot, arena in (("/Adam", g.m), ("/Adam_1", g.v)):
+                if name + slot in state:
+                    arena[off:off + n].view(shape).copy_(torch.as_tensor(np.asarray(state[name + slot]),
+                                                                         dtype=torch.float32).to(arena.device).reshape(shape))
+        self.t = Stage1Engine._restored_step_count(state, "", 0.999, False, self.t)
+
     @staticmethod
     def normalise(pose_rcv, img_h, img_w):
         """(row, col, visible) pixels -> [-1,1] x [-1,1] x {0,1} (trainer.py:639-644)."""
@@ -401,6 +424,37 @@ class Stage2Engine:
             for name in grp.specs:
                 out[name] = (grp.gview(name) if grads else grp.view(name)).detach().cpu().numpy().copy()
         return out
+
+    def get_state(self):
+        """Variables plus the optimiser slots under TensorFlow's slot names (`<var>/RMSProp` for the shipped wgan mode,
+        `<var>/Adam`, `<var>/Adam_1` otherwise) and the per-factor step counters: what a --ckpt_path resume needs
+        (tf.train.Saver() covers the slots, trainer.py:177-179)."""
+        out = self.get_params()
+        rms = self.mode in ("wgan", "lsgan")
+        for fname, f in self.f.items():
+            for which, grp in (("g", f.gp), ("d", f.dp)):
+                for name, (off, n, shape) in grp.specs.items():
+                    if rms:
+                        out[name + "/RMSProp"] = grp.v[off:off + n].view(shape).detach().cpu().numpy().copy()
+                    else:
+                        out[name + "/Adam"] = grp.m[off:off + n].view(shape).detach().cpu().numpy().copy()
+                        out[name + "/Adam_1"] = grp.v[off:off + n].view(shape).detach().cpu().numpy().copy()
+                out["dpig_step_count/%s/%s" % (fname, which)] = np.int64(f.t[which])
+        return out
+
+    def load_state(self, state):
+        self.load_params(state)
+        rms = self.mode in ("wgan", "lsgan")
+        for fname, f in self.f.items():
+            for which, grp in (("g", f.gp), ("d", f.dp)):
+                for name, (off, n, shape) in grp.specs.items():
+                    for slot, arena in ((("/RMSProp", grp.v),) if rms else (("/Adam", grp.m), ("/Adam_1", grp.v))):
+                        if name + slot in state:
+                            arena[off:off + n].view(shape).copy_(torch.as_tensor(
+                                np.asarray(state[name + slot]), dtype=torch.float32).to(arena.device).reshape(shape))
+                key = "dpig_step_count/%s/%s" % (fname, which)
+                if key in state:
+                    f.t[which] = int(np.asarray(state[key]))
 
     def sample_noise(self, factor, z=None):
         f = self.f[factor]

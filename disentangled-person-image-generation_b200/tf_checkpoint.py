@@ -263,12 +263,13 @@ def read_table(path, verify=True):
 
 
 class _BlockBuilder:
-    def __init__(self):
+    def __init__(self, restart_interval=None):
         self.buf, self.restarts, self.count, self.last = bytearray(), [0], 0, b""
+        self.interval = restart_interval or _RESTART_INTERVAL
 
     def add(self, key, value):
         shared = 0
-        if self.count < _RESTART_INTERVAL:
+        if self.count < self.interval:
             m = min(len(key), len(self.last))
             while shared < m and key[shared] == self.last[shared]:
                 shared += 1
@@ -315,7 +316,7 @@ def _short_successor(a):
 def write_table(path, items):
     """items: (key bytes, value bytes) sorted by key.  Uncompressed blocks, like TensorFlow's BundleWriter."""
     out = bytearray()
-    index = _BlockBuilder()
+    index = _BlockBuilder(restart_interval=1)    # TensorFlow's table builder: index_block(index_block_restart_interval = 1)
     pending = None   # (last key of the finished block, handle)
 
     def emit(block_bytes):

@@ -36,22 +36,45 @@ class SyntheticLoader:
         return synth.make_batch(self.batch_size, self.img_h, self.img_w, seed=self.seed + self.i)
 
 
-def make_loader(config, batch_size, img_h, img_w):
-    """trainer.py:35-42 / 1049-1055: dataset name -> market1501 / deepfashion get_split('train' | 'test', data_path) with
-    data_path = <data_dir>/<dataset> (utils.py:136).  `--synthetic_data=true` (default here: no dataset ships) draws
-    synthetic batches of the same shapes instead."""
-    if getattr(config, "synthetic_data", True):
-        return SyntheticLoader(batch_size, img_h, img_w, config.random_seed)
-    name = config.dataset.lower()
-    if "market" in name:
-        data_name = "Market1501"
-    elif "deepfashion" in name or "df" in name:
-        data_name = "DeepFashion"
-    else:
-        raise Exception("dataset %r: expected a Market-1501 or DeepFashion TFRecord directory" % config.dataset)
+def _dataset_files(config):
+    """(data_name, data_path, TFRecord files of the active split) for `--dataset`, or (None, data_path, [])."""
+    import glob
+    name = (config.dataset or "").lower()
+    data_name = "Market1501" if "market" in name else ("DeepFashion" if ("deepfashion" in name or "df" in name) else None)
     data_path = getattr(config, "data_path", None) or os.path.join(config.data_dir, config.dataset)
+    if data_name is None:
+        return None, data_path, []
+    split = "train" if config.is_train else "test"
+    return data_name, data_path, sorted(glob.glob(os.path.join(data_path, "%s_%s_*.tfrecord" % (data_name, split))))
+
+
+def make_loader(config, batch_size, img_h, img_w, rank=0, world=1):
+    """trainer.py:35-42 / 1049-1055: dataset name -> market1501 / deepfashion get_split('train' | 'test', data_path) with
+    data_path = <data_dir>/<dataset> (utils.py:136).
+    `--synthetic_data` unset (the default): the reference's TFRecords are read when they exist under data_path -- the
+    run_market_*.sh command lines then train on the dataset, as they do in the reference -- and synthetic batches of the
+    same shapes are drawn, with a loud warning, only when no record file is there (no dataset ships with this repo).
+    `--synthetic_data=true / false` forces either; false without files raises.  The choice is recorded in
+    config.synthetic_data_effective (params.json) and in every summary line.
+    rank / world: data-parallel ranks read different data (seed offset; the record files are dealt round-robin)."""
+    data_name, data_path, files = _dataset_files(config)
+    want = getattr(config, "synthetic_data", None)
+    synthetic = (not files) if want is None else bool(want)
+    config.synthetic_data_effective = synthetic
+    if synthetic:
+        if want is None:
+            import warnings
+            warnings.warn("DPIG: no %s TFRecords under %r -- training / testing on SYNTHETIC batches (random pixels, "
+                          "synthetic keypoints); pass --data_dir / --dataset of the converted dataset, or "
+                          "--synthetic_data=true to silence this" % (data_name or config.dataset, data_path), stacklevel=2)
+        return SyntheticLoader(batch_size, img_h, img_w, config.random_seed + 7919 * rank)
+    if data_name is None:
+        raise Exception("dataset %r: expected a Market-1501 or DeepFashion TFRecord directory" % config.dataset)
+    if not files:
+        raise IOError("--synthetic_data=false but no %s_%s_*.tfrecord under %s" % (
+            data_name, "train" if config.is_train else "test", data_path))
     return datasets.get_split("train" if config.is_train else "test", data_path, data_name=data_name,
-                              batch_size=batch_size, seed=config.random_seed)
+                              batch_size=batch_size, seed=config.random_seed + 7919 * rank)
 
 
 class DPIG_Encoder_GAN_BodyROI_FgBg(object):
@@ -60,8 +83,10 @@ class DPIG_Encoder_GAN_BodyROI_FgBg(object):
         self.D_arch = config.D_arch
         self.part_num = 37
         self.keypoint_num = 18
-        self.loader = loader or make_loader(config, self.batch_size, self.img_H, self.img_W)
         self.dist = dist
+        self.loader = loader or make_loader(config, self.batch_size, self.img_H, self.img_W,
+                                            rank=dist.rank if dist is not None else 0,
+                                            world=dist.world_size if dist is not None else 1)
         self.net = None
 
     def _common_init(self, config):
@@ -102,7 +127,14 @@ class DPIG_Encoder_GAN_BodyROI_FgBg(object):
         if self.pretrained_path:
             self.net.load_params(tf_checkpoint.load_any(self.pretrained_path, scopes=["Encoder", "ID_AE"]))
         if self.ckpt_path:
-            self.net.load_state(tf_checkpoint.load_any(self.ckpt_path))
+            state = tf_checkpoint.load_any(self.ckpt_path)
+            self.net.load_state(state)
+            # the learning rates are tf.Variables of the reference graph (trainer.py:55-59) and come back with the
+            # checkpoint: a run resumed after an lr halving continues at the halved rate
+            for name in ("g_lr", "d_lr"):
+                if name in state:
+                    setattr(self, name, float(np.asarray(state[name])))
+                    setattr(self.net, name, float(np.asarray(state[name])))
         self._log = open(os.path.join(self.model_dir, "summary.jsonl"), "a")
 
     # ------------------------------------------------------------------ train
@@ -114,6 +146,16 @@ class DPIG_Encoder_GAN_BodyROI_FgBg(object):
         net = self.net
         disc_iters = 1 if self.gan_mode in ("dcgan", "lsgan") else 5   # wgan_gp.CRITIC_ITERS = 5 (wgan_gp.py:113)
         t0 = time.time()
+        # trainer.py:327-334: one fixed batch for the periodic previews, its inputs saved as sample sheets once
+        period = self.log_step * 3
+        first = self.start_step + ((period - 1 - self.start_step) % period)       # first step with step % period == period-1
+        previews = self.max_step > self.start_step and (self.start_step == 0 or first < self.max_step)
+        fixed = None
+        if previews and (self.dist is None or self.dist.rank == 0):
+            fixed = self.loader.next_batch()
+            outputs.save_image((np.asarray(fixed["x"]) + 1.0) * 127.5, os.path.join(self.model_dir, "x_fixed.png"))
+            outputs.save_image(np.asarray(fixed["mask"]) * 255.0, os.path.join(self.model_dir, "mask_fixed.png"))
+            outputs.save_image(self._pose_max_img(fixed["pose_rcv"])[..., None], os.path.join(self.model_dir, "pose_fixed.png"))
         for step in range(self.start_step, self.max_step):
             if step > 0:
                 net.set_batch(self.loader.next_batch())
@@ -127,10 +169,15 @@ class DPIG_Encoder_GAN_BodyROI_FgBg(object):
                 net.set_batch(self.loader.next_batch())
                 net.forward(with_disc=True)
                 g_gan, d_loss, l1 = net.losses()
-                rec = {"step": step, "loss/L1Loss": l1, "loss/g_loss_only": g_gan, "loss/g_loss": g_gan + 20.0 * l1,
+                rec = {"step": step, "synthetic_data": bool(getattr(self.config, "synthetic_data_effective", False)),
+                       "loss/L1Loss": l1, "loss/g_loss_only": g_gan, "loss/g_loss": g_gan + 20.0 * l1,
                        "loss/d_loss": d_loss, "misc/g_lr": net.g_lr, "misc/d_lr": net.d_lr, "wall_s": time.time() - t0}
                 self._log.write(json.dumps(rec) + "\n")
                 self._log.flush()
+            if fixed is not None and (step == 0 or step % (self.log_step * 3) == (self.log_step * 3) - 1):
+                # trainer.py:356-359: generate() on the fixed batch -> <model_dir>/<step>_G_ssim<mean>.png
+                self.generate(fixed["x"], fixed.get("x_target", fixed["x"]), fixed["pose_rcv"], fixed["part_bbox"],
+                              fixed["part_vis"], self.model_dir, idx=step, save=True, mask=fixed["mask"])
             if step % self.lr_update_step == self.lr_update_step - 1:
                 net.g_lr *= 0.5
                 net.d_lr *= 0.5
@@ -141,16 +188,21 @@ class DPIG_Encoder_GAN_BodyROI_FgBg(object):
     def save(self, step):
         """saver.save(sess, model_dir/model.ckpt, global_step=step) (trainer.py:365-366): a TensorFlow V2 checkpoint
         (model.ckpt-<step>.index / .data-00000-of-00001 + the `checkpoint` state file) readable by the reference."""
+        if self.dist is not None and self.dist.rank != 0:      # every rank holds the same weights: rank 0 writes
+            return None
         state = self.net.get_state()
         state["step"] = np.int32(step)
         state["g_lr"], state["d_lr"] = np.float32(self.net.g_lr), np.float32(self.net.d_lr)
+        state["phase"] = np.bool_(self.is_train)               # tf.Variable(self.is_train, name='phase') of _define_input
         return tf_checkpoint.save_checkpoint(os.path.join(self.model_dir, "model.ckpt-%d" % step), state)
 
     # ------------------------------------------------------------------ inference
     def generate(self, x, x_target, pose, part_bbox, part_vis, root_path=None, path=None, idx=None, save=False,
                  mask=None):
         """Reference generate() (trainer.py:498-526): returns the generated images as NHWC numpy in [0,255].
-        Unlike the reference (quirk q3) the matching foreground mask is fed when given."""
+        Unlike the reference (quirk q3) the matching foreground mask is fed when given.  `pose` is the KEYPOINT array
+        pose_rcv [B,18,3] (row, col, visible): the reference feeds the ready 18-channel maps; here they are rasterised
+        and inflated on the device (dpig_pose_rasterize), so the argument is one step earlier in the same pipeline."""
         B = x.shape[0]
         if mask is None:
             mask = np.ones((B, self.img_H, self.img_W, 1), np.float32)
@@ -171,12 +223,42 @@ class DPIG_Encoder_GAN_BodyROI_FgBg(object):
             outputs.save_image(G, path or os.path.join(root_path, "%s_G_ssim%s.png" % (idx, float(self.last_ssim.mean()))))
         return G
 
-    def test(self):
-        """Reconstruction pass over the loader (tester-style): writes G as .npy batches under model_dir/test_result."""
+    def _pose_max_img(self, pose_rcv):
+        """(amax over the 18 inflated keypoint maps + 1) * 127.5 (trainer.py:401-402) for a [B,18,3] keypoint array."""
+        B = self.batch_size
+        rcv = torch.as_tensor(np.asarray(pose_rcv, np.float32)).to(self.net.device)
+        maps = torch.empty((B, self.img_H, self.img_W, self.keypoint_num), dtype=torch.float32, device=self.net.device)
+        self.ctx.pose_rasterize(ptr(rcv), B, self.keypoint_num, self.img_H, self.img_W, 4, None, ptr(maps),
+                                torch.cuda.current_stream().cuda_stream)
+        return ((maps.amax(dim=-1) + 1.0) * 127.5).cpu().numpy()
+
+    def test(self, num_batches=100):
+        """Reference test() (trainer.py:368-427): 100 batches through generate(); per-sample PNGs under
+        <model_dir>/test_result/{x, x_target, G, pose, pose_target, mask, mask_target}/%05d.png -- the directories
+        score.py reads (score.py:33-36) -- plus the sample sheets of the first batch.  PNG encoding is batched over host
+        threads (outputs.ResultWriter)."""
         out_dir = os.path.join(self.model_dir, self.test_dir_name)
-        os.makedirs(out_dir, exist_ok=True)
-        for i in range(4):
+        wr = outputs.ResultWriter(out_dir)
+        B = self.batch_size
+        for i in range(num_batches):
             b = self.loader.next_batch()
-            g = self.generate(b["x"], b["x"], b["pose_rcv"], b["part_bbox"], b["part_vis"], mask=b["mask"])
-            np.save(os.path.join(out_dir, "G_%05d.npy" % i), g)
+            xt = b.get("x_target", b["x"])
+            G = self.generate(b["x"], xt, b["pose_rcv"], b["part_bbox"], b["part_vis"], out_dir, idx=self.start_step,
+                              save=(i == 0), mask=b["mask"])
+            x255, xt255 = (np.asarray(b["x"]) + 1.0) * 127.5, (np.asarray(xt) + 1.0) * 127.5
+            mask, maskt = np.asarray(b["mask"]) * 255.0, np.asarray(b.get("mask_target", b["mask"])) * 255.0
+            p, pt = self._pose_max_img(b["pose_rcv"]), self._pose_max_img(b.get("pose_rcv_target", b["pose_rcv"]))
+            for j in range(B):
+                idx = i * B + j
+                for d, arr in (("x", x255[j]), ("x_target", xt255[j]), ("G", G[j]), ("pose", p[j]), ("pose_target", pt[j]),
+                               ("mask", np.squeeze(mask[j])), ("mask_target", np.squeeze(maskt[j]))):
+                    wr._submit(arr, "%s/%s/%05d.png" % (out_dir, d, idx))
+            if i == 0:
+                wr.add_grid(x255, "x_fixed.png")
+                wr.add_grid(xt255, "x_target_fixed.png")
+                wr.add_grid(mask, "mask_fixed.png")
+                wr.add_grid(maskt, "mask_target_fixed.png")
+                wr.add_grid(p[..., None], "pose_fixed.png")
+                wr.add_grid(pt[..., None], "pose_target_fixed.png")
+        self.files_written = wr.close()
         return out_dir

@@ -35,10 +35,24 @@ def _load_npz(paths):
     return out
 
 
-def _save(model_dir, step, tensors):
+def _save(model_dir, step, tensors, trainer=None):
+    """model.ckpt-<step> with everything the reference's full tf.train.Saver() writes for a resume: the variables, the
+    optimiser slots (the engines' get_state) and the step / g_lr / d_lr / phase variables of _common_init / _define_input."""
     tensors = dict(tensors)
     tensors["step"] = np.int32(step)
+    if trainer is not None:
+        if trainer.dist is not None and trainer.dist.rank != 0:
+            return None
+        tensors["g_lr"], tensors["d_lr"] = np.float32(trainer.g_lr), np.float32(trainer.d_lr)
+        tensors["phase"] = np.bool_(trainer.is_train)
     return tf_checkpoint.save_checkpoint(os.path.join(model_dir, "model.ckpt-%d" % step), tensors)
+
+
+def _restore_lr(trainer, state):
+    """--ckpt_path resume: the halved learning rates come back with the checkpoint (trainer.py:55-59, 211-213)."""
+    for name in ("g_lr", "d_lr"):
+        if name in state:
+            setattr(trainer, name, float(np.asarray(state[name])))
 
 
 class DPIG_PoseRCV_AE_BodyROI(DPIG_Encoder_GAN_BodyROI_FgBg):
@@ -52,8 +66,12 @@ class DPIG_PoseRCV_AE_BodyROI(DPIG_Encoder_GAN_BodyROI_FgBg):
         self.device = torch.device("cuda", 0)
         self.pose_ae = stage2.PoseAE(self.ctx, self.batch_size, self.device, self.keypoint_num)
         params = stage2.init_pose_ae_params(self.keypoint_num, seed=self.config.random_seed)
-        params.update({k: v for k, v in _load_npz([self.pretrained_path, self.ckpt_path]).items() if k in params})
+        params.update({k: v for k, v in _load_npz([self.pretrained_path]).items() if k in params})
         self.pose_ae.load_params(params)
+        if self.ckpt_path:        # full restore: variables, Adam slots, step counter, learning rates
+            state = tf_checkpoint.load_any(self.ckpt_path)
+            self.pose_ae.load_state(state)
+            _restore_lr(self, state)
         self._log = open(os.path.join(self.model_dir, "summary.jsonl"), "a")
 
     def _feed_pose(self, batch):
@@ -80,7 +98,7 @@ class DPIG_PoseRCV_AE_BodyROI(DPIG_Encoder_GAN_BodyROI_FgBg):
         torch.cuda.synchronize()
 
     def save(self, step):
-        return _save(self.model_dir, step, self.pose_ae.get_params())
+        return _save(self.model_dir, step, self.pose_ae.get_state(), self)
 
     def generate(self, pose_rcv):
         """Reconstructed keypoints G_pose_rcv [B,18,3] (normalised r, c and the binary visibility)."""
@@ -115,6 +133,10 @@ class DPIG_Encoder_subSampleAppNetFgBg_GAN_BodyROI(DPIG_Encoder_GAN_BodyROI_FgBg
         p2 = stage2.init_stage2_params(seed=self.config.random_seed)
         p2.update({k: v for k, v in loaded.items() if k in p2})
         self.s2.load_params(p2)
+        if self.ckpt_path:
+            state = tf_checkpoint.load_any(self.ckpt_path)
+            self.s2.load_state(state)
+            _restore_lr(self, state)
         self._log = open(os.path.join(self.model_dir, "summary.jsonl"), "a")
 
     def train(self, on_step=None):
@@ -146,8 +168,8 @@ class DPIG_Encoder_subSampleAppNetFgBg_GAN_BodyROI(DPIG_Encoder_GAN_BodyROI_FgBg
 
     def save(self, step):
         d = self.net.get_params()
-        d.update(self.s2.get_params())
-        return _save(self.model_dir, step, d)
+        d.update(self.s2.get_state())
+        return _save(self.model_dir, step, d, self)
 
     def generate(self, x, x_target, pose, part_bbox, part_vis, root_path=None, path=None, idx=None, save=False,
                  mask=None, z_fg=None, z_bg=None):
@@ -192,6 +214,9 @@ class DPIG_subnetSamplePoseRCV_GAN_BodyROI(DPIG_PoseRCV_AE_BodyROI):
         self.s2 = stage2.Stage2Engine(None, mode="wgan", g_lr=self.g_lr, d_lr=self.d_lr, factors={"pose": self.factor})
         self.s2.load_params(stage2.init_factor_params(self.factor, seed=self.config.random_seed))
         self.s2.load_params(loaded)
+        if self.ckpt_path:
+            self.s2.load_state(loaded)
+            _restore_lr(self, loaded)
         # decoder applied to the SAMPLED embedding (shares the PoseAE parameters, trainer.py:897-899)
         self.sample_dec = stage2.PoseAE(self.ctx, B, dev, self.keypoint_num, group=self.pose_ae.group, encoder=False,
                                         decoder_from=self.factor.fake)
@@ -234,8 +259,8 @@ class DPIG_subnetSamplePoseRCV_GAN_BodyROI(DPIG_PoseRCV_AE_BodyROI):
 
     def save(self, step):
         d = self.pose_ae.get_params()
-        d.update(self.s2.get_params())
-        return _save(self.model_dir, step, d)
+        d.update(self.s2.get_state())
+        return _save(self.model_dir, step, d, self)
 
     def sample_pose_rcv(self, z=None):
         """G_pose_rcv [B,18,3]: noise -> PoseGaussian -> PoseDecoderFCRes -> (r, c in [-1,1], binary visibility)."""
