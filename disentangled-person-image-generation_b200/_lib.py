@@ -48,6 +48,7 @@ _D = C.c_double
 _SIGNATURES = {
     "dpig_ctx_set_fast_mode": [C.c_int],
     "dpig_ctx_set_pair_mode": [C.c_int],
+    "dpig_ctx_set_option": [C.c_char_p, C.c_int],
     "dpig_weight_pack": [_P, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P],
     "dpig_conv2d_fwd": [_T, _P, _P, _I, _I, _I, _I, C.POINTER(ConvEpilogue), _P],
     "dpig_conv2d_bwd_data": [_T, _P, _P, _I, _I, _I, _I, _I, _I, C.POINTER(ConvEpilogue), _P],
@@ -165,6 +166,10 @@ class Context:
     def set_pair_mode(self, mode):
         """2-CTA cluster conv kernel: 0 never, 1 where it measured faster (default), 2 wherever the shape allows."""
         self.call("ctx_set_pair_mode", int(mode))
+
+    def set_option(self, name, value):
+        """Tuning switch by name (see dpig_ctx_set_option); results are identical under every setting."""
+        self.call("ctx_set_option", name.encode(), int(value))
 
     def launch_count(self):
         """Kernels launched through this context, including the kernels of replayed CUDA graphs (the library counts a

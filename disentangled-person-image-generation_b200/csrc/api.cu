@@ -62,11 +62,14 @@ extern "C" int dpig_ctx_create(int device, dpig_ctx** out) {
   if (const char* e = getenv("DPIG_DGRAD_MERGE")) ctx->dgrad_merge = atoi(e) != 0;
   if (const char* e = getenv("DPIG_EPI_TMA")) ctx->epi_tma = atoi(e) != 0;
   if (const char* e = getenv("DPIG_WGRAD_PAIR")) ctx->wgrad_pair = atoi(e) != 0;
+  if (const char* e = getenv("DPIG_WGRAD_SPLIT")) ctx->wgrad_split = atoi(e) != 0;
+  if (const char* e = getenv("DPIG_WGRAD_VEC_RED")) ctx->wgrad_vec_red = atoi(e) != 0;
   if (const char* e = getenv("DPIG_WIDE_B")) ctx->wide_b = atoi(e) != 0;
   if (const char* e = getenv("DPIG_EPI_BUFS")) ctx->epi_bufs = atoi(e);
   if (const char* e = getenv("DPIG_TUNE_SMALL")) ctx->tune_small = atoi(e);
   if (const char* e = getenv("DPIG_ADD_PREFETCH")) ctx->add_prefetch = atoi(e) != 0;
   if (const char* e = getenv("DPIG_CROP_GATHER")) ctx->crop_gather = atoi(e) != 0;
+  if (const char* e = getenv("DPIG_EPI_SPECIALISE")) ctx->epi_specialise = atoi(e) != 0;
   *out = ctx;
   return DPIG_OK;
 }
@@ -87,6 +90,30 @@ extern "C" int dpig_ctx_set_pair_mode(dpig_ctx* ctx, int mode) {
   DPIG_CHECK_CTX(ctx);
   if (mode < 0 || mode > 2) return set_error(ctx, DPIG_EINVAL, "pair mode must be 0, 1 or 2");
   ctx->pair_mode = mode;
+  return DPIG_OK;
+}
+
+// Tuning switches by name (the DPIG_* environment variables read at context creation, settable at run time: A/B
+// measurements inside one process, tests).  Results are identical under every setting.
+extern "C" int dpig_ctx_set_option(dpig_ctx* ctx, const char* name, int value) {
+  DPIG_CHECK_CTX(ctx);
+  if (!name) return set_error(ctx, DPIG_EINVAL, "set_option: null name");
+  const std::string n(name);
+  if (n == "epi_specialise") ctx->epi_specialise = value != 0;
+  else if (n == "wgrad_split") ctx->wgrad_split = value != 0;
+  else if (n == "wgrad_pair") ctx->wgrad_pair = value != 0;
+  else if (n == "wgrad_group") ctx->wgrad_group = value;
+  else if (n == "wgrad_vec_red") ctx->wgrad_vec_red = value != 0;
+  else if (n == "wide_b") ctx->wide_b = value != 0;
+  else if (n == "epi_bufs") ctx->epi_bufs = value;
+  else if (n == "epi_tma") ctx->epi_tma = value != 0;
+  else if (n == "dgrad_merge") ctx->dgrad_merge = value != 0;
+  else if (n == "add_prefetch") ctx->add_prefetch = value != 0;
+  else if (n == "tune_small") ctx->tune_small = value;
+  else if (n == "crop_gather") ctx->crop_gather = value != 0;
+  else if (n == "max_stages") ctx->max_stages = value;
+  else if (n == "merge_planes") ctx->merge_planes = value != 0;
+  else return set_error(ctx, DPIG_EINVAL, "set_option: unknown option '%s'", name);
   return DPIG_OK;
 }
 

@@ -27,8 +27,11 @@ struct dpig_ctx {
   int epi_bufs = 0;          // epilogue staging buffers per warp set: 0 auto, 1 always one, 2 two wherever two stages still fit (DPIG_EPI_BUFS)
   bool wide_b = true;        // hi|lo weight rows as one N = 2*block_n MMA operand for block_n <= 128 (DPIG_WIDE_B=0: three N = block_n MMAs)
   bool wgrad_pair = true;    // filter-gradient kernel as 2-CTA clusters (cta_group::2) where the shape allows (DPIG_WGRAD_PAIR=0: never)
+  bool wgrad_split = true;   // filter gradients of 384- / 640- / 896-wide layers as 256-wide column segments + remainder (DPIG_WGRAD_SPLIT=0: one launch)
+  bool wgrad_vec_red = true; // filter-gradient partials leave as 16-byte vector reductions (red.global.add.v4.f32) (DPIG_WGRAD_VEC_RED=0: scalar atomics)
   int wgrad_group = 0;     // filter taps per wgrad CTA: 0 = default (1); DPIG_WGRAD_GROUP
   int wgrad_px = 0;        // pixels per wgrad pipeline step: 0 = auto, 32 / 64 forced; DPIG_WGRAD_PX
+  bool epi_specialise = true;  // conv launches run on the smallest epilogue instantiation covering them (DPIG_EPI_SPECIALISE=0: generic)
   bool crop_gather = true;  // crop_and_resize image gradient in gather form (DPIG_CROP_GATHER=0: atomic scatter)
   int max_stages = 0;      // >= 2: cap on the conv smem pipeline depth (DPIG_CONV_STAGES, tuning experiments)
   unsigned long long launches = 0;

@@ -142,6 +142,32 @@ __device__ __forceinline__ void store_split32(__nv_bfloat16* hi, __nv_bfloat16* 
   }
 }
 
+// Two fp32 values -> packed bf16x2 hi word and lo word of their split representation.  cvt.rn.bf16x2.f32 (F2FP, the
+// half-rate ALU pipe) converts a pair per instruction; the per-element F2F.BF16.F32 the scalar form compiles to sits on
+// the quarter-rate conversion pipe and was 21 % of all stall samples of an epilogue-bound launch
+// (profiles/r02_epilogue_ncu.txt).  Same round-to-nearest-even values as split_bf16().
+__device__ __forceinline__ void split_pack2(float x0, float x1, uint32_t& h, uint32_t& l) {
+  const __nv_bfloat162 hb = __floats2bfloat162_rn(x0, x1);     // .x (low half) = x0
+  h = *reinterpret_cast<const uint32_t*>(&hb);
+  const float r0 = x0 - __uint_as_float(h << 16), r1 = x1 - __uint_as_float(h & 0xFFFF0000u);
+  const __nv_bfloat162 lb = __floats2bfloat162_rn(r0, r1);
+  l = *reinterpret_cast<const uint32_t*>(&lb);
+}
+
+// Epilogue feature groups a kernel instantiation carries (template parameter kF of the conv kernel).  A launch runs on
+// the smallest instantiation that covers what its epilogue asks for; features outside kF are compiled out -- their
+// code, their branches and their registers -- instead of being skipped at run time by every chunk of every tile
+// (~130 of the 686 instructions per 32-channel chunk were control flow around absent features).
+enum : int {
+  EF_FWD = 1,     // bias, per-pixel class bias, activation, sign-mask output          (forward-type)
+  EF_GRAD = 2,    // second output x incoming sign mask, bias-gradient column sums     (data-gradient-type)
+  EF_F32 = 4,     // fp32 output
+  EF_STATS = 8,   // normalisation sums
+  EF_ADD = 16,    // residual / addend
+  EF_ALL = 31
+};
+constexpr int kEpiFwd = EF_FWD | EF_ADD, kEpiGrad = EF_GRAD | EF_ADD;
+
 constexpr int kEpiWarps = 8;          // two epilogue warps per TMEM lane group: they take alternate 32-column chunks
 constexpr int kConvThreads = 64 + 32 * kEpiWarps;
 // Epilogue staging in shared memory.  The eight epilogue warps form two SETS (the warps taking the even / the odd
@@ -175,13 +201,7 @@ __device__ __forceinline__ void epi_stage_split(uint32_t st, const float (&f)[32
   for (int q = 0; q < 4; ++q) {
     uint32_t h[4], l[4];
 #pragma unroll
-    for (int jj = 0; jj < 4; ++jj) {
-      __nv_bfloat16 h0, l0, h1, l1;
-      split_bf16(f[q * 8 + 2 * jj], h0, l0);
-      split_bf16(f[q * 8 + 2 * jj + 1], h1, l1);
-      h[jj] = pack2(h0, h1);
-      l[jj] = pack2(l0, l1);
-    }
+    for (int jj = 0; jj < 4; ++jj) split_pack2(f[q * 8 + 2 * jj], f[q * 8 + 2 * jj + 1], h[jj], l[jj]);
     ptx::sts128(st + swz64(lane, q), make_uint4(h[0], h[1], h[2], h[3]));
     if (with_lo) ptx::sts128(st + kEpiLoOff + swz64(lane, q), make_uint4(l[0], l[1], l[2], l[3]));
   }
@@ -264,9 +284,12 @@ struct EpiTile {
 // One 32-channel chunk of one accumulator row (pixel): bias / activation / residual / sign mask / outputs.
 // v[i] = raw fp32 accumulator of channel cbase+i; all 32 lanes of the warp, and all four warps of the set, call this
 // together.  colsum: lane l's running total of channel cbase + l of the masked output (see the flush in the kernel).
+template <int kF>
 __device__ __forceinline__ void epi_chunk(const ConvUmmaParams& p, EpiTile& t, uint32_t st0,
                                           const uint32_t (&v)[32], int cbase, bool valid, int lpix, int ppix,
                                           const float* cbias, int lane, float& colsum, float& sqsum) {
+  constexpr bool kFwd = (kF & EF_FWD) != 0, kGrad = (kF & EF_GRAD) != 0, kF32 = (kF & EF_F32) != 0;
+  constexpr bool kStats = (kF & EF_STATS) != 0, kAdd = (kF & EF_ADD) != 0;
   const int nvalid = min(32, p.cout - cbase);
   if (nvalid <= 0) return;  // uniform over the warp set
   const bool full32 = (nvalid == 32);
@@ -290,11 +313,12 @@ __device__ __forceinline__ void epi_chunk(const ConvUmmaParams& p, EpiTile& t, u
   uint32_t mbits = 0;
   // sign mask of the consuming activation (second output): loaded first, used last
   uint32_t mi = 0xFFFFFFFFu;
-  if (p.out2_hi && p.mask_in && valid) mi = __ldg(p.mask_in + static_cast<long long>(ppix) * p.mask_in_words + (cbase >> 5));
+  if (kGrad && p.out2_hi && p.mask_in && valid)
+    mi = __ldg(p.mask_in + static_cast<long long>(ppix) * p.mask_in_words + (cbase >> 5));
   // bias of the chunk's 32 channels: ONE coalesced load per warp, broadcast by shuffles.  (32 predicated scalar loads,
   // each followed by its dependent add, cost ~10k clk per chunk on the long scoreboard -- half of the whole tile time
   // of every short-K layer, profiles/r01_epilogue_bias_ncu.txt.)
-  if (p.bias) {
+  if (kFwd && p.bias) {
     float bl = 0.f;
     if (lane < nvalid) bl = __ldg(p.bias + cbase + lane);
 #pragma unroll
@@ -303,7 +327,7 @@ __device__ __forceinline__ void epi_chunk(const ConvUmmaParams& p, EpiTile& t, u
 #pragma unroll
     for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
   }
-  if (cbias) {  // per-pixel (border class) bias row: vector loads, issued back to back
+  if (kFwd && cbias) {  // per-pixel (border class) bias row: vector loads, issued back to back
     if (full32) {
       const float4* cb4 = reinterpret_cast<const float4*>(cbias + cbase);
       float4 tt[8];
@@ -322,18 +346,26 @@ __device__ __forceinline__ void epi_chunk(const ConvUmmaParams& p, EpiTile& t, u
         if (i < nvalid) f[i] += __ldg(cbias + cbase + i);
     }
   }
-  if (p.mask_out || p.act != DPIG_ACT_NONE) {
+  if (kFwd && (p.mask_out || p.act != DPIG_ACT_NONE)) {
+    if (p.act == DPIG_ACT_RELU) {        // (the activation switch is uniform: one loop per kind, no select per element)
 #pragma unroll
-    for (int i = 0; i < 32; ++i) {
-      float x = f[i];
-      mbits |= (x > 0.f ? 1u : 0u) << i;
-      if (p.act == DPIG_ACT_RELU) x = fmaxf(x, 0.f);
-      else if (p.act == DPIG_ACT_LRELU) x = x > 0.f ? x : p.alpha * x;
-      f[i] = x;
+      for (int i = 0; i < 32; ++i) {
+        mbits |= (f[i] > 0.f ? 1u : 0u) << i;
+        f[i] = fmaxf(f[i], 0.f);
+      }
+    } else if (p.act == DPIG_ACT_LRELU) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        mbits |= (f[i] > 0.f ? 1u : 0u) << i;
+        f[i] = f[i] > 0.f ? f[i] : p.alpha * f[i];
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) mbits |= (f[i] > 0.f ? 1u : 0u) << i;
     }
   }
   // ---- residual / addend
-  if (p.add_hi) {
+  if (kAdd && p.add_hi) {
     if (full32 && (p.add_ps % 8 == 0)) {
       acquire();
       epi_gather_rows(st, p.add_hi, p.add_lo, p.add_ps, cbase, ppix, valid, lane);
@@ -369,7 +401,7 @@ __device__ __forceinline__ void epi_chunk(const ConvUmmaParams& p, EpiTile& t, u
         }
     }
   }
-  if (p.mask_out && valid) p.mask_out[static_cast<long long>(lpix) * p.mask_out_words + (cbase >> 5)] = mbits;
+  if (kFwd && p.mask_out && valid) p.mask_out[static_cast<long long>(lpix) * p.mask_out_words + (cbase >> 5)] = mbits;
   // ---- split-bf16 output
   if (p.out_hi) {
     if (full32 && p.out_tma) {
@@ -402,7 +434,7 @@ __device__ __forceinline__ void epi_chunk(const ConvUmmaParams& p, EpiTile& t, u
     }
   }
   // ---- fp32 output
-  if (p.out_f32) {
+  if (kF32 && p.out_f32) {
     if (full32 && (p.out_f32_ps % 4 == 0)) {
       acquire();
 #pragma unroll
@@ -434,7 +466,7 @@ __device__ __forceinline__ void epi_chunk(const ConvUmmaParams& p, EpiTile& t, u
     }
   }
   // ---- second output multiplied by the incoming sign mask (backward of ReLU / LeakyReLU)
-  if (p.out2_hi) {
+  if (kGrad && p.out2_hi) {
 #pragma unroll
     for (int i = 0; i < 32; ++i) f[i] *= ((mi >> i) & 1u) ? 1.f : p.mask_neg;
     if (full32 && p.out2_tma) {
@@ -473,7 +505,7 @@ __device__ __forceinline__ void epi_chunk(const ConvUmmaParams& p, EpiTile& t, u
   // ---- raw normalisation sums of pre = acc + bias (act = none, no addend: f still holds pre).  Runs last, while the
   // stores above drain.  Batch mode: per-channel totals of the warp's 32 rows (lane l = channel cbase + l);
   // layer mode: this row's totals over the chunk's channels (the caller reduces rows of one image).
-  if (p.stat_sums) {
+  if (kStats && p.stat_sums) {
     if (!valid) {
 #pragma unroll
       for (int i = 0; i < 32; ++i) f[i] = 0.f;
@@ -512,7 +544,8 @@ __device__ __forceinline__ void epi_chunk(const ConvUmmaParams& p, EpiTile& t, u
 //   tmem_empty[a]  leader only; count 2*kEpiWarps (peer epilogue warps arrive remotely)
 // kWide: the wide-B form of the three passes (ConvUmmaParams::wide_b), single-CTA kernel only; a template parameter so
 // that the second TMEM read of its epilogue costs the other variants no registers.
-template <bool kPair, bool kWide>
+// kF: epilogue feature groups compiled in (EF_*); see launch_conv for the choice.
+template <bool kPair, bool kWide, int kF>
 // 10 warps = 3+3+2+2 per SM sub-partition (16K registers each) caps the kernel at 168 registers per thread.
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv_umma_kernel(const __grid_constant__ ConvUmmaParams p) {
@@ -721,10 +754,12 @@ conv_umma_kernel(const __grid_constant__ ConvUmmaParams p) {
     float cs0 = 0.f, cs1 = 0.f, cs2 = 0.f, cs3 = 0.f;
     float qs0 = 0.f, qs1 = 0.f, qs2 = 0.f, qs3 = 0.f;
     int cs_nt = -1;
-    const bool stat_batch = p.stat_sums != nullptr && p.stat_mode == DPIG_NORM_BATCH;
-    const bool stat_layer = p.stat_sums != nullptr && p.stat_mode != DPIG_NORM_BATCH;
+    constexpr bool kGrad = (kF & EF_GRAD) != 0, kStats = (kF & EF_STATS) != 0, kAdd = (kF & EF_ADD) != 0;
+    const bool stat_batch = kStats && p.stat_sums != nullptr && p.stat_mode == DPIG_NORM_BATCH;
+    const bool stat_layer = kStats && p.stat_sums != nullptr && p.stat_mode != DPIG_NORM_BATCH;
     auto flush_colsum = [&]() {
-      if ((p.colsum == nullptr && !stat_batch) || cs_nt < 0) return;
+      if (!kGrad && !kStats) return;
+      if (((!kGrad || p.colsum == nullptr) && !stat_batch) || cs_nt < 0) return;
       const float cs[4] = {cs0, cs1, cs2, cs3};
       const float qs[4] = {qs0, qs1, qs2, qs3};
 #pragma unroll
@@ -765,7 +800,7 @@ conv_umma_kernel(const __grid_constant__ ConvUmmaParams p) {
       const int py = h * p.sh + p.cls_oh[cls], px = w * p.sw + p.cls_ow[cls];
       const int ppix = (n * p.out_H + py) * p.out_W + px;
       const float* cbias = nullptr;
-      if (p.class_bias && valid) {
+      if ((kF & EF_FWD) && p.class_bias && valid) {
         const int ch = h == 0 ? 0 : (h == p.Ho - 1 ? 2 : 1), cw = w == 0 ? 0 : (w == p.Wo - 1 ? 2 : 1);
         cbias = p.class_bias + (static_cast<long long>(n) * 9 + ch * 3 + cw) * p.cout;
       }
@@ -773,7 +808,7 @@ conv_umma_kernel(const __grid_constant__ ConvUmmaParams p) {
       // The residual rows of this tile are gathered chunk by chunk further down, each gather an exposed global-load
       // latency (12 % of all stall samples of a two-output data gradient, profiles/r01_dgrad_epilogue_micro.txt):
       // pull them into L2 now, while the tile's MMAs are still running.
-      if (p.add_prefetch && p.add_hi && valid && cpar == 0) {
+      if (kAdd && p.add_prefetch && p.add_hi && valid && cpar == 0) {
         const long long e0 = static_cast<long long>(ppix) * p.add_ps + nt * p.block_n;
         const int ne = min(p.block_n, p.cout - nt * p.block_n);
         for (int e = 0; e < ne; e += 64) {
@@ -811,8 +846,10 @@ conv_umma_kernel(const __grid_constant__ ConvUmmaParams p) {
           released = true;
         }
         float csum = 0.f, qsum = 0.f;
-        epi_chunk(p, et, st, v, nt * p.block_n + c0, valid, lpix, ppix, cbias, lane, csum, qsum);
-        if (stat_layer) {   // this row's sums over the chunk's channels: collected per tile (cs0 / qs0), flushed below
+        epi_chunk<kF>(p, et, st, v, nt * p.block_n + c0, valid, lpix, ppix, cbias, lane, csum, qsum);
+        if (!kGrad && !kStats) {
+          // no column sums in this instantiation
+        } else if (stat_layer) {   // this row's sums over the chunk's channels: collected per tile (cs0 / qs0), flushed below
           cs0 += csum;
           qs0 += qsum;
         } else {
@@ -903,10 +940,12 @@ struct WgradParams {
   int total_tiles, tiles_per_cta;
   int block_n, n_tiles, m_tiles, cin, cout, stages;
   int cin_pitch;  // rows per tap in the HWIO gradient (>= cin when dw is a row-slice of a wider filter)
+  int cout_pitch; // columns per row of the HWIO gradient (>= cout when this launch covers a column segment of it)
   int num_taps, group;      // taps per CTA (accumulators), blockIdx.y = tap group
   int px;                   // pixels (GEMM K) per pipeline step: 32 or 64
   int x_grouped, dy_grouped;  // operand fetched by ONE 5-D TMA per plane (64-channel groups as the 5th box dimension)
   int wide_b;               // single-CTA, one tap, block_n <= 128: dy hi|lo as one N = 2*block_n operand (see ConvUmmaParams)
+  int vec_red;              // rows of dw are 16-byte aligned: partial sums leave as red.global.add.v4.f32
   uint32_t a_bytes;         // one x tile of one plane: 2 boxes of px rows x 128 B
   uint32_t b_bytes, tmem_cols;
   float* dw;
@@ -1125,10 +1164,19 @@ wgrad_umma_kernel(const __grid_constant__ WgradParams p) {
           }
           const int cbase = nt * p.block_n + c0;
           if (active && ci < p.cin) {
-            float* o = p.dw + (static_cast<long long>(wtap) * p.cin_pitch + ci) * p.cout + cbase;
+            float* o = p.dw + (static_cast<long long>(wtap) * p.cin_pitch + ci) * p.cout_pitch + cbase;
+            if (p.vec_red && cbase + 32 <= p.cout) {
+              // 8 vector reductions per row instead of 32 scalar atomics: the partial sums of a few-pixel layer (a short
+              // K loop per CTA) spend longer in this epilogue than in their MMAs
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (cbase + j < p.cout) atomicAdd(o + j, __uint_as_float(v[j]));
+              for (int j = 0; j < 32; j += 4)
+                ptx::red_add_v4(o + j, __uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
+                                __uint_as_float(v[j + 3]));
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (cbase + j < p.cout) atomicAdd(o + j, __uint_as_float(v[j]));
+            }
           }
         }
       }
@@ -1470,11 +1518,24 @@ static int launch_conv(dpig_ctx* ctx, ConvUmmaParams& P, cudaStream_t stream) {
   }
   P.stages = stages;
   const size_t smem = static_cast<size_t>(stages) * stage_bytes + extra;
+  // the smallest epilogue instantiation that covers the launch (EF_*; DPIG_EPI_SPECIALISE=0: always the generic one)
+  int need = 0;
+  if (P.bias || P.class_bias || P.act != DPIG_ACT_NONE || P.mask_out) need |= EF_FWD;
+  if (P.out2_hi || P.colsum) need |= EF_GRAD;
+  if (P.out_f32) need |= EF_F32;
+  if (P.stat_sums) need |= EF_STATS;
+  if (P.add_hi) need |= EF_ADD;
+  const int kind = !ctx->epi_specialise ? 2 : ((need & ~kEpiFwd) == 0 ? 0 : ((need & ~kEpiGrad) == 0 ? 1 : 2));
+  using Kern = void (*)(const ConvUmmaParams);
+  static const Kern kernels[3][3] = {
+      {conv_umma_kernel<false, false, kEpiFwd>, conv_umma_kernel<false, false, kEpiGrad>, conv_umma_kernel<false, false, EF_ALL>},
+      {conv_umma_kernel<false, true, kEpiFwd>, conv_umma_kernel<false, true, kEpiGrad>, conv_umma_kernel<false, true, EF_ALL>},
+      {conv_umma_kernel<true, false, kEpiFwd>, conv_umma_kernel<true, false, kEpiGrad>, conv_umma_kernel<true, false, EF_ALL>}};
   static bool attr_set = false;
   if (!attr_set) {
-    cudaFuncSetAttribute(conv_umma_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->max_smem_optin);
-    cudaFuncSetAttribute(conv_umma_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->max_smem_optin);
-    cudaFuncSetAttribute(conv_umma_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->max_smem_optin);
+    for (int a = 0; a < 3; ++a)
+      for (int b = 0; b < 3; ++b)
+        cudaFuncSetAttribute(kernels[a][b], cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->max_smem_optin);
     attr_set = true;
   }
   const int pix_tiles = P.tiles_w * P.tiles_h * P.tiles_n;
@@ -1498,13 +1559,12 @@ static int launch_conv(dpig_ctx* ctx, ConvUmmaParams& P, cudaStream_t stream) {
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, conv_umma_kernel<true, false>, P);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kernels[2][kind], P);
     if (e != cudaSuccess) return set_error(ctx, DPIG_ECUDA, "conv_umma_kernel<pair> launch: %s", cudaGetErrorString(e));
     return check_launch(ctx, "conv_umma_kernel<pair>");
   }
   dim3 grid(std::min(pix_tiles * n_tiles, ctx->num_sms));
-  if (P.wide_b) conv_umma_kernel<false, true><<<grid, kConvThreads, smem, stream>>>(P);
-  else conv_umma_kernel<false, false><<<grid, kConvThreads, smem, stream>>>(P);
+  kernels[P.wide_b ? 1 : 0][kind]<<<grid, kConvThreads, smem, stream>>>(P);
   return check_launch(ctx, "conv_umma_kernel");
 }
 
@@ -1718,6 +1778,9 @@ extern "C" int dpig_conv2d_bwd_data(dpig_ctx* ctx, const dpig_tensor* dy, const 
 
 static int wgrad_impl(dpig_ctx* ctx, const dpig_tensor* x, const dpig_tensor* dy, int32_t kh, int32_t kw,
                       int32_t stride, int32_t cin, int32_t cout, float* dw, int32_t cin_pitch, dpig_stream stream);
+static int wgrad_segment(dpig_ctx* ctx, const dpig_tensor* x, const dpig_tensor* dy, int32_t kh, int32_t kw,
+                         int32_t stride, int32_t cin, int32_t cout, float* dw, int32_t cin_pitch, int32_t cout_pitch,
+                         dpig_stream stream);
 
 extern "C" int dpig_conv2d_bwd_filter(dpig_ctx* ctx, const dpig_tensor* x, const dpig_tensor* dy,
                                       int32_t kh, int32_t kw, int32_t stride, int32_t cin,
@@ -1731,8 +1794,36 @@ extern "C" int dpig_conv2d_bwd_filter_rows(dpig_ctx* ctx, const dpig_tensor* x, 
   return wgrad_impl(ctx, x, dy, kh, kw, stride, cin, cout, dw_rows, cin_total, stream);
 }
 
+// Output-channel counts that no 256-wide block divides (384, 640, 896: every other level of the pyramids) used to run
+// as 192- / 128-wide blocks on the single-CTA kernel at 290-340 TFLOP/s; they are cut into 256-wide column segments
+// plus the remainder, one launch each, so that all but the remainder run on the 2-CTA pair kernel (520-578 TFLOP/s).
+// The segments write disjoint columns of dw.  (DPIG_WGRAD_SPLIT=0: one launch.)
 static int wgrad_impl(dpig_ctx* ctx, const dpig_tensor* x, const dpig_tensor* dy, int32_t kh, int32_t kw,
                       int32_t stride, int32_t cin, int32_t cout, float* dw, int32_t cin_pitch, dpig_stream stream) {
+  DPIG_CHECK_CTX(ctx);
+  // Measured (profiles/r02_wgrad_split_ab.txt): the segments win where there are many pixel steps to share out and
+  // several input-channel tiles to pair (384 -> 384 on 32x16 / 12x12 maps: -10 %); few-pixel layers lose more to the two
+  // extra launches and their partial-sum epilogues than the pair kernel gains (640 -> 640 on 8x4: +60 %).
+  const long long out_pixels = (x && dy) ? static_cast<long long>(dy->n) * dy->h * dy->w : 0;
+  if (x && dy && dw && ctx->wgrad_split && cout > 256 && cout % 256 != 0 && cout % 64 == 0 && dy->c >= cout &&
+      out_pixels >= 32768 && cin >= 384) {
+    for (int co0 = 0; co0 < cout; co0 += 256) {
+      const int seg = std::min(256, cout - co0);
+      dpig_tensor dyv = *dy;
+      dyv.hi = static_cast<char*>(dy->hi) + static_cast<size_t>(co0) * 2;
+      dyv.lo = dy->lo ? static_cast<char*>(dy->lo) + static_cast<size_t>(co0) * 2 : nullptr;
+      dyv.c = seg;
+      int rc = wgrad_segment(ctx, x, &dyv, kh, kw, stride, cin, seg, dw + co0, cin_pitch, cout, stream);
+      if (rc) return rc;
+    }
+    return DPIG_OK;
+  }
+  return wgrad_segment(ctx, x, dy, kh, kw, stride, cin, cout, dw, cin_pitch, cout, stream);
+}
+
+static int wgrad_segment(dpig_ctx* ctx, const dpig_tensor* x, const dpig_tensor* dy, int32_t kh, int32_t kw,
+                         int32_t stride, int32_t cin, int32_t cout, float* dw, int32_t cin_pitch, int32_t cout_pitch,
+                         dpig_stream stream) {
   DPIG_CHECK_CTX(ctx);
   if (!x || !dy || !dw) return set_error(ctx, DPIG_EINVAL, "conv2d_bwd_filter: null argument");
   if (kh * kw > kMaxTaps || (stride != 1 && stride != 2))
@@ -1749,7 +1840,9 @@ static int wgrad_impl(dpig_ctx* ctx, const dpig_tensor* x, const dpig_tensor* dy
   P.planes = (x->lo && dy->lo && !ctx->fast_mode) ? 2 : 1;
   P.cin = cin;
   P.cin_pitch = cin_pitch;
+  P.cout_pitch = cout_pitch;
   P.cout = cout;
+  P.vec_red = (ctx->wgrad_vec_red && cout_pitch % 4 == 0 && reinterpret_cast<uintptr_t>(dw) % 16 == 0) ? 1 : 0;
   const int c64 = (cout + 63) / 64 * 64;
   P.block_n = c64 <= 256 ? c64 : (c64 % 256 == 0 ? 256 : (c64 % 192 == 0 ? 192 : (c64 % 128 == 0 ? 128 : 64)));
   P.n_tiles = (cout + P.block_n - 1) / P.block_n;

@@ -308,5 +308,11 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int m, int n, int a_mn_ma
          (static_cast<uint32_t>(m >> 4) << 24);
 }
 
+// 16-byte vector reduction into global memory (sm_90+): four fp32 adds per instruction / L2 request.
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
 }  // namespace ptx
+
 }  // namespace dpig

@@ -91,6 +91,8 @@ class LocalGroup:
 class LocalDist:
     """The `dist` object of one LocalGroup rank (same surface as Dist)."""
 
+    capturable = False      # the exchange synchronises host threads: it cannot sit inside a CUDA graph capture
+
     def __init__(self, group, rank):
         self.group, self.rank, self.world_size, self.local_rank = group, rank, group.world_size, 0
 

@@ -342,7 +342,9 @@ class Stage1Engine:
         # cudaGraphLaunch): on by default on one GPU; with torch.distributed the NCCL exchanges would have to be
         # captured too, opt in with DPIG_GRAPHS=2.  DPIG_GRAPHS=0 switches them off.
         gmode = int(os.environ.get("DPIG_GRAPHS", "1"))
-        self.use_graphs = gmode >= 2 or (gmode == 1 and dist is None)
+        # N > 1: the NCCL exchanges (gradient slices, sync-BN sums) are captured into the step graphs too; a `dist` that
+        # cannot be captured (ddp.LocalGroup's in-process ranks) says so with `capturable = False`
+        self.use_graphs = gmode >= 1 and (dist is None or getattr(dist, "capturable", True))
         self._graphs = {}
         self._eager_steps = {"g": 0, "d": 0}
         # N > 1: the ID_AE (U-Net) slice of the gradient arena is complete before the appearance encoder's backward
@@ -351,7 +353,7 @@ class Stage1Engine:
         self.overlap_comm = dist is not None and int(os.environ.get("DPIG_OVERLAP", "1")) != 0
         self._comm_stream = None
         self._comm_done = None
-        self._early_range = None
+        self._early_ranges = []
         self.gp_alpha_fixed = False   # tests pin alpha to compare with the oracle
         self.g_lr = 2e-5
         self.d_lr = 2e-5
@@ -1123,7 +1125,7 @@ class Stage1Engine:
             p.add("add_f32", ptr(self.g_emb), ptr(self.stem_tmp), ptr(self.g_emb) if tap else None, B * e, 1.0, 1.0)
         # ---- appearance encoder (every ID_AE gradient is final here: start its all-reduce when data-parallel)
         if self.dist is not None:
-            p.add_py(lambda s: self._early_allreduce())
+            p.add_py(lambda s: self._early_allreduce("idae"))
         p.add("embedding_assemble", ptr(self.g_fea), ptr(self.g_bg_fea), ptr(self.vis), B, P, cfg.part_z, self.bg_z,
               ptr(self.g_emb), 1)
         w, b, dw, db = self._linear(self.gp, self.n_roi_fc)
@@ -1131,6 +1133,8 @@ class Stage1Engine:
               self.roi_flat, cfg.part_z)
         p.add("pack_f32", ptr(self.g_roi_flat), hn * ern, hn * ern, self.roi_pyr.g_y[ern - 1].ref())
         self.roi_pyr.backward(self, p)
+        if self.dist is not None:     # the ROI pyramid's gradients are final: their all-reduce runs under the Bg pyramid's backward
+            p.add_py(lambda s: self._early_allreduce("roi"))
         if int(os.environ.get("DPIG_CROP_GATHER", "1")) == 0:      # the atomic scatter form accumulates; the gather form overwrites
             p.add_py(lambda s: self.g_crop.zero_())
         p.add("crop_and_resize_bwd", self.roi_pyr.g_in.ref(), ptr(self.fg_mask) if cfg.fgbg else None, ptr(self.boxes),
@@ -1141,6 +1145,8 @@ class Stage1Engine:
                   self.bg_flat, self.bg_z)
             p.add("pack_f32", ptr(self.g_bg_flat), hn * ern, hn * ern, self.bg_pyr.g_y[ern - 1].ref())
             self.bg_pyr.backward(self, p)
+            if self.dist is not None:     # ... and the Bg pyramid's under the stem's backward
+                p.add_py(lambda s: self._early_allreduce("bg"))
             # g_xs = g_crop (already * m) + g_xbg * (1 - m)      (models.py:402-403)
             p.add("mask_split", self.bg_pyr.g_in.ref(), ptr(self.fg_mask), None, self.g_xbg_s.ref())
             p.add("ew_combine", self.g_xs.ref(), self.g_xbg_s.ref(), None, None, ptr(self.g_crop), hn, None, 0.0, 0)
@@ -1286,23 +1292,38 @@ class Stage1Engine:
         t = self.t[which]
         return lr * math.sqrt(1.0 - b2 ** t) / (1.0 - 0.5 ** t)
 
-    def _idae_range(self):
-        """[lo, hi) of the ID_AE/* parameters in the generator arena if they form one contiguous block, else None."""
-        inside = [(o, (n + 63) // 64 * 64) for name, (o, n, _) in self.gp.specs.items() if name.startswith("ID_AE/")]
+    def _slice_range(self, which):
+        """[lo, hi) of a parameter slice of the generator arena whose gradients become final together, if it is one
+        contiguous block, else None: 'idae' = every ID_AE/* parameter (final before the appearance encoder's backward),
+        'roi' / 'bg' = the ROI / background pyramid convolutions and their FC (final after that pyramid's backward)."""
+        if which == "idae":
+            member = lambda name: name.startswith("ID_AE/")  # noqa: E731
+        else:
+            convs = self.n_roi if which == "roi" else getattr(self, "n_bg", [])
+            fc = self.n_roi_fc if which == "roi" else getattr(self, "n_bg_fc", None)
+            names = set()
+            for n in list(convs) + ([fc] if fc else []):
+                names.update((n + "/weights", n + "/biases"))
+            member = lambda name: name in names  # noqa: E731
+        inside = [(o, (n + 63) // 64 * 64) for name, (o, n, _) in self.gp.specs.items() if member(name)]
         if not inside:
             return None
         lo, hi = min(o for o, _ in inside), max(o + n for o, n in inside)
         for name, (o, n, _) in self.gp.specs.items():
-            if not name.startswith("ID_AE/") and lo <= o < hi:
+            if not member(name) and lo <= o < hi:
                 return None
         return lo, hi
 
-    def _early_allreduce(self):
-        """Called from the backward program once every ID_AE gradient is final (before the appearance encoder's
-        backward): all-reduce that slice on the communication stream while the main stream keeps computing."""
+    def _idae_range(self):
+        return self._slice_range("idae")
+
+    def _early_allreduce(self, which="idae"):
+        """Called from the backward program once every gradient of a slice is final: all-reduce that slice on the
+        communication stream while the main stream keeps computing (ID_AE: 285 of the 474 MB under the appearance
+        encoder's backward; ROI pyramid under the Bg pyramid's backward; Bg pyramid under the stem's)."""
         if not self.overlap_comm:
             return
-        rng = self._idae_range()
+        rng = self._slice_range(which)
         if rng is None:
             return
         if self._comm_stream is None:
@@ -1314,19 +1335,19 @@ class Stage1Engine:
             self.dist.all_reduce_sum(self.gp.grad[rng[0]:rng[1]])
             self._comm_done = torch.cuda.Event()
             self._comm_done.record()
-        self._early_range = rng
+        self._early_ranges.append(rng)
 
     def _optim(self, which, s):
         """All-reduce (N > 1), update, re-pack of the bf16 operand copies.  Reads the step size from self.lr_dev."""
         grp = self.gp if which == "g" else self.dp
         if self.dist is not None:
-            if which == "g" and self._early_range is not None:
-                lo, hi = self._early_range
-                self._early_range = None
-                if lo > 0:
-                    self.dist.all_reduce_sum(grp.grad[:lo])
-                if hi < grp.total:
-                    self.dist.all_reduce_sum(grp.grad[hi:])
+            if which == "g" and self._early_ranges:
+                done, self._early_ranges = sorted(self._early_ranges), []
+                pos = 0
+                for lo, hi in done + [(grp.total, grp.total)]:     # what the early all-reduces left: the gaps
+                    if lo > pos:
+                        self.dist.all_reduce_sum(grp.grad[pos:lo])
+                    pos = max(pos, hi)
                 torch.cuda.current_stream().wait_event(self._comm_done)
             else:
                 self.dist.all_reduce_sum(grp.grad)

@@ -389,7 +389,7 @@ class Stage2Engine:
         # whole-call CUDA graphs of train_iteration's optimiser calls (a critic call = frozen-encoder forward, ~100
         # launches, + ~70 small FC launches + the update): same switch as Stage1Engine (DPIG_GRAPHS)
         gmode = int(os.environ.get("DPIG_GRAPHS", "1"))
-        self.use_graphs = gmode >= 2 or (gmode == 1 and dist is None)
+        self.use_graphs = gmode >= 1 and (dist is None or getattr(dist, "capturable", True))
         self._graphs, self._eager_calls, self._lr_dev = {}, {}, {}
         if factors is not None:      # custom factor set (the pose sampler of --model=4); no Stage-I engine needed
             self.f = factors

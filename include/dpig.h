@@ -104,6 +104,9 @@ int dpig_ctx_set_fast_mode(dpig_ctx* ctx, int fast);
  * layers), 2 wherever the shape allows.  Results are identical in every mode (same products, same fp32 accumulation
  * order per output element). */
 int dpig_ctx_set_pair_mode(dpig_ctx* ctx, int mode);
+/* Tuning switches by name ("epi_specialise", "wgrad_split", "wide_b", ... = the DPIG_* environment variables read at
+ * context creation); results are identical under every setting.  For A/B measurements and tests. */
+int dpig_ctx_set_option(dpig_ctx* ctx, const char* name, int value);
 /* number of kernels this ctx has launched so far (bench.py's gpu_launches). */
 unsigned long long dpig_launch_count(const dpig_ctx* ctx);
 const char* dpig_version(void);

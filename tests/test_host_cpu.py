@@ -149,7 +149,21 @@ def test_step_size_and_overlap_slice_host_logic(monkeypatch):
 
     monkeypatch.setenv("DPIG_GRAPHS", "1")
     d = engine.Stage1Engine(NoDeviceCtx(), cfg, 2, mode="dcgan", dist=FakeDist(), device="cpu")
-    assert d.overlap_comm and not d.use_graphs                          # N > 1: eager lists unless DPIG_GRAPHS=2
+    assert d.overlap_comm and d.use_graphs                              # N > 1: the NCCL exchanges are captured too
+    monkeypatch.setenv("DPIG_GRAPHS", "0")
+    assert not engine.Stage1Engine(NoDeviceCtx(), cfg, 2, mode="dcgan", dist=FakeDist(), device="cpu").use_graphs
+    monkeypatch.setenv("DPIG_GRAPHS", "1")
+    # the three slices that are all-reduced while the backward pass is still running are disjoint, 64-aligned blocks
+    rngs = [d._slice_range(w) for w in ("idae", "roi", "bg")]
+    assert all(r is not None and r[0] % 64 == 0 and r[1] % 64 == 0 for r in rngs), rngs
+    srt = sorted(rngs)
+    assert all(a[1] <= b[0] for a, b in zip(srt, srt[1:])), rngs
+    for name, (off, n, _) in d.gp.specs.items():
+        inside = [w for w, r in zip(("idae", "roi", "bg"), rngs) if r[0] <= off and off + n <= r[1]]
+        want = ["idae"] if name.startswith("ID_AE/") else (
+            ["roi"] if any(name.startswith(x + "/") for x in d.n_roi + [d.n_roi_fc]) else (
+                ["bg"] if any(name.startswith(x + "/") for x in d.n_bg + [d.n_bg_fc]) else []))
+        assert inside == want, (name, inside, want)
     lo, hi = d._idae_range()
     assert lo % 64 == 0 and hi % 64 == 0 and 0 < lo < hi <= d.gp.total
     for name, (off, n, _) in d.gp.specs.items():

@@ -368,6 +368,10 @@ CONV_BWD_FILTER_CASES = [
     dict(n=3, h=12, w=12, cin=384, cout=512, k=3, stride=1),
     dict(n=9, h=32, w=32, cin=256, cout=128, k=3, stride=1),
     dict(n=4, h=16, w=16, cin=128, cout=256, k=1, stride=1),
+    # output widths no 256-wide block divides: 256-wide column segments + remainder, one launch each (640 is case 5)
+    dict(n=3, h=12, w=12, cin=384, cout=384, k=3, stride=1),
+    dict(n=2, h=16, w=8, cin=256, cout=384, k=3, stride=2),
+    dict(n=2, h=8, w=4, cin=128, cout=896, k=3, stride=1),
 ]
 
 
