@@ -29,6 +29,13 @@ def _pad8(c):
     return (c + 7) // 8 * 8
 
 
+def halved(size, times):
+    """Spatial size after `times` stride-2 SAME convolutions: ceil(size / 2) each (48 -> 24 -> 12 -> 6 -> 3 -> 2 -> 1)."""
+    for _ in range(times):
+        size = -(-size // 2)
+    return size
+
+
 class NetConfig:
     """Shapes of the Stage-I graphs.
 
@@ -40,8 +47,12 @@ class NetConfig:
     joint batch statistics; the logits are split in half afterwards)."""
 
     def __init__(self, img_h=128, img_w=64, hidden=128, z_num=64, roi_size=48, n_parts=7, part_z=32,
-                 keypoints=18, d_dim=64, repeat_num=None, fgbg=True, enc_repeat=None, unet_repeat=None, d_joint=False):
+                 keypoints=18, d_dim=64, repeat_num=None, fgbg=True, enc_repeat=None, unet_repeat=None, d_joint=False,
+                 use_vis=True):
         self.img_h, self.img_w, self.hidden, self.z_num = img_h, img_w, hidden, z_num
+        # use_vis=False: models.GeneratorCNN_ID_Encoder_BodyROI (models.py:275-325, the DeepFashion samplers --model=103 /
+        # 1002): the part features are NOT multiplied by the part visibilities
+        self.use_vis = use_vis
         self.roi_size, self.n_parts, self.part_z, self.keypoints, self.d_dim = roi_size, n_parts, part_z, keypoints, d_dim
         self.repeat_num = repeat_num if repeat_num is not None else int(math.log2(img_h)) - 2
         self.fgbg, self.d_joint = fgbg, d_joint
@@ -200,15 +211,15 @@ class _Pyramid:
         self.dims = []
         for idx in range(rn):
             c = hn * (idx + 1)
-            hh, ww = h >> idx, w >> idx
+            hh, ww = halved(h, idx), halved(w, idx)
             self.dims.append((hh, ww, c))
             self.a.append(SplitTensor(n, hh, ww, c, dev))
             self.y.append(y_slots[idx] if y_slots else SplitTensor(n, hh, ww, c, dev))
             self.ma.append(_mask(n * hh * ww, c, dev))
             self.mb.append(_mask(n * hh * ww, c, dev))
             if idx < rn - 1:
-                self.x_in.append(SplitTensor(n, hh // 2, ww // 2, c + hn, dev))
-                self.md.append(_mask(n * (hh // 2) * (ww // 2), c + hn, dev))
+                self.x_in.append(SplitTensor(n, halved(hh, 1), halved(ww, 1), c + hn, dev))
+                self.md.append(_mask(n * halved(hh, 1) * halved(ww, 1), c + hn, dev))
         self.in_mask = in_mask
         self.in_layer = None   # ConvLayer producing the pyramid input (set by the owner when in_mask is used)
         if not eng.training:      # forward-only engine (sampling, tester.py): no gradient buffers
@@ -400,7 +411,7 @@ class Stage1Engine:
         self.n_e1 = conv(gspecs, sc, cc, 3, 1, hn, hn)
         self.n_e2 = conv(gspecs, sc, cc, 3, 1, hn, hn)
         self.n_roi = pyramid(sc, cc, ern)
-        roi_f = cfg.roi_size >> (ern - 1)
+        roi_f = halved(cfg.roi_size, ern - 1)
         self.roi_flat = roi_f * roi_f * hn * ern
         self.n_roi_fc = fc(gspecs, sc, fc_c, self.roi_flat, cfg.part_z)
         if cfg.fgbg:   # background branch of the two-branch encoder (models.py:454-464)
@@ -1256,7 +1267,10 @@ class Stage1Engine:
         bb = dev(batch["part_bbox"])[:, :P, :]                      # [B,P,4] pixels (y1,x1,y2,x2)
         scale = torch.tensor([cfg.img_h, cfg.img_w, cfg.img_h, cfg.img_w], dtype=torch.float32, device=self.device)
         self.boxes.copy_((bb / scale).permute(1, 0, 2).reshape(P * B, 4))   # ROI i of image b -> row i*B+b
-        self.vis.copy_(dev(batch["part_vis"])[:, :P])
+        if cfg.use_vis:
+            self.vis.copy_(dev(batch["part_vis"])[:, :P])
+        else:
+            self.vis.fill_(1.0)
 
     def forward(self, with_disc=True):
         """Encoder + U-Net (+ D on x and G) forward; returns nothing (results stay in HBM)."""
@@ -1494,7 +1508,7 @@ def init_params(cfg, seed=1234):
     s.conv(3, hn, hn)
     s.conv(3, hn, hn)
     s.pyramid(ern)
-    rf = cfg.roi_size >> (ern - 1)
+    rf = halved(cfg.roi_size, ern - 1)
     s.fc(rf * rf * hn * ern, cfg.part_z)
     if cfg.fgbg:
         s.pyramid(ern)

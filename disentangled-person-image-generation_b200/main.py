@@ -1,8 +1,7 @@
 """Entry point mirroring the reference's main.py:12-90: `--model` id -> trainer class, `--is_train` -> train()/test().
-Implemented: --model=1 (Stage-I Market-1501, the BASELINE hot path), --model=2 / 3 / 4 (trainer_sub.py), 11 / 12 / 13 and
-1001 (tester.py), 101 / 102 (trainer_256.py: Stage-I DeepFashion 256x256 and its pose auto-encoder stage); the other ids
-(103, 104, 1002: the DeepFashion samplers on the BodyROI encoder) raise NotImplementedError naming the reference class
-they map to."""
+Every id of the reference's table is implemented: 1 (Stage-I Market-1501, the BASELINE hot path), 2 / 3 / 4 (trainer_sub.py),
+11 / 12 / 13 and 1001 / 1002 (tester.py), 101 - 104 (trainer_256.py: the DeepFashion 256x256 stages).  Under torchrun
+(WORLD_SIZE > 1) the trainers that take data-parallel hooks get a ddp.Dist."""
 import os
 
 from .config import get_config, prepare_dirs, save_config

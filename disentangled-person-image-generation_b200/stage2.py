@@ -391,8 +391,8 @@ class Stage2Engine:
         gmode = int(os.environ.get("DPIG_GRAPHS", "1"))
         self.use_graphs = gmode >= 1 and (dist is None or getattr(dist, "capturable", True))
         self._graphs, self._eager_calls, self._lr_dev = {}, {}, {}
-        if factors is not None:      # custom factor set (the pose sampler of --model=4); no Stage-I engine needed
-            self.f = factors
+        if factors is not None:      # custom factor set: the pose sampler of --model=4 (no Stage-I engine), or the single
+            self.f = factors         # 'app' factor of the DeepFashion samplers (--model=103 / 1002) on a Stage-I engine
             first = next(iter(factors.values()))
             self.ctx, self.B = first.ctx, first.B
         else:
@@ -467,6 +467,9 @@ class Stage2Engine:
         """Real embeddings of the current Stage-I batch (frozen encoder forward, trainer.py:737-741)."""
         s = torch.cuda.current_stream().cuda_stream
         self.s1.run_encoder(s)
+        if "app" in self.f:          # one factor over the whole embedding (trainer_256.py:306-330)
+            self.f["app"].real.data.copy_(self.s1.emb)
+            return
         self.f["fg"].real.data.copy_(self.s1.emb[:, :self.fg_dim])
         self.f["bg"].real.data.copy_(self.s1.emb[:, self.fg_dim:])
 
@@ -584,7 +587,7 @@ class Stage2Engine:
         """trainer.py:821-845: per factor, one generator update (skipped at step 0) then CRITIC_ITERS critic updates
         (+clip, fused into the RMSProp kernel), every optimiser call on a fresh batch / fresh noise."""
         iters = 1 if self.mode in ("dcgan", "lsgan") else 5
-        for factor in ("fg", "bg"):
+        for factor in self.f:
             if step > 0:
                 self._call(factor, "g")
             for _ in range(iters):

@@ -53,6 +53,15 @@ class DPIG_FourNetsFgBg_testOnlySampleFactor(object):
         self.s1.load_params(engine.init_params(cfg, seed=self.config.random_seed))
         self.s2 = stage2.Stage2Engine(self.s1, mode="wgan")
         self.s2.load_params(stage2.init_stage2_params())
+        self._build_pose_tape(B, dev)
+        # the four partial restores of tester.py:423-472 (Encoder+ID_AE, Gaussian_FC_*, PoseAE, Discriminator.): any of
+        # --pretrained_path, --pretrained_appSample_path, --pretrained_poseAE_path (TensorFlow V2 checkpoints or .npz)
+        for path in (self.pretrained_path, getattr(self.config, "pretrained_appSample_path", None),
+                     getattr(self.config, "pretrained_poseAE_path", None)):
+            if path:
+                self.load_params(tf_checkpoint.load_any(path))
+
+    def _build_pose_tape(self, B, dev):
         # pose auto-encoder tapes (models.py:488-515), activation_fn=LeakyReLU (tester.py:487, 495)
         self.pp = engine.ParamGroup(pose_specs(self.keypoint_num), dev)
         names = list(self.pp.specs)
@@ -74,12 +83,6 @@ class DPIG_FourNetsFgBg_testOnlySampleFactor(object):
         self.pose_coord = t.linear(h, *dec[9])
         self.pose_vis_logit = t.linear(h, *dec[10])
         self.p_pose = t.forward_program()
-        # the four partial restores of tester.py:423-472 (Encoder+ID_AE, Gaussian_FC_*, PoseAE, Discriminator.): any of
-        # --pretrained_path, --pretrained_appSample_path, --pretrained_poseAE_path (TensorFlow V2 checkpoints or .npz)
-        for path in (self.pretrained_path, getattr(self.config, "pretrained_appSample_path", None),
-                     getattr(self.config, "pretrained_poseAE_path", None)):
-            if path:
-                self.load_params(tf_checkpoint.load_any(path))
 
     def load_params(self, params):
         """Parameters by TF variable name: Encoder/..., ID_AE/..., Discriminator.*, Gaussian_FC_Fg/..., Gaussian_FC_Bg/...,
@@ -128,14 +131,11 @@ class DPIG_FourNetsFgBg_testOnlySampleFactor(object):
         Cc = torch.clamp((g[:, :, 1] + 1) / 2.0 * W, 0, W - 1)
         s1.pose_rcv.copy_(torch.stack([R, Cc, g[:, :, 2]], dim=-1))
         # ---- appearance branch (tester.py:509-554)
-        s2.encode_real()
-        for factor, z in (("fg", z_fg), ("bg", z_bg)):
-            s2.sample_noise(factor, z)
-            s2.f[factor].p_g_fwd.run(st)
+        self._appearance_branch(st, z_fg, z_bg)
         self._fill_embedding()
         # ---- U-Net, denorm, critic score (tester.py:561-571)
         s1.run_unet(st)
-        score = s1.score_generated(st)
+        score = self._score(st)
         G = torch.clamp((s1.G + 1.0) * 127.5, 0, 255)
         pose_maps = s1.gin.slice(0, cfg.keypoints).hi.float()
         pose_img = (pose_maps.amax(dim=-1, keepdim=True).expand(-1, -1, -1, 3) + 1) * 127.5
@@ -145,6 +145,16 @@ class DPIG_FourNetsFgBg_testOnlySampleFactor(object):
     def _held_pose(self, norm):
         """sample_pose=False: the first sample's real pose for the whole batch (tester.py:500-503)."""
         return norm[:1].expand(self.batch_size, -1, -1)
+
+    def _appearance_branch(self, st, z_fg, z_bg):
+        s2 = self.s2
+        s2.encode_real()
+        for factor, z in (("fg", z_fg), ("bg", z_bg)):
+            s2.sample_noise(factor, z)
+            s2.f[factor].p_g_fwd.run(st)
+
+    def _score(self, st):
+        return self.s1.score_generated(st)
 
     def _fill_embedding(self):
         """Which appearance factors reach the U-Net (tester.py:540-554): a sampled factor takes the GaussianFCRes
@@ -351,3 +361,50 @@ class DPIG_ThreeNetsApp_testOnlyCondition_256(DPIG_FourNetsFgBg_testOnlyConditio
     def __init__(self, config, loader=None):
         super().__init__(config, loader=loader)
         self.test_dir_name = "test_result_ROI7_Condition_TargetPose_%dx%d" % (self.test_batch_num, self.batch_size)
+
+
+class DPIG_ThreeNetsApp_testOnlySampleFactor_256(DPIG_FourNetsFgBg_testOnlySampleFactor):
+    """--model=1002 (trainer_256.py:845-1088): the DeepFashion sampler.  Three networks: the Stage-I graph of --model=101
+    (GeneratorCNN_ID_Encoder_BodyROIVis on 64x64 crops, visibility-gated, + the 5-level U-Net), ONE appearance sampler
+    (GaussianFCRes 224 -> 512 x 4 -> 224 in scope Gaussian_FC) and the pose auto-encoder.
+      sample_app:   embedding = Gaussian_FC(z); otherwise the first sample's encoder embedding tiled over the batch
+      sample_pose:  the decoded (encoded real) pose; otherwise the first sample's real pose for the whole batch
+    There is no critic in this graph (trainer_256.py:846-853): the score is zero."""
+
+    def __init__(self, config, loader=None):
+        super().__init__(config, loader=loader)
+        self.sample_app = getattr(config, "sample_app", False)
+        self.test_batch_num = 100                                   # trainer_256.py:1036
+
+    def init_net(self, net_cfg=None):
+        self.ctx = _lib.Context(0)
+        cfg = net_cfg or engine.NetConfig.deepfashion(img_h=self.img_H, img_w=self.img_W, hidden=self.conv_hidden_num,
+                                                      z_num=self.z_num)
+        self.cfg = cfg
+        dev = torch.device("cuda", 0)
+        B = self.batch_size
+        self.s1 = engine.Stage1Engine(self.ctx, cfg, B, mode="dcgan", inference=True)
+        self.s1.load_params(engine.init_params(cfg, seed=self.config.random_seed))
+        self.factor = stage2._Factor(self.ctx, B, cfg.emb_dim, 512, "Gaussian_FC/G_FC", "FCDis_", dev)
+        self.s2 = stage2.Stage2Engine(self.s1, mode="wgan", factors={"app": self.factor})
+        self.s2.load_params(stage2.init_factor_params(self.factor, seed=self.config.random_seed))
+        self._build_pose_tape(B, dev)
+        for path in (self.pretrained_path, getattr(self.config, "pretrained_appSample_path", None),
+                     getattr(self.config, "pretrained_poseAE_path", None)):
+            if path:
+                self.load_params(tf_checkpoint.load_any(path))
+
+    def _fill_embedding(self):
+        s1, B = self.s1, self.batch_size
+        if self.sample_app:
+            s1.emb.copy_(self.factor.fake.data)
+        else:
+            s1.emb.copy_(self.factor.real.data[:1].expand(B, -1))
+
+    def _appearance_branch(self, st, z_fg, z_bg):
+        self.s2.encode_real()
+        self.s2.sample_noise("app", z_fg)
+        self.factor.p_g_fwd.run(st)
+
+    def _score(self, st):
+        return torch.zeros((self.batch_size,), device=self.s1.device)

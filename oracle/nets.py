@@ -37,8 +37,11 @@ class NetConfig:
     D applied once to concat([x, G]) (`d_joint`: joint batch statistics, logits split in half afterwards)."""
 
     def __init__(self, img_h=128, img_w=64, hidden=128, z_num=64, roi_size=48, n_parts=7, part_z=32,
-                 keypoints=18, d_dim=64, repeat_num=None, fgbg=True, enc_repeat=None, unet_repeat=None, d_joint=False):
+                 keypoints=18, d_dim=64, repeat_num=None, fgbg=True, enc_repeat=None, unet_repeat=None, d_joint=False,
+                 use_vis=True):
         self.img_h, self.img_w, self.hidden, self.z_num = img_h, img_w, hidden, z_num
+        # use_vis=False: models.GeneratorCNN_ID_Encoder_BodyROI (models.py:275-325; --model=103 / 1002): no visibility gating
+        self.use_vis = use_vis
         self.roi_size, self.n_parts, self.part_z, self.keypoints, self.d_dim = roi_size, n_parts, part_z, keypoints, d_dim
         self.repeat_num = repeat_num if repeat_num is not None else int(math.log2(img_h)) - 2  # trainer.py:75
         self.fgbg, self.d_joint = fgbg, d_joint
@@ -106,7 +109,9 @@ def init_params(cfg, seed=1234, bias_noise=0.0):
         s.conv(3, c, c)
         if idx < ern - 1:
             s.conv(3, c, hn * (idx + 2))
-    roi_final = cfg.roi_size >> (ern - 1)
+    roi_final = cfg.roi_size
+    for _ in range(ern - 1):          # stride-2 SAME: ceil(size / 2) per level (48 -> ... -> 3 -> 2 -> 1 at 7 levels)
+        roi_final = -(-roi_final // 2)
     s.fc(roi_final * roi_final * hn * ern, cfg.part_z)
     if cfg.fgbg:
         for idx in range(ern):
@@ -263,8 +268,9 @@ def encoder_roi(p, cfg, x, roi_bbox, roi_vis, taps=None):
     body = _pyramid(w, body, cfg.hidden, cfg.enc_repeat, taps, "roi")
     body = w.fc(body.reshape(body.shape[0], -1))
     feats = list(torch.split(body, B, dim=0))
-    for i in range(cfg.n_parts):
-        feats[i] = feats[i] * roi_vis[:, i:i + 1].to(x.dtype)
+    if getattr(cfg, "use_vis", True):
+        for i in range(cfg.n_parts):
+            feats[i] = feats[i] * roi_vis[:, i:i + 1].to(x.dtype)
     return torch.cat(feats, dim=-1)
 
 
@@ -456,6 +462,8 @@ def stage2_losses(p, factor, real, z, mode="wgan"):
     activation_fn=LeakyReLU; critic = FCDiscriminator on real and fake embeddings."""
     if factor == "pose":     # --model=4: PoseGaussian sampler, critic 'Pose_emb_' (trainer.py:893-910)
         scope, name = "PoseGaussian/G_FC", "Pose_emb_"
+    elif factor == "app":    # --model=103: one appearance sampler, critic 'FCDis_' (trainer_256.py:324-334)
+        scope, name = "Gaussian_FC/G_FC", "FCDis_"
     else:
         scope = "Gaussian_FC_%s/G_FC" % ("Fg" if factor == "fg" else "Bg")
         name = "Fg_FCDis_" if factor == "fg" else "Bg_FCDis_"

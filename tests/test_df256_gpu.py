@@ -211,3 +211,72 @@ if __name__ == "__main__":
             for k, v in worst:
                 print("   %-45s L2 %.3e  max %.3e" % (k, v[0], v[1]), flush=True)
     print("golden:", check_golden(small), flush=True)
+
+
+def test_df_sampler_stage_model103_and_tester_1002():
+    """--model=103 (trainer_256.py:266-402) and --model=1002 (:845-1088) at a reduced geometry: the BodyROI encoder of the
+    sampler stages (48x48 crops through 7 levels with TensorFlow's ceil halving 48 -> 24 -> 12 -> 6 -> 3 -> 2 -> 1, part
+    features NOT gated by the visibilities), the single 'app' sampler / critic pair, and the tester's three-network
+    forward -- against the float64 oracle."""
+    import numpy as np
+    from dpig_b200 import config as cfgmod
+    from dpig_b200 import stage2, synth, tester, trainer_256
+    from dpig_b200 import engine
+    B = 2
+    geo = dict(img_h=128, img_w=128, hidden=64)
+    conf, _ = cfgmod.get_config(["--model=103", "--batch_size=%d" % B, "--img_H=128", "--img_W=128", "--conv_hidden_num=64",
+                                 "--synthetic_data=true", "--model_dir=/tmp/dpig_test_103"])
+    tr = trainer_256.DPIG_Encoder_subSampleAppNet_GAN_BodyROI_256(conf)
+    tr.init_net()
+    ecfg = tr.net.cfg
+    assert (ecfg.roi_size, ecfg.use_vis, ecfg.enc_repeat) == (48, False, 6) and tr.net.roi_pyr.dims[-1][:2] == (2, 2)
+    ocfg = nets.NetConfig.deepfashion(roi_size=48, use_vis=False, **geo)
+    p1 = nets.init_params(ocfg, seed=31, bias_noise=0.05)
+    tr.net.load_params(p1)
+    p2 = {k: v + 0 for k, v in stage2.init_factor_params(tr.factor, seed=32).items()}
+    tr.s2.load_params(p2)
+    b = synth.make_batch(B, 128, 128, seed=43)
+    b["part_vis"][:, 2] = 0.0                     # an "invisible" part must still contribute (no visibility gating here)
+    tr.net.set_batch(b)
+    tr.s2.encode_real()
+    po = nets.to_torch(p1, torch.float64)
+    ob = dict(x=torch.tensor(b["x"], dtype=torch.float64), mask=torch.tensor(b["mask"], dtype=torch.float64),
+              part_bbox=torch.tensor(b["part_bbox"][:, :7]), part_vis=torch.tensor(b["part_vis"][:, :7]))
+    emb = nets.encoder(po, ocfg, ob)
+    real = tr.factor.real.data.detach().double().cpu()
+    assert float((real - emb).abs().max()) < 1e-3
+    z = np.random.default_rng(3).normal(0, 0.2, size=(B, ecfg.emb_dim)).astype(np.float32)
+    tr.s2.sample_noise("app", z)
+    p = nets.to_torch(p2, torch.float64, requires_grad=True)
+    out = nets.stage2_losses(p, "app", real, torch.tensor(z, dtype=torch.float64), "wgan")
+    tr.s2.d_grads("app")
+    torch.cuda.synchronize()
+    got = tr.s2.get_params(grads=True)
+    dn = [k for k in p if k.startswith("FCDis_")]
+    for k, g in zip(dn, torch.autograd.grad(out["d_loss"], [p[k] for k in dn], retain_graph=True)):
+        assert float((torch.as_tensor(got[k]).double() - g).norm() / (g.norm() + 1e-30)) < 1e-4, k
+    tr.s2.train_iteration(1, lambda: synth.make_batch(B, 128, 128, seed=44))      # one full step of the stage runs
+    G = tr.generate(b["x"], b["x"], b["pose_rcv"], b["part_bbox"], b["part_vis"], z=z)
+    assert G.shape == (B, 128, 128, 3) and G.dtype == np.uint8
+
+    # ---- --model=1002: Stage-I graph of --model=101 (roi 64, visibility-gated) + Gaussian_FC sampler + pose AE
+    conf2, _ = cfgmod.get_config(["--model=1002", "--is_train=False", "--batch_size=%d" % B, "--img_H=128", "--img_W=128",
+                                  "--conv_hidden_num=64", "--sample_app=True", "--sample_pose=False", "--synthetic_data=true"])
+    te = tester.DPIG_ThreeNetsApp_testOnlySampleFactor_256(conf2)
+    ecfg2 = engine.NetConfig.deepfashion(roi_size=32, **geo)
+    te.init_net(ecfg2)
+    ocfg2 = nets.NetConfig.deepfashion(roi_size=32, **geo)
+    q1 = nets.init_params(ocfg2, seed=33, bias_noise=0.05)
+    q2 = stage2.init_factor_params(te.factor, seed=34)
+    params = dict(q1)
+    params.update(q2)
+    params.update(nets.init_pose_params(seed=35, bias_noise=0.05))
+    te.load_params(params)
+    G, pose_img, score = te.generate(b["x"], None, b["pose_rcv"], b["part_bbox"], b["part_vis"], z_fg=z)
+    assert (score == 0).all() and G.shape == (B, 128, 128, 3)
+    pq = nets.to_torch(params, torch.float64)
+    with torch.no_grad():
+        app = nets.gaussian_fc_res(pq, torch.tensor(z, dtype=torch.float64), 4, "Gaussian_FC/G_FC", lambda t: T.leaky_relu(t, 0.2))
+        rcv = torch.tensor(b["pose_rcv"], dtype=torch.float64)[:1].expand(B, -1, -1)     # sample_pose=False: first sample's pose
+        Gref, _ = nets.unet_generator(pq, ocfg2, app, T.pose_rasterize(rcv, 128, 128))
+    assert float(np.abs(G - T.denorm_img(Gref).numpy()).max()) < 0.2               # 1e-3 on [-1,1] == 0.13 on [0,255]

@@ -104,3 +104,14 @@ def test_forward_only_engine_has_no_gradient_state():
         return total
 
     assert nbytes(eng) < 0.6 * nbytes(full)
+
+
+def test_df_sampler_engine_ceil_halving():
+    """The BodyROI encoder of the DeepFashion sampler stages (--model=103 / 104): 48x48 crops through repeat_num+1 levels
+    with TensorFlow's SAME / stride-2 sizes ceil(s / 2): 48 -> 24 -> 12 -> 6 -> 3 -> 2 -> 1 (models.py:275-325)."""
+    assert [engine.halved(48, k) for k in range(7)] == [48, 24, 12, 6, 3, 2, 1]
+    cfg = engine.NetConfig.deepfashion(img_h=256, img_w=256, hidden=64, roi_size=48, use_vis=False)
+    eng = engine.Stage1Engine(DryContext(), cfg, 1, mode="dcgan", device="cpu", inference=True)
+    assert [d[:2] for d in eng.roi_pyr.dims] == [(48, 48), (24, 24), (12, 12), (6, 6), (3, 3), (2, 2), (1, 1)]
+    assert eng.roi_flat == 1 * 1 * 64 * 7          # same FC input as --model=101's 64x64 crops: the checkpoints interchange
+    assert _check_program(eng.p_fwd_gen) > 0

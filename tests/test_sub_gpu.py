@@ -104,8 +104,20 @@ def test_main_model2_pose_autoencoder(tmp_path):
     g = tr.generate(tr.loader.next_batch()["pose_rcv"])
     assert g.shape == (4, 18, 3) and set(np.unique(g[:, :, 2])) <= {0.0, 1.0}
     from dpig_b200 import tf_checkpoint
+    tr.g_lr = tr.g_lr * 0.5                              # as after an lr halving (trainer.py:362-363)
     z = tf_checkpoint.load_checkpoint(tr.save(2))
-    assert "PoseAE/G_Pose_Encoder/fully_connected/weights" in z and len(z) == 42 + 1 and int(z["step"]) == 2
+    # 42 variables, their Adam slots (`<var>/Adam`, `<var>/Adam_1`), the beta powers + step counter, step / g_lr / d_lr / phase
+    assert "PoseAE/G_Pose_Encoder/fully_connected/weights" in z and int(z["step"]) == 2
+    assert len(z) == 42 * 3 + 3 + 4 and bool(z["phase"]) and "PoseAE/G_Pose_Decoder/fully_connected_3/biases/Adam_1" in z
+    # --ckpt_path resume: weights, Adam moments, step counter and the (halved) learning rate come back
+    import copy
+    from dpig_b200 import main as M
+    cfg2 = copy.copy(tr.config)
+    cfg2.ckpt_path, cfg2.max_step, cfg2.model_dir = str(tmp_path), 0, str(tmp_path / "resumed")
+    tr2 = M.main(cfg2)
+    a, b = tr.pose_ae.get_state(), tr2.pose_ae.get_state()
+    assert set(a) == set(b) and all(np.array_equal(np.asarray(a[k]), np.asarray(b[k])) for k in a)
+    assert tr2.pose_ae.t == tr.pose_ae.t == 2 and tr2.g_lr == pytest.approx(tr.g_lr)
 
 
 def test_main_model3_appearance_samplers(tmp_path):

@@ -57,6 +57,18 @@ def test_main_trains_and_generates(tmp_path, model, extra, cls):
     assert tr2.net.t == tr.net.t
 
 
-def test_main_rejects_unbuilt_models(tmp_path):
-    with pytest.raises(NotImplementedError):
-        _run(tmp_path, 104, [])
+def test_main_rejects_unknown_models(tmp_path):
+    """Every id of the reference's --model table is built (main.py:22-72); anything else is refused like there."""
+    with pytest.raises(Exception, match="unknown --model"):
+        _run(tmp_path, 999, [])
+
+
+def test_main_model104_deepfashion_pose_sampler(tmp_path):
+    """--model=104 (trainer_256.py:511-700): the pose-sampler stage at the DeepFashion normalisation; its preview runs the
+    sampler stages' Stage-I graph (BodyROI encoder on 48x48 crops, no visibility gating)."""
+    tr = _run(tmp_path, 104, ["--img_H=128", "--img_W=128", "--dataset=DF_train_data"])
+    assert type(tr).__name__ == "DPIG_subnetSamplePoseRCV_GAN_BodyROI_256"
+    b = tr.loader.next_batch()
+    g = tr.generate(b["x"], b["x"], b["pose_rcv"], b["part_bbox"], part_vis=b["part_vis"], mask=b["mask"])
+    assert g.shape == (2, 128, 128, 3) and g.dtype == np.uint8
+    assert (tr.net.cfg.roi_size, tr.net.cfg.use_vis) == (48, False)
