@@ -79,10 +79,12 @@ def GeneratorCNN_ID_UAEAfterResidual(x, pose, input_channel, z_num, repeat_num, 
     prog = engine.Program(eng.ctx)
     eng._prog_unet_forward(prog)
     if pose_rcv is None:
-        # drop the rasterisation call and inject the given maps into the stem-input slice instead
-        prog.calls = [c for c in prog.calls if c[0] != "pose_rasterize"]
+        # maps given: drop the two calls that rasterise from keypoints (the maps, and their 3x3 patches for the stem's
+        # patch-form contraction), inject the maps into the stem-input slice and unfold the patches from there
+        prog.calls = [c for c in prog.calls if c[0] not in ("pose_rasterize", "pose_patch")]
         sl = eng.gin.slice(0, eng.cfg.keypoints)
         sl.set_from_float(torch.as_tensor(pose, dtype=torch.float32).to(eng.device))
+        eng.ctx.im2col_small(eng.gin.ref(), eng.cfg.keypoints, 3, 3, 1, 0, eng.pose_patch.ref(), s)
     prog.run(s)
     return eng.G.clone(), eng.z.clone(), _variables(eng, "ID_AE/G")
 
