@@ -66,6 +66,7 @@ _SIGNATURES = {
     "dpig_bias_grad": [_T, _P, _P],
     "dpig_bias_grad_f32": [_P, _L, _I, _P, _P],
     "dpig_ew_combine": [_T, _T, _T, _T, _P, _L, _P, _F, _I, _P],
+    "dpig_ew_combine_colsum": [_T, _T, _T, _T, _P, _L, _P, _F, _I, _P, _P],
     "dpig_pack_f32": [_P, _L, _I, _T, _P],
     "dpig_unpack_f32": [_T, _P, _L, _P],
     "dpig_mask_split": [_T, _P, _T, _T, _P],

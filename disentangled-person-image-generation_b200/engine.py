@@ -248,8 +248,8 @@ class _Pyramid:
         filled by the caller.  skip_grads[idx] (idx < rn-1): extra grad wrt y[idx] (decoder skip path)."""
         rn = self.rn
         # top level: gb = g_y * mask_b
-        prog.add("ew_combine", self.gb[rn - 1].ref(), self.g_y[rn - 1].ref(), None, None, None, 0,
-                 ptr(self.mb[rn - 1]), 0.0, 0)
+        eng.ew_combine_db(prog, self.gb[rn - 1], self.layers[3 * (rn - 1) + 1], self.g_y[rn - 1].ref(), None, None, None, 0,
+                          ptr(self.mb[rn - 1]), 0.0, 0)
         for idx in range(rn - 1, -1, -1):
             l1, l2 = self.layers[3 * idx], self.layers[3 * idx + 1]
             hh, ww, c = self.dims[idx]
@@ -845,6 +845,15 @@ class Stage1Engine:
                  in_h, in_w, layer.cin, ep, flops=2.0 * dy.n * dy.h * dy.w * layer.cout * layer.k * layer.k * layer.cin,
                  tag="%s dy %dx%dx%dx%d->%d k%ds%d" % (layer.wname, dy.n, dy.h, dy.w, layer.cout, layer.cin, layer.k, layer.stride))
 
+    def ew_combine_db(self, prog, out, db_of, *args):
+        """ew_combine whose output is the output-gradient of conv `db_of`: the bias gradient (column sums) is taken in
+        the same pass, and the later conv_wgrad(db_of, ., out) skips its dpig_bias_grad read of the tensor."""
+        if db_of is not None and self.fuse_bias_grad and out.c == db_of.cout and out.c % 8 == 0 and out.c // 8 <= 256:
+            prog.add("ew_combine_colsum", out.ref(), *args, ptr(db_of.db))
+            self._db_done.add((id(prog), id(out), db_of.wname))
+        else:
+            prog.add("ew_combine", out.ref(), *args)
+
     def conv_wgrad(self, prog, layer, x, dy, bias=True):
         prog.add("conv2d_bwd_filter", x.ref(), dy.ref(), layer.k, layer.k, layer.stride, layer.cin, layer.cout,
                  ptr(layer.dw), flops=2.0 * dy.n * dy.h * dy.w * layer.cout * layer.k * layer.k * layer.cin,
@@ -1088,7 +1097,7 @@ class Stage1Engine:
                 lu = self.conv[names[2]]
                 gup = self.g_cat[idx + 1].slice(0, self.dec_c[idx + 1][0])
                 self._keep.append(gup)
-                p.add("ew_combine", self.dec_gu[idx].ref(), gup.ref(), None, None, None, 0, ptr(self.dec_mu[idx]), 0.0, 1)
+                self.ew_combine_db(p, self.dec_gu[idx], lu, gup.ref(), None, None, None, 0, ptr(self.dec_mu[idx]), 0.0, 1)
                 self.conv_wgrad(p, lu, self.dec_y[idx], self.dec_gu[idx])
                 self.conv_dgrad(p, lu, self.dec_gu[idx], hh, ww, out=self.dec_gy[idx], out_masked=self.dec_gb[idx],
                                 mask_in=self.dec_mb[idx], db_of=l2)
@@ -1163,8 +1172,8 @@ class Stage1Engine:
             p.add("ew_combine", self.g_xs.ref(), self.g_xbg_s.ref(), None, None, ptr(self.g_crop), hn, None, 0.0, 0)
         else:
             p.add("pack_f32", ptr(self.g_crop), hn, hn, self.g_xs.ref())
-        p.add("ew_combine", self.g_xs_m.ref(), self.g_xs.ref(), None, None, None, 0, ptr(self.me2), 0.0, 0)
         e0, e1, e2 = self.conv[self.n_e0], self.conv[self.n_e1], self.conv[self.n_e2]
+        self.ew_combine_db(p, self.g_xs_m, e2, self.g_xs.ref(), None, None, None, 0, ptr(self.me2), 0.0, 0)
         self.conv_wgrad(p, e2, self.e1, self.g_xs_m)
         self.conv_dgrad(p, e2, self.g_xs_m, H, W, out_masked=self.g_e1, mask_in=self.me1, db_of=e1)
         self.conv_wgrad(p, e1, self.e0, self.g_e1)

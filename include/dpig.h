@@ -206,6 +206,12 @@ int dpig_ew_combine(dpig_ctx* ctx, const dpig_tensor* out, const dpig_tensor* a,
                     const dpig_tensor* b, const dpig_tensor* c, const float* f32,
                     int64_t f32_pix_stride, const uint32_t* mask, float mask_neg, int32_t pool2,
                     dpig_stream stream);
+/* dpig_ew_combine that also accumulates colsum[c] += sum over pixels of out[., c] (fp32 [out->c]): the bias gradient of
+ * the conv whose output gradient `out` is (tf.gradients of bias_add), without re-reading the tensor (dpig_bias_grad). */
+int dpig_ew_combine_colsum(dpig_ctx* ctx, const dpig_tensor* out, const dpig_tensor* a,
+                           const dpig_tensor* b, const dpig_tensor* c, const float* f32,
+                           int64_t f32_pix_stride, const uint32_t* mask, float mask_neg,
+                           int32_t pool2, float* colsum, dpig_stream stream);
 /* fp32 NHWC -> split (optionally into a channel slice of a wider buffer); pads channels >= c_src
  * with zeros up to out->c. */
 int dpig_pack_f32(dpig_ctx* ctx, const float* src, int64_t src_pix_stride, int32_t c_src,
