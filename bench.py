@@ -34,7 +34,8 @@ sys.path.insert(0, ROOT)
 WORKLOADS = {
     "market": dict(metric="images/sec (G+D step) Market-1501 128x64", batch=64, hw=(128, 64), model=1,
                    text="Stage-I Fg/Bg/Pose reconstruction (--model=1, %(mode)s loss), Market-1501 128x64, batch=%(b)d "
-                        "per GPU: 1 g_optim + 1 d_optim per step, separate batches (trainer.py:336-347)"),
+                        "per GPU: 1 g_optim + disc_ITERS d_optim per step (1 for dcgan, 5 for wgan-gp), separate batches "
+                        "(trainer.py:336-347)"),
     "df256": dict(metric="images/sec (G+D step) DeepFashion 256x256", batch=32, hw=(256, 256), model=101,
                   text="Stage-I DeepFashion 256x256 (--model=101, trainer_256.py path, dcgan loss), batch=%(b)d per GPU: "
                        "1 g_optim + 1 d_optim per step, separate batches"),
@@ -84,7 +85,8 @@ def _ncu_traffic():
                 continue
             r = max(rows, key=lambda x: x.get("time_ns", x.get("time_us", 0)))
             out.append({"launch": shapes[base][0], "dram_bytes": r["dram_read_bytes"] + r["dram_write_bytes"],
-                        "algorithmic_bytes": shapes[base][1], "tensor_pipe_pct": r.get("tensor_pipe_pct"),
+                        "algorithmic_bytes": shapes[base][1],
+                        "tensor_pipe_pct": r.get("tensor_pipe_active_pct_elapsed", r.get("tensor_pipe_pct")),
                         "source": "profiles/" + name})
         if out:
             break
@@ -365,8 +367,10 @@ def main():
     tmp = tempfile.mkdtemp(prefix="dpig_bench_")
 
     # pinned host batches; a step consumes several (one per optimiser call, reference q2)
-    per_step = {"market": 2, "df256": 2, "stage2": 10, "sample": 1}[args.workload]
-    npool = 4 if per_step <= 2 else 10
+    # critic updates per generator update: 1 for dcgan / lsgan, CRITIC_ITERS = 5 for wgan / wgan-gp (trainer.py:339-345)
+    disc_iters = 1 if args.mode in ("dcgan", "lsgan") else 5
+    per_step = {"market": 1 + disc_iters, "df256": 1 + disc_iters, "stage2": 10, "sample": 1}[args.workload]
+    npool = 4 if per_step <= 2 else max(10, per_step)
     pool = []
     for i in range(npool):
         b = synth.make_batch(B, H, Wd, seed=1000 + 17 * rank + i)
@@ -386,10 +390,11 @@ def main():
         d2h = 12
 
         def dev_step(i, timings=None):
-            eng.set_batch(dev_pool[(2 * i) % npool])
+            eng.set_batch(dev_pool[(per_step * i) % npool])
             eng.g_step(timings)
-            eng.set_batch(dev_pool[(2 * i + 1) % npool])
-            eng.d_step(timings)
+            for j in range(disc_iters):
+                eng.set_batch(dev_pool[(per_step * i + 1 + j) % npool])
+                eng.d_step(timings)
 
         def e2e_run(k0, k):
             sink = []
