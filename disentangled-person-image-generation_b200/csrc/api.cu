@@ -105,7 +105,6 @@ extern "C" int dpig_ctx_set_option(dpig_ctx* ctx, const char* name, int value) {
   else if (n == "wgrad_group") ctx->wgrad_group = value;
   else if (n == "wgrad_vec_red") ctx->wgrad_vec_red = value != 0;
   else if (n == "wide_b") ctx->wide_b = value != 0;
-  else if (n == "exp_skip_a") ctx->exp_skip_a = value;
   else if (n == "epi_bufs") ctx->epi_bufs = value;
   else if (n == "epi_tma") ctx->epi_tma = value != 0;
   else if (n == "dgrad_merge") ctx->dgrad_merge = value != 0;

@@ -32,7 +32,6 @@ struct dpig_ctx {
   int wgrad_group = 0;     // filter taps per wgrad CTA: 0 = default (1); DPIG_WGRAD_GROUP
   int wgrad_px = 0;        // pixels per wgrad pipeline step: 0 = auto, 32 / 64 forced; DPIG_WGRAD_PX
   bool epi_specialise = true;  // conv launches run on the smallest epilogue instantiation covering them (DPIG_EPI_SPECIALISE=0: generic)
-  int exp_skip_a = 0;          // timing experiment (wrong results): see ConvUmmaParams::exp_skip_a
   bool crop_gather = true;  // crop_and_resize image gradient in gather form (DPIG_CROP_GATHER=0: atomic scatter)
   int max_stages = 0;      // >= 2: cap on the conv smem pipeline depth (DPIG_CONV_STAGES, tuning experiments)
   unsigned long long launches = 0;

@@ -96,7 +96,6 @@ struct ConvUmmaParams {
   int out_tma, out2_tma;
   int epi_bufs;  // staging buffers per warp set (1 or 2), used alternately by successive TMA stores
   int add_prefetch;  // pull the residual rows of a tile into L2 before its accumulator is awaited
-  int exp_skip_a;    // TIMING EXPERIMENT ONLY (wrong results): skip the activation load of taps with dh != -1
 };
 
 __device__ __forceinline__ uint8_t* align1024(uint8_t* p) {
@@ -643,10 +642,8 @@ conv_umma_kernel(const __grid_constant__ ConvUmmaParams p) {
                   ptx::tma_load_3d_pair(st + b_off + pl * p.b_bytes, &p.b_map[pl], lead_full, kc * 64,
                                         nt * p.block_n + b_row0, tap.wtap);
             } else {
-            const bool skip_a = p.exp_skip_a && tap.dh != -1;
-            ptx::mbar_expect_tx(&full[s], p.planes * ((skip_a ? 0u : p.a_tx_bytes) + p.b_bytes));
-            if (skip_a) {
-            } else if (p.a_merged)
+            ptx::mbar_expect_tx(&full[s], p.planes * (p.a_tx_bytes + p.b_bytes));
+            if (p.a_merged)
               ptx::tma_load_5d(st, &p.a_map[tap.src][0], &full[s], kc * 64, w0 + tap.dw, h0 + tap.dh, n0, 0);
             else
               for (int pl = 0; pl < p.planes; ++pl)
@@ -1500,7 +1497,6 @@ static int fill_epilogue(dpig_ctx* ctx, ConvUmmaParams& P, const dpig_conv_epilo
 
 static int launch_conv(dpig_ctx* ctx, ConvUmmaParams& P, cudaStream_t stream) {
   P.planes = ctx->fast_mode ? 1 : P.planes;
-  P.exp_skip_a = ctx->exp_skip_a;
   const uint32_t stage_bytes = P.planes * (kABytes + P.b_bytes);
   uint32_t extra = 1024 + 256 + kEpiBytes;  // alignment slack + barriers + epilogue staging
   int stages = (ctx->max_smem_optin - static_cast<int>(extra)) / static_cast<int>(stage_bytes);
