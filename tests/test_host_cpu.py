@@ -267,3 +267,22 @@ def test_ddp_plumbing_gloo_world2(tmp_path):
     outs = [p.communicate(timeout=240)[0].decode() for p in procs]
     assert all(p.returncode == 0 for p in procs), outs
     assert all("ok" in o for o in outs), outs
+
+
+def test_bench_reference_arm_uses_all_host_threads_under_torchrun_env():
+    """`bench.py --impl reference` (the CPU arm the driver runs beside the GPU arm, also under torchrun): torchrun exports
+    OMP_NUM_THREADS=1 to its workers, which made the round-1 arm single-threaded at N > 1.  The arm takes every core of the
+    affinity mask regardless, runs exactly the requested steps, and ranks other than 0 exit without work."""
+    import json
+    import subprocess
+    env = dict(os.environ, OMP_NUM_THREADS="1", RANK="0", WORLD_SIZE="2")
+    cmd = [sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "0",
+           "--workload", "sample"]
+    out = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["steps"] == 1 and line["warmup"] == 0 and line["n_gpus"] == 2
+    assert line["cpu_baseline"]["cores"] == len(os.sched_getaffinity(0)) == line["config"]["host_threads"]
+    assert line["value"] > 0 and line["e2e"]["h2d_bytes_per_step"] == 0 and line["metric"].startswith("images/sec")
+    other = subprocess.run(cmd, env=dict(env, RANK="1"), capture_output=True, text=True, timeout=120)
+    assert other.returncode == 0 and other.stdout.strip() == ""
