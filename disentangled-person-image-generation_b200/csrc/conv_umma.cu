@@ -1509,7 +1509,10 @@ static int launch_conv(dpig_ctx* ctx, ConvUmmaParams& P, cudaStream_t stream) {
   if (ctx->epi_bufs != 1 && (P.out_tma || P.out2_tma)) {
     const int stages2 = std::min(6, (ctx->max_smem_optin - static_cast<int>(extra + kEpiBytes)) / static_cast<int>(stage_bytes));
     const int steps = P.num_taps * P.kchunks / std::max(1, P.nclass);
-    const bool heavy = (P.out_tma && P.out2_tma) || steps <= 4;
+    // (round 2, same-process A/B profiles/r02_ab_epi_bufs.txt: two-output data gradients with a K loop of more than four
+    //  steps and no residual gather run 9-22 % FASTER with one buffer and the third pipeline stage; with the residual
+    //  gather or a short K loop the second buffer wins by 3-8 %)
+    const bool heavy = (P.out_tma && P.out2_tma && P.add_hi != nullptr) || steps <= 4;
     if (stages2 >= stages || (stages2 >= 2 && (heavy || ctx->epi_bufs == 2))) {
       P.epi_bufs = 2;
       stages = std::min(stages, stages2);
