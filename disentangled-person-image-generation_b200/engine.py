@@ -166,17 +166,64 @@ class Program:
         self.ctx = ctx
         self.calls = []
         self.keep = []  # keeps ctypes structs / tensors referenced by the frozen arguments alive
+        self.side = set()          # indices of calls that may run on the side stream (see add)
+        self.side_stream = None
+        self.two_streams = int(os.environ.get("DPIG_SIDE_STREAM", "1")) != 0
 
-    def add(self, name, *args, flops=0.0, tag=""):
+    def add(self, name, *args, flops=0.0, tag="", side=False):
+        """side=True: the call may run on the program's side stream, concurrently with the calls that follow it on the
+        main stream, until the next join (a python hook, or the end of the program).  Used for the filter gradients: a
+        layer's wgrad and its dgrad both only READ dy, nothing later in a backward program overwrites what a wgrad
+        reads, and the wgrads of one stream stay ordered among themselves (several accumulate into one dw)."""
         fn = getattr(self.ctx.lib, "dpig_" + name)
+        if side:
+            self.side.add(len(self.calls))
         self.calls.append((name, fn, args, flops, tag))
 
     def add_py(self, fn):
         self.calls.append((None, fn, None, 0.0, ""))
 
+    def _run_two_streams(self, stream):
+        """Main-stream calls in order on `stream` (= torch's current stream), side calls on self.side_stream after an
+        event that covers everything enqueued on the main stream so far; joins before python hooks and at the end.
+        Under CUDA-graph capture the side stream forks from / joins the capturing stream through the same events."""
+        h = self.ctx.handle
+        main = torch.cuda.current_stream()
+        if self.side_stream is None:
+            self.side_stream = torch.cuda.Stream(device=main.device)
+        side = self.side_stream
+        pending = False
+
+        def join():
+            ev = torch.cuda.Event()
+            ev.record(side)
+            main.wait_event(ev)
+
+        for i, (name, fn, args, flops, tag) in enumerate(self.calls):
+            if name is None:
+                if pending:
+                    join()
+                    pending = False
+                fn(stream)
+                continue
+            if i in self.side:
+                ev = torch.cuda.Event()
+                ev.record(main)
+                side.wait_event(ev)
+                rc = fn(h, *args, side.cuda_stream)
+                pending = True
+            else:
+                rc = fn(h, *args, stream)
+            if rc != 0:
+                raise _lib.DpigError("dpig_%s failed (%d): %s" % (name, rc, self.ctx.last_error()))
+        if pending:
+            join()
+
     def run(self, stream, timings=None):
         """timings: optional list; when given, every C-ABI call is bracketed by CUDA events on the
         launching stream and (name, algorithmic_flops, start_event, end_event) is appended."""
+        if self.side and timings is None and self.two_streams:
+            return self._run_two_streams(stream)
         h = self.ctx.handle
         for name, fn, args, flops, tag in self.calls:
             if name is None:
@@ -857,7 +904,8 @@ class Stage1Engine:
     def conv_wgrad(self, prog, layer, x, dy, bias=True):
         prog.add("conv2d_bwd_filter", x.ref(), dy.ref(), layer.k, layer.k, layer.stride, layer.cin, layer.cout,
                  ptr(layer.dw), flops=2.0 * dy.n * dy.h * dy.w * layer.cout * layer.k * layer.k * layer.cin,
-                 tag="%s %dx%dx%dx%d->%d k%ds%d" % (layer.wname, x.n, x.h, x.w, layer.cin, layer.cout, layer.k, layer.stride))
+                 tag="%s %dx%dx%dx%d->%d k%ds%d" % (layer.wname, x.n, x.h, x.w, layer.cin, layer.cout, layer.k, layer.stride),
+                 side=True)
         if not bias or (id(prog), id(dy), layer.wname) in self._db_done:
             return
         if dy.c != layer.cout:  # channel-padded gradient (e.g. the 3-channel image gradient held in 8)
