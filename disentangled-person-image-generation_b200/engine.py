@@ -183,6 +183,10 @@ class Program:
     def add_py(self, fn):
         self.calls.append((None, fn, None, 0.0, ""))
 
+    def add_join(self):
+        """The main stream waits here for everything launched on the side stream so far."""
+        self.calls.append((None, None, None, 0.0, "join"))
+
     def _run_two_streams(self, stream):
         """Main-stream calls in order on `stream` (= torch's current stream), side calls on self.side_stream after an
         event that covers everything enqueued on the main stream so far; joins before python hooks and at the end.
@@ -204,7 +208,8 @@ class Program:
                 if pending:
                     join()
                     pending = False
-                fn(stream)
+                if fn is not None:
+                    fn(stream)
                 continue
             if i in self.side:
                 ev = torch.cuda.Event()
@@ -227,7 +232,8 @@ class Program:
         h = self.ctx.handle
         for name, fn, args, flops, tag in self.calls:
             if name is None:
-                fn(stream)
+                if fn is not None:
+                    fn(stream)
                 continue
             if timings is not None:
                 e0 = torch.cuda.Event(enable_timing=True)
@@ -279,15 +285,15 @@ class _Pyramid:
                    for i in range(rn - 1)]
         self.g_in = SplitTensor(n, h, w, hn, dev)  # grad wrt the pyramid input (masked if in_mask)
 
-    def forward(self, eng, prog):
+    def forward(self, eng, prog, side=False):
         li = 0
         for idx in range(self.rn):
-            eng.conv_fwd(prog, self.layers[li], self.x_in[idx], out=self.a[idx], mask_out=self.ma[idx])
+            eng.conv_fwd(prog, self.layers[li], self.x_in[idx], out=self.a[idx], mask_out=self.ma[idx], side=side)
             eng.conv_fwd(prog, self.layers[li + 1], self.a[idx], out=self.y[idx], addend=self.x_in[idx],
-                         mask_out=self.mb[idx])
+                         mask_out=self.mb[idx], side=side)
             li += 2
             if idx < self.rn - 1:
-                eng.conv_fwd(prog, self.layers[li], self.y[idx], out=self.x_in[idx + 1], mask_out=self.md[idx])
+                eng.conv_fwd(prog, self.layers[li], self.y[idx], out=self.x_in[idx + 1], mask_out=self.md[idx], side=side)
                 li += 1
 
     def backward(self, eng, prog, skip_grads=None, wgrad=True):
@@ -865,7 +871,7 @@ class Stage1Engine:
 
     def conv_fwd(self, prog, layer, x, out=None, act=ACT_RELU, alpha=0.2, addend=None, mask_out=None, out_f32=None,
                  out_f32_ps=0, upsample=1, bias=True, out_masked=None, mask_in=None, mask_neg=0.0, class_bias=None,
-                 stat_sums=None, stat_mode=0):
+                 stat_sums=None, stat_mode=0, side=False):
         ep = self._epilogue(prog, layer.b if bias else None, act, alpha, addend, mask_in, mask_neg, mask_out, out,
                             out_masked, out_f32, out_f32_ps, upsample, class_bias, stat_sums=stat_sums,
                             stat_mode=stat_mode)
@@ -875,7 +881,7 @@ class Stage1Engine:
                  flops=2.0 * x.n * oh * ow * getattr(layer, "flops_cout", layer.cout) * layer.k * layer.k *
                  getattr(layer, "flops_cin", layer.cin),
                  tag="%s %dx%dx%dx%d->%d k%ds%d" % (layer.wname, x.n, x.h, x.w, getattr(layer, "flops_cin", layer.cin),
-                                                    layer.cout, layer.k, layer.stride))
+                                                    layer.cout, layer.k, layer.stride), side=side)
 
     def conv_dgrad(self, prog, layer, dy, in_h, in_w, out=None, out_masked=None, mask_in=None, mask_neg=0.0, addend=None,
                    out_f32=None, out_f32_ps=0, db_of=None):
@@ -1050,7 +1056,14 @@ class Stage1Engine:
         self.conv_fwd(p, e1, self.e0, out=self.e1, mask_out=self.me1)
         self.conv_fwd(p, e2, self.e1, out=self.xs, addend=self.e0, mask_out=self.me2)
         if cfg.fgbg:
+            # the background branch (models.py:454-464) depends on xs only: it runs on the side stream, concurrently with
+            # the ROI branch -- the upper pyramid levels of either branch (8x4 / 3x3 maps) leave half of the SMs idle
             p.add("mask_split", self.xs.ref(), ptr(self.fg_mask), None, self.x_bg.ref())
+            self.bg_pyr.forward(self, p, side=True)
+            p.add("unpack_f32", self.bg_pyr.y[rn - 1].ref(), ptr(self.bg_flat_f32), hn * rn, side=True)
+            w, b, _, _ = self._linear(self.gp, self.n_bg_fc)
+            p.add("linear_fwd", ptr(self.bg_flat_f32), ptr(w), ptr(b), ptr(self.bg_fea), B, self.bg_flat, self.bg_z,
+                  ACT_NONE, 0.0, side=True)
         p.add("crop_and_resize_fwd", self.xs.ref(), ptr(self.fg_mask) if cfg.fgbg else None, ptr(self.boxes),
               ptr(self.box_ind), P * B, self.rois.ref())
         self.roi_pyr.forward(self, p)
@@ -1058,12 +1071,7 @@ class Stage1Engine:
         w, b, _, _ = self._linear(self.gp, self.n_roi_fc)
         p.add("linear_fwd", ptr(self.roi_flat_f32), ptr(w), ptr(b), ptr(self.fea), P * B, self.roi_flat, cfg.part_z,
               ACT_NONE, 0.0)
-        if cfg.fgbg:
-            self.bg_pyr.forward(self, p)
-            p.add("unpack_f32", self.bg_pyr.y[rn - 1].ref(), ptr(self.bg_flat_f32), hn * rn)
-            w, b, _, _ = self._linear(self.gp, self.n_bg_fc)
-            p.add("linear_fwd", ptr(self.bg_flat_f32), ptr(w), ptr(b), ptr(self.bg_fea), B, self.bg_flat, self.bg_z,
-                  ACT_NONE, 0.0)
+        p.add_join()
         p.add("embedding_assemble", ptr(self.fea), ptr(self.bg_fea), ptr(self.vis), B, P, cfg.part_z, self.bg_z,
               ptr(self.emb), 0)
 
@@ -1458,7 +1466,9 @@ class Stage1Engine:
                 return
             graph = torch.cuda.CUDAGraph()
             n0 = self.ctx.launch_count()
-            with torch.cuda.graph(graph):
+            # (thread_local: the NCCL watchdog thread polls events while this thread captures; under the default
+            #  "global" mode such a call from another thread can invalidate the capture)
+            with torch.cuda.graph(graph, capture_error_mode="thread_local" if self.dist is not None else "global"):
                 grads(None)
                 self._optim(which, torch.cuda.current_stream().cuda_stream)
             g = self._graphs[which] = (graph, self.ctx.launch_count() - n0)

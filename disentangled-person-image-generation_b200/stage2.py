@@ -540,7 +540,9 @@ class Stage2Engine:
                 return body()
             graph = torch.cuda.CUDAGraph()
             n0 = self.ctx.launch_count()
-            with torch.cuda.graph(graph):
+            # (thread_local: the NCCL watchdog thread polls events while this thread captures; under the default
+            #  "global" mode such a call from another thread can invalidate the capture)
+            with torch.cuda.graph(graph, capture_error_mode="thread_local" if self.dist is not None else "global"):
                 body()
             g = self._graphs[key] = (graph, self.ctx.launch_count() - n0)
         g[0].replay()
