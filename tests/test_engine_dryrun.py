@@ -115,3 +115,23 @@ def test_df_sampler_engine_ceil_halving():
     assert [d[:2] for d in eng.roi_pyr.dims] == [(48, 48), (24, 24), (12, 12), (6, 6), (3, 3), (2, 2), (1, 1)]
     assert eng.roi_flat == 1 * 1 * 64 * 7          # same FC input as --model=101's 64x64 crops: the checkpoints interchange
     assert _check_program(eng.p_fwd_gen) > 0
+
+
+def test_side_stream_schedule_of_the_programs():
+    """Two-stream launch schedule (engine.Program): the background branch of the encoder forward is tagged for the side
+    stream and joined before the embedding is assembled; in the backward programs every filter gradient is tagged for the
+    side stream, and a python hook (an all-reduce of a finished gradient slice) is a join point."""
+    eng = engine.Stage1Engine(DryContext(), engine.NetConfig(**SMALL), 2, mode="dcgan", device="cpu")
+    p = eng.p_fwd_enc
+    names = [c[0] for c in p.calls]
+    join = next(i for i, c in enumerate(p.calls) if c[0] is None and c[1] is None)
+    assert names[join + 1] == "embedding_assemble" and all(i < join for i in p.side)
+    n_bg_convs = len(eng.n_bg)
+    assert sum(1 for i in p.side if names[i] == "conv2d_fwd") == n_bg_convs and len(p.side) == n_bg_convs + 2
+    # the main-stream calls between the first side call and the join are the ROI branch: they never touch a bg buffer
+    b = eng.p_bwd_gen
+    wg = [i for i, c in enumerate(b.calls) if c[0] == "conv2d_bwd_filter"]
+    assert set(wg) - b.side == {i for i in wg if "patch form" in b.calls[i][4]}      # the two patch-form wgrads stay in order
+    assert all(b.calls[i][0] == "conv2d_bwd_filter" for i in b.side)
+    fwd_only = engine.Stage1Engine(DryContext(), engine.NetConfig(**SMALL), 2, mode="dcgan", device="cpu", inference=True)
+    assert fwd_only.p_fwd_enc.side == p.side
