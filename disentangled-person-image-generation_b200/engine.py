@@ -251,6 +251,12 @@ def _mask(pixels, c, device):
     return torch.zeros((pixels, (c + 31) // 32), dtype=torch.int32, device=device)
 
 
+def unpack_bits(mask, n, h, w, c):
+    """A saved activation bit mask (one int32 word per pixel and 32 channels) as a bool [n, h, w, c] tensor."""
+    bits = (mask.unsqueeze(-1) >> torch.arange(32, device=mask.device, dtype=torch.int32)) & 1
+    return bits.reshape(mask.shape[0], -1)[:, :c].reshape(n, h, w, c).bool()
+
+
 class _Pyramid:
     """`repeat_num` levels of {conv, conv, +res, [conv/s2]} (models.py:421-429, 454-462, 530-539)."""
 
@@ -284,6 +290,17 @@ class _Pyramid:
         self.gd = [SplitTensor(n, self.dims[i + 1][0], self.dims[i + 1][1], self.dims[i + 1][2], dev)
                    for i in range(rn - 1)]
         self.g_in = SplitTensor(n, h, w, hn, dev)  # grad wrt the pyramid input (masked if in_mask)
+
+    def sign_bits(self):
+        """The ReLU bits of the 3*rn - 1 convolutions in creation order (diagnostics, see Stage1Engine.activation_bits)."""
+        out = []
+        for idx in range(self.rn):
+            hh, ww, c = self.dims[idx]
+            out += [unpack_bits(self.ma[idx], self.n, hh, ww, c), unpack_bits(self.mb[idx], self.n, hh, ww, c)]
+            if idx < self.rn - 1:
+                nx = self.x_in[idx + 1]
+                out.append(unpack_bits(self.md[idx], self.n, nx.h, nx.w, nx.c))
+        return out
 
     def forward(self, eng, prog, side=False):
         li = 0
@@ -360,6 +377,13 @@ class _DiscPass:
         self.g_h = [SplitTensor(n, H >> (i + 1), W >> (i + 1), d << i, dev) for i in range(4)]  # grad wrt activated
         self.g_pre = [SplitTensor(n, H >> (i + 1), W >> (i + 1), d << i, dev) for i in range(4)]  # grad wrt conv out
         self.g_x = torch.zeros((n, H, W, 3), device=dev)
+
+
+    def sign_bits(self, i):
+        """The saved `pre-activation > 0` bits of layer i (0-based) as a bool NHWC tensor -- what the backward pass of
+        LeakyReLU branches on (diagnostics; tests hand them to the oracle, oracle/nets.py dcgan_discriminator)."""
+        h = self.h[i]
+        return unpack_bits(self.m[i], h.n, h.h, h.w, h.c)
 
 
 class _DiscHalf:
@@ -1497,6 +1521,33 @@ class Stage1Engine:
         self.g_G.copy_(self.d_fake.g_x)
         self.ctx.loss_l1(ptr(self.G), ptr(self.x), self.G.numel(), 20.0, ptr(self.loss_l1), ptr(self.g_G), s)
         self.p_bwd_gen.run(s, timings)
+
+    def activation_bits(self):
+        """Every ReLU / LeakyReLU decision of the last forward pass, keyed and ordered as oracle/nets.py takes them
+        (`branches` of stage1_forward): the backward programs gate gradients with exactly these bits.  Diagnostics --
+        a device->host sized read; tests use it to put the float64 oracle on the engine's linear piece."""
+        cfg = self.cfg
+        B, H, W, hn, rn = self.B, cfg.img_h, cfg.img_w, cfg.hidden, cfg.unet_repeat
+        enc = [unpack_bits(m, B, H, W, hn) for m in (self.me0, self.me1, self.me2)] + self.roi_pyr.sign_bits()
+        if cfg.fgbg:
+            enc += self.bg_pyr.sign_bits()
+        gen = [unpack_bits(self.mg0, B, H, W, hn)] + self.genc.sign_bits()
+        for idx in range(rn):
+            c = self.dec_c[idx][1]
+            lvl = rn - 1 - idx
+            hh, ww = H >> lvl, W >> lvl
+            gen += [unpack_bits(self.dec_ma[idx], B, hh, ww, c), unpack_bits(self.dec_mb[idx], B, hh, ww, c)]
+            if idx < rn - 1:      # the 1x1 conv runs before the x2 upsample here (after it in models.py:569-570)
+                gen.append(unpack_bits(self.dec_mu[idx], B, hh, ww, self.dec_c[idx + 1][0]))
+        out = {"Encoder/G_encoder": enc, "ID_AE/G": gen}
+        if cfg.d_joint:
+            out["D_pair"] = [self.d_pair.sign_bits(i) for i in range(4)]
+        else:
+            out["D_real"] = [self.d_real.sign_bits(i) for i in range(4)]
+            out["D_fake"] = [self.d_fake.sign_bits(i) for i in range(4)]
+        if hasattr(self, "d_hat"):
+            out["D_hat"] = [self.d_hat.sign_bits(i) for i in range(4)]
+        return {k: [t.cpu() for t in v] for k, v in out.items()}
 
     def d_grads(self, timings=None):
         """Forward + backward of d_loss w.r.t. the discriminator (trainer.py:601-605, 625)."""

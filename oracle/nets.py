@@ -183,14 +183,25 @@ def is_disc_param(name):
 class _Walker:
     """Hands out the slim layer names in creation order while a graph function runs."""
 
-    def __init__(self, prefix, p):
+    def __init__(self, prefix, p, branches=None):
+        """branches (test aid, see dcgan_discriminator): {prefix: [bool NHWC tensor per activated conv, in creation
+        order]} -- `conv output > 0` as the implementation under test decided it; ReLU then gates with those bits."""
         self.prefix, self.p, self.nconv, self.nfc = prefix, p, 0, 0
+        self.signs = iter(branches[prefix]) if branches else None
 
     def conv(self, x, stride=1, act=True):
         name = "%s/Conv%s" % (self.prefix, "" if self.nconv == 0 else "_%d" % self.nconv)
         self.nconv += 1
         y = T.conv2d_same(x, self.p[name + "/weights"], self.p[name + "/biases"], stride)
-        return torch.relu(y) if act else y  # trainers pass activation_fn=tf.nn.relu (trainer.py:581, 595)
+        if not act:
+            return y
+        if self.signs is None:
+            return torch.relu(y)  # trainers pass activation_fn=tf.nn.relu (trainer.py:581, 595)
+        sign = next(self.signs)
+        if sign.shape[1] * 2 == y.shape[1]:     # bits taken before a nearest-neighbour x2 upsample (1x1 conv after it)
+            sign = sign.repeat_interleave(2, dim=1).repeat_interleave(2, dim=2)
+        assert sign.shape == y.shape, (name, sign.shape, y.shape)
+        return torch.where(sign, y, torch.zeros_like(y))
 
     def fc(self, x):
         name = "%s/fully_connected%s" % (self.prefix, "" if self.nfc == 0 else "_%d" % self.nfc)
@@ -218,10 +229,10 @@ def _pyramid(w, x, hn, rn, taps=None, tag=""):
     return x
 
 
-def encoder_fgbg(p, cfg, x, fg_mask, roi_bbox, roi_vis, taps=None):
+def encoder_fgbg(p, cfg, x, fg_mask, roi_bbox, roi_vis, taps=None, branches=None):
     """models.py:390-471.  x [B,H,W,3]; fg_mask [B,H,W,1]; roi_bbox int [B,7,4] (y1,x1,y2,x2 pixels);
     roi_vis [B,7].  Returns the [B,352] embedding."""
-    w = _Walker("Encoder/G_encoder", p)
+    w = _Walker("Encoder/G_encoder", p, branches)
     B, H, W, _ = x.shape
     x = w.conv(x)
     res = x
@@ -247,12 +258,12 @@ def encoder_fgbg(p, cfg, x, fg_mask, roi_bbox, roi_vis, taps=None):
     return torch.cat(feats, dim=-1)
 
 
-def encoder_roi(p, cfg, x, roi_bbox, roi_vis, taps=None):
+def encoder_roi(p, cfg, x, roi_bbox, roi_vis, taps=None, branches=None):
     """models.GeneratorCNN_ID_Encoder_BodyROIVis (models.py:328-388; the DeepFashion encoder, trainer_256.py:40-41):
     same stem / residual block / 7 ROI crops / shared pyramid / FC / visibility gating as the two-branch encoder,
     but the crops are taken from the unmasked feature map and there is no background branch.
     Returns the [B, n_parts*part_z] embedding."""
-    w = _Walker("Encoder/G_encoder", p)
+    w = _Walker("Encoder/G_encoder", p, branches)
     B, H, W, _ = x.shape
     x = w.conv(x)
     res = x
@@ -274,17 +285,17 @@ def encoder_roi(p, cfg, x, roi_bbox, roi_vis, taps=None):
     return torch.cat(feats, dim=-1)
 
 
-def encoder(p, cfg, batch, taps=None):
+def encoder(p, cfg, batch, taps=None, branches=None):
     """The appearance encoder the config selects (trainer.py:581 / trainer_256.py:40)."""
     if cfg.fgbg:
-        return encoder_fgbg(p, cfg, batch["x"], batch["mask"], batch["part_bbox"], batch["part_vis"], taps)
-    return encoder_roi(p, cfg, batch["x"], batch["part_bbox"], batch["part_vis"], taps)
+        return encoder_fgbg(p, cfg, batch["x"], batch["mask"], batch["part_bbox"], batch["part_vis"], taps, branches)
+    return encoder_roi(p, cfg, batch["x"], batch["part_bbox"], batch["part_vis"], taps, branches)
 
 
-def unet_generator(p, cfg, emb, pose, taps=None):
+def unet_generator(p, cfg, emb, pose, taps=None, branches=None):
     """trainer.py:588-590 (spatial broadcast of the embedding) + models.py:518-576.
     emb [B,352]; pose [B,H,W,18].  Returns (G [B,H,W,3], z [B,z_num])."""
-    w = _Walker("ID_AE/G", p)
+    w = _Walker("ID_AE/G", p, branches)
     B = emb.shape[0]
     H, W = pose.shape[1], pose.shape[2]
     hn, rn = cfg.hidden, cfg.unet_repeat
@@ -316,16 +327,23 @@ def unet_generator(p, cfg, emb, pose, taps=None):
     return out, z
 
 
-def dcgan_discriminator(p, cfg, x_nhwc, mode="dcgan"):
+def dcgan_discriminator(p, cfg, x_nhwc, mode="dcgan", lrelu_signs=None):
     """wgan_gp.py:407-440 on an NHWC image (the reference transposes to NCHW first, trainer.py:601-602;
-    the only place the layout matters is the flatten before the Linear, done C-major below)."""
+    the only place the layout matters is the flatten before the Linear, done C-major below).
+    lrelu_signs (test aid): four bool NHWC tensors, `pre-activation > 0` per layer as the implementation under test
+    decided it.  LeakyReLU then takes its branch from them, so that a gradient comparison differentiates the same
+    piecewise-linear function on both sides; a pre-activation within fp32 rounding of zero otherwise flips the branch
+    in one of the two and moves the gradients by O(1/sqrt(#activations)) (tests/probe_grad_flake.py)."""
     norm = T.layernorm if mode == "wgan-gp" else T.batchnorm_train  # wgan_gp.py:34-40
+
+    def lrelu(z, i):
+        return T.leaky_relu(z) if lrelu_signs is None else torch.where(lrelu_signs[i], z, 0.2 * z)
     h = T.conv2d_same(x_nhwc, p["Discriminator.1.Filters"], p["Discriminator.1.Biases"], 2)
-    h = T.leaky_relu(h)
+    h = lrelu(h, 0)
     for i in (2, 3, 4):
         h = T.conv2d_same(h, p["Discriminator.%d.Filters" % i], p["Discriminator.%d.Biases" % i], 2)
         h = norm(h, p["Discriminator.BN%d.scale" % i], p["Discriminator.BN%d.offset" % i])
-        h = T.leaky_relu(h)
+        h = lrelu(h, i - 1)
     # NCHW flatten (index = c*(h*w) + y*w + x), then tf.reshape(output, [-1, 8*4*8*dim]) (wgan_gp.py:433): one row per
     # image at 128x64; at 256x256 the 16x16x512 map becomes 8 rows per image (64 channels each), i.e. 8 logits (q5)
     flat = h.permute(0, 3, 1, 2).reshape(-1, cfg.d_row)
@@ -354,22 +372,26 @@ def gaussian_fc_res(p, z, repeat_num=4, prefix="G_FC", act=torch.relu):
 
 
 # --------------------------------------------------------------------------------- Stage-I model
-def stage1_forward(p, cfg, batch, mode="dcgan", gp_alpha=None, lam=10.0, taps=None):
+def stage1_forward(p, cfg, batch, mode="dcgan", gp_alpha=None, lam=10.0, taps=None, branches=None):
     """build_model of --model=1 (trainer.py:568-625).  batch: dict x, pose, mask, part_bbox, part_vis.
-    Returns dict with emb, z, G, D_real, D_fake, g_loss (incl. 20*L1), d_loss, L1."""
+    Returns dict with emb, z, G, D_real, D_fake, g_loss (incl. 20*L1), d_loss, L1.
+    branches (test aid): the ReLU / LeakyReLU decisions of the implementation under test -- keys "Encoder/G_encoder",
+    "ID_AE/G" (see _Walker) and "D_real", "D_fake" (or "D_pair"), "D_hat" (see dcgan_discriminator).  The graph is
+    piecewise linear in its activations; a gradient comparison means something only on the same piece."""
     x = batch["x"]
-    emb = encoder(p, cfg, batch, taps)
-    G, z = unet_generator(p, cfg, emb, batch["pose"], taps)
+    br = branches or {}
+    emb = encoder(p, cfg, batch, taps, branches)
+    G, z = unet_generator(p, cfg, emb, batch["pose"], taps, branches)
     if cfg.d_joint:   # trainer_256.py:61-66: one call on concat([x, G]) (joint batch statistics), then tf.split(D_z, 2)
-        d_both = dcgan_discriminator(p, cfg, torch.cat([x, G], dim=0), mode)
+        d_both = dcgan_discriminator(p, cfg, torch.cat([x, G], dim=0), mode, br.get("D_pair"))
         d_real, d_fake = d_both[:d_both.shape[0] // 2], d_both[d_both.shape[0] // 2:]
     else:             # trainer.py:601-602: two calls
-        d_real = dcgan_discriminator(p, cfg, x, mode)
-        d_fake = dcgan_discriminator(p, cfg, G, mode)
+        d_real = dcgan_discriminator(p, cfg, x, mode, br.get("D_real"))
+        d_fake = dcgan_discriminator(p, cfg, G, mode, br.get("D_fake"))
     g_gan, d_loss = T.gan_loss(mode, d_real, d_fake)
     out = dict(emb=emb, z=z, G=G, D_real=d_real, D_fake=d_fake)
     if mode == "wgan-gp" and gp_alpha is not None:
-        gp, slopes, _ = T.gradient_penalty(lambda t: dcgan_discriminator(p, cfg, t, mode), x, G, gp_alpha)
+        gp, slopes, _ = T.gradient_penalty(lambda t: dcgan_discriminator(p, cfg, t, mode, br.get("D_hat")), x, G, gp_alpha)
         d_loss = d_loss + lam * gp
         out.update(gp=gp, slopes=slopes)
     l1 = (G - x).abs().mean()
@@ -377,10 +399,10 @@ def stage1_forward(p, cfg, batch, mode="dcgan", gp_alpha=None, lam=10.0, taps=No
     return out
 
 
-def stage1_grads(p, cfg, batch, which, mode="dcgan", gp_alpha=None):
+def stage1_grads(p, cfg, batch, which, mode="dcgan", gp_alpha=None, branches=None):
     """Gradients of g_loss w.r.t. Encoder+G params (which='g') or of d_loss w.r.t. D params (which='d');
     what Optimizer.minimize(var_list=...) differentiates (trainer.py:622-625)."""
-    out = stage1_forward(p, cfg, batch, mode, gp_alpha)
+    out = stage1_forward(p, cfg, batch, mode, gp_alpha, branches=branches)
     if which == "g":
         names = [k for k in p if is_generator_param(k)]
         loss = out["g_loss"]

@@ -1,7 +1,7 @@
 """Run under torchrun with 2+ ranks on GPUs: the data-parallel step with the overlapped ID_AE all-reduce (default),
 with one all-reduce after the backward pass (DPIG_OVERLAP=0) and with the NCCL exchanges captured into the step graphs
 (the default; DPIG_GRAPHS=0 replays eager launch lists) must leave identical weights on every rank and agree with each other up to the fp32-atomic noise.
-    python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1 tools/ddp_check.py"""
+    python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1 tests/ddp_check.py"""
 import os
 import sys
 
@@ -56,13 +56,17 @@ def oracle_parity(dist):
     gather = lambda t: (lambda out: (td.all_gather(out, t.contiguous()), torch.cat(out))[1])(  # noqa: E731
         [torch.empty_like(t) for _ in range(dist.world_size)])
     lr, lf, G = gather(eng.d_real.logits), gather(eng.d_fake.logits), gather(eng.G)
+    signs = [[gather(dp.sign_bits(i).to(torch.uint8)).bool().cpu() for i in range(4)] for dp in (eng.d_real, eng.d_fake)]
     dl = torch.tensor([eng.losses()[1]], device=G.device)
     dist.all_reduce_sum(dl)
     ok = True
     if dist.rank == 0:
         p = nets.to_torch(params, torch.float64, requires_grad=True)
-        d_real = nets.dcgan_discriminator(p, ocfg, torch.tensor(gb["x"], dtype=torch.float64), "dcgan")
-        d_fake = nets.dcgan_discriminator(p, ocfg, G.double().cpu(), "dcgan")
+        # the oracle takes the LeakyReLU branches the ranks took (their saved sign bits): one pre-activation within fp32
+        # rounding of zero otherwise flips a branch between fp32 and float64 and moves these gradients by ~6e-3 -- seen
+        # on one 8-GPU run; tests/probe_grad_flake.py shows the error stays at 2e-5 with the bits and jumps without
+        d_real = nets.dcgan_discriminator(p, ocfg, torch.tensor(gb["x"], dtype=torch.float64), "dcgan", signs[0])
+        d_fake = nets.dcgan_discriminator(p, ocfg, G.double().cpu(), "dcgan", signs[1])
         _, d_loss = T.gan_loss("dcgan", d_real, d_fake)
         names = ["Discriminator.BN%d.scale" % i for i in (2, 3, 4)]
         gs = torch.autograd.grad(d_loss, [p[k] for k in names])
@@ -73,11 +77,7 @@ def oracle_parity(dist):
         for k, g in zip(names, gs):
             off, n, _ = eng.dp.specs[k]
             e_g = max(e_g, float((grad[off:off + n].double().cpu() - g).norm() / g.norm()))
-        # forward quantities: the north-star bound.  Gradients: at this reduced geometry the last critic layers hold 32
-        # values per channel, and ONE LeakyReLU sign bit that differs between the fp32 engine and the fp64 oracle (a
-        # pre-activation within 1e-6 of zero) moves a BatchNorm-scale gradient by ~6e-3: runs land at 1e-5 .. 6e-4 or, with
-        # such a flip, at ~6e-3 (seen with thread-simulated ranks in tests/test_dp_gpu.py too) -- the bound covers that.
-        ok = e_log < 1e-3 and e_loss < 1e-3 and e_g < 2e-2
+        ok = e_log < 1e-3 and e_loss < 1e-3 and e_g < 1e-3
         print("ddp_check oracle parity (global batch %d over %d ranks): logits %.2e d_loss %.2e BN-scale grads %.2e -> %s"
               % (B, dist.world_size, e_log, e_loss, e_g, "OK" if ok else "FAIL"), flush=True)
     flag = torch.tensor([1.0 if ok else 0.0], device=G.device)

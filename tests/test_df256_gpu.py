@@ -26,8 +26,10 @@ from oracle import tf_ops as T  # noqa: E402
 pytestmark = pytest.mark.gpu
 
 TOL_ABS = 1e-3
-TOL_GVJP = 6e-2
-TOL_DVJP = 3e-2
+# relative L2 per parameter tensor with the oracle on the engine's ReLU / LeakyReLU branches (see test_stage1_gpu.py):
+# measured 2.5e-5 (generator) and 2.1e-5 (critic; 2.0e-4 on the scalar Output.b)
+TOL_GVJP = 5e-4
+TOL_DVJP = 1e-3
 DF_SMALL = dict(img_h=128, img_w=128, hidden=64, roi_size=32)
 
 
@@ -106,7 +108,8 @@ def check_generator_vjp(small=True, batch=2):
     s = torch.cuda.current_stream().cuda_stream
     eng.forward(with_disc=False)
     taps = {}
-    out = nets.stage1_forward(p, cfg, ob, "dcgan", taps=taps)
+    gen_bits = {k: v for k, v in eng.activation_bits().items() if "/" in k}     # the generator's ReLU decisions
+    out = nets.stage1_forward(p, cfg, ob, "dcgan", taps=taps, branches=gen_bits)
     names = [k for k in p if nets.is_generator_param(k)]
     grads = torch.autograd.grad(out["g_loss"], [p[k] for k in names] + [taps["G"]])
     eng.gp.grad.zero_()
@@ -127,8 +130,9 @@ def check_disc_vjp(small=True, batch=2):
     Gc = eng.G.detach().double().cpu()
     names = [k for k in p if nets.is_disc_param(k)]
 
-    def both(g):
-        d = nets.dcgan_discriminator(p, cfg, torch.cat([ob["x"], g], dim=0), "dcgan")
+    def both(g):      # on the LeakyReLU branches the engine's joint pass took (tests/probe_grad_flake.py)
+        bits = [eng.d_pair.sign_bits(i).cpu() for i in range(4)]
+        d = nets.dcgan_discriminator(p, cfg, torch.cat([ob["x"], g], dim=0), "dcgan", bits)
         return d[:d.shape[0] // 2], d[d.shape[0] // 2:]
 
     d_real, d_fake = both(Gc)

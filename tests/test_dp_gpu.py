@@ -4,7 +4,7 @@ the critic in the forward pass, the (sum dy, sum dy*xhat) sums in its backward p
 before the optimiser -- must give the same D logits, d_loss, critic gradients and post-step weights, and both must
 agree with the float64 oracle on the GLOBAL batch (reference trainer.py:601-605: D(x), D(G) with batch statistics,
 tflib/ops/batchnorm.py:29-30).  The ranks run as threads on one GPU (ddp.LocalGroup) through the same `dist` hooks
-torch.distributed uses; tools/ddp_check.py repeats the comparison under torchrun with NCCL.
+torch.distributed uses; tests/ddp_check.py repeats the comparison under torchrun with NCCL.
 """
 import os
 import sys
@@ -34,6 +34,8 @@ def _sequence(eng, batch_d, batch_g):
     torch.cuda.current_stream().synchronize()
     rec = dict(logits_real=eng.d_real.logits.detach().clone(), logits_fake=eng.d_fake.logits.detach().clone(),
                G=eng.G.detach().clone(), d_loss=eng.losses()[1], dgrad=eng.dp.grad.detach().clone())
+    for i in range(4):       # the LeakyReLU branch bits the backward pass used
+        rec["sign_real%d" % i], rec["sign_fake%d" % i] = eng.d_real.sign_bits(i), eng.d_fake.sign_bits(i)
     eng.d_step()
     eng.set_batch(batch_g)
     eng.g_step()
@@ -95,8 +97,10 @@ def run_dp_equivalence(small, B=4, world=2):
     p = nets.to_torch(params, torch.float64, requires_grad=True)
     x = torch.tensor(bd["x"], dtype=torch.float64)
     Gc = cat("G").double().cpu()
-    d_real = nets.dcgan_discriminator(p, ocfg, x, "dcgan")
-    d_fake = nets.dcgan_discriminator(p, ocfg, Gc, "dcgan")
+    # LeakyReLU branches as the ranks took them: a pre-activation within fp32 rounding of zero otherwise flips one
+    # branch between fp32 and float64 and moves the gradients by ~6e-3 at this size (tests/probe_grad_flake.py)
+    d_real = nets.dcgan_discriminator(p, ocfg, x, "dcgan", [cat("sign_real%d" % i).cpu() for i in range(4)])
+    d_fake = nets.dcgan_discriminator(p, ocfg, Gc, "dcgan", [cat("sign_fake%d" % i).cpu() for i in range(4)])
     _, d_loss = T.gan_loss("dcgan", d_real, d_fake)
     names = [k for k in p if nets.is_disc_param(k)]
     grads = torch.autograd.grad(d_loss, [p[k] for k in names])
@@ -124,7 +128,9 @@ def test_two_ranks_equal_one_engine_and_the_oracle(small):
     # forward: the per-image generator is identical work; the critic sees the same global statistics
     # (measured on B200: G 7e-6 / 1.1e-5, logits 1e-5 / 1.1e-4, d_loss 6e-7 -- two tilings of the same sums)
     assert rep["G"] < 1e-4 and rep["logits_real"] < 5e-4 and rep["logits_fake"] < 5e-4 and rep["d_loss"] < 2e-4, rep
-    # critic gradient after the exchange (fp32 atomics + split-bf16 gradients: measured 2.1e-3 between the two tilings)
+    # critic gradient after the exchange, engine against engine: measured 2e-5 small, 3.8e-3 full -- the two tilings round
+    # differently and may sit on different LeakyReLU branches where a pre-activation is ~0; each agrees with the oracle
+    # on its own branches to 3e-5 (below)
     assert rep["dgrad_rel"] < 1e-2, rep
     for k, v in rep.items():
         if k.startswith("grad "):
@@ -133,9 +139,8 @@ def test_two_ranks_equal_one_engine_and_the_oracle(small):
             assert v[0] <= 0.25 * v[1], (k, rep)
     # against the float64 oracle on the global batch (north-star bound on the logits; DVJP bound on the gradients)
     assert rep["oracle logits_real"] < 1e-3 and rep["oracle logits_fake"] < 1e-3 and rep["oracle d_loss"] < 1e-3, rep
-    # (small geometry: the last critic layers normalise over 8 values per channel at this batch -- an ill-conditioned
-    #  BatchNorm backward; measured 6e-4 .. 6e-3 from run to run with the fp32 atomics of the filter gradients)
-    assert rep["oracle dgrad_rel_worst"] < (2e-2 if small else 3e-2), rep
+    # (measured 2.9e-5 small / 2.6e-5 full with the oracle on the ranks' LeakyReLU branches; 6e-4 .. 6e-3 before that)
+    assert rep["oracle dgrad_rel_worst"] < 5e-4, rep
 
 
 if __name__ == "__main__":
