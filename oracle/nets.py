@@ -187,7 +187,9 @@ class _Walker:
         """branches (test aid, see dcgan_discriminator): {prefix: [bool NHWC tensor per activated conv, in creation
         order]} -- `conv output > 0` as the implementation under test decided it; ReLU then gates with those bits."""
         self.prefix, self.p, self.nconv, self.nfc = prefix, p, 0, 0
-        self.signs = iter(branches[prefix]) if branches else None
+        self.signs = iter(branches[prefix]) if branches and prefix in branches else None
+        # branches["record"] (a dict): filled with the decisions this run takes, in the same layout
+        self.rec = branches["record"].setdefault(prefix, []) if branches and "record" in branches else None
 
     def conv(self, x, stride=1, act=True):
         name = "%s/Conv%s" % (self.prefix, "" if self.nconv == 0 else "_%d" % self.nconv)
@@ -195,6 +197,8 @@ class _Walker:
         y = T.conv2d_same(x, self.p[name + "/weights"], self.p[name + "/biases"], stride)
         if not act:
             return y
+        if self.rec is not None:
+            self.rec.append(y.detach() > 0)
         if self.signs is None:
             return torch.relu(y)  # trainers pass activation_fn=tf.nn.relu (trainer.py:581, 595)
         sign = next(self.signs)
@@ -327,7 +331,7 @@ def unet_generator(p, cfg, emb, pose, taps=None, branches=None):
     return out, z
 
 
-def dcgan_discriminator(p, cfg, x_nhwc, mode="dcgan", lrelu_signs=None):
+def dcgan_discriminator(p, cfg, x_nhwc, mode="dcgan", lrelu_signs=None, record=None):
     """wgan_gp.py:407-440 on an NHWC image (the reference transposes to NCHW first, trainer.py:601-602;
     the only place the layout matters is the flatten before the Linear, done C-major below).
     lrelu_signs (test aid): four bool NHWC tensors, `pre-activation > 0` per layer as the implementation under test
@@ -337,6 +341,8 @@ def dcgan_discriminator(p, cfg, x_nhwc, mode="dcgan", lrelu_signs=None):
     norm = T.layernorm if mode == "wgan-gp" else T.batchnorm_train  # wgan_gp.py:34-40
 
     def lrelu(z, i):
+        if record is not None:     # a list: receives this run's own decisions
+            record.append(z.detach() > 0)
         return T.leaky_relu(z) if lrelu_signs is None else torch.where(lrelu_signs[i], z, 0.2 * z)
     h = T.conv2d_same(x_nhwc, p["Discriminator.1.Filters"], p["Discriminator.1.Biases"], 2)
     h = lrelu(h, 0)
@@ -380,18 +386,20 @@ def stage1_forward(p, cfg, batch, mode="dcgan", gp_alpha=None, lam=10.0, taps=No
     piecewise linear in its activations; a gradient comparison means something only on the same piece."""
     x = batch["x"]
     br = branches or {}
+    rec = (lambda k: br["record"].setdefault(k, [])) if "record" in br else (lambda k: None)
     emb = encoder(p, cfg, batch, taps, branches)
     G, z = unet_generator(p, cfg, emb, batch["pose"], taps, branches)
     if cfg.d_joint:   # trainer_256.py:61-66: one call on concat([x, G]) (joint batch statistics), then tf.split(D_z, 2)
-        d_both = dcgan_discriminator(p, cfg, torch.cat([x, G], dim=0), mode, br.get("D_pair"))
+        d_both = dcgan_discriminator(p, cfg, torch.cat([x, G], dim=0), mode, br.get("D_pair"), rec("D_pair"))
         d_real, d_fake = d_both[:d_both.shape[0] // 2], d_both[d_both.shape[0] // 2:]
     else:             # trainer.py:601-602: two calls
-        d_real = dcgan_discriminator(p, cfg, x, mode, br.get("D_real"))
-        d_fake = dcgan_discriminator(p, cfg, G, mode, br.get("D_fake"))
+        d_real = dcgan_discriminator(p, cfg, x, mode, br.get("D_real"), rec("D_real"))
+        d_fake = dcgan_discriminator(p, cfg, G, mode, br.get("D_fake"), rec("D_fake"))
     g_gan, d_loss = T.gan_loss(mode, d_real, d_fake)
     out = dict(emb=emb, z=z, G=G, D_real=d_real, D_fake=d_fake)
     if mode == "wgan-gp" and gp_alpha is not None:
-        gp, slopes, _ = T.gradient_penalty(lambda t: dcgan_discriminator(p, cfg, t, mode, br.get("D_hat")), x, G, gp_alpha)
+        gp, slopes, _ = T.gradient_penalty(lambda t: dcgan_discriminator(p, cfg, t, mode, br.get("D_hat"), rec("D_hat")),
+                                           x, G, gp_alpha)
         d_loss = d_loss + lam * gp
         out.update(gp=gp, slopes=slopes)
     l1 = (G - x).abs().mean()

@@ -234,3 +234,69 @@ def test_ops_against_scipy_as_a_third_implementation():
         got = T.sigmoid_ce(z, torch.full_like(z, lab)).numpy()
         ok = np.isfinite(ref)
         assert np.allclose(got[ok], ref[ok], rtol=1e-10, atol=1e-12)
+
+
+def _small_batch(cfg, n=2, seed=5):
+    from dpig_b200 import synth
+    b = synth.make_batch(n, cfg.img_h, cfg.img_w, seed=seed)
+    return dict(x=torch.tensor(b["x"], dtype=torch.float64), mask=torch.tensor(b["mask"], dtype=torch.float64),
+                pose=T.pose_rasterize(torch.tensor(b["pose_rcv"], dtype=torch.float64), cfg.img_h, cfg.img_w),
+                part_bbox=torch.tensor(b["part_bbox"][:, :7]), part_vis=torch.tensor(b["part_vis"][:, :7]))
+
+
+def test_forced_branches_reproduce_the_free_run_and_move_gradients_when_flipped():
+    """`branches` (the test aid the GPU gradient tests rest on): a run that is handed its own recorded ReLU / LeakyReLU
+    decisions is the free run bit for bit -- values and gradients; flipping ONE late critic bit leaves the loss where it
+    was to first order and moves a BatchNorm-scale gradient visibly (what tests/probe_grad_flake.py measures on the GPU)."""
+    cfg = nets.NetConfig(img_h=32, img_w=16, hidden=64, roi_size=12, d_dim=64)
+    p = nets.to_torch(nets.init_params(cfg, bias_noise=0.05), torch.float64, requires_grad=True)
+    batch = _small_batch(cfg)
+    rec = {}
+    out0, g0 = nets.stage1_grads(p, cfg, batch, "g", branches={"record": rec})
+    assert set(rec) == {"Encoder/G_encoder", "ID_AE/G", "D_real", "D_fake"}
+    assert len(rec["Encoder/G_encoder"]) == 3 + 2 * (3 * cfg.enc_repeat - 1) and len(rec["D_fake"]) == 4
+    assert len(rec["ID_AE/G"]) == 1 + (3 * cfg.unet_repeat - 1) + (3 * cfg.unet_repeat - 1)
+    out1, g1 = nets.stage1_grads(p, cfg, batch, "g", branches=rec)
+    assert torch.equal(out0["G"], out1["G"]) and torch.equal(out0["D_fake"], out1["D_fake"])
+    for k in g0:
+        assert torch.equal(g0[k], g1[k]), k
+    # one flipped bit in the third critic layer of the D(G) pass
+    _, d0 = nets.stage1_grads(p, cfg, batch, "d", branches=rec)
+    flipped = dict(rec)
+    flipped["D_fake"] = [t.clone() for t in rec["D_fake"]]
+    flipped["D_fake"][2][0, 0, 0, 0] ^= True
+    _, d1 = nets.stage1_grads(p, cfg, batch, "d", branches=flipped)
+    k = "Discriminator.BN2.scale"
+    rel = float((d1[k] - d0[k]).norm() / d0[k].norm())
+    assert 1e-5 < rel < 0.5, rel
+
+
+def test_engine_activation_bits_have_the_oracles_layout():
+    """Stage1Engine.activation_bits() (what the GPU gradient tests hand to the oracle) against the oracle's own record:
+    same keys, same number of activated layers in the same order, same shapes -- except the 1x1 convs of the decoder,
+    which the engine runs BEFORE the x2 upsample (half the height and width; the oracle repeats the bits).  Buffers on the
+    CPU, nothing launched."""
+    from test_engine_dryrun import DryContext
+    from dpig_b200 import engine
+    cases = [("market", dict(img_h=32, img_w=16, hidden=64, roi_size=12, d_dim=64), nets.NetConfig, engine.NetConfig, "wgan-gp"),
+             ("deepfashion", dict(img_h=64, img_w=64, hidden=64, roi_size=16), nets.NetConfig.deepfashion,
+              engine.NetConfig.deepfashion, "dcgan")]
+    for name, kw, omk, emk, mode in cases:
+        ocfg, ecfg = omk(**kw), emk(**kw)
+        p = nets.to_torch(nets.init_params(ocfg), torch.float64)
+        rec = {}
+        with torch.no_grad():
+            alpha = torch.tensor([0.3, 0.8], dtype=torch.float64) if mode == "wgan-gp" else None
+            if alpha is None:
+                nets.stage1_forward(p, ocfg, _small_batch(ocfg), mode, branches={"record": rec})
+        if alpha is not None:
+            nets.stage1_forward(p, ocfg, _small_batch(ocfg), mode, gp_alpha=alpha, branches={"record": rec})
+        eng = engine.Stage1Engine(DryContext(), ecfg, 2, mode=mode, device="cpu")
+        bits = eng.activation_bits()
+        assert set(bits) == set(rec), (name, set(bits) ^ set(rec))
+        for key in rec:
+            assert len(bits[key]) == len(rec[key]), (name, key, len(bits[key]), len(rec[key]))
+            for i, (a, b) in enumerate(zip(bits[key], rec[key])):
+                same = tuple(a.shape) == tuple(b.shape)
+                half = (a.shape[0], 2 * a.shape[1], 2 * a.shape[2], a.shape[3]) == tuple(b.shape)
+                assert same or (key == "ID_AE/G" and half), (name, key, i, tuple(a.shape), tuple(b.shape))
