@@ -411,6 +411,11 @@ def main():
         eng, ctx = obj.net, obj.ctx
         d2h = 16
         dev_loader = PoolLoader(dev_pool)
+        # `value` / `e2e` are measured on the reference's work: every critic call runs the WHOLE frozen encoder, as its
+        # sess.run does (fg_embs / bg_embs are slices of the concatenated embedding, trainer.py:741-742).  The product default
+        # runs only the pyramid the trained factor reads (exact, Stage2Engine.prune); that rate is measured after the timed
+        # regions and reported beside the value as config.pruned_encoder.
+        obj.s2.prune = False
 
         def dev_step(i, timings=None):
             obj.s2.train_iteration(1 + i, dev_loader.next_batch)
@@ -475,6 +480,16 @@ def main():
 
     ms_dev, launches, clocks = timed(lambda: [dev_step(i) for i in range(K)])
     ms_e2e, _, clocks_e2e = timed(lambda: e2e_run(W, K))
+    pruned = None
+    if args.workload == "stage2":
+        obj.s2.prune = True
+        for i in range(W):
+            dev_step(i)                 # its own step graphs (captured on the third call of a kind)
+        ms_p, launches_p, _ = timed(lambda: [dev_step(i) for i in range(K)])
+        pruned = {"images_per_s": B * world * K / (ms_p * 1e-3), "ms_per_step": ms_p / K, "gpu_launches": launches_p,
+                  "what": "product default (DPIG_STAGE2_PRUNE=1): a critic call runs only the encoder pyramid its factor "
+                          "reads -- same updates, the other pyramid's output feeds nothing in that call"}
+        obj.s2.prune = False
 
     # ---- per-launch roofline figures: one more step OUTSIDE the timed regions, replayed launch by launch with CUDA events
     # around every C-ABI call (the timed steps are whole-step CUDA graph replays on one GPU)
@@ -563,6 +578,7 @@ def main():
                                    "sample": "tester.DPIG_FourNetsFgBg_testOnlySampleFactor.generate()"}[args.workload] +
                                   " with pinned host batches; losses / images read back every step"},
             "clocks": clocks,
+            **({"pruned_encoder": pruned} if pruned else {}),
             "e2e": {"value": e2e_v, "unit": "images/s", "ms_per_step": ms_e2e / K, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "clocks": clocks_e2e},
             "gpu_launches": launches,

@@ -954,6 +954,11 @@ class Stage1Engine:
         self._prog_forward_generator(self.p_fwd_gen)
         self.p_fwd_enc = Program(self.ctx)     # appearance encoder only (Stage-II real embeddings)
         self._prog_forward_encoder(self.p_fwd_enc)
+        self.p_fwd_enc_only = {}
+        if self.cfg.fgbg:                      # ... and with one of the two pyramids only (Stage2Engine.prune)
+            for which in ("roi", "bg"):
+                self.p_fwd_enc_only[which] = Program(self.ctx)
+                self._prog_forward_encoder(self.p_fwd_enc_only[which], branches=(which,))
         self.p_fwd_unet = Program(self.ctx)    # U-Net only, from self.emb / self.pose_rcv (sampling path, tester.py)
         self._prog_unet_forward(self.p_fwd_unet)
         if self.training:
@@ -1054,9 +1059,11 @@ class Stage1Engine:
         # ---- generator (trainer.py:588-590, models.py:518-576)
         self._prog_unet_forward(p)
 
-    def run_encoder(self, stream=None):
-        """Appearance-encoder forward only: fills self.emb [B, 352] for the current batch."""
-        self.p_fwd_enc.run(stream if stream is not None else torch.cuda.current_stream().cuda_stream)
+    def run_encoder(self, stream=None, only=None):
+        """Appearance-encoder forward only: fills self.emb [B, 352] for the current batch.  only = "roi" / "bg" (two-branch
+        encoder): that pyramid alone -- the other half of self.emb keeps whatever an earlier call left there."""
+        prog = self.p_fwd_enc_only[only] if only else self.p_fwd_enc
+        prog.run(stream if stream is not None else torch.cuda.current_stream().cuda_stream)
 
     def run_unet(self, stream=None):
         """U-Net forward from the embedding in self.emb and the keypoints in self.pose_rcv; fills self.G / self.G8."""
@@ -1069,7 +1076,9 @@ class Stage1Engine:
         self.p_d_fake_fwd.run(stream if stream is not None else torch.cuda.current_stream().cuda_stream)
         return self.d_fake.logits
 
-    def _prog_forward_encoder(self, p):
+    def _prog_forward_encoder(self, p, branches=("roi", "bg")):
+        """branches: which of the two pyramids run (both by default).  Stage-II trains one factor per optimiser call
+        (trainer.py:822-845); the other factor's pyramid feeds nothing in that call, see Stage2Engine.prune."""
         cfg, B = self.cfg, self.B
         H, W, hn, rn, P = cfg.img_h, cfg.img_w, cfg.hidden, cfg.enc_repeat, cfg.n_parts
         e0, e1, e2 = self.conv[self.n_e0], self.conv[self.n_e1], self.conv[self.n_e2]
@@ -1079,22 +1088,24 @@ class Stage1Engine:
         self.conv_fwd(p, self.e0_patch, self.x_patch, out=self.e0, mask_out=self.me0)
         self.conv_fwd(p, e1, self.e0, out=self.e1, mask_out=self.me1)
         self.conv_fwd(p, e2, self.e1, out=self.xs, addend=self.e0, mask_out=self.me2)
-        if cfg.fgbg:
+        if cfg.fgbg and "bg" in branches:
             # the background branch (models.py:454-464) depends on xs only: it runs on the side stream, concurrently with
             # the ROI branch -- the upper pyramid levels of either branch (8x4 / 3x3 maps) leave half of the SMs idle
+            side = "roi" in branches
             p.add("mask_split", self.xs.ref(), ptr(self.fg_mask), None, self.x_bg.ref())
-            self.bg_pyr.forward(self, p, side=True)
-            p.add("unpack_f32", self.bg_pyr.y[rn - 1].ref(), ptr(self.bg_flat_f32), hn * rn, side=True)
+            self.bg_pyr.forward(self, p, side=side)
+            p.add("unpack_f32", self.bg_pyr.y[rn - 1].ref(), ptr(self.bg_flat_f32), hn * rn, side=side)
             w, b, _, _ = self._linear(self.gp, self.n_bg_fc)
             p.add("linear_fwd", ptr(self.bg_flat_f32), ptr(w), ptr(b), ptr(self.bg_fea), B, self.bg_flat, self.bg_z,
-                  ACT_NONE, 0.0, side=True)
-        p.add("crop_and_resize_fwd", self.xs.ref(), ptr(self.fg_mask) if cfg.fgbg else None, ptr(self.boxes),
-              ptr(self.box_ind), P * B, self.rois.ref())
-        self.roi_pyr.forward(self, p)
-        p.add("unpack_f32", self.roi_pyr.y[rn - 1].ref(), ptr(self.roi_flat_f32), hn * rn)
-        w, b, _, _ = self._linear(self.gp, self.n_roi_fc)
-        p.add("linear_fwd", ptr(self.roi_flat_f32), ptr(w), ptr(b), ptr(self.fea), P * B, self.roi_flat, cfg.part_z,
-              ACT_NONE, 0.0)
+                  ACT_NONE, 0.0, side=side)
+        if "roi" in branches:
+            p.add("crop_and_resize_fwd", self.xs.ref(), ptr(self.fg_mask) if cfg.fgbg else None, ptr(self.boxes),
+                  ptr(self.box_ind), P * B, self.rois.ref())
+            self.roi_pyr.forward(self, p)
+            p.add("unpack_f32", self.roi_pyr.y[rn - 1].ref(), ptr(self.roi_flat_f32), hn * rn)
+            w, b, _, _ = self._linear(self.gp, self.n_roi_fc)
+            p.add("linear_fwd", ptr(self.roi_flat_f32), ptr(w), ptr(b), ptr(self.fea), P * B, self.roi_flat, cfg.part_z,
+                  ACT_NONE, 0.0)
         p.add_join()
         p.add("embedding_assemble", ptr(self.fea), ptr(self.bg_fea), ptr(self.vis), B, P, cfg.part_z, self.bg_z,
               ptr(self.emb), 0)

@@ -391,6 +391,9 @@ class Stage2Engine:
         gmode = int(os.environ.get("DPIG_GRAPHS", "1"))
         self.use_graphs = gmode >= 1 and (dist is None or getattr(dist, "capturable", True))
         self._graphs, self._eager_calls, self._lr_dev = {}, {}, {}
+        # a critic call runs only the encoder pyramid its factor reads (exact: see encode_real); DPIG_STAGE2_PRUNE=0 runs
+        # the whole encoder in every call, as the reference's sess.run does
+        self.prune = os.environ.get("DPIG_STAGE2_PRUNE", "1") != "0"
         if factors is not None:      # custom factor set: the pose sampler of --model=4 (no Stage-I engine), or the single
             self.f = factors         # 'app' factor of the DeepFashion samplers (--model=103 / 1002) on a Stage-I engine
             first = next(iter(factors.values()))
@@ -463,15 +466,27 @@ class Stage2Engine:
         else:
             f.z.data.copy_(torch.as_tensor(z, dtype=torch.float32).to(f.z.data.device))
 
-    def encode_real(self):
-        """Real embeddings of the current Stage-I batch (frozen encoder forward, trainer.py:737-741)."""
+    def encode_real(self, factor=None):
+        """Real embeddings of the current Stage-I batch (frozen encoder forward, trainer.py:737-741).
+        factor = "fg" / "bg" with self.prune: only the pyramid that factor's critic reads is run.  The reference's
+        sess.run(d_optim_embs_fg) evaluates the whole encoder because fg_embs is a tf.slice of the concatenated
+        embedding (trainer.py:741-742), but the Bg pyramid's output reaches nothing that call updates (and vice versa):
+        the launches that produce the trained factor's embedding are the same ones on the same inputs, so dropping the
+        other pyramid changes no result (tests/test_stage2_gpu.py::test_stage2_pruned_encoder_*)."""
         s = torch.cuda.current_stream().cuda_stream
-        self.s1.run_encoder(s)
         if "app" in self.f:          # one factor over the whole embedding (trainer_256.py:306-330)
+            self.s1.run_encoder(s)
             self.f["app"].real.data.copy_(self.s1.emb)
             return
-        self.f["fg"].real.data.copy_(self.s1.emb[:, :self.fg_dim])
-        self.f["bg"].real.data.copy_(self.s1.emb[:, self.fg_dim:])
+        if factor is not None and self.prune:
+            self.s1.run_encoder(s, only="roi" if factor == "fg" else "bg")
+        else:
+            factor = None
+            self.s1.run_encoder(s)
+        if factor in (None, "fg"):
+            self.f["fg"].real.data.copy_(self.s1.emb[:, :self.fg_dim])
+        if factor in (None, "bg"):
+            self.f["bg"].real.data.copy_(self.s1.emb[:, self.fg_dim:])
 
     def _optim(self, f, which, s):
         grp = f.gp if which == "g" else f.dp
@@ -516,7 +531,7 @@ class Stage2Engine:
         (a critic call first runs the frozen encoder on the batch).  The first two calls of a kind run eagerly, the
         third is captured into a CUDA graph while it runs, later ones replay it; the step size is a device scalar."""
         f = self.f[factor]
-        key = (factor, which)
+        key = (factor, which, bool(self.prune))
         lr_dev = self._lr_dev.get(key)
         if lr_dev is None:
             lr_dev = self._lr_dev[key] = torch.zeros(1, dtype=torch.float32, device=f.loss.device)
@@ -526,7 +541,7 @@ class Stage2Engine:
         def body():
             s = torch.cuda.current_stream().cuda_stream
             if which == "d" and self.s1 is not None:
-                self.encode_real()
+                self.encode_real(factor)
             self.sample_noise(factor)
             (self.g_grads if which == "g" else self.d_grads)(factor)
             self._optim_dev(f, which, lr_dev, s)

@@ -97,6 +97,51 @@ def test_stage2_rmsprop_and_clip_step():
         assert float(np.abs(after[k]).max()) <= 0.01 + 1e-9
 
 
+@pytest.mark.parametrize("factor", ["fg", "bg"])
+def test_stage2_pruned_encoder_embedding(factor):
+    """A critic call runs only the encoder pyramid its factor reads (Stage2Engine.prune; the reference's sess.run evaluates
+    both because fg_embs / bg_embs are slices of the concatenated embedding, trainer.py:741-742): the factor's real
+    embedding must be what the whole encoder gives, although the other half of the embedding is never computed."""
+    s1, s2, p1, p2, b, cfg = _setup()
+    assert s2.prune                                   # the default
+    s2.prune = False
+    s2.encode_real(factor)
+    torch.cuda.synchronize()
+    full = s2.f[factor].real.data.clone()
+    other = "bg" if factor == "fg" else "fg"
+    # poison everything the pruned run must not depend on / must recompute
+    s1.emb.fill_(float("nan"))
+    s2.f[factor].real.data.fill_(float("nan"))
+    (s1.bg_fea if factor == "fg" else s1.fea).fill_(float("nan"))
+    keep_other = s2.f[other].real.data.clone()
+    s2.prune = True
+    s2.encode_real(factor)
+    torch.cuda.synchronize()
+    got = s2.f[factor].real.data
+    assert torch.isfinite(got).all()
+    # same launches on the same inputs; the FC at the top of a pyramid sums its split-K partials with fp32 atomics
+    assert float((got - full).abs().max()) <= 1e-6 * float(full.abs().max())
+    assert torch.equal(s2.f[other].real.data, keep_other)        # the other factor's buffer is not touched
+
+
+def test_stage2_pruned_iteration_matches_the_full_encoder():
+    """One train_iteration (2 g_optim + 10 d_optim, trainer.py:822-845) with and without the pruning, same batches and
+    the same noise: the updated samplers and critics agree to fp32-atomic noise."""
+    from dpig_b200 import synth
+    outs = []
+    for prune in (False, True):
+        s1, s2, p1, p2, b, cfg = _setup()
+        s2.prune = prune
+        torch.manual_seed(1234)
+        it = iter(range(10 ** 6))
+        s2.train_iteration(1, lambda: synth.make_batch(s2.B, 32, 16, seed=100 + next(it)))
+        torch.cuda.synchronize()
+        outs.append(s2.get_params())
+    for k in outs[0]:
+        d = float(np.abs(outs[0][k] - outs[1][k]).max())
+        assert d <= 1e-6, (k, d)
+
+
 def test_stage2_iteration_runs():
     from dpig_b200 import synth
     s1, s2, p1, p2, b, cfg = _setup()
