@@ -36,6 +36,7 @@ class DPIG_FourNetsFgBg_testOnlySampleFactor(object):
         self.img_H, self.img_W = config.img_H, config.img_W
         self.conv_hidden_num, self.z_num = config.conv_hidden_num, config.z_num
         self.sample_fg, self.sample_bg, self.sample_pose = config.sample_fg, config.sample_bg, config.sample_pose
+        self.encode_unused = os.environ.get("DPIG_TESTER_ENCODE_UNUSED", "0") == "1"
         self.keypoint_num = 18
         self.model_dir = config.model_dir or os.path.join(config.log_dir, "dpig_model%d" % config.model)
         self.pretrained_path = config.pretrained_path
@@ -147,11 +148,24 @@ class DPIG_FourNetsFgBg_testOnlySampleFactor(object):
         return norm[:1].expand(self.batch_size, -1, -1)
 
     def _appearance_branch(self, st, z_fg, z_bg):
+        """tester.py:509-554.  The encoder is an ancestor of the fetched G only through a HELD factor (the first sample's
+        embedding tiled over the batch, tester.py:539, 550): with --sample_fg and --sample_bg both set (run_market_test.sh:
+        64-80) tf.Session.run never executes it, and neither does this.  One held factor needs its own pyramid only
+        (Stage2Engine.prune).  encode_unused=True (DPIG_TESTER_ENCODE_UNUSED=1) runs the whole encoder regardless --
+        BASELINE.json's configs[4] counts it in the sampling pass, bench.py measures both."""
         s2 = self.s2
-        s2.encode_real()
+        held = self._held_factors()
+        if self.encode_unused or len(held) == 2:
+            s2.encode_real()
+        elif held:
+            s2.encode_real(held[0])
         for factor, z in (("fg", z_fg), ("bg", z_bg)):
             s2.sample_noise(factor, z)
             s2.f[factor].p_g_fwd.run(st)
+
+    def _held_factors(self):
+        """The appearance factors whose embedding comes from the encoder rather than from a sampler."""
+        return [f for f, sampled in (("fg", self.sample_fg), ("bg", self.sample_bg)) if not sampled]
 
     def _score(self, st):
         return self.s1.score_generated(st)
@@ -234,6 +248,9 @@ class DPIG_FourNetsFgBg_testOnly(DPIG_FourNetsFgBg_testOnlySampleFactor):
 
     def _held_pose(self, norm):
         return norm
+
+    def _held_factors(self):
+        return [] if self.sample_app else ["fg", "bg"]
 
     def _fill_embedding(self):
         s1, s2, B = self.s1, self.s2, self.batch_size
@@ -402,7 +419,8 @@ class DPIG_ThreeNetsApp_testOnlySampleFactor_256(DPIG_FourNetsFgBg_testOnlySampl
             s1.emb.copy_(self.factor.real.data[:1].expand(B, -1))
 
     def _appearance_branch(self, st, z_fg, z_bg):
-        self.s2.encode_real()
+        if self.encode_unused or not self.sample_app:     # a sampled appearance does not read the encoder (see the base class)
+            self.s2.encode_real()
         self.s2.sample_noise("app", z_fg)
         self.factor.p_g_fwd.run(st)
 

@@ -14,15 +14,18 @@ from oracle import nets  # noqa: E402
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("sample", [True, False])
+@pytest.mark.parametrize("sample", [True, False, (True, False, True), (False, True, False)])
 def test_sample_factor_forward(sample):
+    """sample = all three switches, or (sample_fg, sample_bg, sample_pose).  The encoder runs as far as the fetched G needs
+    it (tester._appearance_branch): not at all when both appearance factors are sampled, one pyramid when one is held."""
     from dpig_b200 import config as cfgmod
+    s_fg, s_bg, s_pose = sample if isinstance(sample, tuple) else (sample, sample, sample)
     from dpig_b200 import engine, synth, tester
     B = 4
     kw = dict(img_h=32, img_w=16, hidden=64, roi_size=12, d_dim=64)
     conf, _ = cfgmod.get_config(["--model=13", "--is_train=False", "--batch_size=%d" % B, "--img_H=32", "--img_W=16",
-                                 "--conv_hidden_num=64", "--sample_fg=%s" % sample, "--sample_bg=%s" % sample,
-                                 "--sample_pose=%s" % sample])
+                                 "--conv_hidden_num=64", "--sample_fg=%s" % s_fg, "--sample_bg=%s" % s_bg,
+                                 "--sample_pose=%s" % s_pose])
     t = tester.DPIG_FourNetsFgBg_testOnlySampleFactor(conf)
     t.init_net(engine.NetConfig(**kw))
     ocfg = nets.NetConfig(**kw)
@@ -34,14 +37,18 @@ def test_sample_factor_forward(sample):
     rng = np.random.default_rng(5)
     z_fg = rng.normal(0, 0.2, size=(B, 224)).astype(np.float32)
     z_bg = rng.normal(0, 0.2, size=(B, 128)).astype(np.float32)
+    t.s1.emb.fill_(float("nan"))          # nothing may read an embedding half the run did not produce
+    t.s1.fea.fill_(float("nan"))
+    t.s1.bg_fea.fill_(float("nan"))
     G, pose_img, score = t.generate(b["x"], None, b["pose_rcv"], b["part_bbox"], b["part_vis"], mask=b["mask"],
                                     z_fg=z_fg, z_bg=z_bg)
+    assert np.isfinite(G).all() and np.isfinite(score).all()
     p = nets.to_torch(params, torch.float64)
     ob = dict(x=torch.tensor(b["x"], dtype=torch.float64), mask=torch.tensor(b["mask"], dtype=torch.float64),
               pose_rcv=torch.tensor(b["pose_rcv"], dtype=torch.float64),
               part_bbox=torch.tensor(b["part_bbox"][:, :7]), part_vis=torch.tensor(b["part_vis"][:, :7]))
     ref = nets.sample_factor_forward(p, ocfg, ob, torch.tensor(z_fg, dtype=torch.float64),
-                                     torch.tensor(z_bg, dtype=torch.float64), sample, sample, sample)
+                                     torch.tensor(z_bg, dtype=torch.float64), s_fg, s_bg, s_pose)
     # keypoint pixels are truncated to ints by the rasteriser: compare the maps, then the image
     maps = t.s1.gin.slice(0, 18).hi.float().cpu().double()
     mism = float((maps != ref["pose_maps"]).double().mean())
