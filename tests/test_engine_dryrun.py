@@ -135,3 +135,46 @@ def test_side_stream_schedule_of_the_programs():
     assert all(b.calls[i][0] == "conv2d_bwd_filter" for i in b.side)
     fwd_only = engine.Stage1Engine(DryContext(), engine.NetConfig(**SMALL), 2, mode="dcgan", device="cpu", inference=True)
     assert fwd_only.p_fwd_enc.side == p.side
+
+
+def test_single_pyramid_encoder_programs():
+    """Stage2Engine.prune / tester._appearance_branch launch the encoder with one pyramid only: the ROI program has no
+    Bg-pyramid launch and no mask_split, the Bg program no crop_and_resize; both end in the embedding assembly, and together
+    they hold the full program's launches (plus the shared stem twice)."""
+    eng = engine.Stage1Engine(DryContext(), engine.NetConfig(**SMALL), 2, mode="dcgan", device="cpu", inference=True)
+    full = [c[0] for c in eng.p_fwd_enc.calls if c[0]]
+    roi = [c[0] for c in eng.p_fwd_enc_only["roi"].calls if c[0]]
+    bg = [c[0] for c in eng.p_fwd_enc_only["bg"].calls if c[0]]
+    for prog in (eng.p_fwd_enc, eng.p_fwd_enc_only["roi"], eng.p_fwd_enc_only["bg"]):
+        assert _check_program(prog) > 0
+    assert "crop_and_resize_fwd" in roi and "mask_split" not in roi
+    assert "mask_split" in bg and "crop_and_resize_fwd" not in bg
+    assert roi[-1] == bg[-1] == full[-1] == "embedding_assemble"
+    stem = 5                      # pack, im2col, three stem convs
+    assert len(roi) + len(bg) == len(full) + stem + 1
+    # the tags name the layers: the ROI program touches no Bg-pyramid weights and vice versa
+    tags = lambda prog: {c[4].split()[0] for c in prog.calls if c[0] == "conv2d_fwd"}      # noqa: E731
+    w_roi, w_bg = {n + "/weights" for n in eng.n_roi}, {n + "/weights" for n in eng.n_bg}
+    assert w_roi <= tags(eng.p_fwd_enc_only["roi"]) and not (w_bg & tags(eng.p_fwd_enc_only["roi"]))
+    assert w_bg <= tags(eng.p_fwd_enc_only["bg"]) and not (w_roi & tags(eng.p_fwd_enc_only["bg"]))
+    # no side-stream launches when a pyramid runs alone
+    assert not eng.p_fwd_enc_only["bg"].side and not eng.p_fwd_enc_only["roi"].side
+    # the DeepFashion encoder has one pyramid: nothing to prune
+    df = engine.Stage1Engine(DryContext(), engine.NetConfig.deepfashion(img_h=64, img_w=64, hidden=64, roi_size=16), 2,
+                             mode="dcgan", device="cpu", inference=True)
+    assert df.p_fwd_enc_only == {}
+
+
+def test_sampler_held_factors():
+    """Which factors make the tester run the encoder (tester.py:536-552: a held factor reads the first sample's encoder
+    embedding; a sampled one does not)."""
+    from dpig_b200 import tester
+    t = tester.DPIG_FourNetsFgBg_testOnlySampleFactor.__new__(tester.DPIG_FourNetsFgBg_testOnlySampleFactor)
+    for fg, bg, want in ((True, True, []), (False, True, ["fg"]), (True, False, ["bg"]), (False, False, ["fg", "bg"])):
+        t.sample_fg, t.sample_bg = fg, bg
+        assert t._held_factors() == want
+    t11 = tester.DPIG_FourNetsFgBg_testOnly.__new__(tester.DPIG_FourNetsFgBg_testOnly)
+    t11.sample_app = True
+    assert t11._held_factors() == []
+    t11.sample_app = False
+    assert t11._held_factors() == ["fg", "bg"]
