@@ -300,3 +300,26 @@ def test_engine_activation_bits_have_the_oracles_layout():
                 same = tuple(a.shape) == tuple(b.shape)
                 half = (a.shape[0], 2 * a.shape[1], 2 * a.shape[2], a.shape[3]) == tuple(b.shape)
                 assert same or (key == "ID_AE/G" and half), (name, key, i, tuple(a.shape), tuple(b.shape))
+
+
+def test_float32_run_matches_float64_on_its_own_branches():
+    """The statement the GPU gradient bounds rest on, checked without a GPU: an fp32 evaluation of the graph and the
+    float64 one agree on every parameter gradient to fp32 rounding (< 2e-4 relative L2) when the float64 run takes the
+    ReLU / LeakyReLU branches the fp32 run took -- whatever they do when each decides for itself."""
+    cfg = nets.NetConfig(img_h=32, img_w=16, hidden=64, roi_size=12, d_dim=64)
+    params = nets.init_params(cfg, seed=1234, bias_noise=0.05)
+    b64 = _small_batch(cfg, seed=123)
+    b32 = {k: (v.float() if v.is_floating_point() else v) for k, v in b64.items()}
+    p32 = nets.to_torch(params, torch.float32, requires_grad=True)
+    p64 = nets.to_torch(params, torch.float64, requires_grad=True)
+    for which in ("g", "d"):
+        rec = {}
+        _, g32 = nets.stage1_grads(p32, cfg, b32, which, branches={"record": rec})
+        _, g64 = nets.stage1_grads(p64, cfg, b64, which, branches=rec)
+        top = max(float(g.abs().max()) for g in g64.values())
+        worst = 0.0
+        for k, g in g64.items():
+            if float(g.abs().max()) < 1e-9 * top:        # conv biases under a BatchNorm: exactly-zero gradient
+                continue
+            worst = max(worst, float((g32[k].double() - g).norm() / g.norm()))
+        assert worst < 2e-4, (which, worst)
