@@ -5,6 +5,7 @@ TensorFlow semantics listed in SURVEY.md §8c.  (Parity with real TF is unpinned
 import math
 
 import numpy as np
+import pytest
 import torch
 
 from oracle import nets, np_ref
@@ -302,12 +303,15 @@ def test_engine_activation_bits_have_the_oracles_layout():
                 assert same or (key == "ID_AE/G" and half), (name, key, i, tuple(a.shape), tuple(b.shape))
 
 
-def test_float32_run_matches_float64_on_its_own_branches():
+@pytest.mark.parametrize("seed", [1234, 77])
+def test_float32_run_matches_float64_on_its_own_branches(seed):
     """The statement the GPU gradient bounds rest on, checked without a GPU: an fp32 evaluation of the graph and the
     float64 one agree on every parameter gradient to fp32 rounding (< 2e-4 relative L2) when the float64 run takes the
-    ReLU / LeakyReLU branches the fp32 run took -- whatever they do when each decides for itself."""
+    ReLU / LeakyReLU branches the fp32 run took -- whatever they do when each decides for itself (with this
+    torch build seed 77 has ONE activation whose sign differs between the two precisions, and the free-running g_loss
+    gradients then differ by 3.6e-3 instead of 1.7e-5)."""
     cfg = nets.NetConfig(img_h=32, img_w=16, hidden=64, roi_size=12, d_dim=64)
-    params = nets.init_params(cfg, seed=1234, bias_noise=0.05)
+    params = nets.init_params(cfg, seed=seed, bias_noise=0.05)
     b64 = _small_batch(cfg, seed=123)
     b32 = {k: (v.float() if v.is_floating_point() else v) for k, v in b64.items()}
     p32 = nets.to_torch(params, torch.float32, requires_grad=True)
