@@ -131,10 +131,12 @@ def test_two_ranks_equal_one_engine_and_the_oracle(small):
     # critic gradient after the exchange, engine against engine: measured 2e-5 small, 3.8e-3 full -- the two tilings round
     # differently and may sit on different LeakyReLU branches where a pre-activation is ~0; each agrees with the oracle
     # on its own branches to 3e-5 (below)
-    assert rep["dgrad_rel"] < 1e-2, rep
+    # (one differing branch bit moves these by up to 6e-3 at the reduced geometry, tests/probe_grad_flake.py: the bound
+    #  leaves room for a few; the sharp statement is the oracle comparison on the ranks' own branches at the end)
+    assert rep["dgrad_rel"] < 3e-2, rep
     for k, v in rep.items():
         if k.startswith("grad "):
-            assert v < 1e-2, (k, rep)
+            assert v < 3e-2, (k, rep)
         if k.startswith("step "):
             assert v[0] <= 0.25 * v[1], (k, rep)
     # against the float64 oracle on the global batch (north-star bound on the logits; DVJP bound on the gradients)
